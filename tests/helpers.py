@@ -1,0 +1,42 @@
+"""Shared helpers for the test-suite: load golden fixtures, build the CPU oracle from them."""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import nerf3p, umhs_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+WAVELENGTHS = np.linspace(400, 1000, 128).astype(int).tolist()
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+    d = {k: z[k] for k in z.files}
+    meta = json.loads(str(d.pop("meta"))) if "meta" in d else {}
+    return d, meta
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def oracle_model_from_golden(d, meta, training=True):
+    cfg = O.OracleConfig(method="rgb+spectral", temperature=meta["temperature"], pred_specular=meta["specular"],
+                         log2_hashmap_size=meta["log2_T"], grid_resolution=meta.get("grid_res", 32))
+    aabb = torch.tensor([[-1.0, -1, -1], [1, 1, 1]])
+    m = O.OracleModel(cfg, aabb, WAVELENGTHS, meta["K"])
+    sd = {k[len("param."):]: t(v) for k, v in d.items() if k.startswith("param.")}
+    missing, unexpected = m.field.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert not missing, missing
+    if "binaries" in d:
+        res = meta["grid_res"]
+        bits = np.unpackbits(d["binaries"])[: 4 * res ** 3].reshape(4, res, res, res).astype(bool)
+        m.occupancy_grid.binaries.copy_(t(bits))
+        m.occupancy_grid.occs.copy_(m.occupancy_grid.binaries.flatten().float() * float(d["occs_scale"]))
+    m.train(training)
+    return m
