@@ -1,0 +1,282 @@
+/*
+ * umhs.h -- C ABI of libumhs_sm100.so: the B200 (sm_100a) kernels behind the UMHS
+ * nerfstudio plugin's hot path.
+ *
+ * The reference (Factral/unsupervised-hyperspectral-nerf) is pure Python: it owns no
+ * FFI.  Each entry point below replaces the chain of ATen / nerfacc / nerfstudio calls
+ * the reference makes at the cited file:line; the Python host code in
+ * unsupervised-hyperspectral-nerf_b200/umhs_b200/ binds them with ctypes and keeps the
+ * reference's UMHSField / SpectralRenderer / UMHSModel interfaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless said
+ *    otherwise; the CALLER allocates every buffer (torch does, in the plugin);
+ *  - kernels never allocate, never synchronise the device, and are enqueued on
+ *    `stream` (a cudaStream_t passed as void*); no global mutable state: safe to call
+ *    from any host thread on any stream;
+ *  - return 0 on success, a negative code on error; umhs_last_error() returns a
+ *    thread-local message.  There is no CPU fallback.
+ *  - packed layout: N samples sorted by ray; packed_info[r] = (start, count), int64;
+ *    ray_indices int64 (nerfacc 0.5.2 dtypes).
+ */
+#ifndef UMHS_H_
+#define UMHS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UMHS_OK 0
+#define UMHS_ERR_INVALID (-1)
+#define UMHS_ERR_CUDA (-2)
+#define UMHS_ERR_UNSUPPORTED (-3)
+
+#define UMHS_MAX_LEVELS 16
+#define UMHS_MAX_CLASSES 16
+#define UMHS_MAX_BANDS 512
+#define UMHS_GEO_FEAT 15 /* geo_feat_dim of NerfactoField */
+#define UMHS_PE_DIM 12   /* NeRFEncoding(3, 2 freqs) */
+#define UMHS_SH_DIM 16   /* SHEncoding(levels=4) */
+#define UMHS_HIDDEN 64   /* hidden_dim / hidden_dim_color */
+#define UMHS_SPEC_HIDDEN 16
+
+const char *umhs_last_error(void);
+int umhs_version(void);
+
+/* ---------------------------------------------------------------------------------
+ * Sample points.  A "point set" is either explicit world positions [n,3], or the
+ * packed samples of a ray batch: position = o[ray] + d[ray] * (t0 + t1) / 2
+ * (nerfstudio Frustums.get_positions, used at ref umhsnerf/umhs_field.py:183,303).
+ * ------------------------------------------------------------------------------- */
+typedef struct {
+    const float *positions;     /* [n,3] world positions, or NULL to use the ray form */
+    const float *directions;    /* [n,3] per-point directions (explicit form), may be NULL */
+    const float *rays_o;        /* [R,3] */
+    const float *rays_d;        /* [R,3] */
+    const int64_t *ray_indices; /* [n]   */
+    const float *t_starts;      /* [n]   */
+    const float *t_ends;        /* [n]   */
+    int32_t contraction;        /* 1: SceneContraction(inf) then (x+2)/4; 0: aabb-normalise */
+    float aabb[6];              /* min xyz, max xyz (used when contraction == 0) */
+} umhs_points;
+
+/* ---------------------------------------------------------------------------------
+ * (1) Multiresolution hash grid  -- replaces HashEncoding.pytorch_fwd reached from
+ *     ref umhsnerf/umhs_field.py:320 (self.mlp_base(positions_flat)) and its autograd
+ *     backward (index_put accumulate).
+ *     table [L*T, 2] f32, level l at rows [l*T,(l+1)*T); scalings [L] f32 (state-dict
+ *     buffer encoder.scalings); enc / d_enc [n, 2L] f32 row-major, level-major columns.
+ * ------------------------------------------------------------------------------- */
+typedef struct {
+    const float *table;
+    const float *scalings;
+    int32_t num_levels;
+    int32_t log2_table_size;
+} umhs_hash_grid;
+
+int umhs_hash_encode_fwd(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid, float *enc, void *stream);
+int umhs_hash_encode_bwd(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid, const float *d_enc,
+                         float *d_table, void *stream);
+/* Same two ops on already-normalised coordinates x01 [n,3] in [0,1] (the HashEncoding module boundary). */
+int umhs_hash_encode_x01_fwd(const float *x01, int64_t n, const umhs_hash_grid *grid, float *enc, void *stream);
+int umhs_hash_encode_x01_bwd(const float *x01, int64_t n, const umhs_hash_grid *grid, const float *d_enc,
+                             float *d_table, void *stream);
+
+/* ---------------------------------------------------------------------------------
+ * (2) Fused field MLPs -- replaces, per sample, ref umhsnerf/umhs_field.py:
+ *     :320-328  base MLP 32->64->16, trunc_exp, selector      -> sigma, emb[15]
+ *     :183-184  NeRF position encoding of the WORLD position  -> pe[12]
+ *     :211-212  mlp_head 27->64->64->K, sigmoid               -> scalar[K]
+ *     :214-226  feature_mlp 27->64->64->K(+1), softmax(/T), sigmoid -> abund[K], s1
+ *     :242-250  mlp_directional first layer [SH16,pe12]->16 ReLU    -> spec_hidden[16]
+ *               (its 16->B sigmoid layer is evaluated inside the compositing kernel)
+ *     All weights are nn.Linear layout [out,in] f32 + bias, state-dict order (A.9).
+ * ------------------------------------------------------------------------------- */
+typedef struct {
+    const float *base_w0, *base_b0, *base_w1, *base_b1;                     /* 64x32, 64, 16x64, 16 */
+    const float *head_w0, *head_b0, *head_w1, *head_b1, *head_w2, *head_b2; /* 64x27,64,64x64,64,Kx64,K */
+    const float *feat_w0, *feat_b0, *feat_w1, *feat_b1, *feat_w2, *feat_b2; /* ..., (K+spec)x64, K+spec */
+    const float *dir_w0, *dir_b0;                                           /* 16x28, 16 (specular only) */
+    int32_t num_classes; /* K */
+    int32_t specular;    /* pred_specular */
+    float temperature;
+} umhs_mlp_params;
+
+typedef struct {
+    float *base_w0, *base_b0, *base_w1, *base_b1;
+    float *head_w0, *head_b0, *head_w1, *head_b1, *head_w2, *head_b2;
+    float *feat_w0, *feat_b0, *feat_w1, *feat_b1, *feat_w2, *feat_b2;
+    float *dir_w0, *dir_b0;
+} umhs_mlp_grads;
+
+typedef struct {
+    float *sigma;       /* [n]            density = trunc_exp(h0) * selector          */
+    float *embedding;   /* [n,15] or NULL base_mlp_out                                */
+    float *scalar;      /* [n,K]  or NULL sigmoid(mlp_head)                           */
+    float *abund;       /* [n,K]  or NULL softmax(logits / T)                         */
+    float *s1;          /* [n]    or NULL (specular)                                  */
+    float *spec_hidden; /* [n,16] or NULL (specular) ReLU(first layer mlp_directional) */
+} umhs_field_out;
+
+typedef struct {
+    const float *d_sigma;       /* [n]    */
+    const float *d_embedding;   /* [n,15] or NULL */
+    const float *d_scalar;      /* [n,K]  */
+    const float *d_abund;       /* [n,K]  */
+    const float *d_s1;          /* [n]    or NULL */
+    const float *d_spec_hidden; /* [n,16] or NULL */
+} umhs_field_out_grads;
+
+/* density only: sampler sigma_fn (ref umhs_model.py:229-237), occupancy update (:549-554), density_fn */
+int umhs_density_fwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p, float *sigma,
+                     void *stream);
+int umhs_field_mlp_fwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
+                       const umhs_field_out *out, void *stream);
+/* parameter gradients are ACCUMULATED (+=) into *dp; d_enc [n,32] is overwritten (may be NULL).
+ * Activations are recomputed from enc; nothing else is kept from the forward pass. */
+int umhs_field_mlp_bwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
+                       const umhs_field_out_grads *g, float *d_enc, const umhs_mlp_grads *dp, void *stream);
+
+/* ---------------------------------------------------------------------------------
+ * (3) Compositing x unmixing x spec->sRGB, per ray over packed samples -- replaces
+ *     ref umhsnerf/umhs_model.py:245-313: pack weights (nerfacc render_weight_from_density),
+ *     depth / accumulation renderers, SpectralRenderer.forward x4 (umhs_renderer.py:15-30),
+ *     the linear mixing model of umhs_field.py:229-251 (spec = sum_k s_k a_k E[k,:],
+ *     + s1*sigmoid(W h + b) when specular), ColourSystem.forward (utils/spec_to_rgb.py:112-127)
+ *     and ClusterLookup.forward (utils/clusterprobe.py:17-38).
+ * ------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t n_rays, n_samples;
+    int32_t num_classes, num_bands, specular, grad_scaling;
+    const int64_t *packed_info; /* [R,2] */
+    const float *t_starts, *t_ends, *sigma;
+    const float *scalar, *abund; /* [N,K] */
+    const float *s1;             /* [N]    (specular) */
+    const float *spec_hidden;    /* [N,16] (specular) */
+    const float *endmembers;     /* [K,B]  */
+    const float *dir_w1, *dir_b1; /* [B,16], [B] (specular) */
+    const float *rgb_matrix;     /* [B,3]  */
+    const float *palette;        /* [>=K,3] class colours of ref umhs_model.py:146-162, or NULL */
+} umhs_composite_in;
+
+typedef struct {
+    float *trans;        /* [N]   transmittance per sample, or NULL */
+    float *weights;      /* [N]   or NULL */
+    float *spectral;     /* [R,B] */
+    float *spectral2;    /* [R,B] (specular) unmixed part */
+    float *specular;     /* [R,B] (specular) */
+    float *abundances;   /* [R,K] */
+    float *accumulation; /* [R]   */
+    float *depth;        /* [R]   expected depth, unclipped */
+    float *t_minmax;     /* [2]   caller-initialised to (+inf, -inf); min/max of (t0+t1)/2 */
+    float *rgb;          /* [R,3] */
+    float *seg_probs;    /* [R,K] */
+    float *seg_raw;      /* [R]   */
+    float *seg_pred;     /* [R,3] */
+} umhs_composite_out;
+
+typedef struct {
+    const float *d_spectral;  /* [R,B] or NULL */
+    const float *d_spectral2; /* [R,B] or NULL */
+    const float *d_rgb;       /* [R,3] or NULL (gradient w.r.t. the gamma-corrected, clamped rgb) */
+    const float *d_accumulation; /* [R] or NULL */
+    const float *spectral;    /* [R,B] forward output (needed when d_rgb is given) */
+} umhs_composite_grads_in;
+
+typedef struct {
+    float *d_sigma;       /* [N]    */
+    float *d_scalar;      /* [N,K]  */
+    float *d_abund;       /* [N,K]  */
+    float *d_s1;          /* [N]    (specular) */
+    float *d_spec_hidden; /* [N,16] (specular) */
+    float *d_endmembers;  /* [K,B]  accumulated (+=) */
+    float *d_dir_w1;      /* [B,16] accumulated (+=) (specular) */
+    float *d_dir_b1;      /* [B]    accumulated (+=) (specular) */
+} umhs_composite_grads_out;
+
+int umhs_composite_fwd(const umhs_composite_in *in, const umhs_composite_out *out, void *stream);
+int umhs_depth_clip(float *depth, int64_t n_rays, const float *t_minmax, void *stream);
+int umhs_composite_bwd(const umhs_composite_in *in, const umhs_composite_grads_in *gin,
+                       const umhs_composite_grads_out *gout, void *stream);
+
+/* Un-fused pieces at the reference's module boundaries (UMHSField.get_outputs returns per-sample
+ * spectra; SpectralRenderer.forward accumulates arbitrary [N,C] values). */
+int umhs_unmix_fwd(int64_t n, int32_t K, int32_t B, int32_t specular, const float *scalar, const float *abund,
+                   const float *s1, const float *spec_hidden, const float *endmembers, const float *dir_w1,
+                   const float *dir_b1, float *spec /*[n,B] unmixed*/, float *specular_out /*[n,B] s1*spc or NULL*/,
+                   void *stream);
+int umhs_unmix_bwd(int64_t n, int32_t K, int32_t B, int32_t specular, const float *scalar, const float *abund,
+                   const float *s1, const float *spec_hidden, const float *endmembers, const float *dir_w1,
+                   const float *dir_b1, const float *d_spec /*[n,B]*/, const float *d_specular /*[n,B] or NULL*/,
+                   float *d_scalar, float *d_abund, float *d_s1, float *d_spec_hidden, float *d_endmembers,
+                   float *d_dir_w1, float *d_dir_b1, void *stream);
+int umhs_render_weights_fwd(const int64_t *packed_info, int64_t n_rays, const float *t_starts, const float *t_ends,
+                            const float *sigma, float *weights, float *trans, void *stream);
+int umhs_render_weights_bwd(const int64_t *packed_info, int64_t n_rays, const float *t_starts, const float *t_ends,
+                            const float *sigma, const float *trans, const float *d_weights, float *d_sigma,
+                            void *stream);
+int umhs_accumulate_fwd(const float *weights, const float *values /*[N,C] or NULL*/, const int64_t *ray_indices,
+                        int64_t n, int32_t C, float *out /*[R,C], zero-filled by caller*/, void *stream);
+int umhs_accumulate_bwd(const float *weights, const float *values, const int64_t *ray_indices, int64_t n, int32_t C,
+                        const float *d_out, float *d_weights /*or NULL*/, float *d_values /*or NULL*/, void *stream);
+
+/* ---------------------------------------------------------------------------------
+ * (4) Ray-sample packing -- replaces VolumetricSampler / nerfacc OccGridEstimator.sampling
+ *     reached from ref umhsnerf/umhs_model.py:229-237, and nerfacc.pack_info (:245).
+ *     Integer outputs and t values are bit-exact against oracle/pack_oracle.c.
+ * ------------------------------------------------------------------------------- */
+typedef struct {
+    const float *rays_o, *rays_d;    /* [R,3] */
+    const float *near_planes, *far_planes; /* [R] */
+    const uint8_t *binaries;         /* [levels,res,res,res] bool */
+    const float *aabbs;              /* [levels,6] */
+    int32_t levels, resolution;
+    float step_size, cone_angle;
+    int64_t n_rays;
+} umhs_march_args;
+
+int umhs_march_count(const umhs_march_args *a, int64_t *counts, void *stream);
+/* packed_info[r] = (exclusive_scan(counts)[r], counts[r]); *total (device int64) = sum. `counts` may alias
+ * &packed_info[...]: no.  counts [R] int64 in, packed_info [R,2] int64 out. */
+int umhs_pack_scan(const int64_t *counts, int64_t n_rays, int64_t *packed_info, int64_t *total, void *stream);
+int umhs_march_write(const umhs_march_args *a, const int64_t *packed_info, int64_t *ray_indices, float *t_starts,
+                     float *t_ends, void *stream);
+/* visibility: keep = (T >= early_stop_eps) & (alpha >= thre), thre = min(alpha_thre, *occ_mean) when the
+ * device scalar occ_mean is given (nerfacc: min(alpha_thre, occs.mean())); also per-ray kept counts */
+int umhs_visibility_mask(const int64_t *packed_info, int64_t n_rays, const float *t_starts, const float *t_ends,
+                         const float *sigma, float early_stop_eps, float alpha_thre, const float *occ_mean,
+                         uint8_t *keep, int64_t *keep_counts, void *stream);
+int umhs_compact_samples(const int64_t *packed_info_in, const int64_t *packed_info_out, int64_t n_rays,
+                         const uint8_t *keep, const float *t_starts_in, const float *t_ends_in, int64_t *ray_indices,
+                         float *t_starts, float *t_ends, void *stream);
+/* nerfacc.pack_info for arbitrary (sorted or not) ray_indices; counts is scratch [R] */
+int umhs_pack_info(const int64_t *ray_indices, int64_t n, int64_t n_rays, int64_t *counts, int64_t *packed_info,
+                   void *stream);
+
+/* Occupancy grid update (ref umhs_model.py:549-554 -> nerfacc update_every_n_steps):
+ * occs[idx] = max(occs[idx]*decay, occ); then binaries = occs > min(mean(occs), thre). */
+int umhs_occ_cell_points(const int64_t *cell_ids /*or NULL: 0..n-1*/, const float *jitter /*[n,3]*/, int64_t n, int32_t resolution,
+                         const float *aabb6 /*device, level aabb*/, float *positions, void *stream);
+int umhs_occ_ema_update(float *occs, const int64_t *cell_ids, int64_t level_offset, const float *sigma, float scale,
+                        float decay, int64_t n, float *tmp /*[n] scratch*/, void *stream);
+int umhs_occ_binarize(const float *occs, int64_t n_cells, float occ_thre, double *scratch /*[2]*/, uint8_t *binaries,
+                      float *mean_out /*device scalar or NULL: mean(occs)*/, void *stream);
+
+/* ---------------------------------------------------------------------------------
+ * Optimiser: dense Adam over one flat fp32 parameter buffer (torch.optim.Adam
+ * semantics, configured at ref umhsnerf/umhs_config.py:59-64), with the endmember
+ * clamp of ref umhsnerf/umhs_model.py:568-570 folded in for [clamp_begin, clamp_end).
+ * grad is read, multiplied by *inv_scale (device float, may be NULL) and then zeroed.
+ * ------------------------------------------------------------------------------- */
+int umhs_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
+                   float beta2, float eps, int32_t step, const float *inv_scale, const float *found_inf,
+                   int64_t clamp_begin, int64_t clamp_end, int32_t zero_grad, void *stream);
+/* out[i] += sum_s slabs[s*stride + i] */
+int umhs_reduce_slabs(const float *slabs, int64_t n_slabs, int64_t stride, int64_t n, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UMHS_H_ */

@@ -60,6 +60,14 @@ static inline float calc_dt(float t, float cone_angle, float dt_min, float dt_ma
 
 static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+/* voxel index of a normalised coordinate: clamp in the float domain first so that the
+ * float->int conversion is defined for far-away points (C: UB, CUDA: saturating). */
+static inline int voxel_index(float v, float fres, int res)
+{
+    v = v < -1.0f ? -1.0f : (v > fres ? fres : v);
+    return clampi((int)v, 0, res - 1);
+}
+
 /* March one ray.  If out arrays are NULL only counts.  Returns number of samples. */
 static int64_t march_ray(const float o[3], const float d[3], const uint8_t *binaries, const float *aabbs,
                          int levels, int res, float near_plane, float far_plane, float step_size,
@@ -105,8 +113,8 @@ static int64_t march_ray(const float o[3], const float d[3], const uint8_t *bina
             voxel[k] = ext / fres;
             const float rs = o[k] + d[k] * (this_tmin + eps);
             const float re = o[k] + d[k] * (this_tmax - eps);
-            cur[k] = clampi((int)(((rs - aabb[k]) / ext) * fres), 0, res - 1);
-            fin[k] = clampi((int)(((re - aabb[k]) / ext) * fres), 0, res - 1);
+            cur[k] = voxel_index(((rs - aabb[k]) / ext) * fres, fres, res);
+            fin[k] = voxel_index(((re - aabb[k]) / ext) * fres, fres, res);
             const int start_index = cur[k] + (d[k] > 0.0f ? 1 : 0);
             const float tmax_k = ((aabb[k] + (((float)start_index * voxel[k]) - rs)) * inv[k]) + this_tmin;
             const float sf = (d[k] == 0.0f) ? 0.0f : (d[k] > 0.0f ? 1.0f : -1.0f);

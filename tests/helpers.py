@@ -40,3 +40,34 @@ def oracle_model_from_golden(d, meta, training=True):
         m.occupancy_grid.occs.copy_(m.occupancy_grid.binaries.flatten().float() * float(d["occs_scale"]))
     m.train(training)
     return m
+
+
+# ------------------------------------------------------------------ B200 side
+def b200_model_from_golden(d, meta, training=True, device="cuda"):
+    """UMHSModel (the product) carrying the golden parameters / occupancy grid."""
+    import umhs_b200
+
+    cfg = umhs_b200.UMHSConfig(method="rgb+spectral", temperature=meta["temperature"],
+                               pred_specular=meta["specular"], log2_hashmap_size=meta["log2_T"],
+                               grid_resolution=meta.get("grid_res", 32))
+    m = cfg.setup(scene_box=torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), num_train_data=10,
+                  metadata={"wavelengths": WAVELENGTHS, "num_classes": meta["K"]})
+    sd = {k[len("param."):]: t(v) for k, v in d.items() if k.startswith("param.")}
+    missing, unexpected = m.field.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all("converter" in k for k in missing), missing
+    if "binaries" in d:
+        res = meta["grid_res"]
+        bits = np.unpackbits(d["binaries"])[: 4 * res ** 3].reshape(4, res, res, res).astype(bool)
+        m.occupancy_grid.binaries.copy_(t(bits))
+        m.occupancy_grid.occs.copy_(m.occupancy_grid.binaries.flatten().float() * float(d["occs_scale"]))
+        m.occupancy_grid.mark_dirty()
+    m = m.to(device)
+    m.train(training)
+    return m
+
+
+def assert_close(a, b, rtol, atol, name=""):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    np.testing.assert_allclose(a.reshape(b.shape), b, rtol=rtol, atol=atol, err_msg=name)

@@ -1,0 +1,306 @@
+"""GPU parity: each C-ABI kernel family of libumhs_sm100.so against the CPU oracle (oracle/) on seeded inputs.
+fp32 kernels: tolerances are summation-order / FMA-contraction noise.  Packing: bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import WAVELENGTHS, assert_close, load_golden, t
+from oracle import nerf3p, pack_oracle, umhs_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ops():
+    from umhs_b200 import ops
+    return ops
+
+
+# ------------------------------------------------------------------ hash grid
+@pytest.mark.parametrize("log2_T,L", [(10, 16), (19, 16), (14, 5)])
+def test_hash_encode_fwd_bwd(log2_T, L):
+    ops = _ops()
+    g = torch.Generator().manual_seed(0)
+    N = 4099
+    x = torch.rand(N, 3, generator=g)
+    x[0] = 0.0
+    x[1] = 1.0
+    x[2] = torch.tensor([0.5, 0.25, 0.125])  # exact integers at several levels: ceil == floor
+    x[3] = torch.tensor([1.0, 0.0, 0.5])
+    table = (torch.rand((L << log2_T, 2), generator=g) * 2 - 1).requires_grad_(True)
+    scal = nerf3p.hash_scalings(16, 16, 2048)[:L].contiguous()
+    ref = nerf3p.hash_encode(x, table, scal, log2_T)
+    gw = torch.randn(N, 2 * L, generator=g)
+    (ref * gw).sum().backward()
+    enc = ops.hash_encode_x01_fwd(x.to(DEV), table.detach().to(DEV), scal.to(DEV), log2_T)
+    assert_close(enc, ref, 1e-5, 1e-6, "enc")
+    dt = ops.hash_encode_x01_bwd(x.to(DEV), table.detach().to(DEV), scal.to(DEV), log2_T, gw.to(DEV))
+    assert_close(dt, table.grad, 1e-4, 1e-5, "d_table")
+
+
+def test_hash_encode_points_form_and_empty():
+    ops = _ops()
+    g = torch.Generator().manual_seed(1)
+    R, N, log2_T = 37, 1500, 12
+    o = torch.randn(R, 3, generator=g)
+    d = torch.randn(R, 3, generator=g)
+    ri = torch.sort(torch.randint(R, (N,), generator=g)).values
+    t0 = torch.rand(N, generator=g) * 3
+    t1 = t0 + 0.01
+    table = torch.rand((16 << log2_T, 2), generator=g)
+    scal = nerf3p.hash_scalings()
+    pos = o[ri] + d[ri] * (t0 + t1)[:, None] / 2
+    x = (nerf3p.scene_contraction_inf(pos) + 2.0) / 4.0
+    sel = ((x > 0) & (x < 1)).all(-1)
+    ref = nerf3p.hash_encode(x * sel[:, None], table, scal, log2_T)
+    pts = ops.PointSet.from_packed(o.to(DEV), d.to(DEV), ri.to(DEV), t0.to(DEV), t1.to(DEV))
+    enc = ops.hash_encode_fwd(pts, table.to(DEV), scal.to(DEV), log2_T)
+    assert_close(enc, ref, 1e-5, 1e-6)
+    pts0 = ops.PointSet.from_positions(torch.zeros((0, 3), device=DEV))
+    assert ops.hash_encode_fwd(pts0, table.to(DEV), scal.to(DEV), log2_T).shape == (0, 32)
+
+
+# ------------------------------------------------------------------ packing (bit exact)
+def _rays(R, seed):
+    g = torch.Generator().manual_seed(seed)
+    rad = 0.7 + 2.5 * torch.rand(R, 1, generator=g)
+    o = torch.randn(R, 3, generator=g)
+    o = o / o.norm(dim=-1, keepdim=True) * rad
+    d = -o / o.norm(dim=-1, keepdim=True) + 0.2 * torch.randn(R, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    d[0] = torch.tensor([1.0, 0.0, 0.0])
+    o[0] = torch.tensor([-1.5, 0.01, 0.02])
+    d[1] = torch.tensor([0.0, 0.0, 1.0])
+    o[1] = torch.tensor([5.0, 5.0, -3.0])
+    o[2] = torch.tensor([0.1, 0.2, 0.05])  # origin inside the finest box
+    return o, d, torch.rand(R, generator=g)
+
+
+def _grid(res, seed, fill=0.35):
+    g = torch.Generator().manual_seed(seed)
+    c = (torch.arange(res) + 0.5) / res * 2 - 1
+    X, Y, Z = torch.meshgrid(c, c, c, indexing="ij")
+    b = torch.zeros(4, res, res, res, dtype=torch.bool)
+    b[0] = (X ** 2 + Y ** 2 + Z ** 2) < 0.6 ** 2
+    b[1] = torch.rand(res, res, res, generator=g) < fill
+    b[2] = torch.rand(res, res, res, generator=g) < 0.05
+    aabbs = nerf3p.occ_grid_aabbs(torch.tensor([-1.0, -1, -1, 1, 1, 1]), 4)
+    return b, aabbs
+
+
+@pytest.mark.parametrize("R,res,cone,far", [(2048, 32, 0.004, 1e3), (4096, 128, 0.004, 1e3), (777, 64, 0.0, 1e10),
+                                            (1, 32, 0.004, 1e3)])
+def test_march_bit_exact(R, res, cone, far):
+    ops = _ops()
+    o, d, jit = _rays(max(R, 3), 10 + R)
+    o, d, jit = o[:R], d[:R], jit[:R]
+    b, aabbs = _grid(res, res)
+    step = (12 ** 0.5) / 1000
+    near = torch.full((R,), 0.05) + jit * step
+    farp = torch.full((R,), far)
+    ri_r, t0_r, t1_r, pk_r = pack_oracle.traverse_grids(o, d, b, aabbs, near, farp, step, cone)
+    ri, t0, t1, pk = ops.march(o.to(DEV), d.to(DEV), near.to(DEV), farp.to(DEV), b.to(DEV), aabbs.to(DEV), step, cone)
+    assert ri_r.numel() > 0 or R == 1
+    assert np.array_equal(pk.cpu().numpy(), pk_r.numpy())
+    assert np.array_equal(ri.cpu().numpy(), ri_r.numpy())
+    assert np.array_equal(t0.cpu().numpy(), t0_r.numpy())
+    assert np.array_equal(t1.cpu().numpy(), t1_r.numpy())
+    # pack_info on the produced indices reproduces packed_info
+    assert np.array_equal(ops.pack_info(ri, R).cpu().numpy(), pk_r.numpy())
+
+
+def test_visibility_compaction_matches_boolean_mask():
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    R = 513
+    cnt = torch.randint(0, 90, (R,), generator=g)
+    cnt[7] = 0
+    cnt[8] = 300
+    ri = torch.repeat_interleave(torch.arange(R), cnt)
+    N = ri.numel()
+    packed = nerf3p.pack_info(ri, R)
+    t0 = torch.rand(N, generator=g)
+    t1 = t0 + 0.01 * torch.rand(N, generator=g)
+    sigma = torch.exp(torch.randn(N, generator=g) * 2 + 2)
+    for thre, occ_mean in ((0.01, 0.5), (0.01, 0.004), (0.0, 1.0)):
+        a = min(thre, occ_mean)
+        mask = nerf3p.render_visibility_from_density(t0, t1, sigma, packed, 1e-4, a)
+        # drop borderline samples (scan order changes T in the last ulp)
+        _, T, al = nerf3p.render_weight_from_density(t0, t1, sigma, packed)
+        safe = ((T - 1e-4).abs() > 1e-7) & ((al - a).abs() > 1e-7)
+        om = torch.tensor([occ_mean], device=DEV)
+        ri2, a0, a1, pk2 = ops.visibility_compact(packed.to(DEV), t0.to(DEV), t1.to(DEV), sigma.to(DEV), 1e-4, thre, om)
+        if bool(safe.all()):
+            assert np.array_equal(ri2.cpu().numpy(), ri[mask].numpy())
+            assert np.array_equal(a0.cpu().numpy(), t0[mask].numpy())
+            assert np.array_equal(a1.cpu().numpy(), t1[mask].numpy())
+            assert np.array_equal(pk2.cpu().numpy(), nerf3p.pack_info(ri[mask], R).numpy())
+        else:
+            assert abs(ri2.numel() - int(mask.sum())) <= int((~safe).sum())
+
+
+# ------------------------------------------------------------------ compositing x unmixing
+def _packed_case(R, K, B, specular, seed, smax=70):
+    g = torch.Generator().manual_seed(seed)
+    cnt = torch.randint(0, smax, (R,), generator=g)
+    cnt[0] = 0
+    cnt[1] = 1
+    if R > 4:
+        cnt[3] = 200
+    ri = torch.repeat_interleave(torch.arange(R), cnt)
+    N = ri.numel()
+    t0 = torch.rand(N, generator=g) * 1.3
+    t1 = t0 + 0.02 * torch.rand(N, generator=g)
+    c = dict(R=R, N=N, ri=ri, packed=nerf3p.pack_info(ri, R), t0=t0, t1=t1,
+             sigma=torch.exp(torch.randn(N, generator=g) * 1.5 + 2.5),
+             scalar=torch.rand(N, K, generator=g), abund=torch.softmax(torch.randn(N, K, generator=g), -1),
+             E=torch.rand(K, B, generator=g), M=torch.from_numpy(O.spec_to_rgb_matrix(
+                 np.linspace(400, 1000, B).astype(int))).float(),
+             gS=torch.randn(R, B, generator=g), gS2=torch.randn(R, B, generator=g), gR=torch.randn(R, 3, generator=g),
+             gA=torch.randn(R, generator=g))
+    if specular:
+        c.update(s1=torch.rand(N, generator=g), sh=torch.relu(torch.randn(N, 16, generator=g)),
+                 W=torch.randn(B, 16, generator=g) * 0.3, b=torch.randn(B, generator=g) * 0.1)
+    return c
+
+
+def _oracle_composite(c, specular, grad_scaling):
+    """Reference semantics: per-sample spectra -> (gradient scaler) -> weights -> accumulate -> colour / probe."""
+    leaves = {k: c[k].clone().requires_grad_(True) for k in ("sigma", "scalar", "abund", "E")}
+    if specular:
+        leaves.update({k: c[k].clone().requires_grad_(True) for k in ("s1", "sh", "W", "b")})
+    spec = ((leaves["scalar"] * leaves["abund"]) @ leaves["E"])
+    fo = {"density": leaves["sigma"][:, None], "spectral": spec, "abundances": leaves["abund"]}
+    if specular:
+        spc = torch.sigmoid(leaves["sh"] @ leaves["W"].t() + leaves["b"])
+        term = leaves["s1"][:, None] * spc
+        fo["spectral"] = spec + term
+        fo["spectral2"] = spec
+        fo["specular"] = term.detach()
+    rs = nerf3p.RaySamples(nerf3p.Frustums(None, None, c["t0"][:, None], c["t1"][:, None]))
+    if grad_scaling:
+        fo = nerf3p.scale_gradients_by_distance_squared(fo, rs)
+    w = nerf3p.render_weight_from_density(c["t0"], c["t1"], fo["density"][:, 0], c["packed"])[0][:, None]
+    out = {"weights": w[:, 0]}
+    out["depth"] = nerf3p.render_depth_expected(w, rs, c["ri"], c["R"]) if c["N"] else None
+    out["accumulation"] = nerf3p.render_accumulation(w, c["ri"], c["R"])
+    out["spectral"] = O.spectral_render(fo["spectral"], w, c["ri"], c["R"])
+    if specular:
+        out["spectral2"] = O.spectral_render(fo["spectral2"], w, c["ri"], c["R"])
+        out["specular"] = O.spectral_render(fo["specular"], w, c["ri"], c["R"])
+    out["abundances"] = O.spectral_render(fo["abundances"], w, c["ri"], c["R"]).detach()
+    lin = out["spectral"] @ c["M"]
+    out["rgb"] = O.ColourSystem.gamma_correction(lin).clamp(0, 1)
+    inner, probs = O.cluster_lookup(out["spectral"], 0.2, leaves["E"])
+    out["seg_probs"], out["inner"] = probs.detach(), inner.detach()
+    return out, leaves
+
+
+@pytest.mark.parametrize("R,K,B,specular,gs", [(300, 4, 128, False, True), (300, 9, 128, True, True),
+                                               (64, 16, 512, True, False), (200, 6, 32, False, False),
+                                               (128, 8, 256, False, True), (5, 4, 128, True, True)])
+def test_composite_fwd_bwd(R, K, B, specular, gs):
+    ops = _ops()
+    c = _packed_case(R, K, B, specular, seed=R + K)
+    ref, leaves = _oracle_composite(c, specular, gs)
+    loss = (ref["spectral"] * c["gS"]).sum() + (ref["rgb"] * c["gR"]).sum() + (ref["accumulation"][:, 0] * c["gA"]).sum()
+    if specular:
+        loss = loss + (ref["spectral2"] * c["gS2"]).sum()
+    loss.backward()
+
+    dv = {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in c.items()}
+    req = {k: dv[k].clone().requires_grad_(True) for k in leaves}
+    cfg = {"K": K, "B": B, "specular": specular, "grad_scaling": gs, "want_weights": True}
+    pal = torch.tensor(O.CLASS_COLORS, device=DEV)
+    outs = ops.CompositeFunction.apply(cfg, dv["packed"], dv["t0"], dv["t1"], req["sigma"], req["scalar"], req["abund"],
+                                       req.get("s1"), req.get("sh"), req["E"], req.get("W"), req.get("b"), dv["M"], pal)
+    got = dict(zip(ops.COMPOSITE_OUTPUTS, outs))
+    assert_close(got["weights"], ref["weights"], 2e-4, 1e-6, "weights")
+    assert_close(got["accumulation"], ref["accumulation"], 1e-4, 1e-6, "acc")
+    assert_close(got["depth"], ref["depth"], 1e-4, 1e-6, "depth")
+    assert_close(got["spectral"], ref["spectral"], 1e-4, 2e-6, "spectral")
+    assert_close(got["abundances"], ref["abundances"], 1e-4, 1e-6, "abund")
+    assert_close(got["rgb"], ref["rgb"], 1e-4, 1e-5, "rgb")
+    assert_close(got["seg_probs"], ref["seg_probs"], 1e-4, 1e-6, "seg_probs")
+    if specular:
+        assert_close(got["spectral2"], ref["spectral2"], 1e-4, 2e-6, "spectral2")
+        assert_close(got["specular"], ref["specular"], 1e-4, 2e-6, "specular")
+    # argmax: compare where the top-2 inner products are separated
+    top2 = torch.topk(ref["inner"], min(2, K), dim=1).values
+    clear = (top2[:, 0] - top2[:, -1]) > 1e-5 if K > 1 else torch.ones(R, dtype=torch.bool)
+    gate = (ref["accumulation"][:, 0] > 0.5).float()
+    exp_raw = ref["seg_probs"].argmax(1).float() * gate
+    assert np.array_equal(got["seg_raw"].cpu().numpy()[clear.numpy()], exp_raw.numpy()[clear.numpy()])
+
+    l2 = (got["spectral"] * dv["gS"]).sum() + (got["rgb"] * dv["gR"]).sum() + (got["accumulation"] * dv["gA"]).sum()
+    if specular:
+        l2 = l2 + (got["spectral2"] * dv["gS2"]).sum()
+    l2.backward()
+    for k in leaves:
+        scale = float(leaves[k].grad.abs().max()) + 1e-12
+        assert_close(req[k].grad, leaves[k].grad, 2e-3, 2e-5 * scale, "grad " + k)
+
+
+# ------------------------------------------------------------------ unfused module-boundary ops
+def test_unfused_ops():
+    ops = _ops()
+    c = _packed_case(150, 5, 128, True, seed=3)
+    dv = {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in c.items()}
+    # weights
+    sig = c["sigma"].clone().requires_grad_(True)
+    w_ref = nerf3p.render_weight_from_density(c["t0"], c["t1"], sig, c["packed"])[0]
+    gw = torch.randn(c["N"])
+    (w_ref * gw).sum().backward()
+    sg = dv["sigma"].clone().requires_grad_(True)
+    w, T = ops.RenderWeightsFunction.apply(dv["t0"], dv["t1"], sg, dv["packed"])
+    (w * gw.to(DEV)).sum().backward()
+    assert_close(w, w_ref, 2e-4, 1e-6)
+    assert_close(sg.grad, sig.grad, 2e-3, 1e-5 * float(sig.grad.abs().max()))
+    # accumulate
+    vals = torch.rand(c["N"], 128, requires_grad=True)
+    wr = w_ref.detach().clone().requires_grad_(True)
+    acc_ref = nerf3p.accumulate_along_rays(wr, vals, c["ri"], c["R"])
+    go = torch.randn(c["R"], 128)
+    (acc_ref * go).sum().backward()
+    v2 = vals.detach().to(DEV).requires_grad_(True)
+    w2 = w_ref.detach().to(DEV).requires_grad_(True)
+    acc = ops.AccumulateFunction.apply(w2, v2, dv["ri"], c["R"])
+    (acc * go.to(DEV)).sum().backward()
+    assert_close(acc, acc_ref, 1e-4, 1e-5)
+    assert_close(v2.grad, vals.grad, 1e-5, 1e-7)
+    assert_close(w2.grad, wr.grad, 1e-4, 1e-5)
+    # unmix
+    L = {k: c[k].clone().requires_grad_(True) for k in ("scalar", "abund", "s1", "sh", "E", "W", "b")}
+    spec = (L["scalar"] * L["abund"]) @ L["E"]
+    term = L["s1"][:, None] * torch.sigmoid(L["sh"] @ L["W"].t() + L["b"])
+    g1, g2 = torch.randn(c["N"], 128), torch.randn(c["N"], 128)
+    ((spec * g1).sum() + (term * g2).sum()).backward()
+    D = {k: dv[k].clone().requires_grad_(True) for k in L}
+    s_, t_ = ops.UnmixFunction.apply(D["scalar"], D["abund"], D["s1"], D["sh"], D["E"], D["W"], D["b"])
+    ((s_ * g1.to(DEV)).sum() + (t_ * g2.to(DEV)).sum()).backward()
+    assert_close(s_, spec, 1e-5, 1e-6)
+    assert_close(t_, term, 1e-5, 1e-6)
+    for k in L:
+        assert_close(D[k].grad, L[k].grad, 1e-3, 1e-5 * float(L[k].grad.abs().max()), "unmix grad " + k)
+
+
+# ------------------------------------------------------------------ optimiser
+def test_adam_matches_torch():
+    ops = _ops()
+    g = torch.Generator().manual_seed(0)
+    n = 100003
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=2e-2, eps=1e-15)
+    p = p0.clone().to(DEV)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 6):
+        gr = torch.randn(n, generator=g) * (torch.rand(n, generator=g) < 0.3)
+        ref.grad = gr.clone()
+        opt.step()
+        with torch.no_grad():
+            ref[10:200] = ref[10:200].clamp(0, 1)
+        gd = gr.to(DEV)
+        ops.adam_step(p, gd, m, v, 2e-2, 0.9, 0.999, 1e-15, step, clamp_range=(10, 200))
+        assert float(gd.abs().max()) == 0.0  # zero_grad fused
+    assert_close(p, ref, 1e-5, 1e-6)

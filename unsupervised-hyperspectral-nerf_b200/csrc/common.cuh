@@ -1,0 +1,140 @@
+// common.cuh -- shared device helpers for libumhs_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/umhs.h"
+
+namespace umhs {
+
+void set_error(const char *fmt, ...);
+
+#define UMHS_CHECK_ARG(cond, msg)                                   \
+    do {                                                            \
+        if (!(cond)) {                                              \
+            umhs::set_error("%s: %s", __func__, msg);               \
+            return UMHS_ERR_INVALID;                                \
+        }                                                           \
+    } while (0)
+
+#define UMHS_CHECK_LAUNCH()                                                          \
+    do {                                                                             \
+        cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess) {                                                    \
+            umhs::set_error("%s: CUDA error %s", __func__, cudaGetErrorString(e__)); \
+            return UMHS_ERR_CUDA;                                                    \
+        }                                                                            \
+    } while (0)
+
+#define UMHS_CHECK_CUDA(expr)                                                                  \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            umhs::set_error("%s: %s failed: %s", __func__, #expr, cudaGetErrorString(e__));    \
+            return UMHS_ERR_CUDA;                                                              \
+        }                                                                                      \
+    } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+constexpr unsigned kFull = 0xffffffffu;
+
+static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+// inclusive prefix sum across the warp (lane order)
+__device__ __forceinline__ float warp_incl_scan(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// inclusive suffix sum across the warp (lane i gets sum over lanes >= i)
+__device__ __forceinline__ float warp_incl_rscan(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_down_sync(kFull, v, o);
+        if (lane + o < 32) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// A sample point: world position (for the NeRF position encoding), grid coordinate in [0,1]
+// already multiplied by the selector (ref umhs_field.py:302-310), selector, and direction.
+struct Point {
+    float wx, wy, wz;
+    float x, y, z;
+    float sel;
+    float dx, dy, dz;
+    float tmid;  // (t0 + t1) / 2 for the ray form, 0 for explicit positions
+};
+
+__device__ __forceinline__ Point eval_point(const umhs_points &P, int64_t n) {
+    Point p;
+    if (P.positions != nullptr) {
+        p.wx = __ldg(P.positions + 3 * n + 0);
+        p.wy = __ldg(P.positions + 3 * n + 1);
+        p.wz = __ldg(P.positions + 3 * n + 2);
+        if (P.directions != nullptr) {
+            p.dx = __ldg(P.directions + 3 * n + 0);
+            p.dy = __ldg(P.directions + 3 * n + 1);
+            p.dz = __ldg(P.directions + 3 * n + 2);
+        } else {
+            p.dx = p.dy = p.dz = 1.0f;
+        }
+        p.tmid = 0.0f;
+    } else {
+        const int64_t r = __ldg(P.ray_indices + n);
+        const float tm = (__ldg(P.t_starts + n) + __ldg(P.t_ends + n));
+        p.dx = __ldg(P.rays_d + 3 * r + 0);
+        p.dy = __ldg(P.rays_d + 3 * r + 1);
+        p.dz = __ldg(P.rays_d + 3 * r + 2);
+        // origins + directions * (starts + ends) / 2   (nerfstudio Frustums.get_positions)
+        p.wx = __ldg(P.rays_o + 3 * r + 0) + (p.dx * tm) / 2.0f;
+        p.wy = __ldg(P.rays_o + 3 * r + 1) + (p.dy * tm) / 2.0f;
+        p.wz = __ldg(P.rays_o + 3 * r + 2) + (p.dz * tm) / 2.0f;
+        p.tmid = tm / 2.0f;
+    }
+    float x = p.wx, y = p.wy, z = p.wz;
+    if (P.contraction) {
+        const float mag = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+        if (!(mag < 1.0f)) {
+            const float s = 2.0f - (1.0f / mag);
+            x = s * (x / mag);
+            y = s * (y / mag);
+            z = s * (z / mag);
+        }
+        x = (x + 2.0f) / 4.0f;
+        y = (y + 2.0f) / 4.0f;
+        z = (z + 2.0f) / 4.0f;
+    } else {
+        x = (x - P.aabb[0]) / (P.aabb[3] - P.aabb[0]);
+        y = (y - P.aabb[1]) / (P.aabb[4] - P.aabb[1]);
+        z = (z - P.aabb[2]) / (P.aabb[5] - P.aabb[2]);
+    }
+    const bool sel = (x > 0.0f) && (x < 1.0f) && (y > 0.0f) && (y < 1.0f) && (z > 0.0f) && (z < 1.0f);
+    p.sel = sel ? 1.0f : 0.0f;
+    p.x = sel ? x : 0.0f;
+    p.y = sel ? y : 0.0f;
+    p.z = sel ? z : 0.0f;
+    return p;
+}
+
+}  // namespace umhs

@@ -1,0 +1,266 @@
+// hash_grid.cu -- multiresolution hash-grid encode, forward (gather) and backward (scatter).
+//
+// Replaces nerfstudio HashEncoding.pytorch_fwd reached from ref umhsnerf/umhs_field.py:320
+// (self.mlp_base(positions_flat)) and its autograd backward.  Arithmetic follows
+// oracle/nerf3p.py::hash_encode: ceil/floor corners, ALL levels hashed with
+// (x*1) ^ (y*2654435761) ^ (z*805459861) mod T, blend in the reference's association order.
+//
+// Mapping: one thread per sample, loop over the L levels.  Consecutive threads are consecutive
+// samples of one ray, so at coarse levels a warp reads a handful of distinct 8-byte entries
+// (served from L1/L2); the whole 64 MiB table fits the 126 MB L2.  Each level issues 8
+// independent float2 gathers; two levels are kept in flight (16 loads per thread).
+// Output enc [n, 2L] fp32 row-major (level-major columns), written as float4 per 2 levels.
+//
+// Algorithmic bytes per sample: fwd 8*L*8 gathered + 12 in + 8L out;
+// bwd 8L in + 8*L*8 read-modify-write.
+#include "common.cuh"
+
+namespace umhs {
+
+struct Corners {
+    uint32_t idx[8];
+    float w[8];
+};
+
+// Corner order follows the reference: f0=(c,c,c) f1=(c,f,c) f2=(f,f,c) f3=(f,c,c)
+//                                     f4=(c,c,f) f5=(c,f,f) f6=(f,f,f) f7=(f,c,f)
+__device__ __forceinline__ void level_setup(float x, float y, float z, float scale, uint32_t tmask, uint32_t base,
+                                            uint32_t (&idx)[8], float &ox, float &oy, float &oz) {
+    const float sx = x * scale, sy = y * scale, sz = z * scale;
+    const float flx = floorf(sx), fly = floorf(sy), flz = floorf(sz);
+    const uint32_t cx = (uint32_t)(int)ceilf(sx), cy = (uint32_t)(int)ceilf(sy), cz = (uint32_t)(int)ceilf(sz);
+    const uint32_t fx = (uint32_t)(int)flx, fy = (uint32_t)(int)fly, fz = (uint32_t)(int)flz;
+    ox = sx - flx;
+    oy = sy - fly;
+    oz = sz - flz;
+    // low log2(T) bits of the int64 product == low bits of the uint32-wrapped product
+    const uint32_t hcy = cy * 2654435761u, hfy = fy * 2654435761u;
+    const uint32_t hcz = cz * 805459861u, hfz = fz * 805459861u;
+    idx[0] = ((cx ^ hcy ^ hcz) & tmask) + base;
+    idx[1] = ((cx ^ hfy ^ hcz) & tmask) + base;
+    idx[2] = ((fx ^ hfy ^ hcz) & tmask) + base;
+    idx[3] = ((fx ^ hcy ^ hcz) & tmask) + base;
+    idx[4] = ((cx ^ hcy ^ hfz) & tmask) + base;
+    idx[5] = ((cx ^ hfy ^ hfz) & tmask) + base;
+    idx[6] = ((fx ^ hfy ^ hfz) & tmask) + base;
+    idx[7] = ((fx ^ hcy ^ hfz) & tmask) + base;
+}
+
+__device__ __forceinline__ float2 blend(const float2 (&f)[8], float ox, float oy, float oz) {
+    const float ux = 1.0f - ox, uy = 1.0f - oy, uz = 1.0f - oz;
+    float2 r;
+    {
+        const float f03 = f[0].x * ox + f[3].x * ux;
+        const float f12 = f[1].x * ox + f[2].x * ux;
+        const float f56 = f[5].x * ox + f[6].x * ux;
+        const float f47 = f[4].x * ox + f[7].x * ux;
+        const float f0312 = f03 * oy + f12 * uy;
+        const float f4756 = f47 * oy + f56 * uy;
+        r.x = f0312 * oz + f4756 * uz;
+    }
+    {
+        const float f03 = f[0].y * ox + f[3].y * ux;
+        const float f12 = f[1].y * ox + f[2].y * ux;
+        const float f56 = f[5].y * ox + f[6].y * ux;
+        const float f47 = f[4].y * ox + f[7].y * ux;
+        const float f0312 = f03 * oy + f12 * uy;
+        const float f4756 = f47 * oy + f56 * uy;
+        r.y = f0312 * oz + f4756 * uz;
+    }
+    return r;
+}
+
+struct SrcPoints {
+    umhs_points P;
+    __device__ __forceinline__ void get(int64_t n, float &x, float &y, float &z) const {
+        const Point p = eval_point(P, n);
+        x = p.x;
+        y = p.y;
+        z = p.z;
+    }
+};
+
+struct SrcX01 {
+    const float *x01;
+    __device__ __forceinline__ void get(int64_t n, float &x, float &y, float &z) const {
+        x = __ldg(x01 + 3 * n + 0);
+        y = __ldg(x01 + 3 * n + 1);
+        z = __ldg(x01 + 3 * n + 2);
+    }
+};
+
+constexpr int kHashThreads = 256;
+
+template <class Src>
+__global__ void __launch_bounds__(kHashThreads)
+hash_encode_fwd_kernel(Src src, int64_t n_total, const float2 *__restrict__ table, const float *__restrict__ scalings,
+                       int L, int log2T, float *__restrict__ enc) {
+    const int64_t n = (int64_t)blockIdx.x * kHashThreads + threadIdx.x;
+    if (n >= n_total) return;
+    float x, y, z;
+    src.get(n, x, y, z);
+    const uint32_t tmask = (log2T >= 32) ? 0xffffffffu : ((1u << log2T) - 1u);
+    float *out = enc + n * (2 * L);
+    int l = 0;
+    for (; l + 1 < L; l += 2) {
+        uint32_t i0[8], i1[8];
+        float ox0, oy0, oz0, ox1, oy1, oz1;
+        level_setup(x, y, z, __ldg(scalings + l), tmask, (uint32_t)l << log2T, i0, ox0, oy0, oz0);
+        level_setup(x, y, z, __ldg(scalings + l + 1), tmask, (uint32_t)(l + 1) << log2T, i1, ox1, oy1, oz1);
+        float2 f0[8], f1[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) f0[c] = __ldg(table + i0[c]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) f1[c] = __ldg(table + i1[c]);
+        const float2 a = blend(f0, ox0, oy0, oz0);
+        const float2 b = blend(f1, ox1, oy1, oz1);
+        if ((L & 1) == 0) {
+            *reinterpret_cast<float4 *>(out + 2 * l) = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+            *reinterpret_cast<float2 *>(out + 2 * l) = a;
+            *reinterpret_cast<float2 *>(out + 2 * l + 2) = b;
+        }
+    }
+    if (l < L) {
+        uint32_t i0[8];
+        float ox0, oy0, oz0;
+        level_setup(x, y, z, __ldg(scalings + l), tmask, (uint32_t)l << log2T, i0, ox0, oy0, oz0);
+        float2 f0[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) f0[c] = __ldg(table + i0[c]);
+        *reinterpret_cast<float2 *>(out + 2 * l) = blend(f0, ox0, oy0, oz0);
+    }
+}
+
+// One float2 reduction into the table.  Lanes of a warp hold consecutive samples of a ray, so at
+// coarse levels runs of adjacent lanes hit the same entry: a segmented warp scan sums each run and
+// only its last lane issues the red.global.add.v2.f32 (warp-aggregated atomics).
+template <bool AGGREGATE>
+__device__ __forceinline__ void scatter_add(float2 *table, uint32_t idx, float2 v, int lane) {
+    if (AGGREGATE) {
+        const uint32_t prev = __shfl_up_sync(kFull, idx, 1);
+        const bool head = (lane == 0) || (prev != idx);
+        const unsigned heads = __ballot_sync(kFull, head);
+        // start lane of my run = highest head bit at or below my lane
+        const unsigned below = heads & (0xffffffffu >> (31 - lane));
+        const int start = 31 - __clz(below);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float tx = __shfl_up_sync(kFull, v.x, o);
+            const float ty = __shfl_up_sync(kFull, v.y, o);
+            if (lane - o >= start) {
+                v.x += tx;
+                v.y += ty;
+            }
+        }
+        const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
+        if (tail && (v.x != 0.0f || v.y != 0.0f)) atomicAdd(table + idx, v);
+    } else {
+        if (v.x != 0.0f || v.y != 0.0f) atomicAdd(table + idx, v);
+    }
+}
+
+template <class Src>
+__global__ void __launch_bounds__(kHashThreads)
+hash_encode_bwd_kernel(Src src, int64_t n_total, const float *__restrict__ scalings, int L, int log2T,
+                       const float *__restrict__ d_enc, float2 *__restrict__ d_table, int agg_levels) {
+    const int64_t n = (int64_t)blockIdx.x * kHashThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = n < n_total;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (valid) src.get(n, x, y, z);
+    const uint32_t tmask = (log2T >= 32) ? 0xffffffffu : ((1u << log2T) - 1u);
+    const float *g = d_enc + (valid ? n : 0) * (2 * L);
+    for (int l = 0; l < L; ++l) {
+        uint32_t idx[8];
+        float ox, oy, oz;
+        level_setup(x, y, z, __ldg(scalings + l), tmask, (uint32_t)l << log2T, idx, ox, oy, oz);
+        float2 d = valid ? __ldg(reinterpret_cast<const float2 *>(g + 2 * l)) : make_float2(0.f, 0.f);
+        const float ux = 1.0f - ox, uy = 1.0f - oy, uz = 1.0f - oz;
+        // weight of corner (X,Y,Z): (X==c ? o : 1-o) per axis; cz side carries oz
+        const float wz[2] = {oz, uz};
+        const float wxy[4] = {ox * oy, ox * uy, ux * uy, ux * oy};  // (c,c) (c,f) (f,f) (f,c)
+        if (l < agg_levels) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float w = wxy[c & 3] * wz[c >> 2];
+                scatter_add<true>(d_table, idx[c], make_float2(w * d.x, w * d.y), lane);
+            }
+        } else if (valid) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float w = wxy[c & 3] * wz[c >> 2];
+                scatter_add<false>(d_table, idx[c], make_float2(w * d.x, w * d.y), lane);
+            }
+        }
+    }
+}
+
+static int check_grid(const umhs_hash_grid *g) {
+    if (!g || !g->table || !g->scalings) return -1;
+    if (g->num_levels < 1 || g->num_levels > UMHS_MAX_LEVELS) return -1;
+    if (g->log2_table_size < 1 || g->log2_table_size > 28) return -1;
+    if ((int64_t)g->num_levels << g->log2_table_size > (int64_t)1 << 32) return -1;
+    return 0;
+}
+
+// number of leading (coarse) levels whose scatter is warp-aggregated: cell edge >= ~2 sample steps
+static int agg_levels_for(const umhs_hash_grid *g) { return g->num_levels < 10 ? g->num_levels : 10; }
+
+}  // namespace umhs
+
+using namespace umhs;
+
+extern "C" int umhs_hash_encode_fwd(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid, float *enc,
+                                    void *stream) {
+    UMHS_CHECK_ARG(pts != nullptr && enc != nullptr, "null argument");
+    UMHS_CHECK_ARG(check_grid(grid) == 0, "bad hash grid");
+    UMHS_CHECK_ARG(pts->positions || (pts->rays_o && pts->rays_d && pts->ray_indices && pts->t_starts && pts->t_ends),
+                   "points need positions or the ray form");
+    if (n <= 0) return UMHS_OK;
+    SrcPoints src{*pts};
+    hash_encode_fwd_kernel<<<div_up(n, kHashThreads), kHashThreads, 0, as_stream(stream)>>>(
+        src, n, reinterpret_cast<const float2 *>(grid->table), grid->scalings, grid->num_levels,
+        grid->log2_table_size, enc);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_hash_encode_bwd(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid, const float *d_enc,
+                                    float *d_table, void *stream) {
+    UMHS_CHECK_ARG(pts != nullptr && d_enc != nullptr && d_table != nullptr, "null argument");
+    UMHS_CHECK_ARG(check_grid(grid) == 0, "bad hash grid");
+    if (n <= 0) return UMHS_OK;
+    SrcPoints src{*pts};
+    hash_encode_bwd_kernel<<<div_up(n, kHashThreads), kHashThreads, 0, as_stream(stream)>>>(
+        src, n, grid->scalings, grid->num_levels, grid->log2_table_size, d_enc, reinterpret_cast<float2 *>(d_table),
+        agg_levels_for(grid));
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_hash_encode_x01_fwd(const float *x01, int64_t n, const umhs_hash_grid *grid, float *enc,
+                                        void *stream) {
+    UMHS_CHECK_ARG(x01 != nullptr && enc != nullptr, "null argument");
+    UMHS_CHECK_ARG(check_grid(grid) == 0, "bad hash grid");
+    if (n <= 0) return UMHS_OK;
+    SrcX01 src{x01};
+    hash_encode_fwd_kernel<<<div_up(n, kHashThreads), kHashThreads, 0, as_stream(stream)>>>(
+        src, n, reinterpret_cast<const float2 *>(grid->table), grid->scalings, grid->num_levels,
+        grid->log2_table_size, enc);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_hash_encode_x01_bwd(const float *x01, int64_t n, const umhs_hash_grid *grid, const float *d_enc,
+                                        float *d_table, void *stream) {
+    UMHS_CHECK_ARG(x01 != nullptr && d_enc != nullptr && d_table != nullptr, "null argument");
+    UMHS_CHECK_ARG(check_grid(grid) == 0, "bad hash grid");
+    if (n <= 0) return UMHS_OK;
+    SrcX01 src{x01};
+    hash_encode_bwd_kernel<<<div_up(n, kHashThreads), kHashThreads, 0, as_stream(stream)>>>(
+        src, n, grid->scalings, grid->num_levels, grid->log2_table_size, d_enc, reinterpret_cast<float2 *>(d_table),
+        agg_levels_for(grid));
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}

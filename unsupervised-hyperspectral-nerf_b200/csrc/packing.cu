@@ -1,0 +1,442 @@
+// packing.cu -- occupancy-grid ray marching, sample packing and ray-index bookkeeping.
+//
+// Replaces nerfstudio VolumetricSampler / nerfacc 0.5.2 OccGridEstimator.sampling
+// (traverse_grids, render_visibility_from_density, boolean-mask compaction) reached from
+// ref umhsnerf/umhs_model.py:229-237, nerfacc.pack_info (ref umhsnerf/umhs_model.py:245) and
+// the occupancy-grid update callback (ref umhsnerf/umhs_model.py:549-554).
+//
+// THIS TRANSLATION UNIT IS COMPILED WITH -fmad=false: march_ray() executes the same IEEE fp32
+// operation sequence as oracle/pack_oracle.c (gcc -ffp-contract=off), so ray_indices, t_starts,
+// t_ends and packed_info are bit-exact against it.
+//
+// HBM-bound integer/byte work: one thread per ray for the DDA (divergent by nature; rays of a
+// batch are independent), one warp per ray for the visibility scan and the compaction, a
+// single-CTA scan for the offsets (R is 1e4..5e5).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace umhs {
+
+constexpr int kMaxGridLevels = 8;
+constexpr float kMissT = 1e10f;
+
+__device__ __forceinline__ bool ray_aabb(const float o[3], const float inv[3], const float *aabb, float &tmin_o,
+                                         float &tmax_o) {
+    float tmin, tmax, t0, t1;
+    if (inv[0] >= 0) { tmin = (aabb[0] - o[0]) * inv[0]; tmax = (aabb[3] - o[0]) * inv[0]; }
+    else             { tmin = (aabb[3] - o[0]) * inv[0]; tmax = (aabb[0] - o[0]) * inv[0]; }
+    if (inv[1] >= 0) { t0 = (aabb[1] - o[1]) * inv[1]; t1 = (aabb[4] - o[1]) * inv[1]; }
+    else             { t0 = (aabb[4] - o[1]) * inv[1]; t1 = (aabb[1] - o[1]) * inv[1]; }
+    if (tmin > t1 || t0 > tmax) return false;
+    if (t0 > tmin) tmin = t0;
+    if (t1 < tmax) tmax = t1;
+    if (inv[2] >= 0) { t0 = (aabb[2] - o[2]) * inv[2]; t1 = (aabb[5] - o[2]) * inv[2]; }
+    else             { t0 = (aabb[5] - o[2]) * inv[2]; t1 = (aabb[2] - o[2]) * inv[2]; }
+    if (tmin > t1 || t0 > tmax) return false;
+    if (t0 > tmin) tmin = t0;
+    if (t1 < tmax) tmax = t1;
+    if (tmax <= 0) return false;
+    tmin_o = tmin;
+    tmax_o = tmax;
+    return true;
+}
+
+__device__ __forceinline__ float calc_dt(float t, float cone_angle, float dt_min, float dt_max) {
+    float v = t * cone_angle;
+    v = v < dt_min ? dt_min : v;
+    v = v > dt_max ? dt_max : v;
+    return v;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ __forceinline__ int voxel_index(float v, float fres, int res) {
+    v = v < -1.0f ? -1.0f : (v > fres ? fres : v);
+    return clampi((int)v, 0, res - 1);
+}
+
+// March one ray (twin of oracle/pack_oracle.c::march_ray).  WRITE=false only counts.
+template <bool WRITE>
+__device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *__restrict__ binaries,
+                             const float *__restrict__ aabbs, int levels, int res, float near_plane, float far_plane,
+                             float step_size, float cone_angle, float *t0_out, float *t1_out) {
+    const float inv[3] = {1.0f / d[0], 1.0f / d[1], 1.0f / d[2]};
+    float tmins[kMaxGridLevels], tmaxs[kMaxGridLevels], ts[2 * kMaxGridLevels];
+    bool hits[kMaxGridLevels];
+    for (int l = 0; l < levels; ++l) {
+        float a = kMissT, b = kMissT;
+        hits[l] = ray_aabb(o, inv, aabbs + 6 * l, a, b);
+        if (!hits[l]) { a = kMissT; b = kMissT; }
+        tmins[l] = a; tmaxs[l] = b;
+        ts[l] = a; ts[levels + l] = b;
+    }
+    for (int i = 1; i < 2 * levels; ++i) {  // insertion sort
+        const float v = ts[i];
+        int j = i - 1;
+        while (j >= 0 && ts[j] > v) { ts[j + 1] = ts[j]; --j; }
+        ts[j + 1] = v;
+    }
+    const float fres = (float)res;
+    const int64_t cells_per_level = (int64_t)res * res * res;
+    int64_t n = 0;
+    float t_last = near_plane;
+    for (int i = 0; i < 2 * levels - 1; ++i) {
+        const float a = ts[i], b = ts[i + 1];
+        if (!(a < b)) continue;
+        int level = -1;
+        for (int l = 0; l < levels; ++l)
+            if (hits[l] && tmins[l] <= a && b <= tmaxs[l]) { level = l; break; }
+        if (level < 0) continue;
+        const float this_tmin = fmaxf(a, near_plane);
+        const float this_tmax = fminf(b, far_plane);
+        if (!(this_tmin < this_tmax)) continue;
+        const float *aabb = aabbs + 6 * level;
+        const float eps = 1e-6f;
+        float delta[3], tdist[3];
+        int cur[3], over[3], stepi[3];
+        for (int k = 0; k < 3; ++k) {
+            const float ext = aabb[3 + k] - aabb[k];
+            const float voxel = ext / fres;
+            const float rs = o[k] + d[k] * (this_tmin + eps);
+            const float re = o[k] + d[k] * (this_tmax - eps);
+            cur[k] = voxel_index(((rs - aabb[k]) / ext) * fres, fres, res);
+            const int fin = voxel_index(((re - aabb[k]) / ext) * fres, fres, res);
+            const int start_index = cur[k] + (d[k] > 0.0f ? 1 : 0);
+            const float tmax_k = ((aabb[k] + (((float)start_index * voxel) - rs)) * inv[k]) + this_tmin;
+            const float sf = (d[k] == 0.0f) ? 0.0f : (d[k] > 0.0f ? 1.0f : -1.0f);
+            stepi[k] = (int)sf;
+            tdist[k] = (d[k] == 0.0f) ? this_tmax : tmax_k;
+            delta[k] = (d[k] == 0.0f) ? this_tmax : (voxel * inv[k]) * sf;
+            over[k] = fin + stepi[k];
+        }
+        for (int guard = 0; guard < 4 * res + 8; ++guard) {
+            float t_traverse = fminf(tdist[0], fminf(tdist[1], tdist[2]));
+            t_traverse = fminf(t_traverse, this_tmax);
+            const int64_t cell = (int64_t)level * cells_per_level + ((int64_t)cur[0] * res + cur[1]) * res + cur[2];
+            if (!__ldg(binaries + cell)) {
+                for (;;) {
+                    const float dt = calc_dt(t_last, cone_angle, step_size, 1e10f);
+                    if (t_last + dt * 0.5f >= t_traverse) break;
+                    t_last += dt;
+                }
+            } else {
+                for (;;) {
+                    const float dt = calc_dt(t_last, cone_angle, step_size, 1e10f);
+                    if (t_last + dt * 0.5f >= t_traverse) break;
+                    if (WRITE) { t0_out[n] = t_last; t1_out[n] = t_last + dt; }
+                    ++n;
+                    t_last += dt;
+                }
+            }
+            int ax;
+            if (tdist[0] < tdist[1] && tdist[0] < tdist[2]) ax = 0;
+            else if (tdist[1] < tdist[2]) ax = 1;
+            else ax = 2;
+            // register-friendly update of axis `ax`
+            if (ax == 0)      { cur[0] += stepi[0]; tdist[0] += delta[0]; if (cur[0] == over[0] || cur[0] < 0 || cur[0] >= res) break; }
+            else if (ax == 1) { cur[1] += stepi[1]; tdist[1] += delta[1]; if (cur[1] == over[1] || cur[1] < 0 || cur[1] >= res) break; }
+            else              { cur[2] += stepi[2]; tdist[2] += delta[2]; if (cur[2] == over[2] || cur[2] < 0 || cur[2] >= res) break; }
+        }
+    }
+    return n;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(128)
+march_kernel(umhs_march_args a, int64_t *counts, const int64_t *packed_info, int64_t *ray_indices, float *t_starts,
+             float *t_ends) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n_rays) return;
+    const float o[3] = {__ldg(a.rays_o + 3 * r), __ldg(a.rays_o + 3 * r + 1), __ldg(a.rays_o + 3 * r + 2)};
+    const float d[3] = {__ldg(a.rays_d + 3 * r), __ldg(a.rays_d + 3 * r + 1), __ldg(a.rays_d + 3 * r + 2)};
+    if (!WRITE) {
+        counts[r] = march_ray<false>(o, d, a.binaries, a.aabbs, a.levels, a.resolution, __ldg(a.near_planes + r),
+                                     __ldg(a.far_planes + r), a.step_size, a.cone_angle, nullptr, nullptr);
+    } else {
+        const int64_t off = __ldg(packed_info + 2 * r);
+        const int64_t n = march_ray<true>(o, d, a.binaries, a.aabbs, a.levels, a.resolution, __ldg(a.near_planes + r),
+                                          __ldg(a.far_planes + r), a.step_size, a.cone_angle, t_starts + off,
+                                          t_ends + off);
+        for (int64_t i = 0; i < n; ++i) ray_indices[off + i] = r;
+    }
+}
+
+// Single-CTA exclusive scan of int64 counts -> packed_info[r] = (offset, count); *total = sum.
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads)
+pack_scan_kernel(const int64_t *__restrict__ counts, int64_t n, int64_t *__restrict__ packed_info, int64_t *total) {
+    __shared__ int64_t warp_sums[32];
+    __shared__ int64_t base_s, tile_total_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    // tiles of kScanThreads consecutive elements: coalesced loads, warp-shuffle scan per tile
+    for (int64_t t0 = 0; t0 < n; t0 += kScanThreads) {
+        const int64_t i = t0 + tid;
+        const int64_t v = i < n ? counts[i] : 0;
+        int64_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int64_t w = warp_sums[lane];
+            int64_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t t = __shfl_up_sync(kFull, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_sums[lane] = wi - w;  // exclusive warp offsets
+            if (lane == 31) tile_total_s = wi;
+        }
+        __syncthreads();
+        const int64_t excl = base_s + warp_sums[warp] + (incl - v);
+        if (i < n) {
+            packed_info[2 * i] = excl;
+            packed_info[2 * i + 1] = v;
+        }
+        __syncthreads();
+        if (tid == 0) base_s += tile_total_s;
+        __syncthreads();
+    }
+    if (tid == 0 && total) *total = base_s;
+}
+
+// keep = (T >= early_stop_eps) & (alpha >= alpha_thre), one warp per ray.
+constexpr int kVisWarps = 8;
+__global__ void __launch_bounds__(kVisWarps * 32)
+visibility_kernel(const int64_t *__restrict__ packed_info, int64_t n_rays, const float *__restrict__ t_starts,
+                  const float *__restrict__ t_ends, const float *__restrict__ sigma, float early_stop_eps,
+                  float alpha_thre, const float *__restrict__ occ_mean, uint8_t *__restrict__ keep,
+                  int64_t *__restrict__ keep_counts) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * kVisWarps + (threadIdx.x >> 5);
+    if (r >= n_rays) return;
+    float thre = alpha_thre;
+    if (occ_mean) thre = fminf(thre, __ldg(occ_mean));
+    const int64_t start = __ldg(packed_info + 2 * r), cnt = __ldg(packed_info + 2 * r + 1);
+    float carry = 0.f;
+    int64_t kept = 0;
+    for (int64_t c0 = 0; c0 < cnt; c0 += 32) {
+        const int64_t n = start + c0 + lane;
+        const bool v = c0 + lane < cnt;
+        float sd = 0.f;
+        if (v) sd = __ldg(sigma + n) * (__ldg(t_ends + n) - __ldg(t_starts + n));
+        const float incl = warp_incl_scan(sd, lane);
+        const float T = expf(-(carry + (incl - sd)));
+        const float alpha = 1.0f - expf(-sd);
+        carry += __shfl_sync(kFull, incl, 31);
+        bool k = v && (T >= early_stop_eps);
+        if (thre > 0.0f) k = k && (alpha >= thre);
+        if (v) keep[n] = k ? 1 : 0;
+        kept += __popc(__ballot_sync(kFull, k));
+    }
+    if (lane == 0) keep_counts[r] = kept;
+}
+
+__global__ void __launch_bounds__(kVisWarps * 32)
+compact_kernel(const int64_t *__restrict__ pin, const int64_t *__restrict__ pout, int64_t n_rays,
+               const uint8_t *__restrict__ keep, const float *__restrict__ t0_in, const float *__restrict__ t1_in,
+               int64_t *__restrict__ ray_indices, float *__restrict__ t0, float *__restrict__ t1) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * kVisWarps + (threadIdx.x >> 5);
+    if (r >= n_rays) return;
+    const int64_t start = __ldg(pin + 2 * r), cnt = __ldg(pin + 2 * r + 1);
+    int64_t dst = __ldg(pout + 2 * r);
+    for (int64_t c0 = 0; c0 < cnt; c0 += 32) {
+        const int64_t n = start + c0 + lane;
+        const bool k = (c0 + lane < cnt) && keep[n];
+        const unsigned m = __ballot_sync(kFull, k);
+        if (k) {
+            const int64_t j = dst + __popc(m & ((1u << lane) - 1u));
+            ray_indices[j] = r;
+            t0[j] = t0_in[n];
+            t1[j] = t1_in[n];
+        }
+        dst += __popc(m);
+    }
+}
+
+__global__ void count_rays_kernel(const int64_t *__restrict__ ray_indices, int64_t n, int64_t n_rays,
+                                  unsigned long long *counts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t r = ray_indices[i];
+    if (r >= 0 && r < n_rays) atomicAdd(counts + r, 1ull);
+}
+
+// ------------------------------------------------------------------ occupancy grid maintenance
+__global__ void occ_cell_points_kernel(const int64_t *__restrict__ cell_ids, const float *__restrict__ jitter,
+                                       int64_t n, int res, const float *__restrict__ aabb, float *__restrict__ pos) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t id = cell_ids ? cell_ids[i] : i;
+    const float fres = (float)res;
+    const float c[3] = {(float)(id / ((int64_t)res * res)), (float)((id / res) % res), (float)(id % res)};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float x = (c[k] + jitter[3 * i + k]) / fres;
+        pos[3 * i + k] = aabb[k] + x * (aabb[3 + k] - aabb[k]);
+    }
+}
+
+// occs[id] = max(occs[id] * decay, sigma * scale): phase 1 reads, phase 2 scatters (torch index-assign
+// semantics: the right-hand side sees only old values; duplicate ids: any one of them wins)
+__global__ void occ_ema_read_kernel(const float *__restrict__ occs, const int64_t *__restrict__ cell_ids,
+                                    int64_t level_offset, const float *__restrict__ sigma, float scale, float decay,
+                                    int64_t n, float *__restrict__ tmp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t id = (cell_ids ? cell_ids[i] : i) + level_offset;
+    tmp[i] = fmaxf(occs[id] * decay, sigma[i] * scale);
+}
+__global__ void occ_ema_write_kernel(float *__restrict__ occs, const int64_t *__restrict__ cell_ids,
+                                     int64_t level_offset, int64_t n, const float *__restrict__ tmp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    occs[(cell_ids ? cell_ids[i] : i) + level_offset] = tmp[i];
+}
+
+__global__ void occ_sum_kernel(const float *__restrict__ occs, int64_t n, double *scratch) {
+    double s = 0.0, c = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = occs[i];
+        if (v >= 0.f) { s += (double)v; c += 1.0; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(kFull, s, o);
+        c += __shfl_xor_sync(kFull, c, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(scratch, s);
+        atomicAdd(scratch + 1, c);
+    }
+}
+
+__global__ void occ_binarize_kernel(const float *__restrict__ occs, int64_t n, float occ_thre, const double *scratch,
+                                    uint8_t *__restrict__ binaries, float *mean_out) {
+    const float mean = (float)(scratch[0] / fmax(scratch[1], 1.0));
+    const float thre = fminf(mean, occ_thre);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && mean_out) *mean_out = mean;
+    if (i < n) binaries[i] = occs[i] > thre ? 1 : 0;
+}
+
+static int check_march(const umhs_march_args *a) {
+    if (!a || !a->rays_o || !a->rays_d || !a->near_planes || !a->far_planes || !a->binaries || !a->aabbs) return -1;
+    if (a->levels < 1 || a->levels > kMaxGridLevels || a->resolution < 1 || a->resolution > 1024) return -1;
+    return 0;
+}
+
+}  // namespace umhs
+
+using namespace umhs;
+
+extern "C" int umhs_march_count(const umhs_march_args *a, int64_t *counts, void *stream) {
+    UMHS_CHECK_ARG(check_march(a) == 0 && counts, "bad march arguments");
+    if (a->n_rays <= 0) return UMHS_OK;
+    march_kernel<false><<<div_up(a->n_rays, 128), 128, 0, as_stream(stream)>>>(*a, counts, nullptr, nullptr, nullptr,
+                                                                               nullptr);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_pack_scan(const int64_t *counts, int64_t n_rays, int64_t *packed_info, int64_t *total,
+                              void *stream) {
+    UMHS_CHECK_ARG(counts && packed_info, "null argument");
+    UMHS_CHECK_ARG(n_rays >= 0, "negative n_rays");
+    pack_scan_kernel<<<1, kScanThreads, 0, as_stream(stream)>>>(counts, n_rays, packed_info, total);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_march_write(const umhs_march_args *a, const int64_t *packed_info, int64_t *ray_indices,
+                                float *t_starts, float *t_ends, void *stream) {
+    UMHS_CHECK_ARG(check_march(a) == 0 && packed_info && ray_indices && t_starts && t_ends, "bad march arguments");
+    if (a->n_rays <= 0) return UMHS_OK;
+    march_kernel<true><<<div_up(a->n_rays, 128), 128, 0, as_stream(stream)>>>(*a, nullptr, packed_info, ray_indices,
+                                                                              t_starts, t_ends);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_visibility_mask(const int64_t *packed_info, int64_t n_rays, const float *t_starts,
+                                    const float *t_ends, const float *sigma, float early_stop_eps, float alpha_thre,
+                                    const float *occ_mean, uint8_t *keep, int64_t *keep_counts, void *stream) {
+    UMHS_CHECK_ARG(packed_info && t_starts && t_ends && sigma && keep && keep_counts, "null argument");
+    if (n_rays <= 0) return UMHS_OK;
+    visibility_kernel<<<div_up(n_rays, kVisWarps), kVisWarps * 32, 0, as_stream(stream)>>>(
+        packed_info, n_rays, t_starts, t_ends, sigma, early_stop_eps, alpha_thre, occ_mean, keep, keep_counts);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_compact_samples(const int64_t *packed_info_in, const int64_t *packed_info_out, int64_t n_rays,
+                                    const uint8_t *keep, const float *t_starts_in, const float *t_ends_in,
+                                    int64_t *ray_indices, float *t_starts, float *t_ends, void *stream) {
+    UMHS_CHECK_ARG(packed_info_in && packed_info_out && keep && t_starts_in && t_ends_in && ray_indices && t_starts &&
+                       t_ends,
+                   "null argument");
+    if (n_rays <= 0) return UMHS_OK;
+    compact_kernel<<<div_up(n_rays, kVisWarps), kVisWarps * 32, 0, as_stream(stream)>>>(
+        packed_info_in, packed_info_out, n_rays, keep, t_starts_in, t_ends_in, ray_indices, t_starts, t_ends);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_pack_info(const int64_t *ray_indices, int64_t n, int64_t n_rays, int64_t *counts,
+                              int64_t *packed_info, void *stream) {
+    UMHS_CHECK_ARG(counts && packed_info && (ray_indices || n == 0), "null argument");
+    UMHS_CHECK_ARG(n_rays >= 0 && n >= 0, "negative size");
+    cudaStream_t st = as_stream(stream);
+    if (n_rays > 0) UMHS_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(int64_t) * n_rays, st));
+    if (n > 0) {
+        count_rays_kernel<<<div_up(n, 256), 256, 0, st>>>(ray_indices, n, n_rays,
+                                                         reinterpret_cast<unsigned long long *>(counts));
+        UMHS_CHECK_LAUNCH();
+    }
+    pack_scan_kernel<<<1, kScanThreads, 0, st>>>(counts, n_rays, packed_info, nullptr);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_occ_cell_points(const int64_t *cell_ids, const float *jitter, int64_t n, int32_t resolution,
+                                    const float *aabb6, float *positions, void *stream) {
+    UMHS_CHECK_ARG(jitter && aabb6 && positions && resolution > 0, "bad argument");
+    if (n <= 0) return UMHS_OK;
+    occ_cell_points_kernel<<<div_up(n, 256), 256, 0, as_stream(stream)>>>(cell_ids, jitter, n, resolution, aabb6,
+                                                                          positions);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_occ_ema_update(float *occs, const int64_t *cell_ids, int64_t level_offset, const float *sigma,
+                                   float scale, float decay, int64_t n, float *tmp, void *stream) {
+    UMHS_CHECK_ARG(occs && sigma && tmp, "null argument");
+    if (n <= 0) return UMHS_OK;
+    occ_ema_read_kernel<<<div_up(n, 256), 256, 0, as_stream(stream)>>>(occs, cell_ids, level_offset, sigma, scale,
+                                                                       decay, n, tmp);
+    UMHS_CHECK_LAUNCH();
+    occ_ema_write_kernel<<<div_up(n, 256), 256, 0, as_stream(stream)>>>(occs, cell_ids, level_offset, n, tmp);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_occ_binarize(const float *occs, int64_t n_cells, float occ_thre, double *scratch,
+                                 uint8_t *binaries, float *mean_out, void *stream) {
+    UMHS_CHECK_ARG(occs && scratch && binaries, "null argument");
+    if (n_cells <= 0) return UMHS_OK;
+    cudaStream_t st = as_stream(stream);
+    UMHS_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(double), st));
+    occ_sum_kernel<<<kNumSMs * 4, 256, 0, st>>>(occs, n_cells, scratch);
+    UMHS_CHECK_LAUNCH();
+    occ_binarize_kernel<<<div_up(n_cells, 256), 256, 0, st>>>(occs, n_cells, occ_thre, scratch, binaries, mean_out);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}

@@ -1,0 +1,163 @@
+"""Occupancy grid + packed ray-sample generation (B200-native twin of nerfacc 0.5.2 OccGridEstimator and
+nerfstudio VolumetricSampler, reached from ref umhsnerf/umhs_model.py:198-212, 229-237, 549-554).
+
+State-dict names and shapes follow nerfacc (``resolution``, ``aabbs``, ``occs``, ``binaries``) so reference
+checkpoints load.  Marching, the visibility filter, compaction and the grid update run in
+libumhs_sm100.so (csrc/packing.cu).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Callable, List, Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib, ops
+from ._lib import check, ptr, stream_ptr
+from .ops import PointSet
+
+
+class OccGridEstimator(nn.Module):
+    def __init__(self, roi_aabb: Tensor, resolution: int = 128, levels: int = 4):
+        super().__init__()
+        roi = torch.as_tensor(roi_aabb, dtype=torch.float32).flatten()
+        self.levels = int(levels)
+        res = int(resolution)
+        c, half = (roi[:3] + roi[3:]) / 2, (roi[3:] - roi[:3]) / 2
+        aabbs = torch.stack([torch.cat([c - half * 2 ** l, c + half * 2 ** l]) for l in range(levels)], dim=0)
+        self.register_buffer("resolution", torch.tensor([res] * 3, dtype=torch.int32))
+        self.register_buffer("aabbs", aabbs)
+        self.register_buffer("occs", torch.zeros(levels * res ** 3))
+        self.register_buffer("binaries", torch.zeros((levels, res, res, res), dtype=torch.bool))
+        self._res = res
+        self._occ_mean: Optional[Tensor] = None  # device scalar cache of occs.mean()
+
+    def mark_dirty(self) -> None:
+        """Call after writing ``occs`` by hand (tests, checkpoint surgery)."""
+        self._occ_mean = None
+
+    def _load_from_state_dict(self, *a, **k):
+        self._occ_mean = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def occ_mean(self) -> Tensor:
+        if self._occ_mean is None or self._occ_mean.device != self.occs.device:
+            self._occ_mean = self.occs.mean().reshape(1).contiguous()
+        return self._occ_mean
+
+    # ------------------------------------------------------------------ sampling (A.4)
+    @torch.no_grad()
+    def sampling(self, rays_o: Tensor, rays_d: Tensor, sigma_fn: Optional[Callable] = None, near_plane: float = 0.0,
+                 far_plane: float = 1e10, t_min: Optional[Tensor] = None, t_max: Optional[Tensor] = None,
+                 render_step_size: float = 1e-3, early_stop_eps: float = 1e-4, alpha_thre: float = 0.0,
+                 stratified: bool = False, cone_angle: float = 0.0, jitter: Optional[Tensor] = None,
+                 return_packed_info: bool = False):
+        """-> (ray_indices int64 [N], t_starts [N], t_ends [N]) (+ packed_info [R,2]).  ``sigma_fn(t_starts, t_ends,
+        ray_indices) -> sigma [N]`` enables the visibility filter, as in nerfacc.  ``jitter`` injects the stratified
+        draw (nerfacc: ``torch.rand_like(near_planes)``) so parity tests see identical near planes."""
+        near = torch.full_like(rays_o[..., 0], fill_value=near_plane)
+        far = torch.full_like(rays_o[..., 0], fill_value=far_plane)
+        if t_min is not None:
+            near = torch.clamp(near, min=t_min)
+        if t_max is not None:
+            far = torch.clamp(far, max=t_max)
+        if stratified:
+            if jitter is None:
+                jitter = torch.rand_like(near)
+            near = near + jitter * render_step_size
+        ri, t0, t1, packed = ops.march(rays_o, rays_d, near, far, self.binaries, self.aabbs, render_step_size,
+                                       cone_angle)
+        if (alpha_thre > 0.0 or early_stop_eps > 0.0) and sigma_fn is not None and t0.shape[0] > 0:
+            sigma = sigma_fn(t0, t1, ri)
+            ri, t0, t1, packed = ops.visibility_compact(packed, t0, t1, sigma, early_stop_eps, alpha_thre,
+                                                        self.occ_mean() if alpha_thre > 0.0 else None)
+        if return_packed_info:
+            return ri, t0, t1, packed
+        return ri, t0, t1
+
+    # ------------------------------------------------------------------ update (A.4)
+    @torch.no_grad()
+    def update_every_n_steps(self, step: int, occ_eval_fn: Callable, occ_thre: float = 1e-2, ema_decay: float = 0.95,
+                             warmup_steps: int = 256, n: int = 16, cell_ids: Optional[List[Tensor]] = None,
+                             cell_jitter: Optional[List[Tensor]] = None) -> None:
+        """occs[id] = max(occs[id]*decay, occ_eval_fn(x)); binaries = occs > min(mean(occs), occ_thre).
+        ``cell_ids`` / ``cell_jitter`` (per level) inject the random draws for parity tests."""
+        if not (self.training and step % n == 0):
+            return
+        lib = _lib.load()
+        dev = self.occs.device
+        res, n_cells = self._res, self._res ** 3
+        st = stream_ptr(dev)
+        for lvl in range(self.levels):
+            if cell_ids is not None:
+                idx = cell_ids[lvl].to(torch.int64).contiguous()
+            elif step < warmup_steps:
+                idx = None  # all cells, in order
+            else:
+                n_u = n_cells // 4
+                uni = torch.randint(n_cells, (n_u,), device=dev)
+                occ_idx = torch.nonzero(self.binaries[lvl].flatten())[:, 0]
+                if n_u < len(occ_idx):
+                    occ_idx = occ_idx[torch.randint(len(occ_idx), (n_u,), device=dev)]
+                idx = torch.cat([uni, occ_idx], dim=0).contiguous()
+            m = n_cells if idx is None else int(idx.shape[0])
+            if m == 0:
+                continue
+            jit = cell_jitter[lvl].to(torch.float32).contiguous() if cell_jitter is not None else \
+                torch.rand((m, 3), device=dev)
+            pos = torch.empty((m, 3), dtype=torch.float32, device=dev)
+            aabb = self.aabbs[lvl].contiguous()
+            check(lib.umhs_occ_cell_points(ptr(idx), ptr(jit), m, res, ptr(aabb), ptr(pos), st),
+                  "umhs_occ_cell_points")
+            occ = occ_eval_fn(pos).reshape(-1).to(torch.float32).contiguous()
+            tmp = torch.empty((m,), dtype=torch.float32, device=dev)
+            check(lib.umhs_occ_ema_update(ptr(self.occs), ptr(idx), lvl * n_cells, ptr(occ), 1.0, float(ema_decay), m,
+                                          ptr(tmp), st), "umhs_occ_ema_update")
+        scratch = torch.empty((2,), dtype=torch.float64, device=dev)
+        mean = torch.empty((1,), dtype=torch.float32, device=dev)
+        bn = self.binaries.view(torch.uint8)
+        check(lib.umhs_occ_binarize(ptr(self.occs), self.occs.numel(), float(occ_thre), ptr(scratch), ptr(bn),
+                                    ptr(mean), st), "umhs_occ_binarize")
+        self._occ_mean = mean
+
+
+class VolumetricSampler(nn.Module):
+    """nerfstudio VolumetricSampler over the grid above.  ``__call__`` returns packed samples of a ray batch:
+    (PointSet, ray_indices, t_starts, t_ends, packed_info)."""
+
+    def __init__(self, occupancy_grid: OccGridEstimator, field):
+        super().__init__()
+        self.occupancy_grid = occupancy_grid
+        self._field = [field]  # not a submodule: the model owns the field
+
+    @torch.no_grad()
+    def forward(self, ray_bundle, render_step_size: float, near_plane: float = 0.0, far_plane: Optional[float] = None,
+                alpha_thre: float = 0.01, cone_angle: float = 0.0, jitter: Optional[Tensor] = None):
+        field = self._field[0]
+        rays_o = ray_bundle.origins.reshape(-1, 3).to(torch.float32).contiguous()
+        rays_d = ray_bundle.directions.reshape(-1, 3).to(torch.float32).contiguous()
+        t_min = t_max = None
+        if ray_bundle.nears is not None and ray_bundle.fars is not None:
+            t_min = ray_bundle.nears.contiguous().reshape(-1)
+            t_max = ray_bundle.fars.contiguous().reshape(-1)
+        if far_plane is None:
+            far_plane = 1e10
+        sigma_fn = None
+        if self.training:  # nerfstudio builds sigma_fn only while training
+            def sigma_fn(t0, t1, ri):
+                pts = PointSet.from_packed(rays_o, rays_d, ri, t0, t1, contraction=field.contraction,
+                                           aabb=field._aabb6())
+                return field.density_packed(pts)
+        ri, t0, t1, packed = self.occupancy_grid.sampling(
+            rays_o, rays_d, sigma_fn=sigma_fn, near_plane=near_plane, far_plane=far_plane, t_min=t_min, t_max=t_max,
+            render_step_size=render_step_size, stratified=self.training, cone_angle=cone_angle, alpha_thre=alpha_thre,
+            jitter=jitter, return_packed_info=True)
+        if t0.shape[0] == 0:  # nerfstudio fabricates one sample so downstream shapes are never empty
+            dev = rays_o.device
+            ri = torch.zeros((1,), dtype=torch.int64, device=dev)
+            t0 = torch.ones((1,), dtype=torch.float32, device=dev)
+            t1 = torch.ones((1,), dtype=torch.float32, device=dev)
+            packed = ops.pack_info(ri, rays_o.shape[0])
+        pts = PointSet.from_packed(rays_o, rays_d, ri, t0, t1, contraction=field.contraction, aabb=field._aabb6())
+        return pts, ri, t0, t1, packed

@@ -1,0 +1,508 @@
+"""Host-side operators: thin wrappers + torch.autograd.Functions over the C-ABI kernels.
+
+Every function here enqueues hand-written sm_100a kernels from libumhs_sm100.so on torch's
+current CUDA stream.  torch is used for device memory, streams and autograd plumbing only.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import check, f32, ptr, stream_ptr
+
+ENC_DIM = 32  # 16 levels x 2 features
+
+
+# --------------------------------------------------------------------------------------- points
+@dataclass
+class PointSet:
+    """Sample points for the field kernels: explicit positions, or packed samples of a ray batch
+    (position = o[ray] + d[ray] * (t0 + t1) / 2, nerfstudio Frustums.get_positions)."""
+    n: int
+    positions: Optional[Tensor] = None
+    directions: Optional[Tensor] = None
+    rays_o: Optional[Tensor] = None
+    rays_d: Optional[Tensor] = None
+    ray_indices: Optional[Tensor] = None
+    t_starts: Optional[Tensor] = None
+    t_ends: Optional[Tensor] = None
+    contraction: bool = True
+    aabb: Sequence[float] = (-1.0, -1.0, -1.0, 1.0, 1.0, 1.0)
+
+    def struct(self) -> _lib.Points:
+        s = _lib.Points()
+        s.positions = ptr(self.positions)
+        s.directions = ptr(self.directions)
+        s.rays_o = ptr(self.rays_o)
+        s.rays_d = ptr(self.rays_d)
+        s.ray_indices = ptr(self.ray_indices)
+        s.t_starts = ptr(self.t_starts)
+        s.t_ends = ptr(self.t_ends)
+        s.contraction = 1 if self.contraction else 0
+        for i, v in enumerate(self.aabb):
+            s.aabb[i] = float(v)
+        return s
+
+    @property
+    def device(self):
+        return (self.positions if self.positions is not None else self.t_starts).device
+
+    @staticmethod
+    def from_positions(positions: Tensor, directions: Optional[Tensor] = None, contraction=True, aabb=None):
+        p = f32(positions).reshape(-1, 3)
+        d = f32(directions).reshape(-1, 3) if directions is not None else None
+        return PointSet(n=p.shape[0], positions=p, directions=d, contraction=contraction,
+                        aabb=tuple(aabb) if aabb is not None else PointSet.aabb)
+
+    @staticmethod
+    def from_packed(rays_o, rays_d, ray_indices, t_starts, t_ends, contraction=True, aabb=None):
+        return PointSet(n=int(t_starts.shape[0]), rays_o=f32(rays_o), rays_d=f32(rays_d),
+                        ray_indices=ray_indices.to(torch.int64).contiguous(), t_starts=f32(t_starts).reshape(-1),
+                        t_ends=f32(t_ends).reshape(-1), contraction=contraction,
+                        aabb=tuple(aabb) if aabb is not None else PointSet.aabb)
+
+
+def _grid_struct(table: Tensor, scalings: Tensor, log2_T: int) -> _lib.HashGrid:
+    g = _lib.HashGrid()
+    g.table = ptr(table)
+    g.scalings = ptr(scalings)
+    g.num_levels = int(scalings.shape[0])
+    g.log2_table_size = int(log2_T)
+    return g
+
+
+# --------------------------------------------------------------------------------------- hash grid
+def hash_encode_fwd(pts: PointSet, table: Tensor, scalings: Tensor, log2_T: int) -> Tensor:
+    lib = _lib.load()
+    L = int(scalings.shape[0])
+    enc = torch.empty((pts.n, 2 * L), dtype=torch.float32, device=table.device)
+    ps, gs = pts.struct(), _grid_struct(table, scalings, log2_T)
+    check(lib.umhs_hash_encode_fwd(ctypes.byref(ps), pts.n, ctypes.byref(gs), ptr(enc), stream_ptr(table.device)),
+          "umhs_hash_encode_fwd")
+    return enc
+
+
+def hash_encode_bwd(pts: PointSet, table: Tensor, scalings: Tensor, log2_T: int, d_enc: Tensor,
+                    d_table: Optional[Tensor] = None) -> Tensor:
+    """Scatter d_enc into d_table (accumulating).  Allocates a zero table gradient when none is given."""
+    lib = _lib.load()
+    if d_table is None:
+        d_table = torch.zeros_like(table, dtype=torch.float32)
+    ps, gs = pts.struct(), _grid_struct(table, scalings, log2_T)
+    check(lib.umhs_hash_encode_bwd(ctypes.byref(ps), pts.n, ctypes.byref(gs), ptr(d_enc), ptr(d_table),
+                                   stream_ptr(table.device)), "umhs_hash_encode_bwd")
+    return d_table
+
+
+def hash_encode_x01_fwd(x01: Tensor, table: Tensor, scalings: Tensor, log2_T: int) -> Tensor:
+    lib = _lib.load()
+    x = f32(x01).reshape(-1, 3)
+    enc = torch.empty((x.shape[0], 2 * int(scalings.shape[0])), dtype=torch.float32, device=table.device)
+    gs = _grid_struct(table, scalings, log2_T)
+    check(lib.umhs_hash_encode_x01_fwd(ptr(x), x.shape[0], ctypes.byref(gs), ptr(enc), stream_ptr(table.device)),
+          "umhs_hash_encode_x01_fwd")
+    return enc
+
+
+def hash_encode_x01_bwd(x01: Tensor, table: Tensor, scalings: Tensor, log2_T: int, d_enc: Tensor) -> Tensor:
+    lib = _lib.load()
+    x = f32(x01).reshape(-1, 3)
+    d_table = torch.zeros_like(table, dtype=torch.float32)
+    gs = _grid_struct(table, scalings, log2_T)
+    check(lib.umhs_hash_encode_x01_bwd(ptr(x), x.shape[0], ctypes.byref(gs), ptr(f32(d_enc)), ptr(d_table),
+                                       stream_ptr(table.device)), "umhs_hash_encode_x01_bwd")
+    return d_table
+
+
+class HashEncodeFunction(torch.autograd.Function):
+    """HashEncoding.forward at its module boundary: x01 [N,3] in [0,1] -> [N, 2L]."""
+
+    @staticmethod
+    def forward(ctx, x01, table, scalings, log2_T):
+        ctx.save_for_backward(x01, table, scalings)
+        ctx.log2_T = log2_T
+        return hash_encode_x01_fwd(x01, table, scalings, log2_T)
+
+    @staticmethod
+    def backward(ctx, d_enc):
+        x01, table, scalings = ctx.saved_tensors
+        return None, hash_encode_x01_bwd(x01, table, scalings, ctx.log2_T, d_enc.contiguous()), None, None
+
+
+# --------------------------------------------------------------------------------------- field MLPs
+MLP_NAMES = _lib._MLP_NAMES
+
+
+def mlp_struct(weights: Dict[str, Optional[Tensor]], num_classes: int, specular: bool,
+               temperature: float) -> _lib.MlpParams:
+    s = _lib.MlpParams()
+    for name in MLP_NAMES:
+        setattr(s, name, ptr(weights.get(name)))
+    s.num_classes = int(num_classes)
+    s.specular = 1 if specular else 0
+    s.temperature = float(temperature)
+    return s
+
+
+def density_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor]) -> Tensor:
+    lib = _lib.load()
+    sigma = torch.empty((pts.n,), dtype=torch.float32, device=enc.device)
+    ps, ms = pts.struct(), mlp_struct(weights, 1, False, 1.0)
+    check(lib.umhs_density_fwd(ctypes.byref(ps), pts.n, ptr(enc), ctypes.byref(ms), ptr(sigma),
+                               stream_ptr(enc.device)), "umhs_density_fwd")
+    return sigma
+
+
+def field_mlp_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int, specular: bool,
+                  temperature: float, want_embedding: bool = True) -> Dict[str, Tensor]:
+    lib = _lib.load()
+    dev, n = enc.device, pts.n
+    out = {"sigma": torch.empty((n,), dtype=torch.float32, device=dev),
+           "embedding": torch.empty((n, 15), dtype=torch.float32, device=dev) if want_embedding else None,
+           "scalar": torch.empty((n, K), dtype=torch.float32, device=dev),
+           "abund": torch.empty((n, K), dtype=torch.float32, device=dev),
+           "s1": torch.empty((n,), dtype=torch.float32, device=dev) if specular else None,
+           "spec_hidden": torch.empty((n, 16), dtype=torch.float32, device=dev) if specular else None}
+    fo = _lib.FieldOut()
+    for k, v in out.items():
+        setattr(fo, k, ptr(v))
+    ps, ms = pts.struct(), mlp_struct(weights, K, specular, temperature)
+    check(lib.umhs_field_mlp_fwd(ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(fo), stream_ptr(dev)),
+          "umhs_field_mlp_fwd")
+    return out
+
+
+def field_mlp_bwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int, specular: bool, temperature: float,
+                  grads: Dict[str, Optional[Tensor]], d_weights: Optional[Dict[str, Tensor]] = None,
+                  want_d_enc: bool = True) -> Tuple[Optional[Tensor], Dict[str, Tensor]]:
+    """-> (d_enc [n,32] or None, parameter grads).  Parameter grads are accumulated into d_weights if given."""
+    lib = _lib.load()
+    dev, n = enc.device, pts.n
+    if d_weights is None:
+        d_weights = {k: torch.zeros_like(v, dtype=torch.float32) for k, v in weights.items() if v is not None}
+    d_enc = torch.empty((n, ENC_DIM), dtype=torch.float32, device=dev) if want_d_enc else None
+    g = _lib.FieldOutGrads()
+    for k in ("d_sigma", "d_embedding", "d_scalar", "d_abund", "d_s1", "d_spec_hidden"):
+        setattr(g, k, ptr(grads.get(k)))
+    dp = _lib.MlpGrads()
+    for name in MLP_NAMES:
+        setattr(dp, name, ptr(d_weights.get(name)))
+    ps, ms = pts.struct(), mlp_struct(weights, K, specular, temperature)
+    check(lib.umhs_field_mlp_bwd(ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(g), ptr(d_enc),
+                                 ctypes.byref(dp), stream_ptr(dev)), "umhs_field_mlp_bwd")
+    return d_enc, d_weights
+
+
+class FieldFunction(torch.autograd.Function):
+    """hash-grid encode + fused field MLPs.  inputs: table, then the MLP tensors in MLP_NAMES order
+    (dir_* may be None).  outputs: sigma [N], embedding [N,15], scalar [N,K], abund [N,K], s1 [N], spec_hidden [N,16]
+    (the last two are empty tensors when not specular)."""
+
+    @staticmethod
+    def forward(ctx, pts: PointSet, cfg: dict, table: Tensor, scalings: Tensor, *mlp: Optional[Tensor]):
+        weights = {n: (w.detach() if w is not None else None) for n, w in zip(MLP_NAMES, mlp)}
+        enc = hash_encode_fwd(pts, table.detach(), scalings, cfg["log2_T"])
+        out = field_mlp_fwd(pts, enc, weights, cfg["K"], cfg["specular"], cfg["temperature"])
+        ctx.pts, ctx.cfg = pts, cfg
+        ctx.n_mlp = len(mlp)
+        ctx.save_for_backward(enc, table, scalings, *[w for w in mlp if w is not None])
+        ctx.mlp_present = [w is not None for w in mlp]
+        empty = torch.empty((0,), device=enc.device)
+        s1 = out["s1"] if out["s1"] is not None else empty
+        sh = out["spec_hidden"] if out["spec_hidden"] is not None else empty
+        return out["sigma"], out["embedding"], out["scalar"], out["abund"], s1, sh
+
+    @staticmethod
+    def backward(ctx, d_sigma, d_emb, d_scalar, d_abund, d_s1, d_sh):
+        enc, table, scalings, *present = ctx.saved_tensors
+        it = iter(present)
+        weights = {n: (next(it) if p else None) for n, p in zip(MLP_NAMES, ctx.mlp_present)}
+        cfg, pts = ctx.cfg, ctx.pts
+        n, K, dev = pts.n, cfg["K"], enc.device
+
+        def c(g, shape):
+            return torch.zeros(shape, dtype=torch.float32, device=dev) if g is None else f32(g)
+
+        grads = {"d_sigma": c(d_sigma, (n,)), "d_embedding": None if d_emb is None else f32(d_emb),
+                 "d_scalar": c(d_scalar, (n, K)), "d_abund": c(d_abund, (n, K))}
+        if cfg["specular"]:
+            grads["d_s1"] = c(d_s1, (n,))
+            grads["d_spec_hidden"] = c(d_sh, (n, 16))
+        d_enc, d_w = field_mlp_bwd(pts, enc, weights, K, cfg["specular"], cfg["temperature"], grads)
+        d_table = hash_encode_bwd(pts, table, scalings, cfg["log2_T"], d_enc)
+        return (None, None, d_table, None, *[d_w.get(n) if p else None for n, p in zip(MLP_NAMES, ctx.mlp_present)])
+
+
+# --------------------------------------------------------------------------------------- compositing
+def _composite_in(R, N, K, B, specular, grad_scaling, packed_info, t0, t1, sigma, scalar, abund, s1, spec_hidden,
+                  endmembers, dir_w1, dir_b1, rgb_matrix, palette) -> _lib.CompositeIn:
+    ci = _lib.CompositeIn()
+    ci.n_rays, ci.n_samples, ci.num_classes, ci.num_bands = R, N, K, B
+    ci.specular, ci.grad_scaling = (1 if specular else 0), (1 if grad_scaling else 0)
+    ci.packed_info, ci.t_starts, ci.t_ends, ci.sigma = ptr(packed_info), ptr(t0), ptr(t1), ptr(sigma)
+    ci.scalar, ci.abund = ptr(scalar), ptr(abund)
+    ci.s1 = ptr(s1) if specular else None
+    ci.spec_hidden = ptr(spec_hidden) if specular else None
+    ci.endmembers, ci.rgb_matrix = ptr(endmembers), ptr(rgb_matrix)
+    ci.dir_w1 = ptr(dir_w1) if specular else None
+    ci.dir_b1 = ptr(dir_b1) if specular else None
+    ci.palette = ptr(palette)
+    return ci
+
+
+COMPOSITE_OUTPUTS = ("spectral", "spectral2", "specular", "abundances", "accumulation", "depth", "rgb", "seg_probs",
+                     "seg_raw", "seg_pred", "weights")
+
+
+class CompositeFunction(torch.autograd.Function):
+    """Per-ray compositing x unmixing x spec->sRGB x cluster probe over packed samples (fused kernel).
+    Differentiable outputs: spectral, spectral2, rgb, accumulation.  Everything else is marked
+    non-differentiable (the reference renders abundances / specular under no_grad and uses depth and the
+    segmentation outputs in no loss)."""
+
+    @staticmethod
+    def forward(ctx, cfg: dict, packed_info, t0, t1, sigma, scalar, abund, s1, spec_hidden, endmembers, dir_w1,
+                dir_b1, rgb_matrix, palette):
+        lib = _lib.load()
+        dev = sigma.device
+        R, N, K, B, specular = int(packed_info.shape[0]), int(sigma.shape[0]), cfg["K"], cfg["B"], cfg["specular"]
+        tens = [f32(x) if x is not None and x.numel() else None
+                for x in (t0, t1, sigma, scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1, rgb_matrix,
+                          palette)]
+        t0, t1, sigma, scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1, rgb_matrix, palette = tens
+        ci = _composite_in(R, N, K, B, specular, cfg["grad_scaling"], packed_info, t0, t1, sigma, scalar, abund, s1,
+                           spec_hidden, endmembers, dir_w1, dir_b1, rgb_matrix, palette)
+        z = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)  # noqa: E731
+        out = {"spectral": z(R, B), "spectral2": z(R, B) if specular else None,
+               "specular": z(R, B) if specular else None, "abundances": z(R, K), "accumulation": z(R),
+               "depth": z(R), "rgb": z(R, 3), "seg_probs": z(R, K), "seg_raw": z(R), "seg_pred": z(R, 3),
+               "weights": z(N) if cfg.get("want_weights", False) else None}
+        tmm = torch.tensor([float("inf"), float("-inf")], dtype=torch.float32, device=dev)
+        co = _lib.CompositeOut()
+        for k, v in out.items():
+            setattr(co, k, ptr(v))
+        co.t_minmax = ptr(tmm)
+        check(lib.umhs_composite_fwd(ctypes.byref(ci), ctypes.byref(co), stream_ptr(dev)), "umhs_composite_fwd")
+        check(lib.umhs_depth_clip(ptr(out["depth"]), R, ptr(tmm), stream_ptr(dev)), "umhs_depth_clip")
+        ctx.cfg = cfg
+        ctx.save_for_backward(packed_info, t0, t1, sigma, scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1,
+                              rgb_matrix, out["spectral"])
+        empty = torch.empty((0,), device=dev)
+        res = tuple(out[k] if out[k] is not None else empty for k in COMPOSITE_OUTPUTS)
+        ctx.mark_non_differentiable(*[res[i] for i, k in enumerate(COMPOSITE_OUTPUTS)
+                                      if k not in ("spectral", "spectral2", "rgb", "accumulation")])
+        return res
+
+    @staticmethod
+    def backward(ctx, d_spectral, d_spectral2, d_specular, d_abundances, d_acc, d_depth, d_rgb, *_):
+        lib = _lib.load()
+        (packed_info, t0, t1, sigma, scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1, rgb_matrix,
+         spectral) = ctx.saved_tensors
+        cfg = ctx.cfg
+        dev = sigma.device
+        R, N, K, B, specular = int(packed_info.shape[0]), int(sigma.shape[0]), cfg["K"], cfg["B"], cfg["specular"]
+        ci = _composite_in(R, N, K, B, specular, cfg["grad_scaling"], packed_info, t0, t1, sigma, scalar, abund, s1,
+                           spec_hidden, endmembers, dir_w1, dir_b1, rgb_matrix, None)
+        gi = _lib.CompositeGradsIn()
+        keep = [f32(g) if g is not None else None for g in (d_spectral, d_spectral2 if specular else None, d_rgb,
+                                                            d_acc)]
+        gi.d_spectral, gi.d_spectral2, gi.d_rgb, gi.d_accumulation = (ptr(k) for k in keep)
+        gi.spectral = ptr(spectral)
+        z = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)  # noqa: E731
+        d_sigma, d_scalar, d_abund = z(N), z(N, K), z(N, K)
+        d_s1 = z(N) if specular else None
+        d_sh = z(N, 16) if specular else None
+        d_E = torch.zeros((K, B), dtype=torch.float32, device=dev)
+        d_w1 = torch.zeros((B, 16), dtype=torch.float32, device=dev) if specular else None
+        d_b1 = torch.zeros((B,), dtype=torch.float32, device=dev) if specular else None
+        go = _lib.CompositeGradsOut()
+        go.d_sigma, go.d_scalar, go.d_abund = ptr(d_sigma), ptr(d_scalar), ptr(d_abund)
+        go.d_s1, go.d_spec_hidden = ptr(d_s1), ptr(d_sh)
+        go.d_endmembers, go.d_dir_w1, go.d_dir_b1 = ptr(d_E), ptr(d_w1), ptr(d_b1)
+        check(lib.umhs_composite_bwd(ctypes.byref(ci), ctypes.byref(gi), ctypes.byref(go), stream_ptr(dev)),
+              "umhs_composite_bwd")
+        return (None, None, None, None, d_sigma, d_scalar, d_abund, d_s1, d_sh, d_E, d_w1, d_b1, None, None)
+
+
+# --------------------------------------------------------------------------------------- unfused module-boundary ops
+class UnmixFunction(torch.autograd.Function):
+    """Per-sample linear mixing model of UMHSField.get_outputs (ref umhs_field.py:229-251):
+    spec[n,b] = sum_k s a E[k,b]; specular term s1 * sigmoid(W h + b).  -> (spec, specular_term)"""
+
+    @staticmethod
+    def forward(ctx, scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1):
+        lib = _lib.load()
+        specular = s1 is not None
+        scalar, abund, endmembers = f32(scalar), f32(abund), f32(endmembers)
+        n, K = scalar.shape
+        B = endmembers.shape[1]
+        dev = scalar.device
+        spec = torch.empty((n, B), dtype=torch.float32, device=dev)
+        sp = torch.empty((n, B), dtype=torch.float32, device=dev) if specular else None
+        if specular:
+            s1, spec_hidden, dir_w1, dir_b1 = f32(s1).reshape(-1), f32(spec_hidden), f32(dir_w1), f32(dir_b1)
+        check(lib.umhs_unmix_fwd(n, K, B, int(specular), ptr(scalar), ptr(abund), ptr(s1), ptr(spec_hidden),
+                                 ptr(endmembers), ptr(dir_w1), ptr(dir_b1), ptr(spec), ptr(sp), stream_ptr(dev)),
+              "umhs_unmix_fwd")
+        ctx.specular = specular
+        ctx.save_for_backward(scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1)
+        return spec, (sp if specular else torch.empty((0,), device=dev))
+
+    @staticmethod
+    def backward(ctx, d_spec, d_sp):
+        lib = _lib.load()
+        scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1 = ctx.saved_tensors
+        specular = ctx.specular
+        n, K = scalar.shape
+        B = endmembers.shape[1]
+        dev = scalar.device
+        d_spec = f32(d_spec) if d_spec is not None else torch.zeros((n, B), device=dev)
+        d_sp = f32(d_sp) if (specular and d_sp is not None) else None
+        d_scalar, d_abund = torch.empty_like(scalar), torch.empty_like(abund)
+        d_E = torch.zeros_like(endmembers)
+        d_s1 = torch.zeros_like(s1) if specular else None
+        d_sh = torch.zeros_like(spec_hidden) if specular else None
+        d_w1 = torch.zeros_like(dir_w1) if specular else None
+        d_b1 = torch.zeros_like(dir_b1) if specular else None
+        check(lib.umhs_unmix_bwd(n, K, B, int(specular), ptr(scalar), ptr(abund), ptr(s1), ptr(spec_hidden),
+                                 ptr(endmembers), ptr(dir_w1), ptr(dir_b1), ptr(d_spec), ptr(d_sp), ptr(d_scalar),
+                                 ptr(d_abund), ptr(d_s1), ptr(d_sh), ptr(d_E), ptr(d_w1), ptr(d_b1), stream_ptr(dev)),
+              "umhs_unmix_bwd")
+        return d_scalar, d_abund, d_s1, d_sh, d_E, d_w1, d_b1
+
+
+def pack_info(ray_indices: Tensor, n_rays: int) -> Tensor:
+    """nerfacc.pack_info: [n_rays, 2] (start, count), int64."""
+    lib = _lib.load()
+    ri = ray_indices.to(torch.int64).contiguous()
+    dev = ri.device
+    counts = torch.empty((n_rays,), dtype=torch.int64, device=dev)
+    packed = torch.empty((n_rays, 2), dtype=torch.int64, device=dev)
+    check(lib.umhs_pack_info(ptr(ri), ri.shape[0], n_rays, ptr(counts), ptr(packed), stream_ptr(dev)),
+          "umhs_pack_info")
+    return packed
+
+
+class RenderWeightsFunction(torch.autograd.Function):
+    """nerfacc.render_weight_from_density on packed samples -> (weights, transmittance)."""
+
+    @staticmethod
+    def forward(ctx, t0, t1, sigma, packed_info):
+        lib = _lib.load()
+        t0, t1, sigma = f32(t0).reshape(-1), f32(t1).reshape(-1), f32(sigma).reshape(-1)
+        w, T = torch.empty_like(sigma), torch.empty_like(sigma)
+        check(lib.umhs_render_weights_fwd(ptr(packed_info), packed_info.shape[0], ptr(t0), ptr(t1), ptr(sigma),
+                                          ptr(w), ptr(T), stream_ptr(sigma.device)), "umhs_render_weights_fwd")
+        ctx.save_for_backward(t0, t1, sigma, packed_info, T)
+        ctx.mark_non_differentiable(T)
+        return w, T
+
+    @staticmethod
+    def backward(ctx, d_w, _):
+        lib = _lib.load()
+        t0, t1, sigma, packed_info, T = ctx.saved_tensors
+        d_sigma = torch.empty_like(sigma)
+        check(lib.umhs_render_weights_bwd(ptr(packed_info), packed_info.shape[0], ptr(t0), ptr(t1), ptr(sigma),
+                                          ptr(T), ptr(f32(d_w).reshape(-1)), ptr(d_sigma), stream_ptr(sigma.device)),
+              "umhs_render_weights_bwd")
+        return None, None, d_sigma, None
+
+
+class AccumulateFunction(torch.autograd.Function):
+    """nerfacc.accumulate_along_rays on packed samples: out[ray[n], :] += w[n] * v[n, :]."""
+
+    @staticmethod
+    def forward(ctx, weights, values, ray_indices, n_rays):
+        lib = _lib.load()
+        w = f32(weights).reshape(-1)
+        v = f32(values) if values is not None else None
+        C = v.shape[-1] if v is not None else 1
+        ri = ray_indices.to(torch.int64).contiguous()
+        out = torch.zeros((n_rays, C), dtype=torch.float32, device=w.device)
+        check(lib.umhs_accumulate_fwd(ptr(w), ptr(v), ptr(ri), w.shape[0], C, ptr(out), stream_ptr(w.device)),
+              "umhs_accumulate_fwd")
+        ctx.save_for_backward(w, v, ri)
+        ctx.has_values = v is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        w, v, ri = ctx.saved_tensors
+        C = v.shape[-1] if ctx.has_values else 1
+        d_w = torch.empty_like(w)
+        d_v = torch.empty_like(v) if ctx.has_values else None
+        check(lib.umhs_accumulate_bwd(ptr(w), ptr(v), ptr(ri), w.shape[0], C, ptr(f32(d_out)), ptr(d_w), ptr(d_v),
+                                      stream_ptr(w.device)), "umhs_accumulate_bwd")
+        return d_w, d_v, None, None
+
+
+# --------------------------------------------------------------------------------------- packing
+def march(rays_o: Tensor, rays_d: Tensor, near_planes: Tensor, far_planes: Tensor, binaries: Tensor, aabbs: Tensor,
+          step_size: float, cone_angle: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Occupancy-grid ray marching (nerfacc traverse_grids).  -> (ray_indices, t_starts, t_ends, packed_info).
+    One host sync (the sample count sizes the output buffers), as in the reference."""
+    lib = _lib.load()
+    dev = rays_o.device
+    R = int(rays_o.shape[0])
+    a = _lib.MarchArgs()
+    ro, rd, nr, fr = f32(rays_o), f32(rays_d), f32(near_planes).reshape(-1), f32(far_planes).reshape(-1)
+    bn = binaries.contiguous().view(torch.uint8) if binaries.dtype == torch.bool else binaries.contiguous()
+    ab = f32(aabbs)
+    a.rays_o, a.rays_d, a.near_planes, a.far_planes = ptr(ro), ptr(rd), ptr(nr), ptr(fr)
+    a.binaries, a.aabbs = ptr(bn), ptr(ab)
+    a.levels, a.resolution = int(bn.shape[0]), int(bn.shape[1])
+    a.step_size, a.cone_angle, a.n_rays = float(step_size), float(cone_angle), R
+    counts = torch.empty((R,), dtype=torch.int64, device=dev)
+    packed = torch.empty((R, 2), dtype=torch.int64, device=dev)
+    total = torch.zeros((1,), dtype=torch.int64, device=dev)
+    st = stream_ptr(dev)
+    check(lib.umhs_march_count(ctypes.byref(a), ptr(counts), st), "umhs_march_count")
+    check(lib.umhs_pack_scan(ptr(counts), R, ptr(packed), ptr(total), st), "umhs_pack_scan")
+    N = int(total.item())
+    ri = torch.empty((N,), dtype=torch.int64, device=dev)
+    t0 = torch.empty((N,), dtype=torch.float32, device=dev)
+    t1 = torch.empty((N,), dtype=torch.float32, device=dev)
+    if N > 0:
+        check(lib.umhs_march_write(ctypes.byref(a), ptr(packed), ptr(ri), ptr(t0), ptr(t1), st), "umhs_march_write")
+    return ri, t0, t1, packed
+
+
+def visibility_compact(packed_info: Tensor, t0: Tensor, t1: Tensor, sigma: Tensor, early_stop_eps: float,
+                       alpha_thre: float, occ_mean: Optional[Tensor] = None):
+    """render_visibility_from_density + boolean-mask compaction.  -> (ray_indices, t0, t1, packed_info)."""
+    lib = _lib.load()
+    dev = t0.device
+    R, N = int(packed_info.shape[0]), int(t0.shape[0])
+    keep = torch.empty((N,), dtype=torch.uint8, device=dev)
+    kc = torch.empty((R,), dtype=torch.int64, device=dev)
+    packed2 = torch.empty((R, 2), dtype=torch.int64, device=dev)
+    total = torch.zeros((1,), dtype=torch.int64, device=dev)
+    st = stream_ptr(dev)
+    check(lib.umhs_visibility_mask(ptr(packed_info), R, ptr(t0), ptr(t1), ptr(f32(sigma).reshape(-1)),
+                                   float(early_stop_eps), float(alpha_thre), ptr(occ_mean), ptr(keep), ptr(kc), st),
+          "umhs_visibility_mask")
+    check(lib.umhs_pack_scan(ptr(kc), R, ptr(packed2), ptr(total), st), "umhs_pack_scan")
+    M = int(total.item())
+    ri = torch.empty((M,), dtype=torch.int64, device=dev)
+    o0 = torch.empty((M,), dtype=torch.float32, device=dev)
+    o1 = torch.empty((M,), dtype=torch.float32, device=dev)
+    if M > 0:
+        check(lib.umhs_compact_samples(ptr(packed_info), ptr(packed2), R, ptr(keep), ptr(t0), ptr(t1), ptr(ri),
+                                       ptr(o0), ptr(o1), st), "umhs_compact_samples")
+    return ri, o0, o1, packed2
+
+
+# --------------------------------------------------------------------------------------- optimiser
+def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, lr: float, beta1: float, beta2: float,
+              eps: float, step: int, inv_scale: Optional[Tensor] = None, found_inf: Optional[Tensor] = None,
+              clamp_range: Tuple[int, int] = (0, 0), zero_grad: bool = True) -> None:
+    lib = _lib.load()
+    check(lib.umhs_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1, beta2,
+                             eps, step, ptr(inv_scale), ptr(found_inf), clamp_range[0], clamp_range[1],
+                             1 if zero_grad else 0, stream_ptr(param.device)), "umhs_adam_step")
