@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- UMHS hot-path benchmark (BASELINE.json metric: train rays/s at 128 bands on 1-8 B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload = "hotdog-synthetic-train-step"): BASELINE.json configs[1] -- full training step of the
+hotdog-shaped synthetic scene, 16384 rays per GPU per step, 128 bands, K=4 endmembers (endmembers_hotdog[:, :128],
+frozen in tests/golden/colour.npz), temperature 0.4, hash grid 16x2 @ 2^19, occupancy grid 128^3 x 4 with a
+spherical-shell surface (radius 0.5, thickness 0.08 -> ~50 kept samples per ray).  One step = occupancy-grid update
+(steady-state cadence) + march/pack + sampler density pass + visibility/compaction + field forward + fused
+compositing/unmixing/sRGB + loss + full backward + [NCCL all-reduce of the flat gradient] + fused Adam.
+
+`value`     : whole-job rays/s, inputs resident in HBM, CUDA-event timed, max over ranks.
+`e2e`       : same metric through the public API (UMHSTrainer.train_step) with the batch copied from pinned host
+              memory every step and the loss read back every step.
+`roofline`  : dominant kernel, CUDA events on the launching stream in a second timed pass of the same K steps.
+`cpu_baseline` / `--impl reference`: the CPU oracle (oracle/, the restatement of the reference's PyTorch path
+              pinned by tests/golden) running the SAME training step on a bounded ray sample on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "unsupervised-hyperspectral-nerf_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+RAYS_PER_GPU = 16384
+BANDS, K_CLASSES, TEMPERATURE, LOG2_T, GRID_RES = 128, 4, 0.4, 19, 128
+SHELL_R, SHELL_T = 0.5, 0.08
+WAVELENGTHS = np.linspace(400, 1000, BANDS).astype(int).tolist()
+CPU_SAMPLE_RAYS = 1024
+
+
+# ------------------------------------------------------------------------------------------ synthetic scene
+def make_rays(R, seed):
+    g = torch.Generator().manual_seed(seed)
+    o = torch.randn(R, 3, generator=g)
+    o = o / o.norm(dim=-1, keepdim=True) * (0.8 + 0.2 * torch.rand(R, 1, generator=g))
+    d = -o / o.norm(dim=-1, keepdim=True) + 0.25 * torch.randn(R, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    image = torch.rand(R, 3, generator=g)
+    hs = torch.rand(R, BANDS, generator=g)
+    return o.contiguous(), d.contiguous(), image, hs
+
+
+def shell_binaries():
+    c = (torch.arange(GRID_RES) + 0.5) / GRID_RES * 2 - 1
+    X, Y, Z = torch.meshgrid(c, c, c, indexing="ij")
+    rr = (X ** 2 + Y ** 2 + Z ** 2).sqrt()
+    b = torch.zeros(4, GRID_RES, GRID_RES, GRID_RES, dtype=torch.bool)
+    b[0] = (rr > SHELL_R - SHELL_T / 2) & (rr < SHELL_R + SHELL_T / 2)
+    return b
+
+
+def endmembers():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "colour.npz"))
+    return torch.from_numpy(z["endmembers"].astype(np.float32))  # endmembers_hotdog.npy[:, :128]
+
+
+def init_field_(field, seed=0):
+    """Deterministic random-init weights of the reference architecture (nn.Linear default init, hash table
+    U(-1e-3, 1e-3)), hotdog endmembers, density bias so that sigma ~ e^3 (partially terminating rays)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for _, p in sorted(field.named_parameters()):  # same draw order for the product and the oracle
+            if p.dim() == 2 and p.shape[1] == 2 and p.shape[0] > 4096:  # hash table
+                p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * 1e-3)
+            else:
+                bound = 1.0 / max(p.shape[-1], 1) ** 0.5 if p.dim() == 2 else 0.1
+                p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * bound)
+        field.endmembers.copy_(endmembers())
+        field.mlp_base.mlp.layers[1].bias[0] = 3.0
+
+
+# ------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU oracle arm
+def oracle_trainer(seed=0):
+    from oracle import umhs_oracle as O
+
+    cfg = O.OracleConfig(method="rgb+spectral", temperature=TEMPERATURE, pred_specular=False, log2_hashmap_size=LOG2_T,
+                         grid_resolution=GRID_RES)
+    m = O.OracleModel(cfg, torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), WAVELENGTHS, K_CLASSES)
+    init_field_(m.field, seed)
+    m.occupancy_grid.binaries.copy_(shell_binaries())
+    m.occupancy_grid.occs.copy_(m.occupancy_grid.binaries.flatten().float() * 0.05)
+    m.train()
+    opt = torch.optim.Adam(m.field.parameters(), lr=2e-2, eps=1e-15)
+    return m, opt
+
+
+def oracle_step(m, opt, R, seed):
+    from oracle import nerf3p
+
+    o, d, image, hs = make_rays(R, seed)
+    opt.zero_grad(set_to_none=True)
+    out = m.get_outputs(nerf3p.RayBundle(o, d))
+    loss = sum(m.get_loss_dict(out, {"image": image, "hs_image": hs}).values())
+    loss.backward()
+    opt.step()
+    m.clamp_endmembers()
+    return float(loss.detach())
+
+
+def time_oracle(steps, warmup, R=CPU_SAMPLE_RAYS):
+    torch.set_num_threads(os.cpu_count() or 1)
+    m, opt = oracle_trainer()
+    for i in range(warmup):
+        oracle_step(m, opt, R, 1000 + i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        oracle_step(m, opt, R, 2000 + i)
+    dt = time.perf_counter() - t0
+    return {"value": R * steps / dt, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} full training steps of {R} rays of the same synthetic scene (oracle/ fp32 torch CPU, "
+                      f"C packing march, torch.optim.Adam), {warmup} warm-up", "ms_per_step": dt / steps * 1e3}
+
+
+# ------------------------------------------------------------------------------------------ roofline bookkeeping
+def algorithmic_bytes(name, units, samples_per_ray):
+    """Algorithmic bytes per launch (DESIGN.md 'Kernels'); units = what the wrapper passed (samples, rays, params)."""
+    L = 16
+    per = {
+        "umhs_hash_encode_fwd": 8 * L * 8 + 16 + 8 * L,            # gathers + (ray_idx,t0,t1) + enc out
+        "umhs_hash_encode_bwd": 8 * L + 16 + 2 * 8 * L * 8,        # d_enc in + points + table read-modify-write
+        "umhs_density_fwd": 8 * L + 16 + 4,                        # enc in + points + sigma out
+        "umhs_field_mlp_fwd": 8 * L + 16 + 4 + 60 + 8 * K_CLASSES,  # enc + points + sigma + emb + scalar/abund
+        "umhs_field_mlp_bwd": 8 * L + 16 + 4 + 8 * K_CLASSES + 8 * L,  # enc + points + grads in + d_enc out
+        "umhs_composite_fwd": None,
+        "umhs_composite_bwd": None,
+        "umhs_adam_step": 32,                                      # p,g,m,v read; p,m,v,g written
+    }.get(name, None)
+    if name == "umhs_composite_fwd":
+        S = samples_per_ray
+        return units * (S * (12 + 8 * K_CLASSES) + 16 + 4 * BANDS + 4 * K_CLASSES + 20 + 4 * S)  # + weights out
+    if name == "umhs_composite_bwd":
+        S = samples_per_ray
+        return units * (2 * S * (12 + 8 * K_CLASSES) + 8 * BANDS)
+    return None if per is None else units * per
+
+
+# ------------------------------------------------------------------------------------------ main arms
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: ~8k rays of CPU work in total whatever K is (a 1024-ray oracle step takes seconds)
+    R = int(min(1024, max(128, 8192 // max(args.steps, 1))))
+    r = time_oracle(max(args.steps, 1), max(args.warmup, 1), R)
+    line = {"impl": "reference", "metric": "train rays/s", "value": r["value"], "unit": "rays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {**workload_config(args.gpus, cpu=True), "rays_per_gpu_per_step": R},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, cpu=False, samples_per_ray=None):
+    c = {"workload": "hotdog-synthetic-train-step", "rays_per_gpu_per_step": RAYS_PER_GPU if not cpu else CPU_SAMPLE_RAYS,
+         "bands": BANDS, "endmembers": K_CLASSES, "temperature": TEMPERATURE, "hash": "16x2@2^19",
+         "occupancy": f"128^3x4 shell r={SHELL_R} t={SHELL_T}", "method": "rgb+spectral", "specular": False,
+         "parallelism": f"dp{n_gpus} ray-sharded, 1 all-reduce/step" if n_gpus > 1 else "single",
+         "l2_policy": "working set > L2: Adam state 4 x 64 MiB streamed every step + rotating batches"}
+    if samples_per_ray is not None:
+        c["kept_samples_per_ray"] = samples_per_ray
+    return c
+
+
+def run_b200(args):
+    import torch.distributed as dist
+
+    import umhs_b200
+    from umhs_b200 import ops
+    from umhs_b200.rays import RayBundle
+    from umhs_b200.trainer import UMHSTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = umhs_b200.UMHSConfig(method="rgb+spectral", temperature=TEMPERATURE, pred_specular=False,
+                               log2_hashmap_size=LOG2_T, grid_resolution=GRID_RES)
+    model = cfg.setup(metadata={"wavelengths": WAVELENGTHS, "num_classes": K_CLASSES})
+    init_field_(model.field, 0)
+    model.occupancy_grid.binaries.copy_(shell_binaries())
+    model.occupancy_grid.occs.copy_(model.occupancy_grid.binaries.flatten().float() * 0.05)
+    model.occupancy_grid.mark_dirty()
+    model = model.to(dev)
+    # steady-state occupancy update cadence (step >= warm-up 256), binaries frozen so the synthetic scene stays fixed
+    trainer = UMHSTrainer(model, world_size=world, rank=rank, occ_update=True, freeze_binaries=True, start_step=256)
+
+    R, POOL = RAYS_PER_GPU, 8
+    host = [make_rays(R, 7919 * rank + i) for i in range(POOL)]
+    pinned = [tuple(t.pin_memory() for t in b) for b in host]
+    resident = [tuple(t.to(dev) for t in b) for b in host]
+
+    def step_resident(i):
+        o, d, image, hs = resident[i % POOL]
+        return trainer.train_step(RayBundle(o, d), {"image": image, "hs_image": hs})
+
+    def step_e2e(i):
+        o, d, image, hs = (t.to(dev, non_blocking=True) for t in pinned[i % POOL])
+        out = trainer.train_step(RayBundle(o, d), {"image": image, "hs_image": hs})
+        return float(out["loss"].item())  # device -> host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            fn(i)
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(args.warmup):
+        step_resident(i)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ops.Profiler.reset(enabled=True, timing=False)
+    ms = timed(step_resident, args.steps)
+    launches = ops.Profiler.launches
+    ops.Profiler.reset(enabled=False)
+    ms_e2e = timed(step_e2e, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+
+    # second pass of the same K steps with per-entry-point CUDA events (roofline shares)
+    ops.Profiler.reset(enabled=True, timing=True)
+    n_samples = 0
+    barrier()
+    for i in range(args.steps):
+        n_samples += int(step_resident(i)["num_samples"].item())
+    torch.cuda.synchronize()
+    summ = ops.Profiler.summary()
+    ops.Profiler.reset(enabled=False)
+    spr = n_samples / (args.steps * R)
+
+    if rank == 0:
+        peaks = {}
+        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk_path):
+            peaks = json.load(open(pk_path))
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+        kernels = {}
+        for name, d in summ.items():
+            per_launch_ms = d["ms"] / d["calls"]
+            ab = algorithmic_bytes(name, d["units"] / d["calls"], spr)
+            kernels[name] = {"calls_per_step": d["calls"] / args.steps, "ms_per_step": d["ms"] / args.steps,
+                             "ms_per_launch": per_launch_ms,
+                             "achieved_gbs": None if ab is None else ab / (per_launch_ms * 1e-3) / 1e9}
+        total_k = sum(v["ms_per_step"] for v in kernels.values())
+        top = max(kernels, key=lambda n: kernels[n]["ms_per_step"])
+        roof = {"kernel": top, "bound": "hbm", "achieved": kernels[top]["achieved_gbs"], "peak": hbm_peak,
+                "unit": "GB/s", "frac": (kernels[top]["achieved_gbs"] or 0.0) / hbm_peak, "traffic": None,
+                "peak_source": peak_src, "share_of_kernel_time": kernels[top]["ms_per_step"] / max(total_k, 1e-9),
+                "kernel_ms_per_step_sum": total_k}
+        cpu = time_oracle(steps=4, warmup=1)
+        h2d = sum(t.numel() * t.element_size() for t in pinned[0])
+        line = {"metric": "train rays/s", "value": world * R * args.steps / (ms * 1e-3), "unit": "rays/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(world, samples_per_ray=spr),
+                "e2e": {"value": world * R * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clk, "roofline": roof,
+                "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "train_msamples_per_s": world * n_samples / args.steps / (ms / args.steps * 1e-3) / 1e6,
+                "kernels": kernels}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

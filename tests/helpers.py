@@ -70,4 +70,13 @@ def b200_model_from_golden(d, meta, training=True, device="cuda"):
 def assert_close(a, b, rtol, atol, name=""):
     a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
     b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
-    np.testing.assert_allclose(a.reshape(b.shape), b, rtol=rtol, atol=atol, err_msg=name)
+    a = a.reshape(b.shape).astype(np.float64)
+    b = b.astype(np.float64)
+    err = np.abs(a - b)
+    bad = err > atol + rtol * np.abs(b)
+    if bad.any():
+        i = np.unravel_index(np.argmax(err - (atol + rtol * np.abs(b))), b.shape) if b.ndim else ()
+        raise AssertionError(
+            f"{name}: {int(bad.sum())}/{bad.size} elements differ (rtol={rtol}, atol={atol:.3g}); worst at {i}: "
+            f"got {a[i]:.9g} want {b[i]:.9g}; max|err|={err.max():.3g}, max|want|={np.abs(b).max():.3g}, "
+            f"rel L2 err={np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30):.3g}")

@@ -213,6 +213,7 @@ using namespace umhs;
 
 extern "C" int umhs_hash_encode_fwd(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid, float *enc,
                                     void *stream) {
+    if (n <= 0) return UMHS_OK;
     UMHS_CHECK_ARG(pts != nullptr && enc != nullptr, "null argument");
     UMHS_CHECK_ARG(check_grid(grid) == 0, "bad hash grid");
     UMHS_CHECK_ARG(pts->positions || (pts->rays_o && pts->rays_d && pts->ray_indices && pts->t_starts && pts->t_ends),
@@ -228,6 +229,7 @@ extern "C" int umhs_hash_encode_fwd(const umhs_points *pts, int64_t n, const umh
 
 extern "C" int umhs_hash_encode_bwd(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid, const float *d_enc,
                                     float *d_table, void *stream) {
+    if (n <= 0) return UMHS_OK;
     UMHS_CHECK_ARG(pts != nullptr && d_enc != nullptr && d_table != nullptr, "null argument");
     UMHS_CHECK_ARG(check_grid(grid) == 0, "bad hash grid");
     if (n <= 0) return UMHS_OK;
@@ -241,6 +243,7 @@ extern "C" int umhs_hash_encode_bwd(const umhs_points *pts, int64_t n, const umh
 
 extern "C" int umhs_hash_encode_x01_fwd(const float *x01, int64_t n, const umhs_hash_grid *grid, float *enc,
                                         void *stream) {
+    if (n <= 0) return UMHS_OK;
     UMHS_CHECK_ARG(x01 != nullptr && enc != nullptr, "null argument");
     UMHS_CHECK_ARG(check_grid(grid) == 0, "bad hash grid");
     if (n <= 0) return UMHS_OK;
@@ -254,6 +257,7 @@ extern "C" int umhs_hash_encode_x01_fwd(const float *x01, int64_t n, const umhs_
 
 extern "C" int umhs_hash_encode_x01_bwd(const float *x01, int64_t n, const umhs_hash_grid *grid, const float *d_enc,
                                         float *d_table, void *stream) {
+    if (n <= 0) return UMHS_OK;
     UMHS_CHECK_ARG(x01 != nullptr && d_enc != nullptr && d_table != nullptr, "null argument");
     UMHS_CHECK_ARG(check_grid(grid) == 0, "bad hash grid");
     if (n <= 0) return UMHS_OK;

@@ -80,15 +80,21 @@ class OccGridEstimator(nn.Module):
     @torch.no_grad()
     def update_every_n_steps(self, step: int, occ_eval_fn: Callable, occ_thre: float = 1e-2, ema_decay: float = 0.95,
                              warmup_steps: int = 256, n: int = 16, cell_ids: Optional[List[Tensor]] = None,
-                             cell_jitter: Optional[List[Tensor]] = None) -> None:
+                             cell_jitter: Optional[List[Tensor]] = None, freeze_binaries: bool = False) -> None:
         """occs[id] = max(occs[id]*decay, occ_eval_fn(x)); binaries = occs > min(mean(occs), occ_thre).
-        ``cell_ids`` / ``cell_jitter`` (per level) inject the random draws for parity tests."""
+        ``cell_ids`` / ``cell_jitter`` (per level) inject the random draws for parity tests.  ``freeze_binaries``
+        (bench only) does all the work but writes occs / binaries of a scratch copy, so a synthetic scene stays fixed."""
         if not (self.training and step % n == 0):
             return
         lib = _lib.load()
         dev = self.occs.device
         res, n_cells = self._res, self._res ** 3
         st = stream_ptr(dev)
+        occs, binaries = self.occs, self.binaries
+        if freeze_binaries:
+            if getattr(self, "_scratch", None) is None:
+                self._scratch = (self.occs.clone(), self.binaries.clone())
+            occs, binaries = self._scratch
         for lvl in range(self.levels):
             if cell_ids is not None:
                 idx = cell_ids[lvl].to(torch.int64).contiguous()
@@ -97,7 +103,7 @@ class OccGridEstimator(nn.Module):
             else:
                 n_u = n_cells // 4
                 uni = torch.randint(n_cells, (n_u,), device=dev)
-                occ_idx = torch.nonzero(self.binaries[lvl].flatten())[:, 0]
+                occ_idx = torch.nonzero(binaries[lvl].flatten())[:, 0]
                 if n_u < len(occ_idx):
                     occ_idx = occ_idx[torch.randint(len(occ_idx), (n_u,), device=dev)]
                 idx = torch.cat([uni, occ_idx], dim=0).contiguous()
@@ -108,18 +114,18 @@ class OccGridEstimator(nn.Module):
                 torch.rand((m, 3), device=dev)
             pos = torch.empty((m, 3), dtype=torch.float32, device=dev)
             aabb = self.aabbs[lvl].contiguous()
-            check(lib.umhs_occ_cell_points(ptr(idx), ptr(jit), m, res, ptr(aabb), ptr(pos), st),
-                  "umhs_occ_cell_points")
+            ops._call("umhs_occ_cell_points", m, ptr(idx), ptr(jit), m, res, ptr(aabb), ptr(pos), st)
             occ = occ_eval_fn(pos).reshape(-1).to(torch.float32).contiguous()
             tmp = torch.empty((m,), dtype=torch.float32, device=dev)
-            check(lib.umhs_occ_ema_update(ptr(self.occs), ptr(idx), lvl * n_cells, ptr(occ), 1.0, float(ema_decay), m,
-                                          ptr(tmp), st), "umhs_occ_ema_update")
+            ops._call("umhs_occ_ema_update", m, ptr(occs), ptr(idx), lvl * n_cells, ptr(occ), 1.0, float(ema_decay), m,
+                      ptr(tmp), st)
         scratch = torch.empty((2,), dtype=torch.float64, device=dev)
         mean = torch.empty((1,), dtype=torch.float32, device=dev)
-        bn = self.binaries.view(torch.uint8)
-        check(lib.umhs_occ_binarize(ptr(self.occs), self.occs.numel(), float(occ_thre), ptr(scratch), ptr(bn),
-                                    ptr(mean), st), "umhs_occ_binarize")
-        self._occ_mean = mean
+        bn = binaries.view(torch.uint8)
+        ops._call("umhs_occ_binarize", occs.numel(), ptr(occs), occs.numel(), float(occ_thre), ptr(scratch), ptr(bn),
+                  ptr(mean), st)
+        if not freeze_binaries:
+            self._occ_mean = mean
 
 
 class VolumetricSampler(nn.Module):

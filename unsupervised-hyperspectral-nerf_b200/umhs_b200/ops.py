@@ -17,6 +17,68 @@ from ._lib import check, f32, ptr, stream_ptr
 
 ENC_DIM = 32  # 16 levels x 2 features
 
+# kernels launched per C-ABI entry point (for the bench's gpu_launches count)
+_LAUNCHES = {"umhs_hash_encode_fwd": 1, "umhs_hash_encode_bwd": 1, "umhs_hash_encode_x01_fwd": 1,
+             "umhs_hash_encode_x01_bwd": 1, "umhs_density_fwd": 1, "umhs_field_mlp_fwd": 1, "umhs_field_mlp_bwd": 1,
+             "umhs_composite_fwd": 1, "umhs_depth_clip": 1, "umhs_composite_bwd": 1, "umhs_unmix_fwd": 1,
+             "umhs_unmix_bwd": 1, "umhs_render_weights_fwd": 1, "umhs_render_weights_bwd": 1,
+             "umhs_accumulate_fwd": 1, "umhs_accumulate_bwd": 1, "umhs_march_count": 1, "umhs_pack_scan": 1,
+             "umhs_march_write": 1, "umhs_visibility_mask": 1, "umhs_compact_samples": 1, "umhs_pack_info": 2,
+             "umhs_occ_cell_points": 1, "umhs_occ_ema_update": 2, "umhs_occ_binarize": 2, "umhs_adam_step": 1,
+             "umhs_reduce_slabs": 1}
+
+
+class Profiler:
+    """Optional per-entry-point CUDA-event timing on the launching stream + launch counting (bench.py)."""
+    enabled = False
+    timing = False
+    launches = 0
+    records: List[Tuple[str, "torch.cuda.Event", "torch.cuda.Event", int]] = []
+
+    @classmethod
+    def reset(cls, enabled=True, timing=False):
+        cls.enabled, cls.timing, cls.launches, cls.records = enabled, timing, 0, []
+
+    @classmethod
+    def summary(cls) -> Dict[str, Dict[str, float]]:
+        out: Dict[str, Dict[str, float]] = {}
+        for name, a, b, units in cls.records:
+            d = out.setdefault(name, {"calls": 0, "ms": 0.0, "units": 0})
+            d["calls"] += 1
+            d["ms"] += a.elapsed_time(b)
+            d["units"] += units
+        return out
+
+
+def _call(name: str, units: int, *args) -> None:
+    """Invoke a C-ABI entry point (kernels go to torch's current stream) and raise on error."""
+    fn = getattr(_lib.load(), name)
+    if Profiler.enabled:
+        Profiler.launches += _LAUNCHES[name]
+        if Profiler.timing:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = fn(*args)
+            b.record()
+            Profiler.records.append((name, a, b, int(units)))
+            check(rc, name)
+            return
+    check(fn(*args), name)
+
+
+# When True (set by UMHSTrainer), backward kernels accumulate straight into ``param.grad`` of leaf parameters
+# that already own a contiguous fp32 grad buffer (views of the trainer's flat gradient), and autograd gets None.
+DIRECT_GRAD = False
+
+
+def _sink(p: Optional[Tensor]) -> Optional[Tensor]:
+    if not DIRECT_GRAD or p is None or not isinstance(p, Tensor):
+        return None
+    g = p.grad if (p.is_leaf and p.requires_grad) else None
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or not g.is_cuda:
+        return None
+    return g
+
 
 # --------------------------------------------------------------------------------------- points
 @dataclass
@@ -82,8 +144,7 @@ def hash_encode_fwd(pts: PointSet, table: Tensor, scalings: Tensor, log2_T: int)
     L = int(scalings.shape[0])
     enc = torch.empty((pts.n, 2 * L), dtype=torch.float32, device=table.device)
     ps, gs = pts.struct(), _grid_struct(table, scalings, log2_T)
-    check(lib.umhs_hash_encode_fwd(ctypes.byref(ps), pts.n, ctypes.byref(gs), ptr(enc), stream_ptr(table.device)),
-          "umhs_hash_encode_fwd")
+    _call("umhs_hash_encode_fwd", pts.n, ctypes.byref(ps), pts.n, ctypes.byref(gs), ptr(enc), stream_ptr(table.device))
     return enc
 
 
@@ -94,8 +155,8 @@ def hash_encode_bwd(pts: PointSet, table: Tensor, scalings: Tensor, log2_T: int,
     if d_table is None:
         d_table = torch.zeros_like(table, dtype=torch.float32)
     ps, gs = pts.struct(), _grid_struct(table, scalings, log2_T)
-    check(lib.umhs_hash_encode_bwd(ctypes.byref(ps), pts.n, ctypes.byref(gs), ptr(d_enc), ptr(d_table),
-                                   stream_ptr(table.device)), "umhs_hash_encode_bwd")
+    _call("umhs_hash_encode_bwd", pts.n, ctypes.byref(ps), pts.n, ctypes.byref(gs), ptr(d_enc), ptr(d_table),
+                                   stream_ptr(table.device))
     return d_table
 
 
@@ -104,8 +165,7 @@ def hash_encode_x01_fwd(x01: Tensor, table: Tensor, scalings: Tensor, log2_T: in
     x = f32(x01).reshape(-1, 3)
     enc = torch.empty((x.shape[0], 2 * int(scalings.shape[0])), dtype=torch.float32, device=table.device)
     gs = _grid_struct(table, scalings, log2_T)
-    check(lib.umhs_hash_encode_x01_fwd(ptr(x), x.shape[0], ctypes.byref(gs), ptr(enc), stream_ptr(table.device)),
-          "umhs_hash_encode_x01_fwd")
+    _call("umhs_hash_encode_x01_fwd", x.shape[0], ptr(x), x.shape[0], ctypes.byref(gs), ptr(enc), stream_ptr(table.device))
     return enc
 
 
@@ -114,8 +174,8 @@ def hash_encode_x01_bwd(x01: Tensor, table: Tensor, scalings: Tensor, log2_T: in
     x = f32(x01).reshape(-1, 3)
     d_table = torch.zeros_like(table, dtype=torch.float32)
     gs = _grid_struct(table, scalings, log2_T)
-    check(lib.umhs_hash_encode_x01_bwd(ptr(x), x.shape[0], ctypes.byref(gs), ptr(f32(d_enc)), ptr(d_table),
-                                       stream_ptr(table.device)), "umhs_hash_encode_x01_bwd")
+    _call("umhs_hash_encode_x01_bwd", x.shape[0], ptr(x), x.shape[0], ctypes.byref(gs), ptr(f32(d_enc)), ptr(d_table),
+                                       stream_ptr(table.device))
     return d_table
 
 
@@ -153,8 +213,8 @@ def density_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor]) -> Tenso
     lib = _lib.load()
     sigma = torch.empty((pts.n,), dtype=torch.float32, device=enc.device)
     ps, ms = pts.struct(), mlp_struct(weights, 1, False, 1.0)
-    check(lib.umhs_density_fwd(ctypes.byref(ps), pts.n, ptr(enc), ctypes.byref(ms), ptr(sigma),
-                               stream_ptr(enc.device)), "umhs_density_fwd")
+    _call("umhs_density_fwd", pts.n, ctypes.byref(ps), pts.n, ptr(enc), ctypes.byref(ms), ptr(sigma),
+                               stream_ptr(enc.device))
     return sigma
 
 
@@ -172,8 +232,7 @@ def field_mlp_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int
     for k, v in out.items():
         setattr(fo, k, ptr(v))
     ps, ms = pts.struct(), mlp_struct(weights, K, specular, temperature)
-    check(lib.umhs_field_mlp_fwd(ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(fo), stream_ptr(dev)),
-          "umhs_field_mlp_fwd")
+    _call("umhs_field_mlp_fwd", n, ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(fo), stream_ptr(dev))
     return out
 
 
@@ -193,8 +252,8 @@ def field_mlp_bwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int
     for name in MLP_NAMES:
         setattr(dp, name, ptr(d_weights.get(name)))
     ps, ms = pts.struct(), mlp_struct(weights, K, specular, temperature)
-    check(lib.umhs_field_mlp_bwd(ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(g), ptr(d_enc),
-                                 ctypes.byref(dp), stream_ptr(dev)), "umhs_field_mlp_bwd")
+    _call("umhs_field_mlp_bwd", n, ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(g), ptr(d_enc),
+                                 ctypes.byref(dp), stream_ptr(dev))
     return d_enc, d_weights
 
 
@@ -210,6 +269,7 @@ class FieldFunction(torch.autograd.Function):
         out = field_mlp_fwd(pts, enc, weights, cfg["K"], cfg["specular"], cfg["temperature"])
         ctx.pts, ctx.cfg = pts, cfg
         ctx.n_mlp = len(mlp)
+        ctx.param_refs = (table, mlp)  # the Parameter objects themselves (for direct gradient accumulation)
         ctx.save_for_backward(enc, table, scalings, *[w for w in mlp if w is not None])
         ctx.mlp_present = [w is not None for w in mlp]
         empty = torch.empty((0,), device=enc.device)
@@ -233,9 +293,15 @@ class FieldFunction(torch.autograd.Function):
         if cfg["specular"]:
             grads["d_s1"] = c(d_s1, (n,))
             grads["d_spec_hidden"] = c(d_sh, (n, 16))
-        d_enc, d_w = field_mlp_bwd(pts, enc, weights, K, cfg["specular"], cfg["temperature"], grads)
-        d_table = hash_encode_bwd(pts, table, scalings, cfg["log2_T"], d_enc)
-        return (None, None, d_table, None, *[d_w.get(n) if p else None for n, p in zip(MLP_NAMES, ctx.mlp_present)])
+        p_table, p_mlp = ctx.param_refs
+        sinks = {n: _sink(w) for n, w in zip(MLP_NAMES, p_mlp)}
+        d_w_in = {n: (sinks[n] if sinks[n] is not None else torch.zeros_like(w, dtype=torch.float32))
+                  for n, w in weights.items() if w is not None}
+        d_enc, d_w = field_mlp_bwd(pts, enc, weights, K, cfg["specular"], cfg["temperature"], grads, d_w_in)
+        t_sink = _sink(p_table)
+        d_table = hash_encode_bwd(pts, table, scalings, cfg["log2_T"], d_enc, t_sink)
+        return (None, None, None if t_sink is not None else d_table, None,
+                *[(d_w.get(n) if (p and sinks[n] is None) else None) for n, p in zip(MLP_NAMES, ctx.mlp_present)])
 
 
 # --------------------------------------------------------------------------------------- compositing
@@ -271,6 +337,7 @@ class CompositeFunction(torch.autograd.Function):
         lib = _lib.load()
         dev = sigma.device
         R, N, K, B, specular = int(packed_info.shape[0]), int(sigma.shape[0]), cfg["K"], cfg["B"], cfg["specular"]
+        ctx.param_refs = (endmembers, dir_w1, dir_b1)
         tens = [f32(x) if x is not None and x.numel() else None
                 for x in (t0, t1, sigma, scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1, rgb_matrix,
                           palette)]
@@ -287,8 +354,8 @@ class CompositeFunction(torch.autograd.Function):
         for k, v in out.items():
             setattr(co, k, ptr(v))
         co.t_minmax = ptr(tmm)
-        check(lib.umhs_composite_fwd(ctypes.byref(ci), ctypes.byref(co), stream_ptr(dev)), "umhs_composite_fwd")
-        check(lib.umhs_depth_clip(ptr(out["depth"]), R, ptr(tmm), stream_ptr(dev)), "umhs_depth_clip")
+        _call("umhs_composite_fwd", R, ctypes.byref(ci), ctypes.byref(co), stream_ptr(dev))
+        _call("umhs_depth_clip", 0, ptr(out["depth"]), R, ptr(tmm), stream_ptr(dev))
         ctx.cfg = cfg
         ctx.save_for_backward(packed_info, t0, t1, sigma, scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1,
                               rgb_matrix, out["spectral"])
@@ -317,16 +384,17 @@ class CompositeFunction(torch.autograd.Function):
         d_sigma, d_scalar, d_abund = z(N), z(N, K), z(N, K)
         d_s1 = z(N) if specular else None
         d_sh = z(N, 16) if specular else None
-        d_E = torch.zeros((K, B), dtype=torch.float32, device=dev)
-        d_w1 = torch.zeros((B, 16), dtype=torch.float32, device=dev) if specular else None
-        d_b1 = torch.zeros((B,), dtype=torch.float32, device=dev) if specular else None
+        sE, sW, sB = (_sink(p) for p in ctx.param_refs)
+        d_E = sE if sE is not None else torch.zeros((K, B), dtype=torch.float32, device=dev)
+        d_w1 = (sW if sW is not None else torch.zeros((B, 16), dtype=torch.float32, device=dev)) if specular else None
+        d_b1 = (sB if sB is not None else torch.zeros((B,), dtype=torch.float32, device=dev)) if specular else None
         go = _lib.CompositeGradsOut()
         go.d_sigma, go.d_scalar, go.d_abund = ptr(d_sigma), ptr(d_scalar), ptr(d_abund)
         go.d_s1, go.d_spec_hidden = ptr(d_s1), ptr(d_sh)
         go.d_endmembers, go.d_dir_w1, go.d_dir_b1 = ptr(d_E), ptr(d_w1), ptr(d_b1)
-        check(lib.umhs_composite_bwd(ctypes.byref(ci), ctypes.byref(gi), ctypes.byref(go), stream_ptr(dev)),
-              "umhs_composite_bwd")
-        return (None, None, None, None, d_sigma, d_scalar, d_abund, d_s1, d_sh, d_E, d_w1, d_b1, None, None)
+        _call("umhs_composite_bwd", R, ctypes.byref(ci), ctypes.byref(gi), ctypes.byref(go), stream_ptr(dev))
+        return (None, None, None, None, d_sigma, d_scalar, d_abund, d_s1, d_sh, None if sE is not None else d_E,
+                None if sW is not None else d_w1, None if sB is not None else d_b1, None, None)
 
 
 # --------------------------------------------------------------------------------------- unfused module-boundary ops
@@ -346,9 +414,8 @@ class UnmixFunction(torch.autograd.Function):
         sp = torch.empty((n, B), dtype=torch.float32, device=dev) if specular else None
         if specular:
             s1, spec_hidden, dir_w1, dir_b1 = f32(s1).reshape(-1), f32(spec_hidden), f32(dir_w1), f32(dir_b1)
-        check(lib.umhs_unmix_fwd(n, K, B, int(specular), ptr(scalar), ptr(abund), ptr(s1), ptr(spec_hidden),
-                                 ptr(endmembers), ptr(dir_w1), ptr(dir_b1), ptr(spec), ptr(sp), stream_ptr(dev)),
-              "umhs_unmix_fwd")
+        _call("umhs_unmix_fwd", 0, n, K, B, int(specular), ptr(scalar), ptr(abund), ptr(s1), ptr(spec_hidden),
+                                 ptr(endmembers), ptr(dir_w1), ptr(dir_b1), ptr(spec), ptr(sp), stream_ptr(dev))
         ctx.specular = specular
         ctx.save_for_backward(scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1)
         return spec, (sp if specular else torch.empty((0,), device=dev))
@@ -369,10 +436,9 @@ class UnmixFunction(torch.autograd.Function):
         d_sh = torch.zeros_like(spec_hidden) if specular else None
         d_w1 = torch.zeros_like(dir_w1) if specular else None
         d_b1 = torch.zeros_like(dir_b1) if specular else None
-        check(lib.umhs_unmix_bwd(n, K, B, int(specular), ptr(scalar), ptr(abund), ptr(s1), ptr(spec_hidden),
+        _call("umhs_unmix_bwd", 0, n, K, B, int(specular), ptr(scalar), ptr(abund), ptr(s1), ptr(spec_hidden),
                                  ptr(endmembers), ptr(dir_w1), ptr(dir_b1), ptr(d_spec), ptr(d_sp), ptr(d_scalar),
-                                 ptr(d_abund), ptr(d_s1), ptr(d_sh), ptr(d_E), ptr(d_w1), ptr(d_b1), stream_ptr(dev)),
-              "umhs_unmix_bwd")
+                                 ptr(d_abund), ptr(d_s1), ptr(d_sh), ptr(d_E), ptr(d_w1), ptr(d_b1), stream_ptr(dev))
         return d_scalar, d_abund, d_s1, d_sh, d_E, d_w1, d_b1
 
 
@@ -383,8 +449,7 @@ def pack_info(ray_indices: Tensor, n_rays: int) -> Tensor:
     dev = ri.device
     counts = torch.empty((n_rays,), dtype=torch.int64, device=dev)
     packed = torch.empty((n_rays, 2), dtype=torch.int64, device=dev)
-    check(lib.umhs_pack_info(ptr(ri), ri.shape[0], n_rays, ptr(counts), ptr(packed), stream_ptr(dev)),
-          "umhs_pack_info")
+    _call("umhs_pack_info", 0, ptr(ri), ri.shape[0], n_rays, ptr(counts), ptr(packed), stream_ptr(dev))
     return packed
 
 
@@ -396,8 +461,8 @@ class RenderWeightsFunction(torch.autograd.Function):
         lib = _lib.load()
         t0, t1, sigma = f32(t0).reshape(-1), f32(t1).reshape(-1), f32(sigma).reshape(-1)
         w, T = torch.empty_like(sigma), torch.empty_like(sigma)
-        check(lib.umhs_render_weights_fwd(ptr(packed_info), packed_info.shape[0], ptr(t0), ptr(t1), ptr(sigma),
-                                          ptr(w), ptr(T), stream_ptr(sigma.device)), "umhs_render_weights_fwd")
+        _call("umhs_render_weights_fwd", 0, ptr(packed_info), packed_info.shape[0], ptr(t0), ptr(t1), ptr(sigma),
+                                          ptr(w), ptr(T), stream_ptr(sigma.device))
         ctx.save_for_backward(t0, t1, sigma, packed_info, T)
         ctx.mark_non_differentiable(T)
         return w, T
@@ -407,9 +472,8 @@ class RenderWeightsFunction(torch.autograd.Function):
         lib = _lib.load()
         t0, t1, sigma, packed_info, T = ctx.saved_tensors
         d_sigma = torch.empty_like(sigma)
-        check(lib.umhs_render_weights_bwd(ptr(packed_info), packed_info.shape[0], ptr(t0), ptr(t1), ptr(sigma),
-                                          ptr(T), ptr(f32(d_w).reshape(-1)), ptr(d_sigma), stream_ptr(sigma.device)),
-              "umhs_render_weights_bwd")
+        _call("umhs_render_weights_bwd", 0, ptr(packed_info), packed_info.shape[0], ptr(t0), ptr(t1), ptr(sigma),
+                                          ptr(T), ptr(f32(d_w).reshape(-1)), ptr(d_sigma), stream_ptr(sigma.device))
         return None, None, d_sigma, None
 
 
@@ -424,8 +488,7 @@ class AccumulateFunction(torch.autograd.Function):
         C = v.shape[-1] if v is not None else 1
         ri = ray_indices.to(torch.int64).contiguous()
         out = torch.zeros((n_rays, C), dtype=torch.float32, device=w.device)
-        check(lib.umhs_accumulate_fwd(ptr(w), ptr(v), ptr(ri), w.shape[0], C, ptr(out), stream_ptr(w.device)),
-              "umhs_accumulate_fwd")
+        _call("umhs_accumulate_fwd", 0, ptr(w), ptr(v), ptr(ri), w.shape[0], C, ptr(out), stream_ptr(w.device))
         ctx.save_for_backward(w, v, ri)
         ctx.has_values = v is not None
         return out
@@ -437,8 +500,8 @@ class AccumulateFunction(torch.autograd.Function):
         C = v.shape[-1] if ctx.has_values else 1
         d_w = torch.empty_like(w)
         d_v = torch.empty_like(v) if ctx.has_values else None
-        check(lib.umhs_accumulate_bwd(ptr(w), ptr(v), ptr(ri), w.shape[0], C, ptr(f32(d_out)), ptr(d_w), ptr(d_v),
-                                      stream_ptr(w.device)), "umhs_accumulate_bwd")
+        _call("umhs_accumulate_bwd", 0, ptr(w), ptr(v), ptr(ri), w.shape[0], C, ptr(f32(d_out)), ptr(d_w), ptr(d_v),
+                                      stream_ptr(w.device))
         return d_w, d_v, None, None
 
 
@@ -462,14 +525,14 @@ def march(rays_o: Tensor, rays_d: Tensor, near_planes: Tensor, far_planes: Tenso
     packed = torch.empty((R, 2), dtype=torch.int64, device=dev)
     total = torch.zeros((1,), dtype=torch.int64, device=dev)
     st = stream_ptr(dev)
-    check(lib.umhs_march_count(ctypes.byref(a), ptr(counts), st), "umhs_march_count")
-    check(lib.umhs_pack_scan(ptr(counts), R, ptr(packed), ptr(total), st), "umhs_pack_scan")
+    _call("umhs_march_count", R, ctypes.byref(a), ptr(counts), st)
+    _call("umhs_pack_scan", R, ptr(counts), R, ptr(packed), ptr(total), st)
     N = int(total.item())
     ri = torch.empty((N,), dtype=torch.int64, device=dev)
     t0 = torch.empty((N,), dtype=torch.float32, device=dev)
     t1 = torch.empty((N,), dtype=torch.float32, device=dev)
     if N > 0:
-        check(lib.umhs_march_write(ctypes.byref(a), ptr(packed), ptr(ri), ptr(t0), ptr(t1), st), "umhs_march_write")
+        _call("umhs_march_write", R, ctypes.byref(a), ptr(packed), ptr(ri), ptr(t0), ptr(t1), st)
     return ri, t0, t1, packed
 
 
@@ -484,17 +547,16 @@ def visibility_compact(packed_info: Tensor, t0: Tensor, t1: Tensor, sigma: Tenso
     packed2 = torch.empty((R, 2), dtype=torch.int64, device=dev)
     total = torch.zeros((1,), dtype=torch.int64, device=dev)
     st = stream_ptr(dev)
-    check(lib.umhs_visibility_mask(ptr(packed_info), R, ptr(t0), ptr(t1), ptr(f32(sigma).reshape(-1)),
-                                   float(early_stop_eps), float(alpha_thre), ptr(occ_mean), ptr(keep), ptr(kc), st),
-          "umhs_visibility_mask")
-    check(lib.umhs_pack_scan(ptr(kc), R, ptr(packed2), ptr(total), st), "umhs_pack_scan")
+    _call("umhs_visibility_mask", R, ptr(packed_info), R, ptr(t0), ptr(t1), ptr(f32(sigma).reshape(-1)),
+                                   float(early_stop_eps), float(alpha_thre), ptr(occ_mean), ptr(keep), ptr(kc), st)
+    _call("umhs_pack_scan", R, ptr(kc), R, ptr(packed2), ptr(total), st)
     M = int(total.item())
     ri = torch.empty((M,), dtype=torch.int64, device=dev)
     o0 = torch.empty((M,), dtype=torch.float32, device=dev)
     o1 = torch.empty((M,), dtype=torch.float32, device=dev)
     if M > 0:
-        check(lib.umhs_compact_samples(ptr(packed_info), ptr(packed2), R, ptr(keep), ptr(t0), ptr(t1), ptr(ri),
-                                       ptr(o0), ptr(o1), st), "umhs_compact_samples")
+        _call("umhs_compact_samples", R, ptr(packed_info), ptr(packed2), R, ptr(keep), ptr(t0), ptr(t1), ptr(ri),
+                                       ptr(o0), ptr(o1), st)
     return ri, o0, o1, packed2
 
 
@@ -503,6 +565,6 @@ def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, 
               eps: float, step: int, inv_scale: Optional[Tensor] = None, found_inf: Optional[Tensor] = None,
               clamp_range: Tuple[int, int] = (0, 0), zero_grad: bool = True) -> None:
     lib = _lib.load()
-    check(lib.umhs_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1, beta2,
+    _call("umhs_adam_step", param.numel(), ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1, beta2,
                              eps, step, ptr(inv_scale), ptr(found_inf), clamp_range[0], clamp_range[1],
-                             1 if zero_grad else 0, stream_ptr(param.device)), "umhs_adam_step")
+                             1 if zero_grad else 0, stream_ptr(param.device))
