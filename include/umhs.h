@@ -134,6 +134,17 @@ int umhs_density_fwd(const umhs_points *pts, int64_t n, const float *enc, const 
                      void *stream);
 int umhs_field_mlp_fwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
                        const umhs_field_out *out, void *stream);
+/* Tensor-core variants (tcgen05 + TMEM, bf16 operands, fp32 accumulation): same interface and outputs as the
+ * fp32 entry points above within bf16 tolerance.  These are the plugin's default; the fp32 ones are the
+ * "precise" mode used by the tight parity tests. */
+int umhs_density_tc_fwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p, float *sigma,
+                        void *stream);
+int umhs_field_mlp_tc_fwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
+                          const umhs_field_out *out, void *stream);
+/* One-CTA self-test of the three tcgen05 GEMM forms the MLP kernels are built from (fp32 in/out, bf16 operands):
+ * mode 0: D[128xN] = A[128xK] B[NxK]^T; mode 1: D[128xN] = A[128xK] W[KxN]; mode 2: D[64xN] = P[128x64]^T Q[128xN]. */
+int umhs_tc05_selftest(int32_t mode, const float *A, const float *B, float *D, int32_t N, int32_t K, void *stream);
+
 /* parameter gradients are ACCUMULATED (+=) into *dp; d_enc [n,32] is overwritten (may be NULL).
  * Activations are recomputed from enc; nothing else is kept from the forward pass. */
 int umhs_field_mlp_bwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,

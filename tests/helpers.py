@@ -80,3 +80,24 @@ def assert_close(a, b, rtol, atol, name=""):
             f"{name}: {int(bad.sum())}/{bad.size} elements differ (rtol={rtol}, atol={atol:.3g}); worst at {i}: "
             f"got {a[i]:.9g} want {b[i]:.9g}; max|err|={err.max():.3g}, max|want|={np.abs(b).max():.3g}, "
             f"rel L2 err={np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30):.3g}")
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def mlp_precision(mode):
+    """Select the MLP kernel family for a test: "fp32" (SIMT, tight parity) or "bf16" (tcgen05 tensor cores)."""
+    from umhs_b200 import ops
+    old = ops.MLP_PRECISION
+    ops.MLP_PRECISION = mode
+    try:
+        yield
+    finally:
+        ops.MLP_PRECISION = old
+
+
+def rel_l2(a, b):
+    a = a.detach().cpu().double().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float64)
+    b = b.detach().cpu().double().numpy() if isinstance(b, torch.Tensor) else np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a.reshape(b.shape) - b) / (np.linalg.norm(b) + 1e-30))

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import assert_close, b200_model_from_golden, load_golden, t
+from helpers import assert_close, b200_model_from_golden, load_golden, mlp_precision, rel_l2, t
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -54,11 +54,43 @@ def _field_case(name):
 
 
 def test_field_k4_golden():
-    _field_case("field_k4.npz")
+    with mlp_precision("fp32"):
+        _field_case("field_k4.npz")
 
 
 def test_field_k6_specular_golden():
-    _field_case("field_k6_spec.npz")
+    with mlp_precision("fp32"):
+        _field_case("field_k6_spec.npz")
+
+
+def _field_case_bf16(name):
+    """Tensor-core path (bf16 operands, fp32 accumulate) against the fp32 golden vectors: stated bf16 tolerance =
+    relative L2 error <= 2e-2 per output tensor (bf16 has 8 mantissa bits; three chained 64-wide layers)."""
+    from umhs_b200.rays import Frustums, RaySamples
+
+    d, meta = load_golden(name)
+    m = b200_model_from_golden(d, meta)
+    f = m.field
+    rs = RaySamples(Frustums(t(d["origins"]).to(DEV), t(d["directions"]).to(DEV), t(d["starts"]).to(DEV),
+                             t(d["ends"]).to(DEV)))
+    with mlp_precision("bf16"):
+        density, emb = f.get_density(rs)
+        out = f.get_outputs(rs, emb)
+    assert rel_l2(density, d["density"]) < 2e-2
+    assert rel_l2(emb, d["embedding"]) < 2e-2
+    assert rel_l2(out["spectral"], d["spectral"]) < 2e-2
+    assert rel_l2(out["abundances"], d["abundances"]) < 2e-2
+    if meta["specular"]:
+        assert rel_l2(out["spectral2"], d["spectral2"]) < 2e-2
+        assert rel_l2(out["specular"], d["specular"]) < 2e-2
+
+
+def test_field_k4_golden_bf16():
+    _field_case_bf16("field_k4.npz")
+
+
+def test_field_k6_specular_golden_bf16():
+    _field_case_bf16("field_k6_spec.npz")
 
 
 def _model_case(name):
@@ -94,15 +126,18 @@ def _model_case(name):
 
 
 def test_model_train_k4_golden():
-    _model_case("model_train_k4.npz")
+    with mlp_precision("fp32"):
+        _model_case("model_train_k4.npz")
 
 
 def test_model_train_k4_specular_golden():
-    _model_case("model_train_k4_spec.npz")
+    with mlp_precision("fp32"):
+        _model_case("model_train_k4_spec.npz")
 
 
 def test_model_eval_k9_specular_golden():
-    _model_case("model_eval_k9_spec.npz")
+    with mlp_precision("fp32"):
+        _model_case("model_eval_k9_spec.npz")
 
 
 def test_native_library_is_what_ran():

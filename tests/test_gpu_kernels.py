@@ -304,3 +304,61 @@ def test_adam_matches_torch():
         ops.adam_step(p, gd, m, v, 2e-2, 0.9, 0.999, 1e-15, step, clamp_range=(10, 200))
         assert float(gd.abs().max()) == 0.0  # zero_grad fused
     assert_close(p, ref, 1e-5, 1e-6)
+
+
+# ------------------------------------------------------------------ tensor-core building blocks
+@pytest.mark.parametrize("mode,N,K", [(0, 64, 32), (0, 16, 64), (0, 128, 32), (0, 32, 64), (1, 64, 16), (1, 64, 64),
+                                      (1, 32, 64), (2, 64, 128), (2, 16, 128), (2, 32, 128), (2, 48, 128)])
+def test_tc05_gemm_forms(mode, N, K):
+    """tcgen05.mma descriptor forms used by the MLP kernels, against torch on bf16-rounded operands (exact products,
+    fp32 accumulation: only summation order differs)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(mode * 100 + N + K)
+    bf = lambda x: x.to(torch.bfloat16).to(torch.float32)  # noqa: E731
+    if mode == 0:
+        A, B = bf(torch.randn(128, K, generator=g)), bf(torch.randn(N, K, generator=g))
+        ref = A @ B.t()
+    elif mode == 1:
+        A, B = bf(torch.randn(128, K, generator=g)), bf(torch.randn(K, N, generator=g))
+        ref = A @ B
+    else:
+        A, B = bf(torch.randn(128, 64, generator=g)), bf(torch.randn(128, N, generator=g))
+        ref = A.t() @ B
+    D = ops.tc05_selftest(mode, A.to(DEV), B.to(DEV), N, K)
+    assert_close(D, ref, 1e-4, 1e-4, f"tc05 mode {mode} N={N} K={K}")
+
+
+@pytest.mark.parametrize("K,specular", [(4, False), (9, True), (16, True), (16, False), (1, False)])
+def test_field_mlp_tc_fwd_matches_fp32(K, specular):
+    """bf16 tensor-core forward against the fp32 SIMT forward on the same inputs (relative L2 <= 1e-2)."""
+    from helpers import rel_l2
+    ops = _ops()
+    g = torch.Generator().manual_seed(K)
+    N = 1000  # not a multiple of 128: exercises the tail tile
+    pos = (torch.rand(N, 3, generator=g) * 2 - 1) * 1.3
+    dirs = torch.nn.functional.normalize(torch.randn(N, 3, generator=g), dim=-1)
+    enc = torch.randn(N, 32, generator=g)
+    mk = lambda o, i: ((torch.rand(o, i, generator=g) * 2 - 1) / i ** 0.5, (torch.rand(o, generator=g) * 2 - 1) * 0.1)  # noqa: E731
+    w = {}
+    for name, (o, i) in {"base_w0": (64, 32), "base_w1": (16, 64), "head_w0": (64, 27), "head_w1": (64, 64),
+                         "head_w2": (K, 64), "feat_w0": (64, 27), "feat_w1": (64, 64),
+                         "feat_w2": (K + int(specular), 64), "dir_w0": (16, 28)}.items():
+        W, b = mk(o, i)
+        w[name], w[name.replace("_w", "_b")] = W.to(DEV).contiguous(), b.to(DEV).contiguous()
+    if not specular:
+        w["dir_w0"] = w["dir_b0"] = None
+    pts = ops.PointSet.from_positions(pos.to(DEV), dirs.to(DEV))
+    res = {}
+    for mode in ("fp32", "bf16"):
+        ops.MLP_PRECISION = mode
+        try:
+            res[mode] = ops.field_mlp_fwd(pts, enc.to(DEV), w, K, specular, 0.4)
+            res[mode]["density_only"] = ops.density_fwd(pts, enc.to(DEV), w)
+        finally:
+            ops.MLP_PRECISION = "bf16"
+    for k, v in res["fp32"].items():
+        if v is None:
+            continue
+        err = rel_l2(res["bf16"][k], v)
+        assert err < 1e-2, (k, err)
+    assert torch.equal(res["bf16"]["density_only"], res["bf16"]["sigma"])

@@ -1,0 +1,497 @@
+// field_mlp_tc.cu -- the fused field MLPs on the 5th-generation tensor cores (tcgen05 + TMEM), bf16 operands,
+// fp32 accumulation.  Same arithmetic and interface as field_mlp.cu (the fp32 SIMT path); this is the default.
+//
+// One CTA = 128 threads = one tile of 128 samples; thread t owns sample row t (it is also TMEM lane t of every
+// [128 x N] accumulator, so the epilogue -- bias, ReLU, softmax, sigmoid, trunc_exp -- is thread-private).
+// All layer weights are staged once per CTA in shared memory as bf16 UMMA operand tiles; activations are
+// written by their owning threads straight into operand tiles (tc05.cuh layout), one elected thread issues
+// tcgen05.mma, completion comes back through an mbarrier (tcgen05.commit), accumulators are read with
+// tcgen05.ld.  Layers that share an input run as one MMA (mlp_head/feature_mlp layer 0: N = 128) or are
+// issued back to back under one commit.
+//
+// Forward rounds per tile:   enc->[base0] -> [base1 | dir0] -> [head0+feat0] -> [head1, feat1] -> [head2, feat2]
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace umhs {
+using namespace tc05;
+
+constexpr int TM = 128;          // samples per tile == threads per CTA
+constexpr int CH_ACT = 2048;     // chunk stride of a 128-row activation tile
+
+// ---- shared-memory plan (bytes).  Weight tiles: [rows x K] bf16, CH = rows * 16.
+struct TcSmem {
+    // weights
+    static constexpr int w_base0 = 0;                       // [64 x 32]
+    static constexpr int w_base1 = w_base0 + 64 * 32 * 2;   // [16 x 64]
+    static constexpr int w_hf0 = w_base1 + 16 * 64 * 2;     // [128 x 32]  rows 0-63 mlp_head.0, 64-127 feature_mlp.0
+    static constexpr int w_h1 = w_hf0 + 128 * 32 * 2;       // [64 x 64]
+    static constexpr int w_f1 = w_h1 + 64 * 64 * 2;         // [64 x 64]
+    static constexpr int w_h2 = w_f1 + 64 * 64 * 2;         // [16 x 64]
+    static constexpr int w_f2 = w_h2 + 16 * 64 * 2;         // [32 x 64]
+    static constexpr int w_d0 = w_f2 + 32 * 64 * 2;         // [16 x 32]
+    static constexpr int w_end = w_d0 + 16 * 32 * 2;
+    // biases (fp32): base0 64, base1 16, head0 64, feat0 64, head1 64, feat1 64, head2 16, feat2 32, dir0 16
+    static constexpr int b_base0 = w_end;
+    static constexpr int b_base1 = b_base0 + 64 * 4;
+    static constexpr int b_h0 = b_base1 + 16 * 4;
+    static constexpr int b_f0 = b_h0 + 64 * 4;
+    static constexpr int b_h1 = b_f0 + 64 * 4;
+    static constexpr int b_f1 = b_h1 + 64 * 4;
+    static constexpr int b_h2 = b_f1 + 64 * 4;
+    static constexpr int b_f2 = b_h2 + 16 * 4;
+    static constexpr int b_d0 = b_f2 + 32 * 4;
+    static constexpr int b_end = b_d0 + 16 * 4;
+    static constexpr int ctrl = (b_end + 127) / 128 * 128;  // mbarrier (8 B) + tmem address (4 B)
+    static constexpr int act = ctrl + 128;
+    // forward activation tiles
+    static constexpr int f_x = act;                 // [128 x 32]  enc, then [pe, emb]
+    static constexpr int f_x2 = f_x + TM * 32 * 2;  // [128 x 32]  [sh16, pe12] (specular)
+    static constexpr int f_h = f_x2 + TM * 32 * 2;  // [128 x 64]
+    static constexpr int f_f = f_h + TM * 64 * 2;   // [128 x 64]
+    static constexpr int f_end = f_f + TM * 64 * 2;
+};
+
+// stage an nn.Linear weight [out x in] (fp32, global) as a bf16 K-major operand tile with `rows` rows at row0
+__device__ __forceinline__ void stage_weight(uint8_t *tile, int rows, int row0, const float *w, int out, int in,
+                                             int k_pad, int tid) {
+    const int ch = rows * 16;
+    for (int i = tid; i < out * (k_pad / 8); i += TM) {
+        const int j = i / (k_pad / 8), c0 = (i - j * (k_pad / 8)) * 8;
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (c0 + q < in) ? __ldg(w + j * in + c0 + q) : 0.f;
+        store8(tile, row0 + j, c0, ch, v);
+    }
+}
+__device__ __forceinline__ void zero_rows(uint8_t *tile, int rows, int row_from, int row_to, int k_pad, int tid) {
+    const int ch = rows * 16;
+    const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = tid; i < (row_to - row_from) * (k_pad / 8); i += TM) {
+        const int j = i / (k_pad / 8), c0 = (i - j * (k_pad / 8)) * 8;
+        store8(tile, row_from + j, c0, ch, z);
+    }
+}
+__device__ __forceinline__ void stage_bias(float *dst, const float *b, int n, int n_pad, int tid) {
+    for (int i = tid; i < n_pad; i += TM) dst[i] = (b != nullptr && i < n) ? __ldg(b + i) : 0.f;
+}
+
+__device__ __forceinline__ void stage_all_weights(uint8_t *smem, const umhs_mlp_params &mp, bool density_only, int tid) {
+    const int K = mp.num_classes, spec = mp.specular;
+    stage_weight(smem + TcSmem::w_base0, 64, 0, mp.base_w0, 64, 32, 32, tid);
+    stage_weight(smem + TcSmem::w_base1, 16, 0, mp.base_w1, 16, 64, 64, tid);
+    stage_bias(reinterpret_cast<float *>(smem + TcSmem::b_base0), mp.base_b0, 64, 64, tid);
+    stage_bias(reinterpret_cast<float *>(smem + TcSmem::b_base1), mp.base_b1, 16, 16, tid);
+    if (density_only) return;
+    stage_weight(smem + TcSmem::w_hf0, 128, 0, mp.head_w0, 64, 27, 32, tid);
+    stage_weight(smem + TcSmem::w_hf0, 128, 64, mp.feat_w0, 64, 27, 32, tid);
+    stage_weight(smem + TcSmem::w_h1, 64, 0, mp.head_w1, 64, 64, 64, tid);
+    stage_weight(smem + TcSmem::w_f1, 64, 0, mp.feat_w1, 64, 64, 64, tid);
+    stage_weight(smem + TcSmem::w_h2, 16, 0, mp.head_w2, K, 64, 64, tid);
+    zero_rows(smem + TcSmem::w_h2, 16, K, 16, 64, tid);
+    stage_weight(smem + TcSmem::w_f2, 32, 0, mp.feat_w2, K + spec, 64, 64, tid);
+    zero_rows(smem + TcSmem::w_f2, 32, K + spec, 32, 64, tid);
+    stage_bias(reinterpret_cast<float *>(smem + TcSmem::b_h0), mp.head_b0, 64, 64, tid);
+    stage_bias(reinterpret_cast<float *>(smem + TcSmem::b_f0), mp.feat_b0, 64, 64, tid);
+    stage_bias(reinterpret_cast<float *>(smem + TcSmem::b_h1), mp.head_b1, 64, 64, tid);
+    stage_bias(reinterpret_cast<float *>(smem + TcSmem::b_f1), mp.feat_b1, 64, 64, tid);
+    stage_bias(reinterpret_cast<float *>(smem + TcSmem::b_h2), mp.head_b2, K, 16, tid);
+    stage_bias(reinterpret_cast<float *>(smem + TcSmem::b_f2), mp.feat_b2, K + spec, 32, tid);
+    if (spec) {
+        stage_weight(smem + TcSmem::w_d0, 16, 0, mp.dir_w0, 16, 28, 32, tid);
+        stage_bias(reinterpret_cast<float *>(smem + TcSmem::b_d0), mp.dir_b0, 16, 16, tid);
+    }
+}
+
+__device__ __forceinline__ void pos_encoding_tc(const Point &p, float (&pe)[12]) {
+    const float two_pi = 6.283185307179586f, half_pi = 1.5707963267948966f;
+    const float s[3] = {two_pi * p.wx, two_pi * p.wy, two_pi * p.wz};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float a = s[d], b = s[d] * 2.0f;
+        pe[2 * d] = sinf(a);
+        pe[2 * d + 1] = sinf(b);
+        pe[6 + 2 * d] = sinf(a + half_pi);
+        pe[6 + 2 * d + 1] = sinf(b + half_pi);
+    }
+}
+
+__device__ __forceinline__ void sh_deg3_tc(float x, float y, float z, float (&c)[16]) {
+    const float xx = x * x, yy = y * y, zz = z * z;
+    c[0] = 0.28209479177387814f;
+    c[1] = 0.4886025119029199f * y;
+    c[2] = 0.4886025119029199f * z;
+    c[3] = 0.4886025119029199f * x;
+    c[4] = 1.0925484305920792f * x * y;
+    c[5] = 1.0925484305920792f * y * z;
+    c[6] = 0.9461746957575601f * zz - 0.31539156525251999f;
+    c[7] = 1.0925484305920792f * x * z;
+    c[8] = 0.5462742152960396f * (xx - yy);
+    c[9] = 0.5900435899266435f * y * (3.0f * xx - yy);
+    c[10] = 2.890611442640554f * x * y * z;
+    c[11] = 0.4570457994644658f * y * (5.0f * zz - 1.0f);
+    c[12] = 0.3731763325901154f * z * (5.0f * zz - 3.0f);
+    c[13] = 0.4570457994644658f * x * (5.0f * zz - 1.0f);
+    c[14] = 1.445305721320277f * z * (xx - yy);
+    c[15] = 0.5900435899266435f * x * (xx - 3.0f * yy);
+}
+
+// epilogue helper: accumulator columns [col0, col0+ncols) of this thread's row -> + bias, ReLU -> bf16 operand tile
+__device__ __forceinline__ void acc_to_tile_relu(uint32_t trow, int col0, int ncols, const float *bias, uint8_t *tile,
+                                                 int row, int tile_col0) {
+    for (int c = 0; c < ncols; c += 16) {
+        float v[16];
+        tmem_ld16(trow + (uint32_t)(col0 + c), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bias[c + i], 0.f);
+        store8(tile, row, tile_col0 + c, CH_ACT, v);
+        store8(tile, row, tile_col0 + c + 8, CH_ACT, v + 8);
+    }
+}
+
+struct RoundSync {
+    uint64_t *bar;
+    uint32_t parity;
+    // all threads: operand tiles written & accumulators consumed -> one thread may issue MMAs
+    __device__ __forceinline__ void before_issue() {
+        fence_proxy_async();
+        fence_before_sync();
+        __syncthreads();
+    }
+    __device__ __forceinline__ void wait_done() {
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        fence_after_sync();
+    }
+};
+
+template <bool DENSITY_ONLY>
+__global__ void __launch_bounds__(TM)
+field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict__ enc, umhs_mlp_params mp,
+                        umhs_field_out out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int K = mp.num_classes, spec = DENSITY_ONLY ? 0 : mp.specular;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + TcSmem::ctrl);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TcSmem::ctrl + 16);
+    constexpr int NCOLS = 128;
+
+    stage_all_weights(smem, mp, DENSITY_ONLY, tid);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<NCOLS>(tmem_slot);
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tbase = *tmem_slot;
+    const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);  // this warp's lane quarter
+    RoundSync rs{bar, 0u};
+
+    uint8_t *tX = smem + TcSmem::f_x, *tX2 = smem + TcSmem::f_x2, *tH = smem + TcSmem::f_h, *tF = smem + TcSmem::f_f;
+    const uint32_t sX = smem_u32(tX), sX2 = smem_u32(tX2), sH = smem_u32(tH), sF = smem_u32(tF);
+    const uint32_t sWb0 = smem_u32(smem + TcSmem::w_base0), sWb1 = smem_u32(smem + TcSmem::w_base1);
+    const uint32_t sWhf0 = smem_u32(smem + TcSmem::w_hf0), sWh1 = smem_u32(smem + TcSmem::w_h1);
+    const uint32_t sWf1 = smem_u32(smem + TcSmem::w_f1), sWh2 = smem_u32(smem + TcSmem::w_h2);
+    const uint32_t sWf2 = smem_u32(smem + TcSmem::w_f2), sWd0 = smem_u32(smem + TcSmem::w_d0);
+    const float *Bb0 = reinterpret_cast<const float *>(smem + TcSmem::b_base0);
+    const float *Bb1 = reinterpret_cast<const float *>(smem + TcSmem::b_base1);
+    const float *Bh0 = reinterpret_cast<const float *>(smem + TcSmem::b_h0);
+    const float *Bf0 = reinterpret_cast<const float *>(smem + TcSmem::b_f0);
+    const float *Bh1 = reinterpret_cast<const float *>(smem + TcSmem::b_h1);
+    const float *Bf1 = reinterpret_cast<const float *>(smem + TcSmem::b_f1);
+    const float *Bh2 = reinterpret_cast<const float *>(smem + TcSmem::b_h2);
+    const float *Bf2 = reinterpret_cast<const float *>(smem + TcSmem::b_f2);
+    const float *Bd0 = reinterpret_cast<const float *>(smem + TcSmem::b_d0);
+    const float invT = DENSITY_ONLY ? 1.f : 1.0f / mp.temperature;
+
+    const int64_t n_tiles = (n_total + TM - 1) / TM;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t n0 = tile * TM;
+        const bool valid = n0 + tid < n_total;
+        const int64_t n = valid ? n0 + tid : n_total - 1;  // tail threads shadow the last sample, write nothing
+        const Point pt = eval_point(P, n);
+        float pe[12];
+        // ---------------- round 0: enc -> tX ; (specular) [sh, pe] -> tX2 ; MMA base0
+        {
+            const float4 *e4 = reinterpret_cast<const float4 *>(enc + n * 32);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float4 a = __ldg(e4 + 2 * c), b = __ldg(e4 + 2 * c + 1);
+                const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                store8(tX, tid, 8 * c, CH_ACT, v);
+            }
+            if (!DENSITY_ONLY) {
+                pos_encoding_tc(pt, pe);
+                if (spec) {
+                    float x2[32];
+                    float sh[16];
+                    sh_deg3_tc((pt.dx + 1.0f) / 2.0f, (pt.dy + 1.0f) / 2.0f, (pt.dz + 1.0f) / 2.0f, sh);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) x2[i] = sh[i];
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) x2[16 + i] = pe[i];
+#pragma unroll
+                    for (int i = 28; i < 32; ++i) x2[i] = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) store8(tX2, tid, 8 * c, CH_ACT, x2 + 8 * c);
+                }
+            }
+        }
+        rs.before_issue();
+        if (tid == 0) {
+            fence_after_sync();
+            gemm_kmajor(tbase + 0, sX, sWb0, 64, 0, 64, 32, 0);
+            commit(bar);
+        }
+        rs.wait_done();
+        // ---------------- round 1: H0 = relu(. + b) -> tH ; MMA base1 (N=16) [+ dir0 (N=16) at cols 64..79]
+        acc_to_tile_relu(trow, 0, 64, Bb0, tH, tid, 0);
+        rs.before_issue();
+        if (tid == 0) {
+            fence_after_sync();
+            gemm_kmajor(tbase + 0, sH, sWb1, 16, 0, 16, 64, 0);
+            if (spec) gemm_kmajor(tbase + 64, sX2, sWd0, 16, 0, 16, 32, 0);
+            commit(bar);
+        }
+        rs.wait_done();
+        // ---------------- round 2: sigma, emb ; X = [pe, emb] -> tX ; MMA head0|feat0 (N=128)
+        float o16[16];
+        tmem_ld16(trow + 0, o16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o16[i] += Bb1[i];
+        if (valid) {
+            out.sigma[n] = expf(o16[0]) * pt.sel;  // trunc_exp forward == exp; density * selector
+            if (out.embedding) {
+#pragma unroll
+                for (int i = 0; i < 15; ++i) out.embedding[n * 15 + i] = o16[i + 1];
+            }
+        }
+        if (DENSITY_ONLY) {
+            fence_before_sync();  // accumulator reads done before the next tile's MMA overwrites them
+            continue;
+        }
+        if (spec) {
+            float h[16];
+            tmem_ld16(trow + 64, h);
+            if (valid && out.spec_hidden) {
+                float4 *dst = reinterpret_cast<float4 *>(out.spec_hidden + n * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    dst[q] = make_float4(fmaxf(h[4 * q] + Bd0[4 * q], 0.f), fmaxf(h[4 * q + 1] + Bd0[4 * q + 1], 0.f),
+                                         fmaxf(h[4 * q + 2] + Bd0[4 * q + 2], 0.f),
+                                         fmaxf(h[4 * q + 3] + Bd0[4 * q + 3], 0.f));
+            }
+        }
+        {
+            float x[32];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) x[i] = pe[i];
+#pragma unroll
+            for (int i = 0; i < 15; ++i) x[12 + i] = o16[1 + i];
+#pragma unroll
+            for (int i = 27; i < 32; ++i) x[i] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) store8(tX, tid, 8 * c, CH_ACT, x + 8 * c);
+        }
+        rs.before_issue();
+        if (tid == 0) {
+            fence_after_sync();
+            gemm_kmajor(tbase + 0, sX, sWhf0, 128, 0, 128, 32, 0);
+            commit(bar);
+        }
+        rs.wait_done();
+        // ---------------- round 3: hidden 0 of both MLPs -> tH, tF ; MMA head1, feat1
+        acc_to_tile_relu(trow, 0, 64, Bh0, tH, tid, 0);
+        acc_to_tile_relu(trow, 64, 64, Bf0, tF, tid, 0);
+        rs.before_issue();
+        if (tid == 0) {
+            fence_after_sync();
+            gemm_kmajor(tbase + 0, sH, sWh1, 64, 0, 64, 64, 0);
+            gemm_kmajor(tbase + 64, sF, sWf1, 64, 0, 64, 64, 0);
+            commit(bar);
+        }
+        rs.wait_done();
+        // ---------------- round 4: hidden 1 -> tH, tF ; MMA head2 (N=16), feat2 (N=32)
+        acc_to_tile_relu(trow, 0, 64, Bh1, tH, tid, 0);
+        acc_to_tile_relu(trow, 64, 64, Bf1, tF, tid, 0);
+        rs.before_issue();
+        if (tid == 0) {
+            fence_after_sync();
+            gemm_kmajor(tbase + 0, sH, sWh2, 16, 0, 16, 64, 0);
+            gemm_kmajor(tbase + 64, sF, sWf2, 32, 0, 32, 64, 0);
+            commit(bar);
+        }
+        rs.wait_done();
+        // ---------------- round 5: outputs
+        {
+            float zh[16], zf[16], zf2[16];
+            tmem_ld16(trow + 0, zh);
+            tmem_ld16(trow + 64, zf);
+            if (K + spec > 16) tmem_ld16(trow + 80, zf2);
+            if (valid) {
+                float mx = -3.0e38f;
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (k < K) mx = fmaxf(mx, (zf[k] + Bf2[k]) * invT);
+                float den = 0.f, e[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    e[k] = (k < K) ? expf((zf[k] + Bf2[k]) * invT - mx) : 0.f;
+                    den += e[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (k < K) {
+                        out.scalar[n * K + k] = 1.0f / (1.0f + expf(-(zh[k] + Bh2[k])));
+                        out.abund[n * K + k] = e[k] / den;
+                    }
+                }
+                if (spec && out.s1) {
+                    float z = 0.f;
+                    if (K < 16) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k)
+                            if (k == K) z = zf[k];
+                    } else {
+                        z = zf2[0];
+                    }
+                    out.s1[n] = 1.0f / (1.0f + expf(-(z + Bf2[K])));
+                }
+            }
+        }
+        fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<NCOLS>(tbase);
+}
+
+// ------------------------------------------------------------------ descriptor self-test (one CTA)
+// mode 0: D[128xN] = A[128xK] * B[NxK]^T ; mode 1: D[128xN] = A[128xK] * W[KxN] ; mode 2: D[64xN] = P[128x64]^T Q[128xN]
+__global__ void __launch_bounds__(TM)
+tc05_selftest_kernel(int mode, const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ D, int N,
+                     int K) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *tA = smem, *tB = smem + 32768;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 65536);
+    uint32_t *slot = reinterpret_cast<uint32_t *>(smem + 65536 + 16);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<128>(slot);
+    const int acols = (mode == 2) ? 64 : K;
+    for (int c = 0; c < acols; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = A[tid * acols + c + q];
+        store8(tA, tid, c, CH_ACT, v);
+    }
+    if (mode == 0) {  // B [N x K] -> tile with N rows
+        for (int i = tid; i < N * (K / 8); i += TM) {
+            const int j = i / (K / 8), c0 = (i % (K / 8)) * 8;
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = B[j * K + c0 + q];
+            store8(tB, j, c0, N * 16, v);
+        }
+    } else if (mode == 1) {  // W [K(out) x N(in)] -> forward-style tile with K rows, N columns
+        for (int i = tid; i < K * (N / 8); i += TM) {
+            const int j = i / (N / 8), c0 = (i % (N / 8)) * 8;
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = B[j * N + c0 + q];
+            store8(tB, j, c0, K * 16, v);
+        }
+    } else {  // Q [128 x N] activation tile
+        for (int c = 0; c < N; c += 8) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = B[tid * N + c + q];
+            store8(tB, tid, c, CH_ACT, v);
+        }
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tbase = *slot;
+    if (tid == 0) {
+        if (mode == 0) gemm_kmajor(tbase, smem_u32(tA), smem_u32(tB), N, 0, N, K, 0);
+        else if (mode == 1) gemm_dgrad(tbase, smem_u32(tA), smem_u32(tB), K, 0, N, K, 0);
+        else gemm_wgrad(tbase, smem_u32(tA), 0, smem_u32(tB), 0, N, 0);
+        commit(bar);
+    }
+    mbar_wait(bar, 0);
+    fence_after_sync();
+    const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
+    for (int c = 0; c < N; c += 16) {
+        float v[16];
+        tmem_ld16(trow + (uint32_t)c, v);
+        if (mode == 2) {
+            if (lane < 16)
+                for (int i = 0; i < 16; ++i) D[(warp * 16 + lane) * N + c + i] = v[i];
+        } else {
+            for (int i = 0; i < 16; ++i) D[tid * N + c + i] = v[i];
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<128>(tbase);
+}
+
+static int tc_grid(int64_t n, int ctas_per_sm) {
+    const int64_t want = (n + TM - 1) / TM;
+    const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
+    return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+}  // namespace umhs
+
+using namespace umhs;
+
+extern "C" int umhs_tc05_selftest(int32_t mode, const float *A, const float *B, float *D, int32_t N, int32_t K,
+                                  void *stream) {
+    UMHS_CHECK_ARG(A && B && D, "null argument");
+    UMHS_CHECK_ARG(mode >= 0 && mode <= 2 && N >= 16 && N <= 128 && N % 16 == 0 && K >= 16 && K <= 128 && K % 16 == 0,
+                   "bad shape");
+    const int bytes = 65536 + 128;
+    UMHS_CHECK_CUDA(cudaFuncSetAttribute(tc05_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    tc05_selftest_kernel<<<1, TM, bytes, as_stream(stream)>>>(mode, A, B, D, N, K);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_density_tc_fwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
+                                   float *sigma, void *stream) {
+    if (n <= 0) return UMHS_OK;
+    UMHS_CHECK_ARG(pts && enc && sigma && p && p->base_w0 && p->base_b0 && p->base_w1 && p->base_b1, "null argument");
+    umhs_field_out out = {};
+    out.sigma = sigma;
+    const int bytes = TcSmem::f_x2;  // weights + ctrl + tX ... tH is needed too
+    const int need = TcSmem::f_f;    // up to and including tH
+    (void)bytes;
+    UMHS_CHECK_CUDA(cudaFuncSetAttribute(field_mlp_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         need));
+    field_mlp_tc_fwd_kernel<true><<<tc_grid(n, 3), TM, need, as_stream(stream)>>>(*pts, n, enc, *p, out);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_field_mlp_tc_fwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
+                                     const umhs_field_out *out, void *stream) {
+    if (n <= 0) return UMHS_OK;
+    UMHS_CHECK_ARG(pts && enc && out && out->sigma && out->scalar && out->abund && p, "null argument");
+    UMHS_CHECK_ARG(p->num_classes >= 1 && p->num_classes <= UMHS_MAX_CLASSES && p->temperature > 0.f, "bad K / T");
+    UMHS_CHECK_ARG(p->base_w0 && p->head_w0 && p->head_w1 && p->head_w2 && p->feat_w0 && p->feat_w1 && p->feat_w2,
+                   "null weights");
+    UMHS_CHECK_ARG(!p->specular || (p->dir_w0 && p->dir_b0), "specular weights missing");
+    UMHS_CHECK_CUDA(cudaFuncSetAttribute(field_mlp_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TcSmem::f_end));
+    field_mlp_tc_fwd_kernel<false><<<tc_grid(n, 2), TM, TcSmem::f_end, as_stream(stream)>>>(*pts, n, enc, *p, *out);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}

@@ -1,0 +1,191 @@
+// tc05.cuh -- hand-written Blackwell (sm_100a) tensor-core building blocks: tcgen05.mma with
+// shared-memory operands and TMEM accumulators, tcgen05.ld epilogue loads, mbarrier completion.
+//
+// Operand storage ("chunk-slab", the canonical no-swizzle UMMA layout): a [rows x cols] bf16 matrix
+// lives at   byte(row, col) = (col/8)*CH + (row/8)*128 + (row%8)*16 + (col%8)*2,  CH = (rows/8)*128,
+// i.e. 8x8 core matrices of 128 contiguous bytes.  The SAME buffer is
+//   * a K-major operand  (MN = rows, K = cols): SBO = 128 (next 8-row group), LBO = CH (next 8 K);
+//   * an MN-major operand (MN = cols, K = rows): SBO = CH (next 8 MN),        LBO = 128 (next 8 K),
+// so an activation tile [samples x features] feeds forward / dgrad GEMMs (K-major, K = features) and
+// weight-gradient GEMMs (MN-major, K = samples) without any transpose, and an nn.Linear weight
+// [out x in] is the K-major B operand of the forward GEMM and the MN-major B operand of dgrad.
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace tc05 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- shared-memory matrix descriptor (SWIZZLE_NONE, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;  // descriptor version for sm_100
+    return d;
+}
+
+// ---- instruction descriptor: bf16 x bf16 -> f32, dense
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    uint32_t d = 0;
+    d |= 1u << 4;   // c_format = F32
+    d |= 1u << 7;   // a_format = BF16
+    d |= 1u << 10;  // b_format = BF16
+    d |= (uint32_t)(a_mn_major & 1) << 15;
+    d |= (uint32_t)(b_mn_major & 1) << 16;
+    d |= (uint32_t)(N >> 3) << 17;
+    d |= (uint32_t)(M >> 4) << 24;
+    return d;
+}
+
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// all previously issued MMAs of this thread arrive on `bar` when complete
+__device__ __forceinline__ void commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// make generic-proxy smem writes visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// bounded wait: a wrong descriptor must fail loudly (trap), never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t it = 0; it < (1u << 24); ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
+// ---- TMEM allocation (one full warp executes these)
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "n"(NCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+// ---- TMEM -> registers: this warp's 32 lanes x 16 consecutive fp32 columns (lane i <-> TMEM lane 32*(warp%4)+i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- operand tile addressing
+__device__ __forceinline__ uint32_t tile_off(int row, int col, int ch_bytes) {
+    return (uint32_t)((col >> 3) * ch_bytes + (row >> 3) * 128 + (row & 7) * 16 + (col & 7) * 2);
+}
+
+// store 8 consecutive columns [c0, c0+8) of `row` (c0 multiple of 8) as bf16: one 16-byte st.shared
+__device__ __forceinline__ void store8(uint8_t *buf, int row, int c0, int ch_bytes, const float *v) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]);
+    __nv_bfloat162 p3 = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 q;
+    q.x = *reinterpret_cast<uint32_t *>(&p0);
+    q.y = *reinterpret_cast<uint32_t *>(&p1);
+    q.z = *reinterpret_cast<uint32_t *>(&p2);
+    q.w = *reinterpret_cast<uint32_t *>(&p3);
+    *reinterpret_cast<uint4 *>(buf + tile_off(row, c0, ch_bytes)) = q;
+}
+
+__device__ __forceinline__ void load8(const uint8_t *buf, int row, int c0, int ch_bytes, float *v) {
+    const uint4 q = *reinterpret_cast<const uint4 *>(buf + tile_off(row, c0, ch_bytes));
+    const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(p[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+
+// D[128 x N] (+)= A[128 x K] * B[N x K]^T, both operands K-major tiles.
+//   a: tile of 128 rows (CH = 2048); b: tile of `b_rows` rows (CH = b_rows*16), rows [b_row0, b_row0+N) used.
+__device__ __forceinline__ void gemm_kmajor(uint32_t d_tmem, uint32_t a_saddr, uint32_t b_saddr, int b_rows, int b_row0,
+                                            int N, int K, uint32_t accumulate) {
+    const uint32_t idesc = make_idesc(128, N, 0, 0);
+    const uint32_t a_ch = 2048, b_ch = (uint32_t)b_rows * 16;
+    const uint32_t b0 = b_saddr + (uint32_t)(b_row0 >> 3) * 128;
+    for (int k = 0; k < K; k += 16) {
+        const uint64_t ad = make_desc(a_saddr + (uint32_t)(k >> 3) * a_ch, a_ch, 128);
+        const uint64_t bd = make_desc(b0 + (uint32_t)(k >> 3) * b_ch, b_ch, 128);
+        mma_ss(d_tmem, ad, bd, idesc, (k > 0) ? 1u : accumulate);
+    }
+}
+
+// dgrad: D[128 x N] = A[128 x K] * W[K x N], A K-major (delta tile), W stored as nn.Linear [K(out) x N(in)]
+// K-major-for-forward, read here as an MN-major B operand (MN = in, K = out).  Rows (out) [w_row0, w_row0+K).
+__device__ __forceinline__ void gemm_dgrad(uint32_t d_tmem, uint32_t a_saddr, uint32_t w_saddr, int w_rows, int w_row0,
+                                           int N, int K, uint32_t accumulate) {
+    const uint32_t idesc = make_idesc(128, N, 0, 1);
+    const uint32_t a_ch = 2048, w_ch = (uint32_t)w_rows * 16;
+    const uint32_t w0 = w_saddr + (uint32_t)(w_row0 >> 3) * 128;
+    for (int k = 0; k < K; k += 16) {
+        const uint64_t ad = make_desc(a_saddr + (uint32_t)(k >> 3) * a_ch, a_ch, 128);
+        // MN-major: SBO = stride between 8-wide MN chunks (= w_ch), LBO = stride between 8-deep K groups (= 128)
+        const uint64_t bd = make_desc(w0 + (uint32_t)(k >> 3) * 128, 128, w_ch);
+        mma_ss(d_tmem, ad, bd, idesc, (k > 0) ? 1u : accumulate);
+    }
+}
+
+// wgrad: D[64 x N] += P[128 samples x 64]^T * Q[128 samples x N]: both are activation tiles (CH = 2048) read as
+// MN-major operands with K = samples.  P columns [p_col0, p_col0+64), Q columns [q_col0, q_col0+N).
+__device__ __forceinline__ void gemm_wgrad(uint32_t d_tmem, uint32_t p_saddr, int p_col0, uint32_t q_saddr, int q_col0,
+                                           int N, uint32_t accumulate) {
+    const uint32_t idesc = make_idesc(64, N, 1, 1);
+    const uint32_t ch = 2048;
+    const uint32_t p0 = p_saddr + (uint32_t)(p_col0 >> 3) * ch, q0 = q_saddr + (uint32_t)(q_col0 >> 3) * ch;
+    for (int s = 0; s < 128; s += 16) {
+        const uint64_t ad = make_desc(p0 + (uint32_t)(s >> 3) * 128, 128, ch);
+        const uint64_t bd = make_desc(q0 + (uint32_t)(s >> 3) * 128, 128, ch);
+        mma_ss(d_tmem, ad, bd, idesc, (s > 0) ? 1u : accumulate);
+    }
+}
+
+}  // namespace tc05

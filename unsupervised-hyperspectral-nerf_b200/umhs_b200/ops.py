@@ -25,7 +25,12 @@ _LAUNCHES = {"umhs_hash_encode_fwd": 1, "umhs_hash_encode_bwd": 1, "umhs_hash_en
              "umhs_accumulate_fwd": 1, "umhs_accumulate_bwd": 1, "umhs_march_count": 1, "umhs_pack_scan": 1,
              "umhs_march_write": 1, "umhs_visibility_mask": 1, "umhs_compact_samples": 1, "umhs_pack_info": 2,
              "umhs_occ_cell_points": 1, "umhs_occ_ema_update": 2, "umhs_occ_binarize": 2, "umhs_adam_step": 1,
-             "umhs_reduce_slabs": 1}
+             "umhs_reduce_slabs": 1, "umhs_density_tc_fwd": 1, "umhs_field_mlp_tc_fwd": 1, "umhs_field_mlp_tc_bwd": 1,
+             "umhs_tc05_selftest": 1}
+
+# "bf16": tensor-core MLP kernels (tcgen05 + TMEM, bf16 operands, fp32 accumulate) -- the default.
+# "fp32": fp32 SIMT MLP kernels (precise mode for tight parity tests).
+MLP_PRECISION = "bf16"
 
 
 class Profiler:
@@ -213,7 +218,7 @@ def density_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor]) -> Tenso
     lib = _lib.load()
     sigma = torch.empty((pts.n,), dtype=torch.float32, device=enc.device)
     ps, ms = pts.struct(), mlp_struct(weights, 1, False, 1.0)
-    _call("umhs_density_fwd", pts.n, ctypes.byref(ps), pts.n, ptr(enc), ctypes.byref(ms), ptr(sigma),
+    _call("umhs_density_tc_fwd" if MLP_PRECISION == "bf16" else "umhs_density_fwd", pts.n, ctypes.byref(ps), pts.n, ptr(enc), ctypes.byref(ms), ptr(sigma),
                                stream_ptr(enc.device))
     return sigma
 
@@ -232,7 +237,7 @@ def field_mlp_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int
     for k, v in out.items():
         setattr(fo, k, ptr(v))
     ps, ms = pts.struct(), mlp_struct(weights, K, specular, temperature)
-    _call("umhs_field_mlp_fwd", n, ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(fo), stream_ptr(dev))
+    _call("umhs_field_mlp_tc_fwd" if MLP_PRECISION == "bf16" else "umhs_field_mlp_fwd", n, ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(fo), stream_ptr(dev))
     return out
 
 
@@ -568,3 +573,10 @@ def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, 
     _call("umhs_adam_step", param.numel(), ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1, beta2,
                              eps, step, ptr(inv_scale), ptr(found_inf), clamp_range[0], clamp_range[1],
                              1 if zero_grad else 0, stream_ptr(param.device))
+
+
+def tc05_selftest(mode: int, A: Tensor, B: Tensor, N: int, K: int) -> Tensor:
+    """One-CTA tcgen05 GEMM self-test (see include/umhs.h)."""
+    D = torch.zeros((64 if mode == 2 else 128, N), dtype=torch.float32, device=A.device)
+    _call("umhs_tc05_selftest", 0, mode, ptr(f32(A)), ptr(f32(B)), ptr(D), N, K, stream_ptr(A.device))
+    return D
