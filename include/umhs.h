@@ -141,6 +141,8 @@ int umhs_density_tc_fwd(const umhs_points *pts, int64_t n, const float *enc, con
                         void *stream);
 int umhs_field_mlp_tc_fwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
                           const umhs_field_out *out, void *stream);
+int umhs_field_mlp_tc_bwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
+                          const umhs_field_out_grads *g, float *d_enc, const umhs_mlp_grads *dp, void *stream);
 /* One-CTA self-test of the three tcgen05 GEMM forms the MLP kernels are built from (fp32 in/out, bf16 operands):
  * mode 0: D[128xN] = A[128xK] B[NxK]^T; mode 1: D[128xN] = A[128xK] W[KxN]; mode 2: D[64xN] = P[128x64]^T Q[128xN]. */
 int umhs_tc05_selftest(int32_t mode, const float *A, const float *B, float *D, int32_t N, int32_t K, void *stream);

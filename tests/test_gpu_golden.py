@@ -140,6 +140,38 @@ def test_model_eval_k9_specular_golden():
         _model_case("model_eval_k9_spec.npz")
 
 
+@pytest.mark.parametrize("name", ["model_train_k4.npz", "model_train_k4_spec.npz", "model_eval_k9_spec.npz"])
+def test_model_golden_bf16(name):
+    """Default (tensor-core, bf16-operand) path end to end against the reference's fp32 golden vectors.  Stated
+    tolerance: per-ray outputs relative L2 <= 3e-2, losses 3e-2 relative, gradients relative L2 <= 6e-2; the kept
+    sample count may differ by the few samples whose visibility sits on a threshold (alpha_thre / T >= 1e-4)."""
+    from umhs_b200.rays import RayBundle
+
+    d, meta = load_golden(name)
+    training = meta["training"]
+    m = b200_model_from_golden(d, meta, training)
+    with mlp_precision("bf16"):
+        rb = m.collider(RayBundle(t(d["origins"]).to(DEV), t(d["directions"]).to(DEV)))
+        out = m.get_outputs(rb, jitter=t(d["jitter"]).to(DEV))
+        n_ref = int(d["ray_indices"].shape[0])
+        assert abs(int(m._last["t_starts"].shape[0]) - n_ref) <= max(8, n_ref // 200)
+        for k in ("accumulation", "depth", "spectral", "rgb", "abundances", "seg_probs", "spectral2", "specular"):
+            if "out." + k in d:
+                assert rel_l2(out[k], d["out." + k]) < 3e-2, k
+        m._bg_override = t(d["bg"]).to(DEV)
+        loss = m.get_loss_dict(out, {"image": t(d["image"]).to(DEV), "hs_image": t(d["hs_image"]).to(DEV)})
+        for k, v in loss.items():
+            assert abs(float(v) - float(d["loss." + k])) < 3e-2 * abs(float(d["loss." + k])), k
+        if training:
+            sum(loss.values()).backward()
+            n = 0
+            for k, p in m.field.named_parameters():
+                if "grad." + k in d and p.grad is not None:
+                    assert rel_l2(p.grad, d["grad." + k]) < 6e-2, k
+                    n += 1
+            assert n >= 10
+
+
 def test_native_library_is_what_ran():
     """The GPU tests must have exercised libumhs_sm100.so (no silent fallback exists, but make it observable)."""
     from umhs_b200 import _lib

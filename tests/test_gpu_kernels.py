@@ -362,3 +362,48 @@ def test_field_mlp_tc_fwd_matches_fp32(K, specular):
         err = rel_l2(res["bf16"][k], v)
         assert err < 1e-2, (k, err)
     assert torch.equal(res["bf16"]["density_only"], res["bf16"]["sigma"])
+
+
+@pytest.mark.parametrize("K,specular,N", [(4, False, 1000), (9, True, 700), (16, True, 300), (4, False, 128 * 150 + 5)])
+def test_field_mlp_tc_bwd_matches_fp32(K, specular, N):
+    """bf16 tensor-core backward (dgrad + TMEM-resident wgrad) against the fp32 SIMT backward on the same inputs.
+    Stated bf16 tolerance: relative L2 error <= 1e-1 per gradient tensor on these adversarial inputs (N(0,1)
+    encodings and N(0,1) output gradients).  The last layers agree to ~4e-3; each hidden layer further back adds
+    ~4e-2, which is ReLU-mask flips: a unit whose pre-activation is within bf16 rounding of zero takes a different
+    branch in the bf16 and fp32 recomputations, and flipping a fraction f of units costs sqrt(f) in relative L2
+    (f ~ 2e-3 here).  The tensor-core path is self-consistent (its mask is the one its own forward used).  The
+    end-to-end bound on the reference's golden vectors is tighter: tests/test_gpu_golden.py::test_model_golden_bf16."""
+    from helpers import rel_l2
+    ops = _ops()
+    g = torch.Generator().manual_seed(K + N)
+    pos = (torch.rand(N, 3, generator=g) * 2 - 1) * 1.3
+    dirs = torch.nn.functional.normalize(torch.randn(N, 3, generator=g), dim=-1)
+    enc = torch.randn(N, 32, generator=g)
+    mk = lambda o, i: ((torch.rand(o, i, generator=g) * 2 - 1) / i ** 0.5, (torch.rand(o, generator=g) * 2 - 1) * 0.1)  # noqa: E731
+    w = {}
+    for name, (o, i) in {"base_w0": (64, 32), "base_w1": (16, 64), "head_w0": (64, 27), "head_w1": (64, 64),
+                         "head_w2": (K, 64), "feat_w0": (64, 27), "feat_w1": (64, 64),
+                         "feat_w2": (K + int(specular), 64), "dir_w0": (16, 28)}.items():
+        W, b = mk(o, i)
+        w[name], w[name.replace("_w", "_b")] = W.to(DEV).contiguous(), b.to(DEV).contiguous()
+    if not specular:
+        w["dir_w0"] = w["dir_b0"] = None
+    grads = {"d_sigma": torch.randn(N, generator=g).to(DEV), "d_scalar": torch.randn(N, K, generator=g).to(DEV),
+             "d_abund": torch.randn(N, K, generator=g).to(DEV), "d_embedding": None}
+    if specular:
+        grads["d_s1"] = torch.randn(N, generator=g).to(DEV)
+        grads["d_spec_hidden"] = torch.randn(N, 16, generator=g).to(DEV)
+    pts = ops.PointSet.from_positions(pos.to(DEV), dirs.to(DEV))
+    res = {}
+    for mode in ("fp32", "bf16"):
+        ops.MLP_PRECISION = mode
+        try:
+            res[mode] = ops.field_mlp_bwd(pts, enc.to(DEV), w, K, specular, 0.4, grads)
+        finally:
+            ops.MLP_PRECISION = "bf16"
+    errs = {"d_enc": rel_l2(res["bf16"][0], res["fp32"][0])}
+    for k, v in res["fp32"][1].items():
+        errs[k] = rel_l2(res["bf16"][1][k], v)
+    print({k: round(v, 4) for k, v in errs.items()})
+    assert max(errs.values()) < 1e-1, errs
+    assert max(errs[k] for k in ('head_w2', 'feat_w2', 'base_w1')) < 2e-2, errs

@@ -495,3 +495,454 @@ extern "C" int umhs_field_mlp_tc_fwd(const umhs_points *pts, int64_t n, const fl
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }
+
+// =====================================================================================================
+// Backward on the tensor cores.
+//
+// Per tile of 128 samples the activations are recomputed from the hash encoding (bf16 operand tiles kept in
+// shared memory), then for every layer one commit group issues
+//     wgrad   P[64 x N] += Delta^T[64 x 128 samples] * Act[128 samples x N]     (MN-major operands, M = 64)
+//     dgrad   W0[128 x N] = Delta[128 x K] * W[K x N]                            (weights read MN-major)
+// The weight-gradient accumulators P_* live in TMEM for the whole kernel (accumulated over all tiles of the
+// persistent CTA) and are flushed once at the end with one atomic per element per CTA.  Bias gradients of the
+// 64-wide layers are one more N = 8 MMA against a tile of ones; the narrow output layers use warp shuffles.
+// Rounds per tile: base0 | base1(+dir0 wgrad) | head0+feat0 | head1 | head2 | dL2 | dL1 | dL0 | feat1 | feat2 |
+//                  dL2 | dL1 | dL0 | dbase1 | dbase0 | d_enc.
+// =====================================================================================================
+namespace umhs {
+
+struct TcBwd {
+    static constexpr int ones = TcSmem::ctrl + 128;          // [128 x 8] bf16 ones
+    static constexpr int sbias = ones + 2048;                // fp32 accumulators: h2[16] f2[32] b1[16] d0[16]
+    static constexpr int act = (sbias + 80 * 4 + 127) / 128 * 128;
+    static constexpr int tA0 = act;                 // [128 x 32]
+    static constexpr int tX = tA0 + TM * 32 * 2;    // [128 x 32]
+    static constexpr int tH0 = tX + TM * 32 * 2;    // [128 x 64]
+    static constexpr int tX2 = tH0 + TM * 64 * 2;   // [128 x 64]
+    static constexpr int tH1 = tX2 + TM * 64 * 2;
+    static constexpr int tH2 = tH1 + TM * 64 * 2;
+    static constexpr int tD1 = tH2 + TM * 64 * 2;
+    static constexpr int tD2 = tD1 + TM * 64 * 2;
+    static constexpr int end = tD2 + TM * 64 * 2;
+    // TMEM columns
+    static constexpr int W0 = 0, W1 = 64;
+    static constexpr int P_h2t = 128, P_h1 = 144, P_h0 = 208, P_f2t = 240, P_f1 = 272, P_f0 = 336;
+    static constexpr int P_b1t = 368, P_b0 = 384, P_d0t = 416;
+    static constexpr int Pb_h1 = 432, Pb_h0 = 440, Pb_f1 = 448, Pb_f0 = 456, Pb_b0 = 464;
+    static constexpr int ncols = 512;
+};
+
+// accumulator columns [col0, col0+64) of this row, masked by relu'(act tile row) -> bf16 delta tile
+__device__ __forceinline__ void acc_to_delta_masked(uint32_t trow, int col0, const uint8_t *act_tile, uint8_t *delta_tile,
+                                                    int row, bool valid) {
+    for (int c = 0; c < 64; c += 16) {
+        float v[16], h[16];
+        tmem_ld16(trow + (uint32_t)(col0 + c), v);
+        load8(act_tile, row, c, CH_ACT, h);
+        load8(act_tile, row, c + 8, CH_ACT, h + 8);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (valid && h[i] > 0.f) ? v[i] : 0.f;
+        store8(delta_tile, row, c, CH_ACT, v);
+        store8(delta_tile, row, c + 8, CH_ACT, v + 8);
+    }
+}
+
+template <int NMAX>
+__device__ __forceinline__ void warp_colsum_to_smem(const float (&v)[NMAX], int n, float *dst, int lane) {
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) {
+        if (k < n) {  // warp-uniform
+            const float s = warp_sum(v[k]);
+            if (lane == 0 && s != 0.f) atomicAdd(dst + k, s);
+        }
+    }
+}
+
+// flush one persistent [64 x ncols] accumulator: this thread's row r = 16*warp + lane (lane < 16)
+template <class F>
+__device__ __forceinline__ void flush_acc(uint32_t trow, int col0, int ncols, int lane, F &&sink) {
+    for (int c = 0; c < ncols; c += 16) {
+        float v[16];
+        tmem_ld16(trow + (uint32_t)(col0 + c), v);  // .sync.aligned: every lane participates
+        if (lane < 16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (c + i < ncols) sink(c + i, v[i]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TM)
+field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict__ enc, umhs_mlp_params mp,
+                        umhs_field_out_grads g, float *__restrict__ d_enc, umhs_mlp_grads dp) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K = mp.num_classes, spec = mp.specular;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + TcSmem::ctrl);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TcSmem::ctrl + 16);
+
+    stage_all_weights(smem, mp, false, tid);
+    {
+        const float one[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        store8(smem + TcBwd::ones, tid, 0, CH_ACT, one);
+        float *sb = reinterpret_cast<float *>(smem + TcBwd::sbias);
+        if (tid < 80) sb[tid] = 0.f;
+        // zero the padding columns 32..63 of the specular input tile once (columns 0..31 are rewritten per tile)
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 32; c < 64; c += 8) store8(smem + TcBwd::tX2, tid, c, CH_ACT, z);
+    }
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<TcBwd::ncols>(tmem_slot);
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tbase = *tmem_slot;
+    const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
+    RoundSync rs{bar, 0u};
+
+    uint8_t *tA0 = smem + TcBwd::tA0, *tX = smem + TcBwd::tX, *tH0 = smem + TcBwd::tH0, *tX2 = smem + TcBwd::tX2;
+    uint8_t *tH1 = smem + TcBwd::tH1, *tH2 = smem + TcBwd::tH2, *tD1 = smem + TcBwd::tD1, *tD2 = smem + TcBwd::tD2;
+    const uint32_t sA0 = smem_u32(tA0), sX = smem_u32(tX), sH0 = smem_u32(tH0), sX2 = smem_u32(tX2);
+    const uint32_t sH1 = smem_u32(tH1), sH2 = smem_u32(tH2), sD1 = smem_u32(tD1), sD2 = smem_u32(tD2);
+    const uint32_t sOnes = smem_u32(smem + TcBwd::ones);
+    const uint32_t sWb0 = smem_u32(smem + TcSmem::w_base0), sWb1 = smem_u32(smem + TcSmem::w_base1);
+    const uint32_t sWhf0 = smem_u32(smem + TcSmem::w_hf0), sWh1 = smem_u32(smem + TcSmem::w_h1);
+    const uint32_t sWf1 = smem_u32(smem + TcSmem::w_f1), sWh2 = smem_u32(smem + TcSmem::w_h2);
+    const uint32_t sWf2 = smem_u32(smem + TcSmem::w_f2), sWd0 = smem_u32(smem + TcSmem::w_d0);
+    const float *Bb0 = reinterpret_cast<const float *>(smem + TcSmem::b_base0);
+    const float *Bb1 = reinterpret_cast<const float *>(smem + TcSmem::b_base1);
+    const float *Bh0 = reinterpret_cast<const float *>(smem + TcSmem::b_h0);
+    const float *Bf0 = reinterpret_cast<const float *>(smem + TcSmem::b_f0);
+    const float *Bh1 = reinterpret_cast<const float *>(smem + TcSmem::b_h1);
+    const float *Bf1 = reinterpret_cast<const float *>(smem + TcSmem::b_f1);
+    const float *Bh2 = reinterpret_cast<const float *>(smem + TcSmem::b_h2);
+    const float *Bf2 = reinterpret_cast<const float *>(smem + TcSmem::b_f2);
+    const float *Bd0 = reinterpret_cast<const float *>(smem + TcSmem::b_d0);
+    float *sb_h2 = reinterpret_cast<float *>(smem + TcBwd::sbias), *sb_f2 = sb_h2 + 16, *sb_b1 = sb_f2 + 32,
+          *sb_d0 = sb_b1 + 16;
+    const float invT = 1.0f / mp.temperature;
+
+    const int64_t n_tiles = (n_total + TM - 1) / TM;
+    uint32_t acc = 0;  // 0 on this CTA's first tile: the persistent accumulators are initialised, not accumulated
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, acc = 1) {
+        const int64_t n0 = tile * TM;
+        const bool valid = n0 + tid < n_total;
+        const int64_t n = valid ? n0 + tid : n_total - 1;
+        const Point pt = eval_point(P, n);
+        float pe[12];
+        pos_encoding_tc(pt, pe);
+        // ---------------- T0: enc -> tA0 ; (specular) [sh, pe] -> tX2 ; base0 [, dir0]
+        {
+            const float4 *e4 = reinterpret_cast<const float4 *>(enc + n * 32);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float4 a = __ldg(e4 + 2 * c), b = __ldg(e4 + 2 * c + 1);
+                const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                store8(tA0, tid, 8 * c, CH_ACT, v);
+            }
+            if (spec) {
+                float x2[32], sh[16];
+                sh_deg3_tc((pt.dx + 1.0f) / 2.0f, (pt.dy + 1.0f) / 2.0f, (pt.dz + 1.0f) / 2.0f, sh);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x2[i] = sh[i];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) x2[16 + i] = pe[i];
+#pragma unroll
+                for (int i = 28; i < 32; ++i) x2[i] = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) store8(tX2, tid, 8 * c, CH_ACT, x2 + 8 * c);
+            }
+        }
+        rs.before_issue();
+        if (tid == 0) {
+            fence_after_sync();
+            gemm_kmajor(tbase + TcBwd::W0, sA0, sWb0, 64, 0, 64, 32, 0);
+            if (spec) gemm_kmajor(tbase + TcBwd::W1, sX2, sWd0, 16, 0, 16, 32, 0);
+            commit(bar);
+        }
+        rs.wait_done();
+        // ---------------- T1: H0 -> tH0 ; (specular) d spec_hidden -> tD2[:, :16] ; base1 [, dir0 wgrad]
+        acc_to_tile_relu(trow, TcBwd::W0, 64, Bb0, tH0, tid, 0);
+        if (spec) {
+            float h[16], dsh[16];
+            tmem_ld16(trow + TcBwd::W1, h);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid && g.d_spec_hidden) gq = __ldg(reinterpret_cast<const float4 *>(g.d_spec_hidden + n * 16) + q);
+                dsh[4 * q] = (h[4 * q] + Bd0[4 * q] > 0.f) ? gq.x : 0.f;
+                dsh[4 * q + 1] = (h[4 * q + 1] + Bd0[4 * q + 1] > 0.f) ? gq.y : 0.f;
+                dsh[4 * q + 2] = (h[4 * q + 2] + Bd0[4 * q + 2] > 0.f) ? gq.z : 0.f;
+                dsh[4 * q + 3] = (h[4 * q + 3] + Bd0[4 * q + 3] > 0.f) ? gq.w : 0.f;
+            }
+            store8(tD2, tid, 0, CH_ACT, dsh);
+            store8(tD2, tid, 8, CH_ACT, dsh + 8);
+            warp_colsum_to_smem(dsh, 16, sb_d0, lane);
+        }
+        rs.before_issue();
+        if (tid == 0) {
+            fence_after_sync();
+            gemm_kmajor(tbase + TcBwd::W0, sH0, sWb1, 16, 0, 16, 64, 0);
+            if (spec) gemm_wgrad(tbase + TcBwd::P_d0t, sX2, 0, sD2, 0, 16, acc);
+            commit(bar);
+        }
+        rs.wait_done();
+        // ---------------- T2: o16 ; X = [pe, emb] -> tX ; head0 -> W0, feat0 -> W1
+        float o16[16], demb[15];
+        tmem_ld16(trow + TcBwd::W0, o16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o16[i] += Bb1[i];
+#pragma unroll
+        for (int i = 0; i < 15; ++i) demb[i] = (valid && g.d_embedding) ? __ldg(g.d_embedding + n * 15 + i) : 0.f;
+        {
+            float x[32];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) x[i] = pe[i];
+#pragma unroll
+            for (int i = 0; i < 15; ++i) x[12 + i] = o16[1 + i];
+#pragma unroll
+            for (int i = 27; i < 32; ++i) x[i] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) store8(tX, tid, 8 * c, CH_ACT, x + 8 * c);
+        }
+        rs.before_issue();
+        if (tid == 0) {
+            fence_after_sync();
+            gemm_kmajor(tbase + TcBwd::W0, sX, sWhf0, 128, 0, 64, 32, 0);
+            gemm_kmajor(tbase + TcBwd::W1, sX, sWhf0, 128, 64, 64, 32, 0);
+            commit(bar);
+        }
+        rs.wait_done();
+
+        // ================= the two 27->64->64->nout MLPs: m = 0 mlp_head (sigmoid), m = 1 feature_mlp (softmax, s1)
+#pragma unroll 1
+        for (int m = 0; m < 2; ++m) {
+            const float *B0 = m ? Bf0 : Bh0, *B1 = m ? Bf1 : Bh1, *B2 = m ? Bf2 : Bh2;
+            const uint32_t sW1 = m ? sWf1 : sWh1, sW2 = m ? sWf2 : sWh2;
+            const int w2_rows = m ? 32 : 16;   // rows of the last-layer weight tile == padded nout
+            const int nout = m ? K + spec : K;
+            // ---- hidden 0 -> tH1 (head: from W0; feat: from W1, computed in T2) ; [feat: also collect head's dX]
+            if (m == 1) {
+                float dx[16];
+                tmem_ld16(trow + TcBwd::W0, dx);       // columns 0..15 of d X (head)
+#pragma unroll
+                for (int i = 12; i < 16; ++i) demb[i - 12] += dx[i];
+                tmem_ld16(trow + TcBwd::W0 + 16, dx);  // columns 16..31
+#pragma unroll
+                for (int i = 0; i < 11; ++i) demb[4 + i] += dx[i];
+            }
+            acc_to_tile_relu(trow, m ? TcBwd::W1 : TcBwd::W0, 64, B0, tH1, tid, 0);
+            rs.before_issue();
+            if (tid == 0) {
+                fence_after_sync();
+                gemm_kmajor(tbase + TcBwd::W0, sH1, sW1, 64, 0, 64, 64, 0);
+                commit(bar);
+            }
+            rs.wait_done();
+            // ---- hidden 1 -> tH2 ; last layer
+            acc_to_tile_relu(trow, TcBwd::W0, 64, B1, tH2, tid, 0);
+            rs.before_issue();
+            if (tid == 0) {
+                fence_after_sync();
+                gemm_kmajor(tbase + TcBwd::W0, sH2, sW2, w2_rows, 0, w2_rows, 64, 0);
+                commit(bar);
+            }
+            rs.wait_done();
+            // ---- dz -> tD2[:, :w2_rows] ; wgrad L2 (transposed: rows = in-features) + dgrad L2
+            {
+                float z[32], dz[32];
+                {
+                    float t16[16];
+                    tmem_ld16(trow + TcBwd::W0, t16);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) z[k] = t16[k];
+                    if (m == 1) tmem_ld16(trow + TcBwd::W0 + 16, t16);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) z[16 + k] = (m == 1) ? t16[k] : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < 32; ++k) dz[k] = 0.f;
+                if (valid) {
+                    if (m == 0) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            if (k < K) {
+                                const float s = 1.0f / (1.0f + expf(-(z[k] + B2[k])));
+                                dz[k] = __ldg(g.d_scalar + n * K + k) * s * (1.0f - s);
+                            }
+                        }
+                    } else {
+                        float mx = -3.0e38f, e[16], den = 0.f, dot = 0.f, da[16];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k)
+                            if (k < K) mx = fmaxf(mx, (z[k] + B2[k]) * invT);
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            e[k] = (k < K) ? expf((z[k] + B2[k]) * invT - mx) : 0.f;
+                            da[k] = (k < K) ? __ldg(g.d_abund + n * K + k) : 0.f;
+                            den += e[k];
+                        }
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) dot += (e[k] / den) * da[k];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) dz[k] = (e[k] / den) * invT * (da[k] - dot);
+                        if (spec) {
+                            float zs = 0.f;
+#pragma unroll
+                            for (int k = 0; k < 17; ++k)
+                                if (k == K) zs = z[k];
+                            const float s = 1.0f / (1.0f + expf(-(zs + B2[K])));
+                            const float ds = (g.d_s1 ? __ldg(g.d_s1 + n) : 0.f) * s * (1.0f - s);
+#pragma unroll
+                            for (int k = 0; k < 17; ++k)
+                                if (k == K) dz[k] = ds;
+                        }
+                    }
+                }
+                store8(tD2, tid, 0, CH_ACT, dz);
+                store8(tD2, tid, 8, CH_ACT, dz + 8);
+                if (m == 1) {
+                    store8(tD2, tid, 16, CH_ACT, dz + 16);
+                    store8(tD2, tid, 24, CH_ACT, dz + 24);
+                }
+                warp_colsum_to_smem(dz, nout, m ? sb_f2 : sb_h2, lane);
+            }
+            rs.before_issue();
+            if (tid == 0) {
+                fence_after_sync();
+                gemm_wgrad(tbase + (m ? TcBwd::P_f2t : TcBwd::P_h2t), sH2, 0, sD2, 0, w2_rows, acc);
+                gemm_dgrad(tbase + TcBwd::W0, sD2, sW2, w2_rows, 0, 64, w2_rows, 0);
+                commit(bar);
+            }
+            rs.wait_done();
+            // ---- d hidden1 -> tD1 ; wgrad L1 (+bias) + dgrad L1
+            acc_to_delta_masked(trow, TcBwd::W0, tH2, tD1, tid, valid);
+            rs.before_issue();
+            if (tid == 0) {
+                fence_after_sync();
+                gemm_wgrad(tbase + (m ? TcBwd::P_f1 : TcBwd::P_h1), sD1, 0, sH1, 0, 64, acc);
+                gemm_wgrad(tbase + (m ? TcBwd::Pb_f1 : TcBwd::Pb_h1), sD1, 0, sOnes, 0, 8, acc);
+                gemm_dgrad(tbase + TcBwd::W0, sD1, sW1, 64, 0, 64, 64, 0);
+                commit(bar);
+            }
+            rs.wait_done();
+            // ---- d hidden0 -> tD2 ; wgrad L0 (+bias) + dgrad L0 (N = 32: d [pe, emb])
+            acc_to_delta_masked(trow, TcBwd::W0, tH1, tD2, tid, valid);
+            rs.before_issue();
+            if (tid == 0) {
+                fence_after_sync();
+                gemm_wgrad(tbase + (m ? TcBwd::P_f0 : TcBwd::P_h0), sD2, 0, sX, 0, 32, acc);
+                gemm_wgrad(tbase + (m ? TcBwd::Pb_f0 : TcBwd::Pb_h0), sD2, 0, sOnes, 0, 8, acc);
+                gemm_dgrad(tbase + TcBwd::W0, sD2, sWhf0, 128, m ? 64 : 0, 32, 64, 0);
+                commit(bar);
+            }
+            rs.wait_done();
+        }
+        // ================= base MLP backward
+        {
+            float dx[16], dO[16];
+            tmem_ld16(trow + TcBwd::W0, dx);  // d X (feature_mlp), columns 0..15
+#pragma unroll
+            for (int i = 12; i < 16; ++i) demb[i - 12] += dx[i];
+            tmem_ld16(trow + TcBwd::W0 + 16, dx);
+#pragma unroll
+            for (int i = 0; i < 11; ++i) demb[4 + i] += dx[i];
+            // density = trunc_exp(o0) * sel  ->  d o0 = d_sigma * sel * exp(clamp(o0, -15, 15))
+            const float dsg = (valid && g.d_sigma) ? __ldg(g.d_sigma + n) : 0.f;
+            dO[0] = dsg * pt.sel * expf(fminf(fmaxf(o16[0], -15.0f), 15.0f));
+#pragma unroll
+            for (int i = 0; i < 15; ++i) dO[1 + i] = valid ? demb[i] : 0.f;
+            store8(tD2, tid, 0, CH_ACT, dO);
+            store8(tD2, tid, 8, CH_ACT, dO + 8);
+            warp_colsum_to_smem(dO, 16, sb_b1, lane);
+        }
+        rs.before_issue();
+        if (tid == 0) {
+            fence_after_sync();
+            gemm_wgrad(tbase + TcBwd::P_b1t, sH0, 0, sD2, 0, 16, acc);
+            gemm_dgrad(tbase + TcBwd::W0, sD2, sWb1, 16, 0, 64, 16, 0);
+            commit(bar);
+        }
+        rs.wait_done();
+        acc_to_delta_masked(trow, TcBwd::W0, tH0, tD1, tid, valid);
+        rs.before_issue();
+        if (tid == 0) {
+            fence_after_sync();
+            gemm_wgrad(tbase + TcBwd::P_b0, sD1, 0, sA0, 0, 32, acc);
+            gemm_wgrad(tbase + TcBwd::Pb_b0, sD1, 0, sOnes, 0, 8, acc);
+            if (d_enc) gemm_dgrad(tbase + TcBwd::W0, sD1, sWb0, 64, 0, 32, 64, 0);
+            commit(bar);
+        }
+        rs.wait_done();
+        if (d_enc) {
+            float v[16];
+            float4 *dst = reinterpret_cast<float4 *>(d_enc + n * 32);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                tmem_ld16(trow + TcBwd::W0 + 16 * c, v);
+                if (valid) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dst[4 * c + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+            }
+        }
+        fence_before_sync();
+    }
+
+    // ================= flush the persistent weight-gradient accumulators (row r = 16*warp + lane, lane < 16)
+    __syncthreads();
+    fence_after_sync();
+    const int r = warp * 16 + lane;
+    flush_acc(trow, TcBwd::P_h2t, K, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.head_w2 + c * 64 + r, v); });
+    flush_acc(trow, TcBwd::P_h1, 64, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.head_w1 + r * 64 + c, v); });
+    flush_acc(trow, TcBwd::P_h0, 27, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.head_w0 + r * 27 + c, v); });
+    flush_acc(trow, TcBwd::P_f2t, K + spec, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.feat_w2 + c * 64 + r, v); });
+    flush_acc(trow, TcBwd::P_f1, 64, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.feat_w1 + r * 64 + c, v); });
+    flush_acc(trow, TcBwd::P_f0, 27, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.feat_w0 + r * 27 + c, v); });
+    flush_acc(trow, TcBwd::P_b1t, 16, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.base_w1 + c * 64 + r, v); });
+    flush_acc(trow, TcBwd::P_b0, 32, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.base_w0 + r * 32 + c, v); });
+    if (spec)
+        flush_acc(trow, TcBwd::P_d0t, 16, lane, [&](int c, float v) { if (r < 28 && v != 0.f) atomicAdd(dp.dir_w0 + c * 28 + r, v); });
+    flush_acc(trow, TcBwd::Pb_h1, 1, lane, [&](int, float v) { if (v != 0.f) atomicAdd(dp.head_b1 + r, v); });
+    flush_acc(trow, TcBwd::Pb_h0, 1, lane, [&](int, float v) { if (v != 0.f) atomicAdd(dp.head_b0 + r, v); });
+    flush_acc(trow, TcBwd::Pb_f1, 1, lane, [&](int, float v) { if (v != 0.f) atomicAdd(dp.feat_b1 + r, v); });
+    flush_acc(trow, TcBwd::Pb_f0, 1, lane, [&](int, float v) { if (v != 0.f) atomicAdd(dp.feat_b0 + r, v); });
+    flush_acc(trow, TcBwd::Pb_b0, 1, lane, [&](int, float v) { if (v != 0.f) atomicAdd(dp.base_b0 + r, v); });
+    if (tid < K && sb_h2[tid] != 0.f) atomicAdd(dp.head_b2 + tid, sb_h2[tid]);
+    if (tid < K + spec && sb_f2[tid] != 0.f) atomicAdd(dp.feat_b2 + tid, sb_f2[tid]);
+    if (tid < 16 && sb_b1[tid] != 0.f) atomicAdd(dp.base_b1 + tid, sb_b1[tid]);
+    if (spec && tid < 16 && sb_d0[tid] != 0.f) atomicAdd(dp.dir_b0 + tid, sb_d0[tid]);
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<TcBwd::ncols>(tbase);
+}
+
+}  // namespace umhs
+
+extern "C" int umhs_field_mlp_tc_bwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
+                                     const umhs_field_out_grads *g, float *d_enc, const umhs_mlp_grads *dp,
+                                     void *stream) {
+    if (n <= 0) return UMHS_OK;
+    UMHS_CHECK_ARG(pts && enc && g && dp && p, "null argument");
+    UMHS_CHECK_ARG(p->num_classes >= 1 && p->num_classes <= UMHS_MAX_CLASSES && p->temperature > 0.f, "bad K / T");
+    UMHS_CHECK_ARG(g->d_scalar && g->d_abund, "d_scalar/d_abund are required");
+    UMHS_CHECK_ARG(dp->base_w0 && dp->base_b0 && dp->base_w1 && dp->base_b1 && dp->head_w0 && dp->head_b0 &&
+                       dp->head_w1 && dp->head_b1 && dp->head_w2 && dp->head_b2 && dp->feat_w0 && dp->feat_b0 &&
+                       dp->feat_w1 && dp->feat_b1 && dp->feat_w2 && dp->feat_b2,
+                   "null parameter-gradient pointer");
+    UMHS_CHECK_ARG(!p->specular || (p->dir_w0 && p->dir_b0 && dp->dir_w0 && dp->dir_b0), "specular pointers missing");
+    UMHS_CHECK_CUDA(cudaFuncSetAttribute(umhs::field_mlp_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         umhs::TcBwd::end));
+    // one persistent CTA per SM (TMEM: 512 columns hold the weight-gradient accumulators); never more CTAs than tiles
+    const int64_t n_tiles = (n + umhs::TM - 1) / umhs::TM;
+    const int grid = (int)(n_tiles < umhs::kNumSMs ? n_tiles : umhs::kNumSMs);
+    umhs::field_mlp_tc_bwd_kernel<<<grid, umhs::TM, umhs::TcBwd::end, umhs::as_stream(stream)>>>(*pts, n, enc, *p, *g,
+                                                                                                d_enc, *dp);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}

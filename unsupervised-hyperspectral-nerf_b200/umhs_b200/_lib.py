@@ -94,6 +94,8 @@ _SIGNATURES = {
                            POINTER(MlpGrads), P],
     "umhs_density_tc_fwd": [POINTER(Points), c_int64, P, POINTER(MlpParams), P, P],
     "umhs_field_mlp_tc_fwd": [POINTER(Points), c_int64, P, POINTER(MlpParams), POINTER(FieldOut), P],
+    "umhs_field_mlp_tc_bwd": [POINTER(Points), c_int64, P, POINTER(MlpParams), POINTER(FieldOutGrads), P,
+                              POINTER(MlpGrads), P],
     "umhs_tc05_selftest": [c_int32, P, P, P, c_int32, c_int32, P],
     "umhs_composite_fwd": [POINTER(CompositeIn), POINTER(CompositeOut), P],
     "umhs_depth_clip": [P, c_int64, P, P],
