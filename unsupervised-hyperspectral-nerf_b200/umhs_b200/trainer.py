@@ -28,6 +28,26 @@ from .rays import RayBundle
 from .umhs_model import UMHSModel
 
 
+def tile_pixel_indices(H: int, W: int, tile: int, rank: int, world_size: int, device=None) -> Tensor:
+    """Flat pixel ids (row-major) of the tile x tile image tiles dealt round-robin to ``rank``.  The union over ranks
+    covers every pixel exactly once: evaluation needs no collective."""
+    ty, tx = (H + tile - 1) // tile, (W + tile - 1) // tile
+    ids = []
+    for t in range(rank, ty * tx, world_size):
+        y0, x0 = (t // tx) * tile, (t % tx) * tile
+        ys = torch.arange(y0, min(y0 + tile, H), device=device)
+        xs = torch.arange(x0, min(x0 + tile, W), device=device)
+        ids.append((ys[:, None] * W + xs[None, :]).reshape(-1))
+    return torch.cat(ids) if ids else torch.zeros((0,), dtype=torch.int64, device=device)
+
+
+def average_gradients(flat_grad: Tensor, world_size: int) -> None:
+    """The one exchange step of data-parallel training: all-reduce(sum) of the flat gradient.  The 1/world_size
+    factor (DDP semantics: each rank's loss is a mean over its own ray shard) is applied inside the fused Adam."""
+    if world_size > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+
+
 class FlatParams:
     """Re-home a list of parameters into one contiguous fp32 buffer (16-byte aligned segments)."""
 
@@ -89,8 +109,7 @@ class UMHSTrainer:
         loss_dict = m.get_loss_dict(outputs, batch)
         loss = sum(loss_dict.values())
         loss.backward()  # kernels accumulate straight into the flat gradient buffer's views
-        if self.world_size > 1:
-            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM)
+        average_gradients(self.flat.grad, self.world_size)
         self.opt_steps += 1
         ops.adam_step(self.flat.data, self.flat.grad, self.flat.exp_avg, self.flat.exp_avg_sq, self.lr_at(self.step),
                       self.betas[0], self.betas[1], self.eps, self.opt_steps,
@@ -108,15 +127,8 @@ class UMHSTrainer:
         m = self.model
         m.eval()
         H, W = camera_ray_bundle.origins.shape[:2]
-        ty, tx = (H + tile - 1) // tile, (W + tile - 1) // tile
         dev = m.device
-        ids = []
-        for t in range(self.rank, ty * tx, self.world_size):
-            y0, x0 = (t // tx) * tile, (t % tx) * tile
-            ys = torch.arange(y0, min(y0 + tile, H), device=dev)
-            xs = torch.arange(x0, min(x0 + tile, W), device=dev)
-            ids.append((ys[:, None] * W + xs[None, :]).reshape(-1))
-        index = torch.cat(ids) if ids else torch.zeros((0,), dtype=torch.int64, device=dev)
+        index = tile_pixel_indices(H, W, tile, self.rank, self.world_size, dev)
         o = camera_ray_bundle.origins.reshape(-1, 3).to(dev)[index]
         d = camera_ray_bundle.directions.reshape(-1, 3).to(dev)[index]
         out: Dict[str, List[Tensor]] = {}
