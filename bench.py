@@ -203,6 +203,7 @@ def workload_config(n_gpus, cpu=False, samples_per_ray=None):
          "bands": BANDS, "endmembers": K_CLASSES, "temperature": TEMPERATURE, "hash": "16x2@2^19",
          "occupancy": f"128^3x4 shell r={SHELL_R} t={SHELL_T}", "method": "rgb+spectral", "specular": False,
          "parallelism": f"dp{n_gpus} ray-sharded, 1 all-reduce/step" if n_gpus > 1 else "single",
+         "launch": "whole step replayed as one CUDA graph (fwd+loss+bwd+Adam); occupancy update eager every 16 steps",
          "l2_policy": "working set > L2: Adam state 4 x 64 MiB streamed every step + rotating batches"}
     if samples_per_ray is not None:
         c["kept_samples_per_ray"] = samples_per_ray
@@ -238,7 +239,8 @@ def run_b200(args):
     # steady-state occupancy update cadence (step >= warm-up 256), binaries frozen so the synthetic scene stays fixed;
     # late-training learning rate (step 29000 of the 30000-step exponential decay, lr ~ 1.3e-5) keeps the synthetic
     # workload stationary across timed steps: same Adam arithmetic, the density field barely moves
-    trainer = UMHSTrainer(model, world_size=world, rank=rank, occ_update=True, freeze_binaries=True, start_step=29008)
+    trainer = UMHSTrainer(model, world_size=world, rank=rank, occ_update=True, freeze_binaries=True, start_step=29008,
+                          cuda_graph=not args.no_graph)
 
     R, POOL = RAYS_PER_GPU, 8
     host = [make_rays(R, 7919 * rank + i) for i in range(POOL)]
@@ -250,7 +252,7 @@ def run_b200(args):
         return trainer.train_step(RayBundle(o, d), {"image": image, "hs_image": hs})
 
     def step_e2e(i):
-        o, d, image, hs = (t.to(dev, non_blocking=True) for t in pinned[i % POOL])
+        o, d, image, hs = pinned[i % POOL]  # pinned host memory; train_step copies them to the device (async H2D)
         out = trainer.train_step(RayBundle(o, d), {"image": image, "hs_image": hs})
         return float(out["loss"].item())  # device -> host read of the step's result
 
@@ -277,14 +279,13 @@ def run_b200(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ops.Profiler.reset(enabled=True, timing=False)
     ms = timed(step_resident, args.steps)
-    launches = ops.Profiler.launches
-    ops.Profiler.reset(enabled=False)
     ms_e2e = timed(step_e2e, args.steps)
     clk = clocks.stop() if rank == 0 else None
 
-    # second pass of the same K steps with per-entry-point CUDA events (roofline shares)
+    # second pass of the same K steps with per-entry-point CUDA events (roofline shares); eager launches so that
+    # every entry point can be bracketed (the timed passes above replay the whole step as one CUDA graph)
+    trainer.cuda_graph = False
     ops.Profiler.reset(enabled=True, timing=True)
     n_samples = 0
     barrier()
@@ -292,6 +293,8 @@ def run_b200(args):
         n_samples += int(step_resident(i)["num_samples"].item())
     torch.cuda.synchronize()
     summ = ops.Profiler.summary()
+    # kernels of this repo launched per timed pass of K steps (the graph replays the same launches)
+    launches = ops.Profiler.launches
     ops.Profiler.reset(enabled=False)
     spr = n_samples / (args.steps * R)
 
@@ -339,6 +342,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the whole-step CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

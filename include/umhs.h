@@ -60,6 +60,10 @@ typedef struct {
     const float *t_ends;        /* [n]   */
     int32_t contraction;        /* 1: SceneContraction(inf) then (x+2)/4; 0: aabb-normalise */
     float aabb[6];              /* min xyz, max xyz (used when contraction == 0) */
+    const int32_t *enc_index;   /* optional [n]: row of point i in the `enc` array handed to the MLP entry points
+                                   (lets the kept samples reuse the encodings of the sampler's candidate pass) */
+    const int64_t *n_dev;       /* optional DEVICE count: kernels process min(n, *n_dev) points, so a step can run
+                                   on capacity-sized buffers without a host sync on the sample count */
 } umhs_points;
 
 /* ---------------------------------------------------------------------------------
@@ -143,6 +147,9 @@ int umhs_field_mlp_tc_fwd(const umhs_points *pts, int64_t n, const float *enc, c
                           const umhs_field_out *out, void *stream);
 int umhs_field_mlp_tc_bwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
                           const umhs_field_out_grads *g, float *d_enc, const umhs_mlp_grads *dp, void *stream);
+/* Developer aid: install (or with NULL remove) a device buffer of 4*capacity_slots int64 in which CTA 0 of the
+ * tensor-core MLP kernels records (tag, clock64) pairs at the stages of every MMA round (threads 0 and 96). */
+int umhs_debug_trace(int64_t *buffer, int32_t capacity_slots, void *stream);
 /* One-CTA self-test of the three tcgen05 GEMM forms the MLP kernels are built from (fp32 in/out, bf16 operands):
  * mode 0: D[128xN] = A[128xK] B[NxK]^T; mode 1: D[128xN] = A[128xK] W[KxN]; mode 2: D[64xN] = P[128x64]^T Q[128xN]. */
 int umhs_tc05_selftest(int32_t mode, const float *A, const float *B, float *D, int32_t N, int32_t K, void *stream);
@@ -248,12 +255,20 @@ typedef struct {
     int32_t levels, resolution;
     float step_size, cone_angle;
     int64_t n_rays;
+    const int32_t *level_any;        /* [8] device flags from umhs_march_level_any, or NULL (always fetch occupancy) */
 } umhs_march_args;
 
+/* level_any[l] = 1 iff grid level l holds an occupied cell (lets the march skip occupancy fetches there) */
+int umhs_march_level_any(const umhs_march_args *a, int32_t *level_any /*[8]*/, void *stream);
+
 int umhs_march_count(const umhs_march_args *a, int64_t *counts, void *stream);
-/* packed_info[r] = (exclusive_scan(counts)[r], counts[r]); *total (device int64) = sum. `counts` may alias
- * &packed_info[...]: no.  counts [R] int64 in, packed_info [R,2] int64 out. */
-int umhs_pack_scan(const int64_t *counts, int64_t n_rays, int64_t *packed_info, int64_t *total, void *stream);
+/* packed_info[r] = (exclusive_scan(counts)[r], counts[r]); counts [R] int64 in, packed_info [R,2] int64 out.
+ * total (device int64[2], may be NULL): total[0] = number of packed samples, total[1] = the unclamped sum.
+ * capacity > 0 clamps the packing to `capacity` samples (trailing rays are truncated; total[1] > capacity tells the
+ * host, after the fact, that the buffers were too small); capacity <= 0: unlimited. */
+int umhs_pack_scan(const int64_t *counts, int64_t n_rays, int64_t *packed_info, int64_t *total, int64_t capacity,
+                   void *stream);
+/* writes exactly packed_info[r].count samples of ray r at packed_info[r].start */
 int umhs_march_write(const umhs_march_args *a, const int64_t *packed_info, int64_t *ray_indices, float *t_starts,
                      float *t_ends, void *stream);
 /* visibility: keep = (T >= early_stop_eps) & (alpha >= thre), thre = min(alpha_thre, *occ_mean) when the
@@ -261,9 +276,10 @@ int umhs_march_write(const umhs_march_args *a, const int64_t *packed_info, int64
 int umhs_visibility_mask(const int64_t *packed_info, int64_t n_rays, const float *t_starts, const float *t_ends,
                          const float *sigma, float early_stop_eps, float alpha_thre, const float *occ_mean,
                          uint8_t *keep, int64_t *keep_counts, void *stream);
+/* src_index (optional, int32 [n_out]): index of each kept sample in the input arrays */
 int umhs_compact_samples(const int64_t *packed_info_in, const int64_t *packed_info_out, int64_t n_rays,
                          const uint8_t *keep, const float *t_starts_in, const float *t_ends_in, int64_t *ray_indices,
-                         float *t_starts, float *t_ends, void *stream);
+                         float *t_starts, float *t_ends, int32_t *src_index, void *stream);
 /* nerfacc.pack_info for arbitrary (sorted or not) ray_indices; counts is scratch [R] */
 int umhs_pack_info(const int64_t *ray_indices, int64_t n, int64_t n_rays, int64_t *counts, int64_t *packed_info,
                    void *stream);
@@ -286,6 +302,11 @@ int umhs_occ_binarize(const float *occs, int64_t n_cells, float occ_thre, double
 int umhs_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
                    float beta2, float eps, int32_t step, const float *inv_scale, const float *found_inf,
                    int64_t clamp_begin, int64_t clamp_end, int32_t zero_grad, void *stream);
+/* Same step with the per-step scalars read from DEVICE memory: hyper = [lr, 1 - beta1^t, sqrt(1 - beta2^t)].
+ * Lets a whole training step be replayed as one CUDA graph while lr / bias corrections change every step. */
+int umhs_adam_step_dev(float *param, float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float beta1,
+                       float beta2, float eps, const float *hyper, const float *inv_scale, const float *found_inf,
+                       int64_t clamp_begin, int64_t clamp_end, int32_t zero_grad, void *stream);
 /* out[i] += sum_s slabs[s*stride + i] */
 int umhs_reduce_slabs(const float *slabs, int64_t n_slabs, int64_t stride, int64_t n, float *out, void *stream);
 

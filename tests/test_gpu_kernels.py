@@ -88,18 +88,30 @@ def _grid(res, seed, fill=0.35):
     return b, aabbs
 
 
-@pytest.mark.parametrize("R,res,cone,far", [(2048, 32, 0.004, 1e3), (4096, 128, 0.004, 1e3), (777, 64, 0.0, 1e10),
-                                            (1, 32, 0.004, 1e3)])
-def test_march_bit_exact(R, res, cone, far):
+@pytest.mark.parametrize("R,res,cone,far,variant", [(2048, 32, 0.004, 1e3, 0), (4096, 128, 0.004, 1e3, 0),
+                                                    (777, 64, 0.0, 1e10, 0), (1, 32, 0.004, 1e3, 0),
+                                                    (3000, 64, 0.004, 1e3, 1), (3000, 128, 0.004, 1e3, 2)])
+def test_march_bit_exact(R, res, cone, far, variant):
     ops = _ops()
     o, d, jit = _rays(max(R, 3), 10 + R)
+    if variant == 1:  # axis-aligned and planar rays: zero direction components
+        g = torch.Generator().manual_seed(99)
+        axis = torch.randint(3, (d.shape[0],), generator=g)
+        planar = torch.rand(d.shape[0], generator=g) < 0.5
+        d2 = torch.zeros_like(d)
+        d2[torch.arange(d.shape[0]), axis] = torch.sign(d[torch.arange(d.shape[0]), axis]) + (d[torch.arange(d.shape[0]), axis] == 0)
+        d = torch.where(planar[:, None], torch.nn.functional.normalize(d * (torch.arange(3)[None, :] != axis[:, None]), dim=-1), d2)
+        d[d.abs().sum(-1) == 0] = torch.tensor([0.0, 1.0, 0.0])
     o, d, jit = o[:R], d[:R], jit[:R]
     b, aabbs = _grid(res, res)
+    if variant == 2:  # only the finest level occupied (outer levels skipped without occupancy fetches)
+        b[1:] = False
     step = (12 ** 0.5) / 1000
     near = torch.full((R,), 0.05) + jit * step
     farp = torch.full((R,), far)
     ri_r, t0_r, t1_r, pk_r = pack_oracle.traverse_grids(o, d, b, aabbs, near, farp, step, cone)
-    ri, t0, t1, pk = ops.march(o.to(DEV), d.to(DEV), near.to(DEV), farp.to(DEV), b.to(DEV), aabbs.to(DEV), step, cone)
+    ri, t0, t1, pk, tot = ops.march(o.to(DEV), d.to(DEV), near.to(DEV), farp.to(DEV), b.to(DEV), aabbs.to(DEV), step, cone)
+    assert int(tot[0]) == int(tot[1]) == ri_r.numel()
     assert ri_r.numel() > 0 or R == 1
     assert np.array_equal(pk.cpu().numpy(), pk_r.numpy())
     assert np.array_equal(ri.cpu().numpy(), ri_r.numpy())
@@ -129,12 +141,13 @@ def test_visibility_compaction_matches_boolean_mask():
         _, T, al = nerf3p.render_weight_from_density(t0, t1, sigma, packed)
         safe = ((T - 1e-4).abs() > 1e-7) & ((al - a).abs() > 1e-7)
         om = torch.tensor([occ_mean], device=DEV)
-        ri2, a0, a1, pk2 = ops.visibility_compact(packed.to(DEV), t0.to(DEV), t1.to(DEV), sigma.to(DEV), 1e-4, thre, om)
+        ri2, a0, a1, pk2, _, src = ops.visibility_compact(packed.to(DEV), t0.to(DEV), t1.to(DEV), sigma.to(DEV), 1e-4, thre, om)
         if bool(safe.all()):
             assert np.array_equal(ri2.cpu().numpy(), ri[mask].numpy())
             assert np.array_equal(a0.cpu().numpy(), t0[mask].numpy())
             assert np.array_equal(a1.cpu().numpy(), t1[mask].numpy())
             assert np.array_equal(pk2.cpu().numpy(), nerf3p.pack_info(ri[mask], R).numpy())
+            assert np.array_equal(src.cpu().numpy(), torch.nonzero(mask)[:, 0].numpy())
         else:
             assert abs(ri2.numel() - int(mask.sum())) <= int((~safe).sum())
 

@@ -86,6 +86,18 @@ struct Point {
     float tmid;  // (t0 + t1) / 2 for the ray form, 0 for explicit positions
 };
 
+// number of points a kernel processes: the host-side n, clamped by the optional device-side count
+__device__ __forceinline__ int64_t effective_n(const umhs_points &P, int64_t n) {
+    if (P.n_dev == nullptr) return n;
+    const int64_t m = __ldg(P.n_dev);
+    return m < n ? (m < 0 ? 0 : m) : n;
+}
+
+// row of point n in the hash-encoding array given to the MLP kernels
+__device__ __forceinline__ int64_t enc_row(const umhs_points &P, int64_t n) {
+    return P.enc_index ? (int64_t)__ldg(P.enc_index + n) : n;
+}
+
 __device__ __forceinline__ Point eval_point(const umhs_points &P, int64_t n) {
     Point p;
     if (P.positions != nullptr) {

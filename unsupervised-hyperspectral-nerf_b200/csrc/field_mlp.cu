@@ -237,12 +237,13 @@ field_mlp_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict__ e
     float *rowB = smem + L.bufB + tid * LDH;
     const float invT = 1.0f / mp.temperature;
 
+    n_total = effective_n(P, n_total);
     for (int64_t n = (int64_t)blockIdx.x * kFwdThreads + tid; n < n_total; n += (int64_t)gridDim.x * kFwdThreads) {
         const Point pt = eval_point(P, n);
         float o16[16];
         {
             float in[ENC];
-            const float4 *e4 = reinterpret_cast<const float4 *>(enc + n * ENC);
+            const float4 *e4 = reinterpret_cast<const float4 *>(enc + enc_row(P, n) * ENC);
 #pragma unroll
             for (int i = 0; i < ENC / 4; ++i) {
                 const float4 t = __ldg(e4 + i);
@@ -435,6 +436,7 @@ field_mlp_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict__ e
           *rowD2 = D2s + tid * LDH;
     const float invT = 1.0f / mp.temperature;
     const WOff oh = mlp3_offsets(K), of = mlp3_offsets(K + (spec ? 1 : 0));
+    n_total = effective_n(P, n_total);
     const int64_t n_tiles = (n_total + kBwdThreads - 1) / kBwdThreads;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -453,7 +455,7 @@ field_mlp_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict__ e
         float o16[16];
         {
             float in[ENC];
-            const float4 *e4 = reinterpret_cast<const float4 *>(enc + n * ENC);
+            const float4 *e4 = reinterpret_cast<const float4 *>(enc + enc_row(P, n) * ENC);
 #pragma unroll
             for (int i = 0; i < ENC / 4; ++i) {
                 const float4 t = __ldg(e4 + i);
@@ -525,7 +527,7 @@ field_mlp_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict__ e
         __syncthreads();
         {
             float in[ENC];
-            const float4 *e4 = reinterpret_cast<const float4 *>(enc + n * ENC);
+            const float4 *e4 = reinterpret_cast<const float4 *>(enc + enc_row(P, n) * ENC);
 #pragma unroll
             for (int i = 0; i < ENC / 4; ++i) {
                 const float4 t = __ldg(e4 + i);

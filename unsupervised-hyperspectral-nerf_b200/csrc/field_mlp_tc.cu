@@ -109,10 +109,18 @@ __device__ __forceinline__ void pos_encoding_tc(const Point &p, float (&pe)[12])
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         const float a = s[d], b = s[d] * 2.0f;
-        pe[2 * d] = sinf(a);
-        pe[2 * d + 1] = sinf(b);
-        pe[6 + 2 * d] = sinf(a + half_pi);
-        pe[6 + 2 * d + 1] = sinf(b + half_pi);
+        // the encoding is rounded to bf16 right after: the fast sine (abs. error ~1e-6 for |x| < 48) is exact enough
+        if (fabsf(b) < 48.0f) {
+            pe[2 * d] = __sinf(a);
+            pe[2 * d + 1] = __sinf(b);
+            pe[6 + 2 * d] = __sinf(a + half_pi);
+            pe[6 + 2 * d + 1] = __sinf(b + half_pi);
+        } else {
+            pe[2 * d] = sinf(a);
+            pe[2 * d + 1] = sinf(b);
+            pe[6 + 2 * d] = sinf(a + half_pi);
+            pe[6 + 2 * d + 1] = sinf(b + half_pi);
+        }
     }
 }
 
@@ -136,32 +144,52 @@ __device__ __forceinline__ void sh_deg3_tc(float x, float y, float z, float (&c)
     c[15] = 0.5900435899266435f * x * (xx - 3.0f * yy);
 }
 
-// epilogue helper: accumulator columns [col0, col0+ncols) of this thread's row -> + bias, ReLU -> bf16 operand tile
+// epilogue helper: 64 accumulator columns [col0, col0+64) of this thread's row -> + bias, ReLU -> bf16 operand tile
 __device__ __forceinline__ void acc_to_tile_relu(uint32_t trow, int col0, int ncols, const float *bias, uint8_t *tile,
                                                  int row, int tile_col0) {
-    for (int c = 0; c < ncols; c += 16) {
-        float v[16];
-        tmem_ld16(trow + (uint32_t)(col0 + c), v);
+    (void)ncols;  // always 64
+    float v[64];
+    tmem_ld64(trow + (uint32_t)col0, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bias[c + i], 0.f);
-        store8(tile, row, tile_col0 + c, CH_ACT, v);
-        store8(tile, row, tile_col0 + c + 8, CH_ACT, v + 8);
+    for (int c = 0; c < 64; c += 8) {
+        const float4 b0 = *reinterpret_cast<const float4 *>(bias + c), b1 = *reinterpret_cast<const float4 *>(bias + c + 4);
+        float o[8] = {fmaxf(v[c] + b0.x, 0.f),     fmaxf(v[c + 1] + b0.y, 0.f), fmaxf(v[c + 2] + b0.z, 0.f),
+                      fmaxf(v[c + 3] + b0.w, 0.f), fmaxf(v[c + 4] + b1.x, 0.f), fmaxf(v[c + 5] + b1.y, 0.f),
+                      fmaxf(v[c + 6] + b1.z, 0.f), fmaxf(v[c + 7] + b1.w, 0.f)};
+        store8(tile, row, tile_col0 + c, CH_ACT, o);
+    }
+}
+
+// Optional cycle trace (developer aid, off unless umhs_debug_trace() installs a buffer): CTA 0 stamps clock64()
+// at the stages of every round so that the latency chain of a tile can be read back.
+__device__ long long *g_trace = nullptr;
+__device__ int g_trace_cap = 0;
+__device__ __forceinline__ void trace(int &slot, int tag) {
+    if (g_trace != nullptr && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 96) && slot < g_trace_cap) {
+        g_trace[2 * (slot * 2 + (threadIdx.x ? 1 : 0))] = tag;
+        g_trace[2 * (slot * 2 + (threadIdx.x ? 1 : 0)) + 1] = clock64();
+        ++slot;
     }
 }
 
 struct RoundSync {
     uint64_t *bar;
     uint32_t parity;
+    int slot = 0;
     // all threads: operand tiles written & accumulators consumed -> one thread may issue MMAs
     __device__ __forceinline__ void before_issue() {
+        trace(slot, 1);  // epilogue of the previous round finished
         fence_proxy_async();
         fence_before_sync();
         __syncthreads();
+        trace(slot, 2);  // CTA barrier passed
     }
     __device__ __forceinline__ void wait_done() {
+        trace(slot, 3);  // (thread 0: MMAs issued + commit) waiting for the tensor core
         mbar_wait(bar, parity);
         parity ^= 1u;
         fence_after_sync();
+        trace(slot, 4);  // accumulators ready
     }
 };
 
@@ -207,6 +235,7 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
     const float *Bd0 = reinterpret_cast<const float *>(smem + TcSmem::b_d0);
     const float invT = DENSITY_ONLY ? 1.f : 1.0f / mp.temperature;
 
+    n_total = effective_n(P, n_total);
     const int64_t n_tiles = (n_total + TM - 1) / TM;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t n0 = tile * TM;
@@ -216,7 +245,7 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         float pe[12];
         // ---------------- round 0: enc -> tX ; (specular) [sh, pe] -> tX2 ; MMA base0
         {
-            const float4 *e4 = reinterpret_cast<const float4 *>(enc + n * 32);
+            const float4 *e4 = reinterpret_cast<const float4 *>(enc + enc_row(P, n) * 32);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const float4 a = __ldg(e4 + 2 * c), b = __ldg(e4 + 2 * c + 1);
@@ -246,6 +275,7 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             gemm_kmajor(tbase + 0, sX, sWb0, 64, 0, 64, 32, 0);
             commit(bar);
         }
+    if (warp == 0) __syncwarp();  // lanes 1-31 must not spin on the mbarrier while lane 0 is still issuing
         rs.wait_done();
         // ---------------- round 1: H0 = relu(. + b) -> tH ; MMA base1 (N=16) [+ dir0 (N=16) at cols 64..79]
         acc_to_tile_relu(trow, 0, 64, Bb0, tH, tid, 0);
@@ -256,6 +286,7 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             if (spec) gemm_kmajor(tbase + 64, sX2, sWd0, 16, 0, 16, 32, 0);
             commit(bar);
         }
+        if (warp == 0) __syncwarp();  // lanes 1-31 must not spin on the mbarrier while lane 0 is still issuing
         rs.wait_done();
         // ---------------- round 2: sigma, emb ; X = [pe, emb] -> tX ; MMA head0|feat0 (N=128)
         float o16[16];
@@ -302,6 +333,7 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             gemm_kmajor(tbase + 0, sX, sWhf0, 128, 0, 128, 32, 0);
             commit(bar);
         }
+        if (warp == 0) __syncwarp();  // lanes 1-31 must not spin on the mbarrier while lane 0 is still issuing
         rs.wait_done();
         // ---------------- round 3: hidden 0 of both MLPs -> tH, tF ; MMA head1, feat1
         acc_to_tile_relu(trow, 0, 64, Bh0, tH, tid, 0);
@@ -313,6 +345,7 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             gemm_kmajor(tbase + 64, sF, sWf1, 64, 0, 64, 64, 0);
             commit(bar);
         }
+        if (warp == 0) __syncwarp();  // lanes 1-31 must not spin on the mbarrier while lane 0 is still issuing
         rs.wait_done();
         // ---------------- round 4: hidden 1 -> tH, tF ; MMA head2 (N=16), feat2 (N=32)
         acc_to_tile_relu(trow, 0, 64, Bh1, tH, tid, 0);
@@ -324,6 +357,7 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             gemm_kmajor(tbase + 64, sF, sWf2, 32, 0, 32, 64, 0);
             commit(bar);
         }
+        if (warp == 0) __syncwarp();  // lanes 1-31 must not spin on the mbarrier while lane 0 is still issuing
         rs.wait_done();
         // ---------------- round 5: outputs
         {
@@ -334,31 +368,30 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             if (valid) {
                 float mx = -3.0e38f;
 #pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    if (k < K) mx = fmaxf(mx, (zf[k] + Bf2[k]) * invT);
+                for (int k = 0; k < 16; ++k) {
+                    zf[k] = (zf[k] + Bf2[k]) * invT;
+                    if (k < K) mx = fmaxf(mx, zf[k]);
+                }
                 float den = 0.f, e[16];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
-                    e[k] = (k < K) ? expf((zf[k] + Bf2[k]) * invT - mx) : 0.f;
+                    e[k] = (k < K) ? __expf(zf[k] - mx) : 0.f;
                     den += e[k];
                 }
+                const float rden = __frcp_rn(den);
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     if (k < K) {
-                        out.scalar[n * K + k] = 1.0f / (1.0f + expf(-(zh[k] + Bh2[k])));
-                        out.abund[n * K + k] = e[k] / den;
+                        out.scalar[n * K + k] = __frcp_rn(1.0f + __expf(-(zh[k] + Bh2[k])));
+                        out.abund[n * K + k] = e[k] * rden;
                     }
                 }
                 if (spec && out.s1) {
-                    float z = 0.f;
-                    if (K < 16) {
+                    float z = zf2[0] + Bf2[16];
 #pragma unroll
-                        for (int k = 0; k < 16; ++k)
-                            if (k == K) z = zf[k];
-                    } else {
-                        z = zf2[0];
-                    }
-                    out.s1[n] = 1.0f / (1.0f + expf(-(z + Bf2[K])));
+                    for (int k = 0; k < 16; ++k)
+                        if (k == K) z = zf[k] * mp.temperature;
+                    out.s1[n] = __frcp_rn(1.0f + __expf(-z));
                 }
             }
         }
@@ -425,6 +458,7 @@ tc05_selftest_kernel(int mode, const float *__restrict__ A, const float *__restr
         else gemm_wgrad(tbase, smem_u32(tA), 0, smem_u32(tB), 0, N, 0);
         commit(bar);
     }
+    if (warp == 0) __syncwarp();  // lanes 1-31 must not spin on the mbarrier while lane 0 is still issuing
     mbar_wait(bar, 0);
     fence_after_sync();
     const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
@@ -443,6 +477,11 @@ tc05_selftest_kernel(int mode, const float *__restrict__ A, const float *__restr
     if (warp == 0) tmem_dealloc<128>(tbase);
 }
 
+__global__ void set_trace_kernel(long long *buf, int cap) {
+    g_trace = buf;
+    g_trace_cap = cap;
+}
+
 static int tc_grid(int64_t n, int ctas_per_sm) {
     const int64_t want = (n + TM - 1) / TM;
     const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
@@ -452,6 +491,12 @@ static int tc_grid(int64_t n, int ctas_per_sm) {
 }  // namespace umhs
 
 using namespace umhs;
+
+extern "C" int umhs_debug_trace(int64_t *buffer, int32_t capacity_slots, void *stream) {
+    set_trace_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<long long *>(buffer), buffer ? capacity_slots : 0);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
 
 extern "C" int umhs_tc05_selftest(int32_t mode, const float *A, const float *B, float *D, int32_t N, int32_t K,
                                   void *stream) {
@@ -512,38 +557,39 @@ extern "C" int umhs_field_mlp_tc_fwd(const umhs_points *pts, int64_t n, const fl
 namespace umhs {
 
 struct TcBwd {
-    static constexpr int ones = TcSmem::ctrl + 128;          // [128 x 8] bf16 ones
-    static constexpr int sbias = ones + 2048;                // fp32 accumulators: h2[16] f2[32] b1[16] d0[16]
-    static constexpr int act = (sbias + 80 * 4 + 127) / 128 * 128;
-    static constexpr int tA0 = act;                 // [128 x 32]
-    static constexpr int tX = tA0 + TM * 32 * 2;    // [128 x 32]
-    static constexpr int tH0 = tX + TM * 32 * 2;    // [128 x 64]
-    static constexpr int tX2 = tH0 + TM * 64 * 2;   // [128 x 64]
-    static constexpr int tH1 = tX2 + TM * 64 * 2;
-    static constexpr int tH2 = tH1 + TM * 64 * 2;
+    // narrow-layer bias gradients: per-thread running column sums (80 rows x 128 threads fp32), reduced once at the end
+    static constexpr int sacc = TcSmem::ctrl + 128;          // rows: h2[16] f2[32] b1[16] d0[16]
+    static constexpr int act = sacc + 80 * TM * 4;
+    // activation tiles; a 2 KB chunk of ones directly behind tA0, tX and tH1 extends those B operands by 8 columns of
+    // ones, so the bias gradient of a 64-wide layer is column 64 (32 for the 32-wide inputs) of its weight-gradient MMA
+    static constexpr int tA0 = act;                        // [128 x 32] + ones chunk
+    static constexpr int tX = tA0 + TM * 32 * 2 + 2048;    // [128 x 32] + ones chunk
+    static constexpr int tH0 = tX + TM * 32 * 2 + 2048;    // [128 x 64]
+    static constexpr int tX2 = tH0 + TM * 64 * 2;          // [128 x 64]
+    static constexpr int tH1 = tX2 + TM * 64 * 2;          // [128 x 64] + ones chunk
+    static constexpr int tH2 = tH1 + TM * 64 * 2 + 2048;
     static constexpr int tD1 = tH2 + TM * 64 * 2;
     static constexpr int tD2 = tD1 + TM * 64 * 2;
     static constexpr int end = tD2 + TM * 64 * 2;
     // TMEM columns
     static constexpr int W0 = 0, W1 = 64;
-    static constexpr int P_h2t = 128, P_h1 = 144, P_h0 = 208, P_f2t = 240, P_f1 = 272, P_f0 = 336;
-    static constexpr int P_b1t = 368, P_b0 = 384, P_d0t = 416;
-    static constexpr int Pb_h1 = 432, Pb_h0 = 440, Pb_f1 = 448, Pb_f0 = 456, Pb_b0 = 464;
+    static constexpr int P_h2t = 128, P_h1 = 144, P_h0 = 216, P_f2t = 256, P_f1 = 288, P_f0 = 360;
+    static constexpr int P_b1t = 400, P_b0 = 416, P_d0t = 456;  // .. 472
     static constexpr int ncols = 512;
 };
 
 // accumulator columns [col0, col0+64) of this row, masked by relu'(act tile row) -> bf16 delta tile
 __device__ __forceinline__ void acc_to_delta_masked(uint32_t trow, int col0, const uint8_t *act_tile, uint8_t *delta_tile,
                                                     int row, bool valid) {
-    for (int c = 0; c < 64; c += 16) {
-        float v[16], h[16];
-        tmem_ld16(trow + (uint32_t)(col0 + c), v);
-        load8(act_tile, row, c, CH_ACT, h);
-        load8(act_tile, row, c + 8, CH_ACT, h + 8);
+    float v[64];
+    tmem_ld64(trow + (uint32_t)col0, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = (valid && h[i] > 0.f) ? v[i] : 0.f;
-        store8(delta_tile, row, c, CH_ACT, v);
-        store8(delta_tile, row, c + 8, CH_ACT, v + 8);
+    for (int c = 0; c < 64; c += 8) {
+        float h[8], o[8];
+        load8(act_tile, row, c, CH_ACT, h);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (valid && h[i] > 0.f) ? v[c + i] : 0.f;
+        store8(delta_tile, row, c, CH_ACT, o);
     }
 }
 
@@ -584,9 +630,11 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
     stage_all_weights(smem, mp, false, tid);
     {
         const float one[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-        store8(smem + TcBwd::ones, tid, 0, CH_ACT, one);
-        float *sb = reinterpret_cast<float *>(smem + TcBwd::sbias);
-        if (tid < 80) sb[tid] = 0.f;
+        store8(smem + TcBwd::tA0, tid, 32, CH_ACT, one);  // chunk 4 of the 32-wide tiles, chunk 8 of tH1
+        store8(smem + TcBwd::tX, tid, 32, CH_ACT, one);
+        store8(smem + TcBwd::tH1, tid, 64, CH_ACT, one);
+        float *sa = reinterpret_cast<float *>(smem + TcBwd::sacc);
+        for (int i = tid; i < 80 * TM; i += TM) sa[i] = 0.f;
         // zero the padding columns 32..63 of the specular input tile once (columns 0..31 are rewritten per tile)
         const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -609,7 +657,6 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
     uint8_t *tH1 = smem + TcBwd::tH1, *tH2 = smem + TcBwd::tH2, *tD1 = smem + TcBwd::tD1, *tD2 = smem + TcBwd::tD2;
     const uint32_t sA0 = smem_u32(tA0), sX = smem_u32(tX), sH0 = smem_u32(tH0), sX2 = smem_u32(tX2);
     const uint32_t sH1 = smem_u32(tH1), sH2 = smem_u32(tH2), sD1 = smem_u32(tD1), sD2 = smem_u32(tD2);
-    const uint32_t sOnes = smem_u32(smem + TcBwd::ones);
     const uint32_t sWb0 = smem_u32(smem + TcSmem::w_base0), sWb1 = smem_u32(smem + TcSmem::w_base1);
     const uint32_t sWhf0 = smem_u32(smem + TcSmem::w_hf0), sWh1 = smem_u32(smem + TcSmem::w_h1);
     const uint32_t sWf1 = smem_u32(smem + TcSmem::w_f1), sWh2 = smem_u32(smem + TcSmem::w_h2);
@@ -623,25 +670,39 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
     const float *Bh2 = reinterpret_cast<const float *>(smem + TcSmem::b_h2);
     const float *Bf2 = reinterpret_cast<const float *>(smem + TcSmem::b_f2);
     const float *Bd0 = reinterpret_cast<const float *>(smem + TcSmem::b_d0);
-    float *sb_h2 = reinterpret_cast<float *>(smem + TcBwd::sbias), *sb_f2 = sb_h2 + 16, *sb_b1 = sb_f2 + 32,
-          *sb_d0 = sb_b1 + 16;
+    // this thread's column of the bias accumulators: row k of a block lives at [k * TM + tid]
+    float *sb_h2 = reinterpret_cast<float *>(smem + TcBwd::sacc) + tid, *sb_f2 = sb_h2 + 16 * TM,
+          *sb_b1 = sb_f2 + 32 * TM, *sb_d0 = sb_b1 + 16 * TM;
     const float invT = 1.0f / mp.temperature;
 
+    n_total = effective_n(P, n_total);
     const int64_t n_tiles = (n_total + TM - 1) / TM;
     uint32_t acc = 0;  // 0 on this CTA's first tile: the persistent accumulators are initialised, not accumulated
+    // the next tile's hash encoding and sample geometry are fetched while the tensor core finishes the current tile
+    float4 pre[8];
+    Point pt_next;
+    auto prefetch = [&](int64_t tile_idx) {
+        if (tile_idx >= n_tiles) return;
+        const int64_t m = tile_idx * TM + tid;
+        const int64_t nn = m < n_total ? m : n_total - 1;
+        const float4 *e4 = reinterpret_cast<const float4 *>(enc + enc_row(P, nn) * 32);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) pre[c] = __ldg(e4 + c);
+        pt_next = eval_point(P, nn);
+    };
+    prefetch(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, acc = 1) {
         const int64_t n0 = tile * TM;
         const bool valid = n0 + tid < n_total;
         const int64_t n = valid ? n0 + tid : n_total - 1;
-        const Point pt = eval_point(P, n);
+        const Point pt = pt_next;
         float pe[12];
         pos_encoding_tc(pt, pe);
         // ---------------- T0: enc -> tA0 ; (specular) [sh, pe] -> tX2 ; base0 [, dir0]
         {
-            const float4 *e4 = reinterpret_cast<const float4 *>(enc + n * 32);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const float4 a = __ldg(e4 + 2 * c), b = __ldg(e4 + 2 * c + 1);
+                const float4 a = pre[2 * c], b = pre[2 * c + 1];
                 const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
                 store8(tA0, tid, 8 * c, CH_ACT, v);
             }
@@ -665,6 +726,7 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             if (spec) gemm_kmajor(tbase + TcBwd::W1, sX2, sWd0, 16, 0, 16, 32, 0);
             commit(bar);
         }
+    if (warp == 0) __syncwarp();  // lanes 1-31 must not spin on the mbarrier while lane 0 is still issuing
         rs.wait_done();
         // ---------------- T1: H0 -> tH0 ; (specular) d spec_hidden -> tD2[:, :16] ; base1 [, dir0 wgrad]
         acc_to_tile_relu(trow, TcBwd::W0, 64, Bb0, tH0, tid, 0);
@@ -682,7 +744,8 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             }
             store8(tD2, tid, 0, CH_ACT, dsh);
             store8(tD2, tid, 8, CH_ACT, dsh + 8);
-            warp_colsum_to_smem(dsh, 16, sb_d0, lane);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) sb_d0[k * TM] += dsh[k];
         }
         rs.before_issue();
         if (tid == 0) {
@@ -691,6 +754,7 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             if (spec) gemm_wgrad(tbase + TcBwd::P_d0t, sX2, 0, sD2, 0, 16, acc);
             commit(bar);
         }
+        if (warp == 0) __syncwarp();  // lanes 1-31 must not spin on the mbarrier while lane 0 is still issuing
         rs.wait_done();
         // ---------------- T2: o16 ; X = [pe, emb] -> tX ; head0 -> W0, feat0 -> W1
         float o16[16], demb[15];
@@ -717,6 +781,7 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             gemm_kmajor(tbase + TcBwd::W1, sX, sWhf0, 128, 64, 64, 32, 0);
             commit(bar);
         }
+        if (warp == 0) __syncwarp();  // lanes 1-31 must not spin on the mbarrier while lane 0 is still issuing
         rs.wait_done();
 
         // ================= the two 27->64->64->nout MLPs: m = 0 mlp_head (sigmoid), m = 1 feature_mlp (softmax, s1)
@@ -743,6 +808,7 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                 gemm_kmajor(tbase + TcBwd::W0, sH1, sW1, 64, 0, 64, 64, 0);
                 commit(bar);
             }
+            if (warp == 0) __syncwarp();  // lanes 1-31 must not spin on the mbarrier while lane 0 is still issuing
             rs.wait_done();
             // ---- hidden 1 -> tH2 ; last layer
             acc_to_tile_relu(trow, TcBwd::W0, 64, B1, tH2, tid, 0);
@@ -752,6 +818,13 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                 gemm_kmajor(tbase + TcBwd::W0, sH2, sW2, w2_rows, 0, w2_rows, 64, 0);
                 commit(bar);
             }
+            if (warp == 0) __syncwarp();  // lanes 1-31 must not spin on the mbarrier while lane 0 is still issuing
+            // incoming gradients of this MLP's outputs: fetched while the tensor core runs the last layer
+            float gin[17];
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                gin[k] = (valid && k < K) ? __ldg((m ? g.d_abund : g.d_scalar) + n * K + k) : 0.f;
+            gin[16] = (valid && m == 1 && spec && g.d_s1) ? __ldg(g.d_s1 + n) : 0.f;
             rs.wait_done();
             // ---- dz -> tD2[:, :w2_rows] ; wgrad L2 (transposed: rows = in-features) + dgrad L2
             {
@@ -768,36 +841,42 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
 #pragma unroll
                 for (int k = 0; k < 32; ++k) dz[k] = 0.f;
                 if (valid) {
+                    // tensor-core path: fast exp / reciprocal (operands are bf16 anyway); one exp per logit
                     if (m == 0) {
 #pragma unroll
                         for (int k = 0; k < 16; ++k) {
                             if (k < K) {
-                                const float s = 1.0f / (1.0f + expf(-(z[k] + B2[k])));
-                                dz[k] = __ldg(g.d_scalar + n * K + k) * s * (1.0f - s);
+                                const float s = __frcp_rn(1.0f + __expf(-(z[k] + B2[k])));
+                                dz[k] = gin[k] * s * (1.0f - s);
                             }
                         }
                     } else {
                         float mx = -3.0e38f, e[16], den = 0.f, dot = 0.f, da[16];
 #pragma unroll
-                        for (int k = 0; k < 16; ++k)
-                            if (k < K) mx = fmaxf(mx, (z[k] + B2[k]) * invT);
-#pragma unroll
                         for (int k = 0; k < 16; ++k) {
-                            e[k] = (k < K) ? expf((z[k] + B2[k]) * invT - mx) : 0.f;
-                            da[k] = (k < K) ? __ldg(g.d_abund + n * K + k) : 0.f;
-                            den += e[k];
+                            z[k] = (z[k] + B2[k]) * invT;
+                            if (k < K) mx = fmaxf(mx, z[k]);
                         }
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) dot += (e[k] / den) * da[k];
+                        for (int k = 0; k < 16; ++k) {
+                            e[k] = (k < K) ? __expf(z[k] - mx) : 0.f;
+                            da[k] = gin[k];
+                            den += e[k];
+                            dot += e[k] * da[k];
+                        }
+                        const float rden = __frcp_rn(den);
+                        dot *= rden;
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) dz[k] = (e[k] / den) * invT * (da[k] - dot);
+                        for (int k = 0; k < 16; ++k) dz[k] = e[k] * rden * invT * (da[k] - dot);
                         if (spec) {
-                            float zs = 0.f;
+                            // logit K of feature_mlp is the specular gate s1 (raw value: undo the /T applied above
+                            // only for columns < 16; column 16 lives in z[16] untouched)
+                            float zs = z[16] + B2[16];
 #pragma unroll
-                            for (int k = 0; k < 17; ++k)
-                                if (k == K) zs = z[k];
-                            const float s = 1.0f / (1.0f + expf(-(zs + B2[K])));
-                            const float ds = (g.d_s1 ? __ldg(g.d_s1 + n) : 0.f) * s * (1.0f - s);
+                            for (int k = 0; k < 16; ++k)
+                                if (k == K) zs = z[k] * mp.temperature;
+                            const float s = __frcp_rn(1.0f + __expf(-zs));
+                            const float ds = gin[16] * s * (1.0f - s);
 #pragma unroll
                             for (int k = 0; k < 17; ++k)
                                 if (k == K) dz[k] = ds;
@@ -810,7 +889,12 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                     store8(tD2, tid, 16, CH_ACT, dz + 16);
                     store8(tD2, tid, 24, CH_ACT, dz + 24);
                 }
-                warp_colsum_to_smem(dz, nout, m ? sb_f2 : sb_h2, lane);
+                {
+                    float *sb = m ? sb_f2 : sb_h2;
+#pragma unroll
+                    for (int k = 0; k < 17; ++k)
+                        if (k < nout) sb[k * TM] += dz[k];
+                }
             }
             rs.before_issue();
             if (tid == 0) {
@@ -819,28 +903,29 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                 gemm_dgrad(tbase + TcBwd::W0, sD2, sW2, w2_rows, 0, 64, w2_rows, 0);
                 commit(bar);
             }
+            if (warp == 0) __syncwarp();  // lanes 1-31 must not spin on the mbarrier while lane 0 is still issuing
             rs.wait_done();
             // ---- d hidden1 -> tD1 ; wgrad L1 (+bias) + dgrad L1
             acc_to_delta_masked(trow, TcBwd::W0, tH2, tD1, tid, valid);
             rs.before_issue();
             if (tid == 0) {
                 fence_after_sync();
-                gemm_wgrad(tbase + (m ? TcBwd::P_f1 : TcBwd::P_h1), sD1, 0, sH1, 0, 64, acc);
-                gemm_wgrad(tbase + (m ? TcBwd::Pb_f1 : TcBwd::Pb_h1), sD1, 0, sOnes, 0, 8, acc);
+                gemm_wgrad(tbase + (m ? TcBwd::P_f1 : TcBwd::P_h1), sD1, 0, sH1, 0, 72, acc);  // 64 + ones
                 gemm_dgrad(tbase + TcBwd::W0, sD1, sW1, 64, 0, 64, 64, 0);
                 commit(bar);
             }
+            if (warp == 0) __syncwarp();  // lanes 1-31 must not spin on the mbarrier while lane 0 is still issuing
             rs.wait_done();
             // ---- d hidden0 -> tD2 ; wgrad L0 (+bias) + dgrad L0 (N = 32: d [pe, emb])
             acc_to_delta_masked(trow, TcBwd::W0, tH1, tD2, tid, valid);
             rs.before_issue();
             if (tid == 0) {
                 fence_after_sync();
-                gemm_wgrad(tbase + (m ? TcBwd::P_f0 : TcBwd::P_h0), sD2, 0, sX, 0, 32, acc);
-                gemm_wgrad(tbase + (m ? TcBwd::Pb_f0 : TcBwd::Pb_h0), sD2, 0, sOnes, 0, 8, acc);
+                gemm_wgrad(tbase + (m ? TcBwd::P_f0 : TcBwd::P_h0), sD2, 0, sX, 0, 40, acc);   // 32 + ones
                 gemm_dgrad(tbase + TcBwd::W0, sD2, sWhf0, 128, m ? 64 : 0, 32, 64, 0);
                 commit(bar);
             }
+            if (warp == 0) __syncwarp();  // lanes 1-31 must not spin on the mbarrier while lane 0 is still issuing
             rs.wait_done();
         }
         // ================= base MLP backward
@@ -859,7 +944,8 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             for (int i = 0; i < 15; ++i) dO[1 + i] = valid ? demb[i] : 0.f;
             store8(tD2, tid, 0, CH_ACT, dO);
             store8(tD2, tid, 8, CH_ACT, dO + 8);
-            warp_colsum_to_smem(dO, 16, sb_b1, lane);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) sb_b1[k * TM] += dO[k];
         }
         rs.before_issue();
         if (tid == 0) {
@@ -868,16 +954,18 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             gemm_dgrad(tbase + TcBwd::W0, sD2, sWb1, 16, 0, 64, 16, 0);
             commit(bar);
         }
+        if (warp == 0) __syncwarp();  // lanes 1-31 must not spin on the mbarrier while lane 0 is still issuing
         rs.wait_done();
         acc_to_delta_masked(trow, TcBwd::W0, tH0, tD1, tid, valid);
         rs.before_issue();
         if (tid == 0) {
             fence_after_sync();
-            gemm_wgrad(tbase + TcBwd::P_b0, sD1, 0, sA0, 0, 32, acc);
-            gemm_wgrad(tbase + TcBwd::Pb_b0, sD1, 0, sOnes, 0, 8, acc);
+            gemm_wgrad(tbase + TcBwd::P_b0, sD1, 0, sA0, 0, 40, acc);  // 32 + ones
             if (d_enc) gemm_dgrad(tbase + TcBwd::W0, sD1, sWb0, 64, 0, 32, 64, 0);
             commit(bar);
         }
+        if (warp == 0) __syncwarp();  // lanes 1-31 must not spin on the mbarrier while lane 0 is still issuing
+        prefetch(tile + gridDim.x);
         rs.wait_done();
         if (d_enc) {
             float v[16];
@@ -897,26 +985,39 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
     // ================= flush the persistent weight-gradient accumulators (row r = 16*warp + lane, lane < 16)
     __syncthreads();
     fence_after_sync();
+    if (acc == 0) {  // this CTA processed no tile (device-side count smaller than the grid): nothing to flush
+        if (warp == 0) tmem_dealloc<TcBwd::ncols>(tbase);
+        return;
+    }
     const int r = warp * 16 + lane;
     flush_acc(trow, TcBwd::P_h2t, K, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.head_w2 + c * 64 + r, v); });
-    flush_acc(trow, TcBwd::P_h1, 64, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.head_w1 + r * 64 + c, v); });
-    flush_acc(trow, TcBwd::P_h0, 27, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.head_w0 + r * 27 + c, v); });
+    flush_acc(trow, TcBwd::P_h1, 65, lane, [&](int c, float v) {
+        if (v != 0.f) atomicAdd(c < 64 ? dp.head_w1 + r * 64 + c : dp.head_b1 + r, v); });
+    flush_acc(trow, TcBwd::P_h0, 33, lane, [&](int c, float v) {
+        if (v != 0.f && (c < 27 || c == 32)) atomicAdd(c < 27 ? dp.head_w0 + r * 27 + c : dp.head_b0 + r, v); });
     flush_acc(trow, TcBwd::P_f2t, K + spec, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.feat_w2 + c * 64 + r, v); });
-    flush_acc(trow, TcBwd::P_f1, 64, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.feat_w1 + r * 64 + c, v); });
-    flush_acc(trow, TcBwd::P_f0, 27, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.feat_w0 + r * 27 + c, v); });
+    flush_acc(trow, TcBwd::P_f1, 65, lane, [&](int c, float v) {
+        if (v != 0.f) atomicAdd(c < 64 ? dp.feat_w1 + r * 64 + c : dp.feat_b1 + r, v); });
+    flush_acc(trow, TcBwd::P_f0, 33, lane, [&](int c, float v) {
+        if (v != 0.f && (c < 27 || c == 32)) atomicAdd(c < 27 ? dp.feat_w0 + r * 27 + c : dp.feat_b0 + r, v); });
     flush_acc(trow, TcBwd::P_b1t, 16, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.base_w1 + c * 64 + r, v); });
-    flush_acc(trow, TcBwd::P_b0, 32, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.base_w0 + r * 32 + c, v); });
+    flush_acc(trow, TcBwd::P_b0, 33, lane, [&](int c, float v) {
+        if (v != 0.f) atomicAdd(c < 32 ? dp.base_w0 + r * 32 + c : dp.base_b0 + r, v); });
     if (spec)
         flush_acc(trow, TcBwd::P_d0t, 16, lane, [&](int c, float v) { if (r < 28 && v != 0.f) atomicAdd(dp.dir_w0 + c * 28 + r, v); });
-    flush_acc(trow, TcBwd::Pb_h1, 1, lane, [&](int, float v) { if (v != 0.f) atomicAdd(dp.head_b1 + r, v); });
-    flush_acc(trow, TcBwd::Pb_h0, 1, lane, [&](int, float v) { if (v != 0.f) atomicAdd(dp.head_b0 + r, v); });
-    flush_acc(trow, TcBwd::Pb_f1, 1, lane, [&](int, float v) { if (v != 0.f) atomicAdd(dp.feat_b1 + r, v); });
-    flush_acc(trow, TcBwd::Pb_f0, 1, lane, [&](int, float v) { if (v != 0.f) atomicAdd(dp.feat_b0 + r, v); });
-    flush_acc(trow, TcBwd::Pb_b0, 1, lane, [&](int, float v) { if (v != 0.f) atomicAdd(dp.base_b0 + r, v); });
-    if (tid < K && sb_h2[tid] != 0.f) atomicAdd(dp.head_b2 + tid, sb_h2[tid]);
-    if (tid < K + spec && sb_f2[tid] != 0.f) atomicAdd(dp.feat_b2 + tid, sb_f2[tid]);
-    if (tid < 16 && sb_b1[tid] != 0.f) atomicAdd(dp.base_b1 + tid, sb_b1[tid]);
-    if (spec && tid < 16 && sb_d0[tid] != 0.f) atomicAdd(dp.dir_b0 + tid, sb_d0[tid]);
+    {   // narrow-layer biases: sum this CTA's per-thread accumulators (row k = 128 consecutive floats)
+        const float *sa = reinterpret_cast<const float *>(smem + TcBwd::sacc);
+        if (tid < 80) {
+            float a = 0.f;
+            for (int i = 0; i < TM; ++i) a += sa[tid * TM + ((i + tid) & (TM - 1))];
+            float *dst = nullptr;
+            if (tid < 16) dst = (tid < K) ? dp.head_b2 + tid : nullptr;
+            else if (tid < 48) dst = (tid - 16 < K + spec) ? dp.feat_b2 + (tid - 16) : nullptr;
+            else if (tid < 64) dst = dp.base_b1 + (tid - 48);
+            else dst = spec ? dp.dir_b0 + (tid - 64) : nullptr;
+            if (dst != nullptr && a != 0.f) atomicAdd(dst, a);
+        }
+    }
     fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc<TcBwd::ncols>(tbase);

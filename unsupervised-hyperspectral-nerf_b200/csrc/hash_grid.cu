@@ -72,6 +72,7 @@ __device__ __forceinline__ float2 blend(const float2 (&f)[8], float ox, float oy
 
 struct SrcPoints {
     umhs_points P;
+    __device__ __forceinline__ int64_t count(int64_t n) const { return effective_n(P, n); }
     __device__ __forceinline__ void get(int64_t n, float &x, float &y, float &z) const {
         const Point p = eval_point(P, n);
         x = p.x;
@@ -82,6 +83,7 @@ struct SrcPoints {
 
 struct SrcX01 {
     const float *x01;
+    __device__ __forceinline__ int64_t count(int64_t n) const { return n; }
     __device__ __forceinline__ void get(int64_t n, float &x, float &y, float &z) const {
         x = __ldg(x01 + 3 * n + 0);
         y = __ldg(x01 + 3 * n + 1);
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(kHashThreads)
 hash_encode_fwd_kernel(Src src, int64_t n_total, const float2 *__restrict__ table, const float *__restrict__ scalings,
                        int L, int log2T, float *__restrict__ enc) {
     const int64_t n = (int64_t)blockIdx.x * kHashThreads + threadIdx.x;
-    if (n >= n_total) return;
+    if (n >= src.count(n_total)) return;
     float x, y, z;
     src.get(n, x, y, z);
     const uint32_t tmask = (log2T >= 32) ? 0xffffffffu : ((1u << log2T) - 1u);
@@ -166,7 +168,9 @@ hash_encode_bwd_kernel(Src src, int64_t n_total, const float *__restrict__ scali
                        const float *__restrict__ d_enc, float2 *__restrict__ d_table, int agg_levels) {
     const int64_t n = (int64_t)blockIdx.x * kHashThreads + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const bool valid = n < n_total;
+    const int64_t n_eff = src.count(n_total);
+    if ((int64_t)blockIdx.x * kHashThreads >= n_eff) return;  // whole CTA beyond the device-side count
+    const bool valid = n < n_eff;
     float x = 0.f, y = 0.f, z = 0.f;
     if (valid) src.get(n, x, y, z);
     const uint32_t tmask = (log2T >= 32) ? 0xffffffffu : ((1u << log2T) - 1u);

@@ -13,6 +13,7 @@ struct AdamArgs {
     int64_t n;
     float lr, beta1, beta2, eps, bc1, bc2_sqrt;
     const float *inv_scale, *found_inf;
+    const float *hyper;  // optional device [lr, 1-beta1^t, sqrt(1-beta2^t)]: per-step scalars of a replayed CUDA graph
     int64_t clamp_begin, clamp_end;
     int zero_grad;
 };
@@ -29,6 +30,11 @@ __device__ __forceinline__ void adam_one(float &p, float &g, float &m, float &v,
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
+    if (a.hyper) {
+        a.lr = __ldg(a.hyper);
+        a.bc1 = __ldg(a.hyper + 1);
+        a.bc2_sqrt = __ldg(a.hyper + 2);
+    }
     if (a.found_inf && *a.found_inf != 0.0f) {
         // GradScaler semantics: skip the step; grads are still cleared for the next iteration
         if (a.zero_grad)
@@ -84,7 +90,27 @@ extern "C" int umhs_adam_step(float *param, float *grad, float *exp_avg, float *
     a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
     a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
     a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
-    a.inv_scale = inv_scale; a.found_inf = found_inf;
+    a.inv_scale = inv_scale; a.found_inf = found_inf; a.hyper = nullptr;
+    a.clamp_begin = clamp_begin; a.clamp_end = clamp_end; a.zero_grad = zero_grad;
+    const int64_t want = (n / 4 + 255) / 256;
+    const int grid = (int)(want < kNumSMs * 8 ? (want < 1 ? 1 : want) : kNumSMs * 8);
+    adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(a);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_adam_step_dev(float *param, float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
+                                  float beta1, float beta2, float eps, const float *hyper, const float *inv_scale,
+                                  const float *found_inf, int64_t clamp_begin, int64_t clamp_end, int32_t zero_grad,
+                                  void *stream) {
+    UMHS_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && hyper, "null argument");
+    UMHS_CHECK_ARG(((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16 == 0,
+                   "buffers must be 16-byte aligned");
+    if (n <= 0) return UMHS_OK;
+    AdamArgs a;
+    a.p = param; a.g = grad; a.m = exp_avg; a.v = exp_avg_sq; a.n = n;
+    a.lr = 0.f; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.bc1 = 1.f; a.bc2_sqrt = 1.f;
+    a.inv_scale = inv_scale; a.found_inf = found_inf; a.hyper = hyper;
     a.clamp_begin = clamp_begin; a.clamp_end = clamp_end; a.zero_grad = zero_grad;
     const int64_t want = (n / 4 + 255) / 256;
     const int grid = (int)(want < kNumSMs * 8 ? (want < 1 ? 1 : want) : kNumSMs * 8);

@@ -57,10 +57,21 @@ __device__ __forceinline__ int voxel_index(float v, float fres, int res) {
 }
 
 // March one ray (twin of oracle/pack_oracle.c::march_ray).  WRITE=false only counts.
+//
+// Same fp32 operation sequence on t_last as the oracle, hence bit-exact outputs, with two shortcuts that cannot
+// change the result:
+//  * lazy empty-space skipping.  t_last walks the orbit t -> t + dt(t); in an EMPTY cell the oracle advances it to
+//    the first orbit point with t + dt/2 >= t_traverse(cell).  The thresholds grow monotonically along the ray and
+//    so does t + dt(t)/2 along the orbit, so advancing once to the LAST pending threshold lands on the same orbit
+//    point as advancing cell by cell.  The advance is therefore deferred until an occupied cell needs t_last, and
+//    never happens for the empty tail of the ray (most of the oracle's iterations);
+//  * in grid levels that hold no occupied cell (level_any[l] == 0) the DDA still runs (its fp32 thresholds are part
+//    of the orbit bookkeeping) but the occupancy bytes are not fetched.
 template <bool WRITE>
 __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *__restrict__ binaries,
-                             const float *__restrict__ aabbs, int levels, int res, float near_plane, float far_plane,
-                             float step_size, float cone_angle, float *t0_out, float *t1_out) {
+                             const float *__restrict__ aabbs, const int *__restrict__ level_any, int levels, int res,
+                             float near_plane, float far_plane, float step_size, float cone_angle, float *t0_out,
+                             float *t1_out, int64_t limit) {
     const float inv[3] = {1.0f / d[0], 1.0f / d[1], 1.0f / d[2]};
     float tmins[kMaxGridLevels], tmaxs[kMaxGridLevels], ts[2 * kMaxGridLevels];
     bool hits[kMaxGridLevels];
@@ -81,6 +92,7 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
     const int64_t cells_per_level = (int64_t)res * res * res;
     int64_t n = 0;
     float t_last = near_plane;
+    float pending = -1.0f;  // largest threshold of the empty cells skipped since t_last was last advanced (< 0: none)
     for (int i = 0; i < 2 * levels - 1; ++i) {
         const float a = ts[i], b = ts[i + 1];
         if (!(a < b)) continue;
@@ -91,6 +103,7 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
         const float this_tmin = fmaxf(a, near_plane);
         const float this_tmax = fminf(b, far_plane);
         if (!(this_tmin < this_tmax)) continue;
+        const bool lookup = (level_any == nullptr) || (level_any[level] != 0);
         const float *aabb = aabbs + 6 * level;
         const float eps = 1e-6f;
         float delta[3], tdist[3];
@@ -110,33 +123,58 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
             delta[k] = (d[k] == 0.0f) ? this_tmax : (voxel * inv[k]) * sf;
             over[k] = fin + stepi[k];
         }
+        const uint8_t *lvl_bin = binaries + (int64_t)level * cells_per_level;
+        // steps each axis may still take before it passes the interval's last cell or leaves the grid
+        int left[3];
+        for (int k = 0; k < 3; ++k) {
+            // d == 0: the oracle's `cur == over` test fires on the first selection of this axis iff fin == cur
+            if (stepi[k] == 0) { left[k] = (cur[k] == over[k]) ? 1 : 0x7fffffff; continue; }
+            const int to_over = (over[k] - cur[k]) * stepi[k];                       // >= 1 when the end is ahead
+            const int to_edge = stepi[k] > 0 ? (res - cur[k]) : (cur[k] + 1);        // steps until outside [0,res)
+            left[k] = (to_over >= 1 && to_over < to_edge) ? to_over : to_edge;
+        }
+        int cell = (cur[0] * res + cur[1]) * res + cur[2];
+        const int stride[3] = {stepi[0] * res * res, stepi[1] * res, stepi[2]};
+        float td0 = tdist[0], td1 = tdist[1], td2 = tdist[2];
+        int l0 = left[0], l1 = left[1], l2 = left[2];
+        uint8_t occ = lookup ? __ldg(lvl_bin + cell) : (uint8_t)0;
         for (int guard = 0; guard < 4 * res + 8; ++guard) {
-            float t_traverse = fminf(tdist[0], fminf(tdist[1], tdist[2]));
+            float t_traverse = fminf(td0, fminf(td1, td2));
             t_traverse = fminf(t_traverse, this_tmax);
-            const int64_t cell = (int64_t)level * cells_per_level + ((int64_t)cur[0] * res + cur[1]) * res + cur[2];
-            if (!__ldg(binaries + cell)) {
-                for (;;) {
-                    const float dt = calc_dt(t_last, cone_angle, step_size, 1e10f);
-                    if (t_last + dt * 0.5f >= t_traverse) break;
-                    t_last += dt;
-                }
+            // single DDA step: x if strictly smallest, else y if < z, else z -- taken now so that the NEXT cell's
+            // occupancy byte is in flight while this cell is processed
+            const bool ax0 = (td0 < td1) && (td0 < td2);
+            const bool ax1 = !ax0 && (td1 < td2);
+            bool last;
+            if (ax0)      { td0 += delta[0]; cell += stride[0]; last = (--l0 == 0); }
+            else if (ax1) { td1 += delta[1]; cell += stride[1]; last = (--l1 == 0); }
+            else          { td2 += delta[2]; cell += stride[2]; last = (--l2 == 0); }
+            const uint8_t occ_next = (lookup && !last) ? __ldg(lvl_bin + cell) : (uint8_t)0;
+            if (!occ) {
+                pending = t_traverse;  // monotone: later thresholds dominate earlier ones
             } else {
+                if (pending >= 0.0f) {
+                    for (;;) {
+                        const float dt = calc_dt(t_last, cone_angle, step_size, 1e10f);
+                        if (t_last + dt * 0.5f >= pending) break;
+                        t_last += dt;
+                    }
+                    pending = -1.0f;
+                }
                 for (;;) {
                     const float dt = calc_dt(t_last, cone_angle, step_size, 1e10f);
                     if (t_last + dt * 0.5f >= t_traverse) break;
-                    if (WRITE) { t0_out[n] = t_last; t1_out[n] = t_last + dt; }
+                    if (WRITE) {
+                        if (n >= limit) return n;  // capacity-truncated ray
+                        t0_out[n] = t_last;
+                        t1_out[n] = t_last + dt;
+                    }
                     ++n;
                     t_last += dt;
                 }
             }
-            int ax;
-            if (tdist[0] < tdist[1] && tdist[0] < tdist[2]) ax = 0;
-            else if (tdist[1] < tdist[2]) ax = 1;
-            else ax = 2;
-            // register-friendly update of axis `ax`
-            if (ax == 0)      { cur[0] += stepi[0]; tdist[0] += delta[0]; if (cur[0] == over[0] || cur[0] < 0 || cur[0] >= res) break; }
-            else if (ax == 1) { cur[1] += stepi[1]; tdist[1] += delta[1]; if (cur[1] == over[1] || cur[1] < 0 || cur[1] >= res) break; }
-            else              { cur[2] += stepi[2]; tdist[2] += delta[2]; if (cur[2] == over[2] || cur[2] < 0 || cur[2] >= res) break; }
+            if (last) break;
+            occ = occ_next;
         }
     }
     return n;
@@ -144,28 +182,47 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
 
 template <bool WRITE>
 __global__ void __launch_bounds__(128)
-march_kernel(umhs_march_args a, int64_t *counts, const int64_t *packed_info, int64_t *ray_indices, float *t_starts,
-             float *t_ends) {
+march_kernel(umhs_march_args a, const int *__restrict__ level_any, int64_t *counts, const int64_t *packed_info,
+             int64_t *ray_indices, float *t_starts, float *t_ends) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.n_rays) return;
     const float o[3] = {__ldg(a.rays_o + 3 * r), __ldg(a.rays_o + 3 * r + 1), __ldg(a.rays_o + 3 * r + 2)};
     const float d[3] = {__ldg(a.rays_d + 3 * r), __ldg(a.rays_d + 3 * r + 1), __ldg(a.rays_d + 3 * r + 2)};
     if (!WRITE) {
-        counts[r] = march_ray<false>(o, d, a.binaries, a.aabbs, a.levels, a.resolution, __ldg(a.near_planes + r),
-                                     __ldg(a.far_planes + r), a.step_size, a.cone_angle, nullptr, nullptr);
+        counts[r] = march_ray<false>(o, d, a.binaries, a.aabbs, level_any, a.levels, a.resolution, __ldg(a.near_planes + r),
+                                     __ldg(a.far_planes + r), a.step_size, a.cone_angle, nullptr, nullptr, 0);
     } else {
-        const int64_t off = __ldg(packed_info + 2 * r);
-        const int64_t n = march_ray<true>(o, d, a.binaries, a.aabbs, a.levels, a.resolution, __ldg(a.near_planes + r),
+        const int64_t off = __ldg(packed_info + 2 * r), lim = __ldg(packed_info + 2 * r + 1);
+        if (lim <= 0) return;
+        const int64_t n = march_ray<true>(o, d, a.binaries, a.aabbs, level_any, a.levels, a.resolution, __ldg(a.near_planes + r),
                                           __ldg(a.far_planes + r), a.step_size, a.cone_angle, t_starts + off,
-                                          t_ends + off);
+                                          t_ends + off, lim);
         for (int64_t i = 0; i < n; ++i) ray_indices[off + i] = r;
     }
+}
+
+// level_any[l] = 1 iff grid level l holds an occupied cell (8 levels max; caller zero-fills)
+__global__ void level_any_kernel(const uint8_t *__restrict__ binaries, int64_t cells_per_level, int levels,
+                                 int *__restrict__ level_any) {
+    const int l = blockIdx.y;
+    const uint4 *p = reinterpret_cast<const uint4 *>(binaries + (int64_t)l * cells_per_level);
+    const int64_t n16 = cells_per_level / 16;
+    bool any = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16 && !any; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(p + i);
+        any = (v.x | v.y | v.z | v.w) != 0u;
+    }
+    for (int64_t i = n16 * 16 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells_per_level;
+         i += (int64_t)gridDim.x * blockDim.x)
+        any = any || binaries[(int64_t)l * cells_per_level + i] != 0;
+    if (__syncthreads_or(any) && threadIdx.x == 0) atomicOr(level_any + l, 1);
 }
 
 // Single-CTA exclusive scan of int64 counts -> packed_info[r] = (offset, count); *total = sum.
 constexpr int kScanThreads = 1024;
 __global__ void __launch_bounds__(kScanThreads)
-pack_scan_kernel(const int64_t *__restrict__ counts, int64_t n, int64_t *__restrict__ packed_info, int64_t *total) {
+pack_scan_kernel(const int64_t *__restrict__ counts, int64_t n, int64_t *__restrict__ packed_info, int64_t *total,
+                 int64_t capacity) {
     __shared__ int64_t warp_sums[32];
     __shared__ int64_t base_s, tile_total_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -197,14 +254,22 @@ pack_scan_kernel(const int64_t *__restrict__ counts, int64_t n, int64_t *__restr
         __syncthreads();
         const int64_t excl = base_s + warp_sums[warp] + (incl - v);
         if (i < n) {
-            packed_info[2 * i] = excl;
-            packed_info[2 * i + 1] = v;
+            int64_t start = excl, cnt = v;
+            if (capacity > 0) {  // truncate the packing at `capacity` samples
+                start = excl < capacity ? excl : capacity;
+                cnt = (excl + v <= capacity) ? v : (capacity - start);
+            }
+            packed_info[2 * i] = start;
+            packed_info[2 * i + 1] = cnt;
         }
         __syncthreads();
         if (tid == 0) base_s += tile_total_s;
         __syncthreads();
     }
-    if (tid == 0 && total) *total = base_s;
+    if (tid == 0 && total) {
+        total[0] = (capacity > 0 && base_s > capacity) ? capacity : base_s;
+        total[1] = base_s;
+    }
 }
 
 // keep = (T >= early_stop_eps) & (alpha >= alpha_thre), one warp per ray.
@@ -242,7 +307,8 @@ visibility_kernel(const int64_t *__restrict__ packed_info, int64_t n_rays, const
 __global__ void __launch_bounds__(kVisWarps * 32)
 compact_kernel(const int64_t *__restrict__ pin, const int64_t *__restrict__ pout, int64_t n_rays,
                const uint8_t *__restrict__ keep, const float *__restrict__ t0_in, const float *__restrict__ t1_in,
-               int64_t *__restrict__ ray_indices, float *__restrict__ t0, float *__restrict__ t1) {
+               int64_t *__restrict__ ray_indices, float *__restrict__ t0, float *__restrict__ t1,
+               int32_t *__restrict__ src_index) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * kVisWarps + (threadIdx.x >> 5);
     if (r >= n_rays) return;
@@ -257,6 +323,7 @@ compact_kernel(const int64_t *__restrict__ pin, const int64_t *__restrict__ pout
             ray_indices[j] = r;
             t0[j] = t0_in[n];
             t1[j] = t1_in[n];
+            if (src_index) src_index[j] = (int32_t)n;
         }
         dst += __popc(m);
     }
@@ -338,20 +405,29 @@ static int check_march(const umhs_march_args *a) {
 
 using namespace umhs;
 
+extern "C" int umhs_march_level_any(const umhs_march_args *a, int32_t *level_any, void *stream) {
+    UMHS_CHECK_ARG(check_march(a) == 0 && level_any, "bad march arguments");
+    const int64_t cells = (int64_t)a->resolution * a->resolution * a->resolution;
+    UMHS_CHECK_CUDA(cudaMemsetAsync(level_any, 0, sizeof(int32_t) * 8, as_stream(stream)));
+    level_any_kernel<<<dim3(64, a->levels), 256, 0, as_stream(stream)>>>(a->binaries, cells, a->levels, level_any);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
 extern "C" int umhs_march_count(const umhs_march_args *a, int64_t *counts, void *stream) {
     UMHS_CHECK_ARG(check_march(a) == 0 && counts, "bad march arguments");
     if (a->n_rays <= 0) return UMHS_OK;
-    march_kernel<false><<<div_up(a->n_rays, 128), 128, 0, as_stream(stream)>>>(*a, counts, nullptr, nullptr, nullptr,
-                                                                               nullptr);
+    march_kernel<false><<<div_up(a->n_rays, 64), 64, 0, as_stream(stream)>>>(*a, a->level_any, counts, nullptr, nullptr,
+                                                                             nullptr, nullptr);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }
 
 extern "C" int umhs_pack_scan(const int64_t *counts, int64_t n_rays, int64_t *packed_info, int64_t *total,
-                              void *stream) {
+                              int64_t capacity, void *stream) {
     UMHS_CHECK_ARG(counts && packed_info, "null argument");
     UMHS_CHECK_ARG(n_rays >= 0, "negative n_rays");
-    pack_scan_kernel<<<1, kScanThreads, 0, as_stream(stream)>>>(counts, n_rays, packed_info, total);
+    pack_scan_kernel<<<1, kScanThreads, 0, as_stream(stream)>>>(counts, n_rays, packed_info, total, capacity);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }
@@ -360,8 +436,8 @@ extern "C" int umhs_march_write(const umhs_march_args *a, const int64_t *packed_
                                 float *t_starts, float *t_ends, void *stream) {
     UMHS_CHECK_ARG(check_march(a) == 0 && packed_info && ray_indices && t_starts && t_ends, "bad march arguments");
     if (a->n_rays <= 0) return UMHS_OK;
-    march_kernel<true><<<div_up(a->n_rays, 128), 128, 0, as_stream(stream)>>>(*a, nullptr, packed_info, ray_indices,
-                                                                              t_starts, t_ends);
+    march_kernel<true><<<div_up(a->n_rays, 64), 64, 0, as_stream(stream)>>>(*a, a->level_any, nullptr, packed_info,
+                                                                            ray_indices, t_starts, t_ends);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }
@@ -379,13 +455,14 @@ extern "C" int umhs_visibility_mask(const int64_t *packed_info, int64_t n_rays, 
 
 extern "C" int umhs_compact_samples(const int64_t *packed_info_in, const int64_t *packed_info_out, int64_t n_rays,
                                     const uint8_t *keep, const float *t_starts_in, const float *t_ends_in,
-                                    int64_t *ray_indices, float *t_starts, float *t_ends, void *stream) {
+                                    int64_t *ray_indices, float *t_starts, float *t_ends, int32_t *src_index,
+                                    void *stream) {
     UMHS_CHECK_ARG(packed_info_in && packed_info_out && keep && t_starts_in && t_ends_in && ray_indices && t_starts &&
                        t_ends,
                    "null argument");
     if (n_rays <= 0) return UMHS_OK;
     compact_kernel<<<div_up(n_rays, kVisWarps), kVisWarps * 32, 0, as_stream(stream)>>>(
-        packed_info_in, packed_info_out, n_rays, keep, t_starts_in, t_ends_in, ray_indices, t_starts, t_ends);
+        packed_info_in, packed_info_out, n_rays, keep, t_starts_in, t_ends_in, ray_indices, t_starts, t_ends, src_index);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }
@@ -401,7 +478,7 @@ extern "C" int umhs_pack_info(const int64_t *ray_indices, int64_t n, int64_t n_r
                                                          reinterpret_cast<unsigned long long *>(counts));
         UMHS_CHECK_LAUNCH();
     }
-    pack_scan_kernel<<<1, kScanThreads, 0, st>>>(counts, n_rays, packed_info, nullptr);
+    pack_scan_kernel<<<1, kScanThreads, 0, st>>>(counts, n_rays, packed_info, nullptr, 0);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }

@@ -145,17 +145,24 @@ __device__ __forceinline__ void load8(const uint8_t *buf, int row, int c0, int c
     }
 }
 
+// The descriptors of consecutive K steps differ only in the 14-bit start-address field (bits 0..13, units of
+// 16 bytes; operand tiles live below 256 KB so the field never carries): they are built once per GEMM and advanced
+// with one 32-bit add each -- the single issuing thread is the critical path of every MMA round.
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+
 // D[128 x N] (+)= A[128 x K] * B[N x K]^T, both operands K-major tiles.
 //   a: tile of 128 rows (CH = 2048); b: tile of `b_rows` rows (CH = b_rows*16), rows [b_row0, b_row0+N) used.
 __device__ __forceinline__ void gemm_kmajor(uint32_t d_tmem, uint32_t a_saddr, uint32_t b_saddr, int b_rows, int b_row0,
                                             int N, int K, uint32_t accumulate) {
     const uint32_t idesc = make_idesc(128, N, 0, 0);
     const uint32_t a_ch = 2048, b_ch = (uint32_t)b_rows * 16;
-    const uint32_t b0 = b_saddr + (uint32_t)(b_row0 >> 3) * 128;
+    uint64_t ad = make_desc(a_saddr, a_ch, 128);
+    uint64_t bd = make_desc(b_saddr + (uint32_t)(b_row0 >> 3) * 128, b_ch, 128);
+#pragma unroll 1
     for (int k = 0; k < K; k += 16) {
-        const uint64_t ad = make_desc(a_saddr + (uint32_t)(k >> 3) * a_ch, a_ch, 128);
-        const uint64_t bd = make_desc(b0 + (uint32_t)(k >> 3) * b_ch, b_ch, 128);
         mma_ss(d_tmem, ad, bd, idesc, (k > 0) ? 1u : accumulate);
+        ad = desc_advance(ad, 2 * a_ch);
+        bd = desc_advance(bd, 2 * b_ch);
     }
 }
 
@@ -165,12 +172,14 @@ __device__ __forceinline__ void gemm_dgrad(uint32_t d_tmem, uint32_t a_saddr, ui
                                            int N, int K, uint32_t accumulate) {
     const uint32_t idesc = make_idesc(128, N, 0, 1);
     const uint32_t a_ch = 2048, w_ch = (uint32_t)w_rows * 16;
-    const uint32_t w0 = w_saddr + (uint32_t)(w_row0 >> 3) * 128;
+    uint64_t ad = make_desc(a_saddr, a_ch, 128);
+    // MN-major: SBO = stride between 8-wide MN chunks (= w_ch), LBO = stride between 8-deep K groups (= 128)
+    uint64_t bd = make_desc(w_saddr + (uint32_t)(w_row0 >> 3) * 128, 128, w_ch);
+#pragma unroll 1
     for (int k = 0; k < K; k += 16) {
-        const uint64_t ad = make_desc(a_saddr + (uint32_t)(k >> 3) * a_ch, a_ch, 128);
-        // MN-major: SBO = stride between 8-wide MN chunks (= w_ch), LBO = stride between 8-deep K groups (= 128)
-        const uint64_t bd = make_desc(w0 + (uint32_t)(k >> 3) * 128, 128, w_ch);
         mma_ss(d_tmem, ad, bd, idesc, (k > 0) ? 1u : accumulate);
+        ad = desc_advance(ad, 2 * a_ch);
+        bd = desc_advance(bd, 256);
     }
 }
 
@@ -180,12 +189,34 @@ __device__ __forceinline__ void gemm_wgrad(uint32_t d_tmem, uint32_t p_saddr, in
                                            int N, uint32_t accumulate) {
     const uint32_t idesc = make_idesc(64, N, 1, 1);
     const uint32_t ch = 2048;
-    const uint32_t p0 = p_saddr + (uint32_t)(p_col0 >> 3) * ch, q0 = q_saddr + (uint32_t)(q_col0 >> 3) * ch;
+    uint64_t ad = make_desc(p_saddr + (uint32_t)(p_col0 >> 3) * ch, 128, ch);
+    uint64_t bd = make_desc(q_saddr + (uint32_t)(q_col0 >> 3) * ch, 128, ch);
+#pragma unroll
     for (int s = 0; s < 128; s += 16) {
-        const uint64_t ad = make_desc(p0 + (uint32_t)(s >> 3) * 128, 128, ch);
-        const uint64_t bd = make_desc(q0 + (uint32_t)(s >> 3) * 128, 128, ch);
         mma_ss(d_tmem, ad, bd, idesc, (s > 0) ? 1u : accumulate);
+        ad = desc_advance(ad, 256);
+        bd = desc_advance(bd, 256);
     }
+}
+
+// ---- TMEM -> registers, 64 consecutive columns with a single wait (four loads in flight)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+    uint32_t r[64];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[16 * q + 0]), "=r"(r[16 * q + 1]), "=r"(r[16 * q + 2]), "=r"(r[16 * q + 3]),
+              "=r"(r[16 * q + 4]), "=r"(r[16 * q + 5]), "=r"(r[16 * q + 6]), "=r"(r[16 * q + 7]),
+              "=r"(r[16 * q + 8]), "=r"(r[16 * q + 9]), "=r"(r[16 * q + 10]), "=r"(r[16 * q + 11]),
+              "=r"(r[16 * q + 12]), "=r"(r[16 * q + 13]), "=r"(r[16 * q + 14]), "=r"(r[16 * q + 15])
+            : "r"(taddr + 16u * q)
+            : "memory");
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 }  // namespace tc05

@@ -23,7 +23,7 @@ class UmhsError(RuntimeError):
 
 class Points(Structure):
     _fields_ = [("positions", P), ("directions", P), ("rays_o", P), ("rays_d", P), ("ray_indices", P),
-                ("t_starts", P), ("t_ends", P), ("contraction", c_int32), ("aabb", c_float * 6)]
+                ("t_starts", P), ("t_ends", P), ("contraction", c_int32), ("aabb", c_float * 6), ("enc_index", P), ("n_dev", P)]
 
 
 class HashGrid(Structure):
@@ -77,7 +77,7 @@ class CompositeGradsOut(Structure):
 class MarchArgs(Structure):
     _fields_ = [("rays_o", P), ("rays_d", P), ("near_planes", P), ("far_planes", P), ("binaries", P), ("aabbs", P),
                 ("levels", c_int32), ("resolution", c_int32), ("step_size", c_float), ("cone_angle", c_float),
-                ("n_rays", c_int64)]
+                ("n_rays", c_int64), ("level_any", P)]
 
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
@@ -96,6 +96,7 @@ _SIGNATURES = {
     "umhs_field_mlp_tc_fwd": [POINTER(Points), c_int64, P, POINTER(MlpParams), POINTER(FieldOut), P],
     "umhs_field_mlp_tc_bwd": [POINTER(Points), c_int64, P, POINTER(MlpParams), POINTER(FieldOutGrads), P,
                               POINTER(MlpGrads), P],
+    "umhs_debug_trace": [P, c_int32, P],
     "umhs_tc05_selftest": [c_int32, P, P, P, c_int32, c_int32, P],
     "umhs_composite_fwd": [POINTER(CompositeIn), POINTER(CompositeOut), P],
     "umhs_depth_clip": [P, c_int64, P, P],
@@ -106,17 +107,19 @@ _SIGNATURES = {
     "umhs_render_weights_bwd": [P, c_int64, P, P, P, P, P, P, P],
     "umhs_accumulate_fwd": [P, P, P, c_int64, c_int32, P, P],
     "umhs_accumulate_bwd": [P, P, P, c_int64, c_int32, P, P, P, P],
+    "umhs_march_level_any": [POINTER(MarchArgs), P, P],
     "umhs_march_count": [POINTER(MarchArgs), P, P],
-    "umhs_pack_scan": [P, c_int64, P, P, P],
+    "umhs_pack_scan": [P, c_int64, P, P, c_int64, P],
     "umhs_march_write": [POINTER(MarchArgs), P, P, P, P, P],
     "umhs_visibility_mask": [P, c_int64, P, P, P, c_float, c_float, P, P, P, P],
-    "umhs_compact_samples": [P, P, c_int64, P, P, P, P, P, P, P],
+    "umhs_compact_samples": [P, P, c_int64, P, P, P, P, P, P, P, P],
     "umhs_pack_info": [P, c_int64, c_int64, P, P, P],
     "umhs_occ_cell_points": [P, P, c_int64, c_int32, P, P, P],
     "umhs_occ_ema_update": [P, P, c_int64, P, c_float, c_float, c_int64, P, P],
     "umhs_occ_binarize": [P, c_int64, c_float, P, P, P, P],
     "umhs_adam_step": [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int32, P, P, c_int64, c_int64,
                        c_int32, P],
+    "umhs_adam_step_dev": [P, P, P, P, c_int64, c_float, c_float, c_float, P, P, P, c_int64, c_int64, c_int32, P],
     "umhs_reduce_slabs": [P, c_int64, c_int64, c_int64, P, P],
 }
 _RESTYPES = {"umhs_last_error": c_char_p}

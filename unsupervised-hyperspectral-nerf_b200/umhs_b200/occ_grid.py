@@ -52,7 +52,7 @@ class OccGridEstimator(nn.Module):
                  far_plane: float = 1e10, t_min: Optional[Tensor] = None, t_max: Optional[Tensor] = None,
                  render_step_size: float = 1e-3, early_stop_eps: float = 1e-4, alpha_thre: float = 0.0,
                  stratified: bool = False, cone_angle: float = 0.0, jitter: Optional[Tensor] = None,
-                 return_packed_info: bool = False):
+                 return_packed_info: bool = False, capacity: Optional[int] = None):
         """-> (ray_indices int64 [N], t_starts [N], t_ends [N]) (+ packed_info [R,2]).  ``sigma_fn(t_starts, t_ends,
         ray_indices) -> sigma [N]`` enables the visibility filter, as in nerfacc.  ``jitter`` injects the stratified
         draw (nerfacc: ``torch.rand_like(near_planes)``) so parity tests see identical near planes."""
@@ -66,14 +66,20 @@ class OccGridEstimator(nn.Module):
             if jitter is None:
                 jitter = torch.rand_like(near)
             near = near + jitter * render_step_size
-        ri, t0, t1, packed = ops.march(rays_o, rays_d, near, far, self.binaries, self.aabbs, render_step_size,
-                                       cone_angle)
+        ri, t0, t1, packed, total = ops.march(rays_o, rays_d, near, far, self.binaries, self.aabbs, render_step_size,
+                                              cone_angle, capacity=capacity)
+        march_total = total
+        self.last_src_index = None
         if (alpha_thre > 0.0 or early_stop_eps > 0.0) and sigma_fn is not None and t0.shape[0] > 0:
-            sigma = sigma_fn(t0, t1, ri)
-            ri, t0, t1, packed = ops.visibility_compact(packed, t0, t1, sigma, early_stop_eps, alpha_thre,
-                                                        self.occ_mean() if alpha_thre > 0.0 else None)
+            # nerfacc's sigma_fn(t_starts, t_ends, ray_indices); the sync-free path also hands over the device count
+            sigma = sigma_fn(t0, t1, ri) if capacity is None else sigma_fn(t0, t1, ri, total)
+            march_total = total
+            ri, t0, t1, packed, total, self.last_src_index = ops.visibility_compact(
+                packed, t0, t1, sigma, early_stop_eps, alpha_thre, self.occ_mean() if alpha_thre > 0.0 else None,
+                capacity=capacity)
+        self.last_totals = (march_total, total)  # device int64[2] each: (packed, unclamped) candidates / kept
         if return_packed_info:
-            return ri, t0, t1, packed
+            return ri, t0, t1, packed, total
         return ri, t0, t1
 
     # ------------------------------------------------------------------ update (A.4)
@@ -139,7 +145,10 @@ class VolumetricSampler(nn.Module):
 
     @torch.no_grad()
     def forward(self, ray_bundle, render_step_size: float, near_plane: float = 0.0, far_plane: Optional[float] = None,
-                alpha_thre: float = 0.01, cone_angle: float = 0.0, jitter: Optional[Tensor] = None):
+                alpha_thre: float = 0.01, cone_angle: float = 0.0, jitter: Optional[Tensor] = None,
+                capacity: Optional[int] = None):
+        """capacity=None: exact-sized packed samples (one host sync per march / compaction, like the reference).
+        capacity=C: sync-free; buffers hold C samples, ``pts.n_dev`` carries the valid count on the device."""
         field = self._field[0]
         rays_o = ray_bundle.origins.reshape(-1, 3).to(torch.float32).contiguous()
         rays_d = ray_bundle.directions.reshape(-1, 3).to(torch.float32).contiguous()
@@ -150,20 +159,26 @@ class VolumetricSampler(nn.Module):
         if far_plane is None:
             far_plane = 1e10
         sigma_fn = None
+        cand_enc = [None]  # hash encodings of the candidate samples (kept samples reuse them)
         if self.training:  # nerfstudio builds sigma_fn only while training
-            def sigma_fn(t0, t1, ri):
+            def sigma_fn(t0, t1, ri, n_dev=None):
                 pts = PointSet.from_packed(rays_o, rays_d, ri, t0, t1, contraction=field.contraction,
-                                           aabb=field._aabb6())
-                return field.density_packed(pts)
-        ri, t0, t1, packed = self.occupancy_grid.sampling(
+                                           aabb=field._aabb6(), n_dev=n_dev)
+                sigma, cand_enc[0] = field.density_packed(pts, return_enc=True)
+                return sigma
+        ri, t0, t1, packed, total = self.occupancy_grid.sampling(
             rays_o, rays_d, sigma_fn=sigma_fn, near_plane=near_plane, far_plane=far_plane, t_min=t_min, t_max=t_max,
             render_step_size=render_step_size, stratified=self.training, cone_angle=cone_angle, alpha_thre=alpha_thre,
-            jitter=jitter, return_packed_info=True)
-        if t0.shape[0] == 0:  # nerfstudio fabricates one sample so downstream shapes are never empty
+            jitter=jitter, return_packed_info=True, capacity=capacity)
+        if capacity is None and t0.shape[0] == 0:  # nerfstudio fabricates one sample so shapes are never empty
             dev = rays_o.device
             ri = torch.zeros((1,), dtype=torch.int64, device=dev)
             t0 = torch.ones((1,), dtype=torch.float32, device=dev)
             t1 = torch.ones((1,), dtype=torch.float32, device=dev)
             packed = ops.pack_info(ri, rays_o.shape[0])
-        pts = PointSet.from_packed(rays_o, rays_d, ri, t0, t1, contraction=field.contraction, aabb=field._aabb6())
+        pts = PointSet.from_packed(rays_o, rays_d, ri, t0, t1, contraction=field.contraction, aabb=field._aabb6(),
+                                   n_dev=total if capacity is not None else None)
+        src = self.occupancy_grid.last_src_index
+        if cand_enc[0] is not None and src is not None and src.shape[0] == t0.shape[0]:
+            pts.enc_src, pts.enc_index = cand_enc[0], src
         return pts, ri, t0, t1, packed

@@ -22,10 +22,10 @@ _LAUNCHES = {"umhs_hash_encode_fwd": 1, "umhs_hash_encode_bwd": 1, "umhs_hash_en
              "umhs_hash_encode_x01_bwd": 1, "umhs_density_fwd": 1, "umhs_field_mlp_fwd": 1, "umhs_field_mlp_bwd": 1,
              "umhs_composite_fwd": 1, "umhs_depth_clip": 1, "umhs_composite_bwd": 1, "umhs_unmix_fwd": 1,
              "umhs_unmix_bwd": 1, "umhs_render_weights_fwd": 1, "umhs_render_weights_bwd": 1,
-             "umhs_accumulate_fwd": 1, "umhs_accumulate_bwd": 1, "umhs_march_count": 1, "umhs_pack_scan": 1,
+             "umhs_accumulate_fwd": 1, "umhs_accumulate_bwd": 1, "umhs_march_count": 1, "umhs_march_level_any": 1, "umhs_pack_scan": 1,
              "umhs_march_write": 1, "umhs_visibility_mask": 1, "umhs_compact_samples": 1, "umhs_pack_info": 2,
              "umhs_occ_cell_points": 1, "umhs_occ_ema_update": 2, "umhs_occ_binarize": 2, "umhs_adam_step": 1,
-             "umhs_reduce_slabs": 1, "umhs_density_tc_fwd": 1, "umhs_field_mlp_tc_fwd": 1, "umhs_field_mlp_tc_bwd": 1,
+             "umhs_reduce_slabs": 1, "umhs_adam_step_dev": 1, "umhs_density_tc_fwd": 1, "umhs_field_mlp_tc_fwd": 1, "umhs_field_mlp_tc_bwd": 1,
              "umhs_tc05_selftest": 1}
 
 # "bf16": tensor-core MLP kernels (tcgen05 + TMEM, bf16 operands, fp32 accumulate) -- the default.
@@ -51,7 +51,7 @@ class Profiler:
             d = out.setdefault(name, {"calls": 0, "ms": 0.0, "units": 0})
             d["calls"] += 1
             d["ms"] += a.elapsed_time(b)
-            d["units"] += units
+            d["units"] += int(units.reshape(-1)[0].item()) if isinstance(units, Tensor) else int(units)
         return out
 
 
@@ -65,7 +65,7 @@ def _call(name: str, units: int, *args) -> None:
             a.record()
             rc = fn(*args)
             b.record()
-            Profiler.records.append((name, a, b, int(units)))
+            Profiler.records.append((name, a, b, units))
             check(rc, name)
             return
     check(fn(*args), name)
@@ -100,6 +100,12 @@ class PointSet:
     t_ends: Optional[Tensor] = None
     contraction: bool = True
     aabb: Sequence[float] = (-1.0, -1.0, -1.0, 1.0, 1.0, 1.0)
+    # optional device-side count (int64[>=1]): kernels process min(n, n_dev[0]) points; n is then a capacity
+    n_dev: Optional[Tensor] = None
+    # optional reuse of encodings computed for a superset of these points (the sampler's candidate pass):
+    # enc_src [M, 32] and enc_index int32 [n] with enc(point i) = enc_src[enc_index[i]]
+    enc_src: Optional[Tensor] = None
+    enc_index: Optional[Tensor] = None
 
     def struct(self) -> _lib.Points:
         s = _lib.Points()
@@ -111,6 +117,8 @@ class PointSet:
         s.t_starts = ptr(self.t_starts)
         s.t_ends = ptr(self.t_ends)
         s.contraction = 1 if self.contraction else 0
+        s.n_dev = ptr(self.n_dev)
+        s.enc_index = ptr(self.enc_index) if self.enc_src is not None else None
         for i, v in enumerate(self.aabb):
             s.aabb[i] = float(v)
         return s
@@ -127,11 +135,15 @@ class PointSet:
                         aabb=tuple(aabb) if aabb is not None else PointSet.aabb)
 
     @staticmethod
-    def from_packed(rays_o, rays_d, ray_indices, t_starts, t_ends, contraction=True, aabb=None):
+    def from_packed(rays_o, rays_d, ray_indices, t_starts, t_ends, contraction=True, aabb=None, n_dev=None):
         return PointSet(n=int(t_starts.shape[0]), rays_o=f32(rays_o), rays_d=f32(rays_d),
                         ray_indices=ray_indices.to(torch.int64).contiguous(), t_starts=f32(t_starts).reshape(-1),
                         t_ends=f32(t_ends).reshape(-1), contraction=contraction,
-                        aabb=tuple(aabb) if aabb is not None else PointSet.aabb)
+                        aabb=tuple(aabb) if aabb is not None else PointSet.aabb, n_dev=n_dev)
+
+    def units(self):
+        """What the profiler should count as processed points (resolved after the timed region)."""
+        return self.n_dev if self.n_dev is not None else self.n
 
 
 def _grid_struct(table: Tensor, scalings: Tensor, log2_T: int) -> _lib.HashGrid:
@@ -149,7 +161,7 @@ def hash_encode_fwd(pts: PointSet, table: Tensor, scalings: Tensor, log2_T: int)
     L = int(scalings.shape[0])
     enc = torch.empty((pts.n, 2 * L), dtype=torch.float32, device=table.device)
     ps, gs = pts.struct(), _grid_struct(table, scalings, log2_T)
-    _call("umhs_hash_encode_fwd", pts.n, ctypes.byref(ps), pts.n, ctypes.byref(gs), ptr(enc), stream_ptr(table.device))
+    _call("umhs_hash_encode_fwd", pts.units(), ctypes.byref(ps), pts.n, ctypes.byref(gs), ptr(enc), stream_ptr(table.device))
     return enc
 
 
@@ -160,7 +172,7 @@ def hash_encode_bwd(pts: PointSet, table: Tensor, scalings: Tensor, log2_T: int,
     if d_table is None:
         d_table = torch.zeros_like(table, dtype=torch.float32)
     ps, gs = pts.struct(), _grid_struct(table, scalings, log2_T)
-    _call("umhs_hash_encode_bwd", pts.n, ctypes.byref(ps), pts.n, ctypes.byref(gs), ptr(d_enc), ptr(d_table),
+    _call("umhs_hash_encode_bwd", pts.units(), ctypes.byref(ps), pts.n, ctypes.byref(gs), ptr(d_enc), ptr(d_table),
                                    stream_ptr(table.device))
     return d_table
 
@@ -218,7 +230,7 @@ def density_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor]) -> Tenso
     lib = _lib.load()
     sigma = torch.empty((pts.n,), dtype=torch.float32, device=enc.device)
     ps, ms = pts.struct(), mlp_struct(weights, 1, False, 1.0)
-    _call("umhs_density_tc_fwd" if MLP_PRECISION == "bf16" else "umhs_density_fwd", pts.n, ctypes.byref(ps), pts.n, ptr(enc), ctypes.byref(ms), ptr(sigma),
+    _call("umhs_density_tc_fwd" if MLP_PRECISION == "bf16" else "umhs_density_fwd", pts.units(), ctypes.byref(ps), pts.n, ptr(enc), ctypes.byref(ms), ptr(sigma),
                                stream_ptr(enc.device))
     return sigma
 
@@ -237,7 +249,7 @@ def field_mlp_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int
     for k, v in out.items():
         setattr(fo, k, ptr(v))
     ps, ms = pts.struct(), mlp_struct(weights, K, specular, temperature)
-    _call("umhs_field_mlp_tc_fwd" if MLP_PRECISION == "bf16" else "umhs_field_mlp_fwd", n, ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(fo), stream_ptr(dev))
+    _call("umhs_field_mlp_tc_fwd" if MLP_PRECISION == "bf16" else "umhs_field_mlp_fwd", pts.units(), ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(fo), stream_ptr(dev))
     return out
 
 
@@ -257,7 +269,7 @@ def field_mlp_bwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int
     for name in MLP_NAMES:
         setattr(dp, name, ptr(d_weights.get(name)))
     ps, ms = pts.struct(), mlp_struct(weights, K, specular, temperature)
-    _call("umhs_field_mlp_tc_bwd" if MLP_PRECISION == "bf16" else "umhs_field_mlp_bwd", n, ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(g), ptr(d_enc),
+    _call("umhs_field_mlp_tc_bwd" if MLP_PRECISION == "bf16" else "umhs_field_mlp_bwd", pts.units(), ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(g), ptr(d_enc),
                                  ctypes.byref(dp), stream_ptr(dev))
     return d_enc, d_weights
 
@@ -270,7 +282,8 @@ class FieldFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pts: PointSet, cfg: dict, table: Tensor, scalings: Tensor, *mlp: Optional[Tensor]):
         weights = {n: (w.detach() if w is not None else None) for n, w in zip(MLP_NAMES, mlp)}
-        enc = hash_encode_fwd(pts, table.detach(), scalings, cfg["log2_T"])
+        # kept samples are a subset of the sampler's candidates: reuse their encodings when the sampler kept them
+        enc = pts.enc_src if pts.enc_src is not None else hash_encode_fwd(pts, table.detach(), scalings, cfg["log2_T"])
         out = field_mlp_fwd(pts, enc, weights, cfg["K"], cfg["specular"], cfg["temperature"])
         ctx.pts, ctx.cfg = pts, cfg
         ctx.n_mlp = len(mlp)
@@ -326,6 +339,16 @@ def _composite_in(R, N, K, B, specular, grad_scaling, packed_info, t0, t1, sigma
     return ci
 
 
+_TMM_INIT: Dict[torch.device, Tensor] = {}
+
+
+def _tminmax_init(dev) -> Tensor:
+    t = _TMM_INIT.get(dev)
+    if t is None:
+        t = _TMM_INIT[dev] = torch.tensor([float("inf"), float("-inf")], dtype=torch.float32, device=dev)
+    return t
+
+
 COMPOSITE_OUTPUTS = ("spectral", "spectral2", "specular", "abundances", "accumulation", "depth", "rgb", "seg_probs",
                      "seg_raw", "seg_pred", "weights")
 
@@ -354,7 +377,7 @@ class CompositeFunction(torch.autograd.Function):
                "specular": z(R, B) if specular else None, "abundances": z(R, K), "accumulation": z(R),
                "depth": z(R), "rgb": z(R, 3), "seg_probs": z(R, K), "seg_raw": z(R), "seg_pred": z(R, 3),
                "weights": z(N) if cfg.get("want_weights", False) else None}
-        tmm = torch.tensor([float("inf"), float("-inf")], dtype=torch.float32, device=dev)
+        tmm = _tminmax_init(dev).clone()  # (+inf, -inf) without a host->device copy per call
         co = _lib.CompositeOut()
         for k, v in out.items():
             setattr(co, k, ptr(v))
@@ -512,10 +535,12 @@ class AccumulateFunction(torch.autograd.Function):
 
 # --------------------------------------------------------------------------------------- packing
 def march(rays_o: Tensor, rays_d: Tensor, near_planes: Tensor, far_planes: Tensor, binaries: Tensor, aabbs: Tensor,
-          step_size: float, cone_angle: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """Occupancy-grid ray marching (nerfacc traverse_grids).  -> (ray_indices, t_starts, t_ends, packed_info).
-    One host sync (the sample count sizes the output buffers), as in the reference."""
-    lib = _lib.load()
+          step_size: float, cone_angle: float, capacity: Optional[int] = None):
+    """Occupancy-grid ray marching (nerfacc traverse_grids).  -> (ray_indices, t_starts, t_ends, packed_info, total).
+
+    capacity=None: exact-sized outputs, one host sync on the sample count (as the reference does).
+    capacity=C:    no host sync; outputs hold C entries of which the first total[0] (device int64) are valid, the
+                   packing is truncated at C samples and total[1] keeps the unclamped count for a later check."""
     dev = rays_o.device
     R = int(rays_o.shape[0])
     a = _lib.MarchArgs()
@@ -528,41 +553,46 @@ def march(rays_o: Tensor, rays_d: Tensor, near_planes: Tensor, far_planes: Tenso
     a.step_size, a.cone_angle, a.n_rays = float(step_size), float(cone_angle), R
     counts = torch.empty((R,), dtype=torch.int64, device=dev)
     packed = torch.empty((R, 2), dtype=torch.int64, device=dev)
-    total = torch.zeros((1,), dtype=torch.int64, device=dev)
+    total = torch.zeros((2,), dtype=torch.int64, device=dev)
     st = stream_ptr(dev)
+    level_any = torch.empty((8,), dtype=torch.int32, device=dev)
+    a.level_any = None
+    _call("umhs_march_level_any", 0, ctypes.byref(a), ptr(level_any), st)
+    a.level_any = ptr(level_any)
     _call("umhs_march_count", R, ctypes.byref(a), ptr(counts), st)
-    _call("umhs_pack_scan", R, ptr(counts), R, ptr(packed), ptr(total), st)
-    N = int(total.item())
+    _call("umhs_pack_scan", R, ptr(counts), R, ptr(packed), ptr(total), int(capacity or 0), st)
+    N = int(total[0].item()) if capacity is None else int(capacity)
     ri = torch.empty((N,), dtype=torch.int64, device=dev)
     t0 = torch.empty((N,), dtype=torch.float32, device=dev)
     t1 = torch.empty((N,), dtype=torch.float32, device=dev)
     if N > 0:
         _call("umhs_march_write", R, ctypes.byref(a), ptr(packed), ptr(ri), ptr(t0), ptr(t1), st)
-    return ri, t0, t1, packed
+    return ri, t0, t1, packed, total
 
 
 def visibility_compact(packed_info: Tensor, t0: Tensor, t1: Tensor, sigma: Tensor, early_stop_eps: float,
-                       alpha_thre: float, occ_mean: Optional[Tensor] = None):
-    """render_visibility_from_density + boolean-mask compaction.  -> (ray_indices, t0, t1, packed_info)."""
-    lib = _lib.load()
+                       alpha_thre: float, occ_mean: Optional[Tensor] = None, capacity: Optional[int] = None):
+    """render_visibility_from_density + boolean-mask compaction.  -> (ray_indices, t0, t1, packed_info, total).
+    capacity: see ``march`` (no host sync; outputs sized `capacity`, total[0] valid entries)."""
     dev = t0.device
     R, N = int(packed_info.shape[0]), int(t0.shape[0])
     keep = torch.empty((N,), dtype=torch.uint8, device=dev)
     kc = torch.empty((R,), dtype=torch.int64, device=dev)
     packed2 = torch.empty((R, 2), dtype=torch.int64, device=dev)
-    total = torch.zeros((1,), dtype=torch.int64, device=dev)
+    total = torch.zeros((2,), dtype=torch.int64, device=dev)
     st = stream_ptr(dev)
     _call("umhs_visibility_mask", R, ptr(packed_info), R, ptr(t0), ptr(t1), ptr(f32(sigma).reshape(-1)),
-                                   float(early_stop_eps), float(alpha_thre), ptr(occ_mean), ptr(keep), ptr(kc), st)
-    _call("umhs_pack_scan", R, ptr(kc), R, ptr(packed2), ptr(total), st)
-    M = int(total.item())
+          float(early_stop_eps), float(alpha_thre), ptr(occ_mean), ptr(keep), ptr(kc), st)
+    _call("umhs_pack_scan", R, ptr(kc), R, ptr(packed2), ptr(total), 0, st)
+    M = int(total[0].item()) if capacity is None else int(capacity)
     ri = torch.empty((M,), dtype=torch.int64, device=dev)
     o0 = torch.empty((M,), dtype=torch.float32, device=dev)
     o1 = torch.empty((M,), dtype=torch.float32, device=dev)
+    src = torch.empty((M,), dtype=torch.int32, device=dev)
     if M > 0:
         _call("umhs_compact_samples", R, ptr(packed_info), ptr(packed2), R, ptr(keep), ptr(t0), ptr(t1), ptr(ri),
-                                       ptr(o0), ptr(o1), st)
-    return ri, o0, o1, packed2
+              ptr(o0), ptr(o1), ptr(src), st)
+    return ri, o0, o1, packed2, total, src
 
 
 # --------------------------------------------------------------------------------------- optimiser
@@ -573,6 +603,15 @@ def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, 
     _call("umhs_adam_step", param.numel(), ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1, beta2,
                              eps, step, ptr(inv_scale), ptr(found_inf), clamp_range[0], clamp_range[1],
                              1 if zero_grad else 0, stream_ptr(param.device))
+
+
+def adam_step_dev(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, beta1: float, beta2: float,
+                  eps: float, hyper: Tensor, inv_scale: Optional[Tensor] = None,
+                  clamp_range: Tuple[int, int] = (0, 0), zero_grad: bool = True) -> None:
+    """Adam step whose lr / bias corrections come from the device tensor hyper = [lr, 1-b1^t, sqrt(1-b2^t)]."""
+    _call("umhs_adam_step_dev", param.numel(), ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(),
+          beta1, beta2, eps, ptr(hyper), ptr(inv_scale), None, clamp_range[0], clamp_range[1], 1 if zero_grad else 0,
+          stream_ptr(param.device))
 
 
 def tc05_selftest(mode: int, A: Tensor, B: Tensor, N: int, K: int) -> Tensor:

@@ -80,7 +80,8 @@ class FlatParams:
 class UMHSTrainer:
     def __init__(self, model: UMHSModel, lr: float = 2e-2, eps: float = 1e-15, betas=(0.9, 0.999),
                  lr_final: float = 1e-5, max_steps: int = 30000, world_size: int = 1, rank: int = 0,
-                 occ_update: bool = True, freeze_binaries: bool = False, start_step: int = 0):
+                 occ_update: bool = True, freeze_binaries: bool = False, start_step: int = 0,
+                 sync_free: bool = True, capacity_check_every: int = 16, cuda_graph: bool = False):
         self.model = model
         self.world_size, self.rank = world_size, rank
         self.lr_init, self.lr_final, self.max_steps = lr, lr_final, max_steps
@@ -90,6 +91,17 @@ class UMHSTrainer:
         self.step = start_step
         self.opt_steps = 0
         self.occ_update, self.freeze_binaries = occ_update, freeze_binaries
+        # sync-free steps: sample buffers are sized to a capacity learnt from a first (synchronising) step and
+        # re-checked every `capacity_check_every` steps; between checks a step issues no host sync at all
+        self.sync_free, self.capacity_check_every = sync_free, capacity_check_every
+        self.truncated_steps = 0
+        # whole-step CUDA graph: forward + loss + backward (+ Adam when single-GPU) captured once and replayed; the
+        # per-step scalars (lr, Adam bias corrections) travel through a 3-float device buffer
+        self.cuda_graph = cuda_graph and sync_free
+        self._graph = None
+        self._hyper = torch.zeros(3, dtype=torch.float32, device=self.flat.data.device)
+        # ring of pinned staging rows: the CPU may run several steps ahead of the asynchronous copies
+        self._hyper_host = torch.zeros((256, 3), dtype=torch.float32).pin_memory() if self.flat.data.is_cuda else None
         ops.DIRECT_GRAD = True  # backward kernels accumulate into the flat gradient views
         self._inv_world = torch.full((1,), 1.0 / world_size, dtype=torch.float32, device=self.flat.data.device)
         if world_size > 1:  # identical replicas
@@ -100,25 +112,113 @@ class UMHSTrainer:
         t = min(max(step / self.max_steps, 0.0), 1.0)
         return self.lr_init * (self.lr_final / self.lr_init) ** t
 
+    def _set_hyper(self) -> None:
+        """lr and Adam bias corrections of this step -> device (pinned staging buffer, async copy on the stream)."""
+        t = self.opt_steps
+        row = self._hyper_host[t % self._hyper_host.shape[0]]
+        row[0] = self.lr_at(self.step)
+        row[1] = 1.0 - self.betas[0] ** t
+        row[2] = (1.0 - self.betas[1] ** t) ** 0.5
+        self._hyper.copy_(row, non_blocking=True)
+
+    def _forward_backward(self, ray_bundle: RayBundle, batch: Dict[str, Tensor]):
+        m = self.model
+        outputs = m.get_outputs(m.collider(ray_bundle), per_band_views=False)
+        loss_dict = m.get_loss_dict(outputs, batch)
+        loss = sum(loss_dict.values())
+        loss.backward()  # kernels accumulate straight into the flat gradient buffer's views
+        loss_dict["loss"] = loss.detach()
+        loss_dict["num_samples"] = outputs["num_samples_per_ray"].sum()
+        return loss_dict
+
+    def _optimizer(self) -> None:
+        ops.adam_step_dev(self.flat.data, self.flat.grad, self.flat.exp_avg, self.flat.exp_avg_sq, self.betas[0],
+                          self.betas[1], self.eps, self._hyper,
+                          inv_scale=self._inv_world if self.world_size > 1 else None, clamp_range=self.clamp_range,
+                          zero_grad=True)
+
     def train_step(self, ray_bundle: RayBundle, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
         m = self.model
         m.train()
         if self.occ_update:
             m.update_occupancy_grid(self.step, freeze_binaries=self.freeze_binaries)
-        outputs = m.get_outputs(m.collider(ray_bundle), per_band_views=False)
-        loss_dict = m.get_loss_dict(outputs, batch)
-        loss = sum(loss_dict.values())
-        loss.backward()  # kernels accumulate straight into the flat gradient buffer's views
-        average_gradients(self.flat.grad, self.world_size)
+        n_rays = int(ray_bundle.origins.shape[0])
+        check = self.sync_free and (m.sample_capacity is None or self.opt_steps % self.capacity_check_every == 0)
         self.opt_steps += 1
-        ops.adam_step(self.flat.data, self.flat.grad, self.flat.exp_avg, self.flat.exp_avg_sq, self.lr_at(self.step),
-                      self.betas[0], self.betas[1], self.eps, self.opt_steps,
-                      inv_scale=self._inv_world if self.world_size > 1 else None, clamp_range=self.clamp_range,
-                      zero_grad=True)
+        self._set_hyper()
+        if self.cuda_graph and m.sample_capacity is not None:
+            loss_dict = self._graph_step(ray_bundle, batch)
+        else:
+            dev = self.flat.data.device
+            if ray_bundle.origins.device != dev:  # host batches (e2e): eager path copies them in first
+                ray_bundle = RayBundle(ray_bundle.origins.to(dev, non_blocking=True),
+                                       ray_bundle.directions.to(dev, non_blocking=True))
+                batch = {k: v.to(dev, non_blocking=True) for k, v in batch.items()}
+            loss_dict = self._forward_backward(ray_bundle, batch)
+            average_gradients(self.flat.grad, self.world_size)
+            self._optimizer()
+        if check:
+            self._update_capacity(n_rays)
         self.step += 1
-        loss_dict["loss"] = loss.detach()
-        loss_dict["num_samples"] = outputs["num_samples_per_ray"].sum()
         return loss_dict
+
+    # ------------------------------------------------------------------ whole-step CUDA graph
+    def _graph_step(self, ray_bundle: RayBundle, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
+        if self._graph is None or self._graph["capacity"] != self.model.sample_capacity or \
+                self._graph["n_rays"] != int(ray_bundle.origins.shape[0]):
+            self._capture(ray_bundle, batch)
+        g = self._graph
+        g["origins"].copy_(ray_bundle.origins, non_blocking=True)
+        g["directions"].copy_(ray_bundle.directions, non_blocking=True)
+        g["image"].copy_(batch["image"], non_blocking=True)
+        g["hs_image"].copy_(batch["hs_image"], non_blocking=True)
+        g["fwd_bwd"].replay()
+        if self.world_size > 1:
+            average_gradients(self.flat.grad, self.world_size)
+            g["opt"].replay()
+        return g["out"]
+
+    def _capture(self, ray_bundle: RayBundle, batch: Dict[str, Tensor]) -> None:
+        dev = self.flat.data.device
+        st = {"capacity": self.model.sample_capacity, "n_rays": int(ray_bundle.origins.shape[0]),
+              "origins": ray_bundle.origins.to(dev).clone(), "directions": ray_bundle.directions.to(dev).clone(),
+              "image": batch["image"].to(dev).clone(), "hs_image": batch["hs_image"].to(dev).clone()}
+        rb = RayBundle(st["origins"], st["directions"])
+        bt = {"image": st["image"], "hs_image": st["hs_image"]}
+        # a capture must not change the training state: snapshot, warm up on a side stream, capture, restore
+        snap = [t.clone() for t in (self.flat.data, self.flat.grad, self.flat.exp_avg, self.flat.exp_avg_sq)]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._forward_backward(rb, bt)
+                self.flat.grad.zero_()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            out = self._forward_backward(rb, bt)
+            if self.world_size == 1:
+                self._optimizer()
+        st["fwd_bwd"], st["out"] = g1, out
+        if self.world_size > 1:
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                self._optimizer()
+            st["opt"] = g2
+        for dst, src in zip((self.flat.data, self.flat.grad, self.flat.exp_avg, self.flat.exp_avg_sq), snap):
+            dst.copy_(src)
+        self._graph = st
+
+    def _update_capacity(self, n_rays: int) -> None:
+        """One host read of the last step's unclamped candidate count; grows the capacity with 30 % headroom."""
+        march_total, _ = self.model.occupancy_grid.last_totals
+        raw = int(march_total[1].item())
+        cap = self.model.sample_capacity
+        if cap is not None and raw > cap:
+            self.truncated_steps += 1
+        if cap is None or raw > cap or raw * 2 < cap:
+            self.model.sample_capacity = int(raw * 1.3) + n_rays
 
     @torch.no_grad()
     def render_tiles(self, camera_ray_bundle: RayBundle, tile: int = 32) -> Dict[str, Tensor]:

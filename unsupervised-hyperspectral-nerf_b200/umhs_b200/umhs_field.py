@@ -113,6 +113,7 @@ class UMHSField(nn.Module):
         self.converter = converter
         self.use_scalar = True
         self.register_buffer("aabb", torch.as_tensor(aabb, dtype=torch.float32))
+        self._aabb_host = None  # host copy of aabb for kernel arguments (refreshed when the buffer object changes)
         self.register_buffer("max_res", torch.tensor(max_res))
         self.register_buffer("num_levels", torch.tensor(num_levels))
         self.register_buffer("log2_hashmap_size", torch.tensor(log2_hashmap_size))
@@ -153,7 +154,12 @@ class UMHSField(nn.Module):
         return self.spatial_distortion is not None
 
     def _aabb6(self):
-        return tuple(float(v) for v in self.aabb.flatten().tolist())
+        """aabb as six Python floats.  Cached: reading a CUDA buffer back is a device sync, and this is called on
+        every step; the cache is keyed on the buffer's identity/version so load_state_dict / .to() refresh it."""
+        key = (self.aabb.data_ptr(), self.aabb._version)
+        if self._aabb_host is None or self._aabb_host[0] != key:
+            self._aabb_host = (key, tuple(float(v) for v in self.aabb.detach().flatten().cpu().tolist()))
+        return self._aabb_host[1]
 
     def _points(self, ray_samples: RaySamples) -> PointSet:
         packed = getattr(ray_samples, "packed", None)
@@ -178,11 +184,12 @@ class UMHSField(nn.Module):
         return out
 
     @torch.no_grad()
-    def density_packed(self, pts: PointSet) -> Tensor:
+    def density_packed(self, pts: PointSet, return_enc: bool = False):
         """Density only, no autograd: the sampler's sigma_fn and the occupancy-grid update."""
         enc = self.mlp_base.encoder
         e = ops.hash_encode_fwd(pts, enc.hash_table.detach(), enc.scalings, self._log2_T)
-        return ops.density_fwd(pts, e, self._weights_dict())
+        sigma = ops.density_fwd(pts, e, self._weights_dict())
+        return (sigma, e) if return_enc else sigma
 
     # ------------------------------------------------------------------ reference module surface
     def get_density(self, ray_samples: RaySamples) -> Tuple[Tensor, Tensor]:

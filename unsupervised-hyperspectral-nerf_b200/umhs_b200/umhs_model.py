@@ -129,6 +129,9 @@ class UMHSModel(nn.Module):
         self.sampler = VolumetricSampler(occupancy_grid=self.occupancy_grid, field=self.field)
         self.cluster_probe = ClusterLookup(len(wl), K)
         self._bg_override: Optional[Tensor] = None  # test hook: fixes the "random" background draw
+        # None: exact-sized sample buffers (host sync on the sample count, reference behaviour).
+        # int: sync-free steps on capacity-sized buffers (set by UMHSTrainer; see VolumetricSampler).
+        self.sample_capacity: Optional[int] = None
 
     # NearFarCollider (A.4): nears = near_plane while training, 0 in eval; fars = far_plane
     def collider(self, ray_bundle: RayBundle) -> RayBundle:
@@ -153,7 +156,7 @@ class UMHSModel(nn.Module):
         pts, ray_indices, t0, t1, packed_info = self.sampler(
             ray_bundle=ray_bundle, near_plane=cfg.near_plane, far_plane=cfg.far_plane,
             render_step_size=cfg.render_step_size, alpha_thre=cfg.alpha_thre, cone_angle=cfg.cone_angle,
-            jitter=jitter)
+            jitter=jitter, capacity=self.sample_capacity)
         fo = self.field.forward_packed(pts)
         K, B, spec = self.field.num_classes, self.field.wavelengths, cfg.pred_specular
         d = self.field.mlp_directional.layers
