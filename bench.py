@@ -85,35 +85,54 @@ def init_field_(field, seed=0):
 
 # ------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed regions.  In-process NVML (nvidia_ml_py): a
+    `nvidia-smi -lms` subprocess holds driver locks long enough to stall kernel launches of a step that syncs every
+    iteration (measured: +1.3 ms/step on the end-to-end pass), NVML queries cost tens of microseconds."""
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period_s=0.02):
+        self.index, self.period, self.rows, self._stop, self._thr, self._nvml = index, period_s, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self._max = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
         except Exception:
-            self.proc = None
+            self._nvml = None
+            return
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _loop(self):
+        nv = self._nvml
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.rows.append((sm, rs))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower() == "active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if self._nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self._stop = True
+        self._thr.join(timeout=1.0)
+        nv = self._nvml
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted({n for _, rs in self.rows for n, bit in names.items() if rs & bit})
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self._max), "reasons": reasons,
+                "samples": len(sm), "source": "nvml, 20 ms period, sampled over the two timed passes"}
 
 
 # ------------------------------------------------------------------------------------------ CPU oracle arm
@@ -251,22 +270,48 @@ def run_b200(args):
         o, d, image, hs = resident[i % POOL]
         return trainer.train_step(RayBundle(o, d), {"image": image, "hs_image": hs})
 
+    e2e_state = {"token": None, "prev_loss": None, "losses": []}
+
     def step_e2e(i):
-        o, d, image, hs = pinned[i % POOL]  # pinned host memory; train_step copies them to the device (async H2D)
-        out = trainer.train_step(RayBundle(o, d), {"image": image, "hs_image": hs})
-        return float(out["loss"].item())  # device -> host read of the step's result
+        """End-to-end step through the public API: batch i is copied from pinned host memory (the copy of batch
+        i+1 is started right after step i is enqueued, so it overlaps the compute), every step's loss is read
+        back to the host (the read of step i-1 is issued after step i is enqueued)."""
+        st = e2e_state
+        if st["token"] is None:
+            o, d, image, hs = pinned[i % POOL]
+            st["token"] = trainer.stage(RayBundle(o, d), {"image": image, "hs_image": hs})
+        out = trainer.train_step(st["token"])
+        loss = out["loss"].clone()  # the graph's output tensor is overwritten by the next replay
+        o, d, image, hs = pinned[(i + 1) % POOL]
+        st["token"] = trainer.stage(RayBundle(o, d), {"image": image, "hs_image": hs})
+        if st["prev_loss"] is not None:
+            st["losses"].append(float(st["prev_loss"].item()))  # device -> host read of a step's result
+        st["prev_loss"] = loss
+
+    def finish_e2e():
+        st = e2e_state
+        if st["prev_loss"] is not None:
+            st["losses"].append(float(st["prev_loss"].item()))
+            st["prev_loss"] = None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
+        stamps = [time.perf_counter()]
         for i in range(steps):
             fn(i)
+            stamps.append(time.perf_counter())
+        if os.environ.get("UMHS_BENCH_DEBUG"):
+            print("cpu ms per iteration:", [round(1e3 * (y - x), 2) for x, y in zip(stamps[:-1], stamps[1:])],
+                  file=sys.stderr)
+        if finish is not None:
+            finish()
         b.record()
         barrier()
         ms = torch.tensor([a.elapsed_time(b)], device=dev)
@@ -280,7 +325,12 @@ def run_b200(args):
     if rank == 0:
         clocks.start()
     ms = timed(step_resident, args.steps)
-    ms_e2e = timed(step_e2e, args.steps)
+    for i in range(max(3, args.warmup)):  # warm the end-to-end path too (staging buffers, copy stream, re-capture)
+        step_e2e(i)
+    finish_e2e()
+    e2e_state["losses"].clear()
+    ms_e2e = timed(step_e2e, args.steps, finish_e2e)
+    assert len(e2e_state["losses"]) == args.steps and all(np.isfinite(e2e_state["losses"]))
     clk = clocks.stop() if rank == 0 else None
 
     # second pass of the same K steps with per-entry-point CUDA events (roofline shares); eager launches so that
@@ -318,16 +368,18 @@ def run_b200(args):
                 "unit": "GB/s", "frac": (kernels[top]["achieved_gbs"] or 0.0) / hbm_peak, "traffic": None,
                 "peak_source": peak_src, "share_of_kernel_time": kernels[top]["ms_per_step"] / max(total_k, 1e-9),
                 "kernel_ms_per_step_sum": total_k}
-        cpu = time_oracle(steps=4, warmup=1)
+        cpu = time_oracle(steps=4, warmup=1) if world == 1 else None
         h2d = sum(t.numel() * t.element_size() for t in pinned[0])
         line = {"metric": "train rays/s", "value": world * R * args.steps / (ms * 1e-3), "unit": "rays/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(world, samples_per_ray=spr),
                 "e2e": {"value": world * R * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
-                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                        "pipeline": "pinned-host batch i+1 copied on a copy stream while step i runs; loss of every "
+                                    "step read back (one step late); all inside the timed region"},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof,
-                "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None,
                 "train_msamples_per_s": world * n_samples / args.steps / (ms / args.steps * 1e-3) / 1e6,
                 "kernels": kernels}
         print(json.dumps(line), flush=True)
@@ -339,7 +391,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=48)  # three occupancy-update periods
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the whole-step CUDA graph")

@@ -240,3 +240,32 @@ def test_trainer_cuda_graph_matches_eager():
     assert torch.isfinite(res[True][0]).all() and torch.isfinite(res[False][0]).all()
     assert (res[True][0] - res[False][0]).abs().max() < 5e-2 * res[False][0].abs().max()
     assert (res[True][1] - res[False][1]).abs().max() < 5e-2
+
+
+def test_occupancy_grid_update_matches_oracle():
+    """update_every_n_steps (cell points -> density * step -> EMA-max -> mean-threshold binarise)
+    against the oracle's restatement of nerfacc, with the random cell choice and in-cell jitter injected."""
+    from helpers import oracle_model_from_golden
+
+    d, meta = load_golden("model_train_k4.npz")
+    res = meta["grid_res"]
+    n_cells = res ** 3
+    g = torch.Generator().manual_seed(3)
+    cell_ids = [torch.randperm(n_cells, generator=g)[: n_cells // 2].contiguous() for _ in range(4)]
+    jitter = [torch.rand(n_cells // 2, 3, generator=g) for _ in range(4)]
+    om = oracle_model_from_golden(d, meta, training=True)
+    om.update_occupancy_grid(32, cell_ids=cell_ids, cell_jitter=jitter)
+    with mlp_precision("fp32"):
+        m = b200_model_from_golden(d, meta, True)
+        m.update_occupancy_grid(32, cell_ids=[c.to(DEV) for c in cell_ids], cell_jitter=[j.to(DEV) for j in jitter])
+    assert_close(m.occupancy_grid.occs, om.occupancy_grid.occs, 1e-4, 1e-7, "occs")
+    thre = float(torch.clamp(om.occupancy_grid.occs.mean(), max=0.01))
+    clear = (om.occupancy_grid.occs - thre).abs() > 1e-6 * max(thre, 1e-12)
+    got = m.occupancy_grid.binaries.flatten().cpu()
+    want = om.occupancy_grid.binaries.flatten()
+    assert torch.equal(got[clear], want[clear])
+    assert_close(m.occupancy_grid.occ_mean(), om.occupancy_grid.occs.mean().reshape(1), 1e-5, 1e-9, "occ mean")
+    # warm-up path (all cells, in order) runs and keeps shapes
+    with mlp_precision("bf16"):
+        m.update_occupancy_grid(0)
+    assert m.occupancy_grid.binaries.shape == (4, res, res, res)

@@ -116,15 +116,23 @@ class OccGridEstimator(nn.Module):
             m = n_cells if idx is None else int(idx.shape[0])
             if m == 0:
                 continue
-            jit = cell_jitter[lvl].to(torch.float32).contiguous() if cell_jitter is not None else \
-                torch.rand((m, 3), device=dev)
-            pos = torch.empty((m, 3), dtype=torch.float32, device=dev)
+            jit_all = cell_jitter[lvl].to(torch.float32).contiguous() if cell_jitter is not None else None
             aabb = self.aabbs[lvl].contiguous()
-            ops._call("umhs_occ_cell_points", m, ptr(idx), ptr(jit), m, res, ptr(aabb), ptr(pos), st)
-            occ = occ_eval_fn(pos).reshape(-1).to(torch.float32).contiguous()
-            tmp = torch.empty((m,), dtype=torch.float32, device=dev)
-            ops._call("umhs_occ_ema_update", m, ptr(occs), ptr(idx), lvl * n_cells, ptr(occ), 1.0, float(ema_decay), m,
-                      ptr(tmp), st)
+            # fixed-size chunks: the temporaries (positions, hash encodings, densities) keep one size from call to
+            # call, so the caching allocator serves them from the same blocks instead of growing with the cell count
+            CH = 1 << 18
+            for c0 in range(0, m, CH):
+                mc = min(CH, m - c0)
+                idx_c = None if idx is None else idx[c0:c0 + mc]
+                if idx is None:  # all cells in order: explicit ids for this chunk
+                    idx_c = torch.arange(c0, c0 + mc, device=dev, dtype=torch.int64)
+                jit = jit_all[c0:c0 + mc].contiguous() if jit_all is not None else torch.rand((mc, 3), device=dev)
+                pos = torch.empty((mc, 3), dtype=torch.float32, device=dev)
+                ops._call("umhs_occ_cell_points", mc, ptr(idx_c), ptr(jit), mc, res, ptr(aabb), ptr(pos), st)
+                occ = occ_eval_fn(pos).reshape(-1).to(torch.float32).contiguous()
+                tmp = torch.empty((mc,), dtype=torch.float32, device=dev)
+                ops._call("umhs_occ_ema_update", mc, ptr(occs), ptr(idx_c), lvl * n_cells, ptr(occ), 1.0,
+                          float(ema_decay), mc, ptr(tmp), st)
         scratch = torch.empty((2,), dtype=torch.float64, device=dev)
         mean = torch.empty((1,), dtype=torch.float32, device=dev)
         bn = binaries.view(torch.uint8)

@@ -112,6 +112,38 @@ class UMHSTrainer:
         t = min(max(step / self.max_steps, 0.0), 1.0)
         return self.lr_init * (self.lr_final / self.lr_init) ** t
 
+    # ------------------------------------------------------------------ input pipeline (host -> device)
+    def stage(self, ray_bundle: RayBundle, batch: Dict[str, Tensor]):
+        """Start the host->device copy of a batch (pinned host tensors) on a copy stream and return a token for
+        ``train_step``.  Two staging slots: the copy of batch i+1 overlaps the compute of step i."""
+        dev = self.flat.data.device
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage_bufs = [None, None]
+            self._slot_free = [None, None]
+            self._stage_slot = 0
+        slot = self._stage_slot
+        self._stage_slot ^= 1
+        src = {"origins": ray_bundle.origins, "directions": ray_bundle.directions, "image": batch["image"],
+               "hs_image": batch["hs_image"]}
+        bufs = self._stage_bufs[slot]
+        if bufs is None or any(bufs[k].shape != v.shape for k, v in src.items()):
+            bufs = self._stage_bufs[slot] = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in src.items()}
+        if self._slot_free[slot] is not None:
+            self._copy_stream.wait_event(self._slot_free[slot])  # the step that last read this slot is done with it
+        with torch.cuda.stream(self._copy_stream):
+            for k, v in src.items():
+                bufs[k].copy_(v, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        return ("staged", slot, ready)
+
+    def _unstage(self, token):
+        _, slot, ready = token
+        torch.cuda.current_stream(self.flat.data.device).wait_event(ready)
+        b = self._stage_bufs[slot]
+        return slot, RayBundle(b["origins"], b["directions"]), {"image": b["image"], "hs_image": b["hs_image"]}
+
     def _set_hyper(self) -> None:
         """lr and Adam bias corrections of this step -> device (pinned staging buffer, async copy on the stream)."""
         t = self.opt_steps
@@ -137,9 +169,14 @@ class UMHSTrainer:
                           inv_scale=self._inv_world if self.world_size > 1 else None, clamp_range=self.clamp_range,
                           zero_grad=True)
 
-    def train_step(self, ray_bundle: RayBundle, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
+    def train_step(self, ray_bundle, batch: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+        """One training step.  ``ray_bundle`` is a RayBundle (device or pinned-host tensors) with its ``batch``, or a
+        token returned by ``stage``."""
         m = self.model
         m.train()
+        slot = None
+        if isinstance(ray_bundle, tuple) and ray_bundle[0] == "staged":
+            slot, ray_bundle, batch = self._unstage(ray_bundle)
         if self.occ_update:
             m.update_occupancy_grid(self.step, freeze_binaries=self.freeze_binaries)
         n_rays = int(ray_bundle.origins.shape[0])
@@ -157,6 +194,10 @@ class UMHSTrainer:
             loss_dict = self._forward_backward(ray_bundle, batch)
             average_gradients(self.flat.grad, self.world_size)
             self._optimizer()
+        if slot is not None:  # the staging slot may be overwritten once this step has consumed it
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.flat.data.device))
+            self._slot_free[slot] = ev
         if check:
             self._update_capacity(n_rays)
         self.step += 1
