@@ -40,6 +40,7 @@ BANDS, K_CLASSES, TEMPERATURE, LOG2_T, GRID_RES = 128, 4, 0.4, 19, 128
 SHELL_R, SHELL_T = 0.5, 0.08
 WAVELENGTHS = np.linspace(400, 1000, BANDS).astype(int).tolist()
 CPU_SAMPLE_RAYS = 1024
+CONDITIONING_STEPS = 34
 
 
 # ------------------------------------------------------------------------------------------ synthetic scene
@@ -222,6 +223,7 @@ def workload_config(n_gpus, cpu=False, samples_per_ray=None):
          "bands": BANDS, "endmembers": K_CLASSES, "temperature": TEMPERATURE, "hash": "16x2@2^19",
          "occupancy": f"128^3x4 shell r={SHELL_R} t={SHELL_T}", "method": "rgb+spectral", "specular": False,
          "parallelism": f"dp{n_gpus} ray-sharded, 1 all-reduce/step" if n_gpus > 1 else "single",
+         "conditioning_steps": CONDITIONING_STEPS,
          "launch": "whole step replayed as one CUDA graph (fwd+loss+bwd+Adam); occupancy update eager every 16 steps",
          "l2_policy": "working set > L2: Adam state 4 x 64 MiB streamed every step + rotating batches"}
     if samples_per_ray is not None:
@@ -319,7 +321,9 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for i in range(args.warmup):
+    # conditioning (untimed, on top of the W warm-up steps): graph capture, capacity learning and the first two
+    # occupancy-update periods allocate their buffers here, not inside the timed region
+    for i in range(args.warmup + CONDITIONING_STEPS):
         step_resident(i)
     clocks = ClockSampler(local)
     if rank == 0:

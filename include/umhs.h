@@ -147,6 +147,10 @@ int umhs_field_mlp_tc_fwd(const umhs_points *pts, int64_t n, const float *enc, c
                           const umhs_field_out *out, void *stream);
 int umhs_field_mlp_tc_bwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
                           const umhs_field_out_grads *g, float *d_enc, const umhs_mlp_grads *dp, void *stream);
+/* Same backward with two 128-sample tiles in flight per SM (9 warps: two data groups + one MMA-issuing warp);
+ * the plugin's default.  Identical interface and results (same bf16 arithmetic) as umhs_field_mlp_tc_bwd. */
+int umhs_field_mlp_tc_bwd2(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
+                           const umhs_field_out_grads *g, float *d_enc, const umhs_mlp_grads *dp, void *stream);
 /* Developer aid: install (or with NULL remove) a device buffer of 4*capacity_slots int64 in which CTA 0 of the
  * tensor-core MLP kernels records (tag, clock64) pairs at the stages of every MMA round (threads 0 and 96). */
 int umhs_debug_trace(int64_t *buffer, int32_t capacity_slots, void *stream);
@@ -256,6 +260,12 @@ typedef struct {
     float step_size, cone_angle;
     int64_t n_rays;
     const int32_t *level_any;        /* [8] device flags from umhs_march_level_any, or NULL (always fetch occupancy) */
+    /* optional staging: umhs_march_count also records the first stage_stride interval starts of every ray in
+     * stage[R, stage_stride]; umhs_march_write then copies them (stage_counts = the counts array of that call)
+     * instead of marching again.  Identical outputs; NULL / 0 disables. */
+    float *stage;
+    const int64_t *stage_counts;
+    int32_t stage_stride;
 } umhs_march_args;
 
 /* level_any[l] = 1 iff grid level l holds an occupied cell (lets the march skip occupancy fetches there) */

@@ -1047,3 +1047,535 @@ extern "C" int umhs_field_mlp_tc_bwd(const umhs_points *pts, int64_t n, const fl
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }
+
+// =====================================================================================================
+// Backward, two tiles in flight per SM ("ping-pong").
+//
+// The single-tile kernel above is bound by its chain of ~16 dependent rounds (epilogue -> CTA barrier -> MMA issue
+// -> tensor core -> mbarrier), with 4 warps on the SM and the tensor pipe idle most of the time
+// (profiles/r1_ncu_full_summary.md).  Here one CTA of 9 warps runs TWO 128-sample tiles at once:
+//   warps 0-3 = group 0, warps 4-7 = group 1 (thread t of a group owns row t & 127 = TMEM lane), warp 8 = MMA issuer.
+// A group finishes an epilogue, arrives on its `ready` mbarrier and waits on its `done` mbarrier; the issuer waits
+// for `ready`, issues that round's tcgen05.mma program for that group and commits it to `done`.  While one group
+// waits for the tensor core the other one runs its epilogue.  All MMAs come from one thread, so the two groups can
+// accumulate into the SAME TMEM-resident weight-gradient accumulators, in program order.
+// Per group: 64 working TMEM columns; shared: 328 (+16 specular) columns of accumulators.  The base MLP's hidden
+// activations stay in registers (packed bf16) between the first and the last rounds of a tile instead of a tile.
+// =====================================================================================================
+namespace umhs {
+
+struct TcBwd2 {
+    static constexpr int sbias = TcSmem::ctrl + 64;       // fp32 [80]: h2[16] f2[32] b1[16] d0[16]  (ctrl holds 5 words)
+    static constexpr int grp = (sbias + 80 * 4 + 127) / 128 * 128;
+    // per-group activation tiles (a ones chunk behind tA0, tX and tH1: see TcBwd)
+    static constexpr int tA0 = 0;
+    static constexpr int tX = tA0 + TM * 32 * 2 + 2048;
+    static constexpr int tH1 = tX + TM * 32 * 2 + 2048;
+    static constexpr int tH2 = tH1 + TM * 64 * 2 + 2048;
+    static constexpr int tD1 = tH2 + TM * 64 * 2;
+    static constexpr int tD2 = tD1 + TM * 64 * 2;
+    static constexpr int tX2 = tD2 + TM * 64 * 2;          // [128 x 32] (specular only)
+    static constexpr int grp_bytes = tX2;                  // without specular
+    static constexpr int grp_bytes_spec = tX2 + TM * 32 * 2;
+    // TMEM columns: working [0,64) group 0, [64,128) group 1; accumulators shared by both groups
+    static constexpr int P_h2t = 128, P_h1 = 144, P_h0 = 216, P_f2t = 256, P_f1 = 288, P_f0 = 360;
+    static constexpr int P_b1t = 400, P_b0 = 416, P_d0 = 456;  // P_d0: [64 (16 real rows) x 32] .. 488
+    static constexpr int ncols = 512;
+    static constexpr int kRounds = 16;
+    static constexpr int kThreads = 288;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct GroupAddr {  // shared-memory addresses (async-proxy view) of one group's operand tiles
+    uint32_t A0, X, H1, H2, D1, D2, X2;
+};
+
+// MMA program of round `r` for one group (executed by the single issuing thread)
+__device__ __forceinline__ void issue_round(int r, const GroupAddr &g, uint32_t tw, uint32_t tbase, uint32_t acc,
+                                            int spec, bool want_denc, uint32_t sWb0, uint32_t sWb1, uint32_t sWhf0,
+                                            uint32_t sWh1, uint32_t sWf1, uint32_t sWh2, uint32_t sWf2, uint32_t sWd0) {
+    switch (r) {
+        case 0:  // base layer 0
+            gemm_kmajor(tw, g.A0, sWb0, 64, 0, 64, 32, 0);
+            break;
+        case 1:  // base layer 1 (N=16) [+ mlp_directional layer 0 (N=16) at working columns 16..31]
+            gemm_kmajor(tw, g.H1, sWb1, 16, 0, 16, 64, 0);
+            if (spec) gemm_kmajor(tw + 16, g.X2, sWd0, 16, 0, 16, 32, 0);
+            break;
+        case 2:  // mlp_head layer 0 [+ wgrad of mlp_directional layer 0: d_hidden^T (padded to 64 rows) x X2]
+            gemm_kmajor(tw, g.X, sWhf0, 128, 0, 64, 32, 0);
+            if (spec) gemm_wgrad(tbase + TcBwd2::P_d0, g.D2, 0, g.X2, 0, 32, acc);
+            break;
+        case 3:
+            gemm_kmajor(tw, g.H1, sWh1, 64, 0, 64, 64, 0);
+            break;
+        case 4:
+            gemm_kmajor(tw, g.H2, sWh2, 16, 0, 16, 64, 0);
+            break;
+        case 5:
+            gemm_dgrad(tw, g.D2, sWh2, 16, 0, 64, 16, 0);
+            gemm_wgrad(tbase + TcBwd2::P_h2t, g.H2, 0, g.D2, 0, 16, acc);
+            break;
+        case 6:
+            gemm_dgrad(tw, g.D1, sWh1, 64, 0, 64, 64, 0);
+            gemm_wgrad(tbase + TcBwd2::P_h1, g.D1, 0, g.H1, 0, 72, acc);
+            break;
+        case 7:
+            gemm_dgrad(tw, g.D2, sWhf0, 128, 0, 32, 64, 0);
+            gemm_wgrad(tbase + TcBwd2::P_h0, g.D2, 0, g.X, 0, 40, acc);
+            break;
+        case 8:  // feature_mlp layer 0
+            gemm_kmajor(tw, g.X, sWhf0, 128, 64, 64, 32, 0);
+            break;
+        case 9:
+            gemm_kmajor(tw, g.H1, sWf1, 64, 0, 64, 64, 0);
+            break;
+        case 10:
+            gemm_kmajor(tw, g.H2, sWf2, 32, 0, 32, 64, 0);
+            break;
+        case 11:
+            gemm_dgrad(tw, g.D2, sWf2, 32, 0, 64, 32, 0);
+            gemm_wgrad(tbase + TcBwd2::P_f2t, g.H2, 0, g.D2, 0, 32, acc);
+            break;
+        case 12:
+            gemm_dgrad(tw, g.D1, sWf1, 64, 0, 64, 64, 0);
+            gemm_wgrad(tbase + TcBwd2::P_f1, g.D1, 0, g.H1, 0, 72, acc);
+            break;
+        case 13:
+            gemm_dgrad(tw, g.D2, sWhf0, 128, 64, 32, 64, 0);
+            gemm_wgrad(tbase + TcBwd2::P_f0, g.D2, 0, g.X, 0, 40, acc);
+            break;
+        case 14:  // base layer 1 backward (H0 is back in tH1)
+            gemm_dgrad(tw, g.D2, sWb1, 16, 0, 64, 16, 0);
+            gemm_wgrad(tbase + TcBwd2::P_b1t, g.H1, 0, g.D2, 0, 16, acc);
+            break;
+        default:  // 15: base layer 0 backward
+            if (want_denc) gemm_dgrad(tw, g.D1, sWb0, 64, 0, 32, 64, 0);
+            gemm_wgrad(tbase + TcBwd2::P_b0, g.D1, 0, g.A0, 0, 40, acc);
+            break;
+    }
+}
+
+__global__ void __launch_bounds__(TcBwd2::kThreads, 1)
+field_mlp_tc_bwd2_kernel(umhs_points P, int64_t n_total, const float *__restrict__ enc, umhs_mlp_params mp,
+                         umhs_field_out_grads g, float *__restrict__ d_enc, umhs_mlp_grads dp) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K = mp.num_classes, spec = mp.specular;
+    const int grp = tid >> 7;          // 0, 1: data groups; 2: the issuer warp
+    const int row = tid & 127;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TcSmem::ctrl);  // ready[0], ready[1], done[0], done[1]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TcSmem::ctrl + 32);
+    float *sbias = reinterpret_cast<float *>(smem + TcBwd2::sbias);
+    const int grp_bytes = spec ? TcBwd2::grp_bytes_spec : TcBwd2::grp_bytes;
+    uint8_t *gbase = smem + TcBwd2::grp + (grp < 2 ? grp : 0) * grp_bytes;
+
+    // ---- one-time setup: weights, ones chunks, barriers, TMEM
+    if (tid < TM) stage_all_weights(smem, mp, false, tid);  // the staging helpers stride by TM threads
+    if (tid < 256) {
+        const float one[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        store8(gbase + TcBwd2::tA0, row, 32, CH_ACT, one);
+        store8(gbase + TcBwd2::tX, row, 32, CH_ACT, one);
+        store8(gbase + TcBwd2::tH1, row, 64, CH_ACT, one);
+    }
+    if (tid < 80) sbias[tid] = 0.f;
+    if (tid == 0) {
+        mbar_init(bars + 0, TM);
+        mbar_init(bars + 1, TM);
+        mbar_init(bars + 2, 1);
+        mbar_init(bars + 3, 1);
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc<TcBwd2::ncols>(tmem_slot);
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tbase = *tmem_slot;
+
+    n_total = effective_n(P, n_total);
+    const int64_t n_tiles = (n_total + TM - 1) / TM;
+    // tile of (iteration it, group q) of this CTA
+    auto tile_of = [&](int64_t it, int q) { return (it * gridDim.x + blockIdx.x) * 2 + q; };
+
+    const uint32_t sWb0 = smem_u32(smem + TcSmem::w_base0), sWb1 = smem_u32(smem + TcSmem::w_base1);
+    const uint32_t sWhf0 = smem_u32(smem + TcSmem::w_hf0), sWh1 = smem_u32(smem + TcSmem::w_h1);
+    const uint32_t sWf1 = smem_u32(smem + TcSmem::w_f1), sWh2 = smem_u32(smem + TcSmem::w_h2);
+    const uint32_t sWf2 = smem_u32(smem + TcSmem::w_f2), sWd0 = smem_u32(smem + TcSmem::w_d0);
+
+    if (grp == 2) {
+        // ======================= MMA issuer warp
+        GroupAddr ga[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint32_t b = smem_u32(smem + TcBwd2::grp + q * grp_bytes);
+            ga[q].A0 = b + TcBwd2::tA0; ga[q].X = b + TcBwd2::tX; ga[q].H1 = b + TcBwd2::tH1; ga[q].H2 = b + TcBwd2::tH2;
+            ga[q].D1 = b + TcBwd2::tD1; ga[q].D2 = b + TcBwd2::tD2; ga[q].X2 = b + TcBwd2::tX2;
+        }
+        uint32_t par[2] = {0u, 0u};
+        for (int64_t it = 0; tile_of(it, 0) < n_tiles; ++it) {
+            const bool act1 = tile_of(it, 1) < n_tiles;
+            for (int r = 0; r < TcBwd2::kRounds; ++r) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (q == 1 && !act1) continue;
+                    if (lane == 0) {
+                        mbar_wait(bars + q, par[q]);  // group q wrote its operand tiles for round r
+                        fence_after_sync();
+                        const uint32_t acc = (it == 0 && q == 0) ? 0u : 1u;  // the very first tile initialises
+                        issue_round(r, ga[q], tbase + 64u * q, tbase, acc, spec, d_enc != nullptr, sWb0, sWb1, sWhf0,
+                                    sWh1, sWf1, sWh2, sWf2, sWd0);
+                        commit(bars + 2 + q);
+                    }
+                    par[q] ^= 1u;
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ======================= data groups: thread `row` of group `grp` owns one sample of the group's tile
+        uint8_t *tA0 = gbase + TcBwd2::tA0, *tX = gbase + TcBwd2::tX, *tH1 = gbase + TcBwd2::tH1;
+        uint8_t *tH2 = gbase + TcBwd2::tH2, *tD1 = gbase + TcBwd2::tD1, *tD2 = gbase + TcBwd2::tD2;
+        uint8_t *tX2 = gbase + TcBwd2::tX2;
+        uint64_t *ready = bars + grp, *done = bars + 2 + grp;
+        uint32_t par = 0;
+        const uint32_t trow = tbase + ((uint32_t)((warp & 3) * 32) << 16) + 64u * grp;
+        const float *Bb0 = reinterpret_cast<const float *>(smem + TcSmem::b_base0);
+        const float *Bb1 = reinterpret_cast<const float *>(smem + TcSmem::b_base1);
+        const float *Bh0 = reinterpret_cast<const float *>(smem + TcSmem::b_h0);
+        const float *Bf0 = reinterpret_cast<const float *>(smem + TcSmem::b_f0);
+        const float *Bh1 = reinterpret_cast<const float *>(smem + TcSmem::b_h1);
+        const float *Bf1 = reinterpret_cast<const float *>(smem + TcSmem::b_f1);
+        const float *Bh2 = reinterpret_cast<const float *>(smem + TcSmem::b_h2);
+        const float *Bf2 = reinterpret_cast<const float *>(smem + TcSmem::b_f2);
+        const float *Bd0 = reinterpret_cast<const float *>(smem + TcSmem::b_d0);
+        float *sb_h2 = sbias, *sb_f2 = sbias + 16, *sb_b1 = sbias + 48, *sb_d0 = sbias + 64;
+        const float invT = 1.0f / mp.temperature;
+        // one round trip with the issuer: operands written -> MMAs of the round done
+        auto round_trip = [&]() {
+            fence_proxy_async();
+            fence_before_sync();
+            mbar_arrive(ready);
+            mbar_wait(done, par);
+            par ^= 1u;
+            fence_after_sync();
+        };
+        auto bias_sum = [&](auto &v, int n, float *dst) {  // column sums of a narrow delta block (n <= 17)
+#pragma unroll
+            for (int k = 0; k < 17; ++k) {
+                if (k < n && k < (int)(sizeof(v) / sizeof(float))) {  // warp-uniform
+                    const float s = warp_sum(v[k]);
+                    if (lane == 0 && s != 0.f) atomicAdd(dst + k, s);
+                }
+            }
+        };
+
+        // (no cross-tile prefetch here: the other group's work hides this group's global-load latency, and the
+        //  registers are needed for the packed H0 activations)
+        for (int64_t it = 0; tile_of(it, grp) < n_tiles; ++it) {
+            const int64_t tile = tile_of(it, grp);
+            const int64_t n0 = tile * TM;
+            const bool valid = n0 + row < n_total;
+            const int64_t n = valid ? n0 + row : n_total - 1;
+            const Point pt = eval_point(P, n);
+            float pe[12];
+            pos_encoding_tc(pt, pe);
+            // ---------------- round 0: enc -> tA0 [, X2 -> tX2]
+            {
+                const float4 *e4 = reinterpret_cast<const float4 *>(enc + enc_row(P, n) * 32);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 a = __ldg(e4 + 2 * c), b = __ldg(e4 + 2 * c + 1);
+                    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    store8(tA0, row, 8 * c, CH_ACT, v);
+                }
+            }
+            if (spec) {
+                float x2[32], sh[16];
+                sh_deg3_tc((pt.dx + 1.0f) / 2.0f, (pt.dy + 1.0f) / 2.0f, (pt.dz + 1.0f) / 2.0f, sh);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x2[i] = sh[i];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) x2[16 + i] = pe[i];
+#pragma unroll
+                for (int i = 28; i < 32; ++i) x2[i] = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) store8(tX2, row, 8 * c, CH_ACT, x2 + 8 * c);
+            }
+            round_trip();
+            // ---------------- round 1: H0 = relu(. + b) -> tH1, and kept in registers as packed bf16
+            uint32_t h0p[32];
+            {
+                float v[64];
+                tmem_ld64(trow, v);
+#pragma unroll
+                for (int c = 0; c < 64; c += 8) {
+                    float o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = fmaxf(v[c + i] + Bb0[c + i], 0.f);
+                    store8(tH1, row, c, CH_ACT, o);
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        __nv_bfloat162 p2 = __floats2bfloat162_rn(o[i], o[i + 1]);
+                        h0p[(c + i) >> 1] = *reinterpret_cast<uint32_t *>(&p2);
+                    }
+                }
+            }
+            round_trip();
+            // ---------------- round 2: o16 ; X = [pe, emb] -> tX [; d spec_hidden (padded to 64 columns) -> tD2]
+            float o16[16], demb[15];
+            tmem_ld16(trow, o16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o16[i] += Bb1[i];
+#pragma unroll
+            for (int i = 0; i < 15; ++i) demb[i] = (valid && g.d_embedding) ? __ldg(g.d_embedding + n * 15 + i) : 0.f;
+            if (spec) {
+                float h[16], dsh[16];
+                tmem_ld16(trow + 16, h);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid && g.d_spec_hidden)
+                        gq = __ldg(reinterpret_cast<const float4 *>(g.d_spec_hidden + n * 16) + q);
+                    dsh[4 * q] = (h[4 * q] + Bd0[4 * q] > 0.f) ? gq.x : 0.f;
+                    dsh[4 * q + 1] = (h[4 * q + 1] + Bd0[4 * q + 1] > 0.f) ? gq.y : 0.f;
+                    dsh[4 * q + 2] = (h[4 * q + 2] + Bd0[4 * q + 2] > 0.f) ? gq.z : 0.f;
+                    dsh[4 * q + 3] = (h[4 * q + 3] + Bd0[4 * q + 3] > 0.f) ? gq.w : 0.f;
+                }
+                const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                store8(tD2, row, 0, CH_ACT, dsh);
+                store8(tD2, row, 8, CH_ACT, dsh + 8);
+#pragma unroll
+                for (int c = 16; c < 64; c += 8) store8(tD2, row, c, CH_ACT, z8);
+                bias_sum(dsh, 16, sb_d0);
+            }
+            {
+                float x[32];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) x[i] = pe[i];
+#pragma unroll
+                for (int i = 0; i < 15; ++i) x[12 + i] = o16[1 + i];
+#pragma unroll
+                for (int i = 27; i < 32; ++i) x[i] = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) store8(tX, row, 8 * c, CH_ACT, x + 8 * c);
+            }
+            round_trip();
+            // ================= mlp_head (m = 0) then feature_mlp (m = 1): rounds 3..7 and 8..13
+#pragma unroll 1
+            for (int m = 0; m < 2; ++m) {
+                const float *B0 = m ? Bf0 : Bh0, *B1 = m ? Bf1 : Bh1, *B2 = m ? Bf2 : Bh2;
+                const int nout = m ? K + spec : K;
+                if (m == 1) {
+                    // collect d X of mlp_head (working columns 0..31), then run feature_mlp layer 0 (round 8)
+                    float dx[16];
+                    tmem_ld16(trow, dx);
+#pragma unroll
+                    for (int i = 12; i < 16; ++i) demb[i - 12] += dx[i];
+                    tmem_ld16(trow + 16, dx);
+#pragma unroll
+                    for (int i = 0; i < 11; ++i) demb[4 + i] += dx[i];
+                    round_trip();
+                }
+                acc_to_tile_relu(trow, 0, 64, B0, tH1, row, 0);
+                round_trip();  // layer 1
+                acc_to_tile_relu(trow, 0, 64, B1, tH2, row, 0);
+                // incoming gradients of this MLP's outputs: fetched while the tensor core runs the last layer
+                float gin[17];
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    gin[k] = (valid && k < K) ? __ldg((m ? g.d_abund : g.d_scalar) + n * K + k) : 0.f;
+                gin[16] = (valid && m == 1 && spec && g.d_s1) ? __ldg(g.d_s1 + n) : 0.f;
+                round_trip();  // layer 2
+                {
+                    float z[32], dz[32];
+                    {
+                        float t16[16];
+                        tmem_ld16(trow, t16);
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) z[k] = t16[k];
+                        if (m == 1) tmem_ld16(trow + 16, t16);
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) z[16 + k] = (m == 1) ? t16[k] : 0.f;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) dz[k] = 0.f;
+                    if (valid) {
+                        if (m == 0) {
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) {
+                                if (k < K) {
+                                    const float s = __frcp_rn(1.0f + __expf(-(z[k] + B2[k])));
+                                    dz[k] = gin[k] * s * (1.0f - s);
+                                }
+                            }
+                        } else {
+                            float mx = -3.0e38f, e[16], den = 0.f, dot = 0.f;
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) {
+                                z[k] = (z[k] + B2[k]) * invT;
+                                if (k < K) mx = fmaxf(mx, z[k]);
+                            }
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) {
+                                e[k] = (k < K) ? __expf(z[k] - mx) : 0.f;
+                                den += e[k];
+                                dot += e[k] * gin[k];
+                            }
+                            const float rden = __frcp_rn(den);
+                            dot *= rden;
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) dz[k] = e[k] * rden * invT * (gin[k] - dot);
+                            if (spec) {
+                                float zs = z[16] + B2[16];
+#pragma unroll
+                                for (int k = 0; k < 16; ++k)
+                                    if (k == K) zs = z[k] * mp.temperature;
+                                const float s = __frcp_rn(1.0f + __expf(-zs));
+                                const float ds = gin[16] * s * (1.0f - s);
+#pragma unroll
+                                for (int k = 0; k < 17; ++k)
+                                    if (k == K) dz[k] = ds;
+                            }
+                        }
+                    }
+                    store8(tD2, row, 0, CH_ACT, dz);
+                    store8(tD2, row, 8, CH_ACT, dz + 8);
+                    if (m == 1) {
+                        store8(tD2, row, 16, CH_ACT, dz + 16);
+                        store8(tD2, row, 24, CH_ACT, dz + 24);
+                    }
+                    bias_sum(dz, nout, m ? sb_f2 : sb_h2);
+                }
+                round_trip();  // d layer 2
+                acc_to_delta_masked(trow, 0, tH2, tD1, row, valid);
+                round_trip();  // d layer 1
+                acc_to_delta_masked(trow, 0, tH1, tD2, row, valid);
+                round_trip();  // d layer 0
+            }
+            // ================= base MLP backward (rounds 14, 15)
+            {
+                float dx[16], dO[16];
+                tmem_ld16(trow, dx);
+#pragma unroll
+                for (int i = 12; i < 16; ++i) demb[i - 12] += dx[i];
+                tmem_ld16(trow + 16, dx);
+#pragma unroll
+                for (int i = 0; i < 11; ++i) demb[4 + i] += dx[i];
+                const float dsg = (valid && g.d_sigma) ? __ldg(g.d_sigma + n) : 0.f;
+                dO[0] = dsg * pt.sel * __expf(fminf(fmaxf(o16[0], -15.0f), 15.0f));
+#pragma unroll
+                for (int i = 0; i < 15; ++i) dO[1 + i] = valid ? demb[i] : 0.f;
+                store8(tD2, row, 0, CH_ACT, dO);
+                store8(tD2, row, 8, CH_ACT, dO + 8);
+                bias_sum(dO, 16, sb_b1);
+                // H0 back into tH1 (operand of the base layer-1 weight gradient)
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<uint4 *>(tH1 + tile_off(row, 8 * c, CH_ACT)) =
+                        make_uint4(h0p[4 * c], h0p[4 * c + 1], h0p[4 * c + 2], h0p[4 * c + 3]);
+            }
+            round_trip();
+            {
+                float v[64];
+                tmem_ld64(trow, v);
+#pragma unroll
+                for (int c = 0; c < 64; c += 8) {
+                    float o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&h0p[(c + i) >> 1]));
+                        o[i] = (valid && h.x > 0.f) ? v[c + i] : 0.f;
+                        o[i + 1] = (valid && h.y > 0.f) ? v[c + i + 1] : 0.f;
+                    }
+                    store8(tD1, row, c, CH_ACT, o);
+                }
+            }
+            round_trip();
+            if (d_enc) {
+                float v[16];
+                float4 *dst = reinterpret_cast<float4 *>(d_enc + n * 32);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    tmem_ld16(trow + 16 * c, v);
+                    if (valid) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            dst[4 * c + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                }
+            }
+            fence_before_sync();
+        }
+    }
+
+    // ================= flush the weight-gradient accumulators: row r = 16 * (warp & 3) + lane (lane < 16)
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (grp < 2) {
+        const uint32_t tq = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+        const int r = (warp & 3) * 16 + lane;
+        if (grp == 0) {
+            flush_acc(tq, TcBwd2::P_h2t, K, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.head_w2 + c * 64 + r, v); });
+            flush_acc(tq, TcBwd2::P_h1, 65, lane, [&](int c, float v) {
+                if (v != 0.f) atomicAdd(c < 64 ? dp.head_w1 + r * 64 + c : dp.head_b1 + r, v); });
+            flush_acc(tq, TcBwd2::P_h0, 33, lane, [&](int c, float v) {
+                if (v != 0.f && (c < 27 || c == 32)) atomicAdd(c < 27 ? dp.head_w0 + r * 27 + c : dp.head_b0 + r, v); });
+            flush_acc(tq, TcBwd2::P_b1t, 16, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.base_w1 + c * 64 + r, v); });
+            if (spec)
+                flush_acc(tq, TcBwd2::P_d0, 28, lane, [&](int c, float v) {
+                    if (r < 16 && v != 0.f) atomicAdd(dp.dir_w0 + r * 28 + c, v); });
+        } else {
+            flush_acc(tq, TcBwd2::P_f2t, K + spec, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.feat_w2 + c * 64 + r, v); });
+            flush_acc(tq, TcBwd2::P_f1, 65, lane, [&](int c, float v) {
+                if (v != 0.f) atomicAdd(c < 64 ? dp.feat_w1 + r * 64 + c : dp.feat_b1 + r, v); });
+            flush_acc(tq, TcBwd2::P_f0, 33, lane, [&](int c, float v) {
+                if (v != 0.f && (c < 27 || c == 32)) atomicAdd(c < 27 ? dp.feat_w0 + r * 27 + c : dp.feat_b0 + r, v); });
+            flush_acc(tq, TcBwd2::P_b0, 33, lane, [&](int c, float v) {
+                if (v != 0.f) atomicAdd(c < 32 ? dp.base_w0 + r * 32 + c : dp.base_b0 + r, v); });
+        }
+    }
+    if (tid < 80) {
+        const float a = sbias[tid];
+        float *dst = nullptr;
+        if (tid < 16) dst = (tid < K) ? dp.head_b2 + tid : nullptr;
+        else if (tid < 48) dst = (tid - 16 < K + spec) ? dp.feat_b2 + (tid - 16) : nullptr;
+        else if (tid < 64) dst = dp.base_b1 + (tid - 48);
+        else dst = spec ? dp.dir_b0 + (tid - 64) : nullptr;
+        if (dst != nullptr && a != 0.f) atomicAdd(dst, a);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc<TcBwd2::ncols>(tbase);
+}
+
+}  // namespace umhs
+
+extern "C" int umhs_field_mlp_tc_bwd2(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
+                                      const umhs_field_out_grads *g, float *d_enc, const umhs_mlp_grads *dp,
+                                      void *stream) {
+    if (n <= 0) return UMHS_OK;
+    UMHS_CHECK_ARG(pts && enc && g && dp && p, "null argument");
+    UMHS_CHECK_ARG(p->num_classes >= 1 && p->num_classes <= UMHS_MAX_CLASSES && p->temperature > 0.f, "bad K / T");
+    UMHS_CHECK_ARG(g->d_scalar && g->d_abund, "d_scalar/d_abund are required");
+    UMHS_CHECK_ARG(dp->base_w0 && dp->base_b0 && dp->base_w1 && dp->base_b1 && dp->head_w0 && dp->head_b0 &&
+                       dp->head_w1 && dp->head_b1 && dp->head_w2 && dp->head_b2 && dp->feat_w0 && dp->feat_b0 &&
+                       dp->feat_w1 && dp->feat_b1 && dp->feat_w2 && dp->feat_b2,
+                   "null parameter-gradient pointer");
+    UMHS_CHECK_ARG(!p->specular || (p->dir_w0 && p->dir_b0 && dp->dir_w0 && dp->dir_b0), "specular pointers missing");
+    const int bytes = umhs::TcBwd2::grp + 2 * (p->specular ? umhs::TcBwd2::grp_bytes_spec : umhs::TcBwd2::grp_bytes);
+    UMHS_CHECK_ARG(bytes <= 232448, "shared-memory plan exceeds 227 KB");
+    UMHS_CHECK_CUDA(cudaFuncSetAttribute(umhs::field_mlp_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         bytes));
+    // one persistent CTA per SM, two tiles per CTA iteration; never more CTAs than tile pairs
+    const int64_t n_pairs = ((n + umhs::TM - 1) / umhs::TM + 1) / 2;
+    const int grid = (int)(n_pairs < umhs::kNumSMs ? n_pairs : umhs::kNumSMs);
+    umhs::field_mlp_tc_bwd2_kernel<<<grid, umhs::TcBwd2::kThreads, bytes, umhs::as_stream(stream)>>>(*pts, n, enc, *p,
+                                                                                                    *g, d_enc, *dp);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}

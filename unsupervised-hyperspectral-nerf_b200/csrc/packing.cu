@@ -168,6 +168,8 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
                         if (n >= limit) return n;  // capacity-truncated ray
                         t0_out[n] = t_last;
                         t1_out[n] = t_last + dt;
+                    } else if (n < limit) {
+                        t0_out[n] = t_last;  // count pass: stage the interval starts (t1 = t0 + calc_dt(t0))
                     }
                     ++n;
                     t_last += dt;
@@ -189,8 +191,12 @@ march_kernel(umhs_march_args a, const int *__restrict__ level_any, int64_t *coun
     const float o[3] = {__ldg(a.rays_o + 3 * r), __ldg(a.rays_o + 3 * r + 1), __ldg(a.rays_o + 3 * r + 2)};
     const float d[3] = {__ldg(a.rays_d + 3 * r), __ldg(a.rays_d + 3 * r + 1), __ldg(a.rays_d + 3 * r + 2)};
     if (!WRITE) {
+        // with a staging buffer the count pass also records the first stage_stride interval starts of the ray, and
+        // the write pass turns into a coalesced copy (rays longer than the stride are re-marched there)
+        float *stage = a.stage ? a.stage + r * a.stage_stride : nullptr;
         counts[r] = march_ray<false>(o, d, a.binaries, a.aabbs, level_any, a.levels, a.resolution, __ldg(a.near_planes + r),
-                                     __ldg(a.far_planes + r), a.step_size, a.cone_angle, nullptr, nullptr, 0);
+                                     __ldg(a.far_planes + r), a.step_size, a.cone_angle, stage, nullptr,
+                                     stage ? a.stage_stride : 0);
     } else {
         const int64_t off = __ldg(packed_info + 2 * r), lim = __ldg(packed_info + 2 * r + 1);
         if (lim <= 0) return;
@@ -198,6 +204,39 @@ march_kernel(umhs_march_args a, const int *__restrict__ level_any, int64_t *coun
                                           __ldg(a.far_planes + r), a.step_size, a.cone_angle, t_starts + off,
                                           t_ends + off, lim);
         for (int64_t i = 0; i < n; ++i) ray_indices[off + i] = r;
+    }
+}
+
+// Write pass from the staging buffer: one warp per ray copies the staged interval starts to the packed arrays
+// (t_end = t_start + calc_dt(t_start): the same fp32 expression the march evaluates).  Rays with more samples
+// than the staging stride are re-marched by lane 0.
+__global__ void __launch_bounds__(256)
+march_write_staged_kernel(umhs_march_args a, const int *__restrict__ level_any, const int64_t *__restrict__ counts,
+                          const int64_t *__restrict__ packed_info, int64_t *__restrict__ ray_indices,
+                          float *__restrict__ t_starts, float *__restrict__ t_ends) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= a.n_rays) return;
+    const int64_t off = __ldg(packed_info + 2 * r), lim = __ldg(packed_info + 2 * r + 1);
+    if (lim <= 0) return;
+    const int64_t full = __ldg(counts + r);
+    if (full <= a.stage_stride) {
+        const float *src = a.stage + r * a.stage_stride;
+        for (int64_t i = lane; i < lim; i += 32) {
+            const float t0 = src[i];
+            const float dt = calc_dt(t0, a.cone_angle, a.step_size, 1e10f);
+            t_starts[off + i] = t0;
+            t_ends[off + i] = t0 + dt;
+            ray_indices[off + i] = r;
+        }
+    } else {
+        if (lane == 0) {
+            const float o[3] = {__ldg(a.rays_o + 3 * r), __ldg(a.rays_o + 3 * r + 1), __ldg(a.rays_o + 3 * r + 2)};
+            const float d[3] = {__ldg(a.rays_d + 3 * r), __ldg(a.rays_d + 3 * r + 1), __ldg(a.rays_d + 3 * r + 2)};
+            march_ray<true>(o, d, a.binaries, a.aabbs, level_any, a.levels, a.resolution, __ldg(a.near_planes + r),
+                            __ldg(a.far_planes + r), a.step_size, a.cone_angle, t_starts + off, t_ends + off, lim);
+        }
+        for (int64_t i = lane; i < lim; i += 32) ray_indices[off + i] = r;
     }
 }
 
@@ -436,6 +475,12 @@ extern "C" int umhs_march_write(const umhs_march_args *a, const int64_t *packed_
                                 float *t_starts, float *t_ends, void *stream) {
     UMHS_CHECK_ARG(check_march(a) == 0 && packed_info && ray_indices && t_starts && t_ends, "bad march arguments");
     if (a->n_rays <= 0) return UMHS_OK;
+    if (a->stage != nullptr && a->stage_stride > 0 && a->stage_counts != nullptr) {
+        march_write_staged_kernel<<<div_up(a->n_rays, 8), 256, 0, as_stream(stream)>>>(
+            *a, a->level_any, a->stage_counts, packed_info, ray_indices, t_starts, t_ends);
+        UMHS_CHECK_LAUNCH();
+        return UMHS_OK;
+    }
     march_kernel<true><<<div_up(a->n_rays, 64), 64, 0, as_stream(stream)>>>(*a, a->level_any, nullptr, packed_info,
                                                                             ray_indices, t_starts, t_ends);
     UMHS_CHECK_LAUNCH();

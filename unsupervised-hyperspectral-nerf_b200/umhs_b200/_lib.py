@@ -77,7 +77,7 @@ class CompositeGradsOut(Structure):
 class MarchArgs(Structure):
     _fields_ = [("rays_o", P), ("rays_d", P), ("near_planes", P), ("far_planes", P), ("binaries", P), ("aabbs", P),
                 ("levels", c_int32), ("resolution", c_int32), ("step_size", c_float), ("cone_angle", c_float),
-                ("n_rays", c_int64), ("level_any", P)]
+                ("n_rays", c_int64), ("level_any", P), ("stage", P), ("stage_counts", P), ("stage_stride", c_int32)]
 
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
@@ -96,6 +96,8 @@ _SIGNATURES = {
     "umhs_field_mlp_tc_fwd": [POINTER(Points), c_int64, P, POINTER(MlpParams), POINTER(FieldOut), P],
     "umhs_field_mlp_tc_bwd": [POINTER(Points), c_int64, P, POINTER(MlpParams), POINTER(FieldOutGrads), P,
                               POINTER(MlpGrads), P],
+    "umhs_field_mlp_tc_bwd2": [POINTER(Points), c_int64, P, POINTER(MlpParams), POINTER(FieldOutGrads), P,
+                               POINTER(MlpGrads), P],
     "umhs_debug_trace": [P, c_int32, P],
     "umhs_tc05_selftest": [c_int32, P, P, P, c_int32, c_int32, P],
     "umhs_composite_fwd": [POINTER(CompositeIn), POINTER(CompositeOut), P],

@@ -178,6 +178,11 @@ class UMHSTrainer:
         if isinstance(ray_bundle, tuple) and ray_bundle[0] == "staged":
             slot, ray_bundle, batch = self._unstage(ray_bundle)
         if self.occ_update:
+            if self.step % 16 == 0 and self.flat.data.is_cuda:
+                # the update synchronises anyway (torch.nonzero); draining the queue first lets the caching
+                # allocator reuse the blocks of the steps in flight instead of growing (measured: 3x faster updates
+                # when the host runs many graph replays ahead)
+                torch.cuda.current_stream(self.flat.data.device).synchronize()
             m.update_occupancy_grid(self.step, freeze_binaries=self.freeze_binaries)
         n_rays = int(ray_bundle.origins.shape[0])
         check = self.sync_free and (m.sample_capacity is None or self.opt_steps % self.capacity_check_every == 0)
