@@ -41,6 +41,10 @@ SHELL_R, SHELL_T = 0.5, 0.08
 WAVELENGTHS = np.linspace(400, 1000, BANDS).astype(int).tolist()
 CPU_SAMPLE_RAYS = 1024
 CONDITIONING_STEPS = 34
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+# (profiles/r1_ncu_full_summary.md, N = 825k samples, R = 16384 rays); None = not captured
+NCU_TRAFFIC = {"umhs_hash_encode_fwd": 204.9e6, "umhs_hash_encode_bwd": 151.3e6, "umhs_composite_fwd": 36.7e6,
+               "umhs_composite_bwd": 54.6e6, "umhs_adam_step": 480.7e6, "umhs_adam_step_dev": 480.7e6}
 
 
 # ------------------------------------------------------------------------------------------ synthetic scene
@@ -191,6 +195,7 @@ def algorithmic_bytes(name, units, samples_per_ray):
         "umhs_composite_fwd": None,
         "umhs_composite_bwd": None,
         "umhs_adam_step": 32,                                      # p,g,m,v read; p,m,v,g written
+        "umhs_adam_step_dev": 32,
     }.get(name, None)
     if name == "umhs_composite_fwd":
         S = samples_per_ray
@@ -198,6 +203,16 @@ def algorithmic_bytes(name, units, samples_per_ray):
     if name == "umhs_composite_bwd":
         S = samples_per_ray
         return units * (2 * S * (12 + 8 * K_CLASSES) + 8 * BANDS)
+    return None if per is None else units * per
+
+
+def algorithmic_flops(name, units):
+    """Algorithmic FLOPs per launch of the tensor-core MLP kernels (SURVEY 8(d): 2 x MACs/sample, K = 4, no specular;
+    the backward recomputes the forward and adds one dgrad + one wgrad GEMM per layer: 3 x forward)."""
+    base = 2 * (32 * 64 + 64 * 16)
+    heads = 2 * 2 * (27 * 64 + 64 * 64 + 64 * K_CLASSES)
+    per = {"umhs_density_tc_fwd": base, "umhs_field_mlp_tc_fwd": base + heads,
+           "umhs_field_mlp_tc_bwd": 3 * (base + heads)}.get(name)
     return None if per is None else units * per
 
 
@@ -359,19 +374,34 @@ def run_b200(args):
             peaks = json.load(open(pk_path))
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+        # kernels timed inside a long step: the sustained tensor figure when the driver measured one
+        tf_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1500.0)))
+        tf_src = ("MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else
+                  "MEASURED_PEAKS.json bf16_tflops" if "bf16_tflops" in peaks else "1500 TFLOP/s dense bf16 (fallback)")
         kernels = {}
         for name, d in summ.items():
             per_launch_ms = d["ms"] / d["calls"]
             ab = algorithmic_bytes(name, d["units"] / d["calls"], spr)
+            af = algorithmic_flops(name, d["units"] / d["calls"])
             kernels[name] = {"calls_per_step": d["calls"] / args.steps, "ms_per_step": d["ms"] / args.steps,
                              "ms_per_launch": per_launch_ms,
-                             "achieved_gbs": None if ab is None else ab / (per_launch_ms * 1e-3) / 1e9}
+                             "achieved_gbs": None if ab is None else ab / (per_launch_ms * 1e-3) / 1e9,
+                             "achieved_tflops": None if af is None else af / (per_launch_ms * 1e-3) / 1e12}
         total_k = sum(v["ms_per_step"] for v in kernels.values())
         top = max(kernels, key=lambda n: kernels[n]["ms_per_step"])
-        roof = {"kernel": top, "bound": "hbm", "achieved": kernels[top]["achieved_gbs"], "peak": hbm_peak,
-                "unit": "GB/s", "frac": (kernels[top]["achieved_gbs"] or 0.0) / hbm_peak, "traffic": None,
-                "peak_source": peak_src, "share_of_kernel_time": kernels[top]["ms_per_step"] / max(total_k, 1e-9),
-                "kernel_ms_per_step_sum": total_k}
+        share = {"share_of_kernel_time": kernels[top]["ms_per_step"] / max(total_k, 1e-9),
+                 "kernel_ms_per_step_sum": total_k, "traffic": NCU_TRAFFIC.get(top)}
+        if kernels[top]["achieved_tflops"] is not None:  # the fused MLP: the only dense contraction on the path
+            roof = {"kernel": top, "bound": "tensor", "achieved": kernels[top]["achieved_tflops"], "peak": tf_peak,
+                    "unit": "TFLOP/s", "frac": kernels[top]["achieved_tflops"] / tf_peak, "peak_source": tf_src, **share}
+        else:
+            roof = {"kernel": top, "bound": "hbm", "achieved": kernels[top]["achieved_gbs"], "peak": hbm_peak,
+                    "unit": "GB/s", "frac": (kernels[top]["achieved_gbs"] or 0.0) / hbm_peak, "peak_source": peak_src,
+                    **share}
+        # the HBM-bound kernels the north star asks about (gather, scatter, compositing, optimiser), same definition
+        roof["hbm_kernels"] = {n: {"achieved": v["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                                   "frac": v["achieved_gbs"] / hbm_peak, "traffic": NCU_TRAFFIC.get(n)}
+                               for n, v in kernels.items() if v["achieved_gbs"] is not None}
         cpu = time_oracle(steps=4, warmup=1) if world == 1 else None
         h2d = sum(t.numel() * t.element_size() for t in pinned[0])
         line = {"metric": "train rays/s", "value": world * R * args.steps / (ms * 1e-3), "unit": "rays/s",

@@ -145,14 +145,12 @@ int umhs_density_tc_fwd(const umhs_points *pts, int64_t n, const float *enc, con
                         void *stream);
 int umhs_field_mlp_tc_fwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
                           const umhs_field_out *out, void *stream);
+/* Backward: two 128-sample tiles in flight per SM (two data groups + one MMA-issuing warp), weight-gradient
+ * accumulators resident in TMEM for the whole persistent CTA. */
 int umhs_field_mlp_tc_bwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
                           const umhs_field_out_grads *g, float *d_enc, const umhs_mlp_grads *dp, void *stream);
-/* Same backward with two 128-sample tiles in flight per SM (9 warps: two data groups + one MMA-issuing warp);
- * the plugin's default.  Identical interface and results (same bf16 arithmetic) as umhs_field_mlp_tc_bwd. */
-int umhs_field_mlp_tc_bwd2(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
-                           const umhs_field_out_grads *g, float *d_enc, const umhs_mlp_grads *dp, void *stream);
 /* Developer aid: install (or with NULL remove) a device buffer of 4*capacity_slots int64 in which CTA 0 of the
- * tensor-core MLP kernels records (tag, clock64) pairs at the stages of every MMA round (threads 0 and 96). */
+ * tensor-core MLP backward records (tag, clock64) pairs: slot-major, [who = 0 data thread 0 | 1 issuer][tag, clock]. */
 int umhs_debug_trace(int64_t *buffer, int32_t capacity_slots, void *stream);
 /* One-CTA self-test of the three tcgen05 GEMM forms the MLP kernels are built from (fp32 in/out, bf16 operands):
  * mode 0: D[128xN] = A[128xK] B[NxK]^T; mode 1: D[128xN] = A[128xK] W[KxN]; mode 2: D[64xN] = P[128x64]^T Q[128xN]. */

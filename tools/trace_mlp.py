@@ -1,4 +1,6 @@
-"""Cycle trace of one CTA of the tensor-core MLP backward kernel: where does a round's latency go?"""
+"""Cycle trace of CTA 0 of the tensor-core MLP backward kernel: where does a round's latency go?
+who = 0: thread 0 of data group 0 (tag 2r = operands of round r written / arrive, 2r+1 = accumulators of round r ready);
+who = 1: the issuer (tag 1000 + 100*group + round, stamped after the commit)."""
 import sys
 
 sys.path.insert(0, ".")
@@ -9,7 +11,7 @@ from umhs_b200 import _lib, ops  # noqa: E402
 
 DEV = "cuda"
 g = torch.Generator().manual_seed(0)
-K, N = 4, 128 * 148 * 4
+K, N = 4, 128 * 148 * 8
 enc = torch.randn(N, 32, generator=g).to(DEV)
 pos = ((torch.rand(N, 3, generator=g) * 2 - 1)).to(DEV)
 mk = lambda o, i: ((torch.rand(o, i, generator=g) * 2 - 1) / i ** 0.5).to(DEV)  # noqa: E731
@@ -31,17 +33,12 @@ ops.field_mlp_bwd(pts, enc, w, K, False, 0.4, grads)
 torch.cuda.synchronize()
 lib.umhs_debug_trace(None, 0, torch.cuda.current_stream().cuda_stream)
 t = buf.view(cap, 2, 2).cpu()
-# thread 0 = issuer, thread 96 = a plain epilogue thread; print deltas for the second tile (16 rounds x 4 tags)
-for who in (0, 1):
-    ev = [(int(t[i, who, 0]), int(t[i, who, 1])) for i in range(cap) if int(t[i, who, 1]) != 0]
-    per_tile = 15 * 4
-    seg = ev[per_tile:2 * per_tile + 1]
-    print("thread", 0 if who == 0 else 96, "events:", len(ev))
-    names = {1: "epilogue done", 2: "barrier passed", 3: "issued/committed", 4: "accumulators ready"}
-    line = []
-    for (ta, ca), (tb, cb) in zip(seg[:-1], seg[1:]):
-        line.append(f"{names[ta][:9]}->{names[tb][:9]}:{cb - ca}")
-    for i in range(0, len(line), 4):
-        print("   ", " | ".join(line[i:i + 4]))
-    tot = seg[-1][1] - seg[0][1]
-    print("   cycles for the tile:", tot)
+ev = [(int(t[i, 0, 0]), int(t[i, 0, 1])) for i in range(cap) if int(t[i, 0, 1]) != 0]
+print("data thread events:", len(ev))
+seg = ev[32:65]  # second tile of group 0
+for (ta, ca), (tb, cb) in zip(seg[:-1], seg[1:]):
+    kind = "wait (issue + tensor core)" if tb % 2 == 1 else "epilogue"
+    print(f"  round {tb // 2:2d} {kind:28s} {cb - ca:6d} cycles")
+print("  cycles for the tile:", seg[-1][1] - seg[0][1])
+iv = [(int(t[i, 1, 0]), int(t[i, 1, 1])) for i in range(cap) if int(t[i, 1, 1]) != 0]
+print("issuer events:", len(iv), "first 40 (tag, delta):", [(a, d - c) for (a, d), (_, c) in zip(iv[1:41], iv[:40])])

@@ -40,6 +40,23 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major, int
     return d;
 }
 
+// One lane of a CONVERGED warp (all 32 lanes call this together with warp-uniform arguments).  The MMA-issuing
+// code must stay warp-uniform: inside a divergent `if (lane == 0)` the compiler wraps every tcgen05 instruction
+// (they live on the uniform datapath) in an elect/branch loop with register->uniform-register moves, which costs
+// ~100+ cycles per MMA on the single thread that paces the whole SM.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// Issued by ONE thread: call inside `if (elect_one()) { ... }` of a converged warp (one elect per MMA round).
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                        uint32_t accumulate) {
     asm volatile(
@@ -51,7 +68,7 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_
         : "memory");
 }
 
-// all previously issued MMAs of this thread arrive on `bar` when complete
+// all previously issued MMAs of this thread arrive on `bar` when complete (same elected thread as the MMAs)
 __device__ __forceinline__ void commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -71,6 +88,7 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // bounded wait: a wrong descriptor must fail loudly (trap), never hang the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 24); ++it) {
         uint32_t ok;
         asm volatile(
@@ -158,7 +176,7 @@ __device__ __forceinline__ void gemm_kmajor(uint32_t d_tmem, uint32_t a_saddr, u
     const uint32_t a_ch = 2048, b_ch = (uint32_t)b_rows * 16;
     uint64_t ad = make_desc(a_saddr, a_ch, 128);
     uint64_t bd = make_desc(b_saddr + (uint32_t)(b_row0 >> 3) * 128, b_ch, 128);
-#pragma unroll 1
+#pragma unroll
     for (int k = 0; k < K; k += 16) {
         mma_ss(d_tmem, ad, bd, idesc, (k > 0) ? 1u : accumulate);
         ad = desc_advance(ad, 2 * a_ch);
@@ -175,7 +193,7 @@ __device__ __forceinline__ void gemm_dgrad(uint32_t d_tmem, uint32_t a_saddr, ui
     uint64_t ad = make_desc(a_saddr, a_ch, 128);
     // MN-major: SBO = stride between 8-wide MN chunks (= w_ch), LBO = stride between 8-deep K groups (= 128)
     uint64_t bd = make_desc(w_saddr + (uint32_t)(w_row0 >> 3) * 128, 128, w_ch);
-#pragma unroll 1
+#pragma unroll
     for (int k = 0; k < K; k += 16) {
         mma_ss(d_tmem, ad, bd, idesc, (k > 0) ? 1u : accumulate);
         ad = desc_advance(ad, 2 * a_ch);
@@ -218,5 +236,79 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
 #pragma unroll
     for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+// ---- mbarrier: arrive / non-blocking test (issuer polling several groups)
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// ---- packed bf16x2 epilogue arithmetic: one instruction converts two fp32 accumulators (and applies ReLU)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// 0xffff per half where the (post-ReLU, hence >= +0) bf16 activation is positive
+__device__ __forceinline__ uint32_t relu_mask_bf16x2(uint32_t h) {
+    uint32_t m;
+    asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(h), "r"(0u));
+    return m;
+}
+
+// ---- TMEM -> registers, raw 32-bit words: 32 / 64 consecutive columns, one wait
+__device__ __forceinline__ void tmem_ld32_raw_nowait(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld64_raw(uint32_t taddr, uint32_t (&r)[64]) {
+    tmem_ld32_raw_nowait(taddr, r);
+    tmem_ld32_raw_nowait(taddr + 32u, r + 32);
+    tmem_wait_ld();
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    tmem_ld32_raw_nowait(taddr, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// One more K = 16 step whose A operand is the constant tile of ones: adds the bias column stored in the weight
+// tile at K columns [kcol, kcol + 16) (bias in column kcol, zeros behind it) to D[128 x N].
+__device__ __forceinline__ void gemm_bias_step(uint32_t d_tmem, uint32_t ones_saddr, uint32_t b_saddr, int b_rows,
+                                               int b_row0, int N, int kcol) {
+    const uint32_t b_ch = (uint32_t)b_rows * 16;
+    mma_ss(d_tmem, make_desc(ones_saddr, 2048, 128),
+           make_desc(b_saddr + (uint32_t)(b_row0 >> 3) * 128 + (uint32_t)(kcol >> 3) * b_ch, b_ch, 128),
+           make_idesc(128, N, 0, 0), 1u);
+}
+
 
 }  // namespace tc05

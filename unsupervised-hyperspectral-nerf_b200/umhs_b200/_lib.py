@@ -96,8 +96,6 @@ _SIGNATURES = {
     "umhs_field_mlp_tc_fwd": [POINTER(Points), c_int64, P, POINTER(MlpParams), POINTER(FieldOut), P],
     "umhs_field_mlp_tc_bwd": [POINTER(Points), c_int64, P, POINTER(MlpParams), POINTER(FieldOutGrads), P,
                               POINTER(MlpGrads), P],
-    "umhs_field_mlp_tc_bwd2": [POINTER(Points), c_int64, P, POINTER(MlpParams), POINTER(FieldOutGrads), P,
-                               POINTER(MlpGrads), P],
     "umhs_debug_trace": [P, c_int32, P],
     "umhs_tc05_selftest": [c_int32, P, P, P, c_int32, c_int32, P],
     "umhs_composite_fwd": [POINTER(CompositeIn), POINTER(CompositeOut), P],

@@ -25,15 +25,12 @@ _LAUNCHES = {"umhs_hash_encode_fwd": 1, "umhs_hash_encode_bwd": 1, "umhs_hash_en
              "umhs_accumulate_fwd": 1, "umhs_accumulate_bwd": 1, "umhs_march_count": 1, "umhs_march_level_any": 1, "umhs_pack_scan": 1,
              "umhs_march_write": 1, "umhs_visibility_mask": 1, "umhs_compact_samples": 1, "umhs_pack_info": 2,
              "umhs_occ_cell_points": 1, "umhs_occ_ema_update": 2, "umhs_occ_binarize": 2, "umhs_adam_step": 1,
-             "umhs_reduce_slabs": 1, "umhs_adam_step_dev": 1, "umhs_density_tc_fwd": 1, "umhs_field_mlp_tc_fwd": 1, "umhs_field_mlp_tc_bwd": 1, "umhs_field_mlp_tc_bwd2": 1, "umhs_debug_trace": 1,
+             "umhs_reduce_slabs": 1, "umhs_adam_step_dev": 1, "umhs_density_tc_fwd": 1, "umhs_field_mlp_tc_fwd": 1, "umhs_field_mlp_tc_bwd": 1, "umhs_debug_trace": 1,
              "umhs_tc05_selftest": 1}
 
 # "bf16": tensor-core MLP kernels (tcgen05 + TMEM, bf16 operands, fp32 accumulate) -- the default.
 # "fp32": fp32 SIMT MLP kernels (precise mode for tight parity tests).
 MLP_PRECISION = "bf16"
-# tensor-core backward variant: "umhs_field_mlp_tc_bwd2" (two tiles in flight per SM, default) or
-# "umhs_field_mlp_tc_bwd" (one tile per SM)
-TC_BWD_ENTRY = "umhs_field_mlp_tc_bwd2"
 
 
 class Profiler:
@@ -272,7 +269,7 @@ def field_mlp_bwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int
     for name in MLP_NAMES:
         setattr(dp, name, ptr(d_weights.get(name)))
     ps, ms = pts.struct(), mlp_struct(weights, K, specular, temperature)
-    _call(TC_BWD_ENTRY if MLP_PRECISION == "bf16" else "umhs_field_mlp_bwd", pts.units(), ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(g), ptr(d_enc),
+    _call("umhs_field_mlp_tc_bwd" if MLP_PRECISION == "bf16" else "umhs_field_mlp_bwd", pts.units(), ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(g), ptr(d_enc),
                                  ctypes.byref(dp), stream_ptr(dev))
     return d_enc, d_weights
 
