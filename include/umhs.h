@@ -155,6 +155,9 @@ int umhs_debug_trace(int64_t *buffer, int32_t capacity_slots, void *stream);
 /* One-CTA self-test of the three tcgen05 GEMM forms the MLP kernels are built from (fp32 in/out, bf16 operands):
  * mode 0: D[128xN] = A[128xK] B[NxK]^T; mode 1: D[128xN] = A[128xK] W[KxN]; mode 2: D[64xN] = P[128x64]^T Q[128xN]. */
 int umhs_tc05_selftest(int32_t mode, const float *A, const float *B, float *D, int32_t N, int32_t K, void *stream);
+/* Developer aid: cycles (device int64 [2]: issue only, issue + execution) of `reps` back-to-back GEMMs of one of the
+ * forms above (mode 3: one K = 16 bias step) on zeroed operands, one CTA. */
+int umhs_tc05_microbench(int32_t mode, int32_t N, int32_t K, int32_t reps, int64_t *cycles, void *stream);
 
 /* parameter gradients are ACCUMULATED (+=) into *dp; d_enc [n,32] is overwritten (may be NULL).
  * Activations are recomputed from enc; nothing else is kept from the forward pass. */

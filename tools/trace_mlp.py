@@ -1,6 +1,7 @@
 """Cycle trace of CTA 0 of the tensor-core MLP backward kernel: where does a round's latency go?
 who = 0: thread 0 of data group 0 (tag 2r = operands of round r written / arrive, 2r+1 = accumulators of round r ready);
 who = 1: the issuer (tag 1000 + 100*group + round, stamped after the commit)."""
+import os
 import sys
 
 sys.path.insert(0, ".")
@@ -24,12 +25,12 @@ w["dir_w0"] = w["dir_b0"] = None
 grads = {"d_sigma": torch.randn(N, device=DEV), "d_scalar": torch.randn(N, K, device=DEV),
          "d_abund": torch.randn(N, K, device=DEV), "d_embedding": None}
 pts = ops.PointSet.from_positions(pos)
-ops.field_mlp_bwd(pts, enc, w, K, False, 0.4, grads)
+ops.field_mlp_bwd(pts, enc, w, K, False, 0.4, grads, want_d_enc=os.environ.get("NO_DENC") is None)
 cap = 4096
 buf = torch.zeros(4 * cap, dtype=torch.int64, device=DEV)
 lib = _lib.load()
 lib.umhs_debug_trace(buf.data_ptr(), cap, torch.cuda.current_stream().cuda_stream)
-ops.field_mlp_bwd(pts, enc, w, K, False, 0.4, grads)
+ops.field_mlp_bwd(pts, enc, w, K, False, 0.4, grads, want_d_enc=os.environ.get("NO_DENC") is None)
 torch.cuda.synchronize()
 lib.umhs_debug_trace(None, 0, torch.cuda.current_stream().cuda_stream)
 t = buf.view(cap, 2, 2).cpu()
@@ -41,4 +42,4 @@ for (ta, ca), (tb, cb) in zip(seg[:-1], seg[1:]):
     print(f"  round {tb // 2:2d} {kind:28s} {cb - ca:6d} cycles")
 print("  cycles for the tile:", seg[-1][1] - seg[0][1])
 iv = [(int(t[i, 1, 0]), int(t[i, 1, 1])) for i in range(cap) if int(t[i, 1, 1]) != 0]
-print("issuer events:", len(iv), "first 40 (tag, delta):", [(a, d - c) for (a, d), (_, c) in zip(iv[1:41], iv[:40])])
+print("issuer events:", len(iv), "first 80 (tag, delta; 2xxx = operands ready seen, 1xxx = round issued):", [(a, d - c) for (a, d), (_, c) in zip(iv[1:81], iv[:80])])

@@ -98,7 +98,25 @@ __device__ __forceinline__ int64_t enc_row(const umhs_points &P, int64_t n) {
     return P.enc_index ? (int64_t)__ldg(P.enc_index + n) : n;
 }
 
-__device__ __forceinline__ Point eval_point(const umhs_points &P, int64_t n) {
+// The index-level loads of a point (first level of the dependent load chain), so that a kernel can issue them
+// early: ray index and interval of the ray form; nothing for explicit positions.
+struct PointIdx {
+    int64_t r;
+    float t0, t1;
+};
+__device__ __forceinline__ PointIdx load_point_idx(const umhs_points &P, int64_t n) {
+    PointIdx i;
+    i.r = 0;
+    i.t0 = i.t1 = 0.f;
+    if (P.positions == nullptr) {
+        i.r = __ldg(P.ray_indices + n);
+        i.t0 = __ldg(P.t_starts + n);
+        i.t1 = __ldg(P.t_ends + n);
+    }
+    return i;
+}
+
+__device__ __forceinline__ Point eval_point(const umhs_points &P, int64_t n, const PointIdx &pi) {
     Point p;
     if (P.positions != nullptr) {
         p.wx = __ldg(P.positions + 3 * n + 0);
@@ -113,8 +131,8 @@ __device__ __forceinline__ Point eval_point(const umhs_points &P, int64_t n) {
         }
         p.tmid = 0.0f;
     } else {
-        const int64_t r = __ldg(P.ray_indices + n);
-        const float tm = (__ldg(P.t_starts + n) + __ldg(P.t_ends + n));
+        const int64_t r = pi.r;
+        const float tm = (pi.t0 + pi.t1);
         p.dx = __ldg(P.rays_d + 3 * r + 0);
         p.dy = __ldg(P.rays_d + 3 * r + 1);
         p.dz = __ldg(P.rays_d + 3 * r + 2);
@@ -147,6 +165,10 @@ __device__ __forceinline__ Point eval_point(const umhs_points &P, int64_t n) {
     p.y = sel ? y : 0.0f;
     p.z = sel ? z : 0.0f;
     return p;
+}
+
+__device__ __forceinline__ Point eval_point(const umhs_points &P, int64_t n) {
+    return eval_point(P, n, load_point_idx(P, n));
 }
 
 }  // namespace umhs

@@ -204,6 +204,47 @@ struct Tracer {
     }
 };
 
+// ---- coalesced movement of [128 x 32] fp32 row blocks (hash encodings in, their gradients out).
+// A thread-per-row access (128 B per lane at a 128 B stride) costs 32 L1 wavefronts per warp instruction; here a warp
+// instruction covers 4 whole rows: lane l handles the 16-byte piece (l & 7) of row 4 * i + (l >> 3), i = 0..7.
+// load: rows come from this warp's own lanes (row index held by lane 4 * i + (l >> 3), shuffled)
+__device__ __forceinline__ void load_enc_rows(const float *__restrict__ enc, int64_t my_row, int lane, float4 (&e)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t r = __shfl_sync(kFull, my_row, 4 * i + (lane >> 3));
+        e[i] = __ldg(reinterpret_cast<const float4 *>(enc + r * 32) + (lane & 7));
+    }
+}
+// ... and go to the bf16 operand tile as 8-byte pieces (4 columns) of rows warp_row0 + 4 * i + (l >> 3)
+__device__ __forceinline__ void store_enc_rows(uint8_t *tile, int warp_row0, int lane, const float4 (&e)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = warp_row0 + 4 * i + (lane >> 3);
+        uint2 q;
+        q.x = pack_bf16x2(e[i].x, e[i].y);
+        q.y = pack_bf16x2(e[i].z, e[i].w);
+        *reinterpret_cast<uint2 *>(tile + tile_off(r, 4 * (lane & 7), CH_ACT)) = q;
+    }
+}
+// store: every lane holds its own row v[32]; the warp transposes through a private 4 KB staging block (XOR-swizzled
+// 16-byte pieces: conflict-free both ways) and writes whole rows.  row_of_lane < 0: that row is not written.
+__device__ __forceinline__ void store_rows_coalesced(float *__restrict__ dst, int64_t my_row, const float (&v)[32],
+                                                     uint8_t *stage, int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4 *>(stage + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+            make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rl = 4 * i + (lane >> 3);
+        const int64_t r = __shfl_sync(kFull, my_row, rl);
+        const float4 x = *reinterpret_cast<const float4 *>(stage + rl * 128 + (((lane & 7) ^ (rl & 7)) << 4));
+        if (r >= 0) reinterpret_cast<float4 *>(dst + r * 32)[lane & 7] = x;
+    }
+}
+
 // ---- group <-> issuer handshake
 struct GroupSync {
     uint64_t *ready, *done;
@@ -212,17 +253,23 @@ struct GroupSync {
     Tracer tr;
     int round = 0;
     // operand tiles written & accumulators consumed -> issuer may run this group's next round; wait for its MMAs
-    __device__ __forceinline__ void round_trip() {
+    __device__ __forceinline__ void arrive() {
         tr.stamp(2 * round);
-        fence_proxy_async();
+        fence_proxy_async();  // NB: also waits for this thread's outstanding GLOBAL stores -- keep those behind it
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(ready);
+    }
+    __device__ __forceinline__ void wait() {
         mbar_wait(done, parity);
         parity ^= 1u;
         fence_after_sync();
         tr.stamp(2 * round + 1);
         ++round;
+    }
+    __device__ __forceinline__ void round_trip() {
+        arrive();
+        wait();
     }
 };
 
@@ -256,6 +303,7 @@ __device__ __forceinline__ void issuer_rotation(uint64_t *bars, const int64_t (&
                     mbar_wait(bars + g, par[g]);
                     par[g] ^= 1u;
                     fence_after_sync();
+                    tr.stamp(2000 + 100 * g + decltype(rc)::value);
                     if (elect_one()) {
                         issue(rc, gc, (it == 0 && g == 0) ? 0u : 1u);
                         commit(bars + G + g);
@@ -285,7 +333,7 @@ struct TcFwd {
 };
 
 template <bool DENSITY_ONLY>
-__global__ void __launch_bounds__(TcFwd::kThreads, 1)
+__global__ void __launch_bounds__(TcFwd::kThreads, 1)  // 17 warps: 5 on one SM sub-partition (16K registers) -> 96
 field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict__ enc, umhs_mlp_params mp,
                         umhs_field_out out) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -370,18 +418,11 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             const int64_t n = valid ? n0 + row : n_total - 1;  // tail threads shadow the last sample, write nothing
             const Point pt = eval_point(P, n);
             float pe[12];
-            // ---------------- round 0: enc -> tX ; base0
+            // ---------------- round 0: enc -> tX (whole rows, coalesced) ; base0
             {
-                const float4 *e4 = reinterpret_cast<const float4 *>(enc + enc_row(P, n) * 32);
                 float4 e[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) e[c] = __ldg(e4 + c);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float v[8] = {e[2 * c].x, e[2 * c].y, e[2 * c].z, e[2 * c].w,
-                                        e[2 * c + 1].x, e[2 * c + 1].y, e[2 * c + 1].z, e[2 * c + 1].w};
-                    store8(tX, row, 8 * c, CH_ACT, v);
-                }
+                load_enc_rows(enc, enc_row(P, n), lane, e);
+                store_enc_rows(tX, (warp & 3) * 32, lane, e);
             }
             if (!DENSITY_ONLY) pos_encoding_tc(pt, pe);
             gs.round_trip();
@@ -521,34 +562,32 @@ struct TcBwd {
 };
 static_assert(TcBwd::smem_bytes <= 232448, "shared-memory plan exceeds 227 KB");
 
-// Column sums of a [32 rows x 16] block held one row per lane, by a butterfly transpose-reduce (16 shuffles instead
-// of 80): returns, in every lane, the sum over the warp of column colsum16_col(lane).
-__device__ __forceinline__ int colsum16_col(int lane) { return (lane >> 1) & 15; }
-__device__ __forceinline__ float warp_colsum16(const float *v, int lane) {
-    float a[8], b[4], c[2], d;
-    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+// Column sums of a [32 rows x KM] block held one row per lane (KM = 4, 8, 16), by a butterfly transpose-reduce
+// (KM - 1 + log2(32 / KM) shuffles instead of 5 * KM): returns, in every lane, the sum over the warp of column
+// colsum_col<KM>(lane).
+template <int KM>
+__device__ __forceinline__ int colsum_col(int lane) { return lane / (32 / KM); }
+template <int KM>
+__device__ __forceinline__ bool colsum_owner(int lane) { return (lane & (32 / KM - 1)) == 0; }
+template <int KM>
+__device__ __forceinline__ float warp_colsum(const float *v, int lane) {
+    float a[KM];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {  // keep columns with bit 3 == h4
-        const float keep = h4 ? v[i + 8] : v[i], send = h4 ? v[i] : v[i + 8];
-        a[i] = keep + __shfl_xor_sync(kFull, send, 16);
+    for (int i = 0; i < KM; ++i) a[i] = v[i];
+    int off = 16;
+#pragma unroll
+    for (int width = KM; width > 1; width >>= 1, off >>= 1) {
+        const bool hi = lane & off;  // lanes with this bit keep the upper half of the remaining columns
+#pragma unroll
+        for (int i = 0; i < width / 2; ++i) {
+            const float keep = hi ? a[i + width / 2] : a[i], send = hi ? a[i] : a[i + width / 2];
+            a[i] = keep + __shfl_xor_sync(kFull, send, off);
+        }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {  // bit 2 == h3
-        const float keep = h3 ? a[i + 4] : a[i], send = h3 ? a[i] : a[i + 4];
-        b[i] = keep + __shfl_xor_sync(kFull, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {  // bit 1 == h2
-        const float keep = h2 ? b[i + 2] : b[i], send = h2 ? b[i] : b[i + 2];
-        c[i] = keep + __shfl_xor_sync(kFull, send, 4);
-    }
-    {
-        const float keep = h1 ? c[1] : c[0], send = h1 ? c[0] : c[1];
-        d = keep + __shfl_xor_sync(kFull, send, 2);
-    }
-    return d + __shfl_xor_sync(kFull, d, 1);
+    for (; off > 0; off >>= 1) a[0] += __shfl_xor_sync(kFull, a[0], off);
+    return a[0];
 }
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // flush one persistent [64 x ncols] accumulator: this thread's row r = 16*warp + lane (lane < 16)
 template <class F>
@@ -564,7 +603,9 @@ __device__ __forceinline__ void flush_acc(uint32_t trow, int col0, int ncols, in
     }
 }
 
-__global__ void __launch_bounds__(TcBwd::kThreads, 1)
+// KM: compile-time bound on the number of classes K (4, 8 or 16): sizes the softmax / sigmoid epilogues
+template <int KM>
+__global__ void __launch_bounds__(TcBwd::kThreads, 1)  // 9 warps: 3 on one SM sub-partition (16K registers) -> 168
 field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict__ enc, umhs_mlp_params mp,
                         umhs_field_out_grads g, float *__restrict__ d_enc, umhs_mlp_grads dp) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -680,27 +721,32 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         const uint32_t trow = tbase + ((uint32_t)((warp & 3) * 32) << 16) + 64u * grp;
         float *sb_h2 = sbias, *sb_f2 = sbias + 16, *sb_b1 = sbias + 48;   // [16], [32], [16]
         const float invT = 1.0f / mp.temperature;
-        // narrow-layer bias gradients: per-lane running sums of column colsum16_col(lane) (see warp_colsum16)
+        // narrow-layer bias gradients: per-lane running sums of column colsum_col<KM>(lane) (see warp_colsum)
         float bs_h2 = 0.f, bs_f2 = 0.f, bs_f2s = 0.f, bs_b1 = 0.f;
-        // the next tile's inputs are pulled into L2 while this tile computes
-        auto prefetch_tile = [&](int64_t tile) {
-            if (tile >= n_tiles) return;
-            const int64_t m = tile * TM + row, nn = m < n_total ? m : n_total - 1;
-            if (P.positions != nullptr) {
-                prefetch_l2(P.positions + 3 * nn);
-            } else {
-                prefetch_l2(P.ray_indices + nn);
-                prefetch_l2(P.t_starts + nn);
-                prefetch_l2(P.t_ends + nn);
-            }
-            if (P.enc_index) prefetch_l2(P.enc_index + nn);
-            else prefetch_l2(enc + nn * 32);
-            if (g.d_sigma) prefetch_l2(g.d_sigma + nn);
-            prefetch_l2(g.d_scalar + nn * K);
-            prefetch_l2(g.d_abund + nn * K);
-            if (g.d_embedding) prefetch_l2(g.d_embedding + nn * 15);
-            if (spec && g.d_spec_hidden) prefetch_l2(g.d_spec_hidden + nn * 16);
+        // Inputs of a tile (hash encoding row + sample geometry).  They sit behind a chain of dependent loads
+        // (ray index -> origin / direction, enc_index -> encoding row), so the NEXT tile's are fetched during the
+        // feature_mlp backward rounds of the current one (a DRAM latency is ~2k cycles, about two rounds).
+        float4 e_in[8];
+        Point pt_in;
+        PointIdx pi_in;
+        int64_t erow_in;
+        auto sample_of = [&](int64_t tile) {
+            const int64_t m = tile * TM + row;
+            return m < n_total ? m : n_total - 1;
         };
+        auto load_idx = [&](int64_t tile) {
+            if (tile >= n_tiles) return;
+            const int64_t nn = sample_of(tile);
+            pi_in = load_point_idx(P, nn);
+            erow_in = enc_row(P, nn);
+        };
+        auto load_rest = [&](int64_t tile) {
+            if (tile >= n_tiles) return;  // group-uniform
+            load_enc_rows(enc, erow_in, lane, e_in);
+            pt_in = eval_point(P, sample_of(tile), pi_in);
+        };
+        load_idx(tile_of(0, grp));
+        load_rest(tile_of(0, grp));
 
         for (int64_t it = 0; tile_of(it, grp) < n_tiles; ++it) {
             gs.round = 0;
@@ -709,23 +755,11 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             const int64_t n = valid ? n0 + row : n_total - 1;
             // Invalid (tail) rows shadow the last sample and run the whole chain with ZERO incoming gradients: every
             // delta they produce is exactly zero, so they add nothing to the weight gradients and write nothing.
-            const Point pt = eval_point(P, n);
+            const Point pt = pt_in;
             float pe[12];
             pos_encoding_tc(pt, pe);
-            prefetch_tile(tile_of(it + 1, grp));
             // ---------------- round 0: enc -> tA0 [, X2 -> tX2]
-            {
-                const float4 *e4 = reinterpret_cast<const float4 *>(enc + enc_row(P, n) * 32);
-                float4 e[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) e[c] = __ldg(e4 + c);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float v[8] = {e[2 * c].x, e[2 * c].y, e[2 * c].z, e[2 * c].w,
-                                        e[2 * c + 1].x, e[2 * c + 1].y, e[2 * c + 1].z, e[2 * c + 1].w};
-                    store8(tA0, row, 8 * c, CH_ACT, v);
-                }
-            }
+            store_enc_rows(tA0, (warp & 3) * 32, lane, e_in);
             if (spec) {
                 float x2[32], sh[16];
                 sh_deg3_tc((pt.dx + 1.0f) / 2.0f, (pt.dy + 1.0f) / 2.0f, (pt.dz + 1.0f) / 2.0f, sh);
@@ -795,42 +829,50 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                 gs.round_trip();  // layer 1
                 epi_relu64<false>(trow, tH2, row, nullptr);
                 // incoming gradients of this MLP's outputs: fetched while the tensor core runs the last layer
-                float gin[17];
+                float gin[KM + 1];
 #pragma unroll
-                for (int k = 0; k < 16; ++k)
+                for (int k = 0; k < KM; ++k)
                     gin[k] = (valid && k < K) ? __ldg((m ? g.d_abund : g.d_scalar) + n * K + k) : 0.f;
-                gin[16] = (valid && m == 1 && spec && g.d_s1) ? __ldg(g.d_s1 + n) : 0.f;
+                gin[KM] = (valid && m == 1 && spec && g.d_s1) ? __ldg(g.d_s1 + n) : 0.f;
                 gs.round_trip();  // layer 2
                 {
-                    float z[32], dz[32];
+                    // z: logits 0..KM-1 and (feature_mlp with specular) the gate logit, which sits at column K
+                    float z[KM + 1], dz[32];
                     {
                         float t16[16];
                         tmem_ld16(trow, t16);
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) z[k] = t16[k];
-                        if (m == 1) tmem_ld16(trow + 16, t16);
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) z[16 + k] = (m == 1) ? t16[k] : 0.f;
+                        for (int k = 0; k < KM; ++k) z[k] = t16[k];
+                        if (KM == 16) {
+                            if (m == 1) tmem_ld16(trow + 16, t16);  // warp-uniform
+                            z[KM] = t16[0];
+                        } else {
+                            z[KM] = t16[KM];
+                        }
                     }
 #pragma unroll
                     for (int k = 0; k < 32; ++k) dz[k] = 0.f;
                     if (m == 0) {
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) {
+                        for (int k = 0; k < KM; ++k) {
                             if (k < K) {
                                 const float s = __frcp_rn(1.0f + __expf(-z[k]));
                                 dz[k] = gin[k] * s * (1.0f - s);
                             }
                         }
                     } else {
-                        float mx = -3.0e38f, e[16], den = 0.f, dot = 0.f;
+                        float zs = z[KM];  // raw gate logit when K == KM
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) {
+                        for (int k = 0; k < KM; ++k)
+                            if (k == K) zs = z[k];
+                        float mx = -3.0e38f, e[KM], den = 0.f, dot = 0.f;
+#pragma unroll
+                        for (int k = 0; k < KM; ++k) {
                             z[k] *= invT;
                             if (k < K) mx = fmaxf(mx, z[k]);
                         }
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) {
+                        for (int k = 0; k < KM; ++k) {
                             e[k] = (k < K) ? __expf(z[k] - mx) : 0.f;
                             den += e[k];
                             dot += e[k] * gin[k];
@@ -838,18 +880,12 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                         const float rden = __frcp_rn(den);
                         dot *= rden;
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) dz[k] = e[k] * rden * invT * (gin[k] - dot);
+                        for (int k = 0; k < KM; ++k) dz[k] = e[k] * rden * invT * (gin[k] - dot);
                         if (spec) {
-                            // logit K of feature_mlp is the specular gate s1 (raw value: undo the /T applied above
-                            // only for columns < 16; column 16 lives in z[16] untouched)
-                            float zs = z[16];
-#pragma unroll
-                            for (int k = 0; k < 16; ++k)
-                                if (k == K) zs = z[k] * mp.temperature;
                             const float s = __frcp_rn(1.0f + __expf(-zs));
-                            const float ds = gin[16] * s * (1.0f - s);
+                            const float ds = gin[KM] * s * (1.0f - s);
 #pragma unroll
-                            for (int k = 0; k < 17; ++k)
+                            for (int k = 0; k <= KM; ++k)
                                 if (k == K) dz[k] = ds;
                         }
                     }
@@ -859,15 +895,17 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                         store8(tD2, row, 16, CH_ACT, dz + 16);
                         store8(tD2, row, 24, CH_ACT, dz + 24);
                     }
-                    if (m == 0) bs_h2 += warp_colsum16(dz, lane);
+                    if (m == 0) bs_h2 += warp_colsum<KM>(dz, lane);
                     else {
-                        bs_f2 += warp_colsum16(dz, lane);
-                        if (nout > 16) bs_f2s += warp_sum(dz[16]);
+                        bs_f2 += warp_colsum<KM>(dz, lane);
+                        if (nout > KM) bs_f2s += warp_sum(dz[KM]);
                     }
                 }
+                if (m == 1) load_idx(tile_of(it + 1, grp));   // next tile: index level of the dependent loads ...
                 gs.round_trip();  // d layer 2
                 epi_mask64(trow, tH2, nullptr, tD1, row);
                 gs.round_trip();  // d layer 1
+                if (m == 1) load_rest(tile_of(it + 1, grp));  // ... then the rows: a DRAM latency ahead of their use
                 epi_mask64(trow, tH1, nullptr, tD2, row);
                 gs.round_trip();  // d layer 0
             }
@@ -884,7 +922,7 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                 for (int i = 0; i < 15; ++i) dO[1 + i] = demb[i];
                 store8(tD2, row, 0, CH_ACT, dO);
                 store8(tD2, row, 8, CH_ACT, dO + 8);
-                bs_b1 += warp_colsum16(dO, lane);
+                bs_b1 += warp_colsum<16>(dO, lane);
                 // H0 back into tH1 (operand of the base layer-1 weight gradient)
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
@@ -895,22 +933,19 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             epi_mask64(trow, nullptr, h0p, tD1, row);
             gs.round_trip();
             if (d_enc) {
+                // whole rows, coalesced, through this warp's 4 KB of the (now idle) tD2 tile
                 float v[32];
                 tmem_ld32(trow, v);
-                if (valid) {
-                    float4 *dst = reinterpret_cast<float4 *>(d_enc + n * 32);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                }
+                store_rows_coalesced(d_enc, valid ? n : -1, v, tD2 + (warp & 3) * 4096, lane);
             }
         }
-        if ((lane & 1) == 0) {  // one lane of each pair owns column colsum16_col(lane)
-            const int col = colsum16_col(lane);
+        if (colsum_owner<KM>(lane)) {  // one lane of each run owns column colsum_col<KM>(lane)
+            const int col = colsum_col<KM>(lane);
             if (bs_h2 != 0.f) atomicAdd(sb_h2 + col, bs_h2);
             if (bs_f2 != 0.f) atomicAdd(sb_f2 + col, bs_f2);
-            if (bs_b1 != 0.f) atomicAdd(sb_b1 + col, bs_b1);
-            if (lane == 0 && bs_f2s != 0.f) atomicAdd(sb_f2 + 16, bs_f2s);
         }
+        if (colsum_owner<16>(lane) && bs_b1 != 0.f) atomicAdd(sb_b1 + colsum_col<16>(lane), bs_b1);
+        if (lane == 0 && bs_f2s != 0.f) atomicAdd(sb_f2 + KM, bs_f2s);
     }
 
     // ================= flush the weight-gradient accumulators: row r = 16 * (warp & 3) + lane (lane < 16)
@@ -1032,6 +1067,50 @@ tc05_selftest_kernel(int mode, const float *__restrict__ A, const float *__restr
     if (warp == 0) tmem_dealloc<128>(tbase);
 }
 
+// ------------------------------------------------------------------ tcgen05 issue / execution micro-benchmark (one CTA)
+// `reps` back-to-back GEMMs of one form on zeroed tiles: out[0] = cycles to ISSUE them (one elected thread),
+// out[1] = cycles until their commit arrives.  mode as in the self-test; mode 3 = bias step (one K = 16 MMA).
+__global__ void __launch_bounds__(TM)
+tc05_microbench_kernel(int mode, int N, int K, int reps, long long *out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *tA = smem, *tB = smem + 32768;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 65536);
+    uint32_t *slot = reinterpret_cast<uint32_t *>(smem + 65536 + 16);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 65536 / 16; i += TM) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<128>(slot);
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tbase = *slot;
+    if (warp == 0) {
+        if (elect_one()) {
+            const long long t0 = clock64();
+            for (int i = 0; i < reps; ++i) {
+                if (mode == 0) gemm_kmajor(tbase, smem_u32(tA), smem_u32(tB), N, 0, N, K, 1);
+                else if (mode == 1) gemm_dgrad(tbase, smem_u32(tA), smem_u32(tB), K, 0, N, K, 1);
+                else if (mode == 2) gemm_wgrad(tbase, smem_u32(tA), 0, smem_u32(tB), 0, N, 1);
+                else gemm_bias_step(tbase, smem_u32(tA), smem_u32(tB), N, 0, N, 0);
+            }
+            const long long t1 = clock64();
+            commit(bar);
+            mbar_wait(bar, 0);
+            const long long t2 = clock64();
+            out[0] = t1 - t0;
+            out[1] = t2 - t0;
+        }
+        __syncwarp();
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<128>(tbase);
+}
+
 __global__ void set_trace_kernel(long long *buf, int cap) {
     g_trace = buf;
     g_trace_cap = cap;
@@ -1062,6 +1141,16 @@ extern "C" int umhs_tc05_selftest(int32_t mode, const float *A, const float *B, 
     const int bytes = 65536 + 128;
     UMHS_CHECK_CUDA(cudaFuncSetAttribute(tc05_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     tc05_selftest_kernel<<<1, TM, bytes, as_stream(stream)>>>(mode, A, B, D, N, K);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_tc05_microbench(int32_t mode, int32_t N, int32_t K, int32_t reps, int64_t *cycles, void *stream) {
+    UMHS_CHECK_ARG(cycles && mode >= 0 && mode <= 3 && N >= 8 && N <= 128 && N % 8 == 0 && K >= 16 && K <= 128 &&
+                       K % 16 == 0 && reps >= 1, "bad argument");
+    const int bytes = 65536 + 128;
+    UMHS_CHECK_CUDA(cudaFuncSetAttribute(tc05_microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    tc05_microbench_kernel<<<1, TM, bytes, as_stream(stream)>>>(mode, N, K, reps, reinterpret_cast<long long *>(cycles));
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }
@@ -1109,10 +1198,11 @@ extern "C" int umhs_field_mlp_tc_bwd(const umhs_points *pts, int64_t n, const fl
                        dp->feat_w1 && dp->feat_b1 && dp->feat_w2 && dp->feat_b2,
                    "null parameter-gradient pointer");
     UMHS_CHECK_ARG(!p->specular || (p->dir_w0 && p->dir_b0 && dp->dir_w0 && dp->dir_b0), "specular pointers missing");
-    UMHS_CHECK_CUDA(cudaFuncSetAttribute(field_mlp_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TcBwd::smem_bytes));
-    field_mlp_tc_bwd_kernel<<<tc_grid(n, TcBwd::G), TcBwd::kThreads, TcBwd::smem_bytes, as_stream(stream)>>>(
-        *pts, n, enc, *p, *g, d_enc, *dp);
+    auto kernel = p->num_classes <= 4 ? field_mlp_tc_bwd_kernel<4>
+                : p->num_classes <= 8 ? field_mlp_tc_bwd_kernel<8> : field_mlp_tc_bwd_kernel<16>;
+    UMHS_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcBwd::smem_bytes));
+    kernel<<<tc_grid(n, TcBwd::G), TcBwd::kThreads, TcBwd::smem_bytes, as_stream(stream)>>>(*pts, n, enc, *p, *g, d_enc,
+                                                                                          *dp);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }

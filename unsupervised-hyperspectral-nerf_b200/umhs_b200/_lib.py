@@ -98,6 +98,7 @@ _SIGNATURES = {
                               POINTER(MlpGrads), P],
     "umhs_debug_trace": [P, c_int32, P],
     "umhs_tc05_selftest": [c_int32, P, P, P, c_int32, c_int32, P],
+    "umhs_tc05_microbench": [c_int32, c_int32, c_int32, c_int32, P, P],
     "umhs_composite_fwd": [POINTER(CompositeIn), POINTER(CompositeOut), P],
     "umhs_depth_clip": [P, c_int64, P, P],
     "umhs_composite_bwd": [POINTER(CompositeIn), POINTER(CompositeGradsIn), POINTER(CompositeGradsOut), P],
