@@ -261,6 +261,9 @@ typedef struct {
     float step_size, cone_angle;
     int64_t n_rays;
     const int32_t *level_any;        /* [8] device flags from umhs_march_level_any, or NULL (always fetch occupancy) */
+    const uint32_t *occ_bits;        /* optional bit-packed copy of binaries from umhs_occ_pack_bits
+                                        ([levels, ceil(res^3 / 32)] words, bit b of word w = cell 32 w + b), or NULL:
+                                        256 KB per 128^3 level instead of 2 MiB, so the march's lookups hit L1 */
     /* optional staging: umhs_march_count also records the first stage_stride interval starts of every ray in
      * stage[R, stage_stride]; umhs_march_write then copies them (stage_counts = the counts array of that call)
      * instead of marching again.  Identical outputs; NULL / 0 disables. */
@@ -271,6 +274,9 @@ typedef struct {
 
 /* level_any[l] = 1 iff grid level l holds an occupied cell (lets the march skip occupancy fetches there) */
 int umhs_march_level_any(const umhs_march_args *a, int32_t *level_any /*[8]*/, void *stream);
+
+/* bits + level_any in one pass over binaries (the march reads the bits when a->occ_bits is set) */
+int umhs_occ_pack_bits(const umhs_march_args *a, uint32_t *bits, int32_t *level_any /*[8]*/, void *stream);
 
 int umhs_march_count(const umhs_march_args *a, int64_t *counts, void *stream);
 /* packed_info[r] = (exclusive_scan(counts)[r], counts[r]); counts [R] int64 in, packed_info [R,2] int64 out.

@@ -90,7 +90,8 @@ def _grid(res, seed, fill=0.35):
 
 @pytest.mark.parametrize("R,res,cone,far,variant", [(2048, 32, 0.004, 1e3, 0), (4096, 128, 0.004, 1e3, 0),
                                                     (777, 64, 0.0, 1e10, 0), (1, 32, 0.004, 1e3, 0),
-                                                    (3000, 64, 0.004, 1e3, 1), (3000, 128, 0.004, 1e3, 2)])
+                                                    (3000, 64, 0.004, 1e3, 1), (3000, 128, 0.004, 1e3, 2),
+                                                    (500, 30, 0.004, 1e3, 0)])
 def test_march_bit_exact(R, res, cone, far, variant):
     ops = _ops()
     o, d, jit = _rays(max(R, 3), 10 + R)
@@ -111,14 +112,16 @@ def test_march_bit_exact(R, res, cone, far, variant):
     farp = torch.full((R,), far)
     ri_r, t0_r, t1_r, pk_r = pack_oracle.traverse_grids(o, d, b, aabbs, near, farp, step, cone)
     assert ri_r.numel() > 0 or R == 1
-    # staged write pass (default), staging too small for most rays (re-march fallback), staging off
-    for stage in (192, 8, 0):
+    # staged write pass (default), staging too small for most rays (re-march fallback), staging off;
+    # bit-packed occupancy lookups (default) and the byte grid
+    for stage, use_bits in ((192, True), (8, True), (0, True), (192, False)):
         old_stage, ops.MARCH_STAGE = ops.MARCH_STAGE, stage
+        old_bits, ops.MARCH_BITS = ops.MARCH_BITS, use_bits
         try:
             ri, t0, t1, pk, tot = ops.march(o.to(DEV), d.to(DEV), near.to(DEV), farp.to(DEV), b.to(DEV), aabbs.to(DEV),
                                             step, cone)
         finally:
-            ops.MARCH_STAGE = old_stage
+            ops.MARCH_STAGE, ops.MARCH_BITS = old_stage, old_bits
         assert int(tot[0]) == int(tot[1]) == ri_r.numel()
         assert np.array_equal(pk.cpu().numpy(), pk_r.numpy())
         assert np.array_equal(ri.cpu().numpy(), ri_r.numpy())

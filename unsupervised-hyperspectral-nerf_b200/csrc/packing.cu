@@ -56,6 +56,63 @@ __device__ __forceinline__ int voxel_index(float v, float fres, int res) {
     return clampi((int)v, 0, res - 1);
 }
 
+// First point of the orbit t -> t + dt(t), dt(t) = clamp(t * cone_angle, step, 1e10), with t + dt/2 >= target:
+// what the oracle reaches by stepping (`for (;;) { dt = calc_dt(t); if (t + dt * 0.5f >= target) break; t += dt; }`).
+//
+// Bit-exact shortcut for the stretch where dt == step (t * cone_angle < step: all of a bounded scene at the
+// reference's cone angle).  Inside one binade [2^e, 2^(e+1)) every orbit point is a multiple of u = 2^(e-23), and
+// fl(t + step) - t is the SAME multiple of u at every point (step rounded to the grid; the only exception, step
+// exactly half-way between two grid points, is left to the plain loop).  So k steps are the integer update
+// m += k * inc on the mantissa, k is found from the target by one division and corrected with the oracle's own fp32
+// test, and only the step that leaves the binade is taken with a real fp32 add.  A few dozen instructions instead of
+// hundreds of dependent iterations per gap.
+__device__ __forceinline__ float advance_orbit(float t, float target, float cone_angle, float step) {
+    const float half = step * 0.5f;  // dt * 0.5f while dt == step
+    for (;;) {
+        float dt = calc_dt(t, cone_angle, step, 1e10f);
+        if (t + dt * 0.5f >= target) return t;
+        const uint32_t tb = __float_as_uint(t), sb = __float_as_uint(step);
+        const int e = (int)(tb >> 23) - 127, es = (int)(sb >> 23) - 127;  // t > 0, step > 0: sign bits clear
+        const int sh = e - es;                                            // step = ms * 2^(es-23), u = 2^(e-23)
+        const bool normal = t > 0.0f && (tb >> 23) != 0 && (tb >> 23) != 255 && (sb >> 23) != 0 && dt == step;
+        bool fast = normal && sh < 24;
+        uint32_t inc = 0;
+        if (fast) {
+            const uint32_t ms = (sb & 0x7fffffu) | 0x800000u;
+            if (sh <= 0) {
+                fast = sh > -8;  // step is a multiple of u: no rounding at all
+                inc = fast ? (ms << (-sh)) : 0u;
+            } else {
+                const uint32_t rem = ms & ((1u << sh) - 1u), halfbit = 1u << (sh - 1);
+                fast = rem != halfbit;                   // a tie rounds to even: alternating increments
+                inc = (ms >> sh) + (rem > halfbit ? 1u : 0u);
+            }
+            fast = fast && inc != 0u;
+        }
+        if (fast) {
+            const float u = __uint_as_float((uint32_t)(e - 23 + 127) << 23);  // 2^(e-23), e >= -100 here in practice
+            const uint32_t m = (tb & 0x7fffffu) | 0x800000u;
+            // points of this binade: m + k * inc < 2^24
+            const uint32_t k_bin = (0xffffffu - m) / inc;
+            // first k with (t_k + half >= target), t_k = (m + k inc) u: estimate, then correct with the exact test
+            const float gap = (target - half) - t;
+            float kf = ceilf(gap / ((float)inc * u));
+            kf = kf < 0.0f ? 0.0f : kf;
+            uint32_t k = kf >= (float)k_bin ? k_bin : (uint32_t)kf;
+            auto at = [&](uint32_t kk) { return (float)(m + kk * inc) * u; };  // exact: integer < 2^24 times 2^n
+            // dt == step must hold at every point used: t * cone_angle is monotone in t, so test the far end
+            while (k > 0 && !(calc_dt(at(k), cone_angle, step, 1e10f) == step)) k >>= 1;
+            while (k > 0 && at(k - 1) + half >= target) --k;
+            while (k < k_bin && !(at(k) + half >= target) && calc_dt(at(k + 1), cone_angle, step, 1e10f) == step) ++k;
+            if (k > 0) {
+                t = at(k);
+                continue;  // re-test at the new point (stop, next binade, or varying dt)
+            }
+        }
+        t += dt;  // plain step: leaves the binade, tie binade, or dt != step
+    }
+}
+
 // March one ray (twin of oracle/pack_oracle.c::march_ray).  WRITE=false only counts.
 //
 // Same fp32 operation sequence on t_last as the oracle, hence bit-exact outputs, with two shortcuts that cannot
@@ -69,7 +126,8 @@ __device__ __forceinline__ int voxel_index(float v, float fres, int res) {
 //    of the orbit bookkeeping) but the occupancy bytes are not fetched.
 template <bool WRITE>
 __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *__restrict__ binaries,
-                             const float *__restrict__ aabbs, const int *__restrict__ level_any, int levels, int res,
+                             const uint32_t *__restrict__ bits, const float *__restrict__ aabbs,
+                             const int *__restrict__ level_any, int levels, int res,
                              float near_plane, float far_plane, float step_size, float cone_angle, float *t0_out,
                              float *t1_out, int64_t limit) {
     const float inv[3] = {1.0f / d[0], 1.0f / d[1], 1.0f / d[2]};
@@ -93,7 +151,20 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
     int64_t n = 0;
     float t_last = near_plane;
     float pending = -1.0f;  // largest threshold of the empty cells skipped since t_last was last advanced (< 0: none)
+    // Intervals behind the last one whose grid level holds any occupied cell can only produce empty cells: nothing
+    // is emitted there and nothing later reads the orbit state they would leave behind, so the march stops before
+    // them (with level_any == nullptr every level counts as possibly occupied).
+    int last_useful = -1;
     for (int i = 0; i < 2 * levels - 1; ++i) {
+        const float a = ts[i], b = ts[i + 1];
+        if (!(a < b)) continue;
+        for (int l = 0; l < levels; ++l)
+            if (hits[l] && tmins[l] <= a && b <= tmaxs[l]) {
+                if (level_any == nullptr || level_any[l] != 0) last_useful = i;
+                break;
+            }
+    }
+    for (int i = 0; i <= last_useful; ++i) {
         const float a = ts[i], b = ts[i + 1];
         if (!(a < b)) continue;
         int level = -1;
@@ -124,6 +195,12 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
             over[k] = fin + stepi[k];
         }
         const uint8_t *lvl_bin = binaries + (int64_t)level * cells_per_level;
+        // bit-packed copy of the level (1 bit per cell, 256 KB at 128^3: L1-resident) when the caller built one
+        const uint32_t *lvl_bits = bits ? bits + (int64_t)level * ((cells_per_level + 31) / 32) : nullptr;
+        auto fetch = [&](int c) -> uint8_t {
+            if (lvl_bits) return (uint8_t)((__ldg(lvl_bits + (c >> 5)) >> (c & 31)) & 1u);
+            return __ldg(lvl_bin + c);
+        };
         // steps each axis may still take before it passes the interval's last cell or leaves the grid
         int left[3];
         for (int k = 0; k < 3; ++k) {
@@ -137,33 +214,41 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
         const int stride[3] = {stepi[0] * res * res, stepi[1] * res, stepi[2]};
         float td0 = tdist[0], td1 = tdist[1], td2 = tdist[2];
         int l0 = left[0], l1 = left[1], l2 = left[2];
-        uint8_t occ = lookup ? __ldg(lvl_bin + cell) : (uint8_t)0;
-        for (int guard = 0; guard < 4 * res + 8; ++guard) {
-            float t_traverse = fminf(td0, fminf(td1, td2));
-            t_traverse = fminf(t_traverse, this_tmax);
-            // single DDA step: x if strictly smallest, else y if < z, else z -- taken now so that the NEXT cell's
-            // occupancy byte is in flight while this cell is processed
-            const bool ax0 = (td0 < td1) && (td0 < td2);
-            const bool ax1 = !ax0 && (td1 < td2);
-            bool last;
-            if (ax0)      { td0 += delta[0]; cell += stride[0]; last = (--l0 == 0); }
-            else if (ax1) { td1 += delta[1]; cell += stride[1]; last = (--l1 == 0); }
-            else          { td2 += delta[2]; cell += stride[2]; last = (--l2 == 0); }
-            const uint8_t occ_next = (lookup && !last) ? __ldg(lvl_bin + cell) : (uint8_t)0;
-            if (!occ) {
-                pending = t_traverse;  // monotone: later thresholds dominate earlier ones
+        uint8_t occ = lookup ? fetch(cell) : (uint8_t)0;
+        bool last = false;
+        int guard = 4 * res + 8;
+        // Runs of cells with equal occupancy are consumed by one tight DDA loop, then one orbit loop handles the
+        // whole run: for an OCCUPIED run c1..cm with thresholds T1 < .. < Tm the oracle emits, cell by cell, the
+        // orbit points with t + dt/2 < Ti -- together exactly the points with t + dt/2 < Tm (same monotonicity as
+        // the lazy skip).  All lanes of a warp reach the orbit loops at the same place in the code, so the loops of
+        // different rays overlap instead of serialising per cell.
+        while (!last && guard > 0) {
+            const uint8_t run_occ = occ;
+            float t_run = 0.0f;  // threshold of the last cell of the run
+            do {
+                float t_traverse = fminf(td0, fminf(td1, td2));
+                t_traverse = fminf(t_traverse, this_tmax);
+                t_run = t_traverse;
+                // single DDA step: x if strictly smallest, else y if < z, else z -- taken now so that the NEXT cell's
+                // occupancy is in flight while this cell is processed
+                const bool ax0 = (td0 < td1) && (td0 < td2);
+                const bool ax1 = !ax0 && (td1 < td2);
+                if (ax0)      { td0 += delta[0]; cell += stride[0]; last = (--l0 == 0); }
+                else if (ax1) { td1 += delta[1]; cell += stride[1]; last = (--l1 == 0); }
+                else          { td2 += delta[2]; cell += stride[2]; last = (--l2 == 0); }
+                occ = (lookup && !last) ? fetch(cell) : (uint8_t)0;
+                --guard;
+            } while (!last && guard > 0 && occ == run_occ);
+            if (!run_occ) {
+                pending = t_run;  // monotone: later thresholds dominate earlier ones
             } else {
                 if (pending >= 0.0f) {
-                    for (;;) {
-                        const float dt = calc_dt(t_last, cone_angle, step_size, 1e10f);
-                        if (t_last + dt * 0.5f >= pending) break;
-                        t_last += dt;
-                    }
+                    t_last = advance_orbit(t_last, pending, cone_angle, step_size);
                     pending = -1.0f;
                 }
                 for (;;) {
                     const float dt = calc_dt(t_last, cone_angle, step_size, 1e10f);
-                    if (t_last + dt * 0.5f >= t_traverse) break;
+                    if (t_last + dt * 0.5f >= t_run) break;
                     if (WRITE) {
                         if (n >= limit) return n;  // capacity-truncated ray
                         t0_out[n] = t_last;
@@ -175,8 +260,6 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
                     t_last += dt;
                 }
             }
-            if (last) break;
-            occ = occ_next;
         }
     }
     return n;
@@ -194,13 +277,13 @@ march_kernel(umhs_march_args a, const int *__restrict__ level_any, int64_t *coun
         // with a staging buffer the count pass also records the first stage_stride interval starts of the ray, and
         // the write pass turns into a coalesced copy (rays longer than the stride are re-marched there)
         float *stage = a.stage ? a.stage + r * a.stage_stride : nullptr;
-        counts[r] = march_ray<false>(o, d, a.binaries, a.aabbs, level_any, a.levels, a.resolution, __ldg(a.near_planes + r),
+        counts[r] = march_ray<false>(o, d, a.binaries, a.occ_bits, a.aabbs, level_any, a.levels, a.resolution, __ldg(a.near_planes + r),
                                      __ldg(a.far_planes + r), a.step_size, a.cone_angle, stage, nullptr,
                                      stage ? a.stage_stride : 0);
     } else {
         const int64_t off = __ldg(packed_info + 2 * r), lim = __ldg(packed_info + 2 * r + 1);
         if (lim <= 0) return;
-        const int64_t n = march_ray<true>(o, d, a.binaries, a.aabbs, level_any, a.levels, a.resolution, __ldg(a.near_planes + r),
+        const int64_t n = march_ray<true>(o, d, a.binaries, a.occ_bits, a.aabbs, level_any, a.levels, a.resolution, __ldg(a.near_planes + r),
                                           __ldg(a.far_planes + r), a.step_size, a.cone_angle, t_starts + off,
                                           t_ends + off, lim);
         for (int64_t i = 0; i < n; ++i) ray_indices[off + i] = r;
@@ -233,7 +316,7 @@ march_write_staged_kernel(umhs_march_args a, const int *__restrict__ level_any, 
         if (lane == 0) {
             const float o[3] = {__ldg(a.rays_o + 3 * r), __ldg(a.rays_o + 3 * r + 1), __ldg(a.rays_o + 3 * r + 2)};
             const float d[3] = {__ldg(a.rays_d + 3 * r), __ldg(a.rays_d + 3 * r + 1), __ldg(a.rays_d + 3 * r + 2)};
-            march_ray<true>(o, d, a.binaries, a.aabbs, level_any, a.levels, a.resolution, __ldg(a.near_planes + r),
+            march_ray<true>(o, d, a.binaries, a.occ_bits, a.aabbs, level_any, a.levels, a.resolution, __ldg(a.near_planes + r),
                             __ldg(a.far_planes + r), a.step_size, a.cone_angle, t_starts + off, t_ends + off, lim);
         }
         for (int64_t i = lane; i < lim; i += 32) ray_indices[off + i] = r;
@@ -245,7 +328,8 @@ __global__ void level_any_kernel(const uint8_t *__restrict__ binaries, int64_t c
                                  int *__restrict__ level_any) {
     const int l = blockIdx.y;
     const uint4 *p = reinterpret_cast<const uint4 *>(binaries + (int64_t)l * cells_per_level);
-    const int64_t n16 = cells_per_level / 16;
+    // 16-byte loads only when this level starts on a 16-byte boundary (res^3 need not be a multiple of 16)
+    const int64_t n16 = (reinterpret_cast<uintptr_t>(p) & 15) == 0 ? cells_per_level / 16 : 0;
     bool any = false;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16 && !any; i += (int64_t)gridDim.x * blockDim.x) {
         const uint4 v = __ldg(p + i);
@@ -255,6 +339,32 @@ __global__ void level_any_kernel(const uint8_t *__restrict__ binaries, int64_t c
          i += (int64_t)gridDim.x * blockDim.x)
         any = any || binaries[(int64_t)l * cells_per_level + i] != 0;
     if (__syncthreads_or(any) && threadIdx.x == 0) atomicOr(level_any + l, 1);
+}
+
+// bits[l][w] bit b = binaries[l][32 w + b]; level_any[l] |= any.  One thread per 32 cells.
+__global__ void __launch_bounds__(256)
+occ_pack_bits_kernel(const uint8_t *__restrict__ binaries, int64_t cells_per_level, int levels,
+                     uint32_t *__restrict__ bits, int *__restrict__ level_any) {
+    const int l = blockIdx.y;
+    const int64_t words = (cells_per_level + 31) / 32;
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t word = 0;
+    if (w < words) {
+        const uint8_t *src = binaries + (int64_t)l * cells_per_level + w * 32;
+        if (w * 32 + 32 <= cells_per_level && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(src)), b = __ldg(reinterpret_cast<const uint4 *>(src) + 1);
+            const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) word |= (((v[q] >> (8 * j)) & 0xffu) ? 1u : 0u) << (4 * q + j);
+            }
+        } else {
+            for (int b = 0; b < 32 && w * 32 + b < cells_per_level; ++b) word |= (src[b] ? 1u : 0u) << b;
+        }
+        bits[(int64_t)l * words + w] = word;
+    }
+    if (__syncthreads_or(word != 0u) && threadIdx.x == 0) atomicOr(level_any + l, 1);
 }
 
 // Single-CTA exclusive scan of int64 counts -> packed_info[r] = (offset, count); *total = sum.
@@ -453,9 +563,21 @@ extern "C" int umhs_march_level_any(const umhs_march_args *a, int32_t *level_any
     return UMHS_OK;
 }
 
+extern "C" int umhs_occ_pack_bits(const umhs_march_args *a, uint32_t *bits, int32_t *level_any, void *stream) {
+    UMHS_CHECK_ARG(check_march(a) == 0 && bits && level_any, "bad march arguments");
+    const int64_t cells = (int64_t)a->resolution * a->resolution * a->resolution;
+    UMHS_CHECK_CUDA(cudaMemsetAsync(level_any, 0, sizeof(int32_t) * 8, as_stream(stream)));
+    occ_pack_bits_kernel<<<dim3(div_up((cells + 31) / 32, 256), a->levels), 256, 0, as_stream(stream)>>>(
+        a->binaries, cells, a->levels, bits, level_any);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
 extern "C" int umhs_march_count(const umhs_march_args *a, int64_t *counts, void *stream) {
     UMHS_CHECK_ARG(check_march(a) == 0 && counts, "bad march arguments");
     if (a->n_rays <= 0) return UMHS_OK;
+    // no shared memory: give the whole 256 KB to L1 (the bit-packed level-0 grid then stays resident)
+    UMHS_CHECK_CUDA(cudaFuncSetAttribute(march_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
     march_kernel<false><<<div_up(a->n_rays, 64), 64, 0, as_stream(stream)>>>(*a, a->level_any, counts, nullptr, nullptr,
                                                                              nullptr, nullptr);
     UMHS_CHECK_LAUNCH();

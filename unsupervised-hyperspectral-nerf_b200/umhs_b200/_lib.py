@@ -77,7 +77,7 @@ class CompositeGradsOut(Structure):
 class MarchArgs(Structure):
     _fields_ = [("rays_o", P), ("rays_d", P), ("near_planes", P), ("far_planes", P), ("binaries", P), ("aabbs", P),
                 ("levels", c_int32), ("resolution", c_int32), ("step_size", c_float), ("cone_angle", c_float),
-                ("n_rays", c_int64), ("level_any", P), ("stage", P), ("stage_counts", P), ("stage_stride", c_int32)]
+                ("n_rays", c_int64), ("level_any", P), ("occ_bits", P), ("stage", P), ("stage_counts", P), ("stage_stride", c_int32)]
 
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
@@ -109,6 +109,7 @@ _SIGNATURES = {
     "umhs_accumulate_fwd": [P, P, P, c_int64, c_int32, P, P],
     "umhs_accumulate_bwd": [P, P, P, c_int64, c_int32, P, P, P, P],
     "umhs_march_level_any": [POINTER(MarchArgs), P, P],
+    "umhs_occ_pack_bits": [POINTER(MarchArgs), P, P, P],
     "umhs_march_count": [POINTER(MarchArgs), P, P],
     "umhs_pack_scan": [P, c_int64, P, P, c_int64, P],
     "umhs_march_write": [POINTER(MarchArgs), P, P, P, P, P],

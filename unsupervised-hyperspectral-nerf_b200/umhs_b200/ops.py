@@ -22,7 +22,7 @@ _LAUNCHES = {"umhs_hash_encode_fwd": 1, "umhs_hash_encode_bwd": 1, "umhs_hash_en
              "umhs_hash_encode_x01_bwd": 1, "umhs_density_fwd": 1, "umhs_field_mlp_fwd": 1, "umhs_field_mlp_bwd": 1,
              "umhs_composite_fwd": 1, "umhs_depth_clip": 1, "umhs_composite_bwd": 1, "umhs_unmix_fwd": 1,
              "umhs_unmix_bwd": 1, "umhs_render_weights_fwd": 1, "umhs_render_weights_bwd": 1,
-             "umhs_accumulate_fwd": 1, "umhs_accumulate_bwd": 1, "umhs_march_count": 1, "umhs_march_level_any": 1, "umhs_pack_scan": 1,
+             "umhs_accumulate_fwd": 1, "umhs_accumulate_bwd": 1, "umhs_march_count": 1, "umhs_march_level_any": 1, "umhs_occ_pack_bits": 1, "umhs_pack_scan": 1,
              "umhs_march_write": 1, "umhs_visibility_mask": 1, "umhs_compact_samples": 1, "umhs_pack_info": 2,
              "umhs_occ_cell_points": 1, "umhs_occ_ema_update": 2, "umhs_occ_binarize": 2, "umhs_adam_step": 1,
              "umhs_reduce_slabs": 1, "umhs_adam_step_dev": 1, "umhs_density_tc_fwd": 1, "umhs_field_mlp_tc_fwd": 1, "umhs_field_mlp_tc_bwd": 1, "umhs_debug_trace": 1,
@@ -535,6 +535,7 @@ class AccumulateFunction(torch.autograd.Function):
 
 # --------------------------------------------------------------------------------------- packing
 MARCH_STAGE = 192  # staged interval starts per ray (0 disables staging: the write pass marches again)
+MARCH_BITS = True   # march on a bit-packed copy of the occupancy grid (identical results)
 
 
 def march(rays_o: Tensor, rays_d: Tensor, near_planes: Tensor, far_planes: Tensor, binaries: Tensor, aabbs: Tensor,
@@ -559,8 +560,15 @@ def march(rays_o: Tensor, rays_d: Tensor, near_planes: Tensor, far_planes: Tenso
     total = torch.zeros((2,), dtype=torch.int64, device=dev)
     st = stream_ptr(dev)
     level_any = torch.empty((8,), dtype=torch.int32, device=dev)
-    a.level_any = None
-    _call("umhs_march_level_any", 0, ctypes.byref(a), ptr(level_any), st)
+    a.level_any = a.occ_bits = None
+    if MARCH_BITS:
+        # one pass over binaries: per-level "any occupied" flags + a bit-packed copy whose lookups hit L1
+        words = (a.resolution ** 3 + 31) // 32
+        bits = torch.empty((a.levels, words), dtype=torch.int32, device=dev)
+        _call("umhs_occ_pack_bits", 0, ctypes.byref(a), ptr(bits), ptr(level_any), st)
+        a.occ_bits = ptr(bits)
+    else:
+        _call("umhs_march_level_any", 0, ctypes.byref(a), ptr(level_any), st)
     a.level_any = ptr(level_any)
     # the count pass stages each ray's first MARCH_STAGE interval starts; the write pass copies them
     stage = torch.empty((R, MARCH_STAGE), dtype=torch.float32, device=dev) if MARCH_STAGE > 0 else None
