@@ -237,7 +237,9 @@ def workload_config(n_gpus, cpu=False, samples_per_ray=None):
     c = {"workload": "hotdog-synthetic-train-step", "rays_per_gpu_per_step": RAYS_PER_GPU if not cpu else CPU_SAMPLE_RAYS,
          "bands": BANDS, "endmembers": K_CLASSES, "temperature": TEMPERATURE, "hash": "16x2@2^19",
          "occupancy": f"128^3x4 shell r={SHELL_R} t={SHELL_T}", "method": "rgb+spectral", "specular": False,
-         "parallelism": f"dp{n_gpus} ray-sharded, 1 all-reduce/step" if n_gpus > 1 else "single",
+         "parallelism": (f"dp{n_gpus} ray-sharded; gradient exchange + Adam fused in one kernel over NVLink peer "
+                         f"memory (reduce-scatter reads, all-gather writes), 2 device barriers/step") if n_gpus > 1
+         else "single",
          "conditioning_steps": CONDITIONING_STEPS,
          "launch": "whole step replayed as one CUDA graph (fwd+loss+bwd+Adam); occupancy update eager every 16 steps",
          "l2_policy": "working set > L2: Adam state 4 x 64 MiB streamed every step + rotating batches"}
@@ -418,6 +420,12 @@ def run_b200(args):
                 "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # data-parallel invariant: after any number of steps every rank holds bit-identical parameters
+        mine = trainer.flat.data.clone()
+        dist.broadcast(mine, src=0)
+        same = torch.tensor([1.0 if torch.equal(mine, trainer.flat.data) else 0.0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        assert float(same.item()) == 1.0, "data-parallel replicas diverged"
         dist.barrier()
         dist.destroy_process_group()
 

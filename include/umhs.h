@@ -36,6 +36,7 @@ extern "C" {
 #define UMHS_MAX_LEVELS 16
 #define UMHS_MAX_CLASSES 16
 #define UMHS_MAX_BANDS 512
+#define UMHS_MAX_RANKS 8 /* GPUs of one NVSwitch box */
 #define UMHS_GEO_FEAT 15 /* geo_feat_dim of NerfactoField */
 #define UMHS_PE_DIM 12   /* NeRFEncoding(3, 2 freqs) */
 #define UMHS_SH_DIM 16   /* SHEncoding(levels=4) */
@@ -324,6 +325,25 @@ int umhs_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq,
 int umhs_adam_step_dev(float *param, float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float beta1,
                        float beta2, float eps, const float *hyper, const float *inv_scale, const float *found_inf,
                        int64_t clamp_begin, int64_t clamp_end, int32_t zero_grad, void *stream);
+
+/* ---------------------------------------------------------------------------------
+ * Data-parallel step: gradient exchange + Adam in ONE kernel over NVLink peer memory.
+ * The reference has no multi-GPU path (world_size forced to 1: ref umhsnerf/umhs_pipeline.py:86,108-113); this
+ * replaces the all-reduce + optimizer.step() a DDP trainer would run.
+ * peer_grads / peer_params: HOST arrays of `world` device pointers, entry w = rank w's flat gradient / parameter
+ * buffer mapped into this process (symmetric memory), all of length n (multiple of 4).  Rank r reduces the shard
+ * [r n / world, (r+1) n / world) of every gradient (x 1/world: DDP mean), applies Adam with its own exp_avg /
+ * exp_avg_sq (only that shard is touched) and stores the new parameters into EVERY rank's buffer.
+ * Bracket it with umhs_dp_barrier: channel A before (all gradients complete), channel B after (all parameters
+ * landed, all gradients consumed -- only then may a rank zero its gradient buffer or start the next forward).
+ * signal_pads: DEVICE array of `world` pointers to each rank's zero-initialised pad of >= 8 x 8 uint32;
+ * epoch: this rank's device counter for the channel pair (zero-initialised, one per signal-pad set).
+ * ------------------------------------------------------------------------------- */
+int umhs_dp_barrier(uint32_t *const *signal_pads, int32_t rank, int32_t world, int32_t channel, uint32_t *epoch,
+                    void *stream);
+int umhs_dp_adam_step(const float *const *peer_grads, float *const *peer_params, float *exp_avg, float *exp_avg_sq,
+                      int64_t n, int32_t rank, int32_t world, float beta1, float beta2, float eps, const float *hyper,
+                      int64_t clamp_begin, int64_t clamp_end, void *stream);
 /* out[i] += sum_s slabs[s*stride + i] */
 int umhs_reduce_slabs(const float *slabs, int64_t n_slabs, int64_t stride, int64_t n, float *out, void *stream);
 

@@ -432,3 +432,31 @@ def test_field_mlp_tc_bwd_matches_fp32(K, specular, N):
     print({k: round(v, 4) for k, v in errs.items()})
     assert max(errs.values()) < 1e-1, errs
     assert max(errs[k] for k in ('head_w2', 'feat_w2', 'base_w1')) < 2e-2, errs
+
+
+@pytest.mark.gpu
+def test_dp_adam_step_world1_matches_adam():
+    """The fused exchange + Adam kernel with a single rank (its own buffers as the only peer) is the plain fused Adam;
+    the cross-GPU barrier with world = 1 returns.  (The 2-GPU exchange itself is checked by tools/dp_check.py.)"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    n = 4 * 50_001
+    p0 = torch.randn(n, generator=g).to(DEV)
+    grad = torch.randn(n, generator=g).to(DEV)
+    hyper = torch.tensor([2e-2, 1 - 0.9 ** 3, (1 - 0.999 ** 3) ** 0.5], device=DEV)
+    ref = {"p": p0.clone(), "g": grad.clone(), "m": torch.rand(n, generator=g).to(DEV) * 0.1,
+           "v": torch.rand(n, generator=g).to(DEV) * 0.01}
+    got = {k: v.clone() for k, v in ref.items()}
+    ops.adam_step_dev(ref["p"], ref["g"], ref["m"], ref["v"], 0.9, 0.999, 1e-15, hyper, clamp_range=(100, 612),
+                      zero_grad=False)
+    pads = torch.zeros(256, dtype=torch.int32, device=DEV)
+    pad_ptrs = torch.tensor([pads.data_ptr()], dtype=torch.int64, device=DEV)
+    epochs = torch.zeros(8, dtype=torch.int32, device=DEV)
+    ops.dp_barrier(pad_ptrs, 0, 1, 0, epochs)
+    ops.dp_adam_step([got["g"].data_ptr()], [got["p"].data_ptr()], got["m"], got["v"], n, 0, 1, 0.9, 0.999, 1e-15, hyper,
+                     clamp_range=(100, 612))
+    ops.dp_barrier(pad_ptrs, 0, 1, 1, epochs)
+    torch.cuda.synchronize()
+    for k in ("p", "m", "v"):  # same expressions; the compiler may contract them into FMAs differently
+        assert_close(got[k], ref[k], 1e-6, 1e-6, k)
+    assert int(epochs[0]) == 1 and int(epochs[1]) == 1 and int(pads[0]) == 1 and int(pads[8]) == 1

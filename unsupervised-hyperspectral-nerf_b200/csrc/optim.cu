@@ -72,6 +72,88 @@ __global__ void reduce_slabs_kernel(const float *__restrict__ slabs, int64_t n_s
     }
 }
 
+// =====================================================================================================
+// Data-parallel optimiser step fused with its gradient exchange over NVLink peer memory.
+//
+// Every rank's flat gradient and flat parameter buffers are peer-mapped (symmetric memory).  Rank r owns the shard
+// [r n / W, (r + 1) n / W): it READS that shard of every rank's gradient through NVLink (the reduce-scatter), runs
+// Adam on it with its own slice of the optimiser state, and WRITES the updated parameters into every rank's
+// parameter buffer (the all-gather) -- one kernel, no intermediate HBM round trip, 1/W of the optimiser traffic per
+// GPU, and the same 2 (W - 1) / W n bytes on the wire as an all-reduce.  Two cross-GPU barriers bracket it
+// (umhs_dp_barrier): gradients complete before, parameters landed / gradients consumed after.
+// =====================================================================================================
+struct DpAdamArgs {
+    const float *peer_grad[UMHS_MAX_RANKS];
+    float *peer_param[UMHS_MAX_RANKS];
+    float *m, *v;
+    int64_t begin, end;  // this rank's shard (multiples of 4)
+    int world, rank;
+    float beta1, beta2, eps, inv_world;
+    const float *hyper;
+    int64_t clamp_begin, clamp_end;
+};
+
+__global__ void __launch_bounds__(256) dp_adam_kernel(DpAdamArgs a) {
+    const float lr = __ldg(a.hyper), bc1 = __ldg(a.hyper + 1), bc2_sqrt = __ldg(a.hyper + 2);
+    const float4 *own_p = reinterpret_cast<const float4 *>(a.peer_param[a.rank]);
+    float4 *m4 = reinterpret_cast<float4 *>(a.m), *v4 = reinterpret_cast<float4 *>(a.v);
+    for (int64_t i = a.begin / 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.end / 4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        // reduce-scatter: this shard of every rank's gradient (peer loads first: they have the longest latency)
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < UMHS_MAX_RANKS; ++w) {
+            if (w < a.world) {
+                const float4 x = reinterpret_cast<const float4 *>(a.peer_grad[w])[i];
+                g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+            }
+        }
+        float4 p = own_p[i], m = m4[i], v = v4[i];
+        float *pp = &p.x, *gg = &g.x, *mm = &m.x, *vv = &v.x;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float gr = gg[c] * a.inv_world;
+            mm[c] = a.beta1 * mm[c] + (1.0f - a.beta1) * gr;
+            vv[c] = a.beta2 * vv[c] + (1.0f - a.beta2) * gr * gr;
+            const float denom = sqrtf(vv[c]) / bc2_sqrt + a.eps;
+            pp[c] -= (lr / bc1) * (mm[c] / denom);
+            const int64_t idx = 4 * i + c;
+            if (idx >= a.clamp_begin && idx < a.clamp_end) pp[c] = fminf(fmaxf(pp[c], 0.0f), 1.0f);
+        }
+        m4[i] = m;
+        v4[i] = v;
+        // all-gather: the updated shard goes to every rank's parameter buffer
+#pragma unroll
+        for (int w = 0; w < UMHS_MAX_RANKS; ++w)
+            if (w < a.world) reinterpret_cast<float4 *>(a.peer_param[w])[i] = p;
+    }
+}
+
+// Cross-GPU barrier on peer-mapped signal pads: pad[channel][src] of rank dst counts the barriers src has entered.
+// Epochs only grow, so nothing is ever reset.  One CTA; thread w < world talks to rank w.
+__global__ void dp_barrier_kernel(DpAdamArgs a_unused, uint32_t *const *pads, int rank, int world, int channel,
+                                  uint32_t *epoch) {
+    (void)a_unused;
+    __shared__ uint32_t e_s;
+    if (threadIdx.x == 0) e_s = ++(*epoch);
+    __syncthreads();
+    const uint32_t e = e_s;
+    __threadfence_system();  // this GPU's earlier kernels' writes are ordered before the signal
+    if ((int)threadIdx.x < world) {
+        const int w = threadIdx.x;
+        uint32_t *remote = pads[w] + channel * UMHS_MAX_RANKS + rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(e) : "memory");
+        const uint32_t *local = pads[rank] + channel * UMHS_MAX_RANKS + w;
+        uint32_t seen;
+        unsigned long long spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(local) : "memory");
+            if (++spins > (1ull << 34)) __trap();  // a missing peer must fail loudly, not hang forever
+        } while ((int32_t)(seen - e) < 0);
+    }
+    __syncthreads();
+}
+
 }  // namespace umhs
 
 using namespace umhs;
@@ -115,6 +197,42 @@ extern "C" int umhs_adam_step_dev(float *param, float *grad, float *exp_avg, flo
     const int64_t want = (n / 4 + 255) / 256;
     const int grid = (int)(want < kNumSMs * 8 ? (want < 1 ? 1 : want) : kNumSMs * 8);
     adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(a);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_dp_barrier(uint32_t *const *signal_pads, int32_t rank, int32_t world, int32_t channel,
+                               uint32_t *epoch, void *stream) {
+    UMHS_CHECK_ARG(signal_pads && epoch && world >= 1 && world <= UMHS_MAX_RANKS && rank >= 0 && rank < world &&
+                       channel >= 0 && channel < 8, "bad argument");
+    dp_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(DpAdamArgs{}, signal_pads, rank, world, channel, epoch);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_dp_adam_step(const float *const *peer_grads, float *const *peer_params, float *exp_avg,
+                                 float *exp_avg_sq, int64_t n, int32_t rank, int32_t world, float beta1, float beta2,
+                                 float eps, const float *hyper, int64_t clamp_begin, int64_t clamp_end, void *stream) {
+    UMHS_CHECK_ARG(peer_grads && peer_params && exp_avg && exp_avg_sq && hyper, "null argument");
+    UMHS_CHECK_ARG(world >= 1 && world <= UMHS_MAX_RANKS && rank >= 0 && rank < world, "bad rank / world");
+    UMHS_CHECK_ARG(n % 4 == 0, "the flat buffer length must be a multiple of 4");
+    if (n <= 0) return UMHS_OK;
+    DpAdamArgs a;
+    for (int w = 0; w < UMHS_MAX_RANKS; ++w) {
+        a.peer_grad[w] = w < world ? peer_grads[w] : nullptr;   // HOST arrays of device pointers
+        a.peer_param[w] = w < world ? peer_params[w] : nullptr;
+        UMHS_CHECK_ARG(w >= world || (a.peer_grad[w] && a.peer_param[w] && ((uintptr_t)a.peer_grad[w] % 16 == 0) &&
+                                      ((uintptr_t)a.peer_param[w] % 16 == 0)), "bad peer pointer");
+    }
+    const int64_t n4 = n / 4, per = (n4 + world - 1) / world;
+    a.begin = 4 * (per * rank < n4 ? per * rank : n4);
+    a.end = 4 * (per * (rank + 1) < n4 ? per * (rank + 1) : n4);
+    a.m = exp_avg; a.v = exp_avg_sq; a.world = world; a.rank = rank;
+    a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.inv_world = 1.0f / (float)world; a.hyper = hyper;
+    a.clamp_begin = clamp_begin; a.clamp_end = clamp_end;
+    const int64_t want = ((a.end - a.begin) / 4 + 255) / 256;
+    const int grid = (int)(want < kNumSMs * 8 ? (want < 1 ? 1 : want) : kNumSMs * 8);
+    dp_adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(a);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }

@@ -25,7 +25,7 @@ _LAUNCHES = {"umhs_hash_encode_fwd": 1, "umhs_hash_encode_bwd": 1, "umhs_hash_en
              "umhs_accumulate_fwd": 1, "umhs_accumulate_bwd": 1, "umhs_march_count": 1, "umhs_march_level_any": 1, "umhs_occ_pack_bits": 1, "umhs_pack_scan": 1,
              "umhs_march_write": 1, "umhs_visibility_mask": 1, "umhs_compact_samples": 1, "umhs_pack_info": 2,
              "umhs_occ_cell_points": 1, "umhs_occ_ema_update": 2, "umhs_occ_binarize": 2, "umhs_adam_step": 1,
-             "umhs_reduce_slabs": 1, "umhs_adam_step_dev": 1, "umhs_density_tc_fwd": 1, "umhs_field_mlp_tc_fwd": 1, "umhs_field_mlp_tc_bwd": 1, "umhs_debug_trace": 1,
+             "umhs_reduce_slabs": 1, "umhs_dp_barrier": 1, "umhs_dp_adam_step": 1, "umhs_adam_step_dev": 1, "umhs_density_tc_fwd": 1, "umhs_field_mlp_tc_fwd": 1, "umhs_field_mlp_tc_bwd": 1, "umhs_debug_trace": 1,
              "umhs_tc05_selftest": 1}
 
 # "bf16": tensor-core MLP kernels (tcgen05 + TMEM, bf16 operands, fp32 accumulate) -- the default.
@@ -626,6 +626,22 @@ def adam_step_dev(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tens
     _call("umhs_adam_step_dev", param.numel(), ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(),
           beta1, beta2, eps, ptr(hyper), ptr(inv_scale), None, clamp_range[0], clamp_range[1], 1 if zero_grad else 0,
           stream_ptr(param.device))
+
+
+def dp_barrier(pads: Tensor, rank: int, world: int, channel: int, epochs: Tensor) -> None:
+    """Cross-GPU barrier on peer-mapped signal pads (pads: device int64 [world] of pad addresses; epochs: device
+    int32 [8] counters of this rank, one per channel).  Enqueued on the current stream; capturable."""
+    _call("umhs_dp_barrier", 0, ptr(pads), rank, world, channel, epochs.data_ptr() + 4 * channel, stream_ptr(pads.device))
+
+
+def dp_adam_step(peer_grads: List[int], peer_params: List[int], exp_avg: Tensor, exp_avg_sq: Tensor, n: int, rank: int,
+                 world: int, beta1: float, beta2: float, eps: float, hyper: Tensor,
+                 clamp_range: Tuple[int, int] = (0, 0)) -> None:
+    """Fused reduce-scatter + Adam + all-gather over NVLink peer memory (include/umhs.h: umhs_dp_adam_step)."""
+    pg = (ctypes.c_void_p * world)(*peer_grads)
+    pp = (ctypes.c_void_p * world)(*peer_params)
+    _call("umhs_dp_adam_step", n // world, pg, pp, ptr(exp_avg), ptr(exp_avg_sq), n, rank, world, beta1, beta2, eps,
+          ptr(hyper), clamp_range[0], clamp_range[1], stream_ptr(exp_avg.device))
 
 
 def tc05_selftest(mode: int, A: Tensor, B: Tensor, N: int, K: int) -> Tensor:

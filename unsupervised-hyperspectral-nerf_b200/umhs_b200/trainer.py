@@ -48,10 +48,32 @@ def average_gradients(flat_grad: Tensor, world_size: int) -> None:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
 
 
-class FlatParams:
-    """Re-home a list of parameters into one contiguous fp32 buffer (16-byte aligned segments)."""
+class PeerMemory:
+    """Peer-mapped (symmetric) device buffers of one process group: every rank allocates the same sizes and gets the
+    device addresses of all ranks' copies, mapped over NVLink (torch.distributed symmetric memory does the handle
+    exchange -- plumbing; the kernels that use the pointers are csrc/optim.cu)."""
 
-    def __init__(self, params: List[nn.Parameter]):
+    def __init__(self, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self._sm = symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self._keep = []
+
+    def empty(self, n: int, dtype, device):
+        """-> (local tensor, [device address of rank w's tensor for w in range(world)])"""
+        t = self._sm.empty(n, dtype=dtype, device=device)
+        hdl = self._sm.rendezvous(t, self.group)
+        self._keep.append(hdl)
+        return t, [int(p) for p in hdl.buffer_ptrs]
+
+
+class FlatParams:
+    """Re-home a list of parameters into one contiguous fp32 buffer (16-byte aligned segments).  With ``peers`` the
+    parameter and gradient buffers are peer-mapped, for the fused data-parallel optimiser step."""
+
+    def __init__(self, params: List[nn.Parameter], peers: Optional[PeerMemory] = None):
         dev = params[0].device
         self.params = params
         self.offsets: List[int] = []
@@ -60,8 +82,15 @@ class FlatParams:
             self.offsets.append(n)
             n += (p.numel() + 3) // 4 * 4
         self.numel = n
-        self.data = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.peer_data = self.peer_grad = None
+        if peers is not None:
+            self.data, self.peer_data = peers.empty(n, torch.float32, dev)
+            self.grad, self.peer_grad = peers.empty(n, torch.float32, dev)
+            self.data.zero_()
+            self.grad.zero_()
+        else:
+            self.data = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         for p, o in zip(params, self.offsets):
@@ -81,12 +110,27 @@ class UMHSTrainer:
     def __init__(self, model: UMHSModel, lr: float = 2e-2, eps: float = 1e-15, betas=(0.9, 0.999),
                  lr_final: float = 1e-5, max_steps: int = 30000, world_size: int = 1, rank: int = 0,
                  occ_update: bool = True, freeze_binaries: bool = False, start_step: int = 0,
-                 sync_free: bool = True, capacity_check_every: int = 16, cuda_graph: bool = False):
+                 sync_free: bool = True, capacity_check_every: int = 16, cuda_graph: bool = False,
+                 fused_dp: bool = True):
         self.model = model
         self.world_size, self.rank = world_size, rank
         self.lr_init, self.lr_final, self.max_steps = lr, lr_final, max_steps
         self.eps, self.betas = eps, betas
-        self.flat = FlatParams([p for p in model.field.parameters() if p.requires_grad])
+        params = [p for p in model.field.parameters() if p.requires_grad]
+        # fused_dp: gradient exchange + Adam as one kernel over NVLink peer memory (csrc/optim.cu); otherwise one
+        # NCCL all-reduce followed by the single-GPU fused Adam on every rank
+        self.fused_dp = bool(fused_dp and world_size > 1 and params[0].is_cuda)
+        self._peers = PeerMemory() if self.fused_dp else None
+        self.flat = FlatParams(params, self._peers)
+        if self.fused_dp:
+            dev = params[0].device
+            pad, pad_ptrs = self._peers.empty(256, torch.int32, dev)   # 8 channels x 8 ranks (+ slack) of uint32
+            pad.zero_()
+            self._dp_pads = torch.tensor(pad_ptrs, dtype=torch.int64, device=dev)
+            self._dp_epochs = torch.zeros(8, dtype=torch.int32, device=dev)
+            self._dp_pad_keep = pad
+            torch.cuda.synchronize(dev)
+            dist.barrier()  # every pad is zero before anyone signals
         self.clamp_range = self.flat.range_of(model.field.endmembers)
         self.step = start_step
         self.opt_steps = 0
@@ -164,6 +208,14 @@ class UMHSTrainer:
         return loss_dict
 
     def _optimizer(self) -> None:
+        if self.fused_dp:
+            f = self.flat
+            ops.dp_barrier(self._dp_pads, self.rank, self.world_size, 0, self._dp_epochs)  # all gradients complete
+            ops.dp_adam_step(f.peer_grad, f.peer_data, f.exp_avg, f.exp_avg_sq, f.numel, self.rank, self.world_size,
+                             self.betas[0], self.betas[1], self.eps, self._hyper, clamp_range=self.clamp_range)
+            ops.dp_barrier(self._dp_pads, self.rank, self.world_size, 1, self._dp_epochs)  # parameters landed
+            f.grad.zero_()
+            return
         ops.adam_step_dev(self.flat.data, self.flat.grad, self.flat.exp_avg, self.flat.exp_avg_sq, self.betas[0],
                           self.betas[1], self.eps, self._hyper,
                           inv_scale=self._inv_world if self.world_size > 1 else None, clamp_range=self.clamp_range,
@@ -197,7 +249,8 @@ class UMHSTrainer:
                                        ray_bundle.directions.to(dev, non_blocking=True))
                 batch = {k: v.to(dev, non_blocking=True) for k, v in batch.items()}
             loss_dict = self._forward_backward(ray_bundle, batch)
-            average_gradients(self.flat.grad, self.world_size)
+            if not self.fused_dp:
+                average_gradients(self.flat.grad, self.world_size)
             self._optimizer()
         if slot is not None:  # the staging slot may be overwritten once this step has consumed it
             ev = torch.cuda.Event()
@@ -219,7 +272,7 @@ class UMHSTrainer:
         g["image"].copy_(batch["image"], non_blocking=True)
         g["hs_image"].copy_(batch["hs_image"], non_blocking=True)
         g["fwd_bwd"].replay()
-        if self.world_size > 1:
+        if "opt" in g:
             average_gradients(self.flat.grad, self.world_size)
             g["opt"].replay()
         return g["out"]
@@ -244,10 +297,10 @@ class UMHSTrainer:
         g1 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1):
             out = self._forward_backward(rb, bt)
-            if self.world_size == 1:
-                self._optimizer()
+            if self.world_size == 1 or self.fused_dp:
+                self._optimizer()  # fused_dp: barrier + exchange/Adam kernel + barrier, all inside the graph
         st["fwd_bwd"], st["out"] = g1, out
-        if self.world_size > 1:
+        if self.world_size > 1 and not self.fused_dp:
             g2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g2):
                 self._optimizer()
