@@ -346,7 +346,8 @@ def run_b200(args):
     if rank == 0:
         clocks.start()
     ms = timed(step_resident, args.steps)
-    for i in range(max(3, args.warmup)):  # warm the end-to-end path too (staging buffers, copy stream, re-capture)
+    # warm the end-to-end path too (staging buffers, copy stream), through one whole occupancy-update period
+    for i in range(max(3, args.warmup) + 16):
         step_e2e(i)
     finish_e2e()
     e2e_state["losses"].clear()

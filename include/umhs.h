@@ -312,6 +312,20 @@ int umhs_occ_binarize(const float *occs, int64_t n_cells, float occ_thre, double
                       float *mean_out /*device scalar or NULL: mean(occs)*/, void *stream);
 
 /* ---------------------------------------------------------------------------------
+ * Training losses + their gradients in one pass -- replaces UMHSModel.get_loss_dict (ref
+ * umhsnerf/umhs_model.py:329-383: 5 * MSE(spectral, hs_image) + w * MSE(rgb blended over a background, image
+ * blended over the same background)) and the autograd backward of those ~15 elementwise / reduction launches.
+ * losses [2] = (spectral_loss, rgb_loss); d_* = d(sum of losses)/d(spectral | rgb | accumulation), the inputs
+ * of umhs_composite_bwd.  background [R,3] (the reference draws it with rand_like; NULL = black);
+ * image [R,3] or [R,4] (RGBA: blended over the background as nerfstudio's blend_background does).
+ * w_rgb = 0 (method "spectral"): the rgb term and its buffers are skipped.
+ * ------------------------------------------------------------------------------- */
+int umhs_train_loss(int64_t n_rays, int32_t num_bands, int32_t image_channels, const float *spectral,
+                    const float *hs_image, const float *rgb, const float *accumulation, const float *image,
+                    const float *background, float w_spectral, float w_rgb, float *losses, float *d_spectral,
+                    float *d_rgb, float *d_accumulation, void *stream);
+
+/* ---------------------------------------------------------------------------------
  * Optimiser: dense Adam over one flat fp32 parameter buffer (torch.optim.Adam
  * semantics, configured at ref umhsnerf/umhs_config.py:59-64), with the endmember
  * clamp of ref umhsnerf/umhs_model.py:568-570 folded in for [clamp_begin, clamp_end).

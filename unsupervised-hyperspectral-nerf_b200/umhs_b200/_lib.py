@@ -123,6 +123,7 @@ _SIGNATURES = {
                        c_int32, P],
     "umhs_adam_step_dev": [P, P, P, P, c_int64, c_float, c_float, c_float, P, P, P, c_int64, c_int64, c_int32, P],
     "umhs_reduce_slabs": [P, c_int64, c_int64, c_int64, P, P],
+    "umhs_train_loss": [c_int64, c_int32, c_int32, P, P, P, P, P, P, c_float, c_float, P, P, P, P, P],
     "umhs_dp_barrier": [P, c_int32, c_int32, c_int32, P, P],
     "umhs_dp_adam_step": [P, P, P, P, c_int64, c_int32, c_int32, c_float, c_float, c_float, P, c_int64, c_int64, P],
 }

@@ -102,17 +102,28 @@ class OccGridEstimator(nn.Module):
                 self._scratch = (self.occs.clone(), self.binaries.clone())
             occs, binaries = self._scratch
         for lvl in range(self.levels):
+            dup_mask = n_valid = None
             if cell_ids is not None:
                 idx = cell_ids[lvl].to(torch.int64).contiguous()
             elif step < warmup_steps:
                 idx = None  # all cells, in order
             else:
+                # nerfacc: n/4 uniform cells + up to n/4 random OCCUPIED cells (all of them when there are fewer).
+                # Sync-free form (no nonzero / len on the host, so the update can be enqueued behind steps that are
+                # still running): a fixed 2 * n/4 entries; the slots beyond the occupied count repeat entry 0 with the
+                # same jitter -- the same point, the same density, and max() is idempotent.
                 n_u = n_cells // 4
                 uni = torch.randint(n_cells, (n_u,), device=dev)
-                occ_idx = torch.nonzero(binaries[lvl].flatten())[:, 0]
-                if n_u < len(occ_idx):
-                    occ_idx = occ_idx[torch.randint(len(occ_idx), (n_u,), device=dev)]
-                idx = torch.cat([uni, occ_idx], dim=0).contiguous()
+                flat = binaries[lvl].flatten()
+                n_occ = flat.sum()                                            # device scalar
+                occ_list = _occupied_cells(flat)                              # occupied ids first, in order
+                slot = torch.arange(n_u, device=dev)
+                pick = (torch.rand(n_u, device=dev) * n_occ).long().clamp_(max=n_cells - 1)
+                occ_idx = torch.where(n_occ > n_u, occ_list[pick], occ_list[:n_u])
+                dup = slot >= n_occ                                           # slots without an occupied cell
+                idx = torch.cat([uni, torch.where(dup, uni[0], occ_idx)], dim=0).contiguous()
+                dup_mask = torch.cat([torch.zeros(n_u, dtype=torch.bool, device=dev), dup])
+                n_valid = n_u + n_occ.clamp(max=n_u)  # device scalar: the duplicates behind it need no evaluation
             m = n_cells if idx is None else int(idx.shape[0])
             if m == 0:
                 continue
@@ -127,9 +138,17 @@ class OccGridEstimator(nn.Module):
                 if idx is None:  # all cells in order: explicit ids for this chunk
                     idx_c = torch.arange(c0, c0 + mc, device=dev, dtype=torch.int64)
                 jit = jit_all[c0:c0 + mc].contiguous() if jit_all is not None else torch.rand((mc, 3), device=dev)
+                if dup_mask is not None:
+                    if c0 == 0:
+                        jit0 = jit[0].clone()
+                    jit = torch.where(dup_mask[c0:c0 + mc, None], jit0, jit)
                 pos = torch.empty((mc, 3), dtype=torch.float32, device=dev)
                 ops._call("umhs_occ_cell_points", mc, ptr(idx_c), ptr(jit), mc, res, ptr(aabb), ptr(pos), st)
-                occ = occ_eval_fn(pos).reshape(-1).to(torch.float32).contiguous()
+                if n_valid is not None:  # zero density for the duplicate slots: max() with it changes nothing
+                    cnt = (n_valid - c0).clamp(min=0, max=mc).to(torch.int64).reshape(1)
+                    occ = occ_eval_fn(pos, n_dev=cnt).reshape(-1).to(torch.float32).contiguous()
+                else:
+                    occ = occ_eval_fn(pos).reshape(-1).to(torch.float32).contiguous()
                 tmp = torch.empty((mc,), dtype=torch.float32, device=dev)
                 ops._call("umhs_occ_ema_update", mc, ptr(occs), ptr(idx_c), lvl * n_cells, ptr(occ), 1.0,
                           float(ema_decay), mc, ptr(tmp), st)
@@ -140,6 +159,12 @@ class OccGridEstimator(nn.Module):
                   ptr(mean), st)
         if not freeze_binaries:
             self._occ_mean = mean
+
+
+def _occupied_cells(flat: Tensor) -> Tensor:
+    """Ids of the set cells of a flat bool grid, in increasing order, followed by the rest: fixed size, no host sync,
+    capturable in a CUDA graph (torch.nonzero / nonzero_static read a count back on the host)."""
+    return torch.sort(flat.to(torch.uint8), descending=True, stable=True).indices
 
 
 class VolumetricSampler(nn.Module):

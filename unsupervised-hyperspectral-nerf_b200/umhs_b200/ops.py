@@ -25,7 +25,7 @@ _LAUNCHES = {"umhs_hash_encode_fwd": 1, "umhs_hash_encode_bwd": 1, "umhs_hash_en
              "umhs_accumulate_fwd": 1, "umhs_accumulate_bwd": 1, "umhs_march_count": 1, "umhs_march_level_any": 1, "umhs_occ_pack_bits": 1, "umhs_pack_scan": 1,
              "umhs_march_write": 1, "umhs_visibility_mask": 1, "umhs_compact_samples": 1, "umhs_pack_info": 2,
              "umhs_occ_cell_points": 1, "umhs_occ_ema_update": 2, "umhs_occ_binarize": 2, "umhs_adam_step": 1,
-             "umhs_reduce_slabs": 1, "umhs_dp_barrier": 1, "umhs_dp_adam_step": 1, "umhs_adam_step_dev": 1, "umhs_density_tc_fwd": 1, "umhs_field_mlp_tc_fwd": 1, "umhs_field_mlp_tc_bwd": 1, "umhs_debug_trace": 1,
+             "umhs_reduce_slabs": 1, "umhs_train_loss": 1, "umhs_dp_barrier": 1, "umhs_dp_adam_step": 1, "umhs_adam_step_dev": 1, "umhs_density_tc_fwd": 1, "umhs_field_mlp_tc_fwd": 1, "umhs_field_mlp_tc_bwd": 1, "umhs_debug_trace": 1,
              "umhs_tc05_selftest": 1}
 
 # "bf16": tensor-core MLP kernels (tcgen05 + TMEM, bf16 operands, fp32 accumulate) -- the default.
@@ -128,11 +128,12 @@ class PointSet:
         return (self.positions if self.positions is not None else self.t_starts).device
 
     @staticmethod
-    def from_positions(positions: Tensor, directions: Optional[Tensor] = None, contraction=True, aabb=None):
+    def from_positions(positions: Tensor, directions: Optional[Tensor] = None, contraction=True, aabb=None,
+                       n_dev: Optional[Tensor] = None):
         p = f32(positions).reshape(-1, 3)
         d = f32(directions).reshape(-1, 3) if directions is not None else None
         return PointSet(n=p.shape[0], positions=p, directions=d, contraction=contraction,
-                        aabb=tuple(aabb) if aabb is not None else PointSet.aabb)
+                        aabb=tuple(aabb) if aabb is not None else PointSet.aabb, n_dev=n_dev)
 
     @staticmethod
     def from_packed(rays_o, rays_d, ray_indices, t_starts, t_ends, contraction=True, aabb=None, n_dev=None):
@@ -228,7 +229,8 @@ def mlp_struct(weights: Dict[str, Optional[Tensor]], num_classes: int, specular:
 
 def density_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor]) -> Tensor:
     lib = _lib.load()
-    sigma = torch.empty((pts.n,), dtype=torch.float32, device=enc.device)
+    # with a device-side count the entries beyond it are not written: they read as zero density
+    sigma = (torch.zeros if pts.n_dev is not None else torch.empty)((pts.n,), dtype=torch.float32, device=enc.device)
     ps, ms = pts.struct(), mlp_struct(weights, 1, False, 1.0)
     _call("umhs_density_tc_fwd" if MLP_PRECISION == "bf16" else "umhs_density_fwd", pts.units(), ctypes.byref(ps), pts.n, ptr(enc), ctypes.byref(ms), ptr(sigma),
                                stream_ptr(enc.device))
@@ -626,6 +628,26 @@ def adam_step_dev(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tens
     _call("umhs_adam_step_dev", param.numel(), ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(),
           beta1, beta2, eps, ptr(hyper), ptr(inv_scale), None, clamp_range[0], clamp_range[1], 1 if zero_grad else 0,
           stream_ptr(param.device))
+
+
+def train_loss(spectral: Tensor, hs_image: Tensor, rgb: Optional[Tensor], accumulation: Optional[Tensor],
+               image: Optional[Tensor], background: Optional[Tensor], w_spectral: float, w_rgb: float):
+    """Both training losses and d(sum)/d(spectral, rgb, accumulation) in one launch.
+    -> (losses [2], d_spectral [R,B], d_rgb [R,3] | None, d_accumulation [R] | None)"""
+    dev = spectral.device
+    R, B = int(spectral.shape[0]), int(spectral.shape[1])
+    sp, hs = f32(spectral), f32(hs_image)
+    losses = torch.empty((2,), dtype=torch.float32, device=dev)
+    d_spec = torch.empty((R, B), dtype=torch.float32, device=dev)
+    use_rgb = w_rgb != 0.0 and rgb is not None
+    d_rgb = torch.empty((R, 3), dtype=torch.float32, device=dev) if use_rgb else None
+    d_acc = torch.empty((R,), dtype=torch.float32, device=dev) if use_rgb else None
+    keep = [f32(t) if (t is not None and use_rgb) else None for t in (rgb, accumulation, image, background)]
+    ch = int(image.shape[-1]) if image is not None else 3
+    _call("umhs_train_loss", R, R, B, ch, ptr(sp), ptr(hs), ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]),
+          float(w_spectral), float(w_rgb if use_rgb else 0.0), ptr(losses), ptr(d_spec), ptr(d_rgb), ptr(d_acc),
+          stream_ptr(dev))
+    return losses, d_spec, d_rgb, d_acc
 
 
 def dp_barrier(pads: Tensor, rank: int, world: int, channel: int, epochs: Tensor) -> None:

@@ -17,6 +17,9 @@ The reference itself never syncs gradients (its pipeline forces world_size = 1: 
 """
 from __future__ import annotations
 
+import os
+import sys
+import time
 from typing import Dict, List, Optional
 
 import torch
@@ -111,8 +114,9 @@ class UMHSTrainer:
                  lr_final: float = 1e-5, max_steps: int = 30000, world_size: int = 1, rank: int = 0,
                  occ_update: bool = True, freeze_binaries: bool = False, start_step: int = 0,
                  sync_free: bool = True, capacity_check_every: int = 16, cuda_graph: bool = False,
-                 fused_dp: bool = True):
+                 fused_dp: bool = True, fused_loss: bool = True):
         self.model = model
+        self.fused_loss = fused_loss
         self.world_size, self.rank = world_size, rank
         self.lr_init, self.lr_final, self.max_steps = lr, lr_final, max_steps
         self.eps, self.betas = eps, betas
@@ -143,6 +147,7 @@ class UMHSTrainer:
         # per-step scalars (lr, Adam bias corrections) travel through a 3-float device buffer
         self.cuda_graph = cuda_graph and sync_free
         self._graph = None
+        self._occ_graph = None  # CUDAGraph of the steady-state occupancy update; False: capture failed, stay eager
         self._hyper = torch.zeros(3, dtype=torch.float32, device=self.flat.data.device)
         # ring of pinned staging rows: the CPU may run several steps ahead of the asynchronous copies
         self._hyper_host = torch.zeros((256, 3), dtype=torch.float32).pin_memory() if self.flat.data.is_cuda else None
@@ -200,6 +205,32 @@ class UMHSTrainer:
     def _forward_backward(self, ray_bundle: RayBundle, batch: Dict[str, Tensor]):
         m = self.model
         outputs = m.get_outputs(m.collider(ray_bundle), per_band_views=False)
+        if self.fused_loss and outputs["spectral"].is_cuda:
+            # UMHSModel.get_loss_dict and its backward as one kernel (csrc/loss.cu): the gradients of the scalar loss
+            # with respect to the rendered outputs go straight into the compositing backward
+            cfg = m.config
+            spectral, rgb, acc = outputs["spectral"], outputs["rgb"], outputs["accumulation"]
+            w_spec = 1.0 if cfg.method == "spectral" else 5.0  # hard-coded 5 of ref umhs_model.py:369 (quirk 4)
+            w_rgb = 0.0 if cfg.method == "spectral" else float(cfg.rgb_loss_weight)
+            if cfg.background_color == "random":
+                bg = m._bg_override if m._bg_override is not None else torch.rand_like(rgb)
+            else:
+                bg = torch.ones_like(rgb) if cfg.background_color == "white" else None
+            dev = spectral.device
+            losses, d_spec, d_rgb, d_acc = ops.train_loss(
+                spectral.detach(), batch["hs_image"].to(dev), rgb.detach(), acc.detach().reshape(-1),
+                batch["image"].to(dev), bg, w_spec, w_rgb)
+            tensors, grads = [spectral], [d_spec]
+            if d_rgb is not None:
+                tensors += [rgb, acc]
+                grads += [d_rgb, d_acc.unsqueeze(-1)]
+            torch.autograd.backward(tensors, grads)  # kernels accumulate straight into the flat gradient views
+            loss_dict = {"spectral_loss": losses[0]}
+            if w_rgb != 0.0:
+                loss_dict["rgb_loss"] = losses[1]
+            loss_dict["loss"] = losses[0] + losses[1]
+            loss_dict["num_samples"] = outputs["num_samples_per_ray"].sum()
+            return loss_dict
         loss_dict = m.get_loss_dict(outputs, batch)
         loss = sum(loss_dict.values())
         loss.backward()  # kernels accumulate straight into the flat gradient buffer's views
@@ -229,13 +260,14 @@ class UMHSTrainer:
         slot = None
         if isinstance(ray_bundle, tuple) and ray_bundle[0] == "staged":
             slot, ray_bundle, batch = self._unstage(ray_bundle)
+        _dbg = os.environ.get("UMHS_TRAINER_DEBUG")
+        _t0 = time.perf_counter() if _dbg else 0.0
         if self.occ_update:
-            if self.step % 16 == 0 and self.flat.data.is_cuda:
-                # the update synchronises anyway (torch.nonzero); draining the queue first lets the caching
-                # allocator reuse the blocks of the steps in flight instead of growing (measured: 3x faster updates
-                # when the host runs many graph replays ahead)
-                torch.cuda.current_stream(self.flat.data.device).synchronize()
-            m.update_occupancy_grid(self.step, freeze_binaries=self.freeze_binaries)
+            self._occupancy_update()
+        if _dbg and self.step % 16 == 0:
+            torch.cuda.synchronize()
+            print(f"[trainer] step {self.step}: occupancy update {1e3 * (time.perf_counter() - _t0):.2f} ms",
+                  file=sys.stderr)
         n_rays = int(ray_bundle.origins.shape[0])
         check = self.sync_free and (m.sample_capacity is None or self.opt_steps % self.capacity_check_every == 0)
         self.opt_steps += 1
@@ -261,6 +293,36 @@ class UMHSTrainer:
         self.step += 1
         return loss_dict
 
+    # ------------------------------------------------------------------ occupancy-grid update (ref umhs_model.py:549-554)
+    def _occupancy_update(self) -> None:
+        """Every 16 steps.  Past the grid's warm-up the update has a fixed shape and no host sync (occ_grid.py), so it
+        is captured once as its own CUDA graph and replayed: one launch instead of ~150 from the host."""
+        m = self.model
+        if self.step % 16 != 0:
+            return
+        use_graph = self.cuda_graph and self.flat.data.is_cuda and self.step >= 256 and self._occ_graph is not False
+        if not use_graph:
+            m.update_occupancy_grid(self.step, freeze_binaries=self.freeze_binaries)
+            return
+        if self._occ_graph is None:
+            g = torch.cuda.CUDAGraph()
+            try:
+                m.field._aabb6()  # host copy of the field's aabb: read back now, not inside the capture
+                torch.cuda.synchronize(self.flat.data.device)
+                with torch.cuda.graph(g):
+                    m.update_occupancy_grid(self.step, freeze_binaries=self.freeze_binaries)
+                self._occ_graph = g
+            except Exception as e:  # noqa: BLE001 - an op that cannot be captured: stay eager
+                import traceback
+
+                print(f"[umhs_b200] occupancy update not captured ({type(e).__name__}: {e}); running it eagerly\n"
+                      + "".join(traceback.format_tb(e.__traceback__)[-4:]), file=sys.stderr)
+                self._occ_graph = False
+                m.update_occupancy_grid(self.step, freeze_binaries=self.freeze_binaries)
+                return
+        m.step = self.step
+        self._occ_graph.replay()
+
     # ------------------------------------------------------------------ whole-step CUDA graph
     def _graph_step(self, ray_bundle: RayBundle, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
         if self._graph is None or self._graph["capacity"] != self.model.sample_capacity or \
@@ -279,6 +341,9 @@ class UMHSTrainer:
 
     def _capture(self, ray_bundle: RayBundle, batch: Dict[str, Tensor]) -> None:
         dev = self.flat.data.device
+        if os.environ.get("UMHS_TRAINER_DEBUG"):
+            print(f"[trainer] step {self.step}: capturing the step graph (capacity {self.model.sample_capacity})",
+                  file=sys.stderr)
         st = {"capacity": self.model.sample_capacity, "n_rays": int(ray_bundle.origins.shape[0]),
               "origins": ray_bundle.origins.to(dev).clone(), "directions": ray_bundle.directions.to(dev).clone(),
               "image": batch["image"].to(dev).clone(), "hs_image": batch["hs_image"].to(dev).clone()}

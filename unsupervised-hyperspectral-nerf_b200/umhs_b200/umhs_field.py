@@ -233,7 +233,8 @@ class UMHSField(nn.Module):
         out["density"] = density
         return out
 
-    def density_fn(self, positions: Tensor, times: Optional[Tensor] = None) -> Tensor:
-        """nerfstudio Field.density_fn: positions [..., 3] -> density [..., 1]."""
-        pts = PointSet.from_positions(positions, None, contraction=self.contraction, aabb=self._aabb6())
+    def density_fn(self, positions: Tensor, times: Optional[Tensor] = None, n_dev: Optional[Tensor] = None) -> Tensor:
+        """nerfstudio Field.density_fn: positions [..., 3] -> density [..., 1].  ``n_dev`` (extension): device int64
+        count; only the first n_dev positions are evaluated, the rest read as zero density (no host sync)."""
+        pts = PointSet.from_positions(positions, None, contraction=self.contraction, aabb=self._aabb6(), n_dev=n_dev)
         return self.density_packed(pts).view(*positions.shape[:-1], 1)

@@ -236,7 +236,7 @@ class UMHSModel(nn.Module):
     def update_occupancy_grid(self, step: int, **kw) -> None:
         self.step = step
         self.occupancy_grid.update_every_n_steps(
-            step=step, occ_eval_fn=lambda x: self.field.density_fn(x) * self.config.render_step_size, **kw)
+            step=step, occ_eval_fn=lambda x, **k: self.field.density_fn(x, **k) * self.config.render_step_size, **kw)
 
     @torch.no_grad()
     def clamp_endmembers(self, step: int = 0) -> None:
