@@ -370,6 +370,28 @@ def run_b200(args):
     ops.Profiler.reset(enabled=False)
     spr = n_samples / (args.steps * R)
 
+    # evaluation rendering (BASELINE config 4 shape: 800 x 600 image, 32 x 32 tiles dealt round-robin to the ranks, no
+    # collective, eval mode: no visibility filter, no jitter): Msamples/s = packed samples evaluated per second
+    H_EVAL, W_EVAL = 600, 800
+    eo, ed, _, _ = make_rays(H_EVAL * W_EVAL, 4242)
+    cam = RayBundle(eo.view(H_EVAL, W_EVAL, 3).to(dev), ed.view(H_EVAL, W_EVAL, 3).to(dev))
+    res = trainer.render_tiles(cam)  # warm-up
+    barrier()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    n_eval = 0
+    for _ in range(3):
+        res = trainer.render_tiles(cam)
+        n_eval = res["num_samples_per_ray"].sum()
+    eb.record()
+    barrier()
+    eval_ms = torch.tensor([ea.elapsed_time(eb) / 3], device=dev)
+    eval_samples = n_eval.to(torch.float32).reshape(1).clone()
+    if world > 1:
+        dist.all_reduce(eval_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(eval_samples, op=dist.ReduceOp.SUM)
+    model.train()
+
     if rank == 0:
         peaks = {}
         pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -418,6 +440,11 @@ def run_b200(args):
                 "gpu_launches": launches, "clocks": clk, "roofline": roof,
                 "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None,
                 "train_msamples_per_s": world * n_samples / args.steps / (ms / args.steps * 1e-3) / 1e6,
+                "render": {"msamples_per_s": float(eval_samples.item()) / (float(eval_ms.item()) * 1e-3) / 1e6,
+                           "image": f"{W_EVAL}x{H_EVAL}", "ms_per_image": float(eval_ms.item()),
+                           "samples_per_image": float(eval_samples.item()),
+                           "rays_per_s": H_EVAL * W_EVAL / (float(eval_ms.item()) * 1e-3),
+                           "sharding": "32x32 tiles round-robin over ranks, no collective"},
                 "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -156,7 +156,7 @@ class UMHSModel(nn.Module):
         pts, ray_indices, t0, t1, packed_info = self.sampler(
             ray_bundle=ray_bundle, near_plane=cfg.near_plane, far_plane=cfg.far_plane,
             render_step_size=cfg.render_step_size, alpha_thre=cfg.alpha_thre, cone_angle=cfg.cone_angle,
-            jitter=jitter, capacity=self.sample_capacity)
+            jitter=jitter, capacity=self.sample_capacity if self.training else None)  # eval: exact-sized packing
         fo = self.field.forward_packed(pts)
         K, B, spec = self.field.num_classes, self.field.wavelengths, cfg.pred_specular
         d = self.field.mlp_directional.layers
