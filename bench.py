@@ -241,7 +241,8 @@ def workload_config(n_gpus, cpu=False, samples_per_ray=None):
                          f"memory (reduce-scatter reads, all-gather writes), 2 device barriers/step") if n_gpus > 1
          else "single",
          "conditioning_steps": CONDITIONING_STEPS,
-         "launch": "whole step replayed as one CUDA graph (fwd+loss+bwd+Adam); occupancy update eager every 16 steps",
+         "launch": "whole step replayed as one CUDA graph (march+fwd+loss+bwd+exchange+Adam); occupancy update = "
+                   "its own graph every 16 steps",
          "l2_policy": "working set > L2: Adam state 4 x 64 MiB streamed every step + rotating batches"}
     if samples_per_ray is not None:
         c["kept_samples_per_ray"] = samples_per_ray
@@ -285,24 +286,32 @@ def run_b200(args):
     pinned = [tuple(t.pin_memory() for t in b) for b in host]
     resident = [tuple(t.to(dev) for t in b) for b in host]
 
+    # UMHS_BENCH_PIPELINE=1: announce the next batch so that its occupancy march runs beside this step (experimental,
+    # measured gain 1-2 %: see trainer._capture); default: every step marches its own batch first
+    PIPE = bool(os.environ.get("UMHS_BENCH_PIPELINE"))
+
     def step_resident(i):
         o, d, image, hs = resident[i % POOL]
-        return trainer.train_step(RayBundle(o, d), {"image": image, "hs_image": hs})
+        nxt = RayBundle(*resident[(i + 1) % POOL][:2]) if PIPE else None
+        return trainer.train_step(RayBundle(o, d), {"image": image, "hs_image": hs}, next_rays=nxt)
 
-    e2e_state = {"token": None, "prev_loss": None, "losses": []}
+    e2e_state = {"tokens": [], "prev_loss": None, "losses": []}
+
+    def stage_e2e(j):
+        o, d, image, hs = pinned[j % POOL]
+        return trainer.stage(RayBundle(o, d), {"image": image, "hs_image": hs})
 
     def step_e2e(i):
-        """End-to-end step through the public API: batch i is copied from pinned host memory (the copy of batch
-        i+1 is started right after step i is enqueued, so it overlaps the compute), every step's loss is read
-        back to the host (the read of step i-1 is issued after step i is enqueued)."""
+        """End-to-end step through the public API: every batch is copied from pinned host memory (batch i+2 while
+        step i computes; batch i+1 is already on the device and its occupancy march runs beside step i), every
+        step's loss is read back to the host (the read of step i-1 is issued after step i is enqueued)."""
         st = e2e_state
-        if st["token"] is None:
-            o, d, image, hs = pinned[i % POOL]
-            st["token"] = trainer.stage(RayBundle(o, d), {"image": image, "hs_image": hs})
-        out = trainer.train_step(st["token"])
+        while len(st["tokens"]) < 2:
+            st["tokens"].append(stage_e2e(i + len(st["tokens"])))
+        out = trainer.train_step(st["tokens"][0], next_rays=st["tokens"][1] if PIPE else None)
         loss = out["loss"].clone()  # the graph's output tensor is overwritten by the next replay
-        o, d, image, hs = pinned[(i + 1) % POOL]
-        st["token"] = trainer.stage(RayBundle(o, d), {"image": image, "hs_image": hs})
+        st["tokens"].pop(0)
+        st["tokens"].append(stage_e2e(i + 2))
         if st["prev_loss"] is not None:
             st["losses"].append(float(st["prev_loss"].item()))  # device -> host read of a step's result
         st["prev_loss"] = loss
@@ -312,6 +321,7 @@ def run_b200(args):
         if st["prev_loss"] is not None:
             st["losses"].append(float(st["prev_loss"].item()))
             st["prev_loss"] = None
+        st["tokens"].clear()
 
     def barrier():
         if world > 1:
@@ -435,8 +445,9 @@ def run_b200(args):
                 "config": workload_config(world, samples_per_ray=spr),
                 "e2e": {"value": world * R * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
-                        "pipeline": "pinned-host batch i+1 copied on a copy stream while step i runs; loss of every "
-                                    "step read back (one step late); all inside the timed region"},
+                        "pipeline": "pinned-host batches copied two steps ahead on a copy stream (3 staging slots) "
+                                    "while earlier steps run; loss of every step read back (one step late); all "
+                                    "inside the timed region"},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof,
                 "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None,
                 "train_msamples_per_s": world * n_samples / args.steps / (ms / args.steps * 1e-3) / 1e6,

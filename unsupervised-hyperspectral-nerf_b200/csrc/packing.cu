@@ -368,7 +368,10 @@ occ_pack_bits_kernel(const uint8_t *__restrict__ binaries, int64_t cells_per_lev
 }
 
 // Single-CTA exclusive scan of int64 counts -> packed_info[r] = (offset, count); *total = sum.
+// Each thread owns kScanItems consecutive elements (16 384 rays = one tile of 1024 x 16): one local serial scan, one
+// warp-shuffle scan of the per-thread sums, one of the per-warp sums -- three barriers per tile instead of per 1024.
 constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 16;
 __global__ void __launch_bounds__(kScanThreads)
 pack_scan_kernel(const int64_t *__restrict__ counts, int64_t n, int64_t *__restrict__ packed_info, int64_t *total,
                  int64_t capacity) {
@@ -377,11 +380,15 @@ pack_scan_kernel(const int64_t *__restrict__ counts, int64_t n, int64_t *__restr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) base_s = 0;
     __syncthreads();
-    // tiles of kScanThreads consecutive elements: coalesced loads, warp-shuffle scan per tile
-    for (int64_t t0 = 0; t0 < n; t0 += kScanThreads) {
-        const int64_t i = t0 + tid;
-        const int64_t v = i < n ? counts[i] : 0;
-        int64_t incl = v;
+    for (int64_t t0 = 0; t0 < n; t0 += (int64_t)kScanThreads * kScanItems) {
+        const int64_t i0 = t0 + (int64_t)tid * kScanItems;
+        int64_t v[kScanItems], sum = 0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            v[k] = (i0 + k < n) ? counts[i0 + k] : 0;
+            sum += v[k];
+        }
+        int64_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int64_t t = __shfl_up_sync(kFull, incl, o);
@@ -401,15 +408,18 @@ pack_scan_kernel(const int64_t *__restrict__ counts, int64_t n, int64_t *__restr
             if (lane == 31) tile_total_s = wi;
         }
         __syncthreads();
-        const int64_t excl = base_s + warp_sums[warp] + (incl - v);
-        if (i < n) {
-            int64_t start = excl, cnt = v;
-            if (capacity > 0) {  // truncate the packing at `capacity` samples
-                start = excl < capacity ? excl : capacity;
-                cnt = (excl + v <= capacity) ? v : (capacity - start);
+        int64_t excl = base_s + warp_sums[warp] + (incl - sum);
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            if (i0 + k < n) {
+                int64_t start = excl, cnt = v[k];
+                if (capacity > 0) {  // truncate the packing at `capacity` samples
+                    start = excl < capacity ? excl : capacity;
+                    cnt = (excl + v[k] <= capacity) ? v[k] : (capacity - start);
+                }
+                reinterpret_cast<longlong2 *>(packed_info)[i0 + k] = make_longlong2(start, cnt);
             }
-            packed_info[2 * i] = start;
-            packed_info[2 * i + 1] = cnt;
+            excl += v[k];
         }
         __syncthreads();
         if (tid == 0) base_s += tile_total_s;
@@ -576,8 +586,8 @@ extern "C" int umhs_occ_pack_bits(const umhs_march_args *a, uint32_t *bits, int3
 extern "C" int umhs_march_count(const umhs_march_args *a, int64_t *counts, void *stream) {
     UMHS_CHECK_ARG(check_march(a) == 0 && counts, "bad march arguments");
     if (a->n_rays <= 0) return UMHS_OK;
-    // no shared memory: give the whole 256 KB to L1 (the bit-packed level-0 grid then stays resident)
-    UMHS_CHECK_CUDA(cudaFuncSetAttribute(march_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+    // The trainer runs this kernel beside the hash scatter and the optimiser of the previous step (kernels without
+    // shared memory, like this one: all of the SM's 256 KB stays L1 and the bit-packed level-0 grid stays resident).
     march_kernel<false><<<div_up(a->n_rays, 64), 64, 0, as_stream(stream)>>>(*a, a->level_any, counts, nullptr, nullptr,
                                                                              nullptr, nullptr);
     UMHS_CHECK_LAUNCH();

@@ -52,10 +52,26 @@ class OccGridEstimator(nn.Module):
                  far_plane: float = 1e10, t_min: Optional[Tensor] = None, t_max: Optional[Tensor] = None,
                  render_step_size: float = 1e-3, early_stop_eps: float = 1e-4, alpha_thre: float = 0.0,
                  stratified: bool = False, cone_angle: float = 0.0, jitter: Optional[Tensor] = None,
-                 return_packed_info: bool = False, capacity: Optional[int] = None):
+                 return_packed_info: bool = False, capacity: Optional[int] = None, premarched=None):
         """-> (ray_indices int64 [N], t_starts [N], t_ends [N]) (+ packed_info [R,2]).  ``sigma_fn(t_starts, t_ends,
         ray_indices) -> sigma [N]`` enables the visibility filter, as in nerfacc.  ``jitter`` injects the stratified
-        draw (nerfacc: ``torch.rand_like(near_planes)``) so parity tests see identical near planes."""
+        draw (nerfacc: ``torch.rand_like(near_planes)``) so parity tests see identical near planes.
+        ``premarched``: the tuple ``march_candidates`` returned for these rays (the march itself is then skipped)."""
+        if premarched is None:
+            premarched = self.march_candidates(rays_o, rays_d, near_plane, far_plane, t_min, t_max, render_step_size,
+                                               stratified, cone_angle, jitter, capacity)
+        ri, t0, t1, packed, total = premarched
+        return self._filter(ri, t0, t1, packed, total, sigma_fn, early_stop_eps, alpha_thre, return_packed_info,
+                            capacity)
+
+    @torch.no_grad()
+    def march_candidates(self, rays_o: Tensor, rays_d: Tensor, near_plane: float = 0.0, far_plane: float = 1e10,
+                         t_min: Optional[Tensor] = None, t_max: Optional[Tensor] = None, render_step_size: float = 1e-3,
+                         stratified: bool = False, cone_angle: float = 0.0, jitter: Optional[Tensor] = None,
+                         capacity: Optional[int] = None):
+        """The parameter-independent half of ``sampling``: near / far planes, stratified jitter, occupancy march.
+        -> (ray_indices, t_starts, t_ends, packed_info, total).  It depends only on the rays and on ``binaries``, so
+        a trainer may run it for the NEXT batch while the current step is still computing."""
         near = torch.full_like(rays_o[..., 0], fill_value=near_plane)
         far = torch.full_like(rays_o[..., 0], fill_value=far_plane)
         if t_min is not None:
@@ -66,8 +82,10 @@ class OccGridEstimator(nn.Module):
             if jitter is None:
                 jitter = torch.rand_like(near)
             near = near + jitter * render_step_size
-        ri, t0, t1, packed, total = ops.march(rays_o, rays_d, near, far, self.binaries, self.aabbs, render_step_size,
-                                              cone_angle, capacity=capacity)
+        return ops.march(rays_o, rays_d, near, far, self.binaries, self.aabbs, render_step_size, cone_angle,
+                         capacity=capacity)
+
+    def _filter(self, ri, t0, t1, packed, total, sigma_fn, early_stop_eps, alpha_thre, return_packed_info, capacity):
         march_total = total
         self.last_src_index = None
         if (alpha_thre > 0.0 or early_stop_eps > 0.0) and sigma_fn is not None and t0.shape[0] > 0:
@@ -177,11 +195,27 @@ class VolumetricSampler(nn.Module):
         self._field = [field]  # not a submodule: the model owns the field
 
     @torch.no_grad()
+    def march_only(self, ray_bundle, render_step_size: float, near_plane: float = 0.0,
+                   far_plane: Optional[float] = None, cone_angle: float = 0.0, jitter: Optional[Tensor] = None,
+                   capacity: Optional[int] = None):
+        """Candidate samples of a ray bundle (``OccGridEstimator.march_candidates``) with this sampler's conventions."""
+        rays_o = ray_bundle.origins.reshape(-1, 3).to(torch.float32).contiguous()
+        rays_d = ray_bundle.directions.reshape(-1, 3).to(torch.float32).contiguous()
+        t_min = t_max = None
+        if ray_bundle.nears is not None and ray_bundle.fars is not None:
+            t_min = ray_bundle.nears.contiguous().reshape(-1)
+            t_max = ray_bundle.fars.contiguous().reshape(-1)
+        return self.occupancy_grid.march_candidates(
+            rays_o, rays_d, near_plane, 1e10 if far_plane is None else far_plane, t_min, t_max, render_step_size,
+            self.training, cone_angle, jitter, capacity)
+
+    @torch.no_grad()
     def forward(self, ray_bundle, render_step_size: float, near_plane: float = 0.0, far_plane: Optional[float] = None,
                 alpha_thre: float = 0.01, cone_angle: float = 0.0, jitter: Optional[Tensor] = None,
-                capacity: Optional[int] = None):
+                capacity: Optional[int] = None, premarched=None):
         """capacity=None: exact-sized packed samples (one host sync per march / compaction, like the reference).
-        capacity=C: sync-free; buffers hold C samples, ``pts.n_dev`` carries the valid count on the device."""
+        capacity=C: sync-free; buffers hold C samples, ``pts.n_dev`` carries the valid count on the device.
+        premarched: result of ``march_only`` on the same ray bundle."""
         field = self._field[0]
         rays_o = ray_bundle.origins.reshape(-1, 3).to(torch.float32).contiguous()
         rays_d = ray_bundle.directions.reshape(-1, 3).to(torch.float32).contiguous()
@@ -202,7 +236,7 @@ class VolumetricSampler(nn.Module):
         ri, t0, t1, packed, total = self.occupancy_grid.sampling(
             rays_o, rays_d, sigma_fn=sigma_fn, near_plane=near_plane, far_plane=far_plane, t_min=t_min, t_max=t_max,
             render_step_size=render_step_size, stratified=self.training, cone_angle=cone_angle, alpha_thre=alpha_thre,
-            jitter=jitter, return_packed_info=True, capacity=capacity)
+            jitter=jitter, return_packed_info=True, capacity=capacity, premarched=premarched)
         if capacity is None and t0.shape[0] == 0:  # nerfstudio fabricates one sample so shapes are never empty
             dev = rays_o.device
             ri = torch.zeros((1,), dtype=torch.int64, device=dev)

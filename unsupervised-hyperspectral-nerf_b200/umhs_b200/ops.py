@@ -318,6 +318,8 @@ class FieldFunction(torch.autograd.Function):
         d_w_in = {n: (sinks[n] if sinks[n] is not None else torch.zeros_like(w, dtype=torch.float32))
                   for n, w in weights.items() if w is not None}
         d_enc, d_w = field_mlp_bwd(pts, enc, weights, K, cfg["specular"], cfg["temperature"], grads, d_w_in)
+        if AFTER_MLP_BACKWARD is not None:
+            AFTER_MLP_BACKWARD()  # trainer hook: fork work that should run beside the hash scatter and the optimiser
         t_sink = _sink(p_table)
         d_table = hash_encode_bwd(pts, table, scalings, cfg["log2_T"], d_enc, t_sink)
         return (None, None, None if t_sink is not None else d_table, None,
@@ -536,6 +538,7 @@ class AccumulateFunction(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------- packing
+AFTER_MLP_BACKWARD = None  # optional callable, see FieldFunction.backward / trainer.UMHSTrainer._capture
 MARCH_STAGE = 192  # staged interval starts per ray (0 disables staging: the write pass marches again)
 MARCH_BITS = True   # march on a bit-packed copy of the occupancy grid (identical results)
 

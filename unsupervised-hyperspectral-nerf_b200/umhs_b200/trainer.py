@@ -147,6 +147,7 @@ class UMHSTrainer:
         # per-step scalars (lr, Adam bias corrections) travel through a 3-float device buffer
         self.cuda_graph = cuda_graph and sync_free
         self._graph = None
+        self._graph_piped = None
         self._occ_graph = None  # CUDAGraph of the steady-state occupancy update; False: capture failed, stay eager
         self._hyper = torch.zeros(3, dtype=torch.float32, device=self.flat.data.device)
         # ring of pinned staging rows: the CPU may run several steps ahead of the asynchronous copies
@@ -164,20 +165,26 @@ class UMHSTrainer:
     # ------------------------------------------------------------------ input pipeline (host -> device)
     def stage(self, ray_bundle: RayBundle, batch: Dict[str, Tensor]):
         """Start the host->device copy of a batch (pinned host tensors) on a copy stream and return a token for
-        ``train_step``.  Two staging slots: the copy of batch i+1 overlaps the compute of step i."""
+        ``train_step``.  Three staging slots: batch i is being trained, batch i+1 is already on the device (its rays
+        are marched while step i runs, see ``train_step(next_rays=...)``), batch i+2 is being copied."""
         dev = self.flat.data.device
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
-            self._stage_bufs = [None, None]
-            self._slot_free = [None, None]
+            self._stage_bufs = [None, None, None]
+            self._slot_free = [None, None, None]
             self._stage_slot = 0
+            self._stage_seq = 0
         slot = self._stage_slot
-        self._stage_slot ^= 1
+        self._stage_slot = (self._stage_slot + 1) % 3
+        self._stage_seq += 1
         src = {"origins": ray_bundle.origins, "directions": ray_bundle.directions, "image": batch["image"],
                "hs_image": batch["hs_image"]}
         bufs = self._stage_bufs[slot]
         if bufs is None or any(bufs[k].shape != v.shape for k, v in src.items()):
             bufs = self._stage_bufs[slot] = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in src.items()}
+            # The caching allocator may hand out blocks that kernels still queued on the compute stream use (freed
+            # in stream order there); the copy stream must not write them before that work has drained.
+            self._copy_stream.wait_stream(torch.cuda.current_stream(dev))
         if self._slot_free[slot] is not None:
             self._copy_stream.wait_event(self._slot_free[slot])  # the step that last read this slot is done with it
         with torch.cuda.stream(self._copy_stream):
@@ -185,10 +192,10 @@ class UMHSTrainer:
                 bufs[k].copy_(v, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(self._copy_stream)
-        return ("staged", slot, ready)
+        return ("staged", slot, ready, self._stage_seq)
 
     def _unstage(self, token):
-        _, slot, ready = token
+        _, slot, ready, _seq = token
         torch.cuda.current_stream(self.flat.data.device).wait_event(ready)
         b = self._stage_bufs[slot]
         return slot, RayBundle(b["origins"], b["directions"]), {"image": b["image"], "hs_image": b["hs_image"]}
@@ -202,9 +209,9 @@ class UMHSTrainer:
         row[2] = (1.0 - self.betas[1] ** t) ** 0.5
         self._hyper.copy_(row, non_blocking=True)
 
-    def _forward_backward(self, ray_bundle: RayBundle, batch: Dict[str, Tensor]):
+    def _forward_backward(self, ray_bundle: RayBundle, batch: Dict[str, Tensor], premarched=None):
         m = self.model
-        outputs = m.get_outputs(m.collider(ray_bundle), per_band_views=False)
+        outputs = m.get_outputs(m.collider(ray_bundle), per_band_views=False, premarched=premarched)
         if self.fused_loss and outputs["spectral"].is_cuda:
             # UMHSModel.get_loss_dict and its backward as one kernel (csrc/loss.cu): the gradients of the scalar loss
             # with respect to the rendered outputs go straight into the compositing backward
@@ -252,12 +259,27 @@ class UMHSTrainer:
                           inv_scale=self._inv_world if self.world_size > 1 else None, clamp_range=self.clamp_range,
                           zero_grad=True)
 
-    def train_step(self, ray_bundle, batch: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+    @staticmethod
+    def _batch_key(rays):
+        """Identity of a batch of rays (a staged token or a RayBundle of device tensors), to recognise at step i+1 the
+        batch announced as ``next_rays`` at step i."""
+        if rays is None:
+            return None
+        if isinstance(rays, tuple) and rays[0] == "staged":
+            return ("staged", rays[1], rays[3])
+        return ("rays", rays.origins.data_ptr(), rays.origins._version, rays.directions.data_ptr(),
+                rays.directions._version, tuple(rays.origins.shape))
+
+    def train_step(self, ray_bundle, batch: Optional[Dict[str, Tensor]] = None, next_rays=None) -> Dict[str, Tensor]:
         """One training step.  ``ray_bundle`` is a RayBundle (device or pinned-host tensors) with its ``batch``, or a
-        token returned by ``stage``."""
+        token returned by ``stage``.  ``next_rays`` (optional, experimental): the RayBundle / token the NEXT call will
+        train on; its occupancy march -- which depends on the rays and the occupancy grid only -- then runs beside this
+        step's hash scatter and optimiser (a parallel branch of the step's CUDA graph) instead of in front of the next
+        step.  Same results; see ``_capture`` for the measured (small) gain."""
         m = self.model
         m.train()
         slot = None
+        key_cur = self._batch_key(ray_bundle)
         if isinstance(ray_bundle, tuple) and ray_bundle[0] == "staged":
             slot, ray_bundle, batch = self._unstage(ray_bundle)
         _dbg = os.environ.get("UMHS_TRAINER_DEBUG")
@@ -272,7 +294,12 @@ class UMHSTrainer:
         check = self.sync_free and (m.sample_capacity is None or self.opt_steps % self.capacity_check_every == 0)
         self.opt_steps += 1
         self._set_hyper()
-        if self.cuda_graph and m.sample_capacity is not None:
+        pipelined = (next_rays is not None and self.cuda_graph and m.sample_capacity is not None
+                     and (self.world_size == 1 or self.fused_dp))
+        if pipelined:
+            loss_dict = self._graph_step(ray_bundle, batch, key_cur, next_rays,
+                                         remarch=self.occ_update and self.step % 16 == 0)
+        elif self.cuda_graph and m.sample_capacity is not None:
             loss_dict = self._graph_step(ray_bundle, batch)
         else:
             dev = self.flat.data.device
@@ -324,26 +351,48 @@ class UMHSTrainer:
         self._occ_graph.replay()
 
     # ------------------------------------------------------------------ whole-step CUDA graph
-    def _graph_step(self, ray_bundle: RayBundle, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
-        if self._graph is None or self._graph["capacity"] != self.model.sample_capacity or \
-                self._graph["n_rays"] != int(ray_bundle.origins.shape[0]):
-            self._capture(ray_bundle, batch)
-        g = self._graph
+    def _graph_step(self, ray_bundle: RayBundle, batch: Dict[str, Tensor], key_cur=None, next_rays=None,
+                    remarch: bool = False) -> Dict[str, Tensor]:
+        piped = next_rays is not None
+        name = "_graph_piped" if piped else "_graph"
+        g = getattr(self, name, None)
+        if g is None or g["capacity"] != self.model.sample_capacity or g["n_rays"] != int(ray_bundle.origins.shape[0]):
+            self._capture(ray_bundle, batch, piped)
+            g = getattr(self, name)
         g["origins"].copy_(ray_bundle.origins, non_blocking=True)
         g["directions"].copy_(ray_bundle.directions, non_blocking=True)
         g["image"].copy_(batch["image"], non_blocking=True)
         g["hs_image"].copy_(batch["hs_image"], non_blocking=True)
+        if piped:
+            dev = self.flat.data.device
+            nxt = next_rays
+            if isinstance(nxt, tuple) and nxt[0] == "staged":  # rays of a staged batch: its copy must have landed
+                torch.cuda.current_stream(dev).wait_event(nxt[2])
+                b = self._stage_bufs[nxt[1]]
+                nxt = RayBundle(b["origins"], b["directions"])
+            g["next_origins"].copy_(nxt.origins, non_blocking=True)
+            g["next_directions"].copy_(nxt.directions, non_blocking=True)
+            if remarch or key_cur is None or g["key_next"] != key_cur:
+                # the candidates in flight are not this batch's (first step, caller changed its mind) or predate an
+                # occupancy update: march this batch now, in line
+                self.model.train()
+                pm = self.model.premarch(self.model.collider(RayBundle(g["origins"], g["directions"])))
+                for dst, src in zip(g["pm_next"], pm):
+                    dst.copy_(src)
+            g["key_next"] = self._batch_key(next_rays)
+        elif getattr(self, "_graph_piped", None) is not None:
+            self._graph_piped["key_next"] = None  # a plain step in between: the announced batch was not consumed
         g["fwd_bwd"].replay()
         if "opt" in g:
             average_gradients(self.flat.grad, self.world_size)
             g["opt"].replay()
         return g["out"]
 
-    def _capture(self, ray_bundle: RayBundle, batch: Dict[str, Tensor]) -> None:
+    def _capture(self, ray_bundle: RayBundle, batch: Dict[str, Tensor], piped: bool = False) -> None:
         dev = self.flat.data.device
         if os.environ.get("UMHS_TRAINER_DEBUG"):
-            print(f"[trainer] step {self.step}: capturing the step graph (capacity {self.model.sample_capacity})",
-                  file=sys.stderr)
+            print(f"[trainer] step {self.step}: capturing the {'pipelined ' if piped else ''}step graph (capacity "
+                  f"{self.model.sample_capacity})", file=sys.stderr)
         st = {"capacity": self.model.sample_capacity, "n_rays": int(ray_bundle.origins.shape[0]),
               "origins": ray_bundle.origins.to(dev).clone(), "directions": ray_bundle.directions.to(dev).clone(),
               "image": batch["image"].to(dev).clone(), "hs_image": batch["hs_image"].to(dev).clone()}
@@ -357,13 +406,54 @@ class UMHSTrainer:
             for _ in range(2):
                 self._forward_backward(rb, bt)
                 self.flat.grad.zero_()
+            if piped:
+                pm0 = self.model.premarch(self.model.collider(rb))
+                st["next_origins"], st["next_directions"] = st["origins"].clone(), st["directions"].clone()
+                st["pm_next"] = [t.clone() for t in pm0]   # candidates of the batch the next replay trains on
+                st["pm_cur"] = [t.clone() for t in pm0]    # candidates of the batch this replay trains on
+                st["key_next"] = None
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         g1 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1):
-            out = self._forward_backward(rb, bt)
+            if piped:
+                for dst, src in zip(st["pm_cur"], st["pm_next"]):
+                    dst.copy_(src)
+                # Parallel branch: march the NEXT batch while this one computes.  It is forked right after the MLP
+                # backward, beside the hash scatter and the optimiser: those kernels use no shared memory, so the march
+                # CTAs can share their SMs, whereas an SM holding a march CTA cannot take a CTA of the persistent MLP
+                # kernels (214-222 KB of shared memory; measured: forked at the start of the step the branch costs its
+                # full serial time, 0.25 ms).  Measured gain of this placement on 1 x B200: 0.02-0.04 ms of a 1.8 ms
+                # step -- the march is latency-bound and slows down under contention about as much as it overlaps -- so
+                # bench.py does not use it by default (UMHS_BENCH_PIPELINE=1).
+                main = torch.cuda.current_stream(dev)
+                forked = []
+
+                def fork_march():
+                    cur = torch.cuda.current_stream(dev)
+                    branch = torch.cuda.Stream(device=dev, priority=-1)  # its few CTAs go first when slots free up
+                    branch.wait_stream(cur)
+                    with torch.cuda.stream(branch):
+                        pm = self.model.premarch(self.model.collider(RayBundle(st["next_origins"],
+                                                                               st["next_directions"])))
+                        for dst, src in zip(st["pm_next"], pm):
+                            dst.copy_(src)
+                    forked.append(branch)
+
+                ops.AFTER_MLP_BACKWARD = fork_march
+                try:
+                    out = self._forward_backward(rb, bt, premarched=tuple(st["pm_cur"]))
+                finally:
+                    ops.AFTER_MLP_BACKWARD = None
+                if not forked:  # no field backward ran (cannot happen in training): march in line
+                    fork_march()
+            else:
+                out = self._forward_backward(rb, bt)
             if self.world_size == 1 or self.fused_dp:
                 self._optimizer()  # fused_dp: barrier + exchange/Adam kernel + barrier, all inside the graph
+            if piped:
+                for branch in forked:
+                    main.wait_stream(branch)
         st["fwd_bwd"], st["out"] = g1, out
         if self.world_size > 1 and not self.fused_dp:
             g2 = torch.cuda.CUDAGraph()
@@ -372,7 +462,10 @@ class UMHSTrainer:
             st["opt"] = g2
         for dst, src in zip((self.flat.data, self.flat.grad, self.flat.exp_avg, self.flat.exp_avg_sq), snap):
             dst.copy_(src)
-        self._graph = st
+        if piped:
+            self._graph_piped = st
+        else:
+            self._graph = st
 
     def _update_capacity(self, n_rays: int) -> None:
         """One host read of the last step's unclamped candidate count; grows the capacity with 30 % headroom."""

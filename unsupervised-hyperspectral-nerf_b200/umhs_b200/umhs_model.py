@@ -147,8 +147,19 @@ class UMHSModel(nn.Module):
         return self.class_colors[labels.long().squeeze(-1)]
 
     # ------------------------------------------------------------------ ref umhs_model.py:225-327
+    @torch.no_grad()
+    def premarch(self, ray_bundle: RayBundle, jitter: Optional[Tensor] = None):
+        """Occupancy march of a (collided) ray bundle: the parameter-independent first stage of ``get_outputs``, for
+        trainers that run it one batch ahead (pass the result back as ``get_outputs(..., premarched=...)``)."""
+        cfg = self.config
+        if ray_bundle.nears is None:
+            ray_bundle = self.collider(ray_bundle)
+        return self.sampler.march_only(
+            ray_bundle, render_step_size=cfg.render_step_size, near_plane=cfg.near_plane, far_plane=cfg.far_plane,
+            cone_angle=cfg.cone_angle, jitter=jitter, capacity=self.sample_capacity if self.training else None)
+
     def get_outputs(self, ray_bundle: RayBundle, jitter: Optional[Tensor] = None,
-                    per_band_views: bool = True) -> Dict[str, Tensor]:
+                    per_band_views: bool = True, premarched=None) -> Dict[str, Tensor]:
         cfg = self.config
         num_rays = int(ray_bundle.origins.reshape(-1, 3).shape[0])
         if ray_bundle.nears is None:
@@ -156,7 +167,8 @@ class UMHSModel(nn.Module):
         pts, ray_indices, t0, t1, packed_info = self.sampler(
             ray_bundle=ray_bundle, near_plane=cfg.near_plane, far_plane=cfg.far_plane,
             render_step_size=cfg.render_step_size, alpha_thre=cfg.alpha_thre, cone_angle=cfg.cone_angle,
-            jitter=jitter, capacity=self.sample_capacity if self.training else None)  # eval: exact-sized packing
+            jitter=jitter, capacity=self.sample_capacity if self.training else None,  # eval: exact-sized packing
+            premarched=premarched)
         fo = self.field.forward_packed(pts)
         K, B, spec = self.field.num_classes, self.field.wavelengths, cfg.pred_specular
         d = self.field.mlp_directional.layers
