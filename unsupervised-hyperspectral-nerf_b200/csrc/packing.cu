@@ -150,7 +150,6 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
     const int64_t cells_per_level = (int64_t)res * res * res;
     int64_t n = 0;
     float t_last = near_plane;
-    float pending = -1.0f;  // largest threshold of the empty cells skipped since t_last was last advanced (< 0: none)
     // Intervals behind the last one whose grid level holds any occupied cell can only produce empty cells: nothing
     // is emitted there and nothing later reads the orbit state they would leave behind, so the march stops before
     // them (with level_any == nullptr every level counts as possibly occupied).
@@ -164,6 +163,33 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
                 break;
             }
     }
+    // occupied runs recorded by phase 1, consumed by phase 2: (last empty threshold before the run or -1, run end)
+    constexpr int kRunCap = 24;
+    float rec_pend[kRunCap], rec_end[kRunCap];
+    int n_rec = 0;
+    float pend = -1.0f;  // threshold of the empty cells passed since the last occupied run (< 0: none)
+    // Phase 2: walk the orbit through the recorded runs.  Returns true when a capacity-truncated ray is full.
+    auto flush_runs = [&]() -> bool {
+        for (int k = 0; k < n_rec; ++k) {
+            if (rec_pend[k] >= 0.0f) t_last = advance_orbit(t_last, rec_pend[k], cone_angle, step_size);
+            const float t_run = rec_end[k];
+            for (;;) {
+                const float dt = calc_dt(t_last, cone_angle, step_size, 1e10f);
+                if (t_last + dt * 0.5f >= t_run) break;
+                if (WRITE) {
+                    if (n >= limit) return true;  // capacity-truncated ray
+                    t0_out[n] = t_last;
+                    t1_out[n] = t_last + dt;
+                } else if (n < limit) {
+                    t0_out[n] = t_last;  // count pass: stage the interval starts (t1 = t0 + calc_dt(t0))
+                }
+                ++n;
+                t_last += dt;
+            }
+        }
+        n_rec = 0;
+        return false;
+    };
     for (int i = 0; i <= last_useful; ++i) {
         const float a = ts[i], b = ts[i + 1];
         if (!(a < b)) continue;
@@ -217,51 +243,38 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
         uint8_t occ = lookup ? fetch(cell) : (uint8_t)0;
         bool last = false;
         int guard = 4 * res + 8;
-        // Runs of cells with equal occupancy are consumed by one tight DDA loop, then one orbit loop handles the
-        // whole run: for an OCCUPIED run c1..cm with thresholds T1 < .. < Tm the oracle emits, cell by cell, the
-        // orbit points with t + dt/2 < Ti -- together exactly the points with t + dt/2 < Tm (same monotonicity as
-        // the lazy skip).  All lanes of a warp reach the orbit loops at the same place in the code, so the loops of
-        // different rays overlap instead of serialising per cell.
+        // Phase 1 (this loop): the DDA alone, one cell per iteration for every lane of the warp, no inner loops.  Runs
+        // of cells with equal occupancy collapse to their last threshold: for an OCCUPIED run c1..cm with thresholds
+        // T1 < .. < Tm the oracle emits, cell by cell, the orbit points with t + dt/2 < Ti -- together exactly the
+        // points with t + dt/2 < Tm (same monotonicity as the lazy skip); an empty run leaves `pend` = its last
+        // threshold.  Every occupied run is RECORDED as (pend before it, Tm); the orbit work happens in phase 2
+        // (flush_runs), where the k-th occupied run of every ray of the warp is processed side by side.  With the orbit
+        // loops inside the DDA loop the lanes of a warp serialised on each other's runs (ncu: 12 of 32 lanes active).
         while (!last && guard > 0) {
-            const uint8_t run_occ = occ;
-            float t_run = 0.0f;  // threshold of the last cell of the run
-            do {
-                float t_traverse = fminf(td0, fminf(td1, td2));
-                t_traverse = fminf(t_traverse, this_tmax);
-                t_run = t_traverse;
-                // single DDA step: x if strictly smallest, else y if < z, else z -- taken now so that the NEXT cell's
-                // occupancy is in flight while this cell is processed
-                const bool ax0 = (td0 < td1) && (td0 < td2);
-                const bool ax1 = !ax0 && (td1 < td2);
-                if (ax0)      { td0 += delta[0]; cell += stride[0]; last = (--l0 == 0); }
-                else if (ax1) { td1 += delta[1]; cell += stride[1]; last = (--l1 == 0); }
-                else          { td2 += delta[2]; cell += stride[2]; last = (--l2 == 0); }
-                occ = (lookup && !last) ? fetch(cell) : (uint8_t)0;
-                --guard;
-            } while (!last && guard > 0 && occ == run_occ);
-            if (!run_occ) {
-                pending = t_run;  // monotone: later thresholds dominate earlier ones
-            } else {
-                if (pending >= 0.0f) {
-                    t_last = advance_orbit(t_last, pending, cone_angle, step_size);
-                    pending = -1.0f;
-                }
-                for (;;) {
-                    const float dt = calc_dt(t_last, cone_angle, step_size, 1e10f);
-                    if (t_last + dt * 0.5f >= t_run) break;
-                    if (WRITE) {
-                        if (n >= limit) return n;  // capacity-truncated ray
-                        t0_out[n] = t_last;
-                        t1_out[n] = t_last + dt;
-                    } else if (n < limit) {
-                        t0_out[n] = t_last;  // count pass: stage the interval starts (t1 = t0 + calc_dt(t0))
-                    }
-                    ++n;
-                    t_last += dt;
+            float t_traverse = fminf(td0, fminf(td1, td2));
+            t_traverse = fminf(t_traverse, this_tmax);
+            // single DDA step: x if strictly smallest, else y if < z, else z
+            const bool ax0 = (td0 < td1) && (td0 < td2);
+            const bool ax1 = !ax0 && (td1 < td2);
+            if (ax0)      { td0 += delta[0]; cell += stride[0]; last = (--l0 == 0); }
+            else if (ax1) { td1 += delta[1]; cell += stride[1]; last = (--l1 == 0); }
+            else          { td2 += delta[2]; cell += stride[2]; last = (--l2 == 0); }
+            const uint8_t occ_next = (lookup && !last) ? fetch(cell) : (uint8_t)0;
+            --guard;
+            if (last || guard == 0 || occ_next != occ) {  // the cell just left ends a run
+                if (!occ) {
+                    pend = t_traverse;  // monotone: later thresholds dominate earlier ones
+                } else {
+                    rec_pend[n_rec] = pend;
+                    rec_end[n_rec] = t_traverse;
+                    pend = -1.0f;
+                    if (++n_rec == kRunCap && flush_runs()) return n;
                 }
             }
+            occ = occ_next;
         }
     }
+    if (flush_runs()) return n;
     return n;
 }
 
