@@ -240,7 +240,8 @@ def workload_config(n_gpus, cpu=False, samples_per_ray=None):
          "bands": BANDS, "endmembers": K_CLASSES, "temperature": TEMPERATURE, "hash": "16x2@2^19",
          "occupancy": f"128^3x4 shell r={SHELL_R} t={SHELL_T}", "method": "rgb+spectral", "specular": False,
          "parallelism": (f"dp{n_gpus} ray-sharded; gradient exchange + Adam fused in one kernel over NVLink peer "
-                         f"memory (reduce-scatter reads, all-gather writes), 2 device barriers/step") if n_gpus > 1
+                         f"memory (reduce-scatter reads, all-gather writes; NVLS multimem when the fabric offers a "
+                         f"multicast address), 2 device barriers/step") if n_gpus > 1
          else "single",
          "conditioning_steps": CONDITIONING_STEPS,
          "launch": "whole step replayed as one CUDA graph (march+fwd+loss+bwd+exchange+Adam); occupancy update = "
@@ -444,7 +445,9 @@ def run_b200(args):
         line = {"metric": "train rays/s", "value": world * R * args.steps / (ms * 1e-3), "unit": "rays/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(world, samples_per_ray=spr),
+                "config": {**workload_config(world, samples_per_ray=spr),
+                           **({"dp_exchange": "nvls multimem" if trainer.flat.mc_grad else "peer loads/stores"}
+                              if world > 1 else {})},
                 "e2e": {"value": world * R * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
                         "pipeline": "pinned-host batches copied two steps ahead on a copy stream (3 staging slots) "

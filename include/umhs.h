@@ -352,12 +352,15 @@ int umhs_adam_step_dev(float *param, float *grad, float *exp_avg, float *exp_avg
  * landed, all gradients consumed -- only then may a rank zero its gradient buffer or start the next forward).
  * signal_pads: DEVICE array of `world` pointers to each rank's zero-initialised pad of >= 8 x 8 uint32;
  * epoch: this rank's device counter for the channel pair (zero-initialised, one per signal-pad set).
+ * mc_grad / mc_param (optional, NULL = off): NVLS multicast addresses of the same gradient / parameter buffers.  The
+ * reduce-scatter then is one multimem.ld_reduce per 16 bytes (summed inside the NVSwitch) and the all-gather one
+ * multimem.st: 1.0 instead of 1.75 buffer sizes on each GPU's links per direction at 8 GPUs.
  * ------------------------------------------------------------------------------- */
 int umhs_dp_barrier(uint32_t *const *signal_pads, int32_t rank, int32_t world, int32_t channel, uint32_t *epoch,
                     void *stream);
 int umhs_dp_adam_step(const float *const *peer_grads, float *const *peer_params, float *exp_avg, float *exp_avg_sq,
                       int64_t n, int32_t rank, int32_t world, float beta1, float beta2, float eps, const float *hyper,
-                      int64_t clamp_begin, int64_t clamp_end, void *stream);
+                      int64_t clamp_begin, int64_t clamp_end, const float *mc_grad, float *mc_param, void *stream);
 /* out[i] += sum_s slabs[s*stride + i] */
 int umhs_reduce_slabs(const float *slabs, int64_t n_slabs, int64_t stride, int64_t n, float *out, void *stream);
 

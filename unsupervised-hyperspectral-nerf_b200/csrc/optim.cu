@@ -86,6 +86,8 @@ struct DpAdamArgs {
     const float *peer_grad[UMHS_MAX_RANKS];
     float *peer_param[UMHS_MAX_RANKS];
     float *m, *v;
+    const float *mc_grad;  // optional NVLS multicast addresses of the same buffers: one multimem.ld_reduce returns the
+    float *mc_param;       // sum over all replicas (reduced in the switch), one multimem.st writes all replicas
     int64_t begin, end;  // this rank's shard (multiples of 4)
     int world, rank;
     float beta1, beta2, eps, inv_world;
@@ -101,11 +103,18 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpAdamArgs a) {
          i += (int64_t)gridDim.x * blockDim.x) {
         // reduce-scatter: this shard of every rank's gradient (peer loads first: they have the longest latency)
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.mc_grad != nullptr) {
+            asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w)
+                         : "l"(a.mc_grad + 4 * i)
+                         : "memory");
+        } else {
 #pragma unroll
-        for (int w = 0; w < UMHS_MAX_RANKS; ++w) {
-            if (w < a.world) {
-                const float4 x = reinterpret_cast<const float4 *>(a.peer_grad[w])[i];
-                g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+            for (int w = 0; w < UMHS_MAX_RANKS; ++w) {
+                if (w < a.world) {
+                    const float4 x = reinterpret_cast<const float4 *>(a.peer_grad[w])[i];
+                    g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+                }
             }
         }
         float4 p = own_p[i], m = m4[i], v = v4[i];
@@ -123,9 +132,15 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpAdamArgs a) {
         m4[i] = m;
         v4[i] = v;
         // all-gather: the updated shard goes to every rank's parameter buffer
+        if (a.mc_param != nullptr) {
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a.mc_param + 4 * i),
+                         "f"(p.x), "f"(p.y), "f"(p.z), "f"(p.w)
+                         : "memory");
+        } else {
 #pragma unroll
-        for (int w = 0; w < UMHS_MAX_RANKS; ++w)
-            if (w < a.world) reinterpret_cast<float4 *>(a.peer_param[w])[i] = p;
+            for (int w = 0; w < UMHS_MAX_RANKS; ++w)
+                if (w < a.world) reinterpret_cast<float4 *>(a.peer_param[w])[i] = p;
+        }
     }
 }
 
@@ -212,8 +227,10 @@ extern "C" int umhs_dp_barrier(uint32_t *const *signal_pads, int32_t rank, int32
 
 extern "C" int umhs_dp_adam_step(const float *const *peer_grads, float *const *peer_params, float *exp_avg,
                                  float *exp_avg_sq, int64_t n, int32_t rank, int32_t world, float beta1, float beta2,
-                                 float eps, const float *hyper, int64_t clamp_begin, int64_t clamp_end, void *stream) {
+                                 float eps, const float *hyper, int64_t clamp_begin, int64_t clamp_end,
+                                 const float *mc_grad, float *mc_param, void *stream) {
     UMHS_CHECK_ARG(peer_grads && peer_params && exp_avg && exp_avg_sq && hyper, "null argument");
+    UMHS_CHECK_ARG(((uintptr_t)mc_grad | (uintptr_t)mc_param) % 16 == 0, "multicast addresses must be 16-byte aligned");
     UMHS_CHECK_ARG(world >= 1 && world <= UMHS_MAX_RANKS && rank >= 0 && rank < world, "bad rank / world");
     UMHS_CHECK_ARG(n % 4 == 0, "the flat buffer length must be a multiple of 4");
     if (n <= 0) return UMHS_OK;
@@ -228,6 +245,7 @@ extern "C" int umhs_dp_adam_step(const float *const *peer_grads, float *const *p
     a.begin = 4 * (per * rank < n4 ? per * rank : n4);
     a.end = 4 * (per * (rank + 1) < n4 ? per * (rank + 1) : n4);
     a.m = exp_avg; a.v = exp_avg_sq; a.world = world; a.rank = rank;
+    a.mc_grad = mc_grad; a.mc_param = mc_param;
     a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.inv_world = 1.0f / (float)world; a.hyper = hyper;
     a.clamp_begin = clamp_begin; a.clamp_end = clamp_end;
     const int64_t want = ((a.end - a.begin) / 4 + 255) / 256;

@@ -125,7 +125,8 @@ _SIGNATURES = {
     "umhs_reduce_slabs": [P, c_int64, c_int64, c_int64, P, P],
     "umhs_train_loss": [c_int64, c_int32, c_int32, P, P, P, P, P, P, c_float, c_float, P, P, P, P, P],
     "umhs_dp_barrier": [P, c_int32, c_int32, c_int32, P, P],
-    "umhs_dp_adam_step": [P, P, P, P, c_int64, c_int32, c_int32, c_float, c_float, c_float, P, c_int64, c_int64, P],
+    "umhs_dp_adam_step": [P, P, P, P, c_int64, c_int32, c_int32, c_float, c_float, c_float, P, c_int64, c_int64, P, P,
+                          P],
 }
 _RESTYPES = {"umhs_last_error": c_char_p}
 

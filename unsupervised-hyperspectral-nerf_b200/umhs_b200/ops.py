@@ -661,12 +661,13 @@ def dp_barrier(pads: Tensor, rank: int, world: int, channel: int, epochs: Tensor
 
 def dp_adam_step(peer_grads: List[int], peer_params: List[int], exp_avg: Tensor, exp_avg_sq: Tensor, n: int, rank: int,
                  world: int, beta1: float, beta2: float, eps: float, hyper: Tensor,
-                 clamp_range: Tuple[int, int] = (0, 0)) -> None:
-    """Fused reduce-scatter + Adam + all-gather over NVLink peer memory (include/umhs.h: umhs_dp_adam_step)."""
+                 clamp_range: Tuple[int, int] = (0, 0), mc_grad: int = 0, mc_param: int = 0) -> None:
+    """Fused reduce-scatter + Adam + all-gather over NVLink peer memory (include/umhs.h: umhs_dp_adam_step).
+    mc_grad / mc_param: NVLS multicast addresses of the buffers (0: plain peer loads / stores)."""
     pg = (ctypes.c_void_p * world)(*peer_grads)
     pp = (ctypes.c_void_p * world)(*peer_params)
     _call("umhs_dp_adam_step", n // world, pg, pp, ptr(exp_avg), ptr(exp_avg_sq), n, rank, world, beta1, beta2, eps,
-          ptr(hyper), clamp_range[0], clamp_range[1], stream_ptr(exp_avg.device))
+          ptr(hyper), clamp_range[0], clamp_range[1], mc_grad or None, mc_param or None, stream_ptr(exp_avg.device))
 
 
 def tc05_selftest(mode: int, A: Tensor, B: Tensor, N: int, K: int) -> Tensor:
