@@ -93,12 +93,12 @@ __device__ __forceinline__ void stage_all_weights(uint8_t *smem, const umhs_mlp_
 
 struct WAddr {  // async-proxy addresses of the weight tiles and of the ones tile
     uint32_t b0, b1, hf0, h1, f1, h2, f2, d0, ones;
-    __device__ __forceinline__ explicit WAddr(uint8_t *smem) {
-        b0 = smem_u32(smem + TcSmem::w_base0); b1 = smem_u32(smem + TcSmem::w_base1);
-        hf0 = smem_u32(smem + TcSmem::w_hf0);  h1 = smem_u32(smem + TcSmem::w_h1);
-        f1 = smem_u32(smem + TcSmem::w_f1);    h2 = smem_u32(smem + TcSmem::w_h2);
-        f2 = smem_u32(smem + TcSmem::w_f2);    d0 = smem_u32(smem + TcSmem::w_d0);
-        ones = smem_u32(smem + TcSmem::ones);
+    __device__ __forceinline__ explicit WAddr(uint32_t sb) {  // sb = shared-window address of the CTA's dynamic smem
+        b0 = sb + TcSmem::w_base0; b1 = sb + TcSmem::w_base1;
+        hf0 = sb + TcSmem::w_hf0;  h1 = sb + TcSmem::w_h1;
+        f1 = sb + TcSmem::w_f1;    h2 = sb + TcSmem::w_h2;
+        f2 = sb + TcSmem::w_f2;    d0 = sb + TcSmem::w_d0;
+        ones = sb + TcSmem::ones;
     }
 };
 
@@ -305,7 +305,10 @@ __device__ __forceinline__ void issuer_rotation(uint64_t *bars, const int64_t (&
                     fence_after_sync();
                     tr.stamp(2000 + 100 * g + decltype(rc)::value);
                     if (elect_one()) {
-                        issue(rc, gc, (it == 0 && g == 0) ? 0u : 1u);
+                        // `it >> 40` is zero, but not provably so: the descriptors of a round are then recomputed in
+                        // the uniform datapath (a couple of UIADD3 per MMA) instead of being hoisted out of the tile
+                        // loop into ~50 vector registers that need an R2UR each before every tcgen05.mma
+                        issue(rc, gc, (it == 0 && g == 0) ? 0u : 1u, (uint32_t)(it >> 40));
                         commit(bars + G + g);
                     }
                     __syncwarp();
@@ -375,11 +378,12 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             const int64_t first = (int64_t)blockIdx.x * G + g, stride = (int64_t)gridDim.x * G;
             n_iter[g] = first < n_tiles ? (n_tiles - 1 - first) / stride + 1 : 0;
         }
-        const WAddr w(smem);
-        const uint32_t gb = smem_u32(smem + TcSmem::groups);
-        issuer_rotation<G, ROUNDS>(bars, n_iter, Tracer(false, 1), [&](auto rc, auto gc, uint32_t) {
+        const uint32_t sbase = smem_u32(smem);
+        issuer_rotation<G, ROUNDS>(bars, n_iter, Tracer(false, 1), [&](auto rc, auto gc, uint32_t, uint32_t zero) {
             constexpr int r = decltype(rc)::value, g = decltype(gc)::value;
-            const uint32_t b = gb + (uint32_t)(g * GRP_BYTES);
+            const uint32_t sb = sbase + zero;
+            const WAddr w(sb);
+            const uint32_t b = sb + (uint32_t)(TcSmem::groups + g * GRP_BYTES);
             const uint32_t sX = b + TcFwd::tX, sH = b + TcFwd::tH, sF = b + TcFwd::tF;
             const uint32_t tw = tbase + (uint32_t)(WCOLS * g);
             if constexpr (r == 0) {
@@ -652,12 +656,14 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             const int64_t first = (int64_t)blockIdx.x * G + q, stride = (int64_t)gridDim.x * G;
             n_iter[q] = first < n_tiles ? (n_tiles - 1 - first) / stride + 1 : 0;
         }
-        const WAddr w(smem);
-        const uint32_t gb = smem_u32(smem + TcSmem::groups);
+        const uint32_t sbase = smem_u32(smem);
         const bool want_denc = d_enc != nullptr;
-        issuer_rotation<G, TcBwd::kRounds>(bars, n_iter, Tracer(lane == 0, 1), [&](auto rc, auto gc, uint32_t acc) {
+        issuer_rotation<G, TcBwd::kRounds>(bars, n_iter, Tracer(lane == 0, 1), [&](auto rc, auto gc, uint32_t acc,
+                                                                                  uint32_t zero) {
             constexpr int r = decltype(rc)::value, q = decltype(gc)::value;
-            const uint32_t b = gb + (uint32_t)(q * TcBwd::grp_bytes);
+            const uint32_t sb = sbase + zero;
+            const WAddr w(sb);
+            const uint32_t b = sb + (uint32_t)(TcSmem::groups + q * TcBwd::grp_bytes);
             const uint32_t sA0 = b + TcBwd::tA0, sX = b + TcBwd::tX, sH1 = b + TcBwd::tH1, sH2 = b + TcBwd::tH2;
             const uint32_t sD1 = b + TcBwd::tD1, sD2 = b + TcBwd::tD2, sX2 = sD1;
             const uint32_t tw = tbase + 64u * q;

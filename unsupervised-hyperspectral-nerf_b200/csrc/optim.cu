@@ -48,7 +48,16 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
     float4 *p4 = reinterpret_cast<float4 *>(a.p), *g4 = reinterpret_cast<float4 *>(a.g);
     float4 *m4 = reinterpret_cast<float4 *>(a.m), *v4 = reinterpret_cast<float4 *>(a.v);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        float4 p = p4[i], g = g4[i], m = m4[i], v = v4[i];
+        float4 g = g4[i], m = m4[i], v = v4[i];
+        // Entries that never received a gradient (g = m = v = 0: most of the coarse, spatially dense hash levels
+        // outside the scene) are left untouched by Adam -- bit-identical to running the update (m, v stay 0, the step
+        // is 0 / (0 + eps) = 0) -- so their parameter read and all four writes are skipped: 48 instead of 128 bytes.
+        if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f && m.x == 0.f && m.y == 0.f && m.z == 0.f &&
+            m.w == 0.f && v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) {
+            const bool clamp = 4 * i + 3 >= a.clamp_begin && 4 * i < a.clamp_end;
+            if (!clamp) continue;  // (clamped entries still need the clamp applied)
+        }
+        float4 p = p4[i];
         adam_one(p.x, g.x, m.x, v.x, a, gs, 4 * i + 0);
         adam_one(p.y, g.y, m.y, v.y, a, gs, 4 * i + 1);
         adam_one(p.z, g.z, m.z, v.z, a, gs, 4 * i + 2);
@@ -117,7 +126,14 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(DpAdamArgs a) {
                 }
             }
         }
-        float4 p = own_p[i], m = m4[i], v = v4[i];
+        float4 m = m4[i], v = v4[i];
+        // untouched entries (no gradient on any rank, no optimiser state): Adam leaves them bit-identical, every
+        // replica already holds them -- skip the update and, above all, the all-gather writes (see adam_kernel)
+        if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f && m.x == 0.f && m.y == 0.f && m.z == 0.f &&
+            m.w == 0.f && v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f &&
+            !(4 * i + 3 >= a.clamp_begin && 4 * i < a.clamp_end))
+            continue;
+        float4 p = own_p[i];
         float *pp = &p.x, *gg = &g.x, *mm = &m.x, *vv = &v.x;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
