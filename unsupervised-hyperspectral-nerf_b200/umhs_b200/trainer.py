@@ -504,7 +504,11 @@ class UMHSTrainer:
         m.eval()
         H, W = camera_ray_bundle.origins.shape[:2]
         dev = m.device
-        index = tile_pixel_indices(H, W, tile, self.rank, self.world_size, dev)
+        key = (H, W, tile, self.rank, self.world_size, str(dev))
+        cache = self.__dict__.setdefault("_tile_index_cache", {})
+        if key not in cache:  # a few hundred tiny launches per image otherwise
+            cache[key] = tile_pixel_indices(H, W, tile, self.rank, self.world_size, dev)
+        index = cache[key]
         o = camera_ray_bundle.origins.reshape(-1, 3).to(dev)[index]
         d = camera_ray_bundle.directions.reshape(-1, 3).to(dev)[index]
         out: Dict[str, List[Tensor]] = {}
