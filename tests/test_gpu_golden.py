@@ -222,19 +222,26 @@ def test_trainer_cuda_graph_matches_eager():
     d, meta = load_golden("model_train_k4.npz")
     batch = {"image": t(d["image"]).to(DEV), "hs_image": t(d["hs_image"]).to(DEV)}
     res = {}
-    for graph in (False, True):
+    rb_fixed = RayBundle(t(d["origins"]).to(DEV), t(d["directions"]).to(DEV))
+    for graph in (False, True, "piped"):
         torch.manual_seed(0)
         m = b200_model_from_golden(d, meta, True)
         m.config.background_color = "black"  # no RNG in the loss; the stratified jitter is reseeded below
-        tr = UMHSTrainer(m, lr=1e-3, occ_update=False, cuda_graph=graph, capacity_check_every=4)
+        tr = UMHSTrainer(m, lr=1e-3, occ_update=False, cuda_graph=bool(graph), capacity_check_every=4)
         losses = []
         for i in range(6):
             torch.manual_seed(100 + i)
             m._fixed_jitter = None
-            rb = RayBundle(t(d["origins"]).to(DEV), t(d["directions"]).to(DEV))
-            losses.append(tr.train_step(rb, batch)["loss"].clone())
+            if graph == "piped":  # the next batch (the same rays) is announced: its march runs as a graph branch
+                losses.append(tr.train_step(rb_fixed, batch, next_rays=rb_fixed)["loss"].clone())
+            else:
+                rb = RayBundle(t(d["origins"]).to(DEV), t(d["directions"]).to(DEV))
+                losses.append(tr.train_step(rb, batch)["loss"].clone())
         res[graph] = (torch.stack(losses).cpu(), tr.flat.data.clone().cpu(), tr.truncated_steps)
-    assert res[True][2] == 0 and res[False][2] == 0
+    assert res[True][2] == 0 and res[False][2] == 0 and res["piped"][2] == 0
+    assert torch.isfinite(res["piped"][0]).all()
+    assert (res["piped"][0] - res[False][0]).abs().max() < 5e-2 * res[False][0].abs().max()
+    assert (res["piped"][1] - res[False][1]).abs().max() < 5e-2
     # stratified jitter differs between the two runs (graph RNG offsets), so compare statistically-identical setups:
     # with jitter removed from the picture the runs are deterministic -> use eval-style near planes
     assert torch.isfinite(res[True][0]).all() and torch.isfinite(res[False][0]).all()
