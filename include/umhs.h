@@ -209,6 +209,7 @@ typedef struct {
     const float *d_rgb;       /* [R,3] or NULL (gradient w.r.t. the gamma-corrected, clamped rgb) */
     const float *d_accumulation; /* [R] or NULL */
     const float *spectral;    /* [R,B] forward output (needed when d_rgb is given) */
+    const float *trans;       /* [N] forward output `trans`, or NULL (the transmittance is then recomputed) */
 } umhs_composite_grads_in;
 
 typedef struct {

@@ -221,7 +221,13 @@ def _oracle_composite(c, specular, grad_scaling):
 
 @pytest.mark.parametrize("R,K,B,specular,gs", [(300, 4, 128, False, True), (300, 9, 128, True, True),
                                                (64, 16, 512, True, False), (200, 6, 32, False, False),
-                                               (128, 8, 256, False, True), (5, 4, 128, True, True)])
+                                               (128, 8, 256, False, True), (5, 4, 128, True, True),
+                                               # lane-group kernels (no specular): bands not a multiple of 4 (the
+                                               # hotdog fixture has 141), K not a multiple of 4, widest shapes,
+                                               # ray counts that leave partly filled warps / CTA iterations
+                                               (257, 4, 141, False, True), (70, 16, 512, False, True),
+                                               (1000, 4, 64, False, False), (33, 12, 100, False, True),
+                                               (19, 16, 32, False, True), (130, 8, 384, False, False)])
 def test_composite_fwd_bwd(R, K, B, specular, gs):
     ops = _ops()
     c = _packed_case(R, K, B, specular, seed=R + K)

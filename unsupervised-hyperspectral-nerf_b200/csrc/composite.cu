@@ -19,7 +19,7 @@
 // one atomic per element per CTA.
 #include <math_constants.h>
 
-#include "common.cuh"
+#include "composite.cuh"
 
 namespace umhs {
 
@@ -45,13 +45,6 @@ __host__ __device__ inline SmemLayout make_layout(int K, int B, bool specular, b
     s.carry = o; o += bwd ? kCompWarps * kMaxChunks : 0;
     s.total = o;
     return s;
-}
-
-__device__ __forceinline__ float gamma_fwd(float x) {
-    return x < 0.0031308f ? 12.92f * x : 1.055f * powf(fmaxf(x, 1e-6f), 1.0f / 2.4f) - 0.055f;
-}
-__device__ __forceinline__ float gamma_grad(float x) {
-    return x < 0.0031308f ? 12.92f : (1.055f / 2.4f) * powf(fmaxf(x, 1e-6f), 1.0f / 2.4f - 1.0f);
 }
 
 __device__ __forceinline__ void load_h16(const float *h, float (&hv)[16]) {
@@ -549,6 +542,7 @@ extern "C" int umhs_composite_fwd(const umhs_composite_in *in, const umhs_compos
     UMHS_CHECK_ARG(check_in(in) == 0, "bad composite input");
     UMHS_CHECK_ARG(out != nullptr, "null output");
     if (in->n_rays <= 0) return UMHS_OK;
+    if (!in->specular) return composite_group_fwd(in, out, as_stream(stream));  // lane-group form (composite_group.cu)
     UMHS_DISPATCH_KB(launch_fwd, in, out, as_stream(stream));
 }
 
@@ -568,5 +562,7 @@ extern "C" int umhs_composite_bwd(const umhs_composite_in *in, const umhs_compos
     UMHS_CHECK_ARG(!gin->d_rgb || gin->spectral, "d_rgb needs the forward spectral output");
     UMHS_CHECK_ARG(!in->specular || (gout->d_s1 && gout->d_spec_hidden), "specular needs d_s1/d_spec_hidden");
     if (in->n_rays <= 0) return UMHS_OK;
+    // lane-group form when the forward's transmittance is at hand; otherwise the warp-per-ray kernel recomputes it
+    if (!in->specular && gin->trans) return composite_group_bwd(in, gin, gout, as_stream(stream));
     UMHS_DISPATCH_KB(launch_bwd, in, gin, gout, as_stream(stream));
 }

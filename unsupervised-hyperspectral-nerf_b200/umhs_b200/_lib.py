@@ -66,7 +66,8 @@ class CompositeOut(Structure):
 
 
 class CompositeGradsIn(Structure):
-    _fields_ = [("d_spectral", P), ("d_spectral2", P), ("d_rgb", P), ("d_accumulation", P), ("spectral", P)]
+    _fields_ = [("d_spectral", P), ("d_spectral2", P), ("d_rgb", P), ("d_accumulation", P), ("spectral", P),
+                ("trans", P)]
 
 
 class CompositeGradsOut(Structure):

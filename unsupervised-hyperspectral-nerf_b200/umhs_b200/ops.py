@@ -381,16 +381,19 @@ class CompositeFunction(torch.autograd.Function):
                "specular": z(R, B) if specular else None, "abundances": z(R, K), "accumulation": z(R),
                "depth": z(R), "rgb": z(R, 3), "seg_probs": z(R, K), "seg_raw": z(R), "seg_pred": z(R, 3),
                "weights": z(N) if cfg.get("want_weights", False) else None}
+        # per-sample transmittance, kept for the backward (4 B/sample instead of a recomputation pass there)
+        trans = z(N) if any(ctx.needs_input_grad) else None
         tmm = _tminmax_init(dev).clone()  # (+inf, -inf) without a host->device copy per call
         co = _lib.CompositeOut()
         for k, v in out.items():
             setattr(co, k, ptr(v))
+        co.trans = ptr(trans)
         co.t_minmax = ptr(tmm)
         _call("umhs_composite_fwd", R, ctypes.byref(ci), ctypes.byref(co), stream_ptr(dev))
         _call("umhs_depth_clip", 0, ptr(out["depth"]), R, ptr(tmm), stream_ptr(dev))
         ctx.cfg = cfg
         ctx.save_for_backward(packed_info, t0, t1, sigma, scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1,
-                              rgb_matrix, out["spectral"])
+                              rgb_matrix, out["spectral"], trans)
         empty = torch.empty((0,), device=dev)
         res = tuple(out[k] if out[k] is not None else empty for k in COMPOSITE_OUTPUTS)
         ctx.mark_non_differentiable(*[res[i] for i, k in enumerate(COMPOSITE_OUTPUTS)
@@ -401,7 +404,7 @@ class CompositeFunction(torch.autograd.Function):
     def backward(ctx, d_spectral, d_spectral2, d_specular, d_abundances, d_acc, d_depth, d_rgb, *_):
         lib = _lib.load()
         (packed_info, t0, t1, sigma, scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1, rgb_matrix,
-         spectral) = ctx.saved_tensors
+         spectral, trans) = ctx.saved_tensors
         cfg = ctx.cfg
         dev = sigma.device
         R, N, K, B, specular = int(packed_info.shape[0]), int(sigma.shape[0]), cfg["K"], cfg["B"], cfg["specular"]
@@ -412,6 +415,7 @@ class CompositeFunction(torch.autograd.Function):
                                                             d_acc)]
         gi.d_spectral, gi.d_spectral2, gi.d_rgb, gi.d_accumulation = (ptr(k) for k in keep)
         gi.spectral = ptr(spectral)
+        gi.trans = ptr(trans)
         z = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)  # noqa: E731
         d_sigma, d_scalar, d_abund = z(N), z(N, K), z(N, K)
         d_s1 = z(N) if specular else None
