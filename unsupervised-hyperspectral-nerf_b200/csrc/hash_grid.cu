@@ -11,6 +11,11 @@
 // independent float2 gathers; two levels are kept in flight (16 loads per thread).
 // Output enc [n, 2L] fp32 row-major (level-major columns), written as float4 per 2 levels.
 //
+// x-pairs: the hash multiplies x by 1, so for an EVEN floor coordinate fx the floor and ceil corners of a cell edge
+// along x are (fx ^ h) and ((fx + 1) ^ h) = (fx ^ h) ^ 1: the two rows of one 16-byte aligned pair of table rows.
+// Such a sample (half of them at fine levels) gathers its 8 corners with 4 LDG.128 and scatters its gradient with
+// 4 red.global.add.v4.f32 instead of 8 eight-byte accesses.
+//
 // Algorithmic bytes per sample: fwd 8*L*8 gathered + 12 in + 8L out;
 // bwd 8L in + 8*L*8 read-modify-write.
 #include "common.cuh"
@@ -24,7 +29,8 @@ struct Corners {
 
 // Corner order follows the reference: f0=(c,c,c) f1=(c,f,c) f2=(f,f,c) f3=(f,c,c)
 //                                     f4=(c,c,f) f5=(c,f,f) f6=(f,f,f) f7=(f,c,f)
-__device__ __forceinline__ void level_setup(float x, float y, float z, float scale, uint32_t tmask, uint32_t base,
+// returns true when the x-neighbours of this sample form aligned row pairs (see the header): (f3,f0) (f2,f1) (f7,f4) (f6,f5)
+__device__ __forceinline__ bool level_setup(float x, float y, float z, float scale, uint32_t tmask, uint32_t base,
                                             uint32_t (&idx)[8], float &ox, float &oy, float &oz) {
     const float sx = x * scale, sy = y * scale, sz = z * scale;
     const float flx = floorf(sx), fly = floorf(sy), flz = floorf(sz);
@@ -44,6 +50,27 @@ __device__ __forceinline__ void level_setup(float x, float y, float z, float sca
     idx[5] = ((cx ^ hfy ^ hfz) & tmask) + base;
     idx[6] = ((fx ^ hfy ^ hfz) & tmask) + base;
     idx[7] = ((fx ^ hcy ^ hfz) & tmask) + base;
+    return ((fx & 1u) == 0u) && (cx != fx);
+}
+
+// the 8 corner rows of one level: 4 aligned row pairs when `pair`, 8 single rows otherwise
+__device__ __forceinline__ void gather_level(const float2 *__restrict__ table, const uint32_t (&idx)[8], bool pair,
+                                             float2 (&f)[8]) {
+    constexpr int kFloor[4] = {3, 2, 7, 6}, kCeil[4] = {0, 1, 4, 5};
+    if (pair) {
+        const float4 *t4 = reinterpret_cast<const float4 *>(table);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const uint32_t fi = idx[kFloor[p]];
+            const float4 v = __ldg(t4 + (fi >> 1));
+            const bool odd = (fi & 1u) != 0u;  // the floor corner is the second row of the pair
+            f[kFloor[p]] = odd ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+            f[kCeil[p]] = odd ? make_float2(v.x, v.y) : make_float2(v.z, v.w);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) f[c] = __ldg(table + idx[c]);
+    }
 }
 
 __device__ __forceinline__ float2 blend(const float2 (&f)[8], float ox, float oy, float oz) {
@@ -93,7 +120,7 @@ struct SrcX01 {
 
 constexpr int kHashThreads = 256;
 
-template <class Src>
+template <class Src, bool PAIRS>
 __global__ void __launch_bounds__(kHashThreads)
 hash_encode_fwd_kernel(Src src, int64_t n_total, const float2 *__restrict__ table, const float *__restrict__ scalings,
                        int L, int log2T, float *__restrict__ enc) {
@@ -107,13 +134,12 @@ hash_encode_fwd_kernel(Src src, int64_t n_total, const float2 *__restrict__ tabl
     for (; l + 1 < L; l += 2) {
         uint32_t i0[8], i1[8];
         float ox0, oy0, oz0, ox1, oy1, oz1;
-        level_setup(x, y, z, __ldg(scalings + l), tmask, (uint32_t)l << log2T, i0, ox0, oy0, oz0);
-        level_setup(x, y, z, __ldg(scalings + l + 1), tmask, (uint32_t)(l + 1) << log2T, i1, ox1, oy1, oz1);
+        const bool p0 = level_setup(x, y, z, __ldg(scalings + l), tmask, (uint32_t)l << log2T, i0, ox0, oy0, oz0);
+        const bool p1 =
+            level_setup(x, y, z, __ldg(scalings + l + 1), tmask, (uint32_t)(l + 1) << log2T, i1, ox1, oy1, oz1);
         float2 f0[8], f1[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) f0[c] = __ldg(table + i0[c]);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) f1[c] = __ldg(table + i1[c]);
+        gather_level(table, i0, PAIRS && p0, f0);
+        gather_level(table, i1, PAIRS && p1, f1);
         const float2 a = blend(f0, ox0, oy0, oz0);
         const float2 b = blend(f1, ox1, oy1, oz1);
         if ((L & 1) == 0) {
@@ -126,10 +152,9 @@ hash_encode_fwd_kernel(Src src, int64_t n_total, const float2 *__restrict__ tabl
     if (l < L) {
         uint32_t i0[8];
         float ox0, oy0, oz0;
-        level_setup(x, y, z, __ldg(scalings + l), tmask, (uint32_t)l << log2T, i0, ox0, oy0, oz0);
+        const bool p0 = level_setup(x, y, z, __ldg(scalings + l), tmask, (uint32_t)l << log2T, i0, ox0, oy0, oz0);
         float2 f0[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) f0[c] = __ldg(table + i0[c]);
+        gather_level(table, i0, PAIRS && p0, f0);
         *reinterpret_cast<float2 *>(out + 2 * l) = blend(f0, ox0, oy0, oz0);
     }
 }
@@ -162,39 +187,62 @@ __device__ __forceinline__ void scatter_add(float2 *table, uint32_t idx, float2 
     }
 }
 
-template <class Src>
-__global__ void __launch_bounds__(kHashThreads)
+// Scatter kernel: 128-thread CTAs, grid-stride over the samples.
+// Measured and dropped (round 1): scattering chunk i of the samples on a second stream, on a grid capped to 3 CTAs per
+// SM so that it fits beside the persistent tensor-core MLP backward of chunk i+1.  The scatter needs its occupancy
+// (capped to 12 warps per SM it is ~2x slower) and every extra launch of the persistent MLP kernel costs ~0.05 ms:
+// 2 chunks 1.54 -> 1.68 ms per step, 3 chunks 1.77 ms.
+constexpr int kScatterThreads = 128;
+
+template <class Src, bool PAIRS>
+__global__ void __launch_bounds__(kScatterThreads)
 hash_encode_bwd_kernel(Src src, int64_t n_total, const float *__restrict__ scalings, int L, int log2T,
                        const float *__restrict__ d_enc, float2 *__restrict__ d_table, int agg_levels) {
-    const int64_t n = (int64_t)blockIdx.x * kHashThreads + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int64_t n_eff = src.count(n_total);
-    if ((int64_t)blockIdx.x * kHashThreads >= n_eff) return;  // whole CTA beyond the device-side count
-    const bool valid = n < n_eff;
-    float x = 0.f, y = 0.f, z = 0.f;
-    if (valid) src.get(n, x, y, z);
     const uint32_t tmask = (log2T >= 32) ? 0xffffffffu : ((1u << log2T) - 1u);
-    const float *g = d_enc + (valid ? n : 0) * (2 * L);
-    for (int l = 0; l < L; ++l) {
-        uint32_t idx[8];
-        float ox, oy, oz;
-        level_setup(x, y, z, __ldg(scalings + l), tmask, (uint32_t)l << log2T, idx, ox, oy, oz);
-        float2 d = valid ? __ldg(reinterpret_cast<const float2 *>(g + 2 * l)) : make_float2(0.f, 0.f);
-        const float ux = 1.0f - ox, uy = 1.0f - oy, uz = 1.0f - oz;
-        // weight of corner (X,Y,Z): (X==c ? o : 1-o) per axis; cz side carries oz
-        const float wz[2] = {oz, uz};
-        const float wxy[4] = {ox * oy, ox * uy, ux * uy, ux * oy};  // (c,c) (c,f) (f,f) (f,c)
-        if (l < agg_levels) {
+    // CTA-uniform trip count: the warp-aggregated levels shuffle across the whole warp
+    for (int64_t base = (int64_t)blockIdx.x * kScatterThreads; base < n_eff; base += (int64_t)gridDim.x * kScatterThreads) {
+        const int64_t n = base + threadIdx.x;
+        const bool valid = n < n_eff;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (valid) src.get(n, x, y, z);
+        const float *g = d_enc + (valid ? n : 0) * (2 * L);
+        for (int l = 0; l < L; ++l) {
+            uint32_t idx[8];
+            float ox, oy, oz;
+            const bool pair = level_setup(x, y, z, __ldg(scalings + l), tmask, (uint32_t)l << log2T, idx, ox, oy, oz);
+            float2 d = valid ? __ldg(reinterpret_cast<const float2 *>(g + 2 * l)) : make_float2(0.f, 0.f);
+            const float ux = 1.0f - ox, uy = 1.0f - oy, uz = 1.0f - oz;
+            // weight of corner (X,Y,Z): (X==c ? o : 1-o) per axis; cz side carries oz
+            const float wz[2] = {oz, uz};
+            const float wxy[4] = {ox * oy, ox * uy, ux * uy, ux * oy};  // (c,c) (c,f) (f,f) (f,c)
+            if (l < agg_levels) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float w = wxy[c & 3] * wz[c >> 2];
-                scatter_add<true>(d_table, idx[c], make_float2(w * d.x, w * d.y), lane);
-            }
-        } else if (valid) {
+                for (int c = 0; c < 8; ++c) {
+                    const float w = wxy[c & 3] * wz[c >> 2];
+                    scatter_add<true>(d_table, idx[c], make_float2(w * d.x, w * d.y), lane);
+                }
+            } else if (PAIRS && valid && pair) {
+                // fine levels: no two lanes share an entry; aligned x-pairs go out as one 16-byte reduction
+                constexpr int kFloor[4] = {3, 2, 7, 6}, kCeil[4] = {0, 1, 4, 5};
+                float4 *t4 = reinterpret_cast<float4 *>(d_table);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float w = wxy[c & 3] * wz[c >> 2];
-                scatter_add<false>(d_table, idx[c], make_float2(w * d.x, w * d.y), lane);
+                for (int p = 0; p < 4; ++p) {
+                    const int cf = kFloor[p], cc = kCeil[p];
+                    const float wf = wxy[cf & 3] * wz[cf >> 2], wc = wxy[cc & 3] * wz[cc >> 2];
+                    const uint32_t fi = idx[cf];
+                    const bool odd = (fi & 1u) != 0u;
+                    const float wa = odd ? wc : wf, wb = odd ? wf : wc;  // first / second row of the pair
+                    const float4 v = make_float4(wa * d.x, wa * d.y, wb * d.x, wb * d.y);
+                    if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f) atomicAdd(t4 + (fi >> 1), v);
+                }
+            } else if (valid) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float w = wxy[c & 3] * wz[c >> 2];
+                    scatter_add<false>(d_table, idx[c], make_float2(w * d.x, w * d.y), lane);
+                }
             }
         }
     }
@@ -211,6 +259,11 @@ static int check_grid(const umhs_hash_grid *g) {
 // number of leading (coarse) levels whose scatter is warp-aggregated: cell edge >= ~2 sample steps
 static int agg_levels_for(const umhs_hash_grid *g) { return g->num_levels < 10 ? g->num_levels : 10; }
 
+static int scatter_grid(int64_t n, int max_ctas) {
+    const int64_t want = (n + kScatterThreads - 1) / kScatterThreads;
+    return (int)((max_ctas > 0 && want > max_ctas) ? max_ctas : want);
+}
+
 }  // namespace umhs
 
 using namespace umhs;
@@ -224,7 +277,7 @@ extern "C" int umhs_hash_encode_fwd(const umhs_points *pts, int64_t n, const umh
                    "points need positions or the ray form");
     if (n <= 0) return UMHS_OK;
     SrcPoints src{*pts};
-    hash_encode_fwd_kernel<<<div_up(n, kHashThreads), kHashThreads, 0, as_stream(stream)>>>(
+    hash_encode_fwd_kernel<decltype(src), true><<<div_up(n, kHashThreads), kHashThreads, 0, as_stream(stream)>>>(
         src, n, reinterpret_cast<const float2 *>(grid->table), grid->scalings, grid->num_levels,
         grid->log2_table_size, enc);
     UMHS_CHECK_LAUNCH();
@@ -238,7 +291,8 @@ extern "C" int umhs_hash_encode_bwd(const umhs_points *pts, int64_t n, const umh
     UMHS_CHECK_ARG(check_grid(grid) == 0, "bad hash grid");
     if (n <= 0) return UMHS_OK;
     SrcPoints src{*pts};
-    hash_encode_bwd_kernel<<<div_up(n, kHashThreads), kHashThreads, 0, as_stream(stream)>>>(
+    const int max_ctas = 0;
+    hash_encode_bwd_kernel<decltype(src), true><<<scatter_grid(n, max_ctas), kScatterThreads, 0, as_stream(stream)>>>(
         src, n, grid->scalings, grid->num_levels, grid->log2_table_size, d_enc, reinterpret_cast<float2 *>(d_table),
         agg_levels_for(grid));
     UMHS_CHECK_LAUNCH();
@@ -252,7 +306,7 @@ extern "C" int umhs_hash_encode_x01_fwd(const float *x01, int64_t n, const umhs_
     UMHS_CHECK_ARG(check_grid(grid) == 0, "bad hash grid");
     if (n <= 0) return UMHS_OK;
     SrcX01 src{x01};
-    hash_encode_fwd_kernel<<<div_up(n, kHashThreads), kHashThreads, 0, as_stream(stream)>>>(
+    hash_encode_fwd_kernel<decltype(src), true><<<div_up(n, kHashThreads), kHashThreads, 0, as_stream(stream)>>>(
         src, n, reinterpret_cast<const float2 *>(grid->table), grid->scalings, grid->num_levels,
         grid->log2_table_size, enc);
     UMHS_CHECK_LAUNCH();
@@ -266,7 +320,8 @@ extern "C" int umhs_hash_encode_x01_bwd(const float *x01, int64_t n, const umhs_
     UMHS_CHECK_ARG(check_grid(grid) == 0, "bad hash grid");
     if (n <= 0) return UMHS_OK;
     SrcX01 src{x01};
-    hash_encode_bwd_kernel<<<div_up(n, kHashThreads), kHashThreads, 0, as_stream(stream)>>>(
+    const int max_ctas = 0;
+    hash_encode_bwd_kernel<decltype(src), true><<<scatter_grid(n, max_ctas), kScatterThreads, 0, as_stream(stream)>>>(
         src, n, grid->scalings, grid->num_levels, grid->log2_table_size, d_enc, reinterpret_cast<float2 *>(d_table),
         agg_levels_for(grid));
     UMHS_CHECK_LAUNCH();
