@@ -313,6 +313,42 @@ int umhs_occ_binarize(const float *occs, int64_t n_cells, float occ_thre, double
                       float *mean_out /*device scalar or NULL: mean(occs)*/, void *stream);
 
 /* ---------------------------------------------------------------------------------
+ * Training batch from device-resident images -- replaces UMHSDataManager.next_train (ref
+ * umhsnerf/data/umhs_datamanager.py:95-108): nerfstudio PixelSampler (floor(rand * [N,H,W]); {key: value[c,y,x]};
+ * indices[:,0] = image_idx[c]) + RayGenerator / Cameras.generate_rays (perspective, pixel centres, no distortion),
+ * on H x W x B hyperspectral cubes (ref umhsnerf/data/utils/hs_dataloader.py:46-50).  SURVEY 8(f) row 2.
+ * The uniform draws u are an input (the caller owns the random stream).  Any output pointer may be NULL.
+ * ------------------------------------------------------------------------------- */
+#define UMHS_DTYPE_F32 0
+#define UMHS_DTYPE_F16 1
+#define UMHS_DTYPE_BF16 2
+#define UMHS_DTYPE_U8 3
+typedef struct {
+    const float *u;            /* [R,3] uniform draws in [0,1): image slot, row, column */
+    int64_t n_rays;
+    int32_t num_images, height, width;
+    int32_t num_bands, hs_dtype;      /* UMHS_DTYPE_F32 / F16 / BF16 */
+    int32_t image_channels, image_dtype; /* 3 or 4; UMHS_DTYPE_F32 or U8 (u8 -> /255) */
+    const int64_t *image_idx;  /* [num_images] dataset (camera) index of each resident image, or NULL = identity */
+    const void *hs;            /* [num_images,H,W,B] or NULL */
+    const void *image;         /* [num_images,H,W,C] or NULL */
+    const float *c2w;          /* [num_cameras,3,4] camera-to-world, or NULL (no rays) */
+    const float *intrinsics;   /* [num_cameras,4] fx, fy, cx, cy (16-byte aligned) */
+} umhs_batch_in;
+
+typedef struct {
+    int64_t *indices;       /* [R,3] (camera, row, column) */
+    float *hs_image;        /* [R,B] */
+    float *image;           /* [R,C] */
+    float *origins;         /* [R,3] */
+    float *directions;      /* [R,3] unit */
+    float *pixel_area;      /* [R]   */
+    float *directions_norm; /* [R]   */
+} umhs_batch_out;
+
+int umhs_sample_batch(const umhs_batch_in *in, const umhs_batch_out *out, void *stream);
+
+/* ---------------------------------------------------------------------------------
  * Training losses + their gradients in one pass -- replaces UMHSModel.get_loss_dict (ref
  * umhsnerf/umhs_model.py:329-383: 5 * MSE(spectral, hs_image) + w * MSE(rgb blended over a background, image
  * blended over the same background)) and the autograd backward of those ~15 elementwise / reduction launches.

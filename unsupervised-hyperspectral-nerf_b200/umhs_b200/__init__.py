@@ -10,7 +10,8 @@ from .spec_to_rgb import ColourSystem  # noqa: F401
 from .clusterprobe import ClusterLookup  # noqa: F401
 from .occ_grid import OccGridEstimator, VolumetricSampler  # noqa: F401
 from .rays import Frustums, RayBundle, RaySamples  # noqa: F401
+from .umhs_datamanager import UMHSDataManager  # noqa: F401
 
 __all__ = ["UMHSField", "SpectralRenderer", "UMHSRenderer", "get_weights_spectral", "UMHSConfig", "UMHSModel",
            "ColourSystem", "ClusterLookup", "OccGridEstimator", "VolumetricSampler", "Frustums", "RayBundle",
-           "RaySamples"]
+           "RaySamples", "UMHSDataManager"]

@@ -75,6 +75,17 @@ class CompositeGradsOut(Structure):
                 ("d_endmembers", P), ("d_dir_w1", P), ("d_dir_b1", P)]
 
 
+class BatchIn(Structure):
+    _fields_ = [("u", P), ("n_rays", c_int64), ("num_images", c_int32), ("height", c_int32), ("width", c_int32),
+                ("num_bands", c_int32), ("hs_dtype", c_int32), ("image_channels", c_int32), ("image_dtype", c_int32),
+                ("image_idx", P), ("hs", P), ("image", P), ("c2w", P), ("intrinsics", P)]
+
+
+class BatchOut(Structure):
+    _fields_ = [("indices", P), ("hs_image", P), ("image", P), ("origins", P), ("directions", P), ("pixel_area", P),
+                ("directions_norm", P)]
+
+
 class MarchArgs(Structure):
     _fields_ = [("rays_o", P), ("rays_d", P), ("near_planes", P), ("far_planes", P), ("binaries", P), ("aabbs", P),
                 ("levels", c_int32), ("resolution", c_int32), ("step_size", c_float), ("cone_angle", c_float),
@@ -124,6 +135,7 @@ _SIGNATURES = {
                        c_int32, P],
     "umhs_adam_step_dev": [P, P, P, P, c_int64, c_float, c_float, c_float, P, P, P, c_int64, c_int64, c_int32, P],
     "umhs_reduce_slabs": [P, c_int64, c_int64, c_int64, P, P],
+    "umhs_sample_batch": [POINTER(BatchIn), POINTER(BatchOut), P],
     "umhs_train_loss": [c_int64, c_int32, c_int32, P, P, P, P, P, P, c_float, c_float, P, P, P, P, P],
     "umhs_dp_barrier": [P, c_int32, c_int32, c_int32, P, P],
     "umhs_dp_adam_step": [P, P, P, P, c_int64, c_int32, c_int32, c_float, c_float, c_float, P, c_int64, c_int64, P, P,

@@ -25,7 +25,7 @@ EXTRA = {
     "packing.cu": ["-fmad=false"],  # same IEEE op sequence as oracle/pack_oracle.c
 }
 SOURCES = ["api.cu", "hash_grid.cu", "field_mlp.cu", "field_mlp_tc.cu", "composite.cu", "composite_group.cu", "unfused.cu", "packing.cu",
-           "optim.cu", "loss.cu"]
+           "optim.cu", "loss.cu", "batch.cu"]
 
 
 def _sources():

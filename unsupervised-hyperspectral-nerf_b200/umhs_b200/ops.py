@@ -26,7 +26,7 @@ _LAUNCHES = {"umhs_hash_encode_fwd": 1, "umhs_hash_encode_bwd": 1, "umhs_hash_en
              "umhs_march_write": 1, "umhs_visibility_mask": 1, "umhs_compact_samples": 1, "umhs_pack_info": 2,
              "umhs_occ_cell_points": 1, "umhs_occ_ema_update": 2, "umhs_occ_binarize": 2, "umhs_adam_step": 1,
              "umhs_reduce_slabs": 1, "umhs_train_loss": 1, "umhs_dp_barrier": 1, "umhs_dp_adam_step": 1, "umhs_adam_step_dev": 1, "umhs_density_tc_fwd": 1, "umhs_field_mlp_tc_fwd": 1, "umhs_field_mlp_tc_bwd": 1, "umhs_debug_trace": 1,
-             "umhs_tc05_selftest": 1}
+             "umhs_tc05_selftest": 1, "umhs_sample_batch": 1}
 
 # "bf16": tensor-core MLP kernels (tcgen05 + TMEM, bf16 operands, fp32 accumulate) -- the default.
 # "fp32": fp32 SIMT MLP kernels (precise mode for tight parity tests).
