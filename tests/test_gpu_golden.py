@@ -276,3 +276,39 @@ def test_occupancy_grid_update_matches_oracle():
     with mlp_precision("bf16"):
         m.update_occupancy_grid(0)
     assert m.occupancy_grid.binaries.shape == (4, res, res, res)
+
+
+def test_packed_grid_follows_binaries():
+    """The march reads a persistent bit-packed copy of ``binaries`` (OccGridEstimator.packed_grid) that is refreshed
+    when the grid changes -- by an occupancy update (kernel writes through the address), by in-place torch writes
+    (tensor version) and by mark_dirty / load_state_dict -- instead of being rebuilt by every march."""
+    from umhs_b200 import ops
+
+    def fresh(g):
+        bits, any_ = ops.occ_pack_bits(g.binaries)
+        return bits.cpu(), any_.cpu()[: g.binaries.shape[0]]
+
+    def cached(g):
+        bits, any_ = g.packed_grid()
+        return bits.cpu(), any_.cpu()[: g.binaries.shape[0]]
+
+    d, meta = load_golden("model_train_k4.npz")
+    with mlp_precision("fp32"):
+        m = b200_model_from_golden(d, meta, True)
+        g = m.occupancy_grid
+        b0, a0 = cached(g)
+        assert torch.equal(b0, fresh(g)[0]) and torch.equal(a0, fresh(g)[1])
+        # reference check of the packing itself: bit b of word w = cell 32 w + b
+        flat = g.binaries.flatten(1).cpu()
+        w, b = 5, 7
+        assert bool((int(b0[0, w]) >> b) & 1) == bool(flat[0, 32 * w + b])
+        buf = g._bits.data_ptr()
+        m.update_occupancy_grid(16)                       # binaries rewritten by the binarise kernel
+        b1, a1 = cached(g)
+        assert torch.equal(b1, fresh(g)[0]) and torch.equal(a1, fresh(g)[1]) and g._bits.data_ptr() == buf
+        g.binaries.copy_(torch.rand(g.binaries.shape, device=DEV) > 0.7)   # in-place torch write
+        b2, _ = cached(g)
+        assert torch.equal(b2, fresh(g)[0]) and not torch.equal(b2, b1) and g._bits.data_ptr() == buf
+        g.binaries.view(torch.uint8).zero_()
+        g.mark_dirty()
+        assert int(cached(g)[0].abs().sum()) == 0 and int(cached(g)[1].sum()) == 0

@@ -13,6 +13,7 @@
 // batch are independent), one warp per ray for the visibility scan and the compaction, a
 // single-CTA scan for the offsets (R is 1e4..5e5).
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -124,7 +125,7 @@ __device__ __forceinline__ float advance_orbit(float t, float target, float cone
 //    never happens for the empty tail of the ray (most of the oracle's iterations);
 //  * in grid levels that hold no occupied cell (level_any[l] == 0) the DDA still runs (its fp32 thresholds are part
 //    of the orbit bookkeeping) but the occupancy bytes are not fetched.
-template <bool WRITE>
+template <bool WRITE, bool BITS>
 __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *__restrict__ binaries,
                              const uint32_t *__restrict__ bits, const float *__restrict__ aabbs,
                              const int *__restrict__ level_any, int levels, int res,
@@ -222,10 +223,10 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
         }
         const uint8_t *lvl_bin = binaries + (int64_t)level * cells_per_level;
         // bit-packed copy of the level (1 bit per cell, 256 KB at 128^3: L1-resident) when the caller built one
-        const uint32_t *lvl_bits = bits ? bits + (int64_t)level * ((cells_per_level + 31) / 32) : nullptr;
-        auto fetch = [&](int c) -> uint8_t {
-            if (lvl_bits) return (uint8_t)((__ldg(lvl_bits + (c >> 5)) >> (c & 31)) & 1u);
-            return __ldg(lvl_bin + c);
+        const uint32_t *lvl_bits = BITS ? bits + (int64_t)level * ((cells_per_level + 31) / 32) : nullptr;
+        auto fetch = [&](int c) -> uint32_t {
+            if (BITS) return (__ldg(lvl_bits + (c >> 5)) >> (c & 31)) & 1u;
+            return (uint32_t)__ldg(lvl_bin + c);
         };
         // steps each axis may still take before it passes the interval's last cell or leaves the grid
         int left[3];
@@ -237,10 +238,11 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
             left[k] = (to_over >= 1 && to_over < to_edge) ? to_over : to_edge;
         }
         int cell = (cur[0] * res + cur[1]) * res + cur[2];
-        const int stride[3] = {stepi[0] * res * res, stepi[1] * res, stepi[2]};
+        const int s0 = stepi[0] * res * res, s1 = stepi[1] * res, s2 = stepi[2];
+        const float dl0 = delta[0], dl1 = delta[1], dl2 = delta[2];
         float td0 = tdist[0], td1 = tdist[1], td2 = tdist[2];
         int l0 = left[0], l1 = left[1], l2 = left[2];
-        uint8_t occ = lookup ? fetch(cell) : (uint8_t)0;
+        uint32_t occ = lookup ? fetch(cell) : 0u;
         bool last = false;
         int guard = 4 * res + 8;
         // Phase 1 (this loop): the DDA alone, one cell per iteration for every lane of the warp, no inner loops.  Runs
@@ -250,16 +252,24 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
         // threshold.  Every occupied run is RECORDED as (pend before it, Tm); the orbit work happens in phase 2
         // (flush_runs), where the k-th occupied run of every ray of the warp is processed side by side.  With the orbit
         // loops inside the DDA loop the lanes of a warp serialised on each other's runs (ncu: 12 of 32 lanes active).
+        // The step itself is written with selects, not branches: the lanes of a warp pick different axes in almost
+        // every iteration, and a three-way divergent branch made the warp execute all three bodies (ncu: ~85
+        // instructions per iteration, 8 cycles each at one to three warps per scheduler).
         while (!last && guard > 0) {
-            float t_traverse = fminf(td0, fminf(td1, td2));
-            t_traverse = fminf(t_traverse, this_tmax);
+            const float t_traverse = fminf(fminf(td0, fminf(td1, td2)), this_tmax);
             // single DDA step: x if strictly smallest, else y if < z, else z
             const bool ax0 = (td0 < td1) && (td0 < td2);
             const bool ax1 = !ax0 && (td1 < td2);
-            if (ax0)      { td0 += delta[0]; cell += stride[0]; last = (--l0 == 0); }
-            else if (ax1) { td1 += delta[1]; cell += stride[1]; last = (--l1 == 0); }
-            else          { td2 += delta[2]; cell += stride[2]; last = (--l2 == 0); }
-            const uint8_t occ_next = (lookup && !last) ? fetch(cell) : (uint8_t)0;
+            const bool ax2 = !ax0 && !ax1;
+            td0 = ax0 ? td0 + dl0 : td0;
+            td1 = ax1 ? td1 + dl1 : td1;
+            td2 = ax2 ? td2 + dl2 : td2;
+            cell += ax0 ? s0 : (ax1 ? s1 : s2);
+            l0 -= ax0 ? 1 : 0;
+            l1 -= ax1 ? 1 : 0;
+            l2 -= ax2 ? 1 : 0;
+            last = (l0 == 0) | (l1 == 0) | (l2 == 0);  // only the stepped axis can have reached 0 (all start >= 1)
+            const uint32_t occ_next = (lookup && !last) ? fetch(cell) : 0u;
             --guard;
             if (last || guard == 0 || occ_next != occ) {  // the cell just left ends a run
                 if (!occ) {
@@ -278,11 +288,17 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
     return n;
 }
 
-template <bool WRITE>
+// rays_per_warp < 32 leaves the upper lanes of every warp idle ON PURPOSE: the DDA is a long dependent instruction
+// stream with data-dependent trip counts, so a full warp runs at the pace of its slowest ray with ~10 of 32 lanes
+// active, and 16 384 rays are only 3.5 warps per SM.  Narrow warps cost nothing (those lanes were idle) and give
+// the schedulers 4x the warps to interleave, each as long as the slowest of 8 rays instead of 32.
+template <bool WRITE, bool BITS>
 __global__ void __launch_bounds__(128)
 march_kernel(umhs_march_args a, const int *__restrict__ level_any, int64_t *counts, const int64_t *packed_info,
-             int64_t *ray_indices, float *t_starts, float *t_ends) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+             int64_t *ray_indices, float *t_starts, float *t_ends, int rays_per_warp) {
+    const int lane = threadIdx.x & 31;
+    if (lane >= rays_per_warp) return;
+    const int64_t r = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * rays_per_warp + lane;
     if (r >= a.n_rays) return;
     const float o[3] = {__ldg(a.rays_o + 3 * r), __ldg(a.rays_o + 3 * r + 1), __ldg(a.rays_o + 3 * r + 2)};
     const float d[3] = {__ldg(a.rays_d + 3 * r), __ldg(a.rays_d + 3 * r + 1), __ldg(a.rays_d + 3 * r + 2)};
@@ -290,13 +306,13 @@ march_kernel(umhs_march_args a, const int *__restrict__ level_any, int64_t *coun
         // with a staging buffer the count pass also records the first stage_stride interval starts of the ray, and
         // the write pass turns into a coalesced copy (rays longer than the stride are re-marched there)
         float *stage = a.stage ? a.stage + r * a.stage_stride : nullptr;
-        counts[r] = march_ray<false>(o, d, a.binaries, a.occ_bits, a.aabbs, level_any, a.levels, a.resolution, __ldg(a.near_planes + r),
+        counts[r] = march_ray<false, BITS>(o, d, a.binaries, a.occ_bits, a.aabbs, level_any, a.levels, a.resolution, __ldg(a.near_planes + r),
                                      __ldg(a.far_planes + r), a.step_size, a.cone_angle, stage, nullptr,
                                      stage ? a.stage_stride : 0);
     } else {
         const int64_t off = __ldg(packed_info + 2 * r), lim = __ldg(packed_info + 2 * r + 1);
         if (lim <= 0) return;
-        const int64_t n = march_ray<true>(o, d, a.binaries, a.occ_bits, a.aabbs, level_any, a.levels, a.resolution, __ldg(a.near_planes + r),
+        const int64_t n = march_ray<true, BITS>(o, d, a.binaries, a.occ_bits, a.aabbs, level_any, a.levels, a.resolution, __ldg(a.near_planes + r),
                                           __ldg(a.far_planes + r), a.step_size, a.cone_angle, t_starts + off,
                                           t_ends + off, lim);
         for (int64_t i = 0; i < n; ++i) ray_indices[off + i] = r;
@@ -306,6 +322,7 @@ march_kernel(umhs_march_args a, const int *__restrict__ level_any, int64_t *coun
 // Write pass from the staging buffer: one warp per ray copies the staged interval starts to the packed arrays
 // (t_end = t_start + calc_dt(t_start): the same fp32 expression the march evaluates).  Rays with more samples
 // than the staging stride are re-marched by lane 0.
+template <bool BITS>
 __global__ void __launch_bounds__(256)
 march_write_staged_kernel(umhs_march_args a, const int *__restrict__ level_any, const int64_t *__restrict__ counts,
                           const int64_t *__restrict__ packed_info, int64_t *__restrict__ ray_indices,
@@ -329,7 +346,7 @@ march_write_staged_kernel(umhs_march_args a, const int *__restrict__ level_any, 
         if (lane == 0) {
             const float o[3] = {__ldg(a.rays_o + 3 * r), __ldg(a.rays_o + 3 * r + 1), __ldg(a.rays_o + 3 * r + 2)};
             const float d[3] = {__ldg(a.rays_d + 3 * r), __ldg(a.rays_d + 3 * r + 1), __ldg(a.rays_d + 3 * r + 2)};
-            march_ray<true>(o, d, a.binaries, a.occ_bits, a.aabbs, level_any, a.levels, a.resolution, __ldg(a.near_planes + r),
+            march_ray<true, BITS>(o, d, a.binaries, a.occ_bits, a.aabbs, level_any, a.levels, a.resolution, __ldg(a.near_planes + r),
                             __ldg(a.far_planes + r), a.step_size, a.cone_angle, t_starts + off, t_ends + off, lim);
         }
         for (int64_t i = lane; i < lim; i += 32) ray_indices[off + i] = r;
@@ -567,6 +584,13 @@ __global__ void occ_binarize_kernel(const float *__restrict__ occs, int64_t n, f
     if (i < n) binaries[i] = occs[i] > thre ? 1 : 0;
 }
 
+// rays per warp of the march kernels (see march_kernel); UMHS_MARCH_RPW overrides it for A/B timing
+static int march_rays_per_warp(int64_t n_rays) {
+    int rpw = n_rays >= 131072 ? 32 : (n_rays >= 65536 ? 16 : 8);  // measured: 16 k rays 0.158 / 0.147 / 0.139 ms at
+    if (const char *e = getenv("UMHS_MARCH_RPW")) rpw = atoi(e);   // 32 / 16 / 8; 480 k rays (eval) fastest at 32
+    return rpw < 1 ? 1 : (rpw > 32 ? 32 : rpw);
+}
+
 static int check_march(const umhs_march_args *a) {
     if (!a || !a->rays_o || !a->rays_d || !a->near_planes || !a->far_planes || !a->binaries || !a->aabbs) return -1;
     if (a->levels < 1 || a->levels > kMaxGridLevels || a->resolution < 1 || a->resolution > 1024) return -1;
@@ -587,7 +611,10 @@ extern "C" int umhs_march_level_any(const umhs_march_args *a, int32_t *level_any
 }
 
 extern "C" int umhs_occ_pack_bits(const umhs_march_args *a, uint32_t *bits, int32_t *level_any, void *stream) {
-    UMHS_CHECK_ARG(check_march(a) == 0 && bits && level_any, "bad march arguments");
+    // only the grid fields of the march arguments are read (a trainer repacks after an occupancy update, without rays)
+    UMHS_CHECK_ARG(a && a->binaries && a->levels >= 1 && a->levels <= kMaxGridLevels && a->resolution >= 1 &&
+                       a->resolution <= 1024 && bits && level_any,
+                   "bad grid arguments");
     const int64_t cells = (int64_t)a->resolution * a->resolution * a->resolution;
     UMHS_CHECK_CUDA(cudaMemsetAsync(level_any, 0, sizeof(int32_t) * 8, as_stream(stream)));
     occ_pack_bits_kernel<<<dim3(div_up((cells + 31) / 32, 256), a->levels), 256, 0, as_stream(stream)>>>(
@@ -601,8 +628,14 @@ extern "C" int umhs_march_count(const umhs_march_args *a, int64_t *counts, void 
     if (a->n_rays <= 0) return UMHS_OK;
     // The trainer runs this kernel beside the hash scatter and the optimiser of the previous step (kernels without
     // shared memory, like this one: all of the SM's 256 KB stays L1 and the bit-packed level-0 grid stays resident).
-    march_kernel<false><<<div_up(a->n_rays, 64), 64, 0, as_stream(stream)>>>(*a, a->level_any, counts, nullptr, nullptr,
-                                                                             nullptr, nullptr);
+    const int rpw = march_rays_per_warp(a->n_rays);
+    const dim3 grid(div_up(div_up(a->n_rays, rpw), 2));
+    if (a->occ_bits)
+        march_kernel<false, true><<<grid, 64, 0, as_stream(stream)>>>(*a, a->level_any, counts, nullptr, nullptr,
+                                                                      nullptr, nullptr, rpw);
+    else
+        march_kernel<false, false><<<grid, 64, 0, as_stream(stream)>>>(*a, a->level_any, counts, nullptr, nullptr,
+                                                                       nullptr, nullptr, rpw);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }
@@ -621,13 +654,23 @@ extern "C" int umhs_march_write(const umhs_march_args *a, const int64_t *packed_
     UMHS_CHECK_ARG(check_march(a) == 0 && packed_info && ray_indices && t_starts && t_ends, "bad march arguments");
     if (a->n_rays <= 0) return UMHS_OK;
     if (a->stage != nullptr && a->stage_stride > 0 && a->stage_counts != nullptr) {
-        march_write_staged_kernel<<<div_up(a->n_rays, 8), 256, 0, as_stream(stream)>>>(
-            *a, a->level_any, a->stage_counts, packed_info, ray_indices, t_starts, t_ends);
+        if (a->occ_bits)
+            march_write_staged_kernel<true><<<div_up(a->n_rays, 8), 256, 0, as_stream(stream)>>>(
+                *a, a->level_any, a->stage_counts, packed_info, ray_indices, t_starts, t_ends);
+        else
+            march_write_staged_kernel<false><<<div_up(a->n_rays, 8), 256, 0, as_stream(stream)>>>(
+                *a, a->level_any, a->stage_counts, packed_info, ray_indices, t_starts, t_ends);
         UMHS_CHECK_LAUNCH();
         return UMHS_OK;
     }
-    march_kernel<true><<<div_up(a->n_rays, 64), 64, 0, as_stream(stream)>>>(*a, a->level_any, nullptr, packed_info,
-                                                                            ray_indices, t_starts, t_ends);
+    const int rpw = march_rays_per_warp(a->n_rays);
+    const dim3 grid(div_up(div_up(a->n_rays, rpw), 2));
+    if (a->occ_bits)
+        march_kernel<true, true><<<grid, 64, 0, as_stream(stream)>>>(*a, a->level_any, nullptr, packed_info,
+                                                                     ray_indices, t_starts, t_ends, rpw);
+    else
+        march_kernel<true, false><<<grid, 64, 0, as_stream(stream)>>>(*a, a->level_any, nullptr, packed_info,
+                                                                      ray_indices, t_starts, t_ends, rpw);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }

@@ -32,14 +32,38 @@ class OccGridEstimator(nn.Module):
         self.register_buffer("binaries", torch.zeros((levels, res, res, res), dtype=torch.bool))
         self._res = res
         self._occ_mean: Optional[Tensor] = None  # device scalar cache of occs.mean()
+        # bit-packed copy of ``binaries`` + per-level "any occupied" flags for the march kernels: persistent buffers,
+        # refreshed when the grid changes (every 16 steps) instead of once per march
+        self._bits: Optional[Tensor] = None
+        self._level_any: Optional[Tensor] = None
+        self._bits_key = None
 
     def mark_dirty(self) -> None:
-        """Call after writing ``occs`` by hand (tests, checkpoint surgery)."""
+        """Call after writing ``occs`` / ``binaries`` by hand (tests, checkpoint surgery)."""
         self._occ_mean = None
+        self._bits_key = None
 
     def _load_from_state_dict(self, *a, **k):
         self._occ_mean = None
+        self._bits_key = None
         return super()._load_from_state_dict(*a, **k)
+
+    def _repack(self) -> None:
+        b = self.binaries
+        if self._bits is None or self._bits.device != b.device:
+            self._bits = self._level_any = None
+        self._bits, self._level_any = ops.occ_pack_bits(b, self._bits, self._level_any)
+        self._bits_key = (b.data_ptr(), b._version)
+
+    def packed_grid(self):
+        """(bits, level_any) of the current ``binaries``.  In-place torch writes are seen through the tensor version;
+        kernels that write ``binaries`` through its address (the occupancy update) repack explicitly."""
+        b = self.binaries
+        if not b.is_cuda:
+            return None
+        if self._bits_key != (b.data_ptr(), b._version):
+            self._repack()
+        return self._bits, self._level_any
 
     def occ_mean(self) -> Tensor:
         if self._occ_mean is None or self._occ_mean.device != self.occs.device:
@@ -83,7 +107,7 @@ class OccGridEstimator(nn.Module):
                 jitter = torch.rand_like(near)
             near = near + jitter * render_step_size
         return ops.march(rays_o, rays_d, near, far, self.binaries, self.aabbs, render_step_size, cone_angle,
-                         capacity=capacity)
+                         capacity=capacity, packed_grid=self.packed_grid())
 
     def _filter(self, ri, t0, t1, packed, total, sigma_fn, early_stop_eps, alpha_thre, return_packed_info, capacity):
         march_total = total
@@ -177,6 +201,8 @@ class OccGridEstimator(nn.Module):
                   ptr(mean), st)
         if not freeze_binaries:
             self._occ_mean = mean
+        if self._bits is not None:  # binaries were (re)written through their address: refresh the packed copy
+            self._repack()
 
 
 def _occupied_cells(flat: Tensor) -> Tensor:

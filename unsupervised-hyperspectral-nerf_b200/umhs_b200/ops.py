@@ -547,8 +547,25 @@ MARCH_STAGE = 192  # staged interval starts per ray (0 disables staging: the wri
 MARCH_BITS = True   # march on a bit-packed copy of the occupancy grid (identical results)
 
 
+def occ_pack_bits(binaries: Tensor, bits: Optional[Tensor] = None, level_any: Optional[Tensor] = None):
+    """Bit-packed copy of ``binaries`` [levels, res, res, res] (bit b of word w = cell 32 w + b) and the per-level
+    "any occupied" flags, in one pass.  Writes into ``bits`` / ``level_any`` when given (persistent buffers)."""
+    dev = binaries.device
+    bn = binaries.contiguous().view(torch.uint8) if binaries.dtype == torch.bool else binaries.contiguous()
+    a = _lib.MarchArgs()
+    a.binaries, a.levels, a.resolution = ptr(bn), int(bn.shape[0]), int(bn.shape[1])
+    words = (a.resolution ** 3 + 31) // 32
+    if bits is None:
+        bits = torch.empty((a.levels, words), dtype=torch.int32, device=dev)
+    if level_any is None:
+        level_any = torch.empty((8,), dtype=torch.int32, device=dev)
+    _call("umhs_occ_pack_bits", 0, ctypes.byref(a), ptr(bits), ptr(level_any), stream_ptr(dev))
+    return bits, level_any
+
+
 def march(rays_o: Tensor, rays_d: Tensor, near_planes: Tensor, far_planes: Tensor, binaries: Tensor, aabbs: Tensor,
-          step_size: float, cone_angle: float, capacity: Optional[int] = None):
+          step_size: float, cone_angle: float, capacity: Optional[int] = None,
+          packed_grid: Optional[Tuple[Tensor, Tensor]] = None):
     """Occupancy-grid ray marching (nerfacc traverse_grids).  -> (ray_indices, t_starts, t_ends, packed_info, total).
 
     capacity=None: exact-sized outputs, one host sync on the sample count (as the reference does).
@@ -568,15 +585,20 @@ def march(rays_o: Tensor, rays_d: Tensor, near_planes: Tensor, far_planes: Tenso
     packed = torch.empty((R, 2), dtype=torch.int64, device=dev)
     total = torch.zeros((2,), dtype=torch.int64, device=dev)
     st = stream_ptr(dev)
-    level_any = torch.empty((8,), dtype=torch.int32, device=dev)
     a.level_any = a.occ_bits = None
-    if MARCH_BITS:
+    if packed_grid is not None and MARCH_BITS:
+        # the grid owner keeps the bit-packed copy up to date (OccGridEstimator.packed_grid): nothing to pack here
+        bits, level_any = packed_grid
+        a.occ_bits = ptr(bits)
+    elif MARCH_BITS:
+        level_any = torch.empty((8,), dtype=torch.int32, device=dev)
         # one pass over binaries: per-level "any occupied" flags + a bit-packed copy whose lookups hit L1
         words = (a.resolution ** 3 + 31) // 32
         bits = torch.empty((a.levels, words), dtype=torch.int32, device=dev)
         _call("umhs_occ_pack_bits", 0, ctypes.byref(a), ptr(bits), ptr(level_any), st)
         a.occ_bits = ptr(bits)
     else:
+        level_any = torch.empty((8,), dtype=torch.int32, device=dev)
         _call("umhs_march_level_any", 0, ctypes.byref(a), ptr(level_any), st)
     a.level_any = ptr(level_any)
     # the count pass stages each ray's first MARCH_STAGE interval starts; the write pass copies them
