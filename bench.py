@@ -357,17 +357,17 @@ def run_b200(args):
         while len(st["tokens"]) < 2:
             st["tokens"].append(stage_e2e(i + len(st["tokens"])))
         out = trainer.train_step(st["tokens"][0], next_rays=st["tokens"][1] if PIPE else None)
-        loss = out["loss"].clone()  # the graph's output tensor is overwritten by the next replay
+        loss = trainer.read_async(out["loss"])  # device -> host copy of this step's result, on a side stream
         st["tokens"].pop(0)
         st["tokens"].append(stage_e2e(i + 2))
         if st["prev_loss"] is not None:
-            st["losses"].append(float(st["prev_loss"].item()))  # device -> host read of a step's result
+            st["losses"].append(st["prev_loss"].result())  # the host reads step i-1's loss while step i runs
         st["prev_loss"] = loss
 
     def finish_e2e():
         st = e2e_state
         if st["prev_loss"] is not None:
-            st["losses"].append(float(st["prev_loss"].item()))
+            st["losses"].append(st["prev_loss"].result())
             st["prev_loss"] = None
         st["tokens"].clear()
 
@@ -437,9 +437,13 @@ def run_b200(args):
         res = trainer.render_tiles(cam)
     barrier()
     ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    N_EVAL_IMAGES = 8
+    eval_clocks = ClockSampler(local, period_s=0.005)
+    if rank == 0:
+        eval_clocks.start()
     ea.record()
     n_eval = 0
-    for _ in range(3):
+    for _ in range(N_EVAL_IMAGES):
         t_it = time.perf_counter()
         res = None  # release the previous image first
         res = trainer.render_tiles(cam)
@@ -450,7 +454,8 @@ def run_b200(args):
                   f"{model.config.eval_tile_rays}", file=sys.stderr)
     eb.record()
     barrier()
-    eval_ms = torch.tensor([ea.elapsed_time(eb) / 3], device=dev)
+    eval_clk = eval_clocks.stop() if rank == 0 else None
+    eval_ms = torch.tensor([ea.elapsed_time(eb) / N_EVAL_IMAGES], device=dev)
     eval_samples = n_eval.to(torch.float32).reshape(1).clone()
     if world > 1:
         dist.all_reduce(eval_ms, op=dist.ReduceOp.MAX)
@@ -513,7 +518,9 @@ def run_b200(args):
                            "image": f"{W_EVAL}x{H_EVAL}", "ms_per_image": float(eval_ms.item()),
                            "samples_per_image": float(eval_samples.item()),
                            "rays_per_s": H_EVAL * W_EVAL / (float(eval_ms.item()) * 1e-3),
-                           "sharding": "32x32 tiles round-robin over ranks, no collective; one fused pass per rank"},
+                           "sharding": "32x32 tiles round-robin over ranks, no collective; one fused pass per rank",
+                           "images_timed": N_EVAL_IMAGES,
+                           "clocks": {k: eval_clk[k] for k in ("sm_mhz", "reasons", "samples")} if eval_clk else None},
                 "next_train": {**next_train, "frac": next_train["achieved_gbs"] / hbm_peak, "peak": hbm_peak},
                 "kernels": kernels}
         print(json.dumps(line), flush=True)

@@ -286,7 +286,8 @@ class FieldFunction(torch.autograd.Function):
         weights = {n: (w.detach() if w is not None else None) for n, w in zip(MLP_NAMES, mlp)}
         # kept samples are a subset of the sampler's candidates: reuse their encodings when the sampler kept them
         enc = pts.enc_src if pts.enc_src is not None else hash_encode_fwd(pts, table.detach(), scalings, cfg["log2_T"])
-        out = field_mlp_fwd(pts, enc, weights, cfg["K"], cfg["specular"], cfg["temperature"])
+        out = field_mlp_fwd(pts, enc, weights, cfg["K"], cfg["specular"], cfg["temperature"],
+                            want_embedding=cfg.get("want_embedding", True))
         ctx.pts, ctx.cfg = pts, cfg
         ctx.n_mlp = len(mlp)
         ctx.param_refs = (table, mlp)  # the Parameter objects themselves (for direct gradient accumulation)
@@ -295,7 +296,8 @@ class FieldFunction(torch.autograd.Function):
         empty = torch.empty((0,), device=enc.device)
         s1 = out["s1"] if out["s1"] is not None else empty
         sh = out["spec_hidden"] if out["spec_hidden"] is not None else empty
-        return out["sigma"], out["embedding"], out["scalar"], out["abund"], s1, sh
+        emb = out["embedding"] if out["embedding"] is not None else empty
+        return out["sigma"], emb, out["scalar"], out["abund"], s1, sh
 
     @staticmethod
     def backward(ctx, d_sigma, d_emb, d_scalar, d_abund, d_s1, d_sh):
@@ -308,7 +310,7 @@ class FieldFunction(torch.autograd.Function):
         def c(g, shape):
             return torch.zeros(shape, dtype=torch.float32, device=dev) if g is None else f32(g)
 
-        grads = {"d_sigma": c(d_sigma, (n,)), "d_embedding": None if d_emb is None else f32(d_emb),
+        grads = {"d_sigma": c(d_sigma, (n,)), "d_embedding": None if (d_emb is None or d_emb.numel() == 0) else f32(d_emb),
                  "d_scalar": c(d_scalar, (n, K)), "d_abund": c(d_abund, (n, K))}
         if cfg["specular"]:
             grads["d_s1"] = c(d_s1, (n,))

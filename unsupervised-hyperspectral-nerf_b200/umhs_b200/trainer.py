@@ -218,6 +218,36 @@ class UMHSTrainer:
         b = self._stage_bufs[slot]
         return slot, RayBundle(b["origins"], b["directions"]), {"image": b["image"], "hs_image": b["hs_image"]}
 
+    # ------------------------------------------------------------------ result read-back (device -> host)
+    def read_async(self, value: Tensor):
+        """Start the device->host copy of a step result (e.g. ``train_step(...)["loss"]``) and return a handle whose
+        ``.result()`` gives the float.  ``float(value)`` / ``.item()`` would queue the copy on the compute stream
+        BEHIND whatever step the host has already enqueued and block until that later step is done; the copy issued
+        here runs on a side stream as soon as the step that produced ``value`` has finished, so the host can stay a
+        step ahead of the GPU."""
+        dev = self.flat.data.device
+        if getattr(self, "_rb_stream", None) is None:
+            self._rb_stream = torch.cuda.Stream(device=dev)
+            self._rb_host = torch.zeros((64,), dtype=torch.float32).pin_memory()
+            self._rb_slot = 0
+        snap = value.detach().reshape(-1)[:1].to(torch.float32).clone()  # graph outputs are overwritten by the next replay
+        slot = self._rb_slot
+        self._rb_slot = (slot + 1) % self._rb_host.shape[0]
+        self._rb_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._rb_stream):
+            self._rb_host[slot:slot + 1].copy_(snap, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._rb_stream)
+        snap.record_stream(self._rb_stream)
+        host = self._rb_host
+
+        class _Handle:
+            def result(self_inner) -> float:
+                done.synchronize()
+                return float(host[slot])
+
+        return _Handle()
+
     def _set_hyper(self) -> None:
         """lr and Adam bias corrections of this step -> device (pinned staging buffer, async copy on the stream)."""
         t = self.opt_steps

@@ -173,10 +173,14 @@ class UMHSField(nn.Module):
         return PointSet.from_positions(pos, d, contraction=self.contraction, aabb=self._aabb6())
 
     # ------------------------------------------------------------------ fused path used by UMHSModel
-    def forward_packed(self, pts: PointSet) -> Dict[str, Tensor]:
-        """sigma [N], embedding [N,15], scalar [N,K], abund [N,K], (s1 [N], spec_hidden [N,16]) with autograd."""
+    def forward_packed(self, pts: PointSet, want_embedding: bool = True) -> Dict[str, Tensor]:
+        """sigma [N], embedding [N,15], scalar [N,K], abund [N,K], (s1 [N], spec_hidden [N,16]) with autograd.
+        want_embedding=False (the model's fused path: both heads run inside the kernel and nothing downstream reads
+        the geometry features) skips the 60 B/sample embedding output."""
         enc = self.mlp_base.encoder
-        sigma, emb, scalar, abund, s1, sh = ops.FieldFunction.apply(pts, self._cfg(), enc.hash_table, enc.scalings,
+        cfg = self._cfg()
+        cfg["want_embedding"] = want_embedding
+        sigma, emb, scalar, abund, s1, sh = ops.FieldFunction.apply(pts, cfg, enc.hash_table, enc.scalings,
                                                                     *self._mlp_tensors())
         out = {"sigma": sigma, "embedding": emb, "scalar": scalar, "abund": abund}
         if self.pred_specular:

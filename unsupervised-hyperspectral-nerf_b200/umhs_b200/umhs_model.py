@@ -171,7 +171,7 @@ class UMHSModel(nn.Module):
             render_step_size=cfg.render_step_size, alpha_thre=cfg.alpha_thre, cone_angle=cfg.cone_angle,
             jitter=jitter, capacity=self.sample_capacity if self.training else None,  # eval: exact-sized packing
             premarched=premarched)
-        fo = self.field.forward_packed(pts)
+        fo = self.field.forward_packed(pts, want_embedding=False)
         K, B, spec = self.field.num_classes, self.field.wavelengths, cfg.pred_specular
         d = self.field.mlp_directional.layers
         ccfg = {"K": K, "B": B, "specular": spec, "grad_scaling": cfg.use_gradient_scaling, "want_weights": True}
