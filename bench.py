@@ -43,9 +43,9 @@ CPU_SAMPLE_RAYS = 1024
 CONDITIONING_STEPS = 34
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
 # (profiles/r1_ncu_full_summary.md, N = 825k samples, R = 16384 rays); None = not captured
-NCU_TRAFFIC = {"umhs_hash_encode_fwd": 201.2e6, "umhs_hash_encode_bwd": 150.4e6, "umhs_composite_fwd": 36.5e6,
-               "umhs_composite_bwd": 55.1e6, "umhs_adam_step": 482.7e6, "umhs_adam_step_dev": 482.7e6,
-               "umhs_field_mlp_tc_bwd": 280.9e6, "umhs_field_mlp_tc_fwd": 166.6e6, "umhs_density_tc_fwd": 125.4e6,
+NCU_TRAFFIC = {"umhs_hash_encode_fwd": 120.8e6, "umhs_hash_encode_bwd": 150.6e6, "umhs_composite_fwd": 36.8e6,
+               "umhs_composite_bwd": 60.6e6, "umhs_adam_step": 283.1e6, "umhs_adam_step_dev": 283.1e6,
+               "umhs_field_mlp_tc_bwd": 225.1e6, "umhs_field_mlp_tc_fwd": 142.3e6, "umhs_density_tc_fwd": 126.4e6,
                "umhs_train_loss": 17.5e6}
 
 
