@@ -224,10 +224,6 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
         const uint8_t *lvl_bin = binaries + (int64_t)level * cells_per_level;
         // bit-packed copy of the level (1 bit per cell, 256 KB at 128^3: L1-resident) when the caller built one
         const uint32_t *lvl_bits = BITS ? bits + (int64_t)level * ((cells_per_level + 31) / 32) : nullptr;
-        auto fetch = [&](int c) -> uint32_t {
-            if (BITS) return (__ldg(lvl_bits + (c >> 5)) >> (c & 31)) & 1u;
-            return (uint32_t)__ldg(lvl_bin + c);
-        };
         // steps each axis may still take before it passes the interval's last cell or leaves the grid
         int left[3];
         for (int k = 0; k < 3; ++k) {
@@ -242,7 +238,16 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
         const float dl0 = delta[0], dl1 = delta[1], dl2 = delta[2];
         float td0 = tdist[0], td1 = tdist[1], td2 = tdist[2];
         int l0 = left[0], l1 = left[1], l2 = left[2];
-        uint32_t occ = lookup ? fetch(cell) : 0u;
+        // raw occupancy word of a cell + the bit to extract from it (bytes: shift 0): the extraction happens where the
+        // value is consumed, one iteration after the load was issued
+        auto fetch_raw = [&](int c, int &sh) -> uint32_t {
+            if (BITS) { sh = c & 31; return __ldg(lvl_bits + (c >> 5)); }
+            sh = 0;
+            return (uint32_t)__ldg(lvl_bin + c);
+        };
+        int sh0 = 0;
+        const uint32_t w0 = lookup ? fetch_raw(cell, sh0) : 0u;
+        uint32_t occ = BITS ? ((w0 >> sh0) & 1u) : w0;
         bool last = false;
         int guard = 4 * res + 8;
         // Phase 1 (this loop): the DDA alone, one cell per iteration for every lane of the warp, no inner loops.  Runs
@@ -255,33 +260,57 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
         // The step itself is written with selects, not branches: the lanes of a warp pick different axes in almost
         // every iteration, and a three-way divergent branch made the warp execute all three bodies (ncu: ~85
         // instructions per iteration, 8 cycles each at one to three warps per scheduler).
-        while (!last && guard > 0) {
-            const float t_traverse = fminf(fminf(td0, fminf(td1, td2)), this_tmax);
-            // single DDA step: x if strictly smallest, else y if < z, else z
-            const bool ax0 = (td0 < td1) && (td0 < td2);
-            const bool ax1 = !ax0 && (td1 < td2);
-            const bool ax2 = !ax0 && !ax1;
-            td0 = ax0 ? td0 + dl0 : td0;
-            td1 = ax1 ? td1 + dl1 : td1;
-            td2 = ax2 ? td2 + dl2 : td2;
-            cell += ax0 ? s0 : (ax1 ? s1 : s2);
-            l0 -= ax0 ? 1 : 0;
-            l1 -= ax1 ? 1 : 0;
-            l2 -= ax2 ? 1 : 0;
-            last = (l0 == 0) | (l1 == 0) | (l2 == 0);  // only the stepped axis can have reached 0 (all start >= 1)
-            const uint32_t occ_next = (lookup && !last) ? fetch(cell) : 0u;
-            --guard;
-            if (last || guard == 0 || occ_next != occ) {  // the cell just left ends a run
-                if (!occ) {
-                    pend = t_traverse;  // monotone: later thresholds dominate earlier ones
-                } else {
-                    rec_pend[n_rec] = pend;
-                    rec_end[n_rec] = t_traverse;
-                    pend = -1.0f;
-                    if (++n_rec == kRunCap && flush_runs()) return n;
-                }
+        // The loop is software-pipelined one deep: iteration i steps to cell i+1 and ISSUES its occupancy load, and
+        // only then does the run bookkeeping of step i-1 with the word loaded an iteration earlier (ncu: 23 % of the
+        // warp samples waited on that load when it was consumed in the iteration that issued it).
+        bool have = false, end_prev = false;
+        float t_prev = 0.0f;
+        uint32_t word_prev = 0u;
+        int sh_prev = 0;
+        for (;;) {
+            bool stepped = false, end = false;
+            float t_traverse = 0.0f;
+            uint32_t word = 0u;
+            int sh = 0;
+            if (!last && guard > 0) {
+                t_traverse = fminf(fminf(td0, fminf(td1, td2)), this_tmax);
+                // single DDA step: x if strictly smallest, else y if < z, else z
+                const bool ax0 = (td0 < td1) && (td0 < td2);
+                const bool ax1 = !ax0 && (td1 < td2);
+                const bool ax2 = !ax0 && !ax1;
+                td0 = ax0 ? td0 + dl0 : td0;
+                td1 = ax1 ? td1 + dl1 : td1;
+                td2 = ax2 ? td2 + dl2 : td2;
+                cell += ax0 ? s0 : (ax1 ? s1 : s2);
+                l0 -= ax0 ? 1 : 0;
+                l1 -= ax1 ? 1 : 0;
+                l2 -= ax2 ? 1 : 0;
+                last = (l0 == 0) | (l1 == 0) | (l2 == 0);  // only the stepped axis can have reached 0 (all start >= 1)
+                if (lookup && !last) word = fetch_raw(cell, sh);
+                --guard;
+                end = last || guard == 0;
+                stepped = true;
             }
-            occ = occ_next;
+            if (have) {  // bookkeeping of the previous step: the cell it left ends a run?
+                const uint32_t occ_next = BITS ? ((word_prev >> sh_prev) & 1u) : word_prev;
+                if (end_prev || occ_next != occ) {
+                    if (!occ) {
+                        pend = t_prev;  // monotone: later thresholds dominate earlier ones
+                    } else {
+                        rec_pend[n_rec] = pend;
+                        rec_end[n_rec] = t_prev;
+                        pend = -1.0f;
+                        if (++n_rec == kRunCap && flush_runs()) return n;
+                    }
+                }
+                occ = occ_next;
+            }
+            if (!stepped) break;
+            have = true;
+            t_prev = t_traverse;
+            end_prev = end;
+            word_prev = word;
+            sh_prev = sh;
         }
     }
     if (flush_runs()) return n;
