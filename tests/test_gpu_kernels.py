@@ -162,6 +162,34 @@ def test_visibility_compaction_matches_boolean_mask():
             assert abs(ri2.numel() - int(mask.sum())) <= int((~safe).sum())
 
 
+@pytest.mark.parametrize("n,capacity", [(1, 0), (31, 0), (1000, 0), (16384, 0), (16385, 0), (50001, 0),
+                                        (480000, 0), (20000, 300000), (16384, 1)])
+def test_pack_scan_sizes(n, capacity):
+    """umhs_pack_scan: packed_info[r] = (exclusive offset, count), totals, capacity truncation -- against cumsum, at
+    sizes around the 16 384-element tile and the 480 k rays of an eval image."""
+    import ctypes  # noqa: F401
+
+    ops = _ops()
+    from umhs_b200._lib import ptr, stream_ptr
+
+    g = torch.Generator().manual_seed(n)
+    counts = torch.randint(0, 90, (n,), generator=g, dtype=torch.int64)
+    counts[0] = 0
+    c = counts.to(DEV)
+    packed = torch.full((n, 2), -7, dtype=torch.int64, device=DEV)
+    total = torch.zeros((2,), dtype=torch.int64, device=DEV)
+    ops._call("umhs_pack_scan", n, ptr(c), n, ptr(packed), ptr(total), int(capacity), stream_ptr(c.device))
+    excl = torch.cumsum(counts, 0) - counts
+    if capacity > 0:
+        start = torch.clamp(excl, max=capacity)
+        cnt = torch.where(excl + counts <= capacity, counts, capacity - start)
+        want_total = [min(int(counts.sum()), capacity), int(counts.sum())]
+    else:
+        start, cnt, want_total = excl, counts, [int(counts.sum())] * 2
+    assert np.array_equal(packed.cpu().numpy(), torch.stack([start, cnt], -1).numpy())
+    assert total.cpu().tolist() == want_total
+
+
 # ------------------------------------------------------------------ compositing x unmixing
 def _packed_case(R, K, B, specular, seed, smax=70):
     g = torch.Generator().manual_seed(seed)

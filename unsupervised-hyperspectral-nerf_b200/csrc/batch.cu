@@ -71,7 +71,7 @@ __device__ __forceinline__ int draw_index(float u, int bound) {
 }
 
 template <int DT>
-__global__ void __launch_bounds__(kBatchThreads)
+__global__ void __launch_bounds__(kBatchThreads, 6)
 sample_batch_kernel(umhs_batch_in in, umhs_batch_out out, int vec) {
     using T = typename HsElem<DT>::type;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,7 +157,7 @@ extern "C" int umhs_sample_batch(const umhs_batch_in *in, const umhs_batch_out *
                    "image must be fp32 or uint8");
     UMHS_CHECK_ARG(in->c2w == nullptr || in->intrinsics != nullptr, "cameras need intrinsics");
     const int64_t want = (in->n_rays + kBatchWarps - 1) / kBatchWarps;
-    const int64_t cap = (int64_t)kNumSMs * 8;
+    const int64_t cap = (int64_t)kNumSMs * 6;  // 40 registers: 6 CTAs of 8 warps per SM
     const int grid = (int)(want < cap ? want : cap);
     const uintptr_t a_in = reinterpret_cast<uintptr_t>(in->hs), a_out = reinterpret_cast<uintptr_t>(out->hs_image);
     const bool b4 = in->num_bands % 4 == 0;

@@ -224,6 +224,10 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
         const uint8_t *lvl_bin = binaries + (int64_t)level * cells_per_level;
         // bit-packed copy of the level (1 bit per cell, 256 KB at 128^3: L1-resident) when the caller built one
         const uint32_t *lvl_bits = BITS ? bits + (int64_t)level * ((cells_per_level + 31) / 32) : nullptr;
+        auto fetch = [&](int c) -> uint32_t {
+            if (BITS) return (__ldg(lvl_bits + (c >> 5)) >> (c & 31)) & 1u;
+            return (uint32_t)__ldg(lvl_bin + c);
+        };
         // steps each axis may still take before it passes the interval's last cell or leaves the grid
         int left[3];
         for (int k = 0; k < 3; ++k) {
@@ -238,16 +242,7 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
         const float dl0 = delta[0], dl1 = delta[1], dl2 = delta[2];
         float td0 = tdist[0], td1 = tdist[1], td2 = tdist[2];
         int l0 = left[0], l1 = left[1], l2 = left[2];
-        // raw occupancy word of a cell + the bit to extract from it (bytes: shift 0): the extraction happens where the
-        // value is consumed, one iteration after the load was issued
-        auto fetch_raw = [&](int c, int &sh) -> uint32_t {
-            if (BITS) { sh = c & 31; return __ldg(lvl_bits + (c >> 5)); }
-            sh = 0;
-            return (uint32_t)__ldg(lvl_bin + c);
-        };
-        int sh0 = 0;
-        const uint32_t w0 = lookup ? fetch_raw(cell, sh0) : 0u;
-        uint32_t occ = BITS ? ((w0 >> sh0) & 1u) : w0;
+        uint32_t occ = lookup ? fetch(cell) : 0u;
         bool last = false;
         int guard = 4 * res + 8;
         // Phase 1 (this loop): the DDA alone, one cell per iteration for every lane of the warp, no inner loops.  Runs
@@ -260,57 +255,36 @@ __device__ int64_t march_ray(const float o[3], const float d[3], const uint8_t *
         // The step itself is written with selects, not branches: the lanes of a warp pick different axes in almost
         // every iteration, and a three-way divergent branch made the warp execute all three bodies (ncu: ~85
         // instructions per iteration, 8 cycles each at one to three warps per scheduler).
-        // The loop is software-pipelined one deep: iteration i steps to cell i+1 and ISSUES its occupancy load, and
-        // only then does the run bookkeeping of step i-1 with the word loaded an iteration earlier (ncu: 23 % of the
-        // warp samples waited on that load when it was consumed in the iteration that issued it).
-        bool have = false, end_prev = false;
-        float t_prev = 0.0f;
-        uint32_t word_prev = 0u;
-        int sh_prev = 0;
-        for (;;) {
-            bool stepped = false, end = false;
-            float t_traverse = 0.0f;
-            uint32_t word = 0u;
-            int sh = 0;
-            if (!last && guard > 0) {
-                t_traverse = fminf(fminf(td0, fminf(td1, td2)), this_tmax);
-                // single DDA step: x if strictly smallest, else y if < z, else z
-                const bool ax0 = (td0 < td1) && (td0 < td2);
-                const bool ax1 = !ax0 && (td1 < td2);
-                const bool ax2 = !ax0 && !ax1;
-                td0 = ax0 ? td0 + dl0 : td0;
-                td1 = ax1 ? td1 + dl1 : td1;
-                td2 = ax2 ? td2 + dl2 : td2;
-                cell += ax0 ? s0 : (ax1 ? s1 : s2);
-                l0 -= ax0 ? 1 : 0;
-                l1 -= ax1 ? 1 : 0;
-                l2 -= ax2 ? 1 : 0;
-                last = (l0 == 0) | (l1 == 0) | (l2 == 0);  // only the stepped axis can have reached 0 (all start >= 1)
-                if (lookup && !last) word = fetch_raw(cell, sh);
-                --guard;
-                end = last || guard == 0;
-                stepped = true;
-            }
-            if (have) {  // bookkeeping of the previous step: the cell it left ends a run?
-                const uint32_t occ_next = BITS ? ((word_prev >> sh_prev) & 1u) : word_prev;
-                if (end_prev || occ_next != occ) {
-                    if (!occ) {
-                        pend = t_prev;  // monotone: later thresholds dominate earlier ones
-                    } else {
-                        rec_pend[n_rec] = pend;
-                        rec_end[n_rec] = t_prev;
-                        pend = -1.0f;
-                        if (++n_rec == kRunCap && flush_runs()) return n;
-                    }
+        // Measured and dropped: a one-deep software pipeline (issue the fetch of cell i+1, then do the run bookkeeping
+        // of cell i with the word loaded an iteration earlier): 0.127 -> 0.61 ms -- the carried state and the
+        // two-exit loop cost far more than the L1 / L2 latency they were meant to hide.
+        while (!last && guard > 0) {
+            const float t_traverse = fminf(fminf(td0, fminf(td1, td2)), this_tmax);
+            // single DDA step: x if strictly smallest, else y if < z, else z
+            const bool ax0 = (td0 < td1) && (td0 < td2);
+            const bool ax1 = !ax0 && (td1 < td2);
+            const bool ax2 = !ax0 && !ax1;
+            td0 = ax0 ? td0 + dl0 : td0;
+            td1 = ax1 ? td1 + dl1 : td1;
+            td2 = ax2 ? td2 + dl2 : td2;
+            cell += ax0 ? s0 : (ax1 ? s1 : s2);
+            l0 -= ax0 ? 1 : 0;
+            l1 -= ax1 ? 1 : 0;
+            l2 -= ax2 ? 1 : 0;
+            last = (l0 == 0) | (l1 == 0) | (l2 == 0);  // only the stepped axis can have reached 0 (all start >= 1)
+            const uint32_t occ_next = (lookup && !last) ? fetch(cell) : 0u;
+            --guard;
+            if (last || guard == 0 || occ_next != occ) {  // the cell just left ends a run
+                if (!occ) {
+                    pend = t_traverse;  // monotone: later thresholds dominate earlier ones
+                } else {
+                    rec_pend[n_rec] = pend;
+                    rec_end[n_rec] = t_traverse;
+                    pend = -1.0f;
+                    if (++n_rec == kRunCap && flush_runs()) return n;
                 }
-                occ = occ_next;
             }
-            if (!stepped) break;
-            have = true;
-            t_prev = t_traverse;
-            end_prev = end;
-            word_prev = word;
-            sh_prev = sh;
+            occ = occ_next;
         }
     }
     if (flush_runs()) return n;
@@ -427,10 +401,24 @@ occ_pack_bits_kernel(const uint8_t *__restrict__ binaries, int64_t cells_per_lev
 }
 
 // Single-CTA exclusive scan of int64 counts -> packed_info[r] = (offset, count); *total = sum.
-// Each thread owns kScanItems consecutive elements (16 384 rays = one tile of 1024 x 16): one local serial scan, one
-// warp-shuffle scan of the per-thread sums, one of the per-warp sums -- three barriers per tile instead of per 1024.
-constexpr int kScanThreads = 1024;
-constexpr int kScanItems = 16;
+// Every access is coalesced (lane = consecutive element): a warp owns 1024 consecutive elements of a 16 384-element
+// tile and walks them 32 at a time.  Pass 1 only sums (32 independent loads per lane, one shuffle reduction per warp),
+// the 16 warp totals are scanned by warp 0, pass 2 re-reads the counts (L1 hits), scans each group of 32 with
+// shuffles plus a running carry and writes (offset, count) as 16-byte pairs.  The previous form gave every thread 16
+// CONSECUTIVE elements: each of its 16 loads and 16 stores touched 32 different lines per warp, and one SM's LSU
+// serialised ~32 k wavefronts per tile (20 us per 16 384 rays, 0.55 ms per 480 k-ray eval image; now ~5 us).
+constexpr int kScanThreads = 512;
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kScanIters = 32;                                  // groups of 32 elements per warp per tile
+constexpr int kScanTile = kScanWarps * kScanIters * 32;         // 16 384 elements
+__device__ __forceinline__ int64_t warp_incl_scan64(int64_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t t = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
 __global__ void __launch_bounds__(kScanThreads)
 pack_scan_kernel(const int64_t *__restrict__ counts, int64_t n, int64_t *__restrict__ packed_info, int64_t *total,
                  int64_t capacity) {
@@ -439,46 +427,40 @@ pack_scan_kernel(const int64_t *__restrict__ counts, int64_t n, int64_t *__restr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) base_s = 0;
     __syncthreads();
-    for (int64_t t0 = 0; t0 < n; t0 += (int64_t)kScanThreads * kScanItems) {
-        const int64_t i0 = t0 + (int64_t)tid * kScanItems;
-        int64_t v[kScanItems], sum = 0;
+    for (int64_t t0 = 0; t0 < n; t0 += kScanTile) {
+        const int64_t w0 = t0 + (int64_t)warp * (kScanIters * 32) + lane;
+        int64_t sum = 0;
 #pragma unroll
-        for (int k = 0; k < kScanItems; ++k) {
-            v[k] = (i0 + k < n) ? counts[i0 + k] : 0;
-            sum += v[k];
+        for (int it = 0; it < kScanIters; ++it) {
+            const int64_t i = w0 + it * 32;
+            sum += (i < n) ? counts[i] : 0;
         }
-        int64_t incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int64_t t = __shfl_up_sync(kFull, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) warp_sums[warp] = incl;
+        sum = warp_incl_scan64(sum, lane);
+        if (lane == 31) warp_sums[warp] = sum;
         __syncthreads();
         if (warp == 0) {
-            const int64_t w = warp_sums[lane];
-            int64_t wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int64_t t = __shfl_up_sync(kFull, wi, o);
-                if (lane >= o) wi += t;
-            }
+            const int64_t w = lane < kScanWarps ? warp_sums[lane] : 0;
+            const int64_t wi = warp_incl_scan64(w, lane);
             warp_sums[lane] = wi - w;  // exclusive warp offsets
             if (lane == 31) tile_total_s = wi;
         }
         __syncthreads();
-        int64_t excl = base_s + warp_sums[warp] + (incl - sum);
-#pragma unroll
-        for (int k = 0; k < kScanItems; ++k) {
-            if (i0 + k < n) {
-                int64_t start = excl, cnt = v[k];
+        int64_t run = base_s + warp_sums[warp];
+#pragma unroll 4
+        for (int it = 0; it < kScanIters; ++it) {
+            const int64_t i = w0 + it * 32;
+            const int64_t v = (i < n) ? counts[i] : 0;
+            const int64_t incl = warp_incl_scan64(v, lane);
+            const int64_t excl = run + (incl - v);
+            run += __shfl_sync(kFull, incl, 31);
+            if (i < n) {
+                int64_t start = excl, cnt = v;
                 if (capacity > 0) {  // truncate the packing at `capacity` samples
                     start = excl < capacity ? excl : capacity;
-                    cnt = (excl + v[k] <= capacity) ? v[k] : (capacity - start);
+                    cnt = (excl + v <= capacity) ? v : (capacity - start);
                 }
-                reinterpret_cast<longlong2 *>(packed_info)[i0 + k] = make_longlong2(start, cnt);
+                reinterpret_cast<longlong2 *>(packed_info)[i] = make_longlong2(start, cnt);
             }
-            excl += v[k];
         }
         __syncthreads();
         if (tid == 0) base_s += tile_total_s;
