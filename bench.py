@@ -495,8 +495,16 @@ def run_b200(args):
                     "unit": "GB/s", "frac": (kernels[top]["achieved_gbs"] or 0.0) / hbm_peak, "peak_source": peak_src,
                     **share}
         # the HBM-bound kernels the north star asks about (gather, scatter, compositing, optimiser), same definition
+        notes = {"umhs_hash_encode_fwd": "gathers are served by L2 (64 MiB table of a 126 MB L2): algorithmic bytes >> DRAM "
+                                         "traffic; the bound is L2 sector throughput + gather latency",
+                 "umhs_hash_encode_bwd": "reductions resolve in L2: algorithmic read-modify-write bytes >> DRAM traffic; "
+                                         "the bound is the L2 reduction rate",
+                 "umhs_adam_step_dev": "entries with g = m = v = 0 are skipped (12 of 32 B): algorithmic bytes count "
+                                       "32 B for every parameter, hence frac > 1",
+                 "umhs_adam_step": "see umhs_adam_step_dev"}
         roof["hbm_kernels"] = {n: {"achieved": v["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                                   "frac": v["achieved_gbs"] / hbm_peak, "traffic": NCU_TRAFFIC.get(n)}
+                                   "frac": v["achieved_gbs"] / hbm_peak, "traffic": NCU_TRAFFIC.get(n),
+                                   **({"note": notes[n]} if n in notes else {})}
                                for n, v in kernels.items() if v["achieved_gbs"] is not None}
         cpu = time_oracle(steps=4, warmup=1) if world == 1 else None
         h2d = sum(t.numel() * t.element_size() for t in pinned[0])
