@@ -28,7 +28,7 @@ constexpr int kCompThreads = kCompWarps * 32;
 constexpr int kMaxChunks = 128;  // chunk carries kept in smem: rays up to 4096 samples (longer: recomputed)
 
 struct SmemLayout {
-    int E, M, W, Bv, En, dE, dW, dB, carry, total;
+    int E, M, W, Bv, En, dE, dW, dB, carry, hbuf, total;
 };
 
 __host__ __device__ inline SmemLayout make_layout(int K, int B, bool specular, bool bwd) {
@@ -43,21 +43,30 @@ __host__ __device__ inline SmemLayout make_layout(int K, int B, bool specular, b
     s.dW = o; o += (bwd && specular) ? B * 17 : 0;
     s.dB = o; o += (bwd && specular) ? B : 0;
     s.carry = o; o += bwd ? kCompWarps * kMaxChunks : 0;
+    o = (o + 3) & ~3;  // 16-byte aligned: float4 rows
+    s.hbuf = o; o += specular ? kCompWarps * 32 * 16 : 0;  // per warp: the spec_hidden rows of one 32-sample chunk
     s.total = o;
     return s;
 }
 
-__device__ __forceinline__ void load_h16(const float *h, float (&hv)[16]) {
-    const float4 *p = reinterpret_cast<const float4 *>(h);
+// The spec_hidden rows [m,16] of a chunk of m <= 32 consecutive samples -> this warp's shared-memory buffer: one
+// coalesced pass (<= 4 float4 per lane, all in flight) instead of one exposed 64-byte global load per sample.
+__device__ __forceinline__ void stage_chunk_h(const float *rows, int m, float4 *hb, int lane) {
+    const float4 *src = reinterpret_cast<const float4 *>(rows);
+    __syncwarp();  // the previous chunk's readers are done
+    for (int q = lane; q < 4 * m; q += 32) hb[q] = __ldg(src + q);
+    __syncwarp();
+}
+__device__ __forceinline__ void read_h16(const float4 *hb, int j, float (&hv)[16]) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const float4 v = __ldg(p + q);
+        const float4 v = hb[4 * j + q];
         hv[4 * q + 0] = v.x; hv[4 * q + 1] = v.y; hv[4 * q + 2] = v.z; hv[4 * q + 3] = v.w;
     }
 }
 
 template <int KMAX, int BPL>
-__global__ void __launch_bounds__(kCompThreads)
+__global__ void __launch_bounds__(kCompThreads, (BPL == 4 && KMAX <= 8) ? 2 : 1)
 composite_fwd_kernel(umhs_composite_in in, umhs_composite_out out) {
     extern __shared__ float smem[];
     const int K = in.num_classes, B = in.num_bands;
@@ -79,6 +88,20 @@ composite_fwd_kernel(umhs_composite_in in, umhs_composite_out out) {
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 *hbuf = reinterpret_cast<float4 *>(smem + L.hbuf) + warp * 128;
+    // B <= 128: the 16 weights (+ bias) of each of this lane's 4 bands live in registers for the whole kernel -- the
+    // per-sample sigmoid(W h + b) term then needs no shared-memory reads at all (it was one LDS per FMA)
+    constexpr bool WREG = (BPL == 4);
+    float W_r[WREG ? 4 : 1][16], b_r[WREG ? 4 : 1];
+    if (WREG && specular) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int b = lane + 32 * i;
+            b_r[i] = b < B ? b_s[b] : 0.f;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) W_r[i][q] = b < B ? W_s[b * 17 + q] : 0.f;
+        }
+    }
     float tmin = CUDART_INF_F, tmax = -CUDART_INF_F;
     for (int64_t r = (int64_t)blockIdx.x * kCompWarps + warp; r < in.n_rays; r += (int64_t)gridDim.x * kCompWarps) {
         const int64_t start = __ldg(in.packed_info + 2 * r), cnt = __ldg(in.packed_info + 2 * r + 1);
@@ -123,19 +146,21 @@ composite_fwd_kernel(umhs_composite_in in, umhs_composite_out out) {
             if (specular) {
                 const float ws = v ? w * __ldg(in.s1 + n) : 0.f;
                 const int m = (int)((cnt - c0) < 32 ? (cnt - c0) : 32);
+                stage_chunk_h(in.spec_hidden + (start + c0) * 16, m, hbuf, lane);
                 for (int j = 0; j < m; ++j) {
                     const float wj = __shfl_sync(kFull, ws, j);
                     if (wj == 0.f) continue;  // warp-uniform
                     float hv[16];
-                    load_h16(in.spec_hidden + (start + c0 + j) * 16, hv);
+                    read_h16(hbuf, j, hv);
 #pragma unroll
                     for (int i = 0; i < BPL; ++i) {
                         const int b = lane + 32 * i;
                         if (b < B) {
-                            float z = b_s[b];
+                            float z = WREG ? b_r[i < 4 ? i : 0] : b_s[b];
 #pragma unroll
-                            for (int q = 0; q < 16; ++q) z += W_s[b * 17 + q] * hv[q];
-                            sacc[i] += wj * (1.0f / (1.0f + expf(-z)));
+                            for (int q = 0; q < 16; ++q)
+                                z += (WREG ? W_r[i < 4 ? i : 0][q] : W_s[b * 17 + q]) * hv[q];
+                            sacc[i] += wj * sigmoidf(z);
                         }
                     }
                 }
@@ -278,6 +303,29 @@ composite_bwd_kernel(umhs_composite_in in, umhs_composite_grads_in gin, umhs_com
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *carries = smem + L.carry + warp * kMaxChunks;
+    float4 *hbuf = reinterpret_cast<float4 *>(smem + L.hbuf) + warp * 128;
+    // B <= 128 (4 bands per lane): dW / db of this lane's bands accumulate in registers for the whole kernel (DREG);
+    // with K <= 4 there is room for the weights themselves too (WREG), so the per-sample term reads no shared memory
+    constexpr bool DREG = (BPL == 4);
+    constexpr bool WREG = (BPL == 4) && (KMAX <= 4);
+    float W_r[WREG ? 4 : 1][16], b_r[WREG ? 4 : 1], dW_r[DREG ? 4 : 1][16], dB_r[DREG ? 4 : 1];
+    if (DREG) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            dB_r[i] = 0.f;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) dW_r[i][t] = 0.f;
+        }
+    }
+    if (WREG && specular) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int b = lane + 32 * i;
+            b_r[i] = b < B ? b_s[b] : 0.f;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) W_r[i][t] = b < B ? W_s[b * 17 + t] : 0.f;
+        }
+    }
     for (int64_t r = (int64_t)blockIdx.x * kCompWarps + warp; r < in.n_rays; r += (int64_t)gridDim.x * kCompWarps) {
         const int64_t start = __ldg(in.packed_info + 2 * r), cnt = __ldg(in.packed_info + 2 * r + 1);
         if (cnt == 0) continue;
@@ -389,12 +437,11 @@ composite_bwd_kernel(umhs_composite_in in, umhs_composite_grads_in gin, umhs_com
                 const float wsg = w * s1v * gs;  // weight of dz accumulation for this lane's sample
                 float q_mine = 0.f;
                 const int m = (int)((cnt - c0) < 32 ? (cnt - c0) : 32);
+                stage_chunk_h(in.spec_hidden + (start + c0) * 16, m, hbuf, lane);
                 for (int j = 0; j < m; ++j) {
                     const float wj = __shfl_sync(kFull, wsg, j);
-                    const float wraw = __shfl_sync(kFull, w, j);
-                    const float gsj = __shfl_sync(kFull, gs, j);
                     float hv[16];
-                    load_h16(in.spec_hidden + (start + c0 + j) * 16, hv);
+                    read_h16(hbuf, j, hv);
                     float q = 0.f, dh[16];
 #pragma unroll
                     for (int t = 0; t < 16; ++t) dh[t] = 0.f;
@@ -402,13 +449,23 @@ composite_bwd_kernel(umhs_composite_in in, umhs_composite_grads_in gin, umhs_com
                     for (int i = 0; i < BPL; ++i) {
                         const int b = lane + 32 * i;
                         if (b < B) {
-                            float z = b_s[b];
+                            float z = WREG ? b_r[i < 4 ? i : 0] : b_s[b];
 #pragma unroll
-                            for (int t = 0; t < 16; ++t) z += W_s[b * 17 + t] * hv[t];
-                            const float sp = 1.0f / (1.0f + expf(-z));
+                            for (int t = 0; t < 16; ++t)
+                                z += (WREG ? W_r[i < 4 ? i : 0][t] : W_s[b * 17 + t]) * hv[t];
+                            const float sp = sigmoidf(z);
                             q += dS[i] * sp;
                             const float u = wj * dS[i] * sp * (1.0f - sp);  // d loss / d z_b (grad-scaled)
-                            if (u != 0.f) {
+                            if (DREG) {
+                                // this lane's 4 x 17 entries of dW / db accumulate in registers over all samples of
+                                // all rays of the warp (they were 17 shared-memory atomics per band per sample)
+                                dB_r[i < 4 ? i : 0] += u;
+#pragma unroll
+                                for (int t = 0; t < 16; ++t) {
+                                    dW_r[i < 4 ? i : 0][t] += u * hv[t];
+                                    dh[t] += u * (WREG ? W_r[i < 4 ? i : 0][t] : W_s[b * 17 + t]);
+                                }
+                            } else if (u != 0.f) {
                                 atomicAdd(dB_s + b, u);
 #pragma unroll
                                 for (int t = 0; t < 16; ++t) {
@@ -419,16 +476,28 @@ composite_bwd_kernel(umhs_composite_in in, umhs_composite_grads_in gin, umhs_com
                         }
                     }
                     q = warp_sum(q);
-                    float mine = 0.f;
+                    // d h[t] = sum over bands (lanes): butterfly transpose-reduce, 16 shuffles instead of 80; lane L ends
+                    // up with t = bits (L4 L3 L2 L1) of its index, both lanes of a pair hold the sum
+                    {
 #pragma unroll
-                    for (int t = 0; t < 16; ++t) {
-                        const float s = warp_sum(dh[t]);
-                        if (lane == t) mine = s;
+                        for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+                            const bool up = (lane & off) != 0;
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                if (k < half) {
+                                    const float send = up ? dh[k] : dh[k + half];
+                                    const float keep = up ? dh[k + half] : dh[k];
+                                    dh[k] = keep + __shfl_xor_sync(kFull, send, off);
+                                }
+                            }
+                        }
+                        dh[0] += __shfl_xor_sync(kFull, dh[0], 1);
+                        const int t_mine = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
+                                           ((lane >> 1) & 1);
+                        if ((lane & 1) == 0 && gout.d_spec_hidden)
+                            gout.d_spec_hidden[(start + c0 + j) * 16 + t_mine] = dh[0];
                     }
-                    if (lane < 16 && gout.d_spec_hidden) gout.d_spec_hidden[(start + c0 + j) * 16 + lane] = mine;
                     if (lane == j) q_mine = q;
-                    (void)wraw;
-                    (void)gsj;
                 }
                 dw += s1v * q_mine;
                 if (v && gout.d_s1) gout.d_s1[n] = w * q_mine * gs;
@@ -462,6 +531,18 @@ composite_bwd_kernel(umhs_composite_in in, umhs_composite_grads_in gin, umhs_com
             }
         }
     }
+    if (DREG && specular) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int b = lane + 32 * i;
+            if (b < B) {
+                if (dB_r[i] != 0.f) atomicAdd(dB_s + b, dB_r[i]);
+#pragma unroll
+                for (int t = 0; t < 16; ++t)
+                    if (dW_r[i][t] != 0.f) atomicAdd(dW_s + b * 17 + t, dW_r[i][t]);
+            }
+        }
+    }
     __syncthreads();
     if (gout.d_endmembers)
         for (int i = threadIdx.x; i < K * B; i += kCompThreads)
@@ -485,22 +566,32 @@ static int check_in(const umhs_composite_in *in) {
     if (!in->packed_info || !in->t_starts || !in->t_ends || !in->sigma || !in->scalar || !in->abund) return -1;
     if (!in->endmembers || !in->rgb_matrix) return -1;
     if (in->specular && (!in->s1 || !in->spec_hidden || !in->dir_w1 || !in->dir_b1)) return -1;
+    if (in->specular && (reinterpret_cast<uintptr_t>(in->spec_hidden) & 15u)) return -1;  // rows are read as float4
     return 0;
 }
 
-static int comp_grid(int64_t n_rays) {
+// persistent grid: as many CTAs as fit the device at once (the specular kernels hold their weights / gradient
+// accumulators in registers: 1-2 CTAs per SM), fewer when there are fewer rays
+template <typename Kern>
+static int comp_grid(Kern kern, size_t smem_bytes, int64_t n_rays, int max_per_sm, int *grid) {
+    int per_sm = 0;
+    UMHS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    UMHS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCompThreads, smem_bytes));
+    per_sm = per_sm < 1 ? 1 : (per_sm > max_per_sm ? max_per_sm : per_sm);
     const int64_t want = (n_rays + kCompWarps - 1) / kCompWarps;
-    const int64_t cap = (int64_t)kNumSMs * 8;
-    return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    const int64_t cap = (int64_t)kNumSMs * per_sm;
+    *grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    return UMHS_OK;
 }
 
 template <int KMAX, int BPL>
 static int launch_fwd(const umhs_composite_in *in, const umhs_composite_out *out, cudaStream_t st) {
     const SmemLayout L = make_layout(in->num_classes, in->num_bands, in->specular != 0, false);
     const size_t bytes = (size_t)L.total * sizeof(float);
-    UMHS_CHECK_CUDA(cudaFuncSetAttribute(composite_fwd_kernel<KMAX, BPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)bytes));
-    composite_fwd_kernel<KMAX, BPL><<<comp_grid(in->n_rays), kCompThreads, bytes, st>>>(*in, *out);
+    int grid = 1;
+    const int rc = comp_grid(composite_fwd_kernel<KMAX, BPL>, bytes, in->n_rays, 8, &grid);
+    if (rc != UMHS_OK) return rc;
+    composite_fwd_kernel<KMAX, BPL><<<grid, kCompThreads, bytes, st>>>(*in, *out);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }
@@ -510,11 +601,10 @@ static int launch_bwd(const umhs_composite_in *in, const umhs_composite_grads_in
                       const umhs_composite_grads_out *gout, cudaStream_t st) {
     const SmemLayout L = make_layout(in->num_classes, in->num_bands, in->specular != 0, true);
     const size_t bytes = (size_t)L.total * sizeof(float);
-    UMHS_CHECK_CUDA(cudaFuncSetAttribute(composite_bwd_kernel<KMAX, BPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)bytes));
     // fewer, fatter CTAs: each flushes K*B (+17B) atomics at the end
-    int grid = comp_grid(in->n_rays);
-    if (grid > kNumSMs * 2) grid = kNumSMs * 2;
+    int grid = 1;
+    const int rc = comp_grid(composite_bwd_kernel<KMAX, BPL>, bytes, in->n_rays, 2, &grid);
+    if (rc != UMHS_OK) return rc;
     composite_bwd_kernel<KMAX, BPL><<<grid, kCompThreads, bytes, st>>>(*in, *gin, *gout);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
