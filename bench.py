@@ -433,28 +433,34 @@ def run_b200(args):
     H_EVAL, W_EVAL = 600, 800
     eo, ed, _, _ = make_rays(H_EVAL * W_EVAL, 4242)
     cam = RayBundle(eo.view(H_EVAL, W_EVAL, 3).to(dev), ed.view(H_EVAL, W_EVAL, 3).to(dev))
-    for _ in range(2):  # warm-up (twice: the caching allocator settles on the block sizes of a whole-image pass)
+    res = None
+    for _ in range(3):  # warm-up with the timed loop's own allocation pattern (previous image released first)
+        res = None
         res = trainer.render_tiles(cam)
     barrier()
-    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     N_EVAL_IMAGES = 8
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(N_EVAL_IMAGES + 1)]
     eval_clocks = ClockSampler(local, period_s=0.005)
     if rank == 0:
         eval_clocks.start()
-    ea.record()
+    mem0 = torch.cuda.memory_stats(dev)
+    marks[0].record()
     n_eval = 0
-    for _ in range(N_EVAL_IMAGES):
-        t_it = time.perf_counter()
+    for it in range(N_EVAL_IMAGES):
         res = None  # release the previous image first
         res = trainer.render_tiles(cam)
         n_eval = res["num_samples_per_ray"].sum()
-        if os.environ.get("UMHS_BENCH_DEBUG"):
-            torch.cuda.synchronize()
-            print(f"[bench] eval image: {1e3 * (time.perf_counter() - t_it):.2f} ms wall, tile rays "
-                  f"{model.config.eval_tile_rays}", file=sys.stderr)
-    eb.record()
+        marks[it + 1].record()
     barrier()
+    mem1 = torch.cuda.memory_stats(dev)
     eval_clk = eval_clocks.stop() if rank == 0 else None
+    per_image = [marks[i].elapsed_time(marks[i + 1]) for i in range(N_EVAL_IMAGES)]
+    # the mean of all images is the reported figure; the list and the allocator counters explain outliers (a
+    # cudaMalloc / cudaFree of the multi-GB transients inside the region shows up here)
+    eval_alloc = {"cuda_malloc": int(mem1.get("segment.all.allocated", 0) - mem0.get("segment.all.allocated", 0)),
+                  "cuda_free": int(mem1.get("segment.all.freed", 0) - mem0.get("segment.all.freed", 0)),
+                  "alloc_retries": int(mem1.get("num_alloc_retries", 0) - mem0.get("num_alloc_retries", 0))}
+    ea, eb = marks[0], marks[-1]
     eval_ms = torch.tensor([ea.elapsed_time(eb) / N_EVAL_IMAGES], device=dev)
     eval_samples = n_eval.to(torch.float32).reshape(1).clone()
     if world > 1:
@@ -527,7 +533,8 @@ def run_b200(args):
                            "samples_per_image": float(eval_samples.item()),
                            "rays_per_s": H_EVAL * W_EVAL / (float(eval_ms.item()) * 1e-3),
                            "sharding": "32x32 tiles round-robin over ranks, no collective; one fused pass per rank",
-                           "images_timed": N_EVAL_IMAGES,
+                           "images_timed": N_EVAL_IMAGES, "ms_per_image_each": [round(x, 3) for x in per_image],
+                           "allocator_in_region": eval_alloc,
                            "clocks": {k: eval_clk[k] for k in ("sm_mhz", "reasons", "samples")} if eval_clk else None},
                 "next_train": {**next_train, "frac": next_train["achieved_gbs"] / hbm_peak, "peak": hbm_peak},
                 "kernels": kernels}

@@ -238,6 +238,9 @@ def test_trainer_cuda_graph_matches_eager():
                 rb = RayBundle(t(d["origins"]).to(DEV), t(d["directions"]).to(DEV))
                 losses.append(tr.train_step(rb, batch)["loss"].clone())
         res[graph] = (torch.stack(losses).cpu(), tr.flat.data.clone().cpu(), tr.truncated_steps)
+        # a step result read through the side-stream copy (UMHSTrainer.read_async) is the value itself
+        handles = [tr.read_async(x) for x in losses[-2:]]
+        assert [h.result() for h in handles] == [float(x) for x in losses[-2:]]
     assert res[True][2] == 0 and res[False][2] == 0 and res["piped"][2] == 0
     assert torch.isfinite(res["piped"][0]).all()
     assert (res["piped"][0] - res[False][0]).abs().max() < 5e-2 * res[False][0].abs().max()
