@@ -96,12 +96,20 @@ class OccGridEstimator(nn.Module):
         """The parameter-independent half of ``sampling``: near / far planes, stratified jitter, occupancy march.
         -> (ray_indices, t_starts, t_ends, packed_info, total).  It depends only on the rays and on ``binaries``, so
         a trainer may run it for the NEXT batch while the current step is still computing."""
-        near = torch.full_like(rays_o[..., 0], fill_value=near_plane)
-        far = torch.full_like(rays_o[..., 0], fill_value=far_plane)
-        if t_min is not None:
-            near = torch.clamp(near, min=t_min)
-        if t_max is not None:
-            far = torch.clamp(far, max=t_max)
+        # the planes before jitter are the same every step when the collider hands over the same constant tensors
+        # (UMHSModel.collider caches them): keep them instead of four fill / clamp launches per march
+        c = getattr(self, "_plane_cache", None)
+        if (c is not None and c[0] is t_min and c[1] is t_max and c[2] == (near_plane, far_plane, tuple(rays_o.shape))
+                and c[3].device == rays_o.device):
+            near, far = c[3], c[4]
+        else:
+            near = torch.full_like(rays_o[..., 0], fill_value=near_plane)
+            far = torch.full_like(rays_o[..., 0], fill_value=far_plane)
+            if t_min is not None:
+                near = torch.clamp(near, min=t_min)
+            if t_max is not None:
+                far = torch.clamp(far, max=t_max)
+            self._plane_cache = (t_min, t_max, (near_plane, far_plane, tuple(rays_o.shape)), near, far)
         if stratified:
             if jitter is None:
                 jitter = torch.rand_like(near)

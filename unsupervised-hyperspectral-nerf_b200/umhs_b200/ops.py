@@ -283,6 +283,7 @@ class FieldFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pts: PointSet, cfg: dict, table: Tensor, scalings: Tensor, *mlp: Optional[Tensor]):
+        ctx.set_materialize_grads(False)  # undefined output gradients arrive as None, not as zero-filled tensors
         weights = {n: (w.detach() if w is not None else None) for n, w in zip(MLP_NAMES, mlp)}
         # kept samples are a subset of the sampler's candidates: reuse their encodings when the sampler kept them
         enc = pts.enc_src if pts.enc_src is not None else hash_encode_fwd(pts, table.detach(), scalings, cfg["log2_T"])
@@ -369,6 +370,7 @@ class CompositeFunction(torch.autograd.Function):
     def forward(ctx, cfg: dict, packed_info, t0, t1, sigma, scalar, abund, s1, spec_hidden, endmembers, dir_w1,
                 dir_b1, rgb_matrix, palette):
         lib = _lib.load()
+        ctx.set_materialize_grads(False)  # undefined output gradients arrive as None, not as zero-filled tensors
         dev = sigma.device
         R, N, K, B, specular = int(packed_info.shape[0]), int(sigma.shape[0]), cfg["K"], cfg["B"], cfg["specular"]
         ctx.param_refs = (endmembers, dir_w1, dir_b1)

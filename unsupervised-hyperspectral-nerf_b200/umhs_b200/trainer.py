@@ -284,7 +284,8 @@ class UMHSTrainer:
             if w_rgb != 0.0:
                 loss_dict["rgb_loss"] = losses[1]
             loss_dict["loss"] = losses[0] + losses[1]
-            loss_dict["num_samples"] = outputs["num_samples_per_ray"].sum()
+            # kept samples of the step: the compaction's device-side count (no reduction launch)
+            loss_dict["num_samples"] = m.occupancy_grid.last_totals[1][0]
             return loss_dict
         loss_dict = m.get_loss_dict(outputs, batch)
         loss = sum(loss_dict.values())

@@ -137,9 +137,16 @@ class UMHSModel(nn.Module):
 
     # NearFarCollider (A.4): nears = near_plane while training, 0 in eval; fars = far_plane
     def collider(self, ray_bundle: RayBundle) -> RayBundle:
-        ones = torch.ones_like(ray_bundle.origins[..., 0:1])
-        ray_bundle.nears = ones * (self.config.near_plane if self.training else 0.0)
-        ray_bundle.fars = ones * self.config.far_plane
+        o = ray_bundle.origins
+        near = float(self.config.near_plane if self.training else 0.0)
+        key = (tuple(o.shape[:-1]), o.device, near, float(self.config.far_plane))
+        cache = self.__dict__.setdefault("_collider_cache", {})
+        if key not in cache:  # constant tensors, reused (read-only downstream): no fill launches per step
+            if len(cache) > 8:
+                cache.clear()
+            ones = torch.ones_like(o[..., 0:1])
+            cache[key] = (ones * near, ones * float(self.config.far_plane))
+        ray_bundle.nears, ray_bundle.fars = cache[key]
         return ray_bundle
 
     def forward(self, ray_bundle: RayBundle) -> Dict[str, Tensor]:
