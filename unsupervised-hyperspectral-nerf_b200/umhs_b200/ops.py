@@ -587,7 +587,7 @@ def march(rays_o: Tensor, rays_d: Tensor, near_planes: Tensor, far_planes: Tenso
     a.step_size, a.cone_angle, a.n_rays = float(step_size), float(cone_angle), R
     counts = torch.empty((R,), dtype=torch.int64, device=dev)
     packed = torch.empty((R, 2), dtype=torch.int64, device=dev)
-    total = torch.zeros((2,), dtype=torch.int64, device=dev)
+    total = torch.empty((2,), dtype=torch.int64, device=dev)  # both entries are written by umhs_pack_scan
     st = stream_ptr(dev)
     a.level_any = a.occ_bits = None
     if packed_grid is not None and MARCH_BITS:
@@ -628,7 +628,7 @@ def visibility_compact(packed_info: Tensor, t0: Tensor, t1: Tensor, sigma: Tenso
     keep = torch.empty((N,), dtype=torch.uint8, device=dev)
     kc = torch.empty((R,), dtype=torch.int64, device=dev)
     packed2 = torch.empty((R, 2), dtype=torch.int64, device=dev)
-    total = torch.zeros((2,), dtype=torch.int64, device=dev)
+    total = torch.empty((2,), dtype=torch.int64, device=dev)  # both entries are written by umhs_pack_scan
     st = stream_ptr(dev)
     _call("umhs_visibility_mask", R, ptr(packed_info), R, ptr(t0), ptr(t1), ptr(f32(sigma).reshape(-1)),
           float(early_stop_eps), float(alpha_thre), ptr(occ_mean), ptr(keep), ptr(kc), st)
