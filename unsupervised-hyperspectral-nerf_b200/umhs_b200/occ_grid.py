@@ -265,7 +265,7 @@ class VolumetricSampler(nn.Module):
             def sigma_fn(t0, t1, ri, n_dev=None):
                 pts = PointSet.from_packed(rays_o, rays_d, ri, t0, t1, contraction=field.contraction,
                                            aabb=field._aabb6(), n_dev=n_dev)
-                sigma, cand_enc[0] = field.density_packed(pts, return_enc=True)
+                sigma, cand_enc[0] = field.density_packed(pts, return_enc=True, zero_tail=False)
                 return sigma
         ri, t0, t1, packed, total = self.occupancy_grid.sampling(
             rays_o, rays_d, sigma_fn=sigma_fn, near_plane=near_plane, far_plane=far_plane, t_min=t_min, t_max=t_max,

@@ -227,10 +227,12 @@ def mlp_struct(weights: Dict[str, Optional[Tensor]], num_classes: int, specular:
     return s
 
 
-def density_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor]) -> Tensor:
+def density_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], zero_tail: bool = True) -> Tensor:
     lib = _lib.load()
-    # with a device-side count the entries beyond it are not written: they read as zero density
-    sigma = (torch.zeros if pts.n_dev is not None else torch.empty)((pts.n,), dtype=torch.float32, device=enc.device)
+    # with a device-side count the entries beyond it are not written: they read as zero density (zero_tail; a caller
+    # that only reads the counted entries -- the sampler's visibility pass -- skips the fill)
+    fill = pts.n_dev is not None and zero_tail
+    sigma = (torch.zeros if fill else torch.empty)((pts.n,), dtype=torch.float32, device=enc.device)
     ps, ms = pts.struct(), mlp_struct(weights, 1, False, 1.0)
     _call("umhs_density_tc_fwd" if MLP_PRECISION == "bf16" else "umhs_density_fwd", pts.units(), ctypes.byref(ps), pts.n, ptr(enc), ctypes.byref(ms), ptr(sigma),
                                stream_ptr(enc.device))
@@ -387,14 +389,19 @@ class CompositeFunction(torch.autograd.Function):
                "weights": z(N) if cfg.get("want_weights", False) else None}
         # per-sample transmittance, kept for the backward (4 B/sample instead of a recomputation pass there)
         trans = z(N) if any(ctx.needs_input_grad) else None
-        tmm = _tminmax_init(dev).clone()  # (+inf, -inf) without a host->device copy per call
+        want_depth = cfg.get("want_depth", True)  # a trainer that never reads the depth skips it (3 launches)
+        if not want_depth:
+            out["depth"] = None
         co = _lib.CompositeOut()
         for k, v in out.items():
             setattr(co, k, ptr(v))
         co.trans = ptr(trans)
-        co.t_minmax = ptr(tmm)
+        if want_depth:
+            tmm = _tminmax_init(dev).clone()  # (+inf, -inf) without a host->device copy per call
+            co.t_minmax = ptr(tmm)
         _call("umhs_composite_fwd", R, ctypes.byref(ci), ctypes.byref(co), stream_ptr(dev))
-        _call("umhs_depth_clip", 0, ptr(out["depth"]), R, ptr(tmm), stream_ptr(dev))
+        if want_depth:
+            _call("umhs_depth_clip", 0, ptr(out["depth"]), R, ptr(tmm), stream_ptr(dev))
         ctx.cfg = cfg
         ctx.save_for_backward(packed_info, t0, t1, sigma, scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1,
                               rgb_matrix, out["spectral"], trans)

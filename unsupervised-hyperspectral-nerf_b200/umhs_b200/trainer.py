@@ -259,7 +259,7 @@ class UMHSTrainer:
 
     def _forward_backward(self, ray_bundle: RayBundle, batch: Dict[str, Tensor], premarched=None):
         m = self.model
-        outputs = m.get_outputs(m.collider(ray_bundle), per_band_views=False, premarched=premarched)
+        outputs = m.get_outputs(m.collider(ray_bundle), per_band_views=False, premarched=premarched, lean=True)
         if self.fused_loss and outputs["spectral"].is_cuda:
             # UMHSModel.get_loss_dict and its backward as one kernel (csrc/loss.cu): the gradients of the scalar loss
             # with respect to the rendered outputs go straight into the compositing backward

@@ -168,7 +168,9 @@ class UMHSModel(nn.Module):
             cone_angle=cfg.cone_angle, jitter=jitter, capacity=self.sample_capacity if self.training else None)
 
     def get_outputs(self, ray_bundle: RayBundle, jitter: Optional[Tensor] = None,
-                    per_band_views: bool = True, premarched=None) -> Dict[str, Tensor]:
+                    per_band_views: bool = True, premarched=None, lean: bool = False) -> Dict[str, Tensor]:
+        """lean=True (the standalone trainer): no "depth" entry and no per-sample weights by-product -- nothing in
+        the training losses reads them (ref umhs_model.py:329-383) -- which saves three launches per step."""
         cfg = self.config
         num_rays = int(ray_bundle.origins.reshape(-1, 3).shape[0])
         if ray_bundle.nears is None:
@@ -181,14 +183,16 @@ class UMHSModel(nn.Module):
         fo = self.field.forward_packed(pts, want_embedding=False)
         K, B, spec = self.field.num_classes, self.field.wavelengths, cfg.pred_specular
         d = self.field.mlp_directional.layers
-        ccfg = {"K": K, "B": B, "specular": spec, "grad_scaling": cfg.use_gradient_scaling, "want_weights": True}
+        ccfg = {"K": K, "B": B, "specular": spec, "grad_scaling": cfg.use_gradient_scaling, "want_weights": not lean,
+                "want_depth": not lean}
         (spectral, spectral2, specular, abund, acc, depth, rgb, seg_probs, seg_raw, seg_pred,
          weights) = ops.CompositeFunction.apply(
             ccfg, packed_info, t0, t1, fo["sigma"], fo["scalar"], fo["abund"], fo.get("s1"), fo.get("spec_hidden"),
             self.field.endmembers, d[1].weight if spec else None, d[1].bias if spec else None,
             self.converter.transform_matrix, self.class_colors)
-        outputs: Dict[str, Tensor] = {"accumulation": acc.unsqueeze(-1), "depth": depth.unsqueeze(-1),
-                                      "spectral": spectral}
+        outputs: Dict[str, Tensor] = {"accumulation": acc.unsqueeze(-1), "spectral": spectral}
+        if not lean:
+            outputs["depth"] = depth.unsqueeze(-1)
         if per_band_views:
             for i in range(B):
                 outputs[f"wv_{i}"] = spectral[..., i]
