@@ -8,10 +8,9 @@
 // on hyperspectral cubes loaded as in ref umhsnerf/data/utils/hs_dataloader.py:46-50 (H x W x B per image).
 // Arithmetic follows oracle/datamanager_oracle.py (perspective cameras, no distortion).
 //
-// Mapping: one warp per ray.  Every lane repeats the few scalar operations of the index / camera math (no
-// divergence, no broadcast), lanes 0-2 write the per-ray vectors, and the warp copies the pixel's B-band spectrum
-// as one contiguous row (128 bands fp32 = 512 B = one float4 per lane).  HBM-bound: a random 4B-byte row read and a
-// 4B-byte row written per ray; algorithmic bytes per ray = 12 (draws) + 24 (indices) + 32 (origin, direction, area,
+// Mapping: one warp per 32 rays: lane = ray for the index / camera math and the per-ray vectors, then the warp copies
+// the 32 pixels' B-band spectra as contiguous rows (128 bands fp32 = 512 B = one float4 per lane), the pixel index
+// broadcast by shuffle.  HBM-bound: a random 4B-byte row read and a 4B-byte row written per ray; algorithmic bytes per ray = 12 (draws) + 24 (indices) + 32 (origin, direction, area,
 // norm) + sizeof(hs) B + 4 B (+ image in / out).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -20,7 +19,7 @@
 
 namespace umhs {
 
-constexpr int kBatchWarps = 8;
+constexpr int kBatchWarps = 2;  // 64 rays per CTA: a 16 k-ray batch still spreads over every SM
 constexpr int kBatchThreads = kBatchWarps * 32;
 
 template <int DT>
@@ -70,73 +69,95 @@ __device__ __forceinline__ int draw_index(float u, int bound) {
     return i < bound ? (i < 0 ? 0 : i) : bound - 1;
 }
 
+// One warp per 32 rays.  Phase 1: lane l does the scalar work of ray base + l (indices, camera ray, RGB pixel) -- one
+// pass of ~150 instructions per 32 rays; the first form of this kernel had every lane repeat it for ONE ray per warp
+// and was bound by instruction issue (200 warp instructions per ray, 1.7 TB/s).  Phase 2: the warp copies the 32
+// spectra row by row (pixel index broadcast by shuffle), four rows in flight.
 template <int DT>
-__global__ void __launch_bounds__(kBatchThreads, 6)
-sample_batch_kernel(umhs_batch_in in, umhs_batch_out out, int vec) {
+__global__ void __launch_bounds__(kBatchThreads, 16)
+sample_batch_kernel(umhs_batch_in in, umhs_batch_out out, int vec, int rpw) {
     using T = typename HsElem<DT>::type;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int B = in.num_bands, C = in.image_channels;
     const T *hs = reinterpret_cast<const T *>(in.hs);
-    for (int64_t r = (int64_t)blockIdx.x * kBatchWarps + warp; r < in.n_rays; r += (int64_t)gridDim.x * kBatchWarps) {
-        const int c = draw_index(__ldg(in.u + 3 * r + 0), in.num_images);
-        const int y = draw_index(__ldg(in.u + 3 * r + 1), in.height);
-        const int x = draw_index(__ldg(in.u + 3 * r + 2), in.width);
-        const int64_t cam = in.image_idx ? __ldg(in.image_idx + c) : (int64_t)c;
-        const int64_t pix = ((int64_t)c * in.height + y) * in.width + x;
-        // ---- spectrum of the pixel: one contiguous row
-        if (hs != nullptr && out.hs_image != nullptr) {
-            const T *src = hs + pix * B;
-            float *dst = out.hs_image + r * B;
-            if (vec) {
-                for (int j = lane; 4 * j < B; j += 32) reinterpret_cast<float4 *>(dst)[j] = load4<DT>(src, j);
-            } else {
-                for (int b = lane; b < B; b += 32) dst[b] = HsElem<DT>::get(src, b);
+    // rpw rays per warp (32 for large batches; fewer for small ones, upper lanes idle in phase 1, so that a 16 k-ray
+    // batch is still thousands of warps and not 512 warps copying 32 rows one after the other)
+    for (int64_t base = ((int64_t)blockIdx.x * kBatchWarps + warp) * rpw; base < in.n_rays;
+         base += (int64_t)gridDim.x * kBatchWarps * rpw) {
+        const int64_t r = base + lane;
+        const bool valid = lane < rpw && r < in.n_rays;
+        int64_t pix = 0;
+        if (valid) {
+            const int c = draw_index(__ldg(in.u + 3 * r + 0), in.num_images);
+            const int y = draw_index(__ldg(in.u + 3 * r + 1), in.height);
+            const int x = draw_index(__ldg(in.u + 3 * r + 2), in.width);
+            const int64_t cam = in.image_idx ? __ldg(in.image_idx + c) : (int64_t)c;
+            pix = ((int64_t)c * in.height + y) * in.width + x;
+            if (out.indices != nullptr) {
+                out.indices[3 * r + 0] = cam;
+                out.indices[3 * r + 1] = y;
+                out.indices[3 * r + 2] = x;
             }
-        }
-        if (in.image != nullptr && out.image != nullptr && lane < C) {
-            out.image[r * C + lane] = in.image_dtype == UMHS_DTYPE_U8
-                ? (float)__ldg(reinterpret_cast<const uint8_t *>(in.image) + pix * C + lane) / 255.0f
-                : __ldg(reinterpret_cast<const float *>(in.image) + pix * C + lane);
-        }
-        if (out.indices != nullptr && lane < 3) out.indices[3 * r + lane] = lane == 0 ? cam : (lane == 1 ? y : x);
-        // ---- camera ray through the pixel centre (Cameras.generate_rays, perspective)
-        if (in.c2w != nullptr) {
-            const float4 k = __ldg(reinterpret_cast<const float4 *>(in.intrinsics) + cam);  // fx, fy, cx, cy
-            const float *M = in.c2w + cam * 12;
-            const float px = (float)x + 0.5f, py = (float)y + 0.5f;
-            // three rays: the pixel's, one pixel to the right, one pixel down (for the pixel area)
-            const float cxs[3] = {(px - k.z) / k.x, (px - k.z + 1.0f) / k.x, (px - k.z) / k.x};
-            const float cys[3] = {-(py - k.w) / k.y, -(py - k.w) / k.y, -(py - k.w + 1.0f) / k.y};
-            float m[12];
+            if (in.image != nullptr && out.image != nullptr) {
+                for (int ch = 0; ch < C; ++ch)
+                    out.image[r * C + ch] = in.image_dtype == UMHS_DTYPE_U8
+                        ? (float)__ldg(reinterpret_cast<const uint8_t *>(in.image) + pix * C + ch) / 255.0f
+                        : __ldg(reinterpret_cast<const float *>(in.image) + pix * C + ch);
+            }
+            // ---- camera ray through the pixel centre (Cameras.generate_rays, perspective)
+            if (in.c2w != nullptr) {
+                const float4 k = __ldg(reinterpret_cast<const float4 *>(in.intrinsics) + cam);  // fx, fy, cx, cy
+                const float *M = in.c2w + cam * 12;
+                const float px = (float)x + 0.5f, py = (float)y + 0.5f;
+                // three rays: the pixel's, one pixel to the right, one pixel down (for the pixel area)
+                const float cxs[3] = {(px - k.z) / k.x, (px - k.z + 1.0f) / k.x, (px - k.z) / k.x};
+                const float cys[3] = {-(py - k.w) / k.y, -(py - k.w) / k.y, -(py - k.w + 1.0f) / k.y};
+                float m[12];
 #pragma unroll
-            for (int i = 0; i < 12; ++i) m[i] = __ldg(M + i);
-            float d[3][3], nrm0 = 0.f;
+                for (int i = 0; i < 12; ++i) m[i] = __ldg(M + i);
+                float d[3][3], nrm0 = 0.f;
 #pragma unroll
-            for (int v = 0; v < 3; ++v) {
-                float w[3], s = 0.f;
+                for (int v = 0; v < 3; ++v) {
+                    float w[3], s = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        w[i] = (cxs[v] * m[4 * i + 0] + cys[v] * m[4 * i + 1]) + (-1.0f) * m[4 * i + 2];
+                        s += w[i] * w[i];
+                    }
+                    const float n = fmaxf(sqrtf(s), 1e-10f);
+                    if (v == 0) nrm0 = sqrtf(s);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) d[v][i] = w[i] / n;
+                }
+                float dx = 0.f, dy = 0.f;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    w[i] = (cxs[v] * m[4 * i + 0] + cys[v] * m[4 * i + 1]) + (-1.0f) * m[4 * i + 2];
-                    s += w[i] * w[i];
+                    dx += (d[0][i] - d[1][i]) * (d[0][i] - d[1][i]);
+                    dy += (d[0][i] - d[2][i]) * (d[0][i] - d[2][i]);
                 }
-                const float n = fmaxf(sqrtf(s), 1e-10f);
-                if (v == 0) nrm0 = sqrtf(s);
 #pragma unroll
-                for (int i = 0; i < 3; ++i) d[v][i] = w[i] / n;
-            }
-            float dx = 0.f, dy = 0.f;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                dx += (d[0][i] - d[1][i]) * (d[0][i] - d[1][i]);
-                dy += (d[0][i] - d[2][i]) * (d[0][i] - d[2][i]);
-            }
-            if (lane < 3) {
-                if (out.origins) out.origins[3 * r + lane] = lane == 0 ? m[3] : (lane == 1 ? m[7] : m[11]);
-                if (out.directions) out.directions[3 * r + lane] = lane == 0 ? d[0][0] : (lane == 1 ? d[0][1] : d[0][2]);
-            }
-            if (lane == 0) {
+                for (int i = 0; i < 3; ++i) {
+                    if (out.origins) out.origins[3 * r + i] = m[4 * i + 3];
+                    if (out.directions) out.directions[3 * r + i] = d[0][i];
+                }
                 if (out.pixel_area) out.pixel_area[r] = sqrtf(dx) * sqrtf(dy);
                 if (out.directions_norm) out.directions_norm[r] = nrm0;
+            }
+        }
+        // ---- spectra of the 32 pixels: one contiguous row each
+        if (hs != nullptr && out.hs_image != nullptr) {
+            const int64_t left = in.n_rays - base;
+            const int m32 = left < rpw ? (int)left : rpw;
+#pragma unroll 4
+            for (int j = 0; j < m32; ++j) {
+                const int64_t pj = __shfl_sync(kFull, pix, j);
+                const T *src = hs + pj * B;
+                float *dst = out.hs_image + (base + j) * B;
+                if (vec) {
+                    for (int q = lane; 4 * q < B; q += 32) reinterpret_cast<float4 *>(dst)[q] = load4<DT>(src, q);
+                } else {
+                    for (int b = lane; b < B; b += 32) dst[b] = HsElem<DT>::get(src, b);
+                }
             }
         }
     }
@@ -156,8 +177,10 @@ extern "C" int umhs_sample_batch(const umhs_batch_in *in, const umhs_batch_out *
     UMHS_CHECK_ARG(in->image == nullptr || in->image_dtype == UMHS_DTYPE_F32 || in->image_dtype == UMHS_DTYPE_U8,
                    "image must be fp32 or uint8");
     UMHS_CHECK_ARG(in->c2w == nullptr || in->intrinsics != nullptr, "cameras need intrinsics");
-    const int64_t want = (in->n_rays + kBatchWarps - 1) / kBatchWarps;
-    const int64_t cap = (int64_t)kNumSMs * 6;  // 40 registers: 6 CTAs of 8 warps per SM
+    // measured at 128 fp32 bands: 32 rays per warp 3.9 TB/s at 262 k rays but 30 us at 16 k rays (one ray per warp: 18 us)
+    const int rpw = in->n_rays >= 131072 ? 32 : (in->n_rays >= 32768 ? 8 : 4);
+    const int64_t want = (in->n_rays + kBatchWarps * rpw - 1) / (kBatchWarps * rpw);
+    const int64_t cap = (int64_t)kNumSMs * 16;
     const int grid = (int)(want < cap ? want : cap);
     const uintptr_t a_in = reinterpret_cast<uintptr_t>(in->hs), a_out = reinterpret_cast<uintptr_t>(out->hs_image);
     const bool b4 = in->num_bands % 4 == 0;
@@ -165,15 +188,15 @@ extern "C" int umhs_sample_batch(const umhs_batch_in *in, const umhs_batch_out *
     switch (in->hs_dtype) {
         case UMHS_DTYPE_F32:
             sample_batch_kernel<UMHS_DTYPE_F32><<<grid, kBatchThreads, 0, st>>>(
-                *in, *out, b4 && a_in % 16 == 0 && a_out % 16 == 0);
+                *in, *out, b4 && a_in % 16 == 0 && a_out % 16 == 0, rpw);
             break;
         case UMHS_DTYPE_F16:
             sample_batch_kernel<UMHS_DTYPE_F16><<<grid, kBatchThreads, 0, st>>>(
-                *in, *out, b4 && a_in % 8 == 0 && a_out % 16 == 0);
+                *in, *out, b4 && a_in % 8 == 0 && a_out % 16 == 0, rpw);
             break;
         case UMHS_DTYPE_BF16:
             sample_batch_kernel<UMHS_DTYPE_BF16><<<grid, kBatchThreads, 0, st>>>(
-                *in, *out, b4 && a_in % 8 == 0 && a_out % 16 == 0);
+                *in, *out, b4 && a_in % 8 == 0 && a_out % 16 == 0, rpw);
             break;
         default:
             UMHS_CHECK_ARG(false, "hs_dtype must be UMHS_DTYPE_F32 / F16 / BF16");
