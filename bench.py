@@ -313,6 +313,10 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the contract is ONE JSON line on stdout: NCCL_DEBUG=VERSION (set in this image) makes NCCL print its version
+        # there; INFO / TRACE asked for by a user are left alone
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = umhs_b200.UMHSConfig(method="rgb+spectral", temperature=TEMPERATURE, pred_specular=False,
