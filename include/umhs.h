@@ -225,6 +225,14 @@ typedef struct {
 
 int umhs_composite_fwd(const umhs_composite_in *in, const umhs_composite_out *out, void *stream);
 int umhs_depth_clip(float *depth, int64_t n_rays, const float *t_minmax, void *stream);
+/* Evaluation: the reference renders an image as separate 512-ray forward calls (ref umhsnerf/umhs_model.py:605-616,
+ * eval_num_rays_per_chunk of ref umhs_config.py:50), so nerfstudio's DepthRenderer clips every call's depth to that
+ * call's own [min, max] sample mid-point.  A fused whole-image pass reproduces it: chunk(r) = (ray_ids ? ray_ids[r] : r)
+ * / chunk_rays; bounds [n_chunks,2] caller-initialised to (+inf, -inf); a chunk without samples clips to [1, 1]
+ * (nerfstudio's fabricated sample).  depth is clipped in place. */
+int umhs_depth_clip_chunks(float *depth, int64_t n_rays, const int64_t *packed_info, const float *t_starts,
+                           const float *t_ends, const int64_t *ray_ids, int64_t chunk_rays, float *bounds,
+                           void *stream);
 int umhs_composite_bwd(const umhs_composite_in *in, const umhs_composite_grads_in *gin,
                        const umhs_composite_grads_out *gout, void *stream);
 
@@ -353,14 +361,16 @@ int umhs_sample_batch(const umhs_batch_in *in, const umhs_batch_out *out, void *
  * umhsnerf/umhs_model.py:329-383: 5 * MSE(spectral, hs_image) + w * MSE(rgb blended over a background, image
  * blended over the same background)) and the autograd backward of those ~15 elementwise / reduction launches.
  * losses [2] = (spectral_loss, rgb_loss); d_* = d(sum of losses)/d(spectral | rgb | accumulation), the inputs
- * of umhs_composite_bwd.  background [R,3] (the reference draws it with rand_like; NULL = black);
- * image [R,3] or [R,4] (RGBA: blended over the background as nerfstudio's blend_background does).
+ * of umhs_composite_bwd.  background [R,3] (NULL = black); blend_pred = 1 (background_color "random": the
+ * reference draws it with rand_like and adds background * (1 - accumulation) to the prediction) or 0 (named
+ * colours: nerfstudio leaves the prediction alone); image [R,3] or [R,4] (RGBA: blended over the background as
+ * nerfstudio's blend_background does, in both cases).
  * w_rgb = 0 (method "spectral"): the rgb term and its buffers are skipped.
  * ------------------------------------------------------------------------------- */
 int umhs_train_loss(int64_t n_rays, int32_t num_bands, int32_t image_channels, const float *spectral,
                     const float *hs_image, const float *rgb, const float *accumulation, const float *image,
-                    const float *background, float w_spectral, float w_rgb, float *losses, float *d_spectral,
-                    float *d_rgb, float *d_accumulation, void *stream);
+                    const float *background, int32_t blend_pred, float w_spectral, float w_rgb, float *losses,
+                    float *d_spectral, float *d_rgb, float *d_accumulation, void *stream);
 
 /* ---------------------------------------------------------------------------------
  * Optimiser: dense Adam over one flat fp32 parameter buffer (torch.optim.Adam

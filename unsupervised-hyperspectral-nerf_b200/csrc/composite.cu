@@ -644,6 +644,48 @@ extern "C" int umhs_depth_clip(float *depth, int64_t n_rays, const float *t_minm
     return UMHS_OK;
 }
 
+// ---- chunk-wise depth clip (evaluation).  The reference renders an image as ceil(H W / 512) separate forward calls
+// (ref umhs_model.py:605-616, eval_num_rays_per_chunk: ref umhs_config.py:50) and nerfstudio's DepthRenderer clips each
+// call's expected depth to that CALL's [min, max] of the sample mid-points; a fused whole-image pass has to reproduce the
+// per-chunk bounds.  Samples are sorted along their ray, so a ray's extremes are its first and last sample.
+// chunk(ray r) = (ray_ids ? ray_ids[r] : r) / chunk_rays  (ray_ids: row-major pixel ids when rays arrive in tile order)
+__global__ void depth_chunk_bounds_kernel(int64_t R, const int64_t *__restrict__ packed_info, const float *__restrict__ t0,
+                                          const float *__restrict__ t1, const int64_t *__restrict__ ray_ids,
+                                          int64_t chunk_rays, float *__restrict__ bounds) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int64_t start = packed_info[2 * r], cnt = packed_info[2 * r + 1];
+    if (cnt <= 0) return;
+    const int64_t c = (ray_ids ? ray_ids[r] : r) / chunk_rays;
+    const float lo = (t0[start] + t1[start]) / 2.0f, hi = (t0[start + cnt - 1] + t1[start + cnt - 1]) / 2.0f;
+    // non-negative floats order like their bit patterns
+    atomicMin(reinterpret_cast<int *>(bounds) + 2 * c, __float_as_int(lo));
+    atomicMax(reinterpret_cast<int *>(bounds) + 2 * c + 1, __float_as_int(hi));
+}
+__global__ void depth_chunk_clip_kernel(int64_t R, const int64_t *__restrict__ ray_ids, int64_t chunk_rays,
+                                        const float *__restrict__ bounds, float *__restrict__ depth) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int64_t c = (ray_ids ? ray_ids[r] : r) / chunk_rays;
+    float lo = bounds[2 * c], hi = bounds[2 * c + 1];
+    // a call without any sample: nerfstudio's VolumetricSampler fabricates one sample at t0 = t1 = 1
+    if (lo > hi) lo = hi = 1.0f;
+    depth[r] = fminf(fmaxf(depth[r], lo), hi);
+}
+
+extern "C" int umhs_depth_clip_chunks(float *depth, int64_t n_rays, const int64_t *packed_info, const float *t_starts,
+                                      const float *t_ends, const int64_t *ray_ids, int64_t chunk_rays, float *bounds,
+                                      void *stream) {
+    UMHS_CHECK_ARG(depth && packed_info && t_starts && t_ends && bounds && chunk_rays > 0, "bad argument");
+    if (n_rays <= 0) return UMHS_OK;
+    depth_chunk_bounds_kernel<<<div_up(n_rays, 256), 256, 0, as_stream(stream)>>>(n_rays, packed_info, t_starts, t_ends,
+                                                                                 ray_ids, chunk_rays, bounds);
+    UMHS_CHECK_LAUNCH();
+    depth_chunk_clip_kernel<<<div_up(n_rays, 256), 256, 0, as_stream(stream)>>>(n_rays, ray_ids, chunk_rays, bounds, depth);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
 extern "C" int umhs_composite_bwd(const umhs_composite_in *in, const umhs_composite_grads_in *gin,
                                   const umhs_composite_grads_out *gout, void *stream) {
     UMHS_CHECK_ARG(check_in(in) == 0, "bad composite input");

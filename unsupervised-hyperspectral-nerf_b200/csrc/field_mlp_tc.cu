@@ -308,8 +308,13 @@ __device__ __forceinline__ void issuer_rotation(uint64_t *bars, const int64_t (&
                         // `it >> 40` is zero, but not provably so: the descriptors of a round are then recomputed in
                         // the uniform datapath (a couple of UIADD3 per MMA) instead of being hoisted out of the tile
                         // loop into ~50 vector registers that need an R2UR each before every tcgen05.mma
-                        issue(rc, gc, (it == 0 && g == 0) ? 0u : 1u, (uint32_t)(it >> 40));
+                        // Phase 0: the MMAs the group's next epilogue waits for (forward / dgrad), committed at once;
+                        // phase 1: MMAs nobody waits for (weight gradients into the persistent accumulators) go out
+                        // BEHIND the commit, while the group already runs its epilogue.  The next commit of this thread
+                        // covers them, so an operand tile they read may be overwritten one round later, not earlier.
+                        issue(rc, gc, (it == 0 && g == 0) ? 0u : 1u, (uint32_t)(it >> 40), std::integral_constant<int, 0>{});
                         commit(bars + G + g);
+                        issue(rc, gc, (it == 0 && g == 0) ? 0u : 1u, (uint32_t)(it >> 40), std::integral_constant<int, 1>{});
                     }
                     __syncwarp();
                     tr.stamp(1000 + 100 * g + decltype(rc)::value);
@@ -379,8 +384,9 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             n_iter[g] = first < n_tiles ? (n_tiles - 1 - first) / stride + 1 : 0;
         }
         const uint32_t sbase = smem_u32(smem);
-        issuer_rotation<G, ROUNDS>(bars, n_iter, Tracer(false, 1), [&](auto rc, auto gc, uint32_t, uint32_t zero) {
+        issuer_rotation<G, ROUNDS>(bars, n_iter, Tracer(false, 1), [&](auto rc, auto gc, uint32_t, uint32_t zero, auto ph) {
             constexpr int r = decltype(rc)::value, g = decltype(gc)::value;
+            if constexpr (decltype(ph)::value != 0) return;  // the forward has no deferred MMAs
             const uint32_t sb = sbase + zero;
             const WAddr w(sb);
             const uint32_t b = sb + (uint32_t)(TcSmem::groups + g * GRP_BYTES);
@@ -659,8 +665,9 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         const uint32_t sbase = smem_u32(smem);
         const bool want_denc = d_enc != nullptr;
         issuer_rotation<G, TcBwd::kRounds>(bars, n_iter, Tracer(lane == 0, 1), [&](auto rc, auto gc, uint32_t acc,
-                                                                                  uint32_t zero) {
+                                                                                  uint32_t zero, auto ph) {
             constexpr int r = decltype(rc)::value, q = decltype(gc)::value;
+            constexpr bool crit = decltype(ph)::value == 0, late = !crit;  // before / behind the round's commit
             const uint32_t sb = sbase + zero;
             const WAddr w(sb);
             const uint32_t b = sb + (uint32_t)(TcSmem::groups + q * TcBwd::grp_bytes);
@@ -668,53 +675,68 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             const uint32_t sD1 = b + TcBwd::tD1, sD2 = b + TcBwd::tD2, sX2 = sD1;
             const uint32_t tw = tbase + 64u * q;
             if constexpr (r == 0) {         // base layer 0
-                gemm_kmajor(tw, sA0, w.b0, 64, 0, 64, 32, 0);
-                gemm_bias_step(tw, w.ones, w.b0, 64, 0, 64, COL_B_BASE0);
+                if (crit) {
+                    gemm_kmajor(tw, sA0, w.b0, 64, 0, 64, 32, 0);
+                    gemm_bias_step(tw, w.ones, w.b0, 64, 0, 64, COL_B_BASE0);
+                }
             } else if constexpr (r == 1) {  // base layer 1 (N=16) [+ mlp_directional layer 0 at working columns 16..31]
-                gemm_kmajor(tw, sH1, w.b1, 16, 0, 16, 64, 0);
-                gemm_bias_step(tw, w.ones, w.b1, 16, 0, 16, COL_B_64);
-                if (spec) gemm_kmajor(tw + 16, sX2, w.d0, 16, 0, 16, 32, 0);
+                if (crit) {
+                    gemm_kmajor(tw, sH1, w.b1, 16, 0, 16, 64, 0);
+                    gemm_bias_step(tw, w.ones, w.b1, 16, 0, 16, COL_B_64);
+                    if (spec) gemm_kmajor(tw + 16, sX2, w.d0, 16, 0, 16, 32, 0);
+                }
             } else if constexpr (r == 2) {  // mlp_head layer 0 [+ wgrad of mlp_directional layer 0]
-                gemm_kmajor(tw, sX, w.hf0, 128, 0, 64, 32, 0);
-                if (spec) gemm_wgrad(tbase + TcBwd::P_d0, sD2, 0, sX2, 0, 32, acc);
+                if (crit) gemm_kmajor(tw, sX, w.hf0, 128, 0, 64, 32, 0);
+                if (late && spec) gemm_wgrad(tbase + TcBwd::P_d0, sD2, 0, sX2, 0, 32, acc);
             } else if constexpr (r == 3) {
-                gemm_kmajor(tw, sH1, w.h1, 64, 0, 64, 64, 0);
-                gemm_bias_step(tw, w.ones, w.h1, 64, 0, 64, COL_B_64);
+                if (crit) {
+                    gemm_kmajor(tw, sH1, w.h1, 64, 0, 64, 64, 0);
+                    gemm_bias_step(tw, w.ones, w.h1, 64, 0, 64, COL_B_64);
+                }
             } else if constexpr (r == 4) {
-                gemm_kmajor(tw, sH2, w.h2, 16, 0, 16, 64, 0);
-                gemm_bias_step(tw, w.ones, w.h2, 16, 0, 16, COL_B_64);
+                if (crit) {
+                    gemm_kmajor(tw, sH2, w.h2, 16, 0, 16, 64, 0);
+                    gemm_bias_step(tw, w.ones, w.h2, 16, 0, 16, COL_B_64);
+                }
             } else if constexpr (r == 5) {
-                gemm_dgrad(tw, sD2, w.h2, 16, 0, 64, 16, 0);
-                gemm_wgrad(tbase + TcBwd::P_h2t, sH2, 0, sD2, 0, 16, acc);
+                if (crit) gemm_dgrad(tw, sD2, w.h2, 16, 0, 64, 16, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_h2t, sH2, 0, sD2, 0, 16, acc);
             } else if constexpr (r == 6) {
-                gemm_dgrad(tw, sD1, w.h1, 64, 0, 64, 64, 0);
-                gemm_wgrad(tbase + TcBwd::P_h1, sD1, 0, sH1, 0, 72, acc);  // 64 + ones
+                if (crit) gemm_dgrad(tw, sD1, w.h1, 64, 0, 64, 64, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_h1, sD1, 0, sH1, 0, 72, acc);  // 64 + ones
             } else if constexpr (r == 7) {
-                gemm_dgrad(tw, sD2, w.hf0, 128, 0, 32, 64, 0);
-                gemm_wgrad(tbase + TcBwd::P_h0, sD2, 0, sX, 0, 32, acc);   // column 27 = ones
+                if (crit) gemm_dgrad(tw, sD2, w.hf0, 128, 0, 32, 64, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_h0, sD2, 0, sX, 0, 32, acc);   // column 27 = ones
             } else if constexpr (r == 8) {  // feature_mlp layer 0
-                gemm_kmajor(tw, sX, w.hf0, 128, 64, 64, 32, 0);
+                if (crit) gemm_kmajor(tw, sX, w.hf0, 128, 64, 64, 32, 0);
             } else if constexpr (r == 9) {
-                gemm_kmajor(tw, sH1, w.f1, 64, 0, 64, 64, 0);
-                gemm_bias_step(tw, w.ones, w.f1, 64, 0, 64, COL_B_64);
+                if (crit) {
+                    gemm_kmajor(tw, sH1, w.f1, 64, 0, 64, 64, 0);
+                    gemm_bias_step(tw, w.ones, w.f1, 64, 0, 64, COL_B_64);
+                }
             } else if constexpr (r == 10) {
-                gemm_kmajor(tw, sH2, w.f2, 32, 0, 32, 64, 0);
-                gemm_bias_step(tw, w.ones, w.f2, 32, 0, 32, COL_B_64);
+                if (crit) {
+                    gemm_kmajor(tw, sH2, w.f2, 32, 0, 32, 64, 0);
+                    gemm_bias_step(tw, w.ones, w.f2, 32, 0, 32, COL_B_64);
+                }
             } else if constexpr (r == 11) {
-                gemm_dgrad(tw, sD2, w.f2, 32, 0, 64, 32, 0);
-                gemm_wgrad(tbase + TcBwd::P_f2t, sH2, 0, sD2, 0, 32, acc);
+                if (crit) gemm_dgrad(tw, sD2, w.f2, 32, 0, 64, 32, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_f2t, sH2, 0, sD2, 0, 32, acc);
             } else if constexpr (r == 12) {
-                gemm_dgrad(tw, sD1, w.f1, 64, 0, 64, 64, 0);
-                gemm_wgrad(tbase + TcBwd::P_f1, sD1, 0, sH1, 0, 72, acc);
+                if (crit) gemm_dgrad(tw, sD1, w.f1, 64, 0, 64, 64, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_f1, sD1, 0, sH1, 0, 72, acc);
             } else if constexpr (r == 13) {
-                gemm_dgrad(tw, sD2, w.hf0, 128, 64, 32, 64, 0);
-                gemm_wgrad(tbase + TcBwd::P_f0, sD2, 0, sX, 0, 32, acc);
-            } else if constexpr (r == 14) {  // base layer 1 backward (H0 is back in tH1)
-                gemm_dgrad(tw, sD2, w.b1, 16, 0, 64, 16, 0);
-                gemm_wgrad(tbase + TcBwd::P_b1t, sH1, 0, sD2, 0, 16, acc);
-            } else {                         // 15: base layer 0 backward (wgrad N = 32 + ones chunk)
-                if (want_denc) gemm_dgrad(tw, sD1, w.b0, 64, 0, 32, 64, 0);
-                gemm_wgrad(tbase + TcBwd::P_b0, sD1, 0, sA0, 0, 40, acc);
+                if (crit) gemm_dgrad(tw, sD2, w.hf0, 128, 64, 32, 64, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_f0, sD2, 0, sX, 0, 32, acc);
+            } else if constexpr (r == 14) {  // base layer 1 backward (H0 is back in tH1; d [o0, emb] sits in tD1)
+                if (crit) gemm_dgrad(tw, sD1, w.b1, 16, 0, 64, 16, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_b1t, sH1, 0, sD1, 0, 16, acc);
+            } else {                         // 15: base layer 0 backward (wgrad N = 32 + ones chunk), delta in tD2
+                // its weight gradient reads tA0, which the NEXT tile's first epilogue overwrites: not deferred
+                if (crit) {
+                    if (want_denc) gemm_dgrad(tw, sD2, w.b0, 64, 0, 32, 64, 0);
+                    gemm_wgrad(tbase + TcBwd::P_b0, sD2, 0, sA0, 0, 40, acc);
+                }
             }
         });
         __syncwarp();
@@ -926,8 +948,9 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                 dO[0] = dsg * pt.sel * __expf(fminf(fmaxf(o16[0], -15.0f), 15.0f));
 #pragma unroll
                 for (int i = 0; i < 15; ++i) dO[1 + i] = demb[i];
-                store8(tD2, row, 0, CH_ACT, dO);
-                store8(tD2, row, 8, CH_ACT, dO + 8);
+                // (tD1, not tD2: the deferred weight-gradient MMAs of round 13 may still be reading tD2)
+                store8(tD1, row, 0, CH_ACT, dO);
+                store8(tD1, row, 8, CH_ACT, dO + 8);
                 bs_b1 += warp_colsum<16>(dO, lane);
                 // H0 back into tH1 (operand of the base layer-1 weight gradient)
 #pragma unroll
@@ -936,13 +959,13 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                         make_uint4(h0p[4 * c], h0p[4 * c + 1], h0p[4 * c + 2], h0p[4 * c + 3]);
             }
             gs.round_trip();
-            epi_mask64(trow, nullptr, h0p, tD1, row);
+            epi_mask64(trow, nullptr, h0p, tD2, row);
             gs.round_trip();
             if (d_enc) {
-                // whole rows, coalesced, through this warp's 4 KB of the (now idle) tD2 tile
+                // whole rows, coalesced, through this warp's 4 KB of the (now idle) tD1 tile
                 float v[32];
                 tmem_ld32(trow, v);
-                store_rows_coalesced(d_enc, valid ? n : -1, v, tD2 + (warp & 3) * 4096, lane);
+                store_rows_coalesced(d_enc, valid ? n : -1, v, tD1 + (warp & 3) * 4096, lane);
             }
         }
         if (colsum_owner<KM>(lane)) {  // one lane of each run owns column colsum_col<KM>(lane)

@@ -1,9 +1,10 @@
 // loss.cu -- the training losses of ref umhsnerf/umhs_model.py:329-383 and their gradients in ONE pass.
 //
 //   spectral_loss = w_spec * mean((spectral - hs_image)^2)                      (ref :369; w_spec = 5, quirk 4)
-//   rgb_loss      = w_rgb  * mean((rgb + bg (1 - acc) - blend(image, bg))^2)    (ref :358-362, :370;
-//                   nerfstudio RGBRenderer.blend_background_for_loss_computation: a 4-channel image is
-//                   alpha-blended over the same background)
+//   rgb_loss      = w_rgb  * mean((rgb [+ bg (1 - acc)] - blend(image, bg))^2)  (ref :358-362, :370;
+//                   nerfstudio RGBRenderer.blend_background_for_loss_computation: the prediction is blended over
+//                   the background only when that background is the per-step RANDOM draw (blend_pred = 1); a named
+//                   colour (white / black) only blends a 4-channel ground-truth image (blend_pred = 0))
 // The reference evaluates this with ~15 elementwise / reduction launches forward and backward.  The gradients of a
 // scalar loss do not depend on anything but these same inputs, so the kernel writes d loss / d spectral,
 // d loss / d rgb and d loss / d accumulation right away; the host feeds them to the compositing backward.
@@ -17,7 +18,7 @@ constexpr int kLossThreads = 256;
 __global__ void __launch_bounds__(kLossThreads)
 train_loss_kernel(int64_t R, int B, int image_channels, const float *__restrict__ spectral,
                   const float *__restrict__ hs_image, const float *__restrict__ rgb, const float *__restrict__ acc,
-                  const float *__restrict__ image, const float *__restrict__ bg, float w_spec, float w_rgb,
+                  const float *__restrict__ image, const float *__restrict__ bg, int blend_pred, float w_spec, float w_rgb,
                   float *__restrict__ losses, float *__restrict__ d_spectral, float *__restrict__ d_rgb,
                   float *__restrict__ d_acc) {
     __shared__ float red[2][kLossThreads / 32];
@@ -51,7 +52,8 @@ train_loss_kernel(int64_t R, int B, int image_channels, const float *__restrict_
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float b = bg ? __ldg(bg + 3 * r + c) : 0.f;
-                const float pred = rgb[3 * r + c] + b * (1.0f - a);
+                const float bp = blend_pred ? b : 0.f;  // background under the prediction: random draws only
+                const float pred = rgb[3 * r + c] + bp * (1.0f - a);
                 float gt = __ldg(image + image_channels * r + c);
                 if (image_channels == 4) {
                     const float al = __ldg(image + 4 * r + 3);
@@ -60,7 +62,7 @@ train_loss_kernel(int64_t R, int B, int image_channels, const float *__restrict_
                 const float d = pred - gt;
                 s_rgb += d * d;
                 d_rgb[3 * r + c] = gr * d;
-                da -= gr * d * b;
+                da -= gr * d * bp;
             }
             d_acc[r] = da;
         }
@@ -89,8 +91,8 @@ using namespace umhs;
 
 extern "C" int umhs_train_loss(int64_t n_rays, int32_t num_bands, int32_t image_channels, const float *spectral,
                                const float *hs_image, const float *rgb, const float *accumulation,
-                               const float *image, const float *background, float w_spectral, float w_rgb,
-                               float *losses, float *d_spectral, float *d_rgb, float *d_accumulation, void *stream) {
+                               const float *image, const float *background, int32_t blend_pred, float w_spectral,
+                               float w_rgb, float *losses, float *d_spectral, float *d_rgb, float *d_accumulation, void *stream) {
     UMHS_CHECK_ARG(spectral && hs_image && losses && d_spectral, "null argument");
     UMHS_CHECK_ARG(w_rgb == 0.0f || (rgb && accumulation && image && d_rgb && d_accumulation), "rgb term needs its buffers");
     UMHS_CHECK_ARG(image_channels == 3 || image_channels == 4, "image must have 3 or 4 channels");
@@ -100,8 +102,8 @@ extern "C" int umhs_train_loss(int64_t n_rays, int32_t num_bands, int32_t image_
     const int64_t want = (n_rays * num_bands / 4 + kLossThreads - 1) / kLossThreads;
     const int grid = (int)(want < kNumSMs * 4 ? (want < 1 ? 1 : want) : kNumSMs * 4);
     train_loss_kernel<<<grid, kLossThreads, 0, as_stream(stream)>>>(n_rays, num_bands, image_channels, spectral, hs_image,
-                                                                  rgb, accumulation, image, background, w_spectral,
-                                                                  w_rgb, losses, d_spectral, d_rgb, d_accumulation);
+                                                                  rgb, accumulation, image, background, blend_pred,
+                                                                  w_spectral, w_rgb, losses, d_spectral, d_rgb, d_accumulation);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }

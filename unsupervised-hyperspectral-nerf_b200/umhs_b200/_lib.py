@@ -113,6 +113,7 @@ _SIGNATURES = {
     "umhs_tc05_microbench": [c_int32, c_int32, c_int32, c_int32, P, P],
     "umhs_composite_fwd": [POINTER(CompositeIn), POINTER(CompositeOut), P],
     "umhs_depth_clip": [P, c_int64, P, P],
+    "umhs_depth_clip_chunks": [P, c_int64, P, P, P, P, c_int64, P, P],
     "umhs_composite_bwd": [POINTER(CompositeIn), POINTER(CompositeGradsIn), POINTER(CompositeGradsOut), P],
     "umhs_unmix_fwd": [c_int64, c_int32, c_int32, c_int32, P, P, P, P, P, P, P, P, P, P],
     "umhs_unmix_bwd": [c_int64, c_int32, c_int32, c_int32, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
@@ -136,7 +137,7 @@ _SIGNATURES = {
     "umhs_adam_step_dev": [P, P, P, P, c_int64, c_float, c_float, c_float, P, P, P, c_int64, c_int64, c_int32, P],
     "umhs_reduce_slabs": [P, c_int64, c_int64, c_int64, P, P],
     "umhs_sample_batch": [POINTER(BatchIn), POINTER(BatchOut), P],
-    "umhs_train_loss": [c_int64, c_int32, c_int32, P, P, P, P, P, P, c_float, c_float, P, P, P, P, P],
+    "umhs_train_loss": [c_int64, c_int32, c_int32, P, P, P, P, P, P, c_int32, c_float, c_float, P, P, P, P, P],
     "umhs_dp_barrier": [P, c_int32, c_int32, c_int32, P, P],
     "umhs_dp_adam_step": [P, P, P, P, c_int64, c_int32, c_int32, c_float, c_float, c_float, P, c_int64, c_int64, P, P,
                           P],

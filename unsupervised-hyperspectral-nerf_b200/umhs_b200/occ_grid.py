@@ -127,7 +127,12 @@ class OccGridEstimator(nn.Module):
             ri, t0, t1, packed, total, self.last_src_index = ops.visibility_compact(
                 packed, t0, t1, sigma, early_stop_eps, alpha_thre, self.occ_mean() if alpha_thre > 0.0 else None,
                 capacity=capacity)
-        self.last_totals = (march_total, total)  # device int64[2] each: (packed, unclamped) candidates / kept
+        # device int64[2] each: (packed, unclamped) candidates / kept.  Training calls only: the trainer's capacity
+        # check reads the LAST TRAINING step's counts (graph replays do not come through here), an evaluation render in
+        # between must not replace them with a whole image's sample count
+        if self.training or not hasattr(self, "last_totals"):
+            self.last_totals = (march_total, total)
+        self.last_eval_totals = (march_total, total)
         if return_packed_info:
             return ri, t0, t1, packed, total
         return ri, t0, t1

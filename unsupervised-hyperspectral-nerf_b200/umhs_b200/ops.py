@@ -20,7 +20,7 @@ ENC_DIM = 32  # 16 levels x 2 features
 # kernels launched per C-ABI entry point (for the bench's gpu_launches count)
 _LAUNCHES = {"umhs_hash_encode_fwd": 1, "umhs_hash_encode_bwd": 1, "umhs_hash_encode_x01_fwd": 1,
              "umhs_hash_encode_x01_bwd": 1, "umhs_density_fwd": 1, "umhs_field_mlp_fwd": 1, "umhs_field_mlp_bwd": 1,
-             "umhs_composite_fwd": 1, "umhs_depth_clip": 1, "umhs_composite_bwd": 1, "umhs_unmix_fwd": 1,
+             "umhs_composite_fwd": 1, "umhs_depth_clip": 1, "umhs_depth_clip_chunks": 2, "umhs_composite_bwd": 1, "umhs_unmix_fwd": 1,
              "umhs_unmix_bwd": 1, "umhs_render_weights_fwd": 1, "umhs_render_weights_bwd": 1,
              "umhs_accumulate_fwd": 1, "umhs_accumulate_bwd": 1, "umhs_march_count": 1, "umhs_march_level_any": 1, "umhs_occ_pack_bits": 1, "umhs_pack_scan": 1,
              "umhs_march_write": 1, "umhs_visibility_mask": 1, "umhs_compact_samples": 1, "umhs_pack_info": 2,
@@ -396,12 +396,21 @@ class CompositeFunction(torch.autograd.Function):
         for k, v in out.items():
             setattr(co, k, ptr(v))
         co.trans = ptr(trans)
-        if want_depth:
+        # depth clip bounds: the whole call (training batches, one reference forward) or, in evaluation, the reference's
+        # 512-ray forward calls: cfg["depth_chunks"] = (chunk_rays, ray_ids | None), see umhs_depth_clip_chunks
+        chunks = cfg.get("depth_chunks") if want_depth else None
+        if want_depth and chunks is None:
             tmm = _tminmax_init(dev).clone()  # (+inf, -inf) without a host->device copy per call
             co.t_minmax = ptr(tmm)
         _call("umhs_composite_fwd", R, ctypes.byref(ci), ctypes.byref(co), stream_ptr(dev))
-        if want_depth:
+        if want_depth and chunks is None:
             _call("umhs_depth_clip", 0, ptr(out["depth"]), R, ptr(tmm), stream_ptr(dev))
+        elif want_depth:
+            chunk_rays, ray_ids = int(chunks[0]), chunks[1]
+            n_chunks = (int(chunks[2]) if len(chunks) > 2 else R) // chunk_rays + 1
+            bounds = _tminmax_init(dev).repeat(n_chunks)
+            _call("umhs_depth_clip_chunks", 0, ptr(out["depth"]), R, ptr(packed_info), ptr(t0), ptr(t1),
+                  ptr(ray_ids), chunk_rays, ptr(bounds), stream_ptr(dev))
         ctx.cfg = cfg
         ctx.save_for_backward(packed_info, t0, t1, sigma, scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1,
                               rgb_matrix, out["spectral"], trans)
@@ -671,8 +680,11 @@ def adam_step_dev(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tens
 
 
 def train_loss(spectral: Tensor, hs_image: Tensor, rgb: Optional[Tensor], accumulation: Optional[Tensor],
-               image: Optional[Tensor], background: Optional[Tensor], w_spectral: float, w_rgb: float):
-    """Both training losses and d(sum)/d(spectral, rgb, accumulation) in one launch.
+               image: Optional[Tensor], background: Optional[Tensor], w_spectral: float, w_rgb: float,
+               blend_pred: bool = True):
+    """Both training losses and d(sum)/d(spectral, rgb, accumulation) in one launch.  ``blend_pred``: the
+    prediction is blended over ``background`` too (nerfstudio does that for background_color="random" only; a named
+    colour blends just an RGBA ground truth).
     -> (losses [2], d_spectral [R,B], d_rgb [R,3] | None, d_accumulation [R] | None)"""
     dev = spectral.device
     R, B = int(spectral.shape[0]), int(spectral.shape[1])
@@ -685,7 +697,7 @@ def train_loss(spectral: Tensor, hs_image: Tensor, rgb: Optional[Tensor], accumu
     keep = [f32(t) if (t is not None and use_rgb) else None for t in (rgb, accumulation, image, background)]
     ch = int(image.shape[-1]) if image is not None else 3
     _call("umhs_train_loss", R, R, B, ch, ptr(sp), ptr(hs), ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]),
-          float(w_spectral), float(w_rgb if use_rgb else 0.0), ptr(losses), ptr(d_spec), ptr(d_rgb), ptr(d_acc),
+          1 if blend_pred else 0, float(w_spectral), float(w_rgb if use_rgb else 0.0), ptr(losses), ptr(d_spec), ptr(d_rgb), ptr(d_acc),
           stream_ptr(dev))
     return losses, d_spec, d_rgb, d_acc
 

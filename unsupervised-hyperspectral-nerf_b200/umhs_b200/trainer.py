@@ -267,14 +267,18 @@ class UMHSTrainer:
             spectral, rgb, acc = outputs["spectral"], outputs["rgb"], outputs["accumulation"]
             w_spec = 1.0 if cfg.method == "spectral" else 5.0  # hard-coded 5 of ref umhs_model.py:369 (quirk 4)
             w_rgb = 0.0 if cfg.method == "spectral" else float(cfg.rgb_loss_weight)
-            if cfg.background_color == "random":
+            # nerfstudio RGBRenderer.blend_background_for_loss_computation: only the RANDOM background is
+            # added to the prediction; a named colour just blends an RGBA ground truth (UMHSModel._blend_background)
+            blend_pred = cfg.background_color == "random"
+            if blend_pred:
                 bg = m._bg_override if m._bg_override is not None else torch.rand_like(rgb)
             else:
-                bg = torch.ones_like(rgb) if cfg.background_color == "white" else None
+                rgba = batch["image"].shape[-1] == 4
+                bg = torch.ones_like(rgb) if (cfg.background_color == "white" and rgba) else None
             dev = spectral.device
             losses, d_spec, d_rgb, d_acc = ops.train_loss(
                 spectral.detach(), batch["hs_image"].to(dev), rgb.detach(), acc.detach().reshape(-1),
-                batch["image"].to(dev), bg, w_spec, w_rgb)
+                batch["image"].to(dev), bg, w_spec, w_rgb, blend_pred=blend_pred)
             tensors, grads = [spectral], [d_spec]
             if d_rgb is not None:
                 tensors += [rgb, acc]
@@ -544,9 +548,11 @@ class UMHSTrainer:
         d = camera_ray_bundle.directions.reshape(-1, 3).to(dev)[index]
         out: Dict[str, List[Tensor]] = {}
         step = int(m.config.eval_tile_rays)
+        chunk = int(m.config.eval_num_rays_per_chunk)  # depth is clipped per reference forward call (512 row-major rays)
         for s in range(0, index.numel(), step):
             rb = RayBundle(origins=o[s:s + step].contiguous(), directions=d[s:s + step].contiguous())
-            res = m.get_outputs(m.collider(rb), per_band_views=False)
+            res = m.get_outputs(m.collider(rb), per_band_views=False,
+                                depth_chunks=(chunk, index[s:s + step].contiguous(), H * W))
             for k, v in res.items():
                 out.setdefault(k, []).append(v.reshape(v.shape[0], -1))
         result = {k: torch.cat(v) for k, v in out.items()}

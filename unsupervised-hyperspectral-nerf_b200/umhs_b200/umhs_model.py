@@ -131,6 +131,9 @@ class UMHSModel(nn.Module):
         self.sampler = VolumetricSampler(occupancy_grid=self.occupancy_grid, field=self.field)
         self.cluster_probe = ClusterLookup(len(wl), K)
         self._bg_override: Optional[Tensor] = None  # test hook: fixes the "random" background draw
+        # test hook: fixes the stratified near-plane draw of the sampler ([R] in [0,1); nerfacc: rand_like(near_planes));
+        # a persistent device tensor, so a captured step graph sees what a test writes into it between replays
+        self._jitter_override: Optional[Tensor] = None
         # None: exact-sized sample buffers (host sync on the sample count, reference behaviour).
         # int: sync-free steps on capacity-sized buffers (set by UMHSTrainer; see VolumetricSampler).
         self.sample_capacity: Optional[int] = None
@@ -163,18 +166,25 @@ class UMHSModel(nn.Module):
         cfg = self.config
         if ray_bundle.nears is None:
             ray_bundle = self.collider(ray_bundle)
+        if jitter is None:
+            jitter = self._jitter_override
         return self.sampler.march_only(
             ray_bundle, render_step_size=cfg.render_step_size, near_plane=cfg.near_plane, far_plane=cfg.far_plane,
             cone_angle=cfg.cone_angle, jitter=jitter, capacity=self.sample_capacity if self.training else None)
 
     def get_outputs(self, ray_bundle: RayBundle, jitter: Optional[Tensor] = None,
-                    per_band_views: bool = True, premarched=None, lean: bool = False) -> Dict[str, Tensor]:
+                    per_band_views: bool = True, premarched=None, lean: bool = False,
+                    depth_chunks=None) -> Dict[str, Tensor]:
         """lean=True (the standalone trainer): no "depth" entry and no per-sample weights by-product -- nothing in
-        the training losses reads them (ref umhs_model.py:329-383) -- which saves three launches per step."""
+        the training losses reads them (ref umhs_model.py:329-383) -- which saves three launches per step.
+        depth_chunks=(chunk_rays, ray_ids | None, n_image_rays): the full-image drivers render many of the reference's
+        512-ray forward calls in one pass; the depth clip then uses each call's own bounds (ops.CompositeFunction)."""
         cfg = self.config
         num_rays = int(ray_bundle.origins.reshape(-1, 3).shape[0])
         if ray_bundle.nears is None:
             ray_bundle = self.collider(ray_bundle)
+        if jitter is None:
+            jitter = self._jitter_override
         pts, ray_indices, t0, t1, packed_info = self.sampler(
             ray_bundle=ray_bundle, near_plane=cfg.near_plane, far_plane=cfg.far_plane,
             render_step_size=cfg.render_step_size, alpha_thre=cfg.alpha_thre, cone_angle=cfg.cone_angle,
@@ -184,7 +194,7 @@ class UMHSModel(nn.Module):
         K, B, spec = self.field.num_classes, self.field.wavelengths, cfg.pred_specular
         d = self.field.mlp_directional.layers
         ccfg = {"K": K, "B": B, "specular": spec, "grad_scaling": cfg.use_gradient_scaling, "want_weights": not lean,
-                "want_depth": not lean}
+                "want_depth": not lean, "depth_chunks": depth_chunks}
         (spectral, spectral2, specular, abund, acc, depth, rgb, seg_probs, seg_raw, seg_pred,
          weights) = ops.CompositeFunction.apply(
             ccfg, packed_info, t0, t1, fo["sigma"], fo["scalar"], fo["abund"], fo.get("s1"), fo.get("spec_hidden"),
@@ -292,12 +302,16 @@ class UMHSModel(nn.Module):
         H, W = camera_ray_bundle.origins.shape[:2]
         num_rays = H * W
         tile = int(self.config.eval_tile_rays)
+        chunk = int(self.config.eval_num_rays_per_chunk)  # the reference's forward calls: depth is clipped per call
         chunks: Dict[str, List[Tensor]] = {}
         for s in range(0, num_rays, tile):
-            rb = camera_ray_bundle.get_row_major_sliced_ray_bundle(s, min(s + tile, num_rays))
+            e = min(s + tile, num_rays)
+            rb = camera_ray_bundle.get_row_major_sliced_ray_bundle(s, e)
             rb = RayBundle(origins=rb.origins.to(self.device), directions=rb.directions.to(self.device),
                            nears=None, fars=None) if not hasattr(rb, "to") else rb.to(self.device)
-            out = self.get_outputs(self.collider(rb), per_band_views=False)
+            ids = None if s % chunk == 0 else torch.arange(s, e, device=self.device, dtype=torch.int64)
+            out = self.get_outputs(self.collider(rb), per_band_views=False,
+                                   depth_chunks=(chunk, ids, e if ids is not None else e - s))
             for k, v in out.items():
                 if isinstance(v, Tensor):
                     chunks.setdefault(k, []).append(v.to(input_device))
