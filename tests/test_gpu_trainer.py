@@ -266,15 +266,23 @@ def test_eval_image_matches_oracle_chunk_loop(precision):
                 assert rel_l2(got[k], want[k]) < 3e-2, (name, k, rel_l2(got[k], want[k]))
         # packing is parameter-independent in eval mode (no visibility filter): bit-exact in both precisions
         assert torch.equal(got["num_samples_per_ray"].reshape(-1).cpu(), n_spr), name
-        # argmax outputs: equal wherever the top-2 class probabilities are not tied within the tolerance
+        # argmax outputs.  fp32: equal wherever the top-2 class probabilities are not tied (gap > 1e-5; rays without
+        # samples have K-way tied probabilities) and the accumulation is not on the 0.5 gate; bf16: the probabilities
+        # are softmax(0.2 cos) -- all within a few percent of 1/K -- so the argmax may flip where two classes are
+        # close: >= 90 % agreement on the pixels away from the gate
         pr = want["seg_probs"].reshape(H * W, -1)
         top2 = pr.topk(2, dim=-1).values
-        clear = (top2[:, 0] - top2[:, 1]) > (1e-5 if precision == "fp32" else 2e-2)
-        acc_clear = (want["accumulation"].reshape(-1) - 0.5).abs() > (1e-4 if precision == "fp32" else 2e-2)
-        sel = (clear & acc_clear).to(got["seg_raw"].device)
-        assert int(sel.sum()) > 0.6 * H * W  # (rays without samples have K-way tied probabilities)
-        assert torch.equal(got["seg_raw"].reshape(-1)[sel].cpu(), want["seg_raw"].reshape(-1)[sel.cpu()].to(torch.float32))
-        assert_close(got["seg_pred"].reshape(-1, 3)[sel], want["seg_pred"].reshape(-1, 3)[sel.cpu()], 1e-6, 1e-7,
-                     f"{name} seg_pred")
+        gate_clear = (want["accumulation"].reshape(-1) - 0.5).abs() > (1e-4 if precision == "fp32" else 2e-2)
+        raw_got, raw_want = got["seg_raw"].reshape(-1).cpu(), want["seg_raw"].reshape(-1).to(torch.float32)
+        if precision == "fp32":
+            sel = gate_clear & ((top2[:, 0] - top2[:, 1]) > 1e-5)
+            assert int(sel.sum()) > 0.6 * H * W
+            assert torch.equal(raw_got[sel], raw_want[sel]), name
+            assert_close(got["seg_pred"].reshape(-1, 3).cpu()[sel], want["seg_pred"].reshape(-1, 3)[sel], 1e-6, 1e-7,
+                         f"{name} seg_pred")
+        else:
+            sel = gate_clear & (n_spr > 0)
+            agree = float((raw_got[sel] == raw_want[sel]).float().mean())
+            assert agree > 0.9, (name, agree)
     for i in (0, 64, 127):
         assert torch.equal(got_a[f"wv_{i}"], got_a["spectral"][..., i:i + 1])

@@ -25,21 +25,44 @@ w["dir_w0"] = w["dir_b0"] = None
 grads = {"d_sigma": torch.randn(N, device=DEV), "d_scalar": torch.randn(N, K, device=DEV),
          "d_abund": torch.randn(N, K, device=DEV), "d_embedding": None}
 pts = ops.PointSet.from_positions(pos)
-ops.field_mlp_bwd(pts, enc, w, K, False, 0.4, grads, want_d_enc=os.environ.get("NO_DENC") is None)
+MODE = sys.argv[1] if len(sys.argv) > 1 else "bwd"   # bwd | fwd | density
+ROUNDS = {"bwd": 16, "fwd": 5, "density": 2}[MODE]
+
+
+def run():
+    if MODE == "bwd":
+        ops.field_mlp_bwd(pts, enc, w, K, False, 0.4, grads, want_d_enc=os.environ.get("NO_DENC") is None)
+    elif MODE == "fwd":
+        ops.field_mlp_fwd(pts, enc, w, K, False, 0.4, want_embedding=False)
+    else:
+        ops.density_fwd(pts, enc, w)
+
+
+run()
 cap = 4096
 buf = torch.zeros(4 * cap, dtype=torch.int64, device=DEV)
 lib = _lib.load()
 lib.umhs_debug_trace(buf.data_ptr(), cap, torch.cuda.current_stream().cuda_stream)
-ops.field_mlp_bwd(pts, enc, w, K, False, 0.4, grads, want_d_enc=os.environ.get("NO_DENC") is None)
+run()
 torch.cuda.synchronize()
 lib.umhs_debug_trace(None, 0, torch.cuda.current_stream().cuda_stream)
 t = buf.view(cap, 2, 2).cpu()
 ev = [(int(t[i, 0, 0]), int(t[i, 0, 1])) for i in range(cap) if int(t[i, 0, 1]) != 0]
-print("data thread events:", len(ev))
-seg = ev[32:65]  # second tile of group 0
+print("data thread events:", len(ev), "(the first tile is skipped)")
+seg = ev[:2 * ROUNDS + 1]  # second tile of group 0
+tot_e = tot_w = 0
 for (ta, ca), (tb, cb) in zip(seg[:-1], seg[1:]):
     kind = "wait (issue + tensor core)" if tb % 2 == 1 else "epilogue"
-    print(f"  round {tb // 2:2d} {kind:28s} {cb - ca:6d} cycles")
-print("  cycles for the tile:", seg[-1][1] - seg[0][1])
+    dt = (cb - ca) & 0xFFFFFFFF
+    tot_w += dt if tb % 2 == 1 else 0
+    tot_e += dt if tb % 2 == 0 else 0
+    print(f"  round {tb // 2:2d} {kind:28s} {dt:6d} cycles")
+print(f"  cycles for the tile: {(seg[-1][1] - seg[0][1]) & 0xFFFFFFFF}  (epilogues {tot_e}, waits {tot_w})")
 iv = [(int(t[i, 1, 0]), int(t[i, 1, 1])) for i in range(cap) if int(t[i, 1, 1]) != 0]
-print("issuer events:", len(iv), "first 80 (tag, delta; 2xxx = operands ready seen, 1xxx = round issued):", [(a, d - c) for (a, d), (_, c) in zip(iv[1:81], iv[:80])])
+print("issuer events:", len(iv), "(tag, delta): 3xxx = ready signal seen, 2xxx = + tcgen05 fence, 4xxx = critical MMAs + commit issued, "
+      "5xxx = deferred MMAs issued, 1xxx = warp reconverged")
+rows = []
+for (ta, ca), (tb, cb) in zip(iv[:-1], iv[1:]):
+    rows.append(f"{tb:5d} {(cb - ca) & 0xFFFFFFFF:5d}")
+for i in range(0, min(len(rows), 204), 6):
+    print("   " + "   ".join(rows[i:i + 6]))

@@ -25,6 +25,27 @@ namespace umhs {
 using namespace tc05;
 
 constexpr int TM = 128;          // samples per tile == threads per group
+#ifndef UMHS_ISSUER_SPIN
+#define UMHS_ISSUER_SPIN 4096
+#endif
+#ifndef UMHS_GROUP_SPIN
+#define UMHS_GROUP_SPIN 0
+#endif
+#ifndef UMHS_FLAG_READY
+#define UMHS_FLAG_READY 2
+#endif
+// 1: the groups signal "operands ready" through a plain shared-memory counter (red.release / ld.acquire) that the
+// issuer polls, instead of an mbarrier: an mbarrier test by the thread that has just issued tcgen05.commit does not
+// return before that commit has arrived (measured: ~230 cycles per round even on a long-completed phase), which
+// serialised the groups on the MMA latency.
+// 2: ... through a named hardware barrier (bar.arrive by the group's 128 threads, bar.sync by the issuer warp): the
+// flag poll is a shared-memory read and queues behind the operand reads of the MMAs the issuer has just launched.
+constexpr bool kFlagReady = UMHS_FLAG_READY == 1;
+constexpr bool kNamedBarReady = UMHS_FLAG_READY == 2;
+constexpr int kReadyBarId0 = 1;            // named barrier of group g = kReadyBarId0 + g (0 is __syncthreads)
+constexpr int kReadyBarCount = TM + 32;    // the group's threads arrive, the issuer warp syncs
+constexpr int kIssuerSpin = UMHS_ISSUER_SPIN;  // test_wait probes before the suspending try_wait (see tc05::mbar_wait)
+constexpr int kGroupSpin = UMHS_GROUP_SPIN;
 constexpr int CH_ACT = 2048;     // chunk stride of a 128-row activation tile
 
 // ---- shared-memory plan (bytes).  Weight tiles: [rows x K] bf16 K-major, CH = rows * 16; bias = one more K column.
@@ -41,9 +62,13 @@ struct TcSmem {
     static constexpr int ones = w_end;                      // [128 x 16] of 1.0
     static constexpr int ctrl = ones + 2 * CH_ACT;          // mbarriers ready[4], done[4]; tmem address
     static constexpr int sbias = ctrl + 128;                // backward: fp32 [64] narrow-layer bias gradients
-    static constexpr int groups = sbias + 256;
+    static constexpr int trace = sbias + 256;               // developer cycle trace: 2 threads x 256 stamps x 8 B
+    static constexpr int groups = trace + 4096;
     static_assert(groups % 128 == 0, "operand tiles must stay 128-byte aligned");
 };
+__device__ __forceinline__ uint32_t *ready_flags(uint8_t *smem) {  // uint32 [4] behind the mbarriers and the TMEM slot
+    return reinterpret_cast<uint32_t *>(smem + TcSmem::ctrl + 96);
+}
 constexpr int COL_B_BASE0 = 32, COL_B_64 = 64, COL_B_X = 27, COL_B_X2 = 28;
 
 // stage an nn.Linear weight [out x in] (+ bias in K column `bias_col`) as a bf16 K-major operand tile
@@ -91,15 +116,10 @@ __device__ __forceinline__ void stage_all_weights(uint8_t *smem, const umhs_mlp_
     if (spec) stage_weight(smem + TcSmem::w_d0, 16, 0, mp.dir_w0, mp.dir_b0, 16, 28, 32, COL_B_X2, tid, nthr);
 }
 
-struct WAddr {  // async-proxy addresses of the weight tiles and of the ones tile
-    uint32_t b0, b1, hf0, h1, f1, h2, f2, d0, ones;
-    __device__ __forceinline__ explicit WAddr(uint32_t sb) {  // sb = shared-window address of the CTA's dynamic smem
-        b0 = sb + TcSmem::w_base0; b1 = sb + TcSmem::w_base1;
-        hf0 = sb + TcSmem::w_hf0;  h1 = sb + TcSmem::w_h1;
-        f1 = sb + TcSmem::w_f1;    h2 = sb + TcSmem::w_h2;
-        f2 = sb + TcSmem::w_f2;    d0 = sb + TcSmem::w_d0;
-        ones = sb + TcSmem::ones;
-    }
+struct WOff {  // byte offsets (from the CTA's dynamic shared memory base) of the weight tiles and of the ones tile
+    static constexpr uint32_t b0 = TcSmem::w_base0, b1 = TcSmem::w_base1, hf0 = TcSmem::w_hf0, h1 = TcSmem::w_h1,
+                              f1 = TcSmem::w_f1, h2 = TcSmem::w_h2, f2 = TcSmem::w_f2, d0 = TcSmem::w_d0,
+                              ones = TcSmem::ones;
 };
 
 __device__ __forceinline__ void pos_encoding_tc(const Point &p, float (&pe)[12]) {
@@ -183,23 +203,37 @@ __device__ __forceinline__ void epi_mask64(uint32_t taddr, const uint8_t *act_ti
 }
 
 // Optional cycle trace (developer aid, off unless umhs_debug_trace() installs a buffer): in CTA 0, thread 0 of
-// group 0 (who = 0) and the issuer (who = 1) stamp (tag, clock64) pairs.
+// group 0 (who = 0) and the issuer (who = 1) stamp (tag, clock) pairs.  Stamps go to SHARED memory and are copied out
+// when the kernel ends: a stamp that stores to global memory perturbs what it measures (the acquire operations of the
+// handshakes then wait for those stores to drain: ~230 phantom cycles per round).
 __device__ long long *g_trace = nullptr;
 __device__ int g_trace_cap = 0;
+constexpr int kTraceCap = 256;  // stamps kept per traced thread
+#ifndef UMHS_TRACE
+#define UMHS_TRACE 0   // build with -DUMHS_TRACE=1 (tools/build_variant.py) for tools/trace_mlp.py; stamps cost cycles
+#endif
 struct Tracer {
-    long long *buf;
-    int cap, slot, who;
-    __device__ __forceinline__ Tracer(bool on, int who_) : buf(nullptr), cap(0), slot(0), who(who_) {
-        if (on && blockIdx.x == 0) {
-            buf = g_trace;
-            cap = g_trace_cap;
-        }
+    uint2 *sbuf;
+    int slot, who, skip;
+    __device__ __forceinline__ Tracer(bool on, int who_, uint8_t *smem, int skip_)
+        : sbuf(nullptr), slot(0), who(who_), skip(skip_) {
+        if (UMHS_TRACE && on && blockIdx.x == 0 && g_trace != nullptr)
+            sbuf = reinterpret_cast<uint2 *>(smem + TcSmem::trace) + who_ * kTraceCap;
     }
     __device__ __forceinline__ void stamp(int tag) {
-        if (buf != nullptr && slot < cap) {
-            buf[2 * (slot * 2 + who)] = tag;
-            buf[2 * (slot * 2 + who) + 1] = clock64();
-            ++slot;
+        if (UMHS_TRACE && sbuf != nullptr) {
+            if (skip > 0) --skip;
+            else if (slot < kTraceCap) {
+                sbuf[slot] = make_uint2((uint32_t)tag, (uint32_t)clock64());
+                ++slot;
+            }
+        }
+    }
+    __device__ __forceinline__ void flush() {
+        if (!UMHS_TRACE || sbuf == nullptr) return;
+        for (int i = 0; i < slot && i < g_trace_cap; ++i) {
+            g_trace[2 * (i * 2 + who)] = sbuf[i].x;
+            g_trace[2 * (i * 2 + who) + 1] = sbuf[i].y;
         }
     }
 };
@@ -251,17 +285,26 @@ struct GroupSync {
     uint32_t parity;
     int lane;
     Tracer tr;
+    uint32_t *flag = nullptr;  // kFlagReady: this group's "operands ready" counter (4 arrivals per round)
+    int bar_id = 0;            // kNamedBarReady: this group's named barrier
     int round = 0;
     // operand tiles written & accumulators consumed -> issuer may run this group's next round; wait for its MMAs
     __device__ __forceinline__ void arrive() {
         tr.stamp(2 * round);
         fence_proxy_async();  // NB: also waits for this thread's outstanding GLOBAL stores -- keep those behind it
         fence_before_sync();
+        if (kNamedBarReady) {
+            named_bar_arrive(bar_id, kReadyBarCount);  // every thread of the group; nobody waits here
+            return;
+        }
         __syncwarp();
-        if (lane == 0) mbar_arrive(ready);
+        if (lane == 0) {
+            if (kFlagReady) flag_release_add(flag);
+            else mbar_arrive(ready);
+        }
     }
     __device__ __forceinline__ void wait() {
-        mbar_wait(done, parity);
+        mbar_wait<kGroupSpin>(done, parity);
         parity ^= 1u;
         fence_after_sync();
         tr.stamp(2 * round + 1);
@@ -292,6 +335,7 @@ __device__ __forceinline__ void static_for(F &&f) {
 template <int G, int ROUNDS, class F>
 __device__ __forceinline__ void issuer_rotation(uint64_t *bars, const int64_t (&n_iter)[G], Tracer tr, F &&issue) {
     uint32_t par[G];
+    const uint32_t *flags = reinterpret_cast<const uint32_t *>(bars) + 24;  // ctrl + 96, see ready_flags()
 #pragma unroll
     for (int g = 0; g < G; ++g) par[g] = 0u;
 #pragma unroll 1
@@ -300,8 +344,17 @@ __device__ __forceinline__ void issuer_rotation(uint64_t *bars, const int64_t (&
             static_for<G>([&](auto gc) {
                 constexpr int g = decltype(gc)::value;
                 if (it < n_iter[g]) {  // warp-uniform
-                    mbar_wait(bars + g, par[g]);
-                    par[g] ^= 1u;
+                    tr.stamp(6000 + 100 * g + decltype(rc)::value);
+                    if (kNamedBarReady) {
+                        named_bar_sync(kReadyBarId0 + g, kReadyBarCount);
+                    } else if (kFlagReady) {
+                        par[g] += 4u;  // running arrival count of this group (one per data warp and round)
+                        flag_wait(flags + g, par[g]);
+                    } else {
+                        mbar_wait<kIssuerSpin>(bars + g, par[g]);
+                        par[g] ^= 1u;
+                    }
+                    tr.stamp(3000 + 100 * g + decltype(rc)::value);
                     fence_after_sync();
                     tr.stamp(2000 + 100 * g + decltype(rc)::value);
                     if (elect_one()) {
@@ -314,7 +367,9 @@ __device__ __forceinline__ void issuer_rotation(uint64_t *bars, const int64_t (&
                         // covers them, so an operand tile they read may be overwritten one round later, not earlier.
                         issue(rc, gc, (it == 0 && g == 0) ? 0u : 1u, (uint32_t)(it >> 40), std::integral_constant<int, 0>{});
                         commit(bars + G + g);
+                        tr.stamp(4000 + 100 * g + decltype(rc)::value);
                         issue(rc, gc, (it == 0 && g == 0) ? 0u : 1u, (uint32_t)(it >> 40), std::integral_constant<int, 1>{});
+                        tr.stamp(5000 + 100 * g + decltype(rc)::value);
                     }
                     __syncwarp();
                     tr.stamp(1000 + 100 * g + decltype(rc)::value);
@@ -322,6 +377,7 @@ __device__ __forceinline__ void issuer_rotation(uint64_t *bars, const int64_t (&
             });
         });
     }
+    tr.flush();
 }
 
 // =====================================================================================================
@@ -362,6 +418,7 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         for (int g = 0; g < G; ++g) {
             mbar_init(bars + g, 4);
             mbar_init(bars + G + g, 1);
+            ready_flags(smem)[g] = 0u;
         }
         fence_mbar_init();
     }
@@ -384,33 +441,33 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             n_iter[g] = first < n_tiles ? (n_tiles - 1 - first) / stride + 1 : 0;
         }
         const uint32_t sbase = smem_u32(smem);
-        issuer_rotation<G, ROUNDS>(bars, n_iter, Tracer(false, 1), [&](auto rc, auto gc, uint32_t, uint32_t zero, auto ph) {
+        issuer_rotation<G, ROUNDS>(bars, n_iter, Tracer(lane == 0, 1, smem, 6 * G * ROUNDS), [&](auto rc, auto gc, uint32_t, uint32_t zero, auto ph) {
             constexpr int r = decltype(rc)::value, g = decltype(gc)::value;
             if constexpr (decltype(ph)::value != 0) return;  // the forward has no deferred MMAs
-            const uint32_t sb = sbase + zero;
-            const WAddr w(sb);
-            const uint32_t b = sb + (uint32_t)(TcSmem::groups + g * GRP_BYTES);
-            const uint32_t sX = b + TcFwd::tX, sH = b + TcFwd::tH, sF = b + TcFwd::tF;
+            const uint32_t B16 = desc_base16(sbase) + zero;   // descriptors = B16 + compile-time constants
+            using w = WOff;
+            constexpr uint32_t b = (uint32_t)(TcSmem::groups + g * GRP_BYTES);
+            constexpr uint32_t sX = b + TcFwd::tX, sH = b + TcFwd::tH, sF = b + TcFwd::tF;
             const uint32_t tw = tbase + (uint32_t)(WCOLS * g);
             if constexpr (r == 0) {
-                gemm_kmajor(tw, sX, w.b0, 64, 0, 64, 32, 0);
-                gemm_bias_step(tw, w.ones, w.b0, 64, 0, 64, COL_B_BASE0);
+                gemm_kmajor(tw, B16, sX, w::b0, 64, 0, 64, 32, 0);
+                gemm_bias_step(tw, B16, w::ones, w::b0, 64, 0, 64, COL_B_BASE0);
             } else if constexpr (r == 1) {
-                gemm_kmajor(tw, sH, w.b1, 16, 0, 16, 64, 0);
-                gemm_bias_step(tw, w.ones, w.b1, 16, 0, 16, COL_B_64);
-                if (spec) gemm_kmajor(tw + 64, sF, w.d0, 16, 0, 16, 32, 0);
+                gemm_kmajor(tw, B16, sH, w::b1, 16, 0, 16, 64, 0);
+                gemm_bias_step(tw, B16, w::ones, w::b1, 16, 0, 16, COL_B_64);
+                if (spec) gemm_kmajor(tw + 64, B16, sF, w::d0, 16, 0, 16, 32, 0);
             } else if constexpr (r == 2) {
-                gemm_kmajor(tw, sX, w.hf0, 128, 0, 128, 32, 0);
+                gemm_kmajor(tw, B16, sX, w::hf0, 128, 0, 128, 32, 0);
             } else if constexpr (r == 3) {
-                gemm_kmajor(tw, sH, w.h1, 64, 0, 64, 64, 0);
-                gemm_kmajor(tw + 64, sF, w.f1, 64, 0, 64, 64, 0);
-                gemm_bias_step(tw, w.ones, w.h1, 64, 0, 64, COL_B_64);
-                gemm_bias_step(tw + 64, w.ones, w.f1, 64, 0, 64, COL_B_64);
+                gemm_kmajor(tw, B16, sH, w::h1, 64, 0, 64, 64, 0);
+                gemm_kmajor(tw + 64, B16, sF, w::f1, 64, 0, 64, 64, 0);
+                gemm_bias_step(tw, B16, w::ones, w::h1, 64, 0, 64, COL_B_64);
+                gemm_bias_step(tw + 64, B16, w::ones, w::f1, 64, 0, 64, COL_B_64);
             } else {
-                gemm_kmajor(tw, sH, w.h2, 16, 0, 16, 64, 0);
-                gemm_kmajor(tw + 64, sF, w.f2, 32, 0, 32, 64, 0);
-                gemm_bias_step(tw, w.ones, w.h2, 16, 0, 16, COL_B_64);
-                gemm_bias_step(tw + 64, w.ones, w.f2, 32, 0, 32, COL_B_64);
+                gemm_kmajor(tw, B16, sH, w::h2, 16, 0, 16, 64, 0);
+                gemm_kmajor(tw + 64, B16, sF, w::f2, 32, 0, 32, 64, 0);
+                gemm_bias_step(tw, B16, w::ones, w::h2, 16, 0, 16, COL_B_64);
+                gemm_bias_step(tw + 64, B16, w::ones, w::f2, 32, 0, 32, COL_B_64);
             }
         });
         __syncwarp();
@@ -418,11 +475,12 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         // ======================= data groups
         uint8_t *gbase = smem + TcSmem::groups + grp * GRP_BYTES;
         uint8_t *tX = gbase + TcFwd::tX, *tH = gbase + TcFwd::tH, *tF = gbase + TcFwd::tF;
-        GroupSync gs{bars + grp, bars + G + grp, 0u, lane, Tracer(false, 0)};
+        GroupSync gs{bars + grp, bars + G + grp, 0u, lane, Tracer(tid == 0, 0, smem, 2 * ROUNDS), ready_flags(smem) + grp, kReadyBarId0 + grp};
         const uint32_t trow = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(WCOLS * grp);
         const float invT = DENSITY_ONLY ? 1.f : 1.0f / mp.temperature;
 
         for (int64_t it = 0; tile_of(it, grp) < n_tiles; ++it) {
+            gs.round = 0;
             const int64_t n0 = tile_of(it, grp) * TM;
             const bool valid = n0 + row < n_total;
             const int64_t n = valid ? n0 + row : n_total - 1;  // tail threads shadow the last sample, write nothing
@@ -530,6 +588,7 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                 }
             }
         }
+        gs.tr.flush();
     }
     fence_before_sync();
     __syncthreads();
@@ -641,6 +700,7 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         for (int q = 0; q < G; ++q) {
             mbar_init(bars + q, 4);
             mbar_init(bars + G + q, 1);
+            ready_flags(smem)[q] = 0u;
         }
         fence_mbar_init();
     }
@@ -664,78 +724,78 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         }
         const uint32_t sbase = smem_u32(smem);
         const bool want_denc = d_enc != nullptr;
-        issuer_rotation<G, TcBwd::kRounds>(bars, n_iter, Tracer(lane == 0, 1), [&](auto rc, auto gc, uint32_t acc,
+        issuer_rotation<G, TcBwd::kRounds>(bars, n_iter, Tracer(lane == 0, 1, smem, 6 * G * TcBwd::kRounds), [&](auto rc, auto gc, uint32_t acc,
                                                                                   uint32_t zero, auto ph) {
             constexpr int r = decltype(rc)::value, q = decltype(gc)::value;
             constexpr bool crit = decltype(ph)::value == 0, late = !crit;  // before / behind the round's commit
-            const uint32_t sb = sbase + zero;
-            const WAddr w(sb);
-            const uint32_t b = sb + (uint32_t)(TcSmem::groups + q * TcBwd::grp_bytes);
-            const uint32_t sA0 = b + TcBwd::tA0, sX = b + TcBwd::tX, sH1 = b + TcBwd::tH1, sH2 = b + TcBwd::tH2;
-            const uint32_t sD1 = b + TcBwd::tD1, sD2 = b + TcBwd::tD2, sX2 = sD1;
+            const uint32_t B16 = desc_base16(sbase) + zero;   // descriptors = B16 + compile-time constants
+            using w = WOff;
+            constexpr uint32_t b = (uint32_t)(TcSmem::groups + q * TcBwd::grp_bytes);
+            constexpr uint32_t sA0 = b + TcBwd::tA0, sX = b + TcBwd::tX, sH1 = b + TcBwd::tH1, sH2 = b + TcBwd::tH2;
+            constexpr uint32_t sD1 = b + TcBwd::tD1, sD2 = b + TcBwd::tD2, sX2 = sD1;
             const uint32_t tw = tbase + 64u * q;
             if constexpr (r == 0) {         // base layer 0
                 if (crit) {
-                    gemm_kmajor(tw, sA0, w.b0, 64, 0, 64, 32, 0);
-                    gemm_bias_step(tw, w.ones, w.b0, 64, 0, 64, COL_B_BASE0);
+                    gemm_kmajor(tw, B16, sA0, w::b0, 64, 0, 64, 32, 0);
+                    gemm_bias_step(tw, B16, w::ones, w::b0, 64, 0, 64, COL_B_BASE0);
                 }
             } else if constexpr (r == 1) {  // base layer 1 (N=16) [+ mlp_directional layer 0 at working columns 16..31]
                 if (crit) {
-                    gemm_kmajor(tw, sH1, w.b1, 16, 0, 16, 64, 0);
-                    gemm_bias_step(tw, w.ones, w.b1, 16, 0, 16, COL_B_64);
-                    if (spec) gemm_kmajor(tw + 16, sX2, w.d0, 16, 0, 16, 32, 0);
+                    gemm_kmajor(tw, B16, sH1, w::b1, 16, 0, 16, 64, 0);
+                    gemm_bias_step(tw, B16, w::ones, w::b1, 16, 0, 16, COL_B_64);
+                    if (spec) gemm_kmajor(tw + 16, B16, sX2, w::d0, 16, 0, 16, 32, 0);
                 }
             } else if constexpr (r == 2) {  // mlp_head layer 0 [+ wgrad of mlp_directional layer 0]
-                if (crit) gemm_kmajor(tw, sX, w.hf0, 128, 0, 64, 32, 0);
-                if (late && spec) gemm_wgrad(tbase + TcBwd::P_d0, sD2, 0, sX2, 0, 32, acc);
+                if (crit) gemm_kmajor(tw, B16, sX, w::hf0, 128, 0, 64, 32, 0);
+                if (late && spec) gemm_wgrad(tbase + TcBwd::P_d0, B16, sD2, 0, sX2, 0, 32, acc);
             } else if constexpr (r == 3) {
                 if (crit) {
-                    gemm_kmajor(tw, sH1, w.h1, 64, 0, 64, 64, 0);
-                    gemm_bias_step(tw, w.ones, w.h1, 64, 0, 64, COL_B_64);
+                    gemm_kmajor(tw, B16, sH1, w::h1, 64, 0, 64, 64, 0);
+                    gemm_bias_step(tw, B16, w::ones, w::h1, 64, 0, 64, COL_B_64);
                 }
             } else if constexpr (r == 4) {
                 if (crit) {
-                    gemm_kmajor(tw, sH2, w.h2, 16, 0, 16, 64, 0);
-                    gemm_bias_step(tw, w.ones, w.h2, 16, 0, 16, COL_B_64);
+                    gemm_kmajor(tw, B16, sH2, w::h2, 16, 0, 16, 64, 0);
+                    gemm_bias_step(tw, B16, w::ones, w::h2, 16, 0, 16, COL_B_64);
                 }
             } else if constexpr (r == 5) {
-                if (crit) gemm_dgrad(tw, sD2, w.h2, 16, 0, 64, 16, 0);
-                if (late) gemm_wgrad(tbase + TcBwd::P_h2t, sH2, 0, sD2, 0, 16, acc);
+                if (crit) gemm_dgrad(tw, B16, sD2, w::h2, 16, 0, 64, 16, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_h2t, B16, sH2, 0, sD2, 0, 16, acc);
             } else if constexpr (r == 6) {
-                if (crit) gemm_dgrad(tw, sD1, w.h1, 64, 0, 64, 64, 0);
-                if (late) gemm_wgrad(tbase + TcBwd::P_h1, sD1, 0, sH1, 0, 72, acc);  // 64 + ones
+                if (crit) gemm_dgrad(tw, B16, sD1, w::h1, 64, 0, 64, 64, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_h1, B16, sD1, 0, sH1, 0, 72, acc);  // 64 + ones
             } else if constexpr (r == 7) {
-                if (crit) gemm_dgrad(tw, sD2, w.hf0, 128, 0, 32, 64, 0);
-                if (late) gemm_wgrad(tbase + TcBwd::P_h0, sD2, 0, sX, 0, 32, acc);   // column 27 = ones
+                if (crit) gemm_dgrad(tw, B16, sD2, w::hf0, 128, 0, 32, 64, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_h0, B16, sD2, 0, sX, 0, 32, acc);   // column 27 = ones
             } else if constexpr (r == 8) {  // feature_mlp layer 0
-                if (crit) gemm_kmajor(tw, sX, w.hf0, 128, 64, 64, 32, 0);
+                if (crit) gemm_kmajor(tw, B16, sX, w::hf0, 128, 64, 64, 32, 0);
             } else if constexpr (r == 9) {
                 if (crit) {
-                    gemm_kmajor(tw, sH1, w.f1, 64, 0, 64, 64, 0);
-                    gemm_bias_step(tw, w.ones, w.f1, 64, 0, 64, COL_B_64);
+                    gemm_kmajor(tw, B16, sH1, w::f1, 64, 0, 64, 64, 0);
+                    gemm_bias_step(tw, B16, w::ones, w::f1, 64, 0, 64, COL_B_64);
                 }
             } else if constexpr (r == 10) {
                 if (crit) {
-                    gemm_kmajor(tw, sH2, w.f2, 32, 0, 32, 64, 0);
-                    gemm_bias_step(tw, w.ones, w.f2, 32, 0, 32, COL_B_64);
+                    gemm_kmajor(tw, B16, sH2, w::f2, 32, 0, 32, 64, 0);
+                    gemm_bias_step(tw, B16, w::ones, w::f2, 32, 0, 32, COL_B_64);
                 }
             } else if constexpr (r == 11) {
-                if (crit) gemm_dgrad(tw, sD2, w.f2, 32, 0, 64, 32, 0);
-                if (late) gemm_wgrad(tbase + TcBwd::P_f2t, sH2, 0, sD2, 0, 32, acc);
+                if (crit) gemm_dgrad(tw, B16, sD2, w::f2, 32, 0, 64, 32, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_f2t, B16, sH2, 0, sD2, 0, 32, acc);
             } else if constexpr (r == 12) {
-                if (crit) gemm_dgrad(tw, sD1, w.f1, 64, 0, 64, 64, 0);
-                if (late) gemm_wgrad(tbase + TcBwd::P_f1, sD1, 0, sH1, 0, 72, acc);
+                if (crit) gemm_dgrad(tw, B16, sD1, w::f1, 64, 0, 64, 64, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_f1, B16, sD1, 0, sH1, 0, 72, acc);
             } else if constexpr (r == 13) {
-                if (crit) gemm_dgrad(tw, sD2, w.hf0, 128, 64, 32, 64, 0);
-                if (late) gemm_wgrad(tbase + TcBwd::P_f0, sD2, 0, sX, 0, 32, acc);
+                if (crit) gemm_dgrad(tw, B16, sD2, w::hf0, 128, 64, 32, 64, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_f0, B16, sD2, 0, sX, 0, 32, acc);
             } else if constexpr (r == 14) {  // base layer 1 backward (H0 is back in tH1; d [o0, emb] sits in tD1)
-                if (crit) gemm_dgrad(tw, sD1, w.b1, 16, 0, 64, 16, 0);
-                if (late) gemm_wgrad(tbase + TcBwd::P_b1t, sH1, 0, sD1, 0, 16, acc);
+                if (crit) gemm_dgrad(tw, B16, sD1, w::b1, 16, 0, 64, 16, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_b1t, B16, sH1, 0, sD1, 0, 16, acc);
             } else {                         // 15: base layer 0 backward (wgrad N = 32 + ones chunk), delta in tD2
                 // its weight gradient reads tA0, which the NEXT tile's first epilogue overwrites: not deferred
                 if (crit) {
-                    if (want_denc) gemm_dgrad(tw, sD2, w.b0, 64, 0, 32, 64, 0);
-                    gemm_wgrad(tbase + TcBwd::P_b0, sD2, 0, sA0, 0, 40, acc);
+                    if (want_denc) gemm_dgrad(tw, B16, sD2, w::b0, 64, 0, 32, 64, 0);
+                    gemm_wgrad(tbase + TcBwd::P_b0, B16, sD2, 0, sA0, 0, 40, acc);
                 }
             }
         });
@@ -745,7 +805,7 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         uint8_t *tA0 = gbase + TcBwd::tA0, *tX = gbase + TcBwd::tX, *tH1 = gbase + TcBwd::tH1;
         uint8_t *tH2 = gbase + TcBwd::tH2, *tD1 = gbase + TcBwd::tD1, *tD2 = gbase + TcBwd::tD2;
         uint8_t *tX2 = tD1;
-        GroupSync gs{bars + grp, bars + G + grp, 0u, lane, Tracer(tid == 0, 0)};
+        GroupSync gs{bars + grp, bars + G + grp, 0u, lane, Tracer(tid == 0, 0, smem, 2 * TcBwd::kRounds), ready_flags(smem) + grp, kReadyBarId0 + grp};
         const uint32_t trow = tbase + ((uint32_t)((warp & 3) * 32) << 16) + 64u * grp;
         float *sb_h2 = sbias, *sb_f2 = sbias + 16, *sb_b1 = sbias + 48;   // [16], [32], [16]
         const float invT = 1.0f / mp.temperature;
@@ -968,6 +1028,7 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                 store_rows_coalesced(d_enc, valid ? n : -1, v, tD1 + (warp & 3) * 4096, lane);
             }
         }
+        gs.tr.flush();
         if (colsum_owner<KM>(lane)) {  // one lane of each run owns column colsum_col<KM>(lane)
             const int col = colsum_col<KM>(lane);
             if (bs_h2 != 0.f) atomicAdd(sb_h2 + col, bs_h2);
@@ -1071,9 +1132,10 @@ tc05_selftest_kernel(int mode, const float *__restrict__ A, const float *__restr
     const uint32_t tbase = *slot;
     if (warp == 0) {
         if (elect_one()) {
-            if (mode == 0) gemm_kmajor(tbase, smem_u32(tA), smem_u32(tB), N, 0, N, K, 0);
-            else if (mode == 1) gemm_dgrad(tbase, smem_u32(tA), smem_u32(tB), K, 0, N, K, 0);
-            else gemm_wgrad(tbase, smem_u32(tA), 0, smem_u32(tB), 0, N, 0);
+            const uint32_t b16 = desc_base16(smem_u32(smem));
+            if (mode == 0) gemm_kmajor(tbase, b16, 0u, 32768u, N, 0, N, K, 0);
+            else if (mode == 1) gemm_dgrad(tbase, b16, 0u, 32768u, K, 0, N, K, 0);
+            else gemm_wgrad(tbase, b16, 0u, 0, 32768u, 0, N, 0);
             commit(bar);
         }
         __syncwarp();
@@ -1121,10 +1183,11 @@ tc05_microbench_kernel(int mode, int N, int K, int reps, long long *out) {
         if (elect_one()) {
             const long long t0 = clock64();
             for (int i = 0; i < reps; ++i) {
-                if (mode == 0) gemm_kmajor(tbase, smem_u32(tA), smem_u32(tB), N, 0, N, K, 1);
-                else if (mode == 1) gemm_dgrad(tbase, smem_u32(tA), smem_u32(tB), K, 0, N, K, 1);
-                else if (mode == 2) gemm_wgrad(tbase, smem_u32(tA), 0, smem_u32(tB), 0, N, 1);
-                else gemm_bias_step(tbase, smem_u32(tA), smem_u32(tB), N, 0, N, 0);
+                const uint32_t b16 = desc_base16(smem_u32(smem));
+                if (mode == 0) gemm_kmajor(tbase, b16, 0u, 32768u, N, 0, N, K, 1);
+                else if (mode == 1) gemm_dgrad(tbase, b16, 0u, 32768u, K, 0, N, K, 1);
+                else if (mode == 2) gemm_wgrad(tbase, b16, 0u, 0, 32768u, 0, N, 1);
+                else gemm_bias_step(tbase, b16, 0u, 32768u, N, 0, N, 0);
             }
             const long long t1 = clock64();
             commit(bar);

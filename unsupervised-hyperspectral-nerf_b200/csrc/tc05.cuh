@@ -85,9 +85,29 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// bounded wait: a wrong descriptor must fail loudly (trap), never hang the GPU
+// bounded wait: a wrong descriptor must fail loudly (trap), never hang the GPU.
+// mbarrier.try_wait suspends the thread in hardware; measured on B200 it costs ~230 cycles even when the phase has
+// long completed, and about as much to wake up.  SPIN polls first: `SPIN` non-blocking mbarrier.test_wait probes (a
+// probe is a shared-memory round trip, ~30 cycles) before falling back to the suspending form.
+template <int SPIN = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
+    if (SPIN > 0) {
+#pragma unroll 1
+        for (int it = 0; it < SPIN; ++it) {
+            uint32_t ok;
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t"
+                "}\n"
+                : "=r"(ok)
+                : "r"(a), "r"(parity)
+                : "memory");
+            if (ok) return;
+        }
+    }
 #pragma unroll 1
     for (uint32_t it = 0; it < (1u << 24); ++it) {
         uint32_t ok;
@@ -163,58 +183,59 @@ __device__ __forceinline__ void load8(const uint8_t *buf, int row, int c0, int c
     }
 }
 
-// The descriptors of consecutive K steps differ only in the 14-bit start-address field (bits 0..13, units of
-// 16 bytes; operand tiles live below 256 KB so the field never carries): they are built once per GEMM and advanced
-// with one 32-bit add each -- the single issuing thread is the critical path of every MMA round.
-__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+// Descriptors as "base + compile-time constant".  The issuing thread paces the SM, and every descriptor it has to
+// assemble at run time (shift, mask, or-in the strides: 4-5 uniform-datapath instructions each) sits on that path.
+// With b16 = (shared-window address of the CTA's dynamic smem) >> 4 -- one warp-uniform value -- the descriptor of
+// the operand at byte offset `off` from that base is
+//     lo = b16 + ((off >> 4) | (LBO >> 4) << 16)         (start address: bits 0..13, LBO: bits 16..29)
+//     hi = (SBO >> 4) | 1 << 14                          (SBO: bits 32..45, descriptor version: bit 46)
+// i.e. ONE add per descriptor once `off` and the strides are constants after inlining (shared memory ends below
+// 256 KB, so the 14-bit address field never carries into the LBO field).
+__device__ __forceinline__ uint32_t desc_base16(uint32_t smem_base_saddr) { return (smem_base_saddr & 0x3FFFFu) >> 4; }
+__device__ __forceinline__ uint64_t desc_at(uint32_t b16, uint32_t off_bytes, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    const uint32_t lo = b16 + ((off_bytes >> 4) | ((lbo_bytes >> 4) << 16));
+    const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);
+    return ((uint64_t)hi << 32) | (uint64_t)lo;
+}
 
-// D[128 x N] (+)= A[128 x K] * B[N x K]^T, both operands K-major tiles.
+// D[128 x N] (+)= A[128 x K] * B[N x K]^T, both operands K-major tiles at byte offsets a_off / b_off from the base.
 //   a: tile of 128 rows (CH = 2048); b: tile of `b_rows` rows (CH = b_rows*16), rows [b_row0, b_row0+N) used.
-__device__ __forceinline__ void gemm_kmajor(uint32_t d_tmem, uint32_t a_saddr, uint32_t b_saddr, int b_rows, int b_row0,
-                                            int N, int K, uint32_t accumulate) {
+__device__ __forceinline__ void gemm_kmajor(uint32_t d_tmem, uint32_t b16, uint32_t a_off, uint32_t b_off, int b_rows,
+                                            int b_row0, int N, int K, uint32_t accumulate) {
     const uint32_t idesc = make_idesc(128, N, 0, 0);
     const uint32_t a_ch = 2048, b_ch = (uint32_t)b_rows * 16;
-    uint64_t ad = make_desc(a_saddr, a_ch, 128);
-    uint64_t bd = make_desc(b_saddr + (uint32_t)(b_row0 >> 3) * 128, b_ch, 128);
+    const uint32_t b0 = b_off + (uint32_t)(b_row0 >> 3) * 128;
 #pragma unroll
-    for (int k = 0; k < K; k += 16) {
-        mma_ss(d_tmem, ad, bd, idesc, (k > 0) ? 1u : accumulate);
-        ad = desc_advance(ad, 2 * a_ch);
-        bd = desc_advance(bd, 2 * b_ch);
-    }
+    for (int k = 0; k < K; k += 16)
+        mma_ss(d_tmem, desc_at(b16, a_off + (uint32_t)(k >> 3) * a_ch, a_ch, 128),
+               desc_at(b16, b0 + (uint32_t)(k >> 3) * b_ch, b_ch, 128), idesc, (k > 0) ? 1u : accumulate);
 }
 
 // dgrad: D[128 x N] = A[128 x K] * W[K x N], A K-major (delta tile), W stored as nn.Linear [K(out) x N(in)]
 // K-major-for-forward, read here as an MN-major B operand (MN = in, K = out).  Rows (out) [w_row0, w_row0+K).
-__device__ __forceinline__ void gemm_dgrad(uint32_t d_tmem, uint32_t a_saddr, uint32_t w_saddr, int w_rows, int w_row0,
-                                           int N, int K, uint32_t accumulate) {
+__device__ __forceinline__ void gemm_dgrad(uint32_t d_tmem, uint32_t b16, uint32_t a_off, uint32_t w_off, int w_rows,
+                                           int w_row0, int N, int K, uint32_t accumulate) {
     const uint32_t idesc = make_idesc(128, N, 0, 1);
     const uint32_t a_ch = 2048, w_ch = (uint32_t)w_rows * 16;
-    uint64_t ad = make_desc(a_saddr, a_ch, 128);
+    const uint32_t w0 = w_off + (uint32_t)(w_row0 >> 3) * 128;
     // MN-major: SBO = stride between 8-wide MN chunks (= w_ch), LBO = stride between 8-deep K groups (= 128)
-    uint64_t bd = make_desc(w_saddr + (uint32_t)(w_row0 >> 3) * 128, 128, w_ch);
 #pragma unroll
-    for (int k = 0; k < K; k += 16) {
-        mma_ss(d_tmem, ad, bd, idesc, (k > 0) ? 1u : accumulate);
-        ad = desc_advance(ad, 2 * a_ch);
-        bd = desc_advance(bd, 256);
-    }
+    for (int k = 0; k < K; k += 16)
+        mma_ss(d_tmem, desc_at(b16, a_off + (uint32_t)(k >> 3) * a_ch, a_ch, 128),
+               desc_at(b16, w0 + (uint32_t)(k >> 3) * 128, 128, w_ch), idesc, (k > 0) ? 1u : accumulate);
 }
 
 // wgrad: D[64 x N] += P[128 samples x 64]^T * Q[128 samples x N]: both are activation tiles (CH = 2048) read as
 // MN-major operands with K = samples.  P columns [p_col0, p_col0+64), Q columns [q_col0, q_col0+N).
-__device__ __forceinline__ void gemm_wgrad(uint32_t d_tmem, uint32_t p_saddr, int p_col0, uint32_t q_saddr, int q_col0,
-                                           int N, uint32_t accumulate) {
+__device__ __forceinline__ void gemm_wgrad(uint32_t d_tmem, uint32_t b16, uint32_t p_off, int p_col0, uint32_t q_off,
+                                           int q_col0, int N, uint32_t accumulate) {
     const uint32_t idesc = make_idesc(64, N, 1, 1);
     const uint32_t ch = 2048;
-    uint64_t ad = make_desc(p_saddr + (uint32_t)(p_col0 >> 3) * ch, 128, ch);
-    uint64_t bd = make_desc(q_saddr + (uint32_t)(q_col0 >> 3) * ch, 128, ch);
+    const uint32_t p0 = p_off + (uint32_t)(p_col0 >> 3) * ch, q0 = q_off + (uint32_t)(q_col0 >> 3) * ch;
 #pragma unroll
-    for (int s = 0; s < 128; s += 16) {
-        mma_ss(d_tmem, ad, bd, idesc, (s > 0) ? 1u : accumulate);
-        ad = desc_advance(ad, 256);
-        bd = desc_advance(bd, 256);
-    }
+    for (int s = 0; s < 128; s += 16)
+        mma_ss(d_tmem, desc_at(b16, p0 + (uint32_t)(s >> 3) * 128, 128, ch),
+               desc_at(b16, q0 + (uint32_t)(s >> 3) * 128, 128, ch), idesc, (s > 0) ? 1u : accumulate);
 }
 
 // ---- TMEM -> registers, 64 consecutive columns with a single wait (four loads in flight)
@@ -235,6 +256,33 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- plain shared-memory signal (release add / acquire load): a handshake that stays out of the mbarrier unit
+__device__ __forceinline__ void flag_release_add(uint32_t *flag) {
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(flag)) : "memory");
+}
+__device__ __forceinline__ uint32_t flag_acquire_load(const uint32_t *flag) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(flag)) : "memory");
+    return v;
+}
+// wait until the counter has reached `want` (wrap-safe); bounded like mbar_wait
+__device__ __forceinline__ void flag_wait(const uint32_t *flag, uint32_t want) {
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 26); ++it)
+        if ((int32_t)(flag_acquire_load(flag) - want) >= 0) return;
+    __trap();
+}
+
+// ---- named CTA barriers (the hardware barrier unit: no shared-memory access, unlike mbarriers / flags, whose
+// probes queue behind the tensor core's operand reads).  Producer / consumer form: the producers bar.arrive (they do
+// not wait), the consumer bar.sync; `count` = all participating threads of both sides (a multiple of 32).
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 // ---- mbarrier: arrive / non-blocking test (issuer polling several groups)
@@ -302,11 +350,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 
 // One more K = 16 step whose A operand is the constant tile of ones: adds the bias column stored in the weight
 // tile at K columns [kcol, kcol + 16) (bias in column kcol, zeros behind it) to D[128 x N].
-__device__ __forceinline__ void gemm_bias_step(uint32_t d_tmem, uint32_t ones_saddr, uint32_t b_saddr, int b_rows,
-                                               int b_row0, int N, int kcol) {
+__device__ __forceinline__ void gemm_bias_step(uint32_t d_tmem, uint32_t b16, uint32_t ones_off, uint32_t b_off,
+                                               int b_rows, int b_row0, int N, int kcol) {
     const uint32_t b_ch = (uint32_t)b_rows * 16;
-    mma_ss(d_tmem, make_desc(ones_saddr, 2048, 128),
-           make_desc(b_saddr + (uint32_t)(b_row0 >> 3) * 128 + (uint32_t)(kcol >> 3) * b_ch, b_ch, 128),
+    mma_ss(d_tmem, desc_at(b16, ones_off, 2048, 128),
+           desc_at(b16, b_off + (uint32_t)(b_row0 >> 3) * 128 + (uint32_t)(kcol >> 3) * b_ch, b_ch, 128),
            make_idesc(128, N, 0, 0), 1u);
 }
 

@@ -12,7 +12,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libumhs_sm100.so")
+# UMHS_LIB_PATH: developer override (A/B runs of kernel variants built by tools/build_variant.py)
+LIB_PATH = os.environ.get("UMHS_LIB_PATH") or os.path.join(_HERE, "libumhs_sm100.so")
 
 P = c_void_p  # every device pointer crosses the ABI as a plain address
 
