@@ -116,31 +116,55 @@ __device__ __forceinline__ PointIdx load_point_idx(const umhs_points &P, int64_t
     return i;
 }
 
-__device__ __forceinline__ Point eval_point(const umhs_points &P, int64_t n, const PointIdx &pi) {
-    Point p;
+// The data-level loads of a point (second level of the chain), kept raw so that a kernel can issue them a tile
+// ahead and do the arithmetic when the values are needed: position (explicit form) or ray origin (ray form) in a*,
+// direction in d*, t0 + t1 in tm.
+struct PointRaw {
+    float a0, a1, a2, d0, d1, d2, tm;
+};
+__device__ __forceinline__ PointRaw load_point_raw(const umhs_points &P, int64_t n, const PointIdx &pi) {
+    PointRaw q;
     if (P.positions != nullptr) {
-        p.wx = __ldg(P.positions + 3 * n + 0);
-        p.wy = __ldg(P.positions + 3 * n + 1);
-        p.wz = __ldg(P.positions + 3 * n + 2);
+        q.a0 = __ldg(P.positions + 3 * n + 0);
+        q.a1 = __ldg(P.positions + 3 * n + 1);
+        q.a2 = __ldg(P.positions + 3 * n + 2);
         if (P.directions != nullptr) {
-            p.dx = __ldg(P.directions + 3 * n + 0);
-            p.dy = __ldg(P.directions + 3 * n + 1);
-            p.dz = __ldg(P.directions + 3 * n + 2);
+            q.d0 = __ldg(P.directions + 3 * n + 0);
+            q.d1 = __ldg(P.directions + 3 * n + 1);
+            q.d2 = __ldg(P.directions + 3 * n + 2);
         } else {
-            p.dx = p.dy = p.dz = 1.0f;
+            q.d0 = q.d1 = q.d2 = 1.0f;
         }
-        p.tmid = 0.0f;
+        q.tm = 0.0f;
     } else {
         const int64_t r = pi.r;
-        const float tm = (pi.t0 + pi.t1);
-        p.dx = __ldg(P.rays_d + 3 * r + 0);
-        p.dy = __ldg(P.rays_d + 3 * r + 1);
-        p.dz = __ldg(P.rays_d + 3 * r + 2);
+        q.tm = (pi.t0 + pi.t1);
+        q.d0 = __ldg(P.rays_d + 3 * r + 0);
+        q.d1 = __ldg(P.rays_d + 3 * r + 1);
+        q.d2 = __ldg(P.rays_d + 3 * r + 2);
+        q.a0 = __ldg(P.rays_o + 3 * r + 0);
+        q.a1 = __ldg(P.rays_o + 3 * r + 1);
+        q.a2 = __ldg(P.rays_o + 3 * r + 2);
+    }
+    return q;
+}
+
+__device__ __forceinline__ Point make_point(const umhs_points &P, const PointRaw &q) {
+    Point p;
+    p.dx = q.d0;
+    p.dy = q.d1;
+    p.dz = q.d2;
+    if (P.positions != nullptr) {
+        p.wx = q.a0;
+        p.wy = q.a1;
+        p.wz = q.a2;
+        p.tmid = 0.0f;
+    } else {
         // origins + directions * (starts + ends) / 2   (nerfstudio Frustums.get_positions)
-        p.wx = __ldg(P.rays_o + 3 * r + 0) + (p.dx * tm) / 2.0f;
-        p.wy = __ldg(P.rays_o + 3 * r + 1) + (p.dy * tm) / 2.0f;
-        p.wz = __ldg(P.rays_o + 3 * r + 2) + (p.dz * tm) / 2.0f;
-        p.tmid = tm / 2.0f;
+        p.wx = q.a0 + (p.dx * q.tm) / 2.0f;
+        p.wy = q.a1 + (p.dy * q.tm) / 2.0f;
+        p.wz = q.a2 + (p.dz * q.tm) / 2.0f;
+        p.tmid = q.tm / 2.0f;
     }
     float x = p.wx, y = p.wy, z = p.wz;
     if (P.contraction) {
@@ -165,6 +189,10 @@ __device__ __forceinline__ Point eval_point(const umhs_points &P, int64_t n, con
     p.y = sel ? y : 0.0f;
     p.z = sel ? z : 0.0f;
     return p;
+}
+
+__device__ __forceinline__ Point eval_point(const umhs_points &P, int64_t n, const PointIdx &pi) {
+    return make_point(P, load_point_raw(P, n, pi));
 }
 
 __device__ __forceinline__ Point eval_point(const umhs_points &P, int64_t n) {

@@ -385,34 +385,48 @@ __device__ __forceinline__ void issuer_rotation(uint64_t *bars, const int64_t (&
 // Group tiles: tX [128 x 32] (enc, then [pe, emb, 1]), tH [128 x 64], tF [128 x 64] (its first 32 columns hold
 // the specular input [sh16, pe12, 1] during round 1).  TMEM: 128 working columns per group.
 // =====================================================================================================
-constexpr int G_FWD = 4;
+// Groups in flight: the MMA issuer saturates with three (it needs ~400 cycles per group and round, a group's own
+// chain is ~900), and 13 warps leave 128 registers per thread -- enough to fetch the NEXT tile's inputs two rounds
+// ahead.  With four groups (17 warps, 96 registers) the tile's inputs were loaded at the top of the tile: every group
+// stalled there together (the strict issue rotation keeps the groups in lock step), ~3.3 k of 13 k cycles per
+// iteration.  The density pass (2 rounds, small epilogues) keeps four groups.
+#ifndef UMHS_DENSITY_G
+#define UMHS_DENSITY_G 4
+#endif
+#ifndef UMHS_DENSITY_PREFETCH
+#define UMHS_DENSITY_PREFETCH 0
+#endif
+template <bool DENSITY_ONLY>
+struct TcFwdCfg {
+    static constexpr int G = DENSITY_ONLY ? UMHS_DENSITY_G : 3;
+    static constexpr int kThreads = G * TM + 32;
+};
 struct TcFwd {
     static constexpr int tX = 0;
     static constexpr int tH = tX + TM * 32 * 2;
     static constexpr int tF = tH + TM * 64 * 2;
     static constexpr int grp_bytes = tF + TM * 64 * 2;     // 40 KB
     static constexpr int grp_bytes_density = tF;           // 24 KB
-    static constexpr int kThreads = G_FWD * TM + 32;
     static constexpr int kRounds = 5, kRoundsDensity = 2;
 };
 
 template <bool DENSITY_ONLY>
-__global__ void __launch_bounds__(TcFwd::kThreads, 1)  // 17 warps: 5 on one SM sub-partition (16K registers) -> 96
+__global__ void __launch_bounds__(TcFwdCfg<DENSITY_ONLY>::kThreads, 1)
 field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict__ enc, umhs_mlp_params mp,
                         umhs_field_out out) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr int G = G_FWD;
+    constexpr int G = TcFwdCfg<DENSITY_ONLY>::G;
     constexpr int ROUNDS = DENSITY_ONLY ? TcFwd::kRoundsDensity : TcFwd::kRounds;
     constexpr int GRP_BYTES = DENSITY_ONLY ? TcFwd::grp_bytes_density : TcFwd::grp_bytes;
     constexpr int WCOLS = DENSITY_ONLY ? 64 : 128;   // working TMEM columns per group
-    constexpr int NCOLS = G * WCOLS;
+    constexpr int NCOLS = (G * WCOLS <= 256) ? 256 : 512;  // tcgen05.alloc takes a power of two
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = mp.num_classes, spec = DENSITY_ONLY ? 0 : mp.specular;
     const int grp = tid >> 7, row = tid & 127;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TcSmem::ctrl);  // ready[G], done[G]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TcSmem::ctrl + 64);
 
-    stage_all_weights(smem, mp, DENSITY_ONLY, tid, TcFwd::kThreads);
+    stage_all_weights(smem, mp, DENSITY_ONLY, tid, TcFwdCfg<DENSITY_ONLY>::kThreads);
     if (tid == 0) {
 #pragma unroll
         for (int g = 0; g < G; ++g) {
@@ -479,21 +493,50 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         const uint32_t trow = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(WCOLS * grp);
         const float invT = DENSITY_ONLY ? 1.f : 1.0f / mp.temperature;
 
+        // Inputs of a tile (hash-encoding rows + sample geometry) sit behind a chain of dependent loads (ray index ->
+        // origin / direction, enc_index -> row): the NEXT tile's are issued while the tensor core works on this one --
+        // the index level behind round 0's / 1's arrive, the rows one round later -- and consumed at the next tile's top.
+        float4 e_in[8];
+        PointRaw raw_in;
+        PointIdx pi_in;
+        int64_t erow_in;
+        auto sample_of = [&](int64_t tile) {
+            const int64_t m = tile * TM + row;
+            return m < n_total ? m : n_total - 1;  // tail threads shadow the last sample, write nothing
+        };
+        auto load_idx = [&](int64_t tile) {
+            if (tile >= n_tiles) return;  // group-uniform
+            const int64_t nn = sample_of(tile);
+            pi_in = load_point_idx(P, nn);
+            erow_in = enc_row(P, nn);
+        };
+        auto load_rest = [&](int64_t tile) {
+            if (tile >= n_tiles) return;
+            load_enc_rows(enc, erow_in, lane, e_in);
+            raw_in = load_point_raw(P, sample_of(tile), pi_in);
+        };
+        if (!(DENSITY_ONLY && !UMHS_DENSITY_PREFETCH)) {
+            load_idx(tile_of(0, grp));
+            load_rest(tile_of(0, grp));
+        }
+
         for (int64_t it = 0; tile_of(it, grp) < n_tiles; ++it) {
             gs.round = 0;
             const int64_t n0 = tile_of(it, grp) * TM;
             const bool valid = n0 + row < n_total;
-            const int64_t n = valid ? n0 + row : n_total - 1;  // tail threads shadow the last sample, write nothing
-            const Point pt = eval_point(P, n);
+            const int64_t n = valid ? n0 + row : n_total - 1;
+            if (DENSITY_ONLY && !UMHS_DENSITY_PREFETCH) {
+                load_idx(tile_of(it, grp));
+                load_rest(tile_of(it, grp));
+            }
+            const Point pt = make_point(P, raw_in);
             float pe[12];
             // ---------------- round 0: enc -> tX (whole rows, coalesced) ; base0
-            {
-                float4 e[8];
-                load_enc_rows(enc, enc_row(P, n), lane, e);
-                store_enc_rows(tX, (warp & 3) * 32, lane, e);
-            }
+            store_enc_rows(tX, (warp & 3) * 32, lane, e_in);
             if (!DENSITY_ONLY) pos_encoding_tc(pt, pe);
-            gs.round_trip();
+            gs.arrive();
+            if (DENSITY_ONLY && UMHS_DENSITY_PREFETCH) load_idx(tile_of(it + 1, grp));
+            gs.wait();
             // ---------------- round 1: H0 = relu(.) -> tH ; (specular) [sh, pe, 1] -> tF[:, :32] ; base1 [, dir0]
             epi_relu64<false>(trow, tH, row, nullptr);
             if (spec) {
@@ -508,7 +551,10 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
 #pragma unroll
                 for (int c = 0; c < 4; ++c) store8(tF, row, 8 * c, CH_ACT, x2 + 8 * c);
             }
-            gs.round_trip();
+            gs.arrive();
+            if (DENSITY_ONLY && UMHS_DENSITY_PREFETCH) load_rest(tile_of(it + 1, grp));
+            else if (!DENSITY_ONLY) load_idx(tile_of(it + 1, grp));
+            gs.wait();
             // ---------------- round 2: sigma, emb ; X = [pe, emb, 1] -> tX ; head0 | feat0 (N = 128)
             float o16[16];
             tmem_ld16(trow, o16);
@@ -542,7 +588,9 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
 #pragma unroll
                 for (int c = 0; c < 4; ++c) store8(tX, row, 8 * c, CH_ACT, x + 8 * c);
             }
-            gs.round_trip();
+            gs.arrive();
+            load_rest(tile_of(it + 1, grp));
+            gs.wait();
             // ---------------- round 3: hidden 0 of both MLPs -> tH, tF ; head1, feat1
             epi_relu64<false>(trow, tH, row, nullptr);
             epi_relu64<false>(trow + 64, tF, row, nullptr);
@@ -1253,10 +1301,11 @@ extern "C" int umhs_density_tc_fwd(const umhs_points *pts, int64_t n, const floa
     UMHS_CHECK_ARG(pts && enc && sigma && p && p->base_w0 && p->base_b0 && p->base_w1 && p->base_b1, "null argument");
     umhs_field_out out = {};
     out.sigma = sigma;
-    const int bytes = TcSmem::groups + G_FWD * TcFwd::grp_bytes_density;
+    const int bytes = TcSmem::groups + TcFwdCfg<true>::G * TcFwd::grp_bytes_density;
     UMHS_CHECK_CUDA(cudaFuncSetAttribute(field_mlp_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          bytes));
-    field_mlp_tc_fwd_kernel<true><<<tc_grid(n, G_FWD), TcFwd::kThreads, bytes, as_stream(stream)>>>(*pts, n, enc, *p, out);
+    field_mlp_tc_fwd_kernel<true><<<tc_grid(n, TcFwdCfg<true>::G), TcFwdCfg<true>::kThreads, bytes, as_stream(stream)>>>(
+        *pts, n, enc, *p, out);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }
@@ -1269,11 +1318,11 @@ extern "C" int umhs_field_mlp_tc_fwd(const umhs_points *pts, int64_t n, const fl
     UMHS_CHECK_ARG(p->base_w0 && p->head_w0 && p->head_w1 && p->head_w2 && p->feat_w0 && p->feat_w1 && p->feat_w2,
                    "null weights");
     UMHS_CHECK_ARG(!p->specular || (p->dir_w0 && p->dir_b0), "specular weights missing");
-    const int bytes = TcSmem::groups + G_FWD * TcFwd::grp_bytes;
+    const int bytes = TcSmem::groups + TcFwdCfg<false>::G * TcFwd::grp_bytes;
     UMHS_CHECK_CUDA(cudaFuncSetAttribute(field_mlp_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          bytes));
-    field_mlp_tc_fwd_kernel<false><<<tc_grid(n, G_FWD), TcFwd::kThreads, bytes, as_stream(stream)>>>(*pts, n, enc, *p,
-                                                                                                   *out);
+    field_mlp_tc_fwd_kernel<false><<<tc_grid(n, TcFwdCfg<false>::G), TcFwdCfg<false>::kThreads, bytes, as_stream(stream)>>>(
+        *pts, n, enc, *p, *out);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }
