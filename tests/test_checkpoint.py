@@ -116,3 +116,75 @@ def test_shape_mismatch_is_an_error(tmp_path):
     del ckpt["pipeline"]["module._model.field.endmembers"]
     with pytest.raises(KeyError):
         ck.load_pipeline(_model(1), ckpt["pipeline"], 1)
+
+
+def test_saved_checkpoint_passes_a_strict_reference_style_load(tmp_path):
+    """what the REFERENCE does with a checkpoint -- nerfstudio's Trainer._load_checkpoint feeds
+    optimizers / schedulers / scalers to torch's own load_state_dict, and UMHSPipeline.load_pipeline (ref
+    umhs_pipeline.py:157-175) does a STRICT load_state_dict.  A stub pipeline with the reference's module tree (this
+    model + the LPIPS buffers of NGPModel) must accept the file when the entries this package does not own are
+    carried over from a reference checkpoint (``extras_from``), and must name exactly those entries otherwise."""
+    m = _model(4)
+    tr = UMHSTrainer(m, occ_update=False, start_step=10)
+    tr.opt_steps = 2
+    tr.flat.exp_avg.copy_(torch.randn_like(tr.flat.exp_avg))
+    tr.flat.exp_avg_sq.copy_(torch.rand_like(tr.flat.exp_avg_sq))
+
+    class _Lpips(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.register_buffer("shift", torch.zeros(1, 3, 1, 1))
+
+    class _RefPipeline(torch.nn.Module):  # the reference's tree: pipeline._model = NGPModel subclass with .lpips
+        def __init__(self, model):
+            super().__init__()
+            self._model = model
+            self._model.lpips = _Lpips()
+
+    # a checkpoint "written by the reference" (supplies _model.lpips.*)
+    ref_like = _RefPipeline(_model(5))
+    ref_path = os.path.join(tmp_path, "ref.ckpt")
+    torch.save({"step": 1, "pipeline": {"module." + k: v for k, v in ref_like.state_dict().items()}}, ref_path)
+
+    bare = torch.load(ck.save_checkpoint(str(tmp_path), m, tr), map_location="cpu", weights_only=False)
+    target = _RefPipeline(_model(6))
+    missing = target.load_state_dict(bare["pipeline"], strict=False).missing_keys
+    assert missing == ["_model.lpips.shift"], missing  # only the module this package does not own
+    assert "_model.sampler.occupancy_grid.binaries" in bare["pipeline"]
+
+    full = torch.load(ck.save_checkpoint(str(tmp_path), m, tr, extras_from=ref_path), map_location="cpu",
+                      weights_only=False)
+    target.load_state_dict(full["pipeline"], strict=True)  # what ref umhs_pipeline.py:167 does
+    assert torch.equal(target._model.field.endmembers, m.field.endmembers)
+    # torch's own loaders accept the trainer-side entries
+    by_name = dict(m.field.named_parameters())
+    opt = torch.optim.Adam([by_name[n] for n in ck.reference_param_order(m.field)], lr=2e-2, eps=1e-15)
+    opt.load_state_dict(full["optimizers"]["fields"])
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=lambda s: 1.0)
+    sched.load_state_dict(full["schedulers"]["fields"])
+    assert sched.last_epoch == 11
+    scaler = torch.amp.GradScaler("cpu", enabled=True)
+    scaler.load_state_dict(full["scalers"])  # an empty dict raises here
+
+
+def test_tcnn_checkpoints_are_rejected_with_a_clear_message():
+    src = _model(0)
+    ckpt, *_ = _reference_style_checkpoint(src, 1)
+    pipe = {k: v for k, v in ckpt["pipeline"].items() if "hash_table" not in k}
+    pipe["module._model.field.mlp_base.encoder.tcnn_encoding.params"] = torch.zeros(1000)
+    with pytest.raises(ValueError, match="tcnn"):
+        ck.load_pipeline(_model(1), pipe, 1)
+
+
+def test_sharded_adam_moments_are_gathered_for_saving():
+    """Fused data-parallel step: rank r keeps Adam moments for shard r only.  ``full_optimizer_state`` (used by
+    save_checkpoint) must return the concatenation; single-process form of the logic (the 2-rank gloo run is in
+    tests/test_dp_cpu.py)."""
+    m = _model(7)
+    tr = UMHSTrainer(m, occ_update=False)
+    n = tr.flat.numel
+    assert tr.dp_shard() == (0, n)
+    tr.world_size = 4
+    spans = [tr.dp_shard(r) for r in range(4)]
+    assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+    assert all(lo % 4 == 0 for lo, _ in spans)

@@ -75,3 +75,51 @@ def test_tile_sharding_partitions_the_image():
         assert torch.equal(torch.sort(allidx).values, torch.arange(H * W))
         if H * W > tile * tile * world:
             assert max(p.numel() for p in parts) - min(p.numel() for p in parts) <= 2 * tile * tile
+
+
+def _sharded_moments(rank, world, port, out_dir):
+    """Each rank owns the Adam moments of one shard (what the fused NVLink exchange + Adam kernel leaves behind):
+    save_checkpoint on every rank must gather them, and the file written by rank 0 must hold ALL of them."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import umhs_b200
+        from umhs_b200 import checkpoint as ck
+        from umhs_b200.trainer import UMHSTrainer
+
+        torch.manual_seed(0)
+        cfg = umhs_b200.UMHSConfig(log2_hashmap_size=8, grid_resolution=16)
+        m = cfg.setup(metadata={"wavelengths": list(range(400, 528)), "num_classes": 4})
+        tr = UMHSTrainer(m, occ_update=False, world_size=world, rank=rank, start_step=5)
+        tr.opt_steps = 3
+        g = torch.Generator().manual_seed(1)
+        full_m, full_v = torch.randn(tr.flat.numel, generator=g), torch.rand(tr.flat.numel, generator=g)
+        lo, hi = tr.dp_shard()
+        tr.flat.exp_avg.zero_()
+        tr.flat.exp_avg_sq.zero_()
+        tr.flat.exp_avg[lo:hi] = full_m[lo:hi]      # this rank's shard only, as the fused kernel keeps it
+        tr.flat.exp_avg_sq[lo:hi] = full_v[lo:hi]
+        tr.fused_dp = True                         # (the CUDA-only fused mode; here only its bookkeeping)
+        path = ck.save_checkpoint(out_dir, m, tr, write=(rank == 0))
+        dist.barrier()
+        if rank == 1:  # a fresh single-process trainer resumes from the file rank 0 wrote
+            m2 = cfg.setup(metadata={"wavelengths": list(range(400, 528)), "num_classes": 4})
+            tr2 = UMHSTrainer(m2, occ_update=False)
+            ck.load_checkpoint(path, m2, tr2)
+            by2 = dict(m2.field.named_parameters())
+            for n, p in m.field.named_parameters():
+                a, b = tr.flat.range_of(p)
+                a2, b2 = tr2.flat.range_of(by2[n])
+                assert torch.equal(tr2.flat.exp_avg[a2:b2], full_m[a:b]), n
+                assert torch.equal(tr2.flat.exp_avg_sq[a2:b2], full_v[a:b]), n
+            assert tr2.opt_steps == 3
+            open(os.path.join(out_dir, "ok"), "w").write("1")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_checkpoint_gathers_sharded_adam_state(tmp_path):
+    world, port = 2, 31500 + (os.getpid() % 2000)
+    mp.spawn(_sharded_moments, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert os.path.exists(tmp_path / "ok")

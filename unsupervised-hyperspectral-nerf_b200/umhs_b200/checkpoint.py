@@ -61,6 +61,13 @@ def load_pipeline(model, loaded_state: Dict[str, Tensor], step: int, endmembers_
     grid resolution are fixed at construction, as in the reference); returns the keys that were not loaded.
     endmembers_npy: where to dump the endmembers like ref umhs_pipeline.py:175 (None: do not write a file)."""
     state, skipped = model_state_from_pipeline(loaded_state)
+    tcnn = [k for k in state if "tcnn_encoding" in k or k.endswith(".params")]
+    if tcnn:
+        raise ValueError(
+            "this checkpoint was trained with implementation='tcnn' (flat tiny-cuda-nn parameter blobs such as "
+            f"{tcnn[0]!r}): tiny-cuda-nn's grid (dense coarse levels, no biases, fp16 MLP layout) is a different "
+            "function from nerfstudio's torch path, which is what this package reproduces (north star: the PyTorch "
+            "path).  Re-train or export with --pipeline.model.implementation torch.")
     own = model.state_dict()
     # the sampler holds the same occupancy grid module: reference checkpoints carry it under both names
     for k in list(own):
@@ -114,30 +121,61 @@ def _adam_from_flat(trainer) -> Dict[str, Any]:
     by_name = dict(field.named_parameters())
     state = {}
     names = reference_param_order(field)
+    # fused data-parallel step: every rank holds the moments of its own shard only -> gather them (a collective: every
+    # rank must call save_checkpoint; single-GPU / all-reduce mode: the local buffers are complete)
+    exp_avg, exp_avg_sq = trainer.full_optimizer_state()
     for i, name in enumerate(names):
         p = by_name[name]
         a, b = trainer.flat.range_of(p)
         state[i] = {"step": torch.tensor(float(trainer.opt_steps)),
-                    "exp_avg": trainer.flat.exp_avg[a:b].reshape(p.shape).detach().cpu().clone(),
-                    "exp_avg_sq": trainer.flat.exp_avg_sq[a:b].reshape(p.shape).detach().cpu().clone()}
+                    "exp_avg": exp_avg[a:b].reshape(p.shape).detach().cpu().clone(),
+                    "exp_avg_sq": exp_avg_sq[a:b].reshape(p.shape).detach().cpu().clone()}
     group = {"lr": trainer.lr_at(trainer.step), "betas": tuple(trainer.betas), "eps": trainer.eps, "weight_decay": 0,
              "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
              "fused": None, "params": list(range(len(names)))}
     return {"state": state, "param_groups": [group]}
 
 
-def save_checkpoint(directory: str, model, trainer=None, step: Optional[int] = None) -> str:
-    """Write ``step-{step:09d}.ckpt`` in nerfstudio's layout (loadable by the reference's ``ns-train --load-dir``)."""
+def save_checkpoint(directory: str, model, trainer=None, step: Optional[int] = None,
+                    extras_from: Optional[str] = None, write: bool = True) -> str:
+    """Write ``step-{step:09d}.ckpt`` in nerfstudio's layout.
+
+    What a nerfstudio ``Trainer._load_checkpoint`` + the reference's ``UMHSPipeline.load_pipeline`` (a STRICT
+    ``load_state_dict``, ref umhs_pipeline.py:157-175) find in it: every ``_model.*`` entry of the hot path, the
+    occupancy grid under both of its names (``_model.occupancy_grid.*`` and ``_model.sampler.occupancy_grid.*``), a
+    complete ``torch.optim.Adam`` state for ``"fields"`` in the reference's parameter order, a ``LambdaLR`` scheduler
+    state and an enabled-``GradScaler`` state (the reference trains with ``mixed_precision=True``: ref
+    umhs_config.py:40; an empty dict makes ``GradScaler.load_state_dict`` raise).  What it can NOT contain by itself:
+    the buffers of modules that are not part of this package -- the pretrained LPIPS network of
+    ``NGPModel.lpips`` (``_model.lpips.*``, torchmetrics) and a datamanager's camera optimiser.  ``extras_from`` = a
+    checkpoint written by the reference: its entries that this model does not own are copied over, which makes the
+    file pass the reference's strict load.  With a fused data-parallel trainer EVERY rank must call this (the Adam
+    moments are gathered); ``write=False`` on the ranks that should not write the file."""
     step = int(step if step is not None else (trainer.step if trainer is not None else getattr(model, "step", 0)))
-    os.makedirs(directory, exist_ok=True)
-    pipeline = {"_model." + k: v.detach().cpu() for k, v in model.state_dict().items()
-                if not k.startswith("sampler.")}
-    ckpt: Dict[str, Any] = {"step": step, "pipeline": pipeline, "optimizers": {}, "schedulers": {}, "scalers": {}}
+    pipeline = {"_model." + k: v.detach().cpu() for k, v in model.state_dict().items()}
+    if extras_from is not None:
+        ref = torch.load(extras_from, map_location="cpu", weights_only=False)["pipeline"]
+        for key, value in ref.items():
+            k = key[len("module."):] if key.startswith("module.") else key
+            if k not in pipeline:
+                pipeline[k] = value
+    ckpt: Dict[str, Any] = {"step": step, "pipeline": pipeline, "optimizers": {}, "schedulers": {},
+                            # torch.amp.GradScaler.state_dict() of an enabled scaler (defaults; bf16/f32 kernels here
+                            # never overflow, so the scale is never consulted by this package)
+                            "scalers": {"scale": 65536.0, "growth_factor": 2.0, "backoff_factor": 0.5,
+                                        "growth_interval": 2000, "_growth_tracker": 0}}
     if trainer is not None:
         ckpt["optimizers"]["fields"] = _adam_from_flat(trainer)
-        ckpt["schedulers"]["fields"] = {"last_epoch": step, "_step_count": step + 1}
+        lr = trainer.lr_at(step + 1)
+        # torch.optim.lr_scheduler.LambdaLR.state_dict() (nerfstudio ExponentialDecayScheduler): plain lambdas are
+        # stored as None and kept by the loading side
+        ckpt["schedulers"]["fields"] = {"base_lrs": [trainer.lr_init], "last_epoch": step + 1, "verbose": False,
+                                        "_step_count": step + 2, "_get_lr_called_within_step": False,
+                                        "_last_lr": [lr], "lr_lambdas": [None]}
     path = os.path.join(directory, checkpoint_name(step))
-    torch.save(ckpt, path)
+    if write:
+        os.makedirs(directory, exist_ok=True)
+        torch.save(ckpt, path)
     return path
 
 

@@ -175,6 +175,30 @@ class UMHSTrainer:
         if world_size > 1:  # identical replicas
             dist.broadcast(self.flat.data, src=0)
 
+    def dp_shard(self, rank: Optional[int] = None):
+        """[begin, end) of the flat buffers whose Adam state rank ``rank`` owns in the fused data-parallel step
+        (csrc/optim.cu::umhs_dp_adam_step: ceil(n/4 / world) float4 groups per rank)."""
+        r = self.rank if rank is None else rank
+        n4 = self.flat.numel // 4
+        per = -(-n4 // self.world_size)
+        return 4 * min(per * r, n4), 4 * min(per * (r + 1), n4)
+
+    def full_optimizer_state(self):
+        """(exp_avg, exp_avg_sq) over ALL parameters.  In the fused data-parallel step every rank keeps the moments
+        of its own shard only (the other entries of its buffers stay zero): the shards are gathered here (one
+        collective; checkpoint saving).  Single GPU / all-reduce mode: the local buffers are already complete."""
+        f = self.flat
+        if not self.fused_dp:
+            return f.exp_avg, f.exp_avg_sq
+        out = []
+        for buf in (f.exp_avg, f.exp_avg_sq):
+            full = torch.zeros_like(buf)
+            lo, hi = self.dp_shard()
+            full[lo:hi] = buf[lo:hi]
+            dist.all_reduce(full, op=dist.ReduceOp.SUM)  # shards are disjoint: the sum is the concatenation
+            out.append(full)
+        return out[0], out[1]
+
     def lr_at(self, step: int) -> float:
         """nerfstudio ExponentialDecayScheduler without warm-up: lr_init * (lr_final/lr_init)^(step/max_steps)."""
         t = min(max(step / self.max_steps, 0.0), 1.0)
