@@ -362,7 +362,7 @@ class Dist:
         if self.world > 1:
             # the contract is ONE JSON line on stdout: NCCL_DEBUG=VERSION (set in this image) makes NCCL print its
             # version there; INFO / TRACE asked for by a user are left alone
-            if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
                 os.environ["NCCL_DEBUG"] = "WARN"
             dist.init_process_group("nccl", device_id=self.dev)
 
