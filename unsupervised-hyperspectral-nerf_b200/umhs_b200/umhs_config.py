@@ -12,13 +12,18 @@ HYPERPARAMS = dict(method_name="umhsnerf", steps_per_eval_batch=500, steps_per_s
 
 
 def _build():
+    """The reference's ``umhs_method`` (ref umhs_config.py:34-69) with ``model=`` the B200-native ``UMHSConfig``.  The
+    trainer, viewer and the DATA side (dataparser, datamanager, dataset, pipeline glue) are nerfstudio's and the
+    reference's own ``umhsnerf`` package -- outside the hot path this package replaces."""
     from nerfstudio.configs.base_config import ViewerConfig  # type: ignore
     from nerfstudio.engine.optimizers import AdamOptimizerConfig  # type: ignore
     from nerfstudio.engine.schedulers import ExponentialDecaySchedulerConfig  # type: ignore
     from nerfstudio.engine.trainer import TrainerConfig  # type: ignore
     from nerfstudio.plugins.types import MethodSpecification  # type: ignore
-    from umhsnerf.data.umhs_datamanager import UMHSDataManagerConfig  # the reference's data side is reused as is
-    from umhsnerf.umhs_pipeline import UMHSPipelineConfig
+    from umhsnerf.data.umhs_datamanager import UMHSDataManager, UMHSDataManagerConfig  # type: ignore
+    from umhsnerf.data.umhs_dataparser import UMHSDataParserConfig  # type: ignore
+    from umhsnerf.data.utils.hs_dataloader import HyperspectralDataset  # type: ignore
+    from umhsnerf.umhs_pipeline import UMHSPipelineConfig  # type: ignore
 
     from .umhs_model import UMHSConfig
 
@@ -27,15 +32,17 @@ def _build():
         config=TrainerConfig(
             method_name=h["method_name"], steps_per_eval_batch=h["steps_per_eval_batch"],
             steps_per_save=h["steps_per_save"], max_num_iterations=h["max_num_iterations"],
-            mixed_precision=h["mixed_precision"],
+            mixed_precision=h["mixed_precision"], save_only_latest_checkpoint=False,
             pipeline=UMHSPipelineConfig(
-                datamanager=UMHSDataManagerConfig(train_num_rays_per_batch=h["train_num_rays_per_batch"],
+                datamanager=UMHSDataManagerConfig(_target=UMHSDataManager[HyperspectralDataset],
+                                                  dataparser=UMHSDataParserConfig(),
+                                                  train_num_rays_per_batch=h["train_num_rays_per_batch"],
                                                   eval_num_rays_per_batch=h["eval_num_rays_per_batch"]),
                 model=UMHSConfig(eval_num_rays_per_chunk=h["eval_num_rays_per_chunk"])),
             optimizers={"fields": {"optimizer": AdamOptimizerConfig(lr=h["lr"], eps=h["eps"]),
                                    "scheduler": ExponentialDecaySchedulerConfig(lr_final=h["lr_final"],
                                                                                 max_steps=h["lr_max_steps"])}},
-            viewer=ViewerConfig(num_rays_per_chunk=1 << 15), vis="viewer"),
+            viewer=ViewerConfig(num_rays_per_chunk=1 << 12), vis="viewer"),
         description="UMHS (UnMix-NeRF) with the B200-native hot path (libumhs_sm100).")
 
 

@@ -18,6 +18,8 @@ from __future__ import annotations
 from dataclasses import dataclass, field as dc_field
 from typing import Dict, List, Literal, Optional, Tuple, Type, Union
 
+import os
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -39,8 +41,19 @@ CLASS_COLORS = [
 ]
 
 
+# nerfstudio's own base classes when it is installed (the plugin is then a real ``InstantNGPModelConfig`` /
+# ``NGPModel`` pair: tyro's ``--pipeline.model.*`` flags and the pipeline's isinstance paths see what they expect, ref
+# umhs_model.py:62,122); plain stand-ins otherwise (nerfstudio is absent from the build container).
+try:  # pragma: no cover - exercised with the stub package of tests/test_plugin_cpu.py
+    from nerfstudio.models.instant_ngp import InstantNGPModelConfig as _NSConfigBase, NGPModel as _NSModelBase
+
+    HAVE_NERFSTUDIO = True
+except Exception:  # ModuleNotFoundError or a broken install
+    _NSConfigBase, _NSModelBase, HAVE_NERFSTUDIO = None, None, False
+
+
 @dataclass
-class UMHSConfig:
+class _UMHSFields:
     """Fields of ref umhs_model.py:61-119 (+ the InstantNGPModelConfig / ModelConfig fields the hot path reads)."""
     _target: Type = dc_field(default_factory=lambda: UMHSModel)
     enable_collider: bool = False
@@ -71,8 +84,22 @@ class UMHSConfig:
     # 12.7 ms per image at 2^16 rays per pass, 10.7 ms at 2^18
     eval_tile_rays: int = 1 << 19
 
-    def setup(self, **kwargs) -> "UMHSModel":
-        return self._target(self, **kwargs)
+
+if HAVE_NERFSTUDIO:  # pragma: no cover
+    @dataclass
+    class UMHSConfig(_UMHSFields, _NSConfigBase):  # type: ignore[misc, valid-type]
+        """UMHS model config (a nerfstudio ``InstantNGPModelConfig``)."""
+
+    _ModelBase = _NSModelBase
+else:
+    @dataclass
+    class UMHSConfig(_UMHSFields):  # type: ignore[no-redef]
+        """UMHS model config (stand-alone: nerfstudio is not installed)."""
+
+        def setup(self, **kwargs) -> "UMHSModel":
+            return self._target(self, **kwargs)
+
+    _ModelBase = nn.Module
 
 
 class _SceneBox:
@@ -80,26 +107,53 @@ class _SceneBox:
         self.aabb = aabb
 
 
-class UMHSModel(nn.Module):
+class NearFarCollider(nn.Module):
+    """nerfstudio NearFarCollider (A.4): nears = near_plane while training, 0 in eval (reset_near_plane); fars =
+    far_plane.  The constant planes are cached per ray-batch shape (read-only downstream): no fill launches per step."""
+
+    def __init__(self, near_plane: float, far_plane: float):
+        super().__init__()
+        self.near_plane, self.far_plane = float(near_plane), float(far_plane)
+        self._cache: Dict = {}
+
+    def forward(self, ray_bundle: RayBundle) -> RayBundle:
+        o = ray_bundle.origins
+        near = self.near_plane if self.training else 0.0
+        key = (tuple(o.shape[:-1]), o.device, near, self.far_plane)
+        if key not in self._cache:
+            if len(self._cache) > 8:
+                self._cache.clear()
+            ones = torch.ones_like(o[..., 0:1])
+            self._cache[key] = (ones * near, ones * self.far_plane)
+        ray_bundle.nears, ray_bundle.fars = self._cache[key]
+        return ray_bundle
+
+
+class UMHSModel(_ModelBase):  # type: ignore[misc, valid-type]
     config: UMHSConfig
 
     def __init__(self, config: UMHSConfig, scene_box=None, num_train_data: int = 0, metadata: Optional[dict] = None,
                  **kwargs):
-        super().__init__()
-        self.config = config
         if scene_box is None:
             scene_box = _SceneBox(torch.tensor([[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]]))
         elif isinstance(scene_box, Tensor):
             scene_box = _SceneBox(scene_box)
+        if HAVE_NERFSTUDIO:  # pragma: no cover - nerfstudio's Model.__init__ stores these and calls populate_modules
+            super().__init__(config=config, scene_box=scene_box, num_train_data=num_train_data,
+                             metadata=metadata or {}, **kwargs)
+            return
+        super().__init__()
+        self.config = config
         self.scene_box = scene_box
         self.num_train_data = num_train_data
         self.kwargs = {"metadata": metadata or {}, **kwargs}
         self.device_indicator_param = nn.Parameter(torch.empty(0))
         self.populate_modules()
 
-    @property
-    def device(self):
-        return self.device_indicator_param.device
+    if not HAVE_NERFSTUDIO:
+        @property
+        def device(self):
+            return self.device_indicator_param.device
 
     # ref umhs_model.py:127-218
     def populate_modules(self):
@@ -130,6 +184,13 @@ class UMHSModel(nn.Module):
         self.occupancy_grid = OccGridEstimator(roi_aabb=self.scene_aabb, resolution=res, levels=cfg.grid_levels)
         self.sampler = VolumetricSampler(occupancy_grid=self.occupancy_grid, field=self.field)
         self.cluster_probe = ClusterLookup(len(wl), K)
+        self.collider = NearFarCollider(near_plane=cfg.near_plane, far_plane=cfg.far_plane)  # ref umhs_model.py:212
+        try:  # the pretrained LPIPS network lives in torchmetrics (ref: NGPModel.populate_modules); optional here
+            from torchmetrics.image.lpip import LearnedPerceptualImagePatchSimilarity  # type: ignore
+
+            self.lpips = LearnedPerceptualImagePatchSimilarity(normalize=True)
+        except Exception:
+            self.lpips = None
         self._bg_override: Optional[Tensor] = None  # test hook: fixes the "random" background draw
         # test hook: fixes the stratified near-plane draw of the sampler ([R] in [0,1); nerfacc: rand_like(near_planes));
         # a persistent device tensor, so a captured step graph sees what a test writes into it between replays
@@ -137,20 +198,6 @@ class UMHSModel(nn.Module):
         # None: exact-sized sample buffers (host sync on the sample count, reference behaviour).
         # int: sync-free steps on capacity-sized buffers (set by UMHSTrainer; see VolumetricSampler).
         self.sample_capacity: Optional[int] = None
-
-    # NearFarCollider (A.4): nears = near_plane while training, 0 in eval; fars = far_plane
-    def collider(self, ray_bundle: RayBundle) -> RayBundle:
-        o = ray_bundle.origins
-        near = float(self.config.near_plane if self.training else 0.0)
-        key = (tuple(o.shape[:-1]), o.device, near, float(self.config.far_plane))
-        cache = self.__dict__.setdefault("_collider_cache", {})
-        if key not in cache:  # constant tensors, reused (read-only downstream): no fill launches per step
-            if len(cache) > 8:
-                cache.clear()
-            ones = torch.ones_like(o[..., 0:1])
-            cache[key] = (ones * near, ones * float(self.config.far_plane))
-        ray_bundle.nears, ray_bundle.fars = cache[key]
-        return ray_bundle
 
     def forward(self, ray_bundle: RayBundle) -> Dict[str, Tensor]:
         return self.get_outputs(self.collider(ray_bundle))
@@ -266,6 +313,65 @@ class UMHSModel(nn.Module):
         m["rmse_spectral"] = torch.sqrt(mse_s)
         m["num_samples_per_batch"] = outputs["num_samples_per_ray"].sum()
         return m
+
+    # ------------------------------------------------------------------ ref umhs_model.py:407-527
+    def _blend_gt_background(self, image: Tensor) -> Tensor:
+        """nerfstudio RGBRenderer.blend_background: an RGBA ground truth over the configured background colour
+        ("random" / "last_sample" count as black here, as in nerfstudio)."""
+        if image.shape[-1] < 4:
+            return image
+        bg = 1.0 if self.config.background_color == "white" else 0.0
+        return image[..., :3] * image[..., 3:] + bg * (1.0 - image[..., 3:])
+
+    @torch.no_grad()
+    def get_image_metrics_and_images(self, outputs: Dict[str, Tensor], batch: Dict[str, Tensor]
+                                     ) -> Tuple[Dict[str, float], Dict[str, Tensor]]:
+        """ref umhs_model.py:407-512: PSNR / SSIM / LPIPS of the rendered sRGB image, PSNR / SSIM / SAM / RMSE of the
+        rendered spectrum, and the viewer's image dictionary.  The reference also writes ``seg_pred`` PNGs into a
+        hard-coded ``./eval/ajar_final`` (ref :495-501): kept behind ``UMHS_EVAL_DUMP_DIR``."""
+        from . import metrics as M
+
+        gt_rgb = self._blend_gt_background(batch["image"].to(self.device))
+        predicted_rgb = outputs["rgb"]
+        acc = M.apply_colormap(outputs["accumulation"])
+        depth = M.apply_depth_colormap(outputs["depth"], accumulation=outputs["accumulation"])
+        combined_rgb = torch.cat([gt_rgb, predicted_rgb], dim=1)
+        gt_c = torch.moveaxis(gt_rgb, -1, 0)[None, ...]         # [H, W, C] -> [1, C, H, W]
+        pr_c = torch.moveaxis(predicted_rgb, -1, 0)[None, ...]
+        se_per_pixel = ((gt_c - pr_c) ** 2).squeeze(0).permute(1, 2, 0).mean(dim=-1).unsqueeze(-1)
+        metrics_dict = {"psnr": float(M.psnr(gt_c, pr_c)), "ssim": float(M.ssim(gt_c, pr_c)),
+                        "lpips": M.lpips_or_nan(self.lpips, gt_c, pr_c)}
+        if "spectral" in self.config.method:
+            gt_s = torch.moveaxis(batch["hs_image"].to(self.device), -1, 0)[None, ...]
+            pr_s = torch.moveaxis(outputs["spectral"], -1, 0)[None, ...]
+            metrics_dict["psnr_spectral"] = float(M.psnr(gt_s, pr_s))
+            metrics_dict["ssim_spectral"] = float(M.ssim(gt_s, pr_s))
+            metrics_dict["sam_spectral"] = float(torch.nanmean(M.spectral_angle(pr_s, gt_s)))
+            metrics_dict["rmse_spectral"] = float(torch.sqrt(F.mse_loss(pr_s, gt_s)))
+            self.i = self.i + 1
+            dump = os.environ.get("UMHS_EVAL_DUMP_DIR")
+            if dump:  # the reference's side effect, opt-in: raw class ids + colour-coded segmentation
+                os.makedirs(os.path.join(dump, "color"), exist_ok=True)
+                np.save(os.path.join(dump, f"seg_pred_{self.i}.npy"),
+                        outputs["seg_raw"].cpu().numpy().astype(np.uint8).squeeze())
+                np.save(os.path.join(dump, "color", f"{self.i}.npy"),
+                        (outputs["seg_pred"].cpu().numpy() * 255).astype(np.uint8))
+        images_dict = {"img": combined_rgb, "accumulation": acc, "depth": depth, "se_per_pixel": se_per_pixel}
+        return metrics_dict, images_dict
+
+    def compute_sam(self, pred: Tensor, gt: Tensor, eps: float = 1e-8) -> Tensor:
+        """ref umhs_model.py:514-527"""
+        from .metrics import compute_sam
+
+        return compute_sam(pred, gt, eps)
+
+    # ------------------------------------------------------------------ ref umhs_model.py:529-540
+    @torch.no_grad()
+    def get_outputs_for_camera(self, camera, obb_box=None) -> Dict[str, Tensor]:
+        """Camera -> ray bundle -> full-image outputs (the viewer's and ``ns-eval``'s entry point).  The reference
+        wraps this in fp16 autocast; the kernels here choose their own precision (bf16 tensor-core operands)."""
+        return self.get_outputs_for_camera_ray_bundle(
+            camera.generate_rays(camera_indices=0, keep_shape=True, obb_box=obb_box))
 
     # ------------------------------------------------------------------ ref umhs_model.py:542-591
     def update_occupancy_grid(self, step: int, **kw) -> None:
