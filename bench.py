@@ -51,6 +51,9 @@ SHELL_R, SHELL_T = 0.5, 0.08
 WAVELENGTHS = np.linspace(400, 1000, BANDS).astype(int).tolist()
 CONDITIONING_STEPS = 34
 STRONG_GLOBAL_RAYS = 32768
+# UMHS_BENCH_PIPELINE=1: announce the next batch so that its occupancy march (parameter-independent) runs as a parallel
+# branch of this step's graph (UMHSTrainer.train_step(next_rays=...)); same results
+PIPELINE = bool(int(os.environ.get("UMHS_BENCH_PIPELINE", "1")))  # measured: 1.349 -> 1.306 ms per step
 CPU_RAYS_PER_STEP = 4096   # the CPU arm's rays per step (2 warm-up + 5 timed, median)
 WORKLOADS = {
     "hotdog": {"name": "hotdog-synthetic-train-step", "rays": RAYS_PER_GPU, "K": K_CLASSES, "T": TEMPERATURE,
@@ -325,7 +328,9 @@ def workload_config(wl_key, n_gpus, samples_per_ray=None, rays=None):
          else "single",
          "conditioning_steps": CONDITIONING_STEPS,
          "launch": "whole step replayed as one CUDA graph (march+fwd+loss+bwd+exchange+Adam); occupancy update = "
-                   "its own graph every 16 steps",
+                   "its own graph every 16 steps" + ("; the NEXT batch's occupancy march (parameter-independent) runs "
+                                                      "as a parallel branch beside the hash scatter and the optimiser "
+                                                      "(train_step(next_rays=...))" if PIPELINE else ""),
          "l2_policy": "working set > L2: Adam state 4 x 64 MiB streamed every step + rotating batches"}
     if samples_per_ray is not None:
         c["kept_samples_per_ray"] = samples_per_ray
@@ -412,7 +417,8 @@ class TrainRun:
         from umhs_b200.rays import RayBundle
 
         o, d, image, hs = self.resident[i % self.POOL]
-        return self.trainer.train_step(RayBundle(o, d), {"image": image, "hs_image": hs})
+        nxt = RayBundle(*self.resident[(i + 1) % self.POOL][:2]) if PIPELINE else None
+        return self.trainer.train_step(RayBundle(o, d), {"image": image, "hs_image": hs}, next_rays=nxt)
 
     def _stage(self, j):
         from umhs_b200.rays import RayBundle
@@ -427,7 +433,7 @@ class TrainRun:
         st = self.e2e_state
         while len(st["tokens"]) < 2:
             st["tokens"].append(self._stage(i + len(st["tokens"])))
-        out = self.trainer.train_step(st["tokens"][0])
+        out = self.trainer.train_step(st["tokens"][0], next_rays=st["tokens"][1] if PIPELINE else None)
         loss = self.trainer.read_async(out["loss"])  # device -> host copy of this step's result, on a side stream
         st["tokens"].pop(0)
         st["tokens"].append(self._stage(i + 2))

@@ -262,14 +262,17 @@ __device__ __forceinline__ void store_enc_rows(uint8_t *tile, int warp_row0, int
 }
 // store: every lane holds its own row v[32]; the warp transposes through a private 4 KB staging block (XOR-swizzled
 // 16-byte pieces: conflict-free both ways) and writes whole rows.  row_of_lane < 0: that row is not written.
-__device__ __forceinline__ void store_rows_coalesced(float *__restrict__ dst, int64_t my_row, const float (&v)[32],
-                                                     uint8_t *stage, int lane) {
+// Two halves, so that the global stores can be issued BEHIND the next operand hand-off (fence.proxy.async also waits
+// for the thread's outstanding global stores: stores issued right before it stall the group until they have drained).
+__device__ __forceinline__ void stage_rows(const float (&v)[32], uint8_t *stage, int lane) {
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < 8; ++q)
         *reinterpret_cast<float4 *>(stage + lane * 128 + ((q ^ (lane & 7)) << 4)) =
             make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     __syncwarp();
+}
+__device__ __forceinline__ void flush_staged_rows(float *__restrict__ dst, int64_t my_row, const uint8_t *stage, int lane) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int rl = 4 * i + (lane >> 3);
@@ -277,6 +280,12 @@ __device__ __forceinline__ void store_rows_coalesced(float *__restrict__ dst, in
         const float4 x = *reinterpret_cast<const float4 *>(stage + rl * 128 + (((lane & 7) ^ (rl & 7)) << 4));
         if (r >= 0) reinterpret_cast<float4 *>(dst + r * 32)[lane & 7] = x;
     }
+    __syncwarp();
+}
+__device__ __forceinline__ void store_rows_coalesced(float *__restrict__ dst, int64_t my_row, const float (&v)[32],
+                                                     uint8_t *stage, int lane) {
+    stage_rows(v, stage, lane);
+    flush_staged_rows(dst, my_row, stage, lane);
 }
 
 // ---- group <-> issuer handshake
@@ -863,9 +872,10 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         // (ray index -> origin / direction, enc_index -> encoding row), so the NEXT tile's are fetched during the
         // feature_mlp backward rounds of the current one (a DRAM latency is ~2k cycles, about two rounds).
         float4 e_in[8];
-        Point pt_in;
+        PointRaw raw_in;   // raw loads only: the arithmetic (contraction, selector) waits for the values -> next tile's top
         PointIdx pi_in;
         int64_t erow_in;
+        int64_t pending_row = -1;  // d_enc row of the PREVIOUS tile, staged in shared memory, not yet stored
         auto sample_of = [&](int64_t tile) {
             const int64_t m = tile * TM + row;
             return m < n_total ? m : n_total - 1;
@@ -879,7 +889,7 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         auto load_rest = [&](int64_t tile) {
             if (tile >= n_tiles) return;  // group-uniform
             load_enc_rows(enc, erow_in, lane, e_in);
-            pt_in = eval_point(P, sample_of(tile), pi_in);
+            raw_in = load_point_raw(P, sample_of(tile), pi_in);
         };
         load_idx(tile_of(0, grp));
         load_rest(tile_of(0, grp));
@@ -891,7 +901,7 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             const int64_t n = valid ? n0 + row : n_total - 1;
             // Invalid (tail) rows shadow the last sample and run the whole chain with ZERO incoming gradients: every
             // delta they produce is exactly zero, so they add nothing to the weight gradients and write nothing.
-            const Point pt = pt_in;
+            const Point pt = make_point(P, raw_in);
             float pe[12];
             pos_encoding_tc(pt, pe);
             // ---------------- round 0: enc -> tA0 [, X2 -> tX2]
@@ -908,7 +918,10 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
 #pragma unroll
                 for (int c = 0; c < 4; ++c) store8(tX2, row, 8 * c, CH_ACT, x2 + 8 * c);
             }
-            gs.round_trip();
+            gs.arrive();
+            // the previous tile's d_enc rows (staged in this warp's 4 KB of tD2, which nothing touches before round 2)
+            if (d_enc && it > 0) flush_staged_rows(d_enc, pending_row, tD2 + (warp & 3) * 4096, lane);
+            gs.wait();
             // ---------------- round 1: H0 = relu(.) -> tH1, and kept in registers as packed bf16
             uint32_t h0p[32];
             epi_relu64<true>(trow, tH1, row, h0p);
@@ -950,9 +963,18 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             }
             gs.round_trip();
             // ================= mlp_head (m = 0) then feature_mlp (m = 1): rounds 3..7 and 8..13
+            float dsg = 0.f;  // d loss / d sigma of this sample (fetched with the second MLP's gradients)
 #pragma unroll 1
             for (int m = 0; m < 2; ++m) {
                 const int nout = m ? K + spec : K;
+                // incoming gradients of this MLP's outputs (and, with the second MLP, of the density): issued three
+                // rounds before their use -- they come from DRAM
+                float gin[KM + 1];
+#pragma unroll
+                for (int k = 0; k < KM; ++k)
+                    gin[k] = (valid && k < K) ? __ldg((m ? g.d_abund : g.d_scalar) + n * K + k) : 0.f;
+                gin[KM] = (valid && m == 1 && spec && g.d_s1) ? __ldg(g.d_s1 + n) : 0.f;
+                if (m == 1) dsg = (valid && g.d_sigma) ? __ldg(g.d_sigma + n) : 0.f;
                 if (m == 1) {
                     // collect d X of mlp_head (working columns 12..26), then run feature_mlp layer 0 (round 8)
                     float dx[32];
@@ -964,12 +986,6 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                 epi_relu64<false>(trow, tH1, row, nullptr);
                 gs.round_trip();  // layer 1
                 epi_relu64<false>(trow, tH2, row, nullptr);
-                // incoming gradients of this MLP's outputs: fetched while the tensor core runs the last layer
-                float gin[KM + 1];
-#pragma unroll
-                for (int k = 0; k < KM; ++k)
-                    gin[k] = (valid && k < K) ? __ldg((m ? g.d_abund : g.d_scalar) + n * K + k) : 0.f;
-                gin[KM] = (valid && m == 1 && spec && g.d_s1) ? __ldg(g.d_s1 + n) : 0.f;
                 gs.round_trip();  // layer 2
                 {
                     // z: logits 0..KM-1 and (feature_mlp with specular) the gate logit, which sits at column K
@@ -1052,7 +1068,6 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
 #pragma unroll
                 for (int i = 0; i < 15; ++i) demb[i] += dx[12 + i];
                 // density = trunc_exp(o0) * sel  ->  d o0 = d_sigma * sel * exp(clamp(o0, -15, 15))
-                const float dsg = (valid && g.d_sigma) ? __ldg(g.d_sigma + n) : 0.f;
                 dO[0] = dsg * pt.sel * __expf(fminf(fmaxf(o16[0], -15.0f), 15.0f));
 #pragma unroll
                 for (int i = 0; i < 15; ++i) dO[1 + i] = demb[i];
@@ -1070,12 +1085,15 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             epi_mask64(trow, nullptr, h0p, tD2, row);
             gs.round_trip();
             if (d_enc) {
-                // whole rows, coalesced, through this warp's 4 KB of the (now idle) tD1 tile
+                // whole rows, coalesced, through this warp's 4 KB of the (now idle) tD2 tile; the global stores go out
+                // behind the next tile's first hand-off (or after the loop)
                 float v[32];
                 tmem_ld32(trow, v);
-                store_rows_coalesced(d_enc, valid ? n : -1, v, tD1 + (warp & 3) * 4096, lane);
+                stage_rows(v, tD2 + (warp & 3) * 4096, lane);
+                pending_row = valid ? n : -1;
             }
         }
+        if (d_enc && tile_of(0, grp) < n_tiles) flush_staged_rows(d_enc, pending_row, tD2 + (warp & 3) * 4096, lane);
         gs.tr.flush();
         if (colsum_owner<KM>(lane)) {  // one lane of each run owns column colsum_col<KM>(lane)
             const int col = colsum_col<KM>(lane);

@@ -634,9 +634,31 @@ extern "C" int umhs_occ_pack_bits(const umhs_march_args *a, uint32_t *bits, int3
     return UMHS_OK;
 }
 
+// Shared-memory carve-out of the march / scan kernels (percent of the SM's unified L1 + shared memory; -1 = the
+// driver's default, i.e. all L1 for these kernels, which use none).  An SM runs ONE carve-out configuration at a time:
+// with the default, a march CTA cannot share an SM with the persistent tensor-core MLP kernels (~222 KB of shared
+// memory) -- set to 100 when the march of the next batch is forked beside them (UMHSTrainer, pipelined mode).
+static int g_march_carveout = -2;
+static void apply_march_carveout() {
+    if (g_march_carveout == -2) {
+        const char *e = getenv("UMHS_MARCH_CARVEOUT");
+        g_march_carveout = e ? atoi(e) : -1;
+        if (g_march_carveout >= 0) {
+            cudaFuncSetAttribute(march_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, g_march_carveout);
+            cudaFuncSetAttribute(march_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, g_march_carveout);
+            cudaFuncSetAttribute(march_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, g_march_carveout);
+            cudaFuncSetAttribute(march_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, g_march_carveout);
+            cudaFuncSetAttribute(march_write_staged_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, g_march_carveout);
+            cudaFuncSetAttribute(march_write_staged_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, g_march_carveout);
+            cudaFuncSetAttribute(pack_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, g_march_carveout);
+        }
+    }
+}
+
 extern "C" int umhs_march_count(const umhs_march_args *a, int64_t *counts, void *stream) {
     UMHS_CHECK_ARG(check_march(a) == 0 && counts, "bad march arguments");
     if (a->n_rays <= 0) return UMHS_OK;
+    apply_march_carveout();
     // The trainer runs this kernel beside the hash scatter and the optimiser of the previous step (kernels without
     // shared memory, like this one: all of the SM's 256 KB stays L1 and the bit-packed level-0 grid stays resident).
     const int rpw = march_rays_per_warp(a->n_rays);

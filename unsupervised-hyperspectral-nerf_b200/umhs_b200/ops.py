@@ -322,6 +322,8 @@ class FieldFunction(torch.autograd.Function):
         sinks = {n: _sink(w) for n, w in zip(MLP_NAMES, p_mlp)}
         d_w_in = {n: (sinks[n] if sinks[n] is not None else torch.zeros_like(w, dtype=torch.float32))
                   for n, w in weights.items() if w is not None}
+        if BEFORE_MLP_BACKWARD is not None:
+            BEFORE_MLP_BACKWARD()  # trainer hook: fork work that should run beside the MLP backward as well
         d_enc, d_w = field_mlp_bwd(pts, enc, weights, K, cfg["specular"], cfg["temperature"], grads, d_w_in)
         if AFTER_MLP_BACKWARD is not None:
             AFTER_MLP_BACKWARD()  # trainer hook: fork work that should run beside the hash scatter and the optimiser
@@ -563,6 +565,7 @@ class AccumulateFunction(torch.autograd.Function):
 
 # --------------------------------------------------------------------------------------- packing
 AFTER_MLP_BACKWARD = None  # optional callable, see FieldFunction.backward / trainer.UMHSTrainer._capture
+BEFORE_MLP_BACKWARD = None
 MARCH_STAGE = 192  # staged interval starts per ray (0 disables staging: the write pass marches again)
 MARCH_BITS = True   # march on a bit-packed copy of the occupancy grid (identical results)
 

@@ -518,11 +518,15 @@ class UMHSTrainer:
                             dst.copy_(src)
                     forked.append(branch)
 
-                ops.AFTER_MLP_BACKWARD = fork_march
+                early = os.environ.get("UMHS_PIPE_FORK", "after") == "before"
+                if early:
+                    ops.BEFORE_MLP_BACKWARD = fork_march
+                else:
+                    ops.AFTER_MLP_BACKWARD = fork_march
                 try:
                     out = self._forward_backward(rb, bt, premarched=tuple(st["pm_cur"]))
                 finally:
-                    ops.AFTER_MLP_BACKWARD = None
+                    ops.AFTER_MLP_BACKWARD = ops.BEFORE_MLP_BACKWARD = None
                 if not forked:  # no field backward ran (cannot happen in training): march in line
                     fork_march()
             else:
