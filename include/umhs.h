@@ -313,8 +313,21 @@ int umhs_pack_info(const int64_t *ray_indices, int64_t n, int64_t n_rays, int64_
 
 /* Occupancy grid update (ref umhs_model.py:549-554 -> nerfacc update_every_n_steps):
  * occs[idx] = max(occs[idx]*decay, occ); then binaries = occs > min(mean(occs), thre). */
-int umhs_occ_cell_points(const int64_t *cell_ids /*or NULL: 0..n-1*/, const float *jitter /*[n,3]*/, int64_t n, int32_t resolution,
+/* cell -> jittered point inside it.  jitter [n,3] in [0,1), or NULL: drawn in the kernel from (seed, index) -- a
+ * counter-based generator, identical on every data-parallel rank that shares the seed; seed_dev (optional device
+ * uint64) is mixed in, so that a captured CUDA graph draws fresh numbers on every replay.  cell id < 0: slot skipped. */
+int umhs_occ_cell_points(const int64_t *cell_ids /*or NULL: 0..n-1*/, const float *jitter /*[n,3] or NULL*/,
+                         uint64_t seed, const uint64_t *seed_dev, int64_t n, int32_t resolution,
                          const float *aabb6 /*device, level aabb*/, float *positions, void *stream);
+/* Steady-state cell choice of nerfacc's update (OccGridEstimator._sample_uniform_and_occupied_cells, one level):
+ * cell_ids [2 n_uniform] = n_uniform uniform cells (floor(u * n_cells)), then the occupied cells: all of them in
+ * increasing order when there are at most n_uniform (unused slots = -1), else n_uniform picks with replacement
+ * (rank = floor(u * count)).  bits = the level's bit-packed binaries (umhs_occ_pack_bits); u_uniform / u_pick
+ * [n_uniform] inject the draws (parity tests) or NULL (drawn from seed); prefix = scratch int32 [n_cells/32 + 2 + ceil(n_cells/32768)];
+ * n_valid (device int64, optional) = n_uniform + min(count, n_uniform).  Replaces nonzero() + randint() + a full sort. */
+int umhs_occ_select_cells(const uint32_t *bits, int64_t n_cells, int64_t n_uniform, const float *u_uniform,
+                          const float *u_pick, uint64_t seed, const uint64_t *seed_dev, int32_t *prefix,
+                          int64_t *cell_ids, int64_t *n_valid, void *stream);
 int umhs_occ_ema_update(float *occs, const int64_t *cell_ids, int64_t level_offset, const float *sigma, float scale,
                         float decay, int64_t n, float *tmp /*[n] scratch*/, void *stream);
 int umhs_occ_binarize(const float *occs, int64_t n_cells, float occ_thre, double *scratch /*[2]*/, uint8_t *binaries,

@@ -439,9 +439,12 @@ class OccGridEstimator(nn.Module):
 
     @torch.no_grad()
     def update_every_n_steps(self, step, occ_eval_fn, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16,
-                             cell_ids: Optional[List[Tensor]] = None, cell_jitter: Optional[List[Tensor]] = None):
+                             cell_ids: Optional[List[Tensor]] = None, cell_jitter: Optional[List[Tensor]] = None,
+                             cell_draws=None):
         """A.4 ``update_every_n_steps``.  The random cell choice / in-cell jitter can be
-        injected (``cell_ids`` / ``cell_jitter`` per level) for parity tests."""
+        injected (``cell_ids`` / ``cell_jitter`` per level) for parity tests; ``cell_draws`` =
+        (uniform draws, pick draws) per level, float32 in [0, 1), stands for the two ``torch.randint``
+        calls of the steady-state selection (randint(n) == floor(u * n) in distribution)."""
         if not (self.training and step % n == 0):
             return
         res = int(self.resolution[0])
@@ -453,10 +456,16 @@ class OccGridEstimator(nn.Module):
                 idx = torch.arange(n_cells)
             else:
                 n_u = n_cells // 4
-                uni = torch.randint(n_cells, (n_u,))
                 occ_idx = torch.nonzero(self.binaries[lvl].flatten())[:, 0]
-                if n_u < len(occ_idx):
-                    occ_idx = occ_idx[torch.randint(len(occ_idx), (n_u,))]
+                if cell_draws is None:
+                    uni = torch.randint(n_cells, (n_u,))
+                    if n_u < len(occ_idx):
+                        occ_idx = occ_idx[torch.randint(len(occ_idx), (n_u,))]
+                else:
+                    uu, up = cell_draws[0][lvl].float(), cell_draws[1][lvl].float()
+                    uni = (uu * float(n_cells)).long().clamp(max=n_cells - 1)
+                    if n_u < len(occ_idx):
+                        occ_idx = occ_idx[(up * float(len(occ_idx))).long().clamp(max=len(occ_idx) - 1)]
                 idx = torch.cat([uni, occ_idx], dim=0)
             coords = torch.stack([idx // (res * res), (idx // res) % res, idx % res], dim=-1).float()
             jit = cell_jitter[lvl] if cell_jitter is not None else torch.rand_like(coords)

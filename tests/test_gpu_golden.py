@@ -315,3 +315,70 @@ def test_packed_grid_follows_binaries():
         g.binaries.view(torch.uint8).zero_()
         g.mark_dirty()
         assert int(cached(g)[0].abs().sum()) == 0 and int(cached(g)[1].sum()) == 0
+
+
+@pytest.mark.parametrize("density", [0.05, 0.6])
+def test_occupancy_steady_state_selection_matches_oracle(density):
+    """the STEADY-STATE path of update_every_n_steps (step >= warm-up: n/4 uniform cells +
+    the occupied cells -- all of them when there are at most n/4 (density 0.05), n/4 random picks otherwise (0.6))
+    runs in ``umhs_occ_select_cells``, not in torch; with the uniform / pick draws and the in-cell jitter injected on
+    both sides, the chosen cells and the updated grid must equal the oracle's nonzero() + randint() restatement.
+    Cells drawn more than once see the OLD occs on every draw (one read phase per level)."""
+    from helpers import oracle_model_from_golden
+
+    d, meta = load_golden("model_train_k4.npz")
+    res = meta["grid_res"]
+    n_cells, n_u = res ** 3, res ** 3 // 4
+    g = torch.Generator().manual_seed(11)
+    occupied = torch.rand(4, res, res, res, generator=g) < density
+    draws = ([torch.rand(n_u, generator=g) for _ in range(4)], [torch.rand(n_u, generator=g) for _ in range(4)])
+    om = oracle_model_from_golden(d, meta, training=True)
+    om.occupancy_grid.binaries = occupied.clone()
+    om.occupancy_grid.occs = torch.rand(4 * n_cells, generator=g) * 0.02
+    occs0 = om.occupancy_grid.occs.clone()
+    # the selection itself, level by level
+    with mlp_precision("fp32"):
+        m = b200_model_from_golden(d, meta, True)
+        m.occupancy_grid.binaries.copy_(occupied.to(DEV))
+        m.occupancy_grid.occs.copy_(occs0.to(DEV))
+        m.occupancy_grid.mark_dirty()
+        from umhs_b200 import ops
+        from umhs_b200._lib import ptr, stream_ptr
+
+        bits = m.occupancy_grid.packed_grid()[0]
+        prefix = torch.empty((n_cells // 32 + 2 + (n_cells + 32767) // 32768,), dtype=torch.int32, device=DEV)
+        chosen = []
+        for lvl in range(4):
+            idx = torch.empty((2 * n_u,), dtype=torch.int64, device=DEV)
+            nv = torch.empty((1,), dtype=torch.int64, device=DEV)
+            uu, up = draws[0][lvl].to(DEV), draws[1][lvl].to(DEV)  # (kept alive: the call takes raw addresses)
+            ops._call("umhs_occ_select_cells", 0, ptr(bits[lvl]), n_cells, n_u, ptr(uu), ptr(up), 0, None,
+                      ptr(prefix), ptr(idx), ptr(nv), stream_ptr(torch.device(DEV)))
+            occ_idx = torch.nonzero(occupied[lvl].flatten())[:, 0]
+            uni = (draws[0][lvl] * float(n_cells)).long().clamp(max=n_cells - 1)
+            if n_u < len(occ_idx):
+                occ_idx = occ_idx[(draws[1][lvl] * float(len(occ_idx))).long().clamp(max=len(occ_idx) - 1)]
+            want = torch.cat([uni, occ_idx])
+            assert int(nv) == want.numel(), (lvl, int(nv), want.numel())
+            assert torch.equal(idx[: int(nv)].cpu(), want), lvl
+            assert bool((idx[int(nv):] == -1).all())
+            chosen.append(want)
+        # the whole update through the model surface, draws + jitter injected
+        jitter = [torch.rand(c.numel(), 3, generator=g) for c in chosen]
+        m.update_occupancy_grid(512, cell_draws=draws, cell_jitter=[torch.cat([j, torch.zeros(2 * n_u - j.shape[0], 3)])
+                                                                     for j in jitter])
+    om.update_occupancy_grid(512, cell_draws=draws, cell_jitter=jitter)
+    got, want = m.occupancy_grid.occs.cpu(), om.occupancy_grid.occs
+    # a cell drawn twice (with two different in-cell offsets) keeps ONE of its candidates, whichever write lands last
+    # (torch index-assign semantics on both sides): compare the cells that were drawn at most once exactly, the rest
+    # against the range of their candidates
+    for lvl in range(4):
+        ids, counts = torch.unique(chosen[lvl], return_counts=True)
+        once = ids[counts == 1] + lvl * n_cells
+        assert_close(got[once], want[once], 1e-4, 1e-7, f"occs level {lvl} (cells drawn once)")
+        untouched = torch.ones(n_cells, dtype=torch.bool)
+        untouched[ids] = False
+        sl = slice(lvl * n_cells, (lvl + 1) * n_cells)
+        assert torch.equal(got[sl][untouched], occs0[sl][untouched])
+        multi = ids[counts > 1] + lvl * n_cells
+        assert bool((got[multi] >= occs0[multi] * 0.95 - 1e-9).all())  # never decayed twice

@@ -538,35 +538,153 @@ __global__ void count_rays_kernel(const int64_t *__restrict__ ray_indices, int64
 }
 
 // ------------------------------------------------------------------ occupancy grid maintenance
+// counter-based uniform draws for the grid update (splitmix64 of seed + counter): deterministic in (seed, index), so
+// data-parallel replicas that share the seed pick the same cells and the same in-cell offsets without a collective
+__device__ __forceinline__ float occ_uniform(uint64_t seed, uint64_t counter) {
+    uint64_t z = seed + (counter + 1ull) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(z >> 40) * (1.0f / 16777216.0f);  // 24 bits -> [0, 1)
+}
+
+// cell -> point inside the cell: x = (coord + jitter) / res mapped into the level's aabb.  jitter NULL: drawn from
+// (seed, 3 i + k).  id < 0 (an unused slot of umhs_occ_select_cells): skipped.
 __global__ void occ_cell_points_kernel(const int64_t *__restrict__ cell_ids, const float *__restrict__ jitter,
-                                       int64_t n, int res, const float *__restrict__ aabb, float *__restrict__ pos) {
+                                       uint64_t seed, const uint64_t *__restrict__ seed_dev, int64_t n, int res,
+                                       const float *__restrict__ aabb, float *__restrict__ pos) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (seed_dev) seed += *seed_dev * 0xD1342543DE82EF95ull;  // device-side epoch: advances across CUDA-graph replays
     const int64_t id = cell_ids ? cell_ids[i] : i;
+    if (id < 0) {
+        pos[3 * i] = pos[3 * i + 1] = pos[3 * i + 2] = 0.f;
+        return;
+    }
     const float fres = (float)res;
     const float c[3] = {(float)(id / ((int64_t)res * res)), (float)((id / res) % res), (float)(id % res)};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const float x = (c[k] + jitter[3 * i + k]) / fres;
+        const float j = jitter ? jitter[3 * i + k] : occ_uniform(seed, (uint64_t)(3 * i + k));
+        const float x = (c[k] + j) / fres;
         pos[3 * i + k] = aabb[k] + x * (aabb[3 + k] - aabb[k]);
     }
 }
 
+// ---- steady-state cell selection (nerfacc OccGridEstimator._sample_uniform_and_occupied_cells for one level):
+// n_u uniform cells, then the occupied cells -- all of them, in increasing order, when there are at most n_u, else n_u
+// random picks with replacement.  The reference uses nonzero() + randint(); here the occupied cells come from the
+// bit-packed grid by rank: prefix[w] = set bits in words [0, w), rank r -> binary search for its word, then the
+// (r - prefix[w] + 1)-th set bit of that word.  No sort, no host sync; unused slots are -1.
+constexpr int kPrefixThreads = 1024;
+// two-level prefix: block b scans its 1024 words (prefix[w] = set bits in the block's words before w) and publishes its
+// total in prefix[n_words + 1 + b]; the select kernel turns the totals into block bases (a handful of blocks: 64 at
+// 128^3 cells) and searches block, then word
+__global__ void __launch_bounds__(kPrefixThreads)
+occ_popc_prefix_kernel(const uint32_t *__restrict__ bits, int64_t n_words, int32_t *__restrict__ prefix) {
+    __shared__ int32_t warp_tot[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t w = (int64_t)blockIdx.x * kPrefixThreads + tid;
+    const int32_t mine = w < n_words ? __popc(bits[w]) : 0;
+    int32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int32_t v = warp_tot[lane];
+        int32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t t = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += t;
+        }
+        warp_tot[lane] = inc - v;
+        if (lane == 31) prefix[n_words + 1 + blockIdx.x] = inc;  // this block's total
+    }
+    __syncthreads();
+    if (w < n_words) prefix[w] = warp_tot[warp] + incl - mine;
+}
+
+constexpr int kMaxPrefixBlocks = 2048;  // 2 M words = 64 M cells per level
+__global__ void occ_select_kernel(const uint32_t *__restrict__ bits, const int32_t *__restrict__ prefix, int64_t n_words,
+                                  int64_t n_cells, int64_t n_u, const float *__restrict__ u_uniform,
+                                  const float *__restrict__ u_pick, uint64_t seed,
+                                  const uint64_t *__restrict__ seed_dev, int64_t *__restrict__ cell_ids,
+                                  int64_t *__restrict__ n_valid) {
+    extern __shared__ int32_t block_base[];  // [n_blocks + 1] exclusive prefix of the block totals
+    const int n_blocks = (int)((n_words + kPrefixThreads - 1) / kPrefixThreads);
+    if (threadIdx.x == 0) {
+        int32_t run = 0;
+        for (int b = 0; b < n_blocks; ++b) {
+            block_base[b] = run;
+            run += prefix[n_words + 1 + b];
+        }
+        block_base[n_blocks] = run;
+    }
+    __syncthreads();
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (seed_dev) seed += *seed_dev * 0xD1342543DE82EF95ull;
+    const int64_t count = block_base[n_blocks];
+    if (j == 0 && n_valid) *n_valid = n_u + (count < n_u ? count : n_u);
+    if (j >= 2 * n_u) return;
+    if (j < n_u) {  // torch.randint(n_cells, (n_u,))
+        const float u = u_uniform ? u_uniform[j] : occ_uniform(seed, (uint64_t)j);
+        int64_t c = (int64_t)(u * (float)n_cells);
+        cell_ids[j] = c < n_cells ? c : n_cells - 1;
+        return;
+    }
+    const int64_t s = j - n_u;
+    int64_t rank;
+    if (count <= n_u) {
+        if (s >= count) {
+            cell_ids[j] = -1;
+            return;
+        }
+        rank = s;  // all occupied cells, in increasing order (nonzero())
+    } else {       // occ_idx[torch.randint(len(occ_idx), (n_u,))]
+        const float u = u_pick ? u_pick[s] : occ_uniform(seed, (uint64_t)(n_u + s));
+        rank = (int64_t)(u * (float)count);
+        if (rank >= count) rank = count - 1;
+    }
+    int lo = 0, hi = n_blocks;  // last block whose base <= rank
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (block_base[mid] <= rank) lo = mid;
+        else hi = mid;
+    }
+    const int32_t r_in = (int32_t)(rank - block_base[lo]);
+    int64_t wl = (int64_t)lo * kPrefixThreads, wh = wl + kPrefixThreads < n_words ? wl + kPrefixThreads : n_words;
+    while (wh - wl > 1) {  // last word of the block whose in-block prefix <= r_in
+        const int64_t mid = (wl + wh) >> 1;
+        if (prefix[mid] <= r_in) wl = mid;
+        else wh = mid;
+    }
+    const int bit = __fns(bits[wl], 0, r_in - prefix[wl] + 1);
+    cell_ids[j] = wl * 32 + bit;
+}
+
 // occs[id] = max(occs[id] * decay, sigma * scale): phase 1 reads, phase 2 scatters (torch index-assign
-// semantics: the right-hand side sees only old values; duplicate ids: any one of them wins)
+// semantics: the right-hand side sees only old values; duplicate ids: any one of them wins).  id < 0: skipped.
 __global__ void occ_ema_read_kernel(const float *__restrict__ occs, const int64_t *__restrict__ cell_ids,
                                     int64_t level_offset, const float *__restrict__ sigma, float scale, float decay,
                                     int64_t n, float *__restrict__ tmp) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int64_t id = (cell_ids ? cell_ids[i] : i) + level_offset;
-    tmp[i] = fmaxf(occs[id] * decay, sigma[i] * scale);
+    const int64_t c = cell_ids ? cell_ids[i] : i;
+    if (c < 0) return;
+    tmp[i] = fmaxf(occs[c + level_offset] * decay, sigma[i] * scale);
 }
 __global__ void occ_ema_write_kernel(float *__restrict__ occs, const int64_t *__restrict__ cell_ids,
                                      int64_t level_offset, int64_t n, const float *__restrict__ tmp) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    occs[(cell_ids ? cell_ids[i] : i) + level_offset] = tmp[i];
+    const int64_t c = cell_ids ? cell_ids[i] : i;
+    if (c < 0) return;
+    occs[c + level_offset] = tmp[i];
 }
 
 __global__ void occ_sum_kernel(const float *__restrict__ occs, int64_t n, double *scratch) {
@@ -749,12 +867,29 @@ extern "C" int umhs_pack_info(const int64_t *ray_indices, int64_t n, int64_t n_r
     return UMHS_OK;
 }
 
-extern "C" int umhs_occ_cell_points(const int64_t *cell_ids, const float *jitter, int64_t n, int32_t resolution,
-                                    const float *aabb6, float *positions, void *stream) {
-    UMHS_CHECK_ARG(jitter && aabb6 && positions && resolution > 0, "bad argument");
+extern "C" int umhs_occ_cell_points(const int64_t *cell_ids, const float *jitter, uint64_t seed,
+                                    const uint64_t *seed_dev, int64_t n, int32_t resolution, const float *aabb6,
+                                    float *positions, void *stream) {
+    UMHS_CHECK_ARG(aabb6 && positions && resolution > 0, "bad argument");
     if (n <= 0) return UMHS_OK;
-    occ_cell_points_kernel<<<div_up(n, 256), 256, 0, as_stream(stream)>>>(cell_ids, jitter, n, resolution, aabb6,
-                                                                          positions);
+    occ_cell_points_kernel<<<div_up(n, 256), 256, 0, as_stream(stream)>>>(cell_ids, jitter, seed, seed_dev, n,
+                                                                          resolution, aabb6, positions);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_occ_select_cells(const uint32_t *bits, int64_t n_cells, int64_t n_uniform, const float *u_uniform,
+                                     const float *u_pick, uint64_t seed, const uint64_t *seed_dev, int32_t *prefix,
+                                     int64_t *cell_ids, int64_t *n_valid, void *stream) {
+    UMHS_CHECK_ARG(bits && prefix && cell_ids && n_cells > 0 && n_uniform > 0, "bad argument");
+    UMHS_CHECK_ARG(n_cells < ((int64_t)1 << 31), "grid too large");
+    const int64_t n_words = (n_cells + 31) / 32;
+    const int n_blocks = div_up(n_words, kPrefixThreads);
+    UMHS_CHECK_ARG(n_blocks <= kMaxPrefixBlocks, "grid too large");
+    occ_popc_prefix_kernel<<<n_blocks, kPrefixThreads, 0, as_stream(stream)>>>(bits, n_words, prefix);
+    UMHS_CHECK_LAUNCH();
+    occ_select_kernel<<<div_up(2 * n_uniform, 256), 256, (n_blocks + 1) * sizeof(int32_t), as_stream(stream)>>>(
+        bits, prefix, n_words, n_cells, n_uniform, u_uniform, u_pick, seed, seed_dev, cell_ids, n_valid);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }

@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_uint64, c_void_p
 from typing import Optional
 
 import torch
@@ -130,7 +130,8 @@ _SIGNATURES = {
     "umhs_visibility_mask": [P, c_int64, P, P, P, c_float, c_float, P, P, P, P],
     "umhs_compact_samples": [P, P, c_int64, P, P, P, P, P, P, P, P],
     "umhs_pack_info": [P, c_int64, c_int64, P, P, P],
-    "umhs_occ_cell_points": [P, P, c_int64, c_int32, P, P, P],
+    "umhs_occ_cell_points": [P, P, c_uint64, P, c_int64, c_int32, P, P, P],
+    "umhs_occ_select_cells": [P, c_int64, c_int64, P, P, c_uint64, P, P, P, P, P],
     "umhs_occ_ema_update": [P, P, c_int64, P, c_float, c_float, c_int64, P, P],
     "umhs_occ_binarize": [P, c_int64, c_float, P, P, P, P],
     "umhs_adam_step": [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int32, P, P, c_int64, c_int64,

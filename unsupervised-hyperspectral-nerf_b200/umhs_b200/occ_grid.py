@@ -141,13 +141,20 @@ class OccGridEstimator(nn.Module):
     @torch.no_grad()
     def update_every_n_steps(self, step: int, occ_eval_fn: Callable, occ_thre: float = 1e-2, ema_decay: float = 0.95,
                              warmup_steps: int = 256, n: int = 16, cell_ids: Optional[List[Tensor]] = None,
-                             cell_jitter: Optional[List[Tensor]] = None, freeze_binaries: bool = False) -> None:
+                             cell_jitter: Optional[List[Tensor]] = None, freeze_binaries: bool = False,
+                             cell_draws: Optional[Tuple[List[Tensor], List[Tensor]]] = None) -> None:
         """occs[id] = max(occs[id]*decay, occ_eval_fn(x)); binaries = occs > min(mean(occs), occ_thre).
-        ``cell_ids`` / ``cell_jitter`` (per level) inject the random draws for parity tests.  ``freeze_binaries``
+
+        Cells: all of them while ``step < warmup_steps``; afterwards nerfacc's n/4 uniform + up to n/4 occupied cells
+        per level, chosen by ``umhs_occ_select_cells`` from the bit-packed grid (no nonzero / sort / host sync: the
+        update can be captured as a CUDA graph).  The random numbers come from a counter-based generator inside the
+        kernels, seeded by (grid seed, level) and a device-side epoch that advances with every update -- identical on
+        all data-parallel ranks.  Test hooks: ``cell_ids`` (per level) replaces the selection, ``cell_draws`` =
+        (uniform draws, pick draws) per level feeds it, ``cell_jitter`` fixes the in-cell offsets.  ``freeze_binaries``
         (bench only) does all the work but writes occs / binaries of a scratch copy, so a synthetic scene stays fixed."""
         if not (self.training and step % n == 0):
             return
-        lib = _lib.load()
+        _lib.load()
         dev = self.occs.device
         res, n_cells = self._res, self._res ** 3
         st = stream_ptr(dev)
@@ -156,57 +163,56 @@ class OccGridEstimator(nn.Module):
             if getattr(self, "_scratch", None) is None:
                 self._scratch = (self.occs.clone(), self.binaries.clone())
             occs, binaries = self._scratch
+        steady = cell_ids is None and step >= warmup_steps
+        if getattr(self, "_epoch", None) is None or self._epoch.device != dev:
+            self._epoch = torch.zeros((1,), dtype=torch.int64, device=dev)   # device-side epoch of the draws
+            self._prefix = torch.empty(((n_cells + 31) // 32 + 2 + (n_cells + 32767) // 32768,), dtype=torch.int32, device=dev)
+        self._epoch.add_(1)  # enqueued (and captured) with the update: every replay draws fresh numbers
+        if steady:
+            bits = self.packed_grid()[0] if not freeze_binaries else ops.occ_pack_bits(binaries)[0]
         for lvl in range(self.levels):
-            dup_mask = n_valid = None
+            n_valid = None
+            seed = (int(getattr(self, "seed", 0)) * 1000003 + 7919 * lvl + 1) & 0xFFFFFFFFFFFFFFFF
             if cell_ids is not None:
                 idx = cell_ids[lvl].to(torch.int64).contiguous()
-            elif step < warmup_steps:
+            elif not steady:
                 idx = None  # all cells, in order
             else:
-                # nerfacc: n/4 uniform cells + up to n/4 random OCCUPIED cells (all of them when there are fewer).
-                # Sync-free form (no nonzero / len on the host, so the update can be enqueued behind steps that are
-                # still running): a fixed 2 * n/4 entries; the slots beyond the occupied count repeat entry 0 with the
-                # same jitter -- the same point, the same density, and max() is idempotent.
                 n_u = n_cells // 4
-                uni = torch.randint(n_cells, (n_u,), device=dev)
-                flat = binaries[lvl].flatten()
-                n_occ = flat.sum()                                            # device scalar
-                occ_list = _occupied_cells(flat)                              # occupied ids first, in order
-                slot = torch.arange(n_u, device=dev)
-                pick = (torch.rand(n_u, device=dev) * n_occ).long().clamp_(max=n_cells - 1)
-                occ_idx = torch.where(n_occ > n_u, occ_list[pick], occ_list[:n_u])
-                dup = slot >= n_occ                                           # slots without an occupied cell
-                idx = torch.cat([uni, torch.where(dup, uni[0], occ_idx)], dim=0).contiguous()
-                dup_mask = torch.cat([torch.zeros(n_u, dtype=torch.bool, device=dev), dup])
-                n_valid = n_u + n_occ.clamp(max=n_u)  # device scalar: the duplicates behind it need no evaluation
+                idx = torch.empty((2 * n_u,), dtype=torch.int64, device=dev)
+                n_valid = torch.empty((1,), dtype=torch.int64, device=dev)
+                uu = cell_draws[0][lvl].to(dev, torch.float32).contiguous() if cell_draws is not None else None
+                up = cell_draws[1][lvl].to(dev, torch.float32).contiguous() if cell_draws is not None else None
+                ops._call("umhs_occ_select_cells", 2 * n_u, ptr(bits[lvl]), n_cells, n_u, ptr(uu), ptr(up), seed,
+                          ptr(self._epoch), ptr(self._prefix), ptr(idx), ptr(n_valid), st)
             m = n_cells if idx is None else int(idx.shape[0])
             if m == 0:
                 continue
-            jit_all = cell_jitter[lvl].to(torch.float32).contiguous() if cell_jitter is not None else None
+            jit_all = cell_jitter[lvl].to(dev, torch.float32).contiguous() if cell_jitter is not None else None
             aabb = self.aabbs[lvl].contiguous()
-            # fixed-size chunks: the temporaries (positions, hash encodings, densities) keep one size from call to
-            # call, so the caching allocator serves them from the same blocks instead of growing with the cell count
+            sigma = torch.empty((m,), dtype=torch.float32, device=dev)
+            # the density pass runs in fixed-size chunks: its temporaries (positions, hash encodings) keep one size
+            # from call to call, so the caching allocator serves them from the same blocks
             CH = 1 << 18
             for c0 in range(0, m, CH):
                 mc = min(CH, m - c0)
                 idx_c = None if idx is None else idx[c0:c0 + mc]
                 if idx is None:  # all cells in order: explicit ids for this chunk
                     idx_c = torch.arange(c0, c0 + mc, device=dev, dtype=torch.int64)
-                jit = jit_all[c0:c0 + mc].contiguous() if jit_all is not None else torch.rand((mc, 3), device=dev)
-                if dup_mask is not None:
-                    if c0 == 0:
-                        jit0 = jit[0].clone()
-                    jit = torch.where(dup_mask[c0:c0 + mc, None], jit0, jit)
+                jit = jit_all[c0:c0 + mc].contiguous() if jit_all is not None else None
                 pos = torch.empty((mc, 3), dtype=torch.float32, device=dev)
-                ops._call("umhs_occ_cell_points", mc, ptr(idx_c), ptr(jit), mc, res, ptr(aabb), ptr(pos), st)
-                if n_valid is not None:  # zero density for the duplicate slots: max() with it changes nothing
+                ops._call("umhs_occ_cell_points", mc, ptr(idx_c), ptr(jit), (seed + 0x51ED27 * (c0 + 1)) & (2 ** 64 - 1),
+                          ptr(self._epoch), mc, res, ptr(aabb), ptr(pos), st)
+                if n_valid is not None:  # the unused slots (-1) sit behind n_valid: they are not evaluated
                     cnt = (n_valid - c0).clamp(min=0, max=mc).to(torch.int64).reshape(1)
-                    occ = occ_eval_fn(pos, n_dev=cnt).reshape(-1).to(torch.float32).contiguous()
+                    sigma[c0:c0 + mc] = occ_eval_fn(pos, n_dev=cnt).reshape(-1)
                 else:
-                    occ = occ_eval_fn(pos).reshape(-1).to(torch.float32).contiguous()
-                tmp = torch.empty((mc,), dtype=torch.float32, device=dev)
-                ops._call("umhs_occ_ema_update", mc, ptr(occs), ptr(idx_c), lvl * n_cells, ptr(occ), 1.0,
-                          float(ema_decay), mc, ptr(tmp), st)
+                    sigma[c0:c0 + mc] = occ_eval_fn(pos).reshape(-1)
+            # ONE read phase over all of the level's cells, then one write phase (torch index-assign semantics: every
+            # right-hand side sees the OLD occs, however often a cell was drawn)
+            tmp = torch.empty((m,), dtype=torch.float32, device=dev)
+            ops._call("umhs_occ_ema_update", m, ptr(occs), ptr(idx), lvl * n_cells, ptr(sigma), 1.0,
+                      float(ema_decay), m, ptr(tmp), st)
         scratch = torch.empty((2,), dtype=torch.float64, device=dev)
         mean = torch.empty((1,), dtype=torch.float32, device=dev)
         bn = binaries.view(torch.uint8)
@@ -216,12 +222,6 @@ class OccGridEstimator(nn.Module):
             self._occ_mean = mean
         if self._bits is not None:  # binaries were (re)written through their address: refresh the packed copy
             self._repack()
-
-
-def _occupied_cells(flat: Tensor) -> Tensor:
-    """Ids of the set cells of a flat bool grid, in increasing order, followed by the rest: fixed size, no host sync,
-    capturable in a CUDA graph (torch.nonzero / nonzero_static read a count back on the host)."""
-    return torch.sort(flat.to(torch.uint8), descending=True, stable=True).indices
 
 
 class VolumetricSampler(nn.Module):

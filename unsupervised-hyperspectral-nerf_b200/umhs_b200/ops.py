@@ -24,7 +24,7 @@ _LAUNCHES = {"umhs_hash_encode_fwd": 1, "umhs_hash_encode_bwd": 1, "umhs_hash_en
              "umhs_unmix_bwd": 1, "umhs_render_weights_fwd": 1, "umhs_render_weights_bwd": 1,
              "umhs_accumulate_fwd": 1, "umhs_accumulate_bwd": 1, "umhs_march_count": 1, "umhs_march_level_any": 1, "umhs_occ_pack_bits": 1, "umhs_pack_scan": 1,
              "umhs_march_write": 1, "umhs_visibility_mask": 1, "umhs_compact_samples": 1, "umhs_pack_info": 2,
-             "umhs_occ_cell_points": 1, "umhs_occ_ema_update": 2, "umhs_occ_binarize": 2, "umhs_adam_step": 1,
+             "umhs_occ_cell_points": 1, "umhs_occ_select_cells": 2, "umhs_occ_ema_update": 2, "umhs_occ_binarize": 2, "umhs_adam_step": 1,
              "umhs_reduce_slabs": 1, "umhs_train_loss": 1, "umhs_dp_barrier": 1, "umhs_dp_adam_step": 1, "umhs_adam_step_dev": 1, "umhs_density_tc_fwd": 1, "umhs_field_mlp_tc_fwd": 1, "umhs_field_mlp_tc_bwd": 1, "umhs_debug_trace": 1,
              "umhs_tc05_selftest": 1, "umhs_sample_batch": 1}
 
