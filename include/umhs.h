@@ -185,6 +185,9 @@ typedef struct {
     const float *dir_w1, *dir_b1; /* [B,16], [B] (specular) */
     const float *rgb_matrix;     /* [B,3]  */
     const float *palette;        /* [>=K,3] class colours of ref umhs_model.py:146-162, or NULL */
+    const float *specular_in;    /* [R,B] or NULL: the composited specular term, computed beforehand by
+                                  * umhs_specular_tc_fwd (then `specular` = 0 here): spectral2 = the unmixed part,
+                                  * spectral = spectral2 + specular_in, and rgb / seg_* follow spectral */
 } umhs_composite_in;
 
 typedef struct {
@@ -210,6 +213,7 @@ typedef struct {
     const float *d_accumulation; /* [R] or NULL */
     const float *spectral;    /* [R,B] forward output (needed when d_rgb is given) */
     const float *trans;       /* [N] forward output `trans`, or NULL (the transmittance is then recomputed) */
+    const float *d_weights;   /* [N] or NULL: extra dL/dw_n (umhs_specular_tc_bwd), added before the reverse scan */
 } umhs_composite_grads_in;
 
 typedef struct {
@@ -235,6 +239,31 @@ int umhs_depth_clip_chunks(float *depth, int64_t n_rays, const int64_t *packed_i
                            void *stream);
 int umhs_composite_bwd(const umhs_composite_in *in, const umhs_composite_grads_in *gin,
                        const umhs_composite_grads_out *gout, void *stream);
+
+/* ---------------------------------------------------------------------------------
+ * Specular head, last layer, on the tensor cores (csrc/specular_tc.cu) -- replaces, over packed samples,
+ *     specular[r,b] = sum_{n in r} w_n s1_n sigmoid(W1[b,:] . h_n + b1[b])
+ * i.e. mlp_directional layer 1 + gate of ref umhsnerf/umhs_field.py:240-251 composited as ref
+ * umhsnerf/umhs_model.py:277-286 (SpectralRenderer.forward of the per-sample `specular`), and its backward.
+ * spec_hidden [N,16] = relu(layer 0) and s1 [N] come from umhs_field_mlp_tc_fwd, weights [N] from
+ * umhs_render_weights_fwd; ray_indices [N] sorted by ray; n_dev (optional device count) bounds n.
+ * bf16 operands / fp32 accumulation.  fwd: specular [R,B] is overwritten.  bwd: d_spec [R,B] = dL/d(composited
+ * spectrum) (umhs_spectral_grad); outputs d_spec_hidden [N,16], d_s1 [N], d_weights [N] (feed
+ * umhs_composite_grads_in.d_weights); d_dir_w1 [B,16] / d_dir_b1 [B] accumulated (+=).  grad_scaling:
+ * scale_gradients_by_distance_squared (ref umhs_model.py:241-242) from t_starts / t_ends.
+ * ------------------------------------------------------------------------------- */
+int umhs_specular_tc_fwd(int64_t n, const int64_t *n_dev, int64_t n_rays, int32_t num_bands, const float *spec_hidden,
+                         const float *s1, const float *weights, const int64_t *ray_indices, const float *dir_w1,
+                         const float *dir_b1, float *specular, void *stream);
+int umhs_specular_tc_bwd(int64_t n, const int64_t *n_dev, int64_t n_rays, int32_t num_bands, int32_t grad_scaling,
+                         const float *spec_hidden, const float *s1, const float *weights, const float *t_starts,
+                         const float *t_ends, const int64_t *ray_indices, const float *dir_w1, const float *dir_b1,
+                         const float *d_spec, float *d_spec_hidden, float *d_s1, float *d_weights, float *d_dir_w1,
+                         float *d_dir_b1, void *stream);
+/* d_spec [R,B] = d_spectral (or 0) + the spec -> sRGB chain of d_rgb (ColourSystem backward, ref
+ * utils/spec_to_rgb.py:112-127): the per-ray band phase of the compositing backward as a kernel of its own. */
+int umhs_spectral_grad(int64_t n_rays, int32_t num_bands, const float *d_spectral, const float *d_rgb,
+                       const float *spectral, const float *rgb_matrix, float *d_spec, void *stream);
 
 /* Un-fused pieces at the reference's module boundaries (UMHSField.get_outputs returns per-sample
  * spectra; SpectralRenderer.forward accumulates arbitrary [N,C] values). */

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import WAVELENGTHS, assert_close, load_golden, t
+from helpers import WAVELENGTHS, assert_close, load_golden, rel_l2, t
 from oracle import nerf3p, pack_oracle, umhs_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -531,3 +531,74 @@ def test_train_loss_matches_reference_formula(R, B, channels, method, color):
         assert_close(d_acc, want_acc, 1e-5, 1e-9, "d_acc")
     else:
         assert d_rgb is None and float(losses[1]) == 0.0
+
+
+def _specular_reference(h, s1, w, ri, R, W1, b1, t0, t1, gs_on, d_spec):
+    """fp64 torch: specular[r,b] = sum_n w s1 sigmoid(W1 h + b1); gradients with scale_gradients_by_distance_squared
+    applied to the field outputs (s1 and the per-sample sigmoid term), as ref umhs_model.py:241-242 does."""
+    h, s1, w, W1, b1 = (x.double().clone().requires_grad_() for x in (h, s1, w, W1, b1))
+    gs = (((t0 + t1) / 2) ** 2).clamp(0, 1).double() if gs_on else torch.ones_like(s1)
+
+    def scale(x, g):  # identity forward, gradient x g backward (nerfstudio _GradientScaler)
+        return x * g + (x * (1 - g)).detach()
+
+    term = scale(s1[:, None] * torch.sigmoid(h @ W1.t() + b1), gs[:, None])
+    out = torch.zeros(R, W1.shape[0], dtype=torch.float64, device=h.device).index_add_(0, ri, w[:, None] * term)
+    (out * d_spec.double()).sum().backward()
+    return out.detach(), h.grad, s1.grad, w.grad, W1.grad, b1.grad
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R,B,gs_on,capacity", [(300, 128, True, False), (64, 21, False, False), (257, 141, True, True),
+                                                (100, 256, True, False), (40, 512, False, False), (5000, 128, True, False)])
+def test_specular_tc_matches_reference(R, B, gs_on, capacity):
+    """csrc/specular_tc.cu (tcgen05, bf16 operands) against fp64 torch on the same inputs: forward relative L2 <= 1e-2,
+    gradients <= 3e-2 (stated bf16 tolerance; the sigmoid is tanh.approx).  Ragged rays (0 .. 120 samples), band counts
+    that are not multiples of 16 / 128, device-side sample count (capacity mode)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(R + B)
+    counts = torch.randint(0, 121, (R,), generator=g)
+    counts[::7] = 0
+    N = int(counts.sum())
+    ri = torch.repeat_interleave(torch.arange(R), counts).to(DEV)
+    h = torch.relu(torch.randn(N, 16, generator=g)).to(DEV)
+    s1, w = torch.rand(N, generator=g).to(DEV), (torch.rand(N, generator=g) * 0.1).to(DEV)
+    t0 = (torch.rand(N, generator=g) * 1.5).to(DEV)
+    t1 = t0 + 0.01
+    W1, b1 = (torch.randn(B, 16, generator=g) * 0.5).to(DEV), (torch.randn(B, generator=g) * 0.5).to(DEV)
+    d_spec = torch.randn(R, B, generator=g).to(DEV)
+    want = _specular_reference(h, s1, w, ri, R, W1, b1, t0, t1, gs_on, d_spec)
+    n_dev, pad = None, 0
+    if capacity:  # buffers larger than the sample count; the tail holds garbage that must not be read as samples
+        pad = 333
+        n_dev = torch.tensor([N, N + 999], dtype=torch.int64, device=DEV)
+        ext = lambda x, v: torch.cat([x, torch.full((pad, *x.shape[1:]), v, dtype=x.dtype, device=DEV)])  # noqa: E731
+        h, s1, w, t0, t1 = ext(h, 1e30), ext(s1, 1e30), ext(w, 1e30), ext(t0, 1.0), ext(t1, 1.0)
+        ri = ext(ri, R + 12345)
+    got = ops.specular_tc_fwd(h, s1, w, ri, R, W1, b1, n_dev=n_dev)
+    assert rel_l2(got, want[0]) < 1e-2, rel_l2(got, want[0])
+    d_w1, d_b1 = torch.zeros_like(W1), torch.zeros_like(b1)
+    d_sh, d_s1, d_w = ops.specular_tc_bwd(h, s1, w, t0, t1, ri, R, W1, b1, d_spec, gs_on, d_w1, d_b1, n_dev=n_dev)
+    for name, a, b in (("d_spec_hidden", d_sh[:N], want[1]), ("d_s1", d_s1[:N], want[2]), ("d_weights", d_w[:N], want[3]),
+                       ("d_w1", d_w1, want[4]), ("d_b1", d_b1, want[5])):
+        assert rel_l2(a, b) < 3e-2, (name, rel_l2(a, b))
+    # empty rays stay exactly zero
+    assert float(got[counts == 0].abs().sum()) == 0.0
+
+
+@pytest.mark.gpu
+def test_spectral_grad_matches_autograd():
+    ops = _ops()
+    from umhs_b200 import ColourSystem
+    from umhs_b200._lib import ptr, stream_ptr
+    R, B = 500, 128
+    g = torch.Generator().manual_seed(0)
+    cs = ColourSystem(bands=np.linspace(400, 1000, B).astype(int).tolist(), cs="sRGB").to(DEV)
+    spectral = (torch.rand(R, B, generator=g) * 1.4 - 0.2).to(DEV).requires_grad_()
+    d_spectral, d_rgb = torch.randn(R, B, generator=g).to(DEV), torch.randn(R, 3, generator=g).to(DEV)
+    rgb = cs(spectral)
+    ((spectral * d_spectral).sum() + (rgb * d_rgb).sum()).backward()
+    out = torch.empty(R, B, device=DEV)
+    ops._call("umhs_spectral_grad", R, R, B, ptr(d_spectral), ptr(d_rgb), ptr(spectral.detach()),
+              ptr(cs.transform_matrix.contiguous()), ptr(out), stream_ptr(torch.device(DEV)))
+    assert_close(out, spectral.grad, 1e-4, 1e-5, "d_spec")

@@ -46,12 +46,14 @@ def full(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rd = csv.reader(io.StringIO(out))
     hdr = next(rd)
-    next(rd)
+    unit_row = next(rd)
     ix = {h: i for i, h in enumerate(hdr)}
     cols = [("gpu__time_duration.sum", "us", 1.0), ("dram__bytes_read.sum", "DRAM rd MB", 1.0),
             ("dram__bytes_write.sum", "DRAM wr MB", 1.0),
             ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %", 1.0),
+            ("lts__t_bytes.sum", "L2 MB", 1.0), ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %", 1.0),
             ("lts__t_sector_hit_rate.pct", "L2 hit %", 1.0), ("l1tex__t_sector_hit_rate.pct", "L1 hit %", 1.0),
+            ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %", 1.0),
             ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps %", 1.0),
             ("smsp__issue_active.avg.per_cycle_active", "IPC / scheduler", 1.0),
             ("smsp__thread_inst_executed_per_inst_executed.ratio", "lanes / instr", 1.0),
@@ -63,14 +65,47 @@ def full(path):
         t = float(r[ix["gpu__time_duration.sum"]])
         if name not in best or t > best[name][0]:
             best[name] = (t, r)
+    # machine-readable per-launch traffic for bench.py's roofline entries (profiles/ncu_traffic.json)
+    if len(sys.argv) > 3:
+        import json
+        import re
+
+        entry = {"field_mlp_tc_bwd": "umhs_field_mlp_tc_bwd", "field_mlp_tc_fwd_kernel<0>": "umhs_field_mlp_tc_fwd",
+                 "field_mlp_tc_fwd_kernel<false>": "umhs_field_mlp_tc_fwd", "field_mlp_tc_fwd_kernel<1>": "umhs_density_tc_fwd",
+                 "field_mlp_tc_fwd_kernel<true>": "umhs_density_tc_fwd", "hash_encode_fwd": "umhs_hash_encode_fwd",
+                 "hash_encode_bwd": "umhs_hash_encode_bwd", "composite_fwd": "umhs_composite_fwd",
+                 "composite_bwd": "umhs_composite_bwd", "adam_kernel": "umhs_adam_step_dev", "train_loss": "umhs_train_loss",
+                 "march_kernel": "umhs_march_count"}
+
+        def num(r, key):
+            try:
+                return float(r[ix[key]]) if key in ix else None
+            except ValueError:
+                return None
+
+        units = {h: u for h, u in zip(hdr, unit_row)}
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        out = {}
+        for name, (t, r) in best.items():
+            for pat, api in entry.items():
+                if pat in name and api not in out:
+                    rd, wr, l2 = num(r, "dram__bytes_read.sum"), num(r, "dram__bytes_write.sum"), num(r, "lts__t_bytes.sum")
+                    out[api] = {"dram_bytes": (rd or 0) * scale.get(units.get("dram__bytes_read.sum", "byte"), 1.0)
+                                + (wr or 0) * scale.get(units.get("dram__bytes_write.sum", "byte"), 1.0),
+                                "lts_bytes": None if l2 is None else l2 * scale.get(units.get("lts__t_bytes.sum", "byte"), 1.0),
+                                "us_under_ncu": t}
+        out["umhs_adam_step"] = out.get("umhs_adam_step_dev")
+        json.dump(out, open(sys.argv[3], "w"), indent=1)
     print("| kernel | " + " | ".join(c[1] for c in cols) + " |")
     print("|---|" + "---:|" * len(cols))
     for name, (t, r) in sorted(best.items(), key=lambda kv: -kv[1][0]):
         vals = []
-        for key, _, _ in cols:
+        for key, label, _ in cols:
             v = r[ix[key]] if key in ix else ""
             try:
                 f = float(v)
+                if label.endswith(" MB") and key in ix:  # ncu picks a unit per column: bring byte counts to MB
+                    f *= {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(unit_row[ix[key]], 1.0)
                 vals.append(f"{f:.0f}" if f >= 100 or f == int(f) else f"{f:.2f}")
             except ValueError:
                 vals.append(v or "-")

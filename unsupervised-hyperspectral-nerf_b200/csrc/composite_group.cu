@@ -237,6 +237,8 @@ composite_fwd_group_kernel(umhs_composite_in in, umhs_composite_out out, int vec
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) dot[k] = 0.f;
         float *srow = out.spectral ? out.spectral + r * B : nullptr;
+        float *s2row = (in.specular_in && out.spectral2) ? out.spectral2 + r * B : nullptr;
+        const float *sprow = in.specular_in ? in.specular_in + r * B : nullptr;
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
             const int b4 = g + G * i;
@@ -245,6 +247,13 @@ composite_fwd_group_kernel(umhs_composite_in in, umhs_composite_out out, int vec
 #pragma unroll
                 for (int k = 0; k < KMAX; ++k)
                     if (k < K) fma4(sp, mix[k], E4[k * nb4 + b4]);
+                if (sprow) {  // specular term composited beforehand (tensor-core kernel): spectral = unmixed + specular
+                    if (rv && s2row) store_bands(s2row, b4, B, vB, sp);
+                    if (rv) {
+                        const float4 a = load_bands(sprow, b4, B, vB);
+                        sp.x += a.x; sp.y += a.y; sp.z += a.z; sp.w += a.w;
+                    }
+                }
                 if (rv && srow) store_bands(srow, b4, B, vB, sp);
                 lin0 += dot4(sp, M4[0 * nb4 + b4]);
                 lin1 += dot4(sp, M4[1 * nb4 + b4]);
@@ -421,6 +430,7 @@ composite_bwd_group_kernel(umhs_composite_in in, umhs_composite_grads_in gin, um
         // ---- sample phase: one sweep in reverse, suffix sum of dw * w carried backwards
         const float *ts = in.t_starts + start, *te = in.t_ends + start, *sgp = in.sigma + start;
         const float *trp = gin.trans + start;
+        const float *dwx = gin.d_weights ? gin.d_weights + start : nullptr;
         const float *scp = in.scalar + start * K, *abp = in.abund + start * K;
         float *dsg = gout.d_sigma + start, *dsc = gout.d_scalar + start * K, *dab = gout.d_abund + start * K;
         const int iters = (__reduce_max_sync(kFull, cnt) + G - 1) / G;
@@ -445,7 +455,7 @@ composite_bwd_group_kernel(umhs_composite_in in, umhs_composite_grads_in gin, um
             const float tm = (cur.t0 + cur.t1) / 2.0f;
             // scale_gradients_by_distance_squared (ref umhs_model.py:241-242): every field-output gradient x clamp(t^2)
             const float gs = in.grad_scaling ? fminf(fmaxf(tm * tm, 0.f), 1.f) : 1.f;
-            float dw = dacc;
+            float dw = dacc + ((dwx && v) ? __ldg(dwx + idx) : 0.f);
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) {
                 if (k < K) {
@@ -531,7 +541,8 @@ static int launch_fwd_group(const umhs_composite_in *in, const umhs_composite_ou
     const size_t bytes = (size_t)(K * Bp + 3 * Bp + K + 4) * sizeof(float);
     const int vecK = (K % 4 == 0) && aligned16(in->scalar) && aligned16(in->abund) &&
                      (!out->abundances || aligned16(out->abundances)) && (!out->seg_probs || aligned16(out->seg_probs));
-    const int vecB = (B % 4 == 0) && (!out->spectral || aligned16(out->spectral));
+    const int vecB = (B % 4 == 0) && (!out->spectral || aligned16(out->spectral)) &&
+                     (!in->specular_in || (aligned16(in->specular_in) && (!out->spectral2 || aligned16(out->spectral2))));
     int grid = 1;
     const int rc = grid_for(composite_fwd_group_kernel<KMAX, G, NI>, bytes, in->n_rays, kGrpWarps * (32 / G), &grid);
     if (rc != UMHS_OK) return rc;

@@ -57,7 +57,7 @@ class CompositeIn(Structure):
     _fields_ = [("n_rays", c_int64), ("n_samples", c_int64), ("num_classes", c_int32), ("num_bands", c_int32),
                 ("specular", c_int32), ("grad_scaling", c_int32), ("packed_info", P), ("t_starts", P), ("t_ends", P),
                 ("sigma", P), ("scalar", P), ("abund", P), ("s1", P), ("spec_hidden", P), ("endmembers", P),
-                ("dir_w1", P), ("dir_b1", P), ("rgb_matrix", P), ("palette", P)]
+                ("dir_w1", P), ("dir_b1", P), ("rgb_matrix", P), ("palette", P), ("specular_in", P)]
 
 
 class CompositeOut(Structure):
@@ -68,7 +68,7 @@ class CompositeOut(Structure):
 
 class CompositeGradsIn(Structure):
     _fields_ = [("d_spectral", P), ("d_spectral2", P), ("d_rgb", P), ("d_accumulation", P), ("spectral", P),
-                ("trans", P)]
+                ("trans", P), ("d_weights", P)]
 
 
 class CompositeGradsOut(Structure):
@@ -116,6 +116,9 @@ _SIGNATURES = {
     "umhs_depth_clip": [P, c_int64, P, P],
     "umhs_depth_clip_chunks": [P, c_int64, P, P, P, P, c_int64, P, P],
     "umhs_composite_bwd": [POINTER(CompositeIn), POINTER(CompositeGradsIn), POINTER(CompositeGradsOut), P],
+    "umhs_specular_tc_fwd": [c_int64, P, c_int64, c_int32, P, P, P, P, P, P, P, P],
+    "umhs_specular_tc_bwd": [c_int64, P, c_int64, c_int32, c_int32, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
+    "umhs_spectral_grad": [c_int64, c_int32, P, P, P, P, P, P],
     "umhs_unmix_fwd": [c_int64, c_int32, c_int32, c_int32, P, P, P, P, P, P, P, P, P, P],
     "umhs_unmix_bwd": [c_int64, c_int32, c_int32, c_int32, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "umhs_render_weights_fwd": [P, c_int64, P, P, P, P, P, P],

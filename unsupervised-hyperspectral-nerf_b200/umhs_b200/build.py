@@ -24,7 +24,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE
 EXTRA = {
     "packing.cu": ["-fmad=false"],  # same IEEE op sequence as oracle/pack_oracle.c
 }
-SOURCES = ["api.cu", "hash_grid.cu", "field_mlp.cu", "field_mlp_tc.cu", "composite.cu", "composite_group.cu", "unfused.cu", "packing.cu",
+SOURCES = ["api.cu", "hash_grid.cu", "field_mlp.cu", "field_mlp_tc.cu", "composite.cu", "composite_group.cu", "specular_tc.cu", "unfused.cu", "packing.cu",
            "optim.cu", "loss.cu", "batch.cu"]
 
 

@@ -20,7 +20,7 @@ ENC_DIM = 32  # 16 levels x 2 features
 # kernels launched per C-ABI entry point (for the bench's gpu_launches count)
 _LAUNCHES = {"umhs_hash_encode_fwd": 1, "umhs_hash_encode_bwd": 1, "umhs_hash_encode_x01_fwd": 1,
              "umhs_hash_encode_x01_bwd": 1, "umhs_density_fwd": 1, "umhs_field_mlp_fwd": 1, "umhs_field_mlp_bwd": 1,
-             "umhs_composite_fwd": 1, "umhs_depth_clip": 1, "umhs_depth_clip_chunks": 2, "umhs_composite_bwd": 1, "umhs_unmix_fwd": 1,
+             "umhs_composite_fwd": 1, "umhs_specular_tc_fwd": 1, "umhs_specular_tc_bwd": 1, "umhs_spectral_grad": 1, "umhs_depth_clip": 1, "umhs_depth_clip_chunks": 2, "umhs_composite_bwd": 1, "umhs_unmix_fwd": 1,
              "umhs_unmix_bwd": 1, "umhs_render_weights_fwd": 1, "umhs_render_weights_bwd": 1,
              "umhs_accumulate_fwd": 1, "umhs_accumulate_bwd": 1, "umhs_march_count": 1, "umhs_march_level_any": 1, "umhs_occ_pack_bits": 1, "umhs_pack_scan": 1,
              "umhs_march_write": 1, "umhs_visibility_mask": 1, "umhs_compact_samples": 1, "umhs_pack_info": 2,
@@ -31,6 +31,10 @@ _LAUNCHES = {"umhs_hash_encode_fwd": 1, "umhs_hash_encode_bwd": 1, "umhs_hash_en
 # "bf16": tensor-core MLP kernels (tcgen05 + TMEM, bf16 operands, fp32 accumulate) -- the default.
 # "fp32": fp32 SIMT MLP kernels (precise mode for tight parity tests).
 MLP_PRECISION = "bf16"
+# True: the specular head's last layer ([N x 16] . [16 x B] + sigmoid + per-ray compositing) runs on the tensor cores
+# (csrc/specular_tc.cu, bf16 operands) whenever MLP_PRECISION is "bf16"; False / fp32 mode: the fp32 warp-per-ray
+# compositing kernel (csrc/composite.cu), the tight-parity bridge.
+SPECULAR_TC = True
 
 
 class Profiler:
@@ -360,6 +364,31 @@ def _tminmax_init(dev) -> Tensor:
     return t
 
 
+def specular_tc_fwd(spec_hidden: Tensor, s1: Tensor, weights: Tensor, ray_indices: Tensor, n_rays: int, dir_w1: Tensor,
+                    dir_b1: Tensor, n_dev: Optional[Tensor] = None) -> Tensor:
+    """specular[r, b] = sum_{n in r} w_n s1_n sigmoid(W1[b,:] . h_n + b1[b]) on the tensor cores (include/umhs.h)."""
+    N, B = int(spec_hidden.shape[0]), int(dir_w1.shape[0])
+    out = torch.empty((n_rays, B), dtype=torch.float32, device=spec_hidden.device)
+    _call("umhs_specular_tc_fwd", N, N, ptr(n_dev), n_rays, B, ptr(spec_hidden), ptr(s1), ptr(weights), ptr(ray_indices),
+          ptr(dir_w1), ptr(dir_b1), ptr(out), stream_ptr(out.device))
+    return out
+
+
+def specular_tc_bwd(spec_hidden: Tensor, s1: Tensor, weights: Tensor, t0: Tensor, t1: Tensor, ray_indices: Tensor,
+                    n_rays: int, dir_w1: Tensor, dir_b1: Tensor, d_spec: Tensor, grad_scaling: bool,
+                    d_w1: Tensor, d_b1: Tensor, n_dev: Optional[Tensor] = None):
+    """-> (d_spec_hidden [N,16], d_s1 [N], d_weights [N]); d_w1 / d_b1 are accumulated into."""
+    N, B = int(spec_hidden.shape[0]), int(dir_w1.shape[0])
+    dev = spec_hidden.device
+    d_sh = torch.empty((N, 16), dtype=torch.float32, device=dev)
+    d_s1 = torch.empty((N,), dtype=torch.float32, device=dev)
+    d_w = torch.empty((N,), dtype=torch.float32, device=dev)
+    _call("umhs_specular_tc_bwd", N, N, ptr(n_dev), n_rays, B, 1 if grad_scaling else 0, ptr(spec_hidden), ptr(s1),
+          ptr(weights), ptr(t0), ptr(t1), ptr(ray_indices), ptr(dir_w1), ptr(dir_b1), ptr(d_spec), ptr(d_sh), ptr(d_s1),
+          ptr(d_w), ptr(d_w1), ptr(d_b1), stream_ptr(dev))
+    return d_sh, d_s1, d_w
+
+
 COMPOSITE_OUTPUTS = ("spectral", "spectral2", "specular", "abundances", "accumulation", "depth", "rgb", "seg_probs",
                      "seg_raw", "seg_pred", "weights")
 
@@ -382,11 +411,27 @@ class CompositeFunction(torch.autograd.Function):
                 for x in (t0, t1, sigma, scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1, rgb_matrix,
                           palette)]
         t0, t1, sigma, scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1, rgb_matrix, palette = tens
-        ci = _composite_in(R, N, K, B, specular, cfg["grad_scaling"], packed_info, t0, t1, sigma, scalar, abund, s1,
-                           spec_hidden, endmembers, dir_w1, dir_b1, rgb_matrix, palette)
         z = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)  # noqa: E731
+        # tensor-core specular path: weights first (the transmittance scan), then the [N x 16] . [16 x B] product +
+        # sigmoid + per-ray sums on tcgen05, then the lane-group compositing kernel adds the result to the unmixed
+        # spectrum before its colour / probe epilogue
+        spec_tc = bool(specular and SPECULAR_TC and MLP_PRECISION == "bf16" and cfg.get("ray_indices") is not None)
+        ctx.spec_tc = spec_tc
+        w_pre = specular_rb = None
+        if spec_tc:
+            ri, n_dev = cfg["ray_indices"], cfg.get("n_dev")
+            w_pre, t_pre = z(N), z(N)
+            _call("umhs_render_weights_fwd", 0, ptr(packed_info), R, ptr(t0), ptr(t1), ptr(sigma), ptr(w_pre), ptr(t_pre),
+                  stream_ptr(dev))
+            specular_rb = z(R, B)
+            _call("umhs_specular_tc_fwd", N, N, ptr(n_dev), R, B, ptr(spec_hidden), ptr(s1), ptr(w_pre), ptr(ri),
+                  ptr(dir_w1), ptr(dir_b1), ptr(specular_rb), stream_ptr(dev))
+        ci = _composite_in(R, N, K, B, specular and not spec_tc, cfg["grad_scaling"], packed_info, t0, t1, sigma, scalar,
+                           abund, s1, spec_hidden, endmembers, dir_w1, dir_b1, rgb_matrix, palette)
+        ci.specular_in = ptr(specular_rb)
         out = {"spectral": z(R, B), "spectral2": z(R, B) if specular else None,
-               "specular": z(R, B) if specular else None, "abundances": z(R, K), "accumulation": z(R),
+               "specular": (specular_rb if spec_tc else z(R, B)) if specular else None, "abundances": z(R, K),
+               "accumulation": z(R),
                "depth": z(R), "rgb": z(R, 3), "seg_probs": z(R, K), "seg_raw": z(R), "seg_pred": z(R, 3),
                "weights": z(N) if cfg.get("want_weights", False) else None}
         # per-sample transmittance, kept for the backward (4 B/sample instead of a recomputation pass there)
@@ -415,7 +460,7 @@ class CompositeFunction(torch.autograd.Function):
                   ptr(ray_ids), chunk_rays, ptr(bounds), stream_ptr(dev))
         ctx.cfg = cfg
         ctx.save_for_backward(packed_info, t0, t1, sigma, scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1,
-                              rgb_matrix, out["spectral"], trans)
+                              rgb_matrix, out["spectral"], trans, w_pre)
         empty = torch.empty((0,), device=dev)
         res = tuple(out[k] if out[k] is not None else empty for k in COMPOSITE_OUTPUTS)
         ctx.mark_non_differentiable(*[res[i] for i, k in enumerate(COMPOSITE_OUTPUTS)
@@ -426,18 +471,16 @@ class CompositeFunction(torch.autograd.Function):
     def backward(ctx, d_spectral, d_spectral2, d_specular, d_abundances, d_acc, d_depth, d_rgb, *_):
         lib = _lib.load()
         (packed_info, t0, t1, sigma, scalar, abund, s1, spec_hidden, endmembers, dir_w1, dir_b1, rgb_matrix,
-         spectral, trans) = ctx.saved_tensors
+         spectral, trans, w_pre) = ctx.saved_tensors
         cfg = ctx.cfg
         dev = sigma.device
         R, N, K, B, specular = int(packed_info.shape[0]), int(sigma.shape[0]), cfg["K"], cfg["B"], cfg["specular"]
-        ci = _composite_in(R, N, K, B, specular, cfg["grad_scaling"], packed_info, t0, t1, sigma, scalar, abund, s1,
-                           spec_hidden, endmembers, dir_w1, dir_b1, rgb_matrix, None)
+        spec_tc = ctx.spec_tc
+        ci = _composite_in(R, N, K, B, specular and not spec_tc, cfg["grad_scaling"], packed_info, t0, t1, sigma, scalar,
+                           abund, s1, spec_hidden, endmembers, dir_w1, dir_b1, rgb_matrix, None)
         gi = _lib.CompositeGradsIn()
         keep = [f32(g) if g is not None else None for g in (d_spectral, d_spectral2 if specular else None, d_rgb,
                                                             d_acc)]
-        gi.d_spectral, gi.d_spectral2, gi.d_rgb, gi.d_accumulation = (ptr(k) for k in keep)
-        gi.spectral = ptr(spectral)
-        gi.trans = ptr(trans)
         z = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)  # noqa: E731
         d_sigma, d_scalar, d_abund = z(N), z(N, K), z(N, K)
         d_s1 = z(N) if specular else None
@@ -446,10 +489,31 @@ class CompositeFunction(torch.autograd.Function):
         d_E = sE if sE is not None else torch.zeros((K, B), dtype=torch.float32, device=dev)
         d_w1 = (sW if sW is not None else torch.zeros((B, 16), dtype=torch.float32, device=dev)) if specular else None
         d_b1 = (sB if sB is not None else torch.zeros((B,), dtype=torch.float32, device=dev)) if specular else None
+        if spec_tc:
+            # dL / d (composited spectrum) first (loss gradient + the spec -> sRGB chain), then the tensor-core
+            # backward of the specular term, whose dL/dw joins the compositing sweep below
+            d_spec = z(R, B)
+            have = keep[0] is not None or keep[2] is not None
+            if have:
+                _call("umhs_spectral_grad", R, R, B, ptr(keep[0]), ptr(keep[2]), ptr(spectral), ptr(rgb_matrix),
+                      ptr(d_spec), stream_ptr(dev))
+            else:
+                d_spec.zero_()
+            dw_x = z(N)
+            _call("umhs_specular_tc_bwd", N, N, ptr(cfg.get("n_dev")), R, B, 1 if cfg["grad_scaling"] else 0,
+                  ptr(spec_hidden), ptr(s1), ptr(w_pre), ptr(t0), ptr(t1), ptr(cfg["ray_indices"]), ptr(dir_w1),
+                  ptr(dir_b1), ptr(d_spec), ptr(d_sh), ptr(d_s1), ptr(dw_x), ptr(d_w1), ptr(d_b1), stream_ptr(dev))
+            d_unmixed = d_spec if keep[1] is None else d_spec + keep[1]  # spectral2 = the unmixed part alone
+            keep = [d_unmixed, None, None, keep[3], dw_x]
+            gi.d_weights = ptr(dw_x)
+        gi.d_spectral, gi.d_spectral2, gi.d_rgb, gi.d_accumulation = (ptr(k) for k in keep[:4])
+        gi.spectral = ptr(spectral)
+        gi.trans = ptr(trans)
         go = _lib.CompositeGradsOut()
         go.d_sigma, go.d_scalar, go.d_abund = ptr(d_sigma), ptr(d_scalar), ptr(d_abund)
-        go.d_s1, go.d_spec_hidden = ptr(d_s1), ptr(d_sh)
-        go.d_endmembers, go.d_dir_w1, go.d_dir_b1 = ptr(d_E), ptr(d_w1), ptr(d_b1)
+        go.d_s1, go.d_spec_hidden = (None, None) if spec_tc else (ptr(d_s1), ptr(d_sh))
+        go.d_endmembers = ptr(d_E)
+        go.d_dir_w1, go.d_dir_b1 = (None, None) if spec_tc else (ptr(d_w1), ptr(d_b1))
         _call("umhs_composite_bwd", R, ctypes.byref(ci), ctypes.byref(gi), ctypes.byref(go), stream_ptr(dev))
         return (None, None, None, None, d_sigma, d_scalar, d_abund, d_s1, d_sh, None if sE is not None else d_E,
                 None if sW is not None else d_w1, None if sB is not None else d_b1, None, None)

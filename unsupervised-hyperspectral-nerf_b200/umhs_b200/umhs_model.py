@@ -241,7 +241,9 @@ class UMHSModel(_ModelBase):  # type: ignore[misc, valid-type]
         K, B, spec = self.field.num_classes, self.field.wavelengths, cfg.pred_specular
         d = self.field.mlp_directional.layers
         ccfg = {"K": K, "B": B, "specular": spec, "grad_scaling": cfg.use_gradient_scaling, "want_weights": not lean,
-                "want_depth": not lean, "depth_chunks": depth_chunks}
+                "want_depth": not lean, "depth_chunks": depth_chunks,
+                # for the tensor-core specular kernels (sample -> ray map, device-side sample count)
+                "ray_indices": ray_indices, "n_dev": pts.n_dev}
         (spectral, spectral2, specular, abund, acc, depth, rgb, seg_probs, seg_raw, seg_pred,
          weights) = ops.CompositeFunction.apply(
             ccfg, packed_info, t0, t1, fo["sigma"], fo["scalar"], fo["abund"], fo.get("s1"), fo.get("spec_hidden"),
