@@ -33,8 +33,9 @@ constexpr int kBarReady = 1, kBarData = 2;
 constexpr int VSTRIDE = 129;       // fp32 words per V row: conflict-free by rows (writes) and by columns (reads)
 
 // shared-memory plan (bytes)
+constexpr int kStageBytes = 8192 + 512 + 512 + 1024 + 1024;  // h, s1, w, ray ids (int64), t0, t1 of one tile
 struct Smem {
-    int w, a, dz, v, rid, ctrl, total;
+    int w, a, dz, v, rid, seg, stage, ctrl, total;
 };
 __host__ __device__ inline Smem plan(int nch, bool bwd) {
     Smem s;
@@ -44,11 +45,50 @@ __host__ __device__ inline Smem plan(int nch, bool bwd) {
     s.dz = o; o += bwd ? TM * 128 * 2 : 0;            // backward: [128 samples x 128 bands] dz of one band chunk
     s.v = o; o += bwd ? 0 : TM * VSTRIDE * 4;         // forward: V[sample][band] fp32
     s.rid = o; o += TM * 4;                           // ray of each sample of the tile (-1: no sample)
-    s.ctrl = o; o += 64;                              // mbarrier `done`, TMEM address
+    s.seg = o; o += bwd ? 0 : (TM + TM + 16) * 4;     // forward: segment heads + segment start list
+    s.stage = o; o += 2 * kStageBytes;                // two tiles of raw inputs, filled by the copy engine (TMA)
+    s.ctrl = o; o += 64;                              // mbarriers `done`, `full[2]`; TMEM address
     s.total = o;
     return s;
 }
 
+// Inputs of a tile arrive by 1-D bulk copies (cp.async.bulk, the TMA engine) two tiles ahead: spec_hidden rows
+// (128 x 64 B, contiguous), s1, weights, ray indices, and for the backward t0 / t1 -- no thread waits on a global load
+// at the top of a tile.  A tile that reaches past the end of the arrays is read with plain loads instead.
+struct Stage {
+    static constexpr int h = 0, s1 = 8192, w = 8192 + 512, rid = 8192 + 1024, t0 = 8192 + 2048, t1 = 8192 + 2560;
+};
+struct Loader {
+    uint8_t *stage;       // 2 x kStageBytes
+    uint64_t *full;       // [2]
+    const float *spec_hidden, *s1, *weights, *t0, *t1;
+    const int64_t *ray_indices;
+    int64_t n_alloc;
+    __device__ __forceinline__ bool bulk_ok(int64_t tile) const { return (tile + 1) * TM <= n_alloc; }
+    // one thread: arm the barrier and start the copies of `tile` into buffer `buf`
+    __device__ __forceinline__ void issue(int64_t tile, int buf) const {
+        if (!bulk_ok(tile)) return;
+        uint8_t *dst = stage + buf * kStageBytes;
+        const int64_t n0 = tile * TM;
+        const uint32_t bytes = 8192 + 512 + 512 + 1024 + (t0 ? 1024 : 0);
+        fence_proxy_async();  // the buffer's last readers (generic proxy) are ordered before the engine's writes
+        mbar_expect_tx(full + buf, bytes);
+        bulk_load(dst + Stage::h, spec_hidden + n0 * 16, 8192, full + buf);
+        bulk_load(dst + Stage::s1, s1 + n0, 512, full + buf);
+        bulk_load(dst + Stage::w, weights + n0, 512, full + buf);
+        bulk_load(dst + Stage::rid, ray_indices + n0, 1024, full + buf);
+        if (t0) {
+            bulk_load(dst + Stage::t0, t0 + n0, 512, full + buf);
+            bulk_load(dst + Stage::t1, t1 + n0, 512, full + buf);
+        }
+    }
+};
+
+__device__ __forceinline__ float fast_tanh_half(float x) {  // tanh(x / 2): one MUFU
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return t;
+}
 __device__ __forceinline__ float fast_sigmoid(float x) {
     float t;
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
@@ -96,6 +136,24 @@ __device__ __forceinline__ Sample load_sample(int64_t tile, int t, int64_t n_eff
     s.s1 = s.valid ? __ldg(s1 + s.n) : 0.f;
     return s;
 }
+// the same from a staged tile (bulk-copied): row t of the buffer
+__device__ __forceinline__ Sample staged_sample(const uint8_t *buf, int64_t tile, int t, int64_t n_eff, float (&h)[16],
+                                                float &tm) {
+    Sample s;
+    s.n = tile * TM + t;
+    s.valid = s.n < n_eff;
+    const float4 *hp = reinterpret_cast<const float4 *>(buf + Stage::h) + 4 * t;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 v = s.valid ? hp[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        h[4 * q] = v.x; h[4 * q + 1] = v.y; h[4 * q + 2] = v.z; h[4 * q + 3] = v.w;
+    }
+    s.rid = s.valid ? (int)reinterpret_cast<const int64_t *>(buf + Stage::rid)[t] : -1;
+    s.w = s.valid ? reinterpret_cast<const float *>(buf + Stage::w)[t] : 0.f;
+    s.s1 = s.valid ? reinterpret_cast<const float *>(buf + Stage::s1)[t] : 0.f;
+    tm = (reinterpret_cast<const float *>(buf + Stage::t0)[t] + reinterpret_cast<const float *>(buf + Stage::t1)[t]) / 2.0f;
+    return s;
+}
 __device__ __forceinline__ void load_h(const float *__restrict__ spec_hidden, const Sample &s, float (&h)[16]) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -137,12 +195,17 @@ specular_tc_fwd_kernel(Common c, float *__restrict__ specular) {
     const Smem L = plan(c.nch, false);
     const int tid = threadIdx.x, warp = tid >> 5;
     uint64_t *done = reinterpret_cast<uint64_t *>(smem + L.ctrl);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.ctrl + 16);
+    uint64_t *full = done + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.ctrl + 32);
     float *V = reinterpret_cast<float *>(smem + L.v);
     int *rid_s = reinterpret_cast<int *>(smem + L.rid);
+    int *head_s = reinterpret_cast<int *>(smem + L.seg);        // [128] 1 where a new ray starts (sample 0 aside)
+    int *seg_s = head_s + TM;                                    // [129] segment starts, n_seg at seg_s[TM + 1]
     stage_w(smem + L.w, c.nch * 128, c.w1, c.b1, c.B, tid, kThreads);
     if (tid == 0) {
         mbar_init(done, 1);
+        mbar_init(full, 1);
+        mbar_init(full + 1, 1);
         fence_mbar_init();
     }
     if (warp == 4) tmem_alloc<128>(tmem_slot);
@@ -174,14 +237,36 @@ specular_tc_fwd_kernel(Common c, float *__restrict__ specular) {
         const int t = tid;
         const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
         uint32_t parity = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const Sample s = load_sample(tile, t, n_eff, c.ray_indices, c.weights, c.s1);
-            float h[16];
-            load_h(c.spec_hidden, s, h);
-            const float coef = s.w * s.s1;
-            named_bar_sync(kBarData, TM);  // the previous tile's readers of V / rid_s are done
+        const Loader ld{smem + L.stage, full, c.spec_hidden, c.s1, c.weights, nullptr, nullptr, c.ray_indices, c.n};
+        if (t == 0) {  // two tiles ahead
+            ld.issue(blockIdx.x, 0);
+            if ((int64_t)blockIdx.x + gridDim.x < n_tiles) ld.issue((int64_t)blockIdx.x + gridDim.x, 1);
+        }
+        int64_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int buf = (int)(it & 1);
+            Sample s;
+            float h[16], tm_unused;
+            if (ld.bulk_ok(tile)) {
+                mbar_wait(full + buf, (uint32_t)((it >> 1) & 1));
+                s = staged_sample(smem + L.stage + buf * kStageBytes, tile, t, n_eff, h, tm_unused);
+            } else {
+                s = load_sample(tile, t, n_eff, c.ray_indices, c.weights, c.s1);
+                load_h(c.spec_hidden, s, h);
+            }
+            const float half_coef = 0.5f * s.w * s.s1;  // w s1 sigmoid(z) = c tanh(z / 2) + c, c = w s1 / 2
+            named_bar_sync(kBarData, TM);  // the previous tile's readers of V / rid_s are done; this tile's buffer is read
+            if (t == 0 && tile + 2 * (int64_t)gridDim.x < n_tiles) ld.issue(tile + 2 * (int64_t)gridDim.x, buf);
             rid_s[t] = s.rid;
             stage_a_row(smem + L.a, t, h);
+            // ray segments of the tile: sample t opens one when its ray differs from sample t-1's (rays are contiguous
+            // runs of samples); seg_s[k] = first sample of segment k, seg_s[n_seg] = 128.  Built with one ballot per warp.
+            {
+                const int prev = __shfl_up_sync(kFull, s.rid, 1);
+                const bool head_in_warp = (t & 31) != 0 && prev != s.rid;
+                // (the first lane of a warp compares with the previous warp's last sample through shared memory below)
+                head_s[t] = head_in_warp ? 1 : 0;
+            }
             for (int ch = 0; ch < c.nch; ++ch) {
                 fence_proxy_async();
                 fence_before_sync();
@@ -197,26 +282,46 @@ specular_tc_fwd_kernel(Common c, float *__restrict__ specular) {
                     float z[32];
                     tmem_ld32(trow + 32u * q, z);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) V[t * VSTRIDE + 32 * q + i] = coef * fast_sigmoid(z[i]);
+                    for (int i = 0; i < 32; ++i) V[t * VSTRIDE + 32 * q + i] = fmaf(half_coef, fast_tanh_half(z[i]), half_coef);
                 }
                 fence_before_sync();           // TMEM reads done before the next round's MMA overwrites the columns
                 named_bar_sync(kBarData, TM);
-                // ---- thread = band: one running sum per ray over the tile's samples
+                if (ch == 0 && warp == 0) {    // segment list of the tile (one warp; the others start summing after it)
+                    int n_seg = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int n = 32 * k + t;
+                        bool head = head_s[n] != 0;
+                        if (t == 0) head = (k == 0) || rid_s[n] != rid_s[n - 1];
+                        const unsigned m = __ballot_sync(kFull, head);
+                        if (head) seg_s[n_seg + __popc(m & ((1u << t) - 1u))] = n;
+                        n_seg += __popc(m);
+                    }
+                    if (t == 0) {
+                        seg_s[n_seg] = TM;
+                        seg_s[TM + 1] = n_seg;
+                    }
+                }
+                if (ch == 0) named_bar_sync(kBarData, TM);
+                // ---- thread = band: one sum per ray segment over the tile's samples (4 independent partial sums)
                 if (t < nb) {
                     float *out = specular + 128 * ch + t;
-                    float acc = 0.f;
-                    int cur = rid_s[0];
-#pragma unroll 4
-                    for (int n = 0; n < TM; ++n) {
-                        const int r = rid_s[n];
-                        if (r != cur) {
-                            if (cur >= 0) atomicAdd(out + (int64_t)cur * c.B, acc);
-                            acc = 0.f;
-                            cur = r;
+                    const int n_seg = seg_s[TM + 1];
+                    for (int k = 0; k < n_seg; ++k) {
+                        const int a = seg_s[k], e = seg_s[k + 1];
+                        const int r = rid_s[a];
+                        if (r < 0) continue;  // rows behind the last sample
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                        int n = a;
+                        for (; n + 4 <= e; n += 4) {
+                            a0 += V[(n + 0) * VSTRIDE + t];
+                            a1 += V[(n + 1) * VSTRIDE + t];
+                            a2 += V[(n + 2) * VSTRIDE + t];
+                            a3 += V[(n + 3) * VSTRIDE + t];
                         }
-                        acc += V[n * VSTRIDE + t];
+                        for (; n < e; ++n) a0 += V[n * VSTRIDE + t];
+                        atomicAdd(out + (int64_t)r * c.B, (a0 + a1) + (a2 + a3));
                     }
-                    if (cur >= 0) atomicAdd(out + (int64_t)cur * c.B, acc);
                 }
                 if (ch + 1 < c.nch) named_bar_sync(kBarData, TM);  // V is rewritten by the next chunk
             }
@@ -244,10 +349,13 @@ specular_tc_bwd_kernel(Common c, BwdArgs g) {
     const Smem L = plan(c.nch, true);
     const int tid = threadIdx.x, warp = tid >> 5;
     uint64_t *done = reinterpret_cast<uint64_t *>(smem + L.ctrl);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.ctrl + 16);
+    uint64_t *full = done + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.ctrl + 32);
     stage_w(smem + L.w, c.nch * 128, c.w1, c.b1, c.B, tid, kThreads);
     if (tid == 0) {
         mbar_init(done, 1);
+        mbar_init(full, 1);
+        mbar_init(full + 1, 1);
         fence_mbar_init();
     }
     if (warp == 4) tmem_alloc<NCOLS>(tmem_slot);
@@ -292,18 +400,33 @@ specular_tc_bwd_kernel(Common c, BwdArgs g) {
         const int t = tid;
         const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
         uint32_t parity = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const Sample s = load_sample(tile, t, n_eff, c.ray_indices, c.weights, c.s1);
-            float h[16];
-            load_h(c.spec_hidden, s, h);
-            float gs = 1.f;
-            if (g.grad_scaling && s.valid) {
-                const float tm = (__ldg(g.t_starts + s.n) + __ldg(g.t_ends + s.n)) / 2.0f;
-                gs = fminf(fmaxf(tm * tm, 0.f), 1.f);
+        const bool use_t = g.grad_scaling != 0;
+        const Loader ld{smem + L.stage, full, c.spec_hidden, c.s1, c.weights, use_t ? g.t_starts : nullptr,
+                        use_t ? g.t_ends : nullptr, c.ray_indices, c.n};
+        if (t == 0) {
+            ld.issue(blockIdx.x, 0);
+            if ((int64_t)blockIdx.x + gridDim.x < n_tiles) ld.issue((int64_t)blockIdx.x + gridDim.x, 1);
+        }
+        int64_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int buf = (int)(it & 1);
+            Sample s;
+            float h[16], tm = 0.f;
+            if (ld.bulk_ok(tile)) {
+                mbar_wait(full + buf, (uint32_t)((it >> 1) & 1));
+                s = staged_sample(smem + L.stage + buf * kStageBytes, tile, t, n_eff, h, tm);
+            } else {
+                s = load_sample(tile, t, n_eff, c.ray_indices, c.weights, c.s1);
+                load_h(c.spec_hidden, s, h);
+                if (use_t && s.valid) tm = (__ldg(g.t_starts + s.n) + __ldg(g.t_ends + s.n)) / 2.0f;
             }
+            const float gs = (use_t && s.valid) ? fminf(fmaxf(tm * tm, 0.f), 1.f) : 1.f;
             const float coef = s.w * s.s1 * gs;
             const float *grow = g.d_spec + (int64_t)(s.valid ? s.rid : 0) * c.B;
+            const bool vec_g = (c.B & 3) == 0 && (reinterpret_cast<uintptr_t>(g.d_spec) & 15u) == 0;
             stage_a_row(smem + L.a, t, h);  // (the previous tile's MMAs on this tile were covered by its last commit)
+            named_bar_sync(kBarData, TM);   // every thread has read its row of the staged tile
+            if (t == 0 && tile + 2 * (int64_t)gridDim.x < n_tiles) ld.issue(tile + 2 * (int64_t)gridDim.x, buf);
             float q = 0.f;
             for (int r = 0; r <= c.nch; ++r) {
                 fence_proxy_async();
@@ -319,12 +442,24 @@ specular_tc_bwd_kernel(Common c, BwdArgs g) {
                 for (int qq = 0; qq < 4; ++qq) {
                     float dz[32];
                     if (32 * qq < nb) {
+                        const int b0 = 128 * r + 32 * qq;
+                        float gv[32];
+                        if (vec_g && b0 + 32 <= c.B) {  // whole 16-byte pieces of the ray's gradient row, all in flight
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const float4 v = s.valid ? __ldg(reinterpret_cast<const float4 *>(grow + b0) + k)
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                                gv[4 * k] = v.x; gv[4 * k + 1] = v.y; gv[4 * k + 2] = v.z; gv[4 * k + 3] = v.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) gv[i] = (s.valid && b0 + i < c.B) ? __ldg(grow + b0 + i) : 0.f;
+                        }
                         float z[32];
                         tmem_ld32(trow + T_Z + 32u * qq, z);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const int b = 128 * r + 32 * qq + i;
-                            const float gb = (s.valid && b < c.B) ? __ldg(grow + b) : 0.f;
+                            const float gb = gv[i];
                             const float sg = fast_sigmoid(z[i]);
                             q = fmaf(gb, sg, q);
                             dz[i] = gb * coef * sg * (1.0f - sg);

@@ -275,6 +275,18 @@ __device__ __forceinline__ void flag_wait(const uint32_t *flag, uint32_t want) {
     __trap();
 }
 
+// ---- TMA, 1-D bulk form: `bytes` (multiple of 16, both addresses 16-byte aligned) from global to shared memory by
+// the copy engine; completion is counted in bytes on an mbarrier (arm it with mbar_expect_tx first).  One thread issues.
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // ---- named CTA barriers (the hardware barrier unit: no shared-memory access, unlike mbarriers / flags, whose
 // probes queue behind the tensor core's operand reads).  Producer / consumer form: the producers bar.arrive (they do
 // not wait), the consumer bar.sync; `count` = all participating threads of both sides (a multiple of 32).
