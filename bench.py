@@ -259,8 +259,10 @@ def algorithmic_bytes(name, units, samples_per_ray, K, adam_touched_frac=None):
     """Algorithmic bytes per launch (DESIGN.md 'Kernels'); units = what the wrapper passed (samples, rays, params)."""
     L = 16
     per = {
-        "umhs_hash_encode_fwd": 8 * L * 8 + 16 + 8 * L,            # gathers + (ray_idx,t0,t1) + enc out
+        "umhs_hash_encode_fwd": 8 * L * 8 + 16 + 8 * L,            # gathers + (ray_idx,t0,t1) + enc out (fp32 rows)
         "umhs_hash_encode_bwd": 8 * L + 16 + 2 * 8 * L * 8,        # d_enc in + points + table read-modify-write
+        "umhs_hash_encode_fwd_tiles": 8 * L * 8 + 16 + 4 * L,      # ... with bf16 tile buffers in between
+        "umhs_hash_encode_bwd_tiles": 4 * L + 16 + 2 * 8 * L * 8,
         "umhs_train_loss": None,
     }.get(name, None)
     S = samples_per_ray

@@ -82,6 +82,14 @@ typedef struct {
 } umhs_hash_grid;
 
 int umhs_hash_encode_fwd(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid, float *enc, void *stream);
+/* The same with the encodings / their gradients in the bf16 tile layout (16 levels x 2 features; element (n, c) at byte
+ * (n >> 7) * 8192 + (c >> 3) * 2048 + ((n & 127) >> 3) * 128 + (n & 7) * 16 + (c & 7) * 2): the format the tensor-core
+ * MLP kernels consume without conversion (umhs_mlp_params.enc_tiles = 1), half the bytes of the fp32 rows.  Buffers
+ * hold ceil(n / 128) * 8192 bytes, 16-byte aligned. */
+int umhs_hash_encode_fwd_tiles(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid, void *enc_tiles,
+                               void *stream);
+int umhs_hash_encode_bwd_tiles(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid, const void *d_enc_tiles,
+                               float *d_table, void *stream);
 int umhs_hash_encode_bwd(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid, const float *d_enc,
                          float *d_table, void *stream);
 /* Same two ops on already-normalised coordinates x01 [n,3] in [0,1] (the HashEncoding module boundary). */
@@ -107,6 +115,9 @@ typedef struct {
     int32_t num_classes; /* K */
     int32_t specular;    /* pred_specular */
     float temperature;
+    int32_t enc_tiles;   /* tensor-core entry points only: 1 = `enc` (and `d_enc`) are bf16 TILE buffers, 128 samples x
+                          * 32 columns per 8 KB tile in the tensor core's K-major operand order (written by
+                          * umhs_hash_encode_fwd_tiles, read by umhs_hash_encode_bwd_tiles); 0 = fp32 rows [n,32] */
 } umhs_mlp_params;
 
 typedef struct {

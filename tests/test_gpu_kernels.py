@@ -602,3 +602,70 @@ def test_spectral_grad_matches_autograd():
     ops._call("umhs_spectral_grad", R, R, B, ptr(d_spectral), ptr(d_rgb), ptr(spectral.detach()),
               ptr(cs.transform_matrix.contiguous()), ptr(out), stream_ptr(torch.device(DEV)))
     assert_close(out, spectral.grad, 1e-4, 1e-5, "d_spec")
+
+
+def _tile_to_rows(buf, n):
+    """bf16 tile buffer [ceil(n/128)*128, 32] (csrc/common.cuh: enc_tile_piece) -> fp32 rows [n, 32]."""
+    raw = buf.view(torch.int16).reshape(-1)
+    nn = torch.arange(n, device=buf.device)[:, None]
+    c = torch.arange(32, device=buf.device)[None, :]
+    byte = (nn >> 7) * 8192 + (c >> 3) * 2048 + ((nn & 127) >> 3) * 128 + (nn & 7) * 16 + (c & 7) * 2
+    return raw[byte // 2].view(torch.bfloat16).float()
+
+
+def _rows_to_tile(rows):
+    n = rows.shape[0]
+    buf = torch.zeros(((n + 127) // 128 * 128, 32), dtype=torch.bfloat16, device=rows.device)
+    raw = buf.view(torch.int16).reshape(-1)
+    nn = torch.arange(n, device=rows.device)[:, None]
+    c = torch.arange(32, device=rows.device)[None, :]
+    byte = (nn >> 7) * 8192 + (c >> 3) * 2048 + ((nn & 127) >> 3) * 128 + (nn & 7) * 16 + (c & 7) * 2
+    raw[(byte // 2).reshape(-1)] = rows.to(torch.bfloat16).view(torch.int16).reshape(-1)
+    return buf
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 127, 128, 1000, 70001])
+def test_enc_tile_layout_round_trip(n):
+    """The bf16 tile layout between the hash-grid and the tensor-core MLP kernels (ops.ENC_TILES): the forward gather
+    writes exactly bf16(fp32 row value) at the documented byte offsets, the MLP kernels give bit-identical outputs from
+    either format (they round the encodings to bf16 on load anyway), the gradient rows come back bf16-rounded, and the
+    scatter of a tile buffer equals the scatter of the same values as fp32 rows."""
+    ops = _ops()
+    from helpers import mlp_precision
+    g = torch.Generator().manual_seed(n)
+    log2_T, L, K = 12, 16, 4
+    table = ((torch.rand(L << log2_T, 2, generator=g) * 2 - 1) * 0.5).to(DEV)
+    scal = torch.floor(16 * torch.exp(torch.arange(L) * (np.log(2048 / 16) / (L - 1)))).float().to(DEV)
+    pos = (torch.rand(n, 3, generator=g) * 2.4 - 1.2).to(DEV)
+    pts = ops.PointSet.from_positions(pos)
+    rows = ops.hash_encode_fwd(pts, table, scal, log2_T)
+    tiles = ops.hash_encode_fwd(pts, table, scal, log2_T, tiles=True)
+    assert tiles.dtype == torch.bfloat16 and tiles.shape == ((n + 127) // 128 * 128, 32)
+    assert torch.equal(_tile_to_rows(tiles, n), rows.to(torch.bfloat16).float())
+    mk = lambda o, i: ((torch.rand(o, i, generator=g) * 2 - 1) / i ** 0.5).to(DEV).contiguous()  # noqa: E731
+    w = {}
+    for name, (o, i) in {"base_w0": (64, 32), "base_w1": (16, 64), "head_w0": (64, 27), "head_w1": (64, 64),
+                         "head_w2": (K, 64), "feat_w0": (64, 27), "feat_w1": (64, 64), "feat_w2": (K, 64)}.items():
+        w[name] = mk(o, i)
+        w[name.replace("_w", "_b")] = (torch.rand(o, generator=g) * 0.1).to(DEV)
+    w["dir_w0"] = w["dir_b0"] = None
+    grads = {"d_sigma": torch.randn(n, generator=g).to(DEV), "d_scalar": torch.randn(n, K, generator=g).to(DEV),
+             "d_abund": torch.randn(n, K, generator=g).to(DEV), "d_embedding": None}
+    with mlp_precision("bf16"):
+        a = ops.field_mlp_fwd(pts, rows, w, K, False, 0.4)
+        b = ops.field_mlp_fwd(pts, tiles, w, K, False, 0.4)
+        for k in ("sigma", "embedding", "scalar", "abund"):
+            assert torch.equal(a[k], b[k]), k
+        assert torch.equal(ops.density_fwd(pts, rows, w), ops.density_fwd(pts, tiles, w))
+        d_rows, gw_rows = ops.field_mlp_bwd(pts, rows, w, K, False, 0.4, grads)
+        d_tiles, gw_tiles = ops.field_mlp_bwd(pts, tiles, w, K, False, 0.4, grads)
+        assert d_tiles.dtype == torch.bfloat16
+        assert torch.equal(_tile_to_rows(d_tiles, n), d_rows.to(torch.bfloat16).float())
+        for k in gw_rows:  # same MMAs on the same operands; only the flush order of the atomics differs
+            assert_close(gw_tiles[k], gw_rows[k], 1e-4, 1e-5 * float(gw_rows[k].abs().max()) + 1e-9, k)
+    # scatter: a tile buffer against the same (bf16-representable) values as fp32 rows
+    d = torch.randn(n, 32, generator=g).to(DEV).to(torch.bfloat16)
+    t_rows = ops.hash_encode_bwd(pts, table, scal, log2_T, d.float().contiguous())
+    t_tiles = ops.hash_encode_bwd(pts, table, scal, log2_T, _rows_to_tile(d.float()))
+    assert_close(t_tiles, t_rows, 1e-5, 1e-6 * float(t_rows.abs().max()) + 1e-9, "d_table")

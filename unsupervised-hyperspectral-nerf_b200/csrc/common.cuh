@@ -199,4 +199,15 @@ __device__ __forceinline__ Point eval_point(const umhs_points &P, int64_t n) {
     return eval_point(P, n, load_point_idx(P, n));
 }
 
+// ---- "tile" layout of the hash encodings / their gradients between the hash-grid and the tensor-core MLP kernels:
+// bf16, 128-sample tiles of 8 KB stored exactly as the tensor core wants its K-major operand (8 x 8 core matrices, no
+// swizzle): element (sample n, column c) lives at
+//     (n >> 7) * 8192 + (c >> 3) * 2048 + ((n & 127) >> 3) * 128 + (n & 7) * 16 + (c & 7) * 2
+// so a tile is ONE contiguous 8 KB block that goes to shared memory without conversion (four 16-byte pieces per row, or a
+// single bulk copy), and a warp's 32 consecutive rows write 512 contiguous bytes per 8-column piece.  Half the bytes of
+// the fp32 row-major form, which stays the format of the module-boundary / fp32 kernels.
+__device__ __forceinline__ int64_t enc_tile_piece(int64_t n, int piece) {  // byte offset of columns [8 piece, 8 piece + 8)
+    return (n >> 7) * 8192 + (int64_t)piece * 2048 + ((n & 127) >> 3) * 128 + (n & 7) * 16;
+}
+
 }  // namespace umhs

@@ -260,6 +260,35 @@ __device__ __forceinline__ void store_enc_rows(uint8_t *tile, int warp_row0, int
         *reinterpret_cast<uint2 *>(tile + tile_off(r, 4 * (lane & 7), CH_ACT)) = q;
     }
 }
+// ---- bf16 tile layout (common.cuh: enc_tile_piece): the row is already in operand order -- four 16-byte pieces per
+// thread, straight from global memory into the tile, no conversion, no cross-lane traffic
+__device__ __forceinline__ void load_enc_pieces(const float *__restrict__ enc_tiles, int64_t my_row, float4 (&e)[8]) {
+    const uint8_t *base = reinterpret_cast<const uint8_t *>(enc_tiles);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) e[c] = __ldg(reinterpret_cast<const float4 *>(base + enc_tile_piece(my_row, c)));
+}
+__device__ __forceinline__ void store_enc_pieces(uint8_t *tile, int row, const float4 (&e)[8]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) *reinterpret_cast<float4 *>(tile + c * CH_ACT + (row >> 3) * 128 + (row & 7) * 16) = e[c];
+}
+// gradient rows in the tile layout: packed to bf16 and parked in the thread's own slots of a shared-memory tile, then
+// (behind the next operand hand-off, see stage_rows) copied out as 16-byte pieces -- a warp writes 512 contiguous bytes
+__device__ __forceinline__ void stage_pieces(const float (&v)[32], uint8_t *tile, int row) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4 *>(tile + c * CH_ACT + (row >> 3) * 128 + (row & 7) * 16) =
+            make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+                       pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+}
+__device__ __forceinline__ void flush_staged_pieces(float *__restrict__ d_enc_tiles, int64_t n, const uint8_t *tile, int row) {
+    if (n < 0) return;
+    uint8_t *base = reinterpret_cast<uint8_t *>(d_enc_tiles);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4 *>(base + enc_tile_piece(n, c)) =
+            *reinterpret_cast<const uint4 *>(tile + c * CH_ACT + (row >> 3) * 128 + (row & 7) * 16);
+}
+
 // store: every lane holds its own row v[32]; the warp transposes through a private 4 KB staging block (XOR-swizzled
 // 16-byte pieces: conflict-free both ways) and writes whole rows.  row_of_lane < 0: that row is not written.
 // Two halves, so that the global stores can be issued BEHIND the next operand hand-off (fence.proxy.async also waits
@@ -521,7 +550,8 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         };
         auto load_rest = [&](int64_t tile) {
             if (tile >= n_tiles) return;
-            load_enc_rows(enc, erow_in, lane, e_in);
+            if (mp.enc_tiles) load_enc_pieces(enc, erow_in, e_in);
+            else load_enc_rows(enc, erow_in, lane, e_in);
             raw_in = load_point_raw(P, sample_of(tile), pi_in);
         };
         if (!(DENSITY_ONLY && !UMHS_DENSITY_PREFETCH)) {
@@ -541,7 +571,8 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             const Point pt = make_point(P, raw_in);
             float pe[12];
             // ---------------- round 0: enc -> tX (whole rows, coalesced) ; base0
-            store_enc_rows(tX, (warp & 3) * 32, lane, e_in);
+            if (mp.enc_tiles) store_enc_pieces(tX, row, e_in);
+            else store_enc_rows(tX, (warp & 3) * 32, lane, e_in);
             if (!DENSITY_ONLY) pos_encoding_tc(pt, pe);
             gs.arrive();
             if (DENSITY_ONLY && UMHS_DENSITY_PREFETCH) load_idx(tile_of(it + 1, grp));
@@ -888,7 +919,8 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         };
         auto load_rest = [&](int64_t tile) {
             if (tile >= n_tiles) return;  // group-uniform
-            load_enc_rows(enc, erow_in, lane, e_in);
+            if (mp.enc_tiles) load_enc_pieces(enc, erow_in, e_in);
+            else load_enc_rows(enc, erow_in, lane, e_in);
             raw_in = load_point_raw(P, sample_of(tile), pi_in);
         };
         load_idx(tile_of(0, grp));
@@ -905,7 +937,8 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             float pe[12];
             pos_encoding_tc(pt, pe);
             // ---------------- round 0: enc -> tA0 [, X2 -> tX2]
-            store_enc_rows(tA0, (warp & 3) * 32, lane, e_in);
+            if (mp.enc_tiles) store_enc_pieces(tA0, row, e_in);
+            else store_enc_rows(tA0, (warp & 3) * 32, lane, e_in);
             if (spec) {
                 float x2[32], sh[16];
                 sh_deg3_tc((pt.dx + 1.0f) / 2.0f, (pt.dy + 1.0f) / 2.0f, (pt.dz + 1.0f) / 2.0f, sh);
@@ -920,7 +953,10 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             }
             gs.arrive();
             // the previous tile's d_enc rows (staged in this warp's 4 KB of tD2, which nothing touches before round 2)
-            if (d_enc && it > 0) flush_staged_rows(d_enc, pending_row, tD2 + (warp & 3) * 4096, lane);
+            if (d_enc && it > 0) {
+                if (mp.enc_tiles) flush_staged_pieces(d_enc, pending_row, tD2, row);
+                else flush_staged_rows(d_enc, pending_row, tD2 + (warp & 3) * 4096, lane);
+            }
             gs.wait();
             // ---------------- round 1: H0 = relu(.) -> tH1, and kept in registers as packed bf16
             uint32_t h0p[32];
@@ -1089,11 +1125,15 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                 // behind the next tile's first hand-off (or after the loop)
                 float v[32];
                 tmem_ld32(trow, v);
-                stage_rows(v, tD2 + (warp & 3) * 4096, lane);
+                if (mp.enc_tiles) stage_pieces(v, tD2, row);
+                else stage_rows(v, tD2 + (warp & 3) * 4096, lane);
                 pending_row = valid ? n : -1;
             }
         }
-        if (d_enc && tile_of(0, grp) < n_tiles) flush_staged_rows(d_enc, pending_row, tD2 + (warp & 3) * 4096, lane);
+        if (d_enc && tile_of(0, grp) < n_tiles) {
+            if (mp.enc_tiles) flush_staged_pieces(d_enc, pending_row, tD2, row);
+            else flush_staged_rows(d_enc, pending_row, tD2 + (warp & 3) * 4096, lane);
+        }
         gs.tr.flush();
         if (colsum_owner<KM>(lane)) {  // one lane of each run owns column colsum_col<KM>(lane)
             const int col = colsum_col<KM>(lane);

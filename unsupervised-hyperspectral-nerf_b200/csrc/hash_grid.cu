@@ -120,7 +120,15 @@ struct SrcX01 {
 
 constexpr int kHashThreads = 256;
 
-template <class Src, bool PAIRS>
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+// TILES: enc is the bf16 tile buffer (common.cuh: enc_tile_piece; L must be 16), written as one 16-byte piece per four
+// levels; otherwise fp32 rows [n, 2L].
+template <class Src, bool PAIRS, bool TILES>
 __global__ void __launch_bounds__(kHashThreads)
 hash_encode_fwd_kernel(Src src, int64_t n_total, const float2 *__restrict__ table, const float *__restrict__ scalings,
                        int L, int log2T, float *__restrict__ enc) {
@@ -130,6 +138,8 @@ hash_encode_fwd_kernel(Src src, int64_t n_total, const float2 *__restrict__ tabl
     src.get(n, x, y, z);
     const uint32_t tmask = (log2T >= 32) ? 0xffffffffu : ((1u << log2T) - 1u);
     float *out = enc + n * (2 * L);
+    uint8_t *tiles = reinterpret_cast<uint8_t *>(enc);
+    uint32_t half_piece[2] = {0u, 0u};  // TILES: columns of the first level pair of a piece
     int l = 0;
     for (; l + 1 < L; l += 2) {
         uint32_t i0[8], i1[8];
@@ -142,7 +152,15 @@ hash_encode_fwd_kernel(Src src, int64_t n_total, const float2 *__restrict__ tabl
         gather_level(table, i1, PAIRS && p1, f1);
         const float2 a = blend(f0, ox0, oy0, oz0);
         const float2 b = blend(f1, ox1, oy1, oz1);
-        if ((L & 1) == 0) {
+        if (TILES) {
+            if ((l & 2) == 0) {
+                half_piece[0] = pack_bf16x2_rn(a.x, a.y);
+                half_piece[1] = pack_bf16x2_rn(b.x, b.y);
+            } else {
+                *reinterpret_cast<uint4 *>(tiles + enc_tile_piece(n, l >> 2)) =
+                    make_uint4(half_piece[0], half_piece[1], pack_bf16x2_rn(a.x, a.y), pack_bf16x2_rn(b.x, b.y));
+            }
+        } else if ((L & 1) == 0) {
             *reinterpret_cast<float4 *>(out + 2 * l) = make_float4(a.x, a.y, b.x, b.y);
         } else {
             *reinterpret_cast<float2 *>(out + 2 * l) = a;
@@ -194,7 +212,7 @@ __device__ __forceinline__ void scatter_add(float2 *table, uint32_t idx, float2 
 // 2 chunks 1.54 -> 1.68 ms per step, 3 chunks 1.77 ms.
 constexpr int kScatterThreads = 128;
 
-template <class Src, bool PAIRS>
+template <class Src, bool PAIRS, bool TILES>
 __global__ void __launch_bounds__(kScatterThreads)
 hash_encode_bwd_kernel(Src src, int64_t n_total, const float *__restrict__ scalings, int L, int log2T,
                        const float *__restrict__ d_enc, float2 *__restrict__ d_table, int agg_levels) {
@@ -208,11 +226,20 @@ hash_encode_bwd_kernel(Src src, int64_t n_total, const float *__restrict__ scali
         float x = 0.f, y = 0.f, z = 0.f;
         if (valid) src.get(n, x, y, z);
         const float *g = d_enc + (valid ? n : 0) * (2 * L);
+        const uint8_t *gt = reinterpret_cast<const uint8_t *>(d_enc);  // TILES: bf16 tile buffer
         for (int l = 0; l < L; ++l) {
             uint32_t idx[8];
             float ox, oy, oz;
             const bool pair = level_setup(x, y, z, __ldg(scalings + l), tmask, (uint32_t)l << log2T, idx, ox, oy, oz);
-            float2 d = valid ? __ldg(reinterpret_cast<const float2 *>(g + 2 * l)) : make_float2(0.f, 0.f);
+            float2 d = make_float2(0.f, 0.f);
+            if (valid) {
+                if (TILES) {  // columns 2 l, 2 l + 1: one bf16 pair inside the row's 16-byte piece l / 4
+                    const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(gt + enc_tile_piece(n, l >> 2)) + (l & 3));
+                    d = make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+                } else {
+                    d = __ldg(reinterpret_cast<const float2 *>(g + 2 * l));
+                }
+            }
             const float ux = 1.0f - ox, uy = 1.0f - oy, uz = 1.0f - oz;
             // weight of corner (X,Y,Z): (X==c ? o : 1-o) per axis; cz side carries oz
             const float wz[2] = {oz, uz};
@@ -277,9 +304,38 @@ extern "C" int umhs_hash_encode_fwd(const umhs_points *pts, int64_t n, const umh
                    "points need positions or the ray form");
     if (n <= 0) return UMHS_OK;
     SrcPoints src{*pts};
-    hash_encode_fwd_kernel<decltype(src), true><<<div_up(n, kHashThreads), kHashThreads, 0, as_stream(stream)>>>(
+    hash_encode_fwd_kernel<decltype(src), true, false><<<div_up(n, kHashThreads), kHashThreads, 0, as_stream(stream)>>>(
         src, n, reinterpret_cast<const float2 *>(grid->table), grid->scalings, grid->num_levels,
         grid->log2_table_size, enc);
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_hash_encode_fwd_tiles(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid, void *enc_tiles,
+                                          void *stream) {
+    if (n <= 0) return UMHS_OK;
+    UMHS_CHECK_ARG(pts != nullptr && enc_tiles != nullptr, "null argument");
+    UMHS_CHECK_ARG(check_grid(grid) == 0 && grid->num_levels == 16, "the tile layout is 16 levels x 2 features wide");
+    UMHS_CHECK_ARG(pts->positions || (pts->rays_o && pts->rays_d && pts->ray_indices && pts->t_starts && pts->t_ends),
+                   "points need positions or the ray form");
+    UMHS_CHECK_ARG((reinterpret_cast<uintptr_t>(enc_tiles) & 15u) == 0, "enc_tiles must be 16-byte aligned");
+    SrcPoints src{*pts};
+    hash_encode_fwd_kernel<decltype(src), true, true><<<div_up(n, kHashThreads), kHashThreads, 0, as_stream(stream)>>>(
+        src, n, reinterpret_cast<const float2 *>(grid->table), grid->scalings, grid->num_levels,
+        grid->log2_table_size, reinterpret_cast<float *>(enc_tiles));
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_hash_encode_bwd_tiles(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid,
+                                          const void *d_enc_tiles, float *d_table, void *stream) {
+    if (n <= 0) return UMHS_OK;
+    UMHS_CHECK_ARG(pts != nullptr && d_enc_tiles != nullptr && d_table != nullptr, "null argument");
+    UMHS_CHECK_ARG(check_grid(grid) == 0 && grid->num_levels == 16, "the tile layout is 16 levels x 2 features wide");
+    SrcPoints src{*pts};
+    hash_encode_bwd_kernel<decltype(src), true, true><<<scatter_grid(n, 0), kScatterThreads, 0, as_stream(stream)>>>(
+        src, n, grid->scalings, grid->num_levels, grid->log2_table_size, reinterpret_cast<const float *>(d_enc_tiles),
+        reinterpret_cast<float2 *>(d_table), agg_levels_for(grid));
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }
@@ -292,7 +348,7 @@ extern "C" int umhs_hash_encode_bwd(const umhs_points *pts, int64_t n, const umh
     if (n <= 0) return UMHS_OK;
     SrcPoints src{*pts};
     const int max_ctas = 0;
-    hash_encode_bwd_kernel<decltype(src), true><<<scatter_grid(n, max_ctas), kScatterThreads, 0, as_stream(stream)>>>(
+    hash_encode_bwd_kernel<decltype(src), true, false><<<scatter_grid(n, max_ctas), kScatterThreads, 0, as_stream(stream)>>>(
         src, n, grid->scalings, grid->num_levels, grid->log2_table_size, d_enc, reinterpret_cast<float2 *>(d_table),
         agg_levels_for(grid));
     UMHS_CHECK_LAUNCH();
@@ -306,7 +362,7 @@ extern "C" int umhs_hash_encode_x01_fwd(const float *x01, int64_t n, const umhs_
     UMHS_CHECK_ARG(check_grid(grid) == 0, "bad hash grid");
     if (n <= 0) return UMHS_OK;
     SrcX01 src{x01};
-    hash_encode_fwd_kernel<decltype(src), true><<<div_up(n, kHashThreads), kHashThreads, 0, as_stream(stream)>>>(
+    hash_encode_fwd_kernel<decltype(src), true, false><<<div_up(n, kHashThreads), kHashThreads, 0, as_stream(stream)>>>(
         src, n, reinterpret_cast<const float2 *>(grid->table), grid->scalings, grid->num_levels,
         grid->log2_table_size, enc);
     UMHS_CHECK_LAUNCH();
@@ -321,7 +377,7 @@ extern "C" int umhs_hash_encode_x01_bwd(const float *x01, int64_t n, const umhs_
     if (n <= 0) return UMHS_OK;
     SrcX01 src{x01};
     const int max_ctas = 0;
-    hash_encode_bwd_kernel<decltype(src), true><<<scatter_grid(n, max_ctas), kScatterThreads, 0, as_stream(stream)>>>(
+    hash_encode_bwd_kernel<decltype(src), true, false><<<scatter_grid(n, max_ctas), kScatterThreads, 0, as_stream(stream)>>>(
         src, n, grid->scalings, grid->num_levels, grid->log2_table_size, d_enc, reinterpret_cast<float2 *>(d_table),
         agg_levels_for(grid));
     UMHS_CHECK_LAUNCH();

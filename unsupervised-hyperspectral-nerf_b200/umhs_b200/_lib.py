@@ -37,7 +37,7 @@ _MLP_NAMES = ["base_w0", "base_b0", "base_w1", "base_b1", "head_w0", "head_b0", 
 
 class MlpParams(Structure):
     _fields_ = [(n, P) for n in _MLP_NAMES] + [("num_classes", c_int32), ("specular", c_int32),
-                                                 ("temperature", c_float)]
+                                                 ("temperature", c_float), ("enc_tiles", c_int32)]
 
 
 class MlpGrads(Structure):
@@ -99,6 +99,8 @@ _SIGNATURES = {
     "umhs_version": [],
     "umhs_hash_encode_fwd": [POINTER(Points), c_int64, POINTER(HashGrid), P, P],
     "umhs_hash_encode_bwd": [POINTER(Points), c_int64, POINTER(HashGrid), P, P, P],
+    "umhs_hash_encode_fwd_tiles": [POINTER(Points), c_int64, POINTER(HashGrid), P, P],
+    "umhs_hash_encode_bwd_tiles": [POINTER(Points), c_int64, POINTER(HashGrid), P, P, P],
     "umhs_hash_encode_x01_fwd": [P, c_int64, POINTER(HashGrid), P, P],
     "umhs_hash_encode_x01_bwd": [P, c_int64, POINTER(HashGrid), P, P, P],
     "umhs_density_fwd": [POINTER(Points), c_int64, P, POINTER(MlpParams), P, P],

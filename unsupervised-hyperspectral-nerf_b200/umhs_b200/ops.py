@@ -18,7 +18,8 @@ from ._lib import check, f32, ptr, stream_ptr
 ENC_DIM = 32  # 16 levels x 2 features
 
 # kernels launched per C-ABI entry point (for the bench's gpu_launches count)
-_LAUNCHES = {"umhs_hash_encode_fwd": 1, "umhs_hash_encode_bwd": 1, "umhs_hash_encode_x01_fwd": 1,
+_LAUNCHES = {"umhs_hash_encode_fwd": 1, "umhs_hash_encode_bwd": 1, "umhs_hash_encode_fwd_tiles": 1,
+             "umhs_hash_encode_bwd_tiles": 1, "umhs_hash_encode_x01_fwd": 1,
              "umhs_hash_encode_x01_bwd": 1, "umhs_density_fwd": 1, "umhs_field_mlp_fwd": 1, "umhs_field_mlp_bwd": 1,
              "umhs_composite_fwd": 1, "umhs_specular_tc_fwd": 1, "umhs_specular_tc_bwd": 1, "umhs_spectral_grad": 1, "umhs_depth_clip": 1, "umhs_depth_clip_chunks": 2, "umhs_composite_bwd": 1, "umhs_unmix_fwd": 1,
              "umhs_unmix_bwd": 1, "umhs_render_weights_fwd": 1, "umhs_render_weights_bwd": 1,
@@ -35,6 +36,19 @@ MLP_PRECISION = "bf16"
 # (csrc/specular_tc.cu, bf16 operands) whenever MLP_PRECISION is "bf16"; False / fp32 mode: the fp32 warp-per-ray
 # compositing kernel (csrc/composite.cu), the tight-parity bridge.
 SPECULAR_TC = True
+# True: between the hash-grid kernels and the tensor-core MLP kernels the encodings and their gradients travel as bf16
+# TILES (8 KB per 128 samples, already in the tensor core's operand order: csrc/common.cuh enc_tile_piece) instead of
+# fp32 rows -- half the bytes on five passes and no conversion / transposition in the MLP kernels.  Bit-identical
+# forward (the tensor-core kernels round the encodings to bf16 on load anyway); fp32 mode always uses fp32 rows.
+ENC_TILES = True
+
+
+def _tiles_on() -> bool:
+    return ENC_TILES and MLP_PRECISION == "bf16"
+
+
+def is_tile_buffer(enc: Tensor) -> bool:
+    return enc.dtype == torch.bfloat16
 
 
 class Profiler:
@@ -161,11 +175,17 @@ def _grid_struct(table: Tensor, scalings: Tensor, log2_T: int) -> _lib.HashGrid:
 
 
 # --------------------------------------------------------------------------------------- hash grid
-def hash_encode_fwd(pts: PointSet, table: Tensor, scalings: Tensor, log2_T: int) -> Tensor:
+def hash_encode_fwd(pts: PointSet, table: Tensor, scalings: Tensor, log2_T: int, tiles: bool = False) -> Tensor:
+    """-> enc [n, 2L] fp32, or (tiles=True, L = 16) the bf16 tile buffer [ceil(n/128)*128, 32] (see ENC_TILES)."""
     lib = _lib.load()
     L = int(scalings.shape[0])
-    enc = torch.empty((pts.n, 2 * L), dtype=torch.float32, device=table.device)
     ps, gs = pts.struct(), _grid_struct(table, scalings, log2_T)
+    if tiles:
+        enc = torch.empty(((pts.n + 127) // 128 * 128, 2 * L), dtype=torch.bfloat16, device=table.device)
+        _call("umhs_hash_encode_fwd_tiles", pts.units(), ctypes.byref(ps), pts.n, ctypes.byref(gs), ptr(enc),
+              stream_ptr(table.device))
+        return enc
+    enc = torch.empty((pts.n, 2 * L), dtype=torch.float32, device=table.device)
     _call("umhs_hash_encode_fwd", pts.units(), ctypes.byref(ps), pts.n, ctypes.byref(gs), ptr(enc), stream_ptr(table.device))
     return enc
 
@@ -177,8 +197,9 @@ def hash_encode_bwd(pts: PointSet, table: Tensor, scalings: Tensor, log2_T: int,
     if d_table is None:
         d_table = torch.zeros_like(table, dtype=torch.float32)
     ps, gs = pts.struct(), _grid_struct(table, scalings, log2_T)
-    _call("umhs_hash_encode_bwd", pts.units(), ctypes.byref(ps), pts.n, ctypes.byref(gs), ptr(d_enc), ptr(d_table),
-                                   stream_ptr(table.device))
+    name = "umhs_hash_encode_bwd_tiles" if is_tile_buffer(d_enc) else "umhs_hash_encode_bwd"
+    _call(name, pts.units(), ctypes.byref(ps), pts.n, ctypes.byref(gs), ptr(d_enc), ptr(d_table),
+          stream_ptr(table.device))
     return d_table
 
 
@@ -221,13 +242,16 @@ MLP_NAMES = _lib._MLP_NAMES
 
 
 def mlp_struct(weights: Dict[str, Optional[Tensor]], num_classes: int, specular: bool,
-               temperature: float) -> _lib.MlpParams:
+               temperature: float, enc_tiles: bool = False) -> _lib.MlpParams:
     s = _lib.MlpParams()
     for name in MLP_NAMES:
         setattr(s, name, ptr(weights.get(name)))
     s.num_classes = int(num_classes)
     s.specular = 1 if specular else 0
     s.temperature = float(temperature)
+    s.enc_tiles = 1 if enc_tiles else 0
+    if enc_tiles and MLP_PRECISION != "bf16":
+        raise _lib.UmhsError("bf16 tile buffers are an interface of the tensor-core kernels only")
     return s
 
 
@@ -237,7 +261,7 @@ def density_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], zero_tai
     # that only reads the counted entries -- the sampler's visibility pass -- skips the fill)
     fill = pts.n_dev is not None and zero_tail
     sigma = (torch.zeros if fill else torch.empty)((pts.n,), dtype=torch.float32, device=enc.device)
-    ps, ms = pts.struct(), mlp_struct(weights, 1, False, 1.0)
+    ps, ms = pts.struct(), mlp_struct(weights, 1, False, 1.0, is_tile_buffer(enc))
     _call("umhs_density_tc_fwd" if MLP_PRECISION == "bf16" else "umhs_density_fwd", pts.units(), ctypes.byref(ps), pts.n, ptr(enc), ctypes.byref(ms), ptr(sigma),
                                stream_ptr(enc.device))
     return sigma
@@ -256,7 +280,7 @@ def field_mlp_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int
     fo = _lib.FieldOut()
     for k, v in out.items():
         setattr(fo, k, ptr(v))
-    ps, ms = pts.struct(), mlp_struct(weights, K, specular, temperature)
+    ps, ms = pts.struct(), mlp_struct(weights, K, specular, temperature, is_tile_buffer(enc))
     _call("umhs_field_mlp_tc_fwd" if MLP_PRECISION == "bf16" else "umhs_field_mlp_fwd", pts.units(), ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(fo), stream_ptr(dev))
     return out
 
@@ -269,14 +293,18 @@ def field_mlp_bwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int
     dev, n = enc.device, pts.n
     if d_weights is None:
         d_weights = {k: torch.zeros_like(v, dtype=torch.float32) for k, v in weights.items() if v is not None}
-    d_enc = torch.empty((n, ENC_DIM), dtype=torch.float32, device=dev) if want_d_enc else None
+    tiles = is_tile_buffer(enc)  # the gradient goes back in the layout the encodings came in
+    d_enc = None
+    if want_d_enc:
+        d_enc = (torch.empty(((n + 127) // 128 * 128, ENC_DIM), dtype=torch.bfloat16, device=dev) if tiles else
+                 torch.empty((n, ENC_DIM), dtype=torch.float32, device=dev))
     g = _lib.FieldOutGrads()
     for k in ("d_sigma", "d_embedding", "d_scalar", "d_abund", "d_s1", "d_spec_hidden"):
         setattr(g, k, ptr(grads.get(k)))
     dp = _lib.MlpGrads()
     for name in MLP_NAMES:
         setattr(dp, name, ptr(d_weights.get(name)))
-    ps, ms = pts.struct(), mlp_struct(weights, K, specular, temperature)
+    ps, ms = pts.struct(), mlp_struct(weights, K, specular, temperature, tiles)
     _call("umhs_field_mlp_tc_bwd" if MLP_PRECISION == "bf16" else "umhs_field_mlp_bwd", pts.units(), ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(g), ptr(d_enc),
                                  ctypes.byref(dp), stream_ptr(dev))
     return d_enc, d_weights
@@ -292,7 +320,8 @@ class FieldFunction(torch.autograd.Function):
         ctx.set_materialize_grads(False)  # undefined output gradients arrive as None, not as zero-filled tensors
         weights = {n: (w.detach() if w is not None else None) for n, w in zip(MLP_NAMES, mlp)}
         # kept samples are a subset of the sampler's candidates: reuse their encodings when the sampler kept them
-        enc = pts.enc_src if pts.enc_src is not None else hash_encode_fwd(pts, table.detach(), scalings, cfg["log2_T"])
+        enc = pts.enc_src if pts.enc_src is not None else hash_encode_fwd(pts, table.detach(), scalings, cfg["log2_T"],
+                                                                           tiles=_tiles_on())
         out = field_mlp_fwd(pts, enc, weights, cfg["K"], cfg["specular"], cfg["temperature"],
                             want_embedding=cfg.get("want_embedding", True))
         ctx.pts, ctx.cfg = pts, cfg

@@ -191,7 +191,7 @@ class UMHSField(nn.Module):
     def density_packed(self, pts: PointSet, return_enc: bool = False, zero_tail: bool = True):
         """Density only, no autograd: the sampler's sigma_fn and the occupancy-grid update."""
         enc = self.mlp_base.encoder
-        e = ops.hash_encode_fwd(pts, enc.hash_table.detach(), enc.scalings, self._log2_T)
+        e = ops.hash_encode_fwd(pts, enc.hash_table.detach(), enc.scalings, self._log2_T, tiles=ops._tiles_on())
         sigma = ops.density_fwd(pts, e, self._weights_dict(), zero_tail=zero_tail)
         return (sigma, e) if return_enc else sigma
 
