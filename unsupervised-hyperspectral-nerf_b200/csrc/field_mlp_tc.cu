@@ -470,6 +470,7 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         for (int g = 0; g < G; ++g) {
             mbar_init(bars + g, 4);
             mbar_init(bars + G + g, 1);
+            mbar_init(reinterpret_cast<uint64_t *>(smem + TcSmem::sbias) + g, 1);  // `full`: bulk-copied tiles
             ready_flags(smem)[g] = 0u;
         }
         fence_mbar_init();
@@ -548,16 +549,29 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             pi_in = load_point_idx(P, nn);
             erow_in = enc_row(P, nn);
         };
+        // Contiguous bf16 tiles (no enc_index gather: the sampler's candidate pass, the occupancy update, evaluation
+        // rendering) do not go through registers at all: ONE bulk copy (cp.async.bulk, the TMA engine) per tile brings
+        // the 8 KB operand tile from global memory straight into tX, a whole tile ahead, completing on an mbarrier.
+        const bool bulk = mp.enc_tiles && P.enc_index == nullptr;
+        uint64_t *full = reinterpret_cast<uint64_t *>(smem + TcSmem::sbias) + grp;  // (sbias is a backward-only region)
+        auto bulk_issue = [&](int64_t tile) {
+            if (!bulk || row != 0 || tile >= n_tiles) return;
+            mbar_expect_tx(full, 8192u);
+            bulk_load(tX, reinterpret_cast<const uint8_t *>(enc) + tile * 8192, 8192u, full);
+        };
         auto load_rest = [&](int64_t tile) {
             if (tile >= n_tiles) return;
-            if (mp.enc_tiles) load_enc_pieces(enc, erow_in, e_in);
-            else load_enc_rows(enc, erow_in, lane, e_in);
+            if (!bulk) {
+                if (mp.enc_tiles) load_enc_pieces(enc, erow_in, e_in);
+                else load_enc_rows(enc, erow_in, lane, e_in);
+            }
             raw_in = load_point_raw(P, sample_of(tile), pi_in);
         };
         if (!(DENSITY_ONLY && !UMHS_DENSITY_PREFETCH)) {
             load_idx(tile_of(0, grp));
             load_rest(tile_of(0, grp));
         }
+        bulk_issue(tile_of(0, grp));
 
         for (int64_t it = 0; tile_of(it, grp) < n_tiles; ++it) {
             gs.round = 0;
@@ -571,12 +585,14 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             const Point pt = make_point(P, raw_in);
             float pe[12];
             // ---------------- round 0: enc -> tX (whole rows, coalesced) ; base0
-            if (mp.enc_tiles) store_enc_pieces(tX, row, e_in);
+            if (bulk) mbar_wait(full, (uint32_t)(it & 1));  // the copy engine has delivered this tile
+            else if (mp.enc_tiles) store_enc_pieces(tX, row, e_in);
             else store_enc_rows(tX, (warp & 3) * 32, lane, e_in);
             if (!DENSITY_ONLY) pos_encoding_tc(pt, pe);
             gs.arrive();
             if (DENSITY_ONLY && UMHS_DENSITY_PREFETCH) load_idx(tile_of(it + 1, grp));
             gs.wait();
+            if (DENSITY_ONLY) bulk_issue(tile_of(it + 1, grp));  // tX is free again: the next tile starts to arrive
             // ---------------- round 1: H0 = relu(.) -> tH ; (specular) [sh, pe, 1] -> tF[:, :32] ; base1 [, dir0]
             epi_relu64<false>(trow, tH, row, nullptr);
             if (spec) {
@@ -631,6 +647,7 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             gs.arrive();
             load_rest(tile_of(it + 1, grp));
             gs.wait();
+            bulk_issue(tile_of(it + 1, grp));  // X in tX has been consumed: the next tile's encodings may land
             // ---------------- round 3: hidden 0 of both MLPs -> tH, tF ; head1, feat1
             epi_relu64<false>(trow, tH, row, nullptr);
             epi_relu64<false>(trow + 64, tF, row, nullptr);
