@@ -72,6 +72,10 @@ NCU_TRAFFIC = {}
 try:
     with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as _fh:
         NCU_TRAFFIC = json.load(_fh)
+    # the capture is of the bf16-tile form of the hash kernels (what the config-2 step launches)
+    for _k in ("umhs_hash_encode_fwd", "umhs_hash_encode_bwd"):
+        if _k in NCU_TRAFFIC:
+            NCU_TRAFFIC.setdefault(_k + "_tiles", NCU_TRAFFIC[_k])
 except Exception:  # noqa: BLE001
     NCU_TRAFFIC = {}
 
