@@ -161,6 +161,13 @@ int umhs_field_mlp_tc_fwd(const umhs_points *pts, int64_t n, const float *enc, c
  * accumulators resident in TMEM for the whole persistent CTA. */
 int umhs_field_mlp_tc_bwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
                           const umhs_field_out_grads *g, float *d_enc, const umhs_mlp_grads *dp, void *stream);
+/* The same backward AND the hash-grid scatter of its d_enc (umhs_hash_encode_bwd_tiles) in one kernel: 11 more warps
+ * per CTA read the rows of d_enc_tiles back as the data warps publish them and add them into d_table (accumulating,
+ * [L * 2^log2_T, 2] f32) -- the autograd backward of `self.mlp_base(positions_flat)` (ref umhsnerf/umhs_field.py:320)
+ * through both of its halves.  Needs p->enc_tiles = 1 and the 16 x 2 grid; d_enc_tiles is still written (scratch). */
+int umhs_field_mlp_tc_bwd_scatter(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
+                                  const umhs_field_out_grads *g, void *d_enc_tiles, const umhs_mlp_grads *dp,
+                                  const umhs_hash_grid *grid, float *d_table, void *stream);
 /* Developer aid: install (or with NULL remove) a device buffer of 4*capacity_slots int64 in which CTA 0 of the
  * tensor-core MLP backward records (tag, clock64) pairs: slot-major, [who = 0 data thread 0 | 1 issuer][tag, clock]. */
 int umhs_debug_trace(int64_t *buffer, int32_t capacity_slots, void *stream);

@@ -625,6 +625,54 @@ def _rows_to_tile(rows):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n,spec", [(1, False), (129, False), (40000, True), (300001, False)])
+def test_mlp_backward_with_scatter_on_board(n, spec):
+    """umhs_field_mlp_tc_bwd_scatter (the opt-in single-kernel form: hash-grid scatter on extra warps of the tensor-core
+    MLP backward) against the two kernels back to back: same weight gradients (same MMAs; atomics reorder), same table
+    gradient (same products; the runs are summed in a different order: fp32 rounding only)."""
+    ops = _ops()
+    from helpers import mlp_precision
+    g = torch.Generator().manual_seed(n)
+    log2_T, L, K = 14, 16, 4
+    table = ((torch.rand(L << log2_T, 2, generator=g) * 2 - 1) * 0.5).to(DEV)
+    scal = torch.floor(16 * torch.exp(torch.arange(L) * (np.log(2048 / 16) / (L - 1)))).float().to(DEV)
+    R = max(1, n // 40)
+    o = torch.rand(R, 3, generator=g) * 1.6 - 0.8
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    idx = torch.arange(n)
+    pos = (o[idx % R] + (idx // R).float()[:, None] * 0.004 * d[idx % R])
+    order = torch.argsort((idx % R) * 100000 + idx // R)  # ray-major: consecutive samples of a ray are neighbours
+    pos = pos[order].contiguous().to(DEV)
+    dirs = d[(idx % R)[order]].contiguous().to(DEV)
+    pts = ops.PointSet.from_positions(pos, dirs, contraction=False, aabb=(-1, -1, -1, 1, 1, 1))
+    mk = lambda o_, i_: ((torch.rand(o_, i_, generator=g) * 2 - 1) / i_ ** 0.5).to(DEV).contiguous()  # noqa: E731
+    w = {}
+    for name, (o_, i_) in {"base_w0": (64, 32), "base_w1": (16, 64), "head_w0": (64, 27), "head_w1": (64, 64),
+                           "head_w2": (K, 64), "feat_w0": (64, 27), "feat_w1": (64, 64), "feat_w2": (K + spec, 64),
+                           "dir_w0": (16, 28)}.items():
+        w[name] = mk(o_, i_)
+        w[name.replace("_w", "_b")] = (torch.rand(o_, generator=g) * 0.1).to(DEV)
+    if not spec:
+        w["dir_w0"] = w["dir_b0"] = None
+    grads = {"d_sigma": torch.randn(n, generator=g).to(DEV), "d_scalar": torch.randn(n, K, generator=g).to(DEV),
+             "d_abund": torch.randn(n, K, generator=g).to(DEV), "d_embedding": None}
+    if spec:
+        grads["d_s1"] = torch.randn(n, generator=g).to(DEV)
+        grads["d_spec_hidden"] = torch.randn(n, 16, generator=g).to(DEV)
+    with mlp_precision("bf16"):
+        enc = ops.hash_encode_fwd(pts, table, scal, log2_T, tiles=True)
+        d_enc, gw_a = ops.field_mlp_bwd(pts, enc, w, K, spec, 0.4, grads)
+        t_a = ops.hash_encode_bwd(pts, table, scal, log2_T, d_enc)
+        t_b = torch.zeros_like(table)
+        d_enc_b, gw_b = ops.field_mlp_bwd(pts, enc, w, K, spec, 0.4, grads, scatter=(table, scal, log2_T, t_b))
+    assert torch.equal(_tile_to_rows(d_enc_b, n), _tile_to_rows(d_enc, n))
+    assert_close(t_b, t_a, 1e-4, 1e-5 * float(t_a.abs().max()) + 1e-9, "d_table")
+    assert float(t_a.abs().max()) > 0
+    for k in gw_a:
+        assert_close(gw_b[k], gw_a[k], 1e-4, 1e-5 * float(gw_a[k].abs().max()) + 1e-9, k)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n", [1, 127, 128, 1000, 70001])
 def test_enc_tile_layout_round_trip(n):
     """The bf16 tile layout between the hash-grid and the tensor-core MLP kernels (ops.ENC_TILES): the forward gather

@@ -19,12 +19,24 @@
 #include <utility>
 
 #include "common.cuh"
+#include "hash_scatter.cuh"
 #include "tc05.cuh"
 
 namespace umhs {
 using namespace tc05;
 
 constexpr int TM = 128;          // samples per tile == threads per group
+#ifndef UMHS_FWD_ISSUERS
+#define UMHS_FWD_ISSUERS 0   // MMA-issuing warps of the forward kernels: 1 = one, 2 = one per data group, 0 = what measured
+#endif                       // best at 825 k samples: density one per group (45.0 against 47.3 us), full forward one (120.8
+                             // against 124.9 us)
+#ifndef UMHS_BWD_ISSUERS
+#define UMHS_BWD_ISSUERS 1   // ... of the backward kernel: 2 = one per data group (each group then owns a copy of the
+#endif                       // weight-gradient accumulators), 1 = one for both.  Measured equal (430 / 431 us): a round is
+                             // bound by the group's own chain epilogue -> hand-off -> MMA -> hand-off, not by queueing
+#ifndef UMHS_SCATTER_WARPS
+#define UMHS_SCATTER_WARPS (8 - UMHS_BWD_ISSUERS)   // fills the fourth warpgroup
+#endif
 #ifndef UMHS_ISSUER_SPIN
 #define UMHS_ISSUER_SPIN 4096
 #endif
@@ -62,7 +74,8 @@ struct TcSmem {
     static constexpr int ones = w_end;                      // [128 x 16] of 1.0
     static constexpr int ctrl = ones + 2 * CH_ACT;          // mbarriers ready[4], done[4]; tmem address
     static constexpr int sbias = ctrl + 128;                // backward: fp32 [64] narrow-layer bias gradients
-    static constexpr int trace = sbias + 256;               // developer cycle trace: 2 threads x 256 stamps x 8 B
+    static constexpr int scat = sbias + 256;                // backward + scatter: uint32 flushed[8], next_unit
+    static constexpr int trace = scat + 128;                // developer cycle trace: 2 threads x 256 stamps x 8 B
     static constexpr int groups = trace + 4096;
     static_assert(groups % 128 == 0, "operand tiles must stay 128-byte aligned");
 };
@@ -317,6 +330,28 @@ __device__ __forceinline__ void store_rows_coalesced(float *__restrict__ dst, in
     flush_staged_rows(dst, my_row, stage, lane);
 }
 
+// ---- data warp -> scatter warps: "the d_enc rows of my first `count` tiles are visible" (SCATTER form of the backward)
+__device__ __forceinline__ void publish_rows(uint32_t *flag, uint32_t count, int lane) {
+    // CTA scope is enough (publisher and readers share the CTA) and it has to be: a GPU-scope fence here waits behind
+    // the thousands of reductions the scatter warps of this SM have in flight (measured: the kernel 3 x slower)
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(flag)), "r"(count) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t *flag) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(flag)) : "memory");
+    return v;
+}
+template <int R>
+__device__ __forceinline__ void setmaxnreg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R));
+}
+template <int R>
+__device__ __forceinline__ void setmaxnreg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R));
+}
+
 // ---- group <-> issuer handshake
 struct GroupSync {
     uint64_t *ready, *done;
@@ -370,17 +405,21 @@ __device__ __forceinline__ void static_for(F &&f) {
 // computes per MMA (runtime descriptor arithmetic, dispatch, divergence handling) is serialised into every round.
 // One lane is elected per round (elect_one) and issues that round's MMAs and their commit.
 // issue(round, group, acc): acc = 0 on the CTA's very first tile (persistent accumulators are initialised).
-template <int G, int ROUNDS, class F>
+// An issuer warp serves the groups [G0, G1) of the CTA's G groups (one warp for all of them, or one warp per group:
+// the MMAs of different groups touch disjoint accumulators, so nothing orders them against each other, and a group no
+// longer queues behind the other groups' visits -- ~450 cycles each -- on every one of its rounds).
+template <int G0, int G1, int G, int ROUNDS, class F>
 __device__ __forceinline__ void issuer_rotation(uint64_t *bars, const int64_t (&n_iter)[G], Tracer tr, F &&issue) {
     uint32_t par[G];
     const uint32_t *flags = reinterpret_cast<const uint32_t *>(bars) + 24;  // ctrl + 96, see ready_flags()
 #pragma unroll
     for (int g = 0; g < G; ++g) par[g] = 0u;
 #pragma unroll 1
-    for (int64_t it = 0; it < n_iter[0]; ++it) {  // group 0 never has fewer tiles than the others
+    for (int64_t it = 0; it < n_iter[G0]; ++it) {  // a group never has fewer tiles than the groups behind it
         static_for<ROUNDS>([&](auto rc) {
-            static_for<G>([&](auto gc) {
-                constexpr int g = decltype(gc)::value;
+            static_for<G1 - G0>([&](auto gi) {
+                constexpr int g = G0 + decltype(gi)::value;
+                constexpr std::integral_constant<int, g> gc{};
                 if (it < n_iter[g]) {  // warp-uniform
                     tr.stamp(6000 + 100 * g + decltype(rc)::value);
                     if (kNamedBarReady) {
@@ -403,10 +442,10 @@ __device__ __forceinline__ void issuer_rotation(uint64_t *bars, const int64_t (&
                         // phase 1: MMAs nobody waits for (weight gradients into the persistent accumulators) go out
                         // BEHIND the commit, while the group already runs its epilogue.  The next commit of this thread
                         // covers them, so an operand tile they read may be overwritten one round later, not earlier.
-                        issue(rc, gc, (it == 0 && g == 0) ? 0u : 1u, (uint32_t)(it >> 40), std::integral_constant<int, 0>{});
+                        issue(rc, gc, (it == 0 && g == G0) ? 0u : 1u, (uint32_t)(it >> 40), std::integral_constant<int, 0>{});
                         commit(bars + G + g);
                         tr.stamp(4000 + 100 * g + decltype(rc)::value);
-                        issue(rc, gc, (it == 0 && g == 0) ? 0u : 1u, (uint32_t)(it >> 40), std::integral_constant<int, 1>{});
+                        issue(rc, gc, (it == 0 && g == G0) ? 0u : 1u, (uint32_t)(it >> 40), std::integral_constant<int, 1>{});
                         tr.stamp(5000 + 100 * g + decltype(rc)::value);
                     }
                     __syncwarp();
@@ -416,6 +455,18 @@ __device__ __forceinline__ void issuer_rotation(uint64_t *bars, const int64_t (&
         });
     }
     tr.flush();
+}
+
+// issuer warp `ii` of `I` serves groups [ii * G / I, (ii + 1) * G / I)
+template <int I, int G, int ROUNDS, class F>
+__device__ __forceinline__ void issuer_dispatch(int ii, uint64_t *bars, const int64_t (&n_iter)[G], uint8_t *smem, int lane,
+                                                F &&issue) {
+    static_for<I>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        if (ii == i)  // warp-uniform
+            issuer_rotation<i * G / I, (i + 1) * G / I, G, ROUNDS>(
+                bars, n_iter, Tracer(lane == 0 && i == 0, 1, smem, 6 * (G / I) * ROUNDS), issue);
+    });
 }
 
 // =====================================================================================================
@@ -437,7 +488,8 @@ __device__ __forceinline__ void issuer_rotation(uint64_t *bars, const int64_t (&
 template <bool DENSITY_ONLY>
 struct TcFwdCfg {
     static constexpr int G = DENSITY_ONLY ? UMHS_DENSITY_G : 3;
-    static constexpr int kThreads = G * TM + 32;
+    static constexpr int I = UMHS_FWD_ISSUERS == 2 || (UMHS_FWD_ISSUERS == 0 && DENSITY_ONLY) ? G : 1;  // MMA-issuing warps
+    static constexpr int kThreads = G * TM + 32 * I;
 };
 struct TcFwd {
     static constexpr int tX = 0;
@@ -485,8 +537,8 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
     const int64_t n_tiles = (n_total + TM - 1) / TM;
     auto tile_of = [&](int64_t it, int q) { return (it * gridDim.x + blockIdx.x) * G + q; };
 
-    if (grp == G) {
-        // ======================= MMA issuer warp (all lanes, warp-uniform)
+    if (grp >= G) {
+        // ======================= MMA issuer warps (all lanes, warp-uniform)
         int64_t n_iter[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) {
@@ -494,7 +546,7 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             n_iter[g] = first < n_tiles ? (n_tiles - 1 - first) / stride + 1 : 0;
         }
         const uint32_t sbase = smem_u32(smem);
-        issuer_rotation<G, ROUNDS>(bars, n_iter, Tracer(lane == 0, 1, smem, 6 * G * ROUNDS), [&](auto rc, auto gc, uint32_t, uint32_t zero, auto ph) {
+        issuer_dispatch<TcFwdCfg<DENSITY_ONLY>::I, G, ROUNDS>(warp - G * 4, bars, n_iter, smem, lane, [&](auto rc, auto gc, uint32_t, uint32_t zero, auto ph) {
             constexpr int r = decltype(rc)::value, g = decltype(gc)::value;
             if constexpr (decltype(ph)::value != 0) return;  // the forward has no deferred MMAs
             const uint32_t B16 = desc_base16(sbase) + zero;   // descriptors = B16 + compile-time constants
@@ -731,8 +783,24 @@ struct TcBwd {
     static constexpr int P_b1t = 384, P_b0 = 400, P_d0 = 440;  // P_d0: [64 (16 real rows) x 32] .. 472
     static constexpr int ncols = 512;
     static constexpr int kRounds = 16;
-    static constexpr int kThreads = G * TM + 32;
+    static constexpr int I = UMHS_BWD_ISSUERS;              // MMA-issuing warps: one per group, or one for both
+    static constexpr int kThreads = G * TM + 32 * I;
+    // with the hash-grid scatter on board: 4 warpgroups -- data, data, [issuer + 3 scatter warps], 4 scatter warps
+    static constexpr int kScatterWarps = UMHS_SCATTER_WARPS;
+    static constexpr int kThreadsScatter = kThreads + 32 * kScatterWarps;  // 512
+    static constexpr int kRegsData = 168, kRegsOther = I + UMHS_SCATTER_WARPS == 8 ? 88 : 168;  // setmaxnreg: 256 * 168 + 256 * 88 = 512 * 128
     static constexpr int smem_bytes = TcSmem::groups + G * grp_bytes;
+};
+static_assert(TcBwd::kThreadsScatter % 128 == 0, "setmaxnreg works on whole warpgroups");
+constexpr bool kScatterSetRegs = TcBwd::kRegsOther != TcBwd::kRegsData;
+static_assert(2 * TM * TcBwd::kRegsData + (TcBwd::kThreadsScatter - 2 * TM) * TcBwd::kRegsOther <= 65536,
+              "register pool of the CTA");
+
+// what the scatter warps need of the hash grid (see umhs_field_mlp_tc_bwd_scatter)
+struct ScatterArgs {
+    const float *scalings;
+    float2 *d_table;
+    int L, log2T, agg_levels;
 };
 static_assert(TcBwd::smem_bytes <= 232448, "shared-memory plan exceeds 227 KB");
 
@@ -764,11 +832,19 @@ __device__ __forceinline__ float warp_colsum(const float *v, int lane) {
 }
 
 // flush one persistent [64 x ncols] accumulator: this thread's row r = 16*warp + lane (lane < 16)
+// (both: lanes 16-31 hold group 1's copy of the same rows; it is added when that group ran at all)
 template <class F>
-__device__ __forceinline__ void flush_acc(uint32_t trow, int col0, int ncols, int lane, F &&sink) {
+__device__ __forceinline__ void flush_acc(uint32_t trow, int col0, int ncols, int lane, bool both, bool hi_valid, F &&sink) {
     for (int c = 0; c < ncols; c += 16) {
         float v[16];
         tmem_ld16(trow + (uint32_t)(col0 + c), v);  // .sync.aligned: every lane participates
+        if (both) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float o = __shfl_down_sync(kFull, v[i], 16);
+                if (hi_valid) v[i] += o;
+            }
+        }
         if (lane < 16) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
@@ -778,22 +854,36 @@ __device__ __forceinline__ void flush_acc(uint32_t trow, int col0, int ncols, in
 }
 
 // KM: compile-time bound on the number of classes K (4, 8 or 16): sizes the softmax / sigmoid epilogues
-template <int KM>
-__global__ void __launch_bounds__(TcBwd::kThreads, 1)  // 9 warps: 3 on one SM sub-partition (16K registers) -> 168
+//
+// SCATTER (opt-in, measured slower than the two kernels back to back: 0.66 against 0.63 ms at 819 k samples): the
+// hash-grid scatter of d_enc (hash_scatter.cuh; otherwise the separate kernel of hash_grid.cu) runs INSIDE this kernel,
+// on 7 more warps per CTA.  On paper the two kernels need different halves of an SM -- this one is a chain of
+// dependent tensor-core rounds that leaves ~80 % of the issue slots idle, the scatter is bound by the reduction path
+// (40 M red sectors) -- but the reductions and the shared-memory stores of the epilogues share the SM's load/store
+// unit: with the reductions switched off the scatter warps cost 0.06 ms, with them 0.30 ms (the whole stand-alone
+// scatter), i.e. nothing overlaps.  With 3 scatter warps (no setmaxnreg) 1.06 ms: a warp waits ~250 cycles per
+// reduction it issues, so few warps cannot keep the reduction path busy either.  A data warp publishes "tile t of my 32 rows is in d_enc" (fence + a counter in shared memory) after its
+// deferred row flush; scatter warps take (tile, quarter) units in that order from a shared ticket, wait for the counter,
+// read the rows back (L2) and issue the reductions.  d_enc must be the bf16 tile buffer.  Registers: the CTA is
+// launched with 512 x 128; the data warpgroups raise themselves to 168, the other two drop to 88 (setmaxnreg).
+template <int KM, bool SCATTER>
+__global__ void __launch_bounds__(SCATTER ? TcBwd::kThreadsScatter : TcBwd::kThreads, 1)  // 9 warps: 3 on one SM sub-partition (16K registers) -> 168
 field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict__ enc, umhs_mlp_params mp,
-                        umhs_field_out_grads g, float *__restrict__ d_enc, umhs_mlp_grads dp) {
+                        umhs_field_out_grads g, float *__restrict__ d_enc, umhs_mlp_grads dp, ScatterArgs sc) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int G = TcBwd::G;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = mp.num_classes, spec = mp.specular;
-    const int grp = tid >> 7, row = tid & 127;
+    const int grp = warp < G * 4 ? (tid >> 7) : G, row = tid & 127;  // grp == G: not a data thread
+    uint32_t *scat = reinterpret_cast<uint32_t *>(smem + TcSmem::scat);  // flushed[G * 4], next_unit
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TcSmem::ctrl);  // ready[G], done[G]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TcSmem::ctrl + 64);
     float *sbias = reinterpret_cast<float *>(smem + TcSmem::sbias);      // h2[16] f2[17 of 32]... see below
     uint8_t *gbase = smem + TcSmem::groups + (grp < G ? grp : 0) * TcBwd::grp_bytes;
 
     // ---- one-time setup: weights, ones chunks, barriers, TMEM
-    stage_all_weights(smem, mp, false, tid, TcBwd::kThreads);
+    stage_all_weights(smem, mp, false, tid, (int)blockDim.x);
+    if (tid < 16) scat[tid] = 0u;
     if (tid < G * TM) {
         const float one[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
         store8(gbase + TcBwd::tA0, row, 32, CH_ACT, one);
@@ -819,17 +909,44 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
     const int64_t n_tiles = (n_total + TM - 1) / TM;
     auto tile_of = [&](int64_t it, int q) { return (it * gridDim.x + blockIdx.x) * G + q; };
 
-    if (grp == G) {
-        // ======================= MMA issuer warp (all lanes, warp-uniform)
-        int64_t n_iter[G];
+    int64_t n_iter[G];
 #pragma unroll
-        for (int q = 0; q < G; ++q) {
-            const int64_t first = (int64_t)blockIdx.x * G + q, stride = (int64_t)gridDim.x * G;
-            n_iter[q] = first < n_tiles ? (n_tiles - 1 - first) / stride + 1 : 0;
+    for (int q = 0; q < G; ++q) {
+        const int64_t first = (int64_t)blockIdx.x * G + q, stride = (int64_t)gridDim.x * G;
+        n_iter[q] = first < n_tiles ? (n_tiles - 1 - first) / stride + 1 : 0;
+    }
+    // (setmaxnreg sits at the top of the two role branches: the register budget of a region is what dominates it)
+    if (grp == G) {
+      if (SCATTER && kScatterSetRegs) setmaxnreg_dec<TcBwd::kRegsOther>();
+      if (SCATTER && warp >= G * 4 + TcBwd::I) {
+        // ======================= scatter warps: units (iteration, group, quarter) in the order the data warps publish
+        const uint32_t total = (uint32_t)(n_iter[0] * (G * 4));  // group 0 never has fewer tiles than the others
+        const uint8_t *gt = reinterpret_cast<const uint8_t *>(d_enc);
+        for (;;) {
+            uint32_t u = 0;
+            if (lane == 0) u = atomicAdd(scat + G * 4, 1u);
+            u = __shfl_sync(kFull, u, 0);
+            if (u >= total) break;
+            const int64_t it = u / (G * 4);
+            const int q = (u >> 2) % G, quarter = u & 3;
+            if (tile_of(it, q) >= n_tiles) continue;
+            while (ld_acquire_shared(scat + q * 4 + quarter) <= (uint32_t)it) __nanosleep(64);
+            const int64_t n = tile_of(it, q) * TM + quarter * 32 + lane;
+            const bool valid = n < n_total;
+            float x = 0.f, y = 0.f, z = 0.f;
+            if (valid) {
+                const Point pt = eval_point(P, n);
+                x = pt.x;
+                y = pt.y;
+                z = pt.z;
+            }
+            scatter_sample_runs(x, y, z, valid, n, gt, sc.scalings, sc.log2T, sc.d_table, sc.agg_levels, lane);
         }
+      } else {
+        // ======================= MMA issuer warp (all lanes, warp-uniform)
         const uint32_t sbase = smem_u32(smem);
         const bool want_denc = d_enc != nullptr;
-        issuer_rotation<G, TcBwd::kRounds>(bars, n_iter, Tracer(lane == 0, 1, smem, 6 * G * TcBwd::kRounds), [&](auto rc, auto gc, uint32_t acc,
+        issuer_dispatch<TcBwd::I, G, TcBwd::kRounds>(warp - G * 4, bars, n_iter, smem, lane, [&](auto rc, auto gc, uint32_t acc,
                                                                                   uint32_t zero, auto ph) {
             constexpr int r = decltype(rc)::value, q = decltype(gc)::value;
             constexpr bool crit = decltype(ph)::value == 0, late = !crit;  // before / behind the round's commit
@@ -839,6 +956,9 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             constexpr uint32_t sA0 = b + TcBwd::tA0, sX = b + TcBwd::tX, sH1 = b + TcBwd::tH1, sH2 = b + TcBwd::tH2;
             constexpr uint32_t sD1 = b + TcBwd::tD1, sD2 = b + TcBwd::tD2, sX2 = sD1;
             const uint32_t tw = tbase + 64u * q;
+            // persistent weight-gradient accumulators ([64 x N], M = 64: TMEM lanes 0-15 of every quarter): with one
+            // issuer per group each group owns a copy -- group 1's in lanes 16-31 of the same columns
+            const uint32_t ta = tbase + ((TcBwd::I == 2 && q == 1) ? (16u << 16) : 0u);
             if constexpr (r == 0) {         // base layer 0
                 if (crit) {
                     gemm_kmajor(tw, B16, sA0, w::b0, 64, 0, 64, 32, 0);
@@ -852,7 +972,7 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                 }
             } else if constexpr (r == 2) {  // mlp_head layer 0 [+ wgrad of mlp_directional layer 0]
                 if (crit) gemm_kmajor(tw, B16, sX, w::hf0, 128, 0, 64, 32, 0);
-                if (late && spec) gemm_wgrad(tbase + TcBwd::P_d0, B16, sD2, 0, sX2, 0, 32, acc);
+                if (late && spec) gemm_wgrad(ta + TcBwd::P_d0, B16, sD2, 0, sX2, 0, 32, acc);
             } else if constexpr (r == 3) {
                 if (crit) {
                     gemm_kmajor(tw, B16, sH1, w::h1, 64, 0, 64, 64, 0);
@@ -865,13 +985,13 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                 }
             } else if constexpr (r == 5) {
                 if (crit) gemm_dgrad(tw, B16, sD2, w::h2, 16, 0, 64, 16, 0);
-                if (late) gemm_wgrad(tbase + TcBwd::P_h2t, B16, sH2, 0, sD2, 0, 16, acc);
+                if (late) gemm_wgrad(ta + TcBwd::P_h2t, B16, sH2, 0, sD2, 0, 16, acc);
             } else if constexpr (r == 6) {
                 if (crit) gemm_dgrad(tw, B16, sD1, w::h1, 64, 0, 64, 64, 0);
-                if (late) gemm_wgrad(tbase + TcBwd::P_h1, B16, sD1, 0, sH1, 0, 72, acc);  // 64 + ones
+                if (late) gemm_wgrad(ta + TcBwd::P_h1, B16, sD1, 0, sH1, 0, 72, acc);  // 64 + ones
             } else if constexpr (r == 7) {
                 if (crit) gemm_dgrad(tw, B16, sD2, w::hf0, 128, 0, 32, 64, 0);
-                if (late) gemm_wgrad(tbase + TcBwd::P_h0, B16, sD2, 0, sX, 0, 32, acc);   // column 27 = ones
+                if (late) gemm_wgrad(ta + TcBwd::P_h0, B16, sD2, 0, sX, 0, 32, acc);   // column 27 = ones
             } else if constexpr (r == 8) {  // feature_mlp layer 0
                 if (crit) gemm_kmajor(tw, B16, sX, w::hf0, 128, 64, 64, 32, 0);
             } else if constexpr (r == 9) {
@@ -886,27 +1006,29 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                 }
             } else if constexpr (r == 11) {
                 if (crit) gemm_dgrad(tw, B16, sD2, w::f2, 32, 0, 64, 32, 0);
-                if (late) gemm_wgrad(tbase + TcBwd::P_f2t, B16, sH2, 0, sD2, 0, 32, acc);
+                if (late) gemm_wgrad(ta + TcBwd::P_f2t, B16, sH2, 0, sD2, 0, 32, acc);
             } else if constexpr (r == 12) {
                 if (crit) gemm_dgrad(tw, B16, sD1, w::f1, 64, 0, 64, 64, 0);
-                if (late) gemm_wgrad(tbase + TcBwd::P_f1, B16, sD1, 0, sH1, 0, 72, acc);
+                if (late) gemm_wgrad(ta + TcBwd::P_f1, B16, sD1, 0, sH1, 0, 72, acc);
             } else if constexpr (r == 13) {
                 if (crit) gemm_dgrad(tw, B16, sD2, w::hf0, 128, 64, 32, 64, 0);
-                if (late) gemm_wgrad(tbase + TcBwd::P_f0, B16, sD2, 0, sX, 0, 32, acc);
+                if (late) gemm_wgrad(ta + TcBwd::P_f0, B16, sD2, 0, sX, 0, 32, acc);
             } else if constexpr (r == 14) {  // base layer 1 backward (H0 is back in tH1; d [o0, emb] sits in tD1)
                 if (crit) gemm_dgrad(tw, B16, sD1, w::b1, 16, 0, 64, 16, 0);
-                if (late) gemm_wgrad(tbase + TcBwd::P_b1t, B16, sH1, 0, sD1, 0, 16, acc);
+                if (late) gemm_wgrad(ta + TcBwd::P_b1t, B16, sH1, 0, sD1, 0, 16, acc);
             } else {                         // 15: base layer 0 backward (wgrad N = 32 + ones chunk), delta in tD2
                 // its weight gradient reads tA0, which the NEXT tile's first epilogue overwrites: not deferred
                 if (crit) {
                     if (want_denc) gemm_dgrad(tw, B16, sD2, w::b0, 64, 0, 32, 64, 0);
-                    gemm_wgrad(tbase + TcBwd::P_b0, B16, sD2, 0, sA0, 0, 40, acc);
+                    gemm_wgrad(ta + TcBwd::P_b0, B16, sD2, 0, sA0, 0, 40, acc);
                 }
             }
         });
         __syncwarp();
+      }
     } else {
         // ======================= data groups: thread `row` of group `grp` owns one sample of the group's tile
+        if (SCATTER && kScatterSetRegs) setmaxnreg_inc<TcBwd::kRegsData>();
         uint8_t *tA0 = gbase + TcBwd::tA0, *tX = gbase + TcBwd::tX, *tH1 = gbase + TcBwd::tH1;
         uint8_t *tH2 = gbase + TcBwd::tH2, *tD1 = gbase + TcBwd::tD1, *tD2 = gbase + TcBwd::tD2;
         uint8_t *tX2 = tD1;
@@ -973,6 +1095,7 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             if (d_enc && it > 0) {
                 if (mp.enc_tiles) flush_staged_pieces(d_enc, pending_row, tD2, row);
                 else flush_staged_rows(d_enc, pending_row, tD2 + (warp & 3) * 4096, lane);
+                if (SCATTER) publish_rows(scat + grp * 4 + (warp & 3), (uint32_t)it, lane);
             }
             gs.wait();
             // ---------------- round 1: H0 = relu(.) -> tH1, and kept in registers as packed bf16
@@ -1150,6 +1273,7 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         if (d_enc && tile_of(0, grp) < n_tiles) {
             if (mp.enc_tiles) flush_staged_pieces(d_enc, pending_row, tD2, row);
             else flush_staged_rows(d_enc, pending_row, tD2 + (warp & 3) * 4096, lane);
+            if (SCATTER) publish_rows(scat + grp * 4 + (warp & 3), (uint32_t)n_iter[grp], lane);
         }
         gs.tr.flush();
         if (colsum_owner<KM>(lane)) {  // one lane of each run owns column colsum_col<KM>(lane)
@@ -1166,27 +1290,28 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
     __syncthreads();
     fence_after_sync();
     const bool any_tile = tile_of(0, 0) < n_tiles;  // group 0 ran >= 1 tile => every accumulator was initialised
+    const bool hi_valid = tile_of(0, 1) < n_tiles;  // (two issuers) group 1 ran >= 1 tile => so was its copy
     if (grp < G && any_tile) {
         const uint32_t tq = tbase + ((uint32_t)((warp & 3) * 32) << 16);
         const int r = (warp & 3) * 16 + lane;
         if (grp == 0) {
-            flush_acc(tq, TcBwd::P_h2t, K, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.head_w2 + c * 64 + r, v); });
-            flush_acc(tq, TcBwd::P_h1, 65, lane, [&](int c, float v) {
-                if (v != 0.f) atomicAdd(c < 64 ? dp.head_w1 + r * 64 + c : dp.head_b1 + r, v); });
-            flush_acc(tq, TcBwd::P_h0, 28, lane, [&](int c, float v) {
-                if (v != 0.f) atomicAdd(c < 27 ? dp.head_w0 + r * 27 + c : dp.head_b0 + r, v); });
-            flush_acc(tq, TcBwd::P_b1t, 16, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.base_w1 + c * 64 + r, v); });
+            flush_acc(tq, TcBwd::P_h2t, K, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) { if (v != 0.f) red_add(dp.head_w2 + c * 64 + r, v); });
+            flush_acc(tq, TcBwd::P_h1, 65, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) {
+                if (v != 0.f) red_add(c < 64 ? dp.head_w1 + r * 64 + c : dp.head_b1 + r, v); });
+            flush_acc(tq, TcBwd::P_h0, 28, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) {
+                if (v != 0.f) red_add(c < 27 ? dp.head_w0 + r * 27 + c : dp.head_b0 + r, v); });
+            flush_acc(tq, TcBwd::P_b1t, 16, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) { if (v != 0.f) red_add(dp.base_w1 + c * 64 + r, v); });
             if (spec)
-                flush_acc(tq, TcBwd::P_d0, 29, lane, [&](int c, float v) {
-                    if (r < 16 && v != 0.f) atomicAdd(c < 28 ? dp.dir_w0 + r * 28 + c : dp.dir_b0 + r, v); });
+                flush_acc(tq, TcBwd::P_d0, 29, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) {
+                    if (r < 16 && v != 0.f) red_add(c < 28 ? dp.dir_w0 + r * 28 + c : dp.dir_b0 + r, v); });
         } else {
-            flush_acc(tq, TcBwd::P_f2t, K + spec, lane, [&](int c, float v) { if (v != 0.f) atomicAdd(dp.feat_w2 + c * 64 + r, v); });
-            flush_acc(tq, TcBwd::P_f1, 65, lane, [&](int c, float v) {
-                if (v != 0.f) atomicAdd(c < 64 ? dp.feat_w1 + r * 64 + c : dp.feat_b1 + r, v); });
-            flush_acc(tq, TcBwd::P_f0, 28, lane, [&](int c, float v) {
-                if (v != 0.f) atomicAdd(c < 27 ? dp.feat_w0 + r * 27 + c : dp.feat_b0 + r, v); });
-            flush_acc(tq, TcBwd::P_b0, 33, lane, [&](int c, float v) {
-                if (v != 0.f) atomicAdd(c < 32 ? dp.base_w0 + r * 32 + c : dp.base_b0 + r, v); });
+            flush_acc(tq, TcBwd::P_f2t, K + spec, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) { if (v != 0.f) red_add(dp.feat_w2 + c * 64 + r, v); });
+            flush_acc(tq, TcBwd::P_f1, 65, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) {
+                if (v != 0.f) red_add(c < 64 ? dp.feat_w1 + r * 64 + c : dp.feat_b1 + r, v); });
+            flush_acc(tq, TcBwd::P_f0, 28, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) {
+                if (v != 0.f) red_add(c < 27 ? dp.feat_w0 + r * 27 + c : dp.feat_b0 + r, v); });
+            flush_acc(tq, TcBwd::P_b0, 33, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) {
+                if (v != 0.f) red_add(c < 32 ? dp.base_w0 + r * 32 + c : dp.base_b0 + r, v); });
         }
     }
     if (tid < 64) {
@@ -1195,7 +1320,7 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         if (tid < 16) dst = (tid < K) ? dp.head_b2 + tid : nullptr;
         else if (tid < 48) dst = (tid - 16 < K + spec) ? dp.feat_b2 + (tid - 16) : nullptr;
         else dst = dp.base_b1 + (tid - 48);
-        if (dst != nullptr && a != 0.f) atomicAdd(dst, a);
+        if (dst != nullptr && a != 0.f) red_add(dst, a);
     }
     fence_before_sync();
     __syncthreads();
@@ -1217,7 +1342,7 @@ tc05_selftest_kernel(int mode, const float *__restrict__ A, const float *__restr
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc<128>(slot);
-    const int acols = (mode == 2) ? 64 : K;
+    const int acols = (mode >= 2) ? 64 : K;
     for (int c = 0; c < acols; c += 8) {
         float v[8];
 #pragma unroll
@@ -1258,7 +1383,8 @@ tc05_selftest_kernel(int mode, const float *__restrict__ A, const float *__restr
             const uint32_t b16 = desc_base16(smem_u32(smem));
             if (mode == 0) gemm_kmajor(tbase, b16, 0u, 32768u, N, 0, N, K, 0);
             else if (mode == 1) gemm_dgrad(tbase, b16, 0u, 32768u, K, 0, N, K, 0);
-            else gemm_wgrad(tbase, b16, 0u, 0, 32768u, 0, N, 0);
+            else if (mode == 2) gemm_wgrad(tbase, b16, 0u, 0, 32768u, 0, N, 0);
+            else gemm_wgrad(tbase + (16u << 16), b16, 0u, 0, 32768u, 0, N, 0);  // mode 3: D at TMEM lanes 16..31 of each quarter
             commit(bar);
         }
         __syncwarp();
@@ -1272,6 +1398,9 @@ tc05_selftest_kernel(int mode, const float *__restrict__ A, const float *__restr
         if (mode == 2) {
             if (lane < 16)
                 for (int i = 0; i < 16; ++i) D[(warp * 16 + lane) * N + c + i] = v[i];
+        } else if (mode == 3) {
+            if (lane >= 16)
+                for (int i = 0; i < 16; ++i) D[(warp * 16 + lane - 16) * N + c + i] = v[i];
         } else {
             for (int i = 0; i < 16; ++i) D[tid * N + c + i] = v[i];
         }
@@ -1351,7 +1480,7 @@ extern "C" int umhs_debug_trace(int64_t *buffer, int32_t capacity_slots, void *s
 extern "C" int umhs_tc05_selftest(int32_t mode, const float *A, const float *B, float *D, int32_t N, int32_t K,
                                   void *stream) {
     UMHS_CHECK_ARG(A && B && D, "null argument");
-    UMHS_CHECK_ARG(mode >= 0 && mode <= 2 && N >= 16 && N <= 128 && N % 16 == 0 && K >= 16 && K <= 128 && K % 16 == 0,
+    UMHS_CHECK_ARG(mode >= 0 && mode <= 3 && N >= 16 && N <= 128 && N % 16 == 0 && K >= 16 && K <= 128 && K % 16 == 0,
                    "bad shape");
     const int bytes = 65536 + 128;
     UMHS_CHECK_CUDA(cudaFuncSetAttribute(tc05_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -1414,11 +1543,38 @@ extern "C" int umhs_field_mlp_tc_bwd(const umhs_points *pts, int64_t n, const fl
                        dp->feat_w1 && dp->feat_b1 && dp->feat_w2 && dp->feat_b2,
                    "null parameter-gradient pointer");
     UMHS_CHECK_ARG(!p->specular || (p->dir_w0 && p->dir_b0 && dp->dir_w0 && dp->dir_b0), "specular pointers missing");
-    auto kernel = p->num_classes <= 4 ? field_mlp_tc_bwd_kernel<4>
-                : p->num_classes <= 8 ? field_mlp_tc_bwd_kernel<8> : field_mlp_tc_bwd_kernel<16>;
+    auto kernel = p->num_classes <= 4 ? field_mlp_tc_bwd_kernel<4, false>
+                : p->num_classes <= 8 ? field_mlp_tc_bwd_kernel<8, false> : field_mlp_tc_bwd_kernel<16, false>;
     UMHS_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcBwd::smem_bytes));
     kernel<<<tc_grid(n, TcBwd::G), TcBwd::kThreads, TcBwd::smem_bytes, as_stream(stream)>>>(*pts, n, enc, *p, *g, d_enc,
-                                                                                          *dp);
+                                                                                          *dp, ScatterArgs{});
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_field_mlp_tc_bwd_scatter(const umhs_points *pts, int64_t n, const float *enc,
+                                             const umhs_mlp_params *p, const umhs_field_out_grads *g, void *d_enc_tiles,
+                                             const umhs_mlp_grads *dp, const umhs_hash_grid *grid, float *d_table,
+                                             void *stream) {
+    if (n <= 0) return UMHS_OK;
+    UMHS_CHECK_ARG(pts && enc && g && dp && p && grid && d_table && d_enc_tiles, "null argument");
+    UMHS_CHECK_ARG(p->enc_tiles == 1, "the fused scatter reads d_enc as the bf16 tile buffer (enc_tiles = 1)");
+    UMHS_CHECK_ARG(grid->scalings && grid->num_levels == 16 && grid->log2_table_size >= 1 && grid->log2_table_size <= 28,
+                   "bad hash grid (the tile layout is 16 levels x 2 features wide)");
+    UMHS_CHECK_ARG(p->num_classes >= 1 && p->num_classes <= UMHS_MAX_CLASSES && p->temperature > 0.f, "bad K / T");
+    UMHS_CHECK_ARG(g->d_scalar && g->d_abund, "d_scalar/d_abund are required");
+    UMHS_CHECK_ARG(dp->base_w0 && dp->base_b0 && dp->base_w1 && dp->base_b1 && dp->head_w0 && dp->head_b0 &&
+                       dp->head_w1 && dp->head_b1 && dp->head_w2 && dp->head_b2 && dp->feat_w0 && dp->feat_b0 &&
+                       dp->feat_w1 && dp->feat_b1 && dp->feat_w2 && dp->feat_b2,
+                   "null parameter-gradient pointer");
+    UMHS_CHECK_ARG(!p->specular || (p->dir_w0 && p->dir_b0 && dp->dir_w0 && dp->dir_b0), "specular pointers missing");
+    auto kernel = p->num_classes <= 4 ? field_mlp_tc_bwd_kernel<4, true>
+                : p->num_classes <= 8 ? field_mlp_tc_bwd_kernel<8, true> : field_mlp_tc_bwd_kernel<16, true>;
+    UMHS_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcBwd::smem_bytes));
+    const ScatterArgs sc{grid->scalings, reinterpret_cast<float2 *>(d_table), grid->num_levels, grid->log2_table_size,
+                         grid->num_levels < 10 ? grid->num_levels : 10};
+    kernel<<<tc_grid(n, TcBwd::G), TcBwd::kThreadsScatter, TcBwd::smem_bytes, as_stream(stream)>>>(
+        *pts, n, enc, *p, *g, reinterpret_cast<float *>(d_enc_tiles), *dp, sc);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }

@@ -19,39 +19,9 @@
 // Algorithmic bytes per sample: fwd 8*L*8 gathered + 12 in + 8L out;
 // bwd 8L in + 8*L*8 read-modify-write.
 #include "common.cuh"
+#include "hash_scatter.cuh"
 
 namespace umhs {
-
-struct Corners {
-    uint32_t idx[8];
-    float w[8];
-};
-
-// Corner order follows the reference: f0=(c,c,c) f1=(c,f,c) f2=(f,f,c) f3=(f,c,c)
-//                                     f4=(c,c,f) f5=(c,f,f) f6=(f,f,f) f7=(f,c,f)
-// returns true when the x-neighbours of this sample form aligned row pairs (see the header): (f3,f0) (f2,f1) (f7,f4) (f6,f5)
-__device__ __forceinline__ bool level_setup(float x, float y, float z, float scale, uint32_t tmask, uint32_t base,
-                                            uint32_t (&idx)[8], float &ox, float &oy, float &oz) {
-    const float sx = x * scale, sy = y * scale, sz = z * scale;
-    const float flx = floorf(sx), fly = floorf(sy), flz = floorf(sz);
-    const uint32_t cx = (uint32_t)(int)ceilf(sx), cy = (uint32_t)(int)ceilf(sy), cz = (uint32_t)(int)ceilf(sz);
-    const uint32_t fx = (uint32_t)(int)flx, fy = (uint32_t)(int)fly, fz = (uint32_t)(int)flz;
-    ox = sx - flx;
-    oy = sy - fly;
-    oz = sz - flz;
-    // low log2(T) bits of the int64 product == low bits of the uint32-wrapped product
-    const uint32_t hcy = cy * 2654435761u, hfy = fy * 2654435761u;
-    const uint32_t hcz = cz * 805459861u, hfz = fz * 805459861u;
-    idx[0] = ((cx ^ hcy ^ hcz) & tmask) + base;
-    idx[1] = ((cx ^ hfy ^ hcz) & tmask) + base;
-    idx[2] = ((fx ^ hfy ^ hcz) & tmask) + base;
-    idx[3] = ((fx ^ hcy ^ hcz) & tmask) + base;
-    idx[4] = ((cx ^ hcy ^ hfz) & tmask) + base;
-    idx[5] = ((cx ^ hfy ^ hfz) & tmask) + base;
-    idx[6] = ((fx ^ hfy ^ hfz) & tmask) + base;
-    idx[7] = ((fx ^ hcy ^ hfz) & tmask) + base;
-    return ((fx & 1u) == 0u) && (cx != fx);
-}
 
 // the 8 corner rows of one level: 4 aligned row pairs when `pair`, 8 single rows otherwise
 __device__ __forceinline__ void gather_level(const float2 *__restrict__ table, const uint32_t (&idx)[8], bool pair,
@@ -177,34 +147,6 @@ hash_encode_fwd_kernel(Src src, int64_t n_total, const float2 *__restrict__ tabl
     }
 }
 
-// One float2 reduction into the table.  Lanes of a warp hold consecutive samples of a ray, so at
-// coarse levels runs of adjacent lanes hit the same entry: a segmented warp scan sums each run and
-// only its last lane issues the red.global.add.v2.f32 (warp-aggregated atomics).
-template <bool AGGREGATE>
-__device__ __forceinline__ void scatter_add(float2 *table, uint32_t idx, float2 v, int lane) {
-    if (AGGREGATE) {
-        const uint32_t prev = __shfl_up_sync(kFull, idx, 1);
-        const bool head = (lane == 0) || (prev != idx);
-        const unsigned heads = __ballot_sync(kFull, head);
-        // start lane of my run = highest head bit at or below my lane
-        const unsigned below = heads & (0xffffffffu >> (31 - lane));
-        const int start = 31 - __clz(below);
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const float tx = __shfl_up_sync(kFull, v.x, o);
-            const float ty = __shfl_up_sync(kFull, v.y, o);
-            if (lane - o >= start) {
-                v.x += tx;
-                v.y += ty;
-            }
-        }
-        const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
-        if (tail && (v.x != 0.0f || v.y != 0.0f)) atomicAdd(table + idx, v);
-    } else {
-        if (v.x != 0.0f || v.y != 0.0f) atomicAdd(table + idx, v);
-    }
-}
-
 // Scatter kernel: 128-thread CTAs, grid-stride over the samples.
 // Measured and dropped (round 1): scattering chunk i of the samples on a second stream, on a grid capped to 3 CTAs per
 // SM so that it fits beside the persistent tensor-core MLP backward of chunk i+1.  The scatter needs its occupancy
@@ -218,7 +160,6 @@ hash_encode_bwd_kernel(Src src, int64_t n_total, const float *__restrict__ scali
                        const float *__restrict__ d_enc, float2 *__restrict__ d_table, int agg_levels) {
     const int lane = threadIdx.x & 31;
     const int64_t n_eff = src.count(n_total);
-    const uint32_t tmask = (log2T >= 32) ? 0xffffffffu : ((1u << log2T) - 1u);
     // CTA-uniform trip count: the warp-aggregated levels shuffle across the whole warp
     for (int64_t base = (int64_t)blockIdx.x * kScatterThreads; base < n_eff; base += (int64_t)gridDim.x * kScatterThreads) {
         const int64_t n = base + threadIdx.x;
@@ -227,51 +168,11 @@ hash_encode_bwd_kernel(Src src, int64_t n_total, const float *__restrict__ scali
         if (valid) src.get(n, x, y, z);
         const float *g = d_enc + (valid ? n : 0) * (2 * L);
         const uint8_t *gt = reinterpret_cast<const uint8_t *>(d_enc);  // TILES: bf16 tile buffer
-        for (int l = 0; l < L; ++l) {
-            uint32_t idx[8];
-            float ox, oy, oz;
-            const bool pair = level_setup(x, y, z, __ldg(scalings + l), tmask, (uint32_t)l << log2T, idx, ox, oy, oz);
-            float2 d = make_float2(0.f, 0.f);
-            if (valid) {
-                if (TILES) {  // columns 2 l, 2 l + 1: one bf16 pair inside the row's 16-byte piece l / 4
-                    const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(gt + enc_tile_piece(n, l >> 2)) + (l & 3));
-                    d = make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
-                } else {
-                    d = __ldg(reinterpret_cast<const float2 *>(g + 2 * l));
-                }
-            }
-            const float ux = 1.0f - ox, uy = 1.0f - oy, uz = 1.0f - oz;
-            // weight of corner (X,Y,Z): (X==c ? o : 1-o) per axis; cz side carries oz
-            const float wz[2] = {oz, uz};
-            const float wxy[4] = {ox * oy, ox * uy, ux * uy, ux * oy};  // (c,c) (c,f) (f,f) (f,c)
-            if (l < agg_levels) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float w = wxy[c & 3] * wz[c >> 2];
-                    scatter_add<true>(d_table, idx[c], make_float2(w * d.x, w * d.y), lane);
-                }
-            } else if (PAIRS && valid && pair) {
-                // fine levels: no two lanes share an entry; aligned x-pairs go out as one 16-byte reduction
-                constexpr int kFloor[4] = {3, 2, 7, 6}, kCeil[4] = {0, 1, 4, 5};
-                float4 *t4 = reinterpret_cast<float4 *>(d_table);
-#pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    const int cf = kFloor[p], cc = kCeil[p];
-                    const float wf = wxy[cf & 3] * wz[cf >> 2], wc = wxy[cc & 3] * wz[cc >> 2];
-                    const uint32_t fi = idx[cf];
-                    const bool odd = (fi & 1u) != 0u;
-                    const float wa = odd ? wc : wf, wb = odd ? wf : wc;  // first / second row of the pair
-                    const float4 v = make_float4(wa * d.x, wa * d.y, wb * d.x, wb * d.y);
-                    if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f) atomicAdd(t4 + (fi >> 1), v);
-                }
-            } else if (valid) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float w = wxy[c & 3] * wz[c >> 2];
-                    scatter_add<false>(d_table, idx[c], make_float2(w * d.x, w * d.y), lane);
-                }
-            }
-        }
+        scatter_sample<PAIRS>(x, y, z, valid, [&](int l) -> float2 {
+            if (TILES)  // one bf16 pair inside the row's 16-byte piece l / 4
+                return unpack_tile_pair(__ldg(reinterpret_cast<const uint32_t *>(gt + enc_tile_piece(n, l >> 2)) + (l & 3)));
+            return __ldg(reinterpret_cast<const float2 *>(g + 2 * l));
+        }, scalings, L, log2T, d_table, agg_levels, lane);
     }
 }
 

@@ -111,6 +111,8 @@ _SIGNATURES = {
     "umhs_field_mlp_tc_fwd": [POINTER(Points), c_int64, P, POINTER(MlpParams), POINTER(FieldOut), P],
     "umhs_field_mlp_tc_bwd": [POINTER(Points), c_int64, P, POINTER(MlpParams), POINTER(FieldOutGrads), P,
                               POINTER(MlpGrads), P],
+    "umhs_field_mlp_tc_bwd_scatter": [POINTER(Points), c_int64, P, POINTER(MlpParams), POINTER(FieldOutGrads), P,
+                                      POINTER(MlpGrads), POINTER(HashGrid), P, P],
     "umhs_debug_trace": [P, c_int32, P],
     "umhs_tc05_selftest": [c_int32, P, P, P, c_int32, c_int32, P],
     "umhs_tc05_microbench": [c_int32, c_int32, c_int32, c_int32, P, P],

@@ -6,6 +6,7 @@ current CUDA stream.  torch is used for device memory, streams and autograd plum
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -26,7 +27,7 @@ _LAUNCHES = {"umhs_hash_encode_fwd": 1, "umhs_hash_encode_bwd": 1, "umhs_hash_en
              "umhs_accumulate_fwd": 1, "umhs_accumulate_bwd": 1, "umhs_march_count": 1, "umhs_march_level_any": 1, "umhs_occ_pack_bits": 1, "umhs_pack_scan": 1,
              "umhs_march_write": 1, "umhs_visibility_mask": 1, "umhs_compact_samples": 1, "umhs_pack_info": 2,
              "umhs_occ_cell_points": 1, "umhs_occ_select_cells": 2, "umhs_occ_ema_update": 2, "umhs_occ_binarize": 2, "umhs_adam_step": 1,
-             "umhs_reduce_slabs": 1, "umhs_train_loss": 1, "umhs_dp_barrier": 1, "umhs_dp_adam_step": 1, "umhs_adam_step_dev": 1, "umhs_density_tc_fwd": 1, "umhs_field_mlp_tc_fwd": 1, "umhs_field_mlp_tc_bwd": 1, "umhs_debug_trace": 1,
+             "umhs_reduce_slabs": 1, "umhs_train_loss": 1, "umhs_dp_barrier": 1, "umhs_dp_adam_step": 1, "umhs_adam_step_dev": 1, "umhs_density_tc_fwd": 1, "umhs_field_mlp_tc_fwd": 1, "umhs_field_mlp_tc_bwd": 1, "umhs_field_mlp_tc_bwd_scatter": 1, "umhs_debug_trace": 1,
              "umhs_tc05_selftest": 1, "umhs_sample_batch": 1}
 
 # "bf16": tensor-core MLP kernels (tcgen05 + TMEM, bf16 operands, fp32 accumulate) -- the default.
@@ -41,6 +42,11 @@ SPECULAR_TC = True
 # fp32 rows -- half the bytes on five passes and no conversion / transposition in the MLP kernels.  Bit-identical
 # forward (the tensor-core kernels round the encodings to bf16 on load anyway); fp32 mode always uses fp32 rows.
 ENC_TILES = True
+# opt-in (UMHS_FUSED_SCATTER=1): the hash-grid scatter runs on 7 extra warps of the tensor-core MLP backward (one kernel
+# instead of two back to back).  Measured and NOT the default: 0.66 ms against 0.63 ms for the two kernels at 819 k
+# samples -- the reductions of the scatter warps and the shared-memory stores of the MLP epilogues share the SM's
+# load/store path, and the MLP's chain of dependent rounds pays for every queued reduction.
+FUSED_SCATTER = os.environ.get("UMHS_FUSED_SCATTER", "0") == "1"
 
 
 def _tiles_on() -> bool:
@@ -287,8 +293,10 @@ def field_mlp_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int
 
 def field_mlp_bwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int, specular: bool, temperature: float,
                   grads: Dict[str, Optional[Tensor]], d_weights: Optional[Dict[str, Tensor]] = None,
-                  want_d_enc: bool = True) -> Tuple[Optional[Tensor], Dict[str, Tensor]]:
-    """-> (d_enc [n,32] or None, parameter grads).  Parameter grads are accumulated into d_weights if given."""
+                  want_d_enc: bool = True, scatter: Optional[tuple] = None) -> Tuple[Optional[Tensor], Dict[str, Tensor]]:
+    """-> (d_enc [n,32] or None, parameter grads).  Parameter grads are accumulated into d_weights if given.
+    scatter = (table, scalings, log2_T, d_table): the hash-grid scatter of d_enc into d_table (accumulating) runs inside
+    the same kernel (tensor-core path with tile buffers only: umhs_field_mlp_tc_bwd_scatter)."""
     lib = _lib.load()
     dev, n = enc.device, pts.n
     if d_weights is None:
@@ -305,6 +313,14 @@ def field_mlp_bwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int
     for name in MLP_NAMES:
         setattr(dp, name, ptr(d_weights.get(name)))
     ps, ms = pts.struct(), mlp_struct(weights, K, specular, temperature, tiles)
+    if scatter is not None:
+        if not (tiles and want_d_enc and MLP_PRECISION == "bf16"):
+            raise RuntimeError("the fused scatter needs the tensor-core path with tile buffers")
+        table, scalings, log2_T, d_table = scatter
+        gs = _grid_struct(table, scalings, log2_T)
+        _call("umhs_field_mlp_tc_bwd_scatter", pts.units(), ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms),
+              ctypes.byref(g), ptr(d_enc), ctypes.byref(dp), ctypes.byref(gs), ptr(d_table), stream_ptr(dev))
+        return d_enc, d_weights
     _call("umhs_field_mlp_tc_bwd" if MLP_PRECISION == "bf16" else "umhs_field_mlp_bwd", pts.units(), ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(g), ptr(d_enc),
                                  ctypes.byref(dp), stream_ptr(dev))
     return d_enc, d_weights
@@ -357,11 +373,18 @@ class FieldFunction(torch.autograd.Function):
                   for n, w in weights.items() if w is not None}
         if BEFORE_MLP_BACKWARD is not None:
             BEFORE_MLP_BACKWARD()  # trainer hook: fork work that should run beside the MLP backward as well
-        d_enc, d_w = field_mlp_bwd(pts, enc, weights, K, cfg["specular"], cfg["temperature"], grads, d_w_in)
-        if AFTER_MLP_BACKWARD is not None:
-            AFTER_MLP_BACKWARD()  # trainer hook: fork work that should run beside the hash scatter and the optimiser
         t_sink = _sink(p_table)
-        d_table = hash_encode_bwd(pts, table, scalings, cfg["log2_T"], d_enc, t_sink)
+        if FUSED_SCATTER and is_tile_buffer(enc) and MLP_PRECISION == "bf16":
+            d_table = t_sink if t_sink is not None else torch.zeros_like(table, dtype=torch.float32)
+            d_enc, d_w = field_mlp_bwd(pts, enc, weights, K, cfg["specular"], cfg["temperature"], grads, d_w_in,
+                                       scatter=(table, scalings, cfg["log2_T"], d_table))
+            if AFTER_MLP_BACKWARD is not None:
+                AFTER_MLP_BACKWARD()
+        else:
+            d_enc, d_w = field_mlp_bwd(pts, enc, weights, K, cfg["specular"], cfg["temperature"], grads, d_w_in)
+            if AFTER_MLP_BACKWARD is not None:
+                AFTER_MLP_BACKWARD()  # trainer hook: fork work that should run beside the hash scatter and the optimiser
+            d_table = hash_encode_bwd(pts, table, scalings, cfg["log2_T"], d_enc, t_sink)
         return (None, None, None if t_sink is not None else d_table, None,
                 *[(d_w.get(n) if (p and sinks[n] is None) else None) for n, p in zip(MLP_NAMES, ctx.mlp_present)])
 
@@ -817,6 +840,6 @@ def dp_adam_step(peer_grads: List[int], peer_params: List[int], exp_avg: Tensor,
 
 def tc05_selftest(mode: int, A: Tensor, B: Tensor, N: int, K: int) -> Tensor:
     """One-CTA tcgen05 GEMM self-test (see include/umhs.h)."""
-    D = torch.zeros((64 if mode == 2 else 128, N), dtype=torch.float32, device=A.device)
+    D = torch.zeros((64 if mode >= 2 else 128, N), dtype=torch.float32, device=A.device)
     _call("umhs_tc05_selftest", 0, mode, ptr(f32(A)), ptr(f32(B)), ptr(D), N, K, stream_ptr(A.device))
     return D
