@@ -543,10 +543,12 @@ def dp_check(D, R=4096, steps=2, lr=1e-3):
     tb, loss_b = run(world, False)    # NCCL all-reduce + single-GPU Adam
     tc, loss_c = run(1, False)        # one GPU, concatenated batch
     n = ta.flat.numel
-    lo, hi = ta.dp_shard()            # this rank's shard of the optimiser state in the fused path
+    own = torch.zeros(n, dtype=torch.bool, device=ta.flat.data.device)
+    for lo, hi in ta.dp_shards():     # this rank's shards of the optimiser state in the fused path
+        own[lo:hi] = True
     pa, pb, pc = ta.flat.data, tb.flat.data, tc.flat.data
     d_ab, d_ac = (pa - pb).abs(), (pa - pc).abs()
-    m_a, m_b, m_c = ta.flat.exp_avg[lo:hi], tb.flat.exp_avg[lo:hi], tc.flat.exp_avg[lo:hi]
+    m_a, m_b, m_c = ta.flat.exp_avg[own], tb.flat.exp_avg[own], tc.flat.exp_avg[own]
     scale = float(m_c.abs().max()) + 1e-30
     res = {"steps": steps, "rays_per_rank": R, "lr": lr,
            "fused_vs_allreduce": {"max_abs_diff": float(d_ab.max()), "mean_abs_diff": float(d_ab.mean()),

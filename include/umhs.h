@@ -90,6 +90,11 @@ int umhs_hash_encode_fwd_tiles(const umhs_points *pts, int64_t n, const umhs_has
                                void *stream);
 int umhs_hash_encode_bwd_tiles(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid, const void *d_enc_tiles,
                                float *d_table, void *stream);
+/* ... levels [level_begin, level_end) only: the table gradient of the other levels is untouched.  The data-parallel
+ * trainer scatters the fine half first and exchanges it over NVLink while the coarse half is being scattered. */
+int umhs_hash_encode_bwd_tiles_levels(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid,
+                                      const void *d_enc_tiles, float *d_table, int32_t level_begin, int32_t level_end,
+                                      void *stream);
 int umhs_hash_encode_bwd(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid, const float *d_enc,
                          float *d_table, void *stream);
 /* Same two ops on already-normalised coordinates x01 [n,3] in [0,1] (the HashEncoding module boundary). */
@@ -468,6 +473,13 @@ int umhs_dp_barrier(uint32_t *const *signal_pads, int32_t rank, int32_t world, i
 int umhs_dp_adam_step(const float *const *peer_grads, float *const *peer_params, float *exp_avg, float *exp_avg_sq,
                       int64_t n, int32_t rank, int32_t world, float beta1, float beta2, float eps, const float *hyper,
                       int64_t clamp_begin, int64_t clamp_end, const float *mc_grad, float *mc_param, void *stream);
+/* The same step on the elements [range_begin, range_end) of the flat buffers only (multiples of 4; rank r then owns
+ * the r-th of `world` equal parts OF THE RANGE): a trainer can exchange a slice whose gradients are already complete
+ * while the backward still produces the rest.  Each slice needs its own pair of barrier channels. */
+int umhs_dp_adam_step_range(const float *const *peer_grads, float *const *peer_params, float *exp_avg,
+                            float *exp_avg_sq, int64_t n, int64_t range_begin, int64_t range_end, int32_t rank,
+                            int32_t world, float beta1, float beta2, float eps, const float *hyper,
+                            int64_t clamp_begin, int64_t clamp_end, const float *mc_grad, float *mc_param, void *stream);
 /* out[i] += sum_s slabs[s*stride + i] */
 int umhs_reduce_slabs(const float *slabs, int64_t n_slabs, int64_t stride, int64_t n, float *out, void *stream);
 

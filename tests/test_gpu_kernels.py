@@ -625,6 +625,36 @@ def _rows_to_tile(rows):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n,split", [(1, 8), (1000, 8), (70001, 3), (70001, 12)])
+def test_scatter_by_level_range(n, split):
+    """umhs_hash_encode_bwd_tiles_levels: scattering levels [split, 16) and then [0, split) equals the one-pass scatter
+    (what the data-parallel trainer does to start the exchange of the fine levels early), and a range leaves the other
+    levels' rows untouched."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(n + split)
+    log2_T, L = 12, 16
+    table = torch.zeros(L << log2_T, 2, device=DEV)
+    scal = torch.floor(16 * torch.exp(torch.arange(L) * (np.log(2048 / 16) / (L - 1)))).float().to(DEV)
+    pos = (torch.rand(n, 3, generator=g) * 2.4 - 1.2).to(DEV)
+    pts = ops.PointSet.from_positions(pos)
+    rows = torch.randn(n, 32, generator=g).to(DEV).to(torch.bfloat16)
+    tiles = torch.zeros(((n + 127) // 128 * 128, 32), dtype=torch.bfloat16, device=DEV)
+    idx = torch.arange(n, device=DEV)
+    # element (n, c) of the tile layout (csrc/common.cuh: enc_tile_piece), in bf16 elements
+    for c in range(32):
+        off = (idx >> 7) * 4096 + (c >> 3) * 1024 + ((idx & 127) >> 3) * 64 + (idx & 7) * 8 + (c & 7)
+        tiles.view(-1)[off] = rows[:, c]
+    whole = ops.hash_encode_bwd(pts, table, scal, log2_T, tiles)
+    fine = ops.hash_encode_bwd(pts, table, scal, log2_T, tiles, levels=(split, L))
+    T = 1 << log2_T
+    assert float(fine[:split * T].abs().max()) == 0.0
+    assert float(fine[split * T:].abs().max()) > 0.0
+    both = ops.hash_encode_bwd(pts, table, scal, log2_T, tiles, fine.clone(), levels=(0, split))
+    assert_close(both, whole, 1e-5, 1e-6 * float(whole.abs().max()) + 1e-12, "split scatter")
+    assert torch.equal(both[split * T:], fine[split * T:])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n,spec", [(1, False), (129, False), (40000, True), (300001, False)])
 def test_mlp_backward_with_scatter_on_board(n, spec):
     """umhs_field_mlp_tc_bwd_scatter (the opt-in single-kernel form: hash-grid scatter on extra warps of the tensor-core

@@ -157,7 +157,8 @@ constexpr int kScatterThreads = 128;
 template <class Src, bool PAIRS, bool TILES>
 __global__ void __launch_bounds__(kScatterThreads)
 hash_encode_bwd_kernel(Src src, int64_t n_total, const float *__restrict__ scalings, int L, int log2T,
-                       const float *__restrict__ d_enc, float2 *__restrict__ d_table, int agg_levels) {
+                       const float *__restrict__ d_enc, float2 *__restrict__ d_table, int agg_levels, int l_begin,
+                       int l_end) {
     const int lane = threadIdx.x & 31;
     const int64_t n_eff = src.count(n_total);
     // CTA-uniform trip count: the warp-aggregated levels shuffle across the whole warp
@@ -172,7 +173,7 @@ hash_encode_bwd_kernel(Src src, int64_t n_total, const float *__restrict__ scali
             if (TILES)  // one bf16 pair inside the row's 16-byte piece l / 4
                 return unpack_tile_pair(__ldg(reinterpret_cast<const uint32_t *>(gt + enc_tile_piece(n, l >> 2)) + (l & 3)));
             return __ldg(reinterpret_cast<const float2 *>(g + 2 * l));
-        }, scalings, L, log2T, d_table, agg_levels, lane);
+        }, scalings, l_begin, l_end, log2T, d_table, agg_levels, lane);
     }
 }
 
@@ -228,17 +229,26 @@ extern "C" int umhs_hash_encode_fwd_tiles(const umhs_points *pts, int64_t n, con
     return UMHS_OK;
 }
 
-extern "C" int umhs_hash_encode_bwd_tiles(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid,
-                                          const void *d_enc_tiles, float *d_table, void *stream) {
+extern "C" int umhs_hash_encode_bwd_tiles_levels(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid,
+                                                 const void *d_enc_tiles, float *d_table, int32_t level_begin,
+                                                 int32_t level_end, void *stream) {
     if (n <= 0) return UMHS_OK;
     UMHS_CHECK_ARG(pts != nullptr && d_enc_tiles != nullptr && d_table != nullptr, "null argument");
     UMHS_CHECK_ARG(check_grid(grid) == 0 && grid->num_levels == 16, "the tile layout is 16 levels x 2 features wide");
+    UMHS_CHECK_ARG(level_begin >= 0 && level_begin <= level_end && level_end <= grid->num_levels, "bad level range");
+    if (level_begin == level_end) return UMHS_OK;
     SrcPoints src{*pts};
     hash_encode_bwd_kernel<decltype(src), true, true><<<scatter_grid(n, 0), kScatterThreads, 0, as_stream(stream)>>>(
         src, n, grid->scalings, grid->num_levels, grid->log2_table_size, reinterpret_cast<const float *>(d_enc_tiles),
-        reinterpret_cast<float2 *>(d_table), agg_levels_for(grid));
+        reinterpret_cast<float2 *>(d_table), agg_levels_for(grid), level_begin, level_end);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
+}
+
+extern "C" int umhs_hash_encode_bwd_tiles(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid,
+                                          const void *d_enc_tiles, float *d_table, void *stream) {
+    UMHS_CHECK_ARG(grid != nullptr, "null argument");
+    return umhs_hash_encode_bwd_tiles_levels(pts, n, grid, d_enc_tiles, d_table, 0, grid->num_levels, stream);
 }
 
 extern "C" int umhs_hash_encode_bwd(const umhs_points *pts, int64_t n, const umhs_hash_grid *grid, const float *d_enc,
@@ -251,7 +261,7 @@ extern "C" int umhs_hash_encode_bwd(const umhs_points *pts, int64_t n, const umh
     const int max_ctas = 0;
     hash_encode_bwd_kernel<decltype(src), true, false><<<scatter_grid(n, max_ctas), kScatterThreads, 0, as_stream(stream)>>>(
         src, n, grid->scalings, grid->num_levels, grid->log2_table_size, d_enc, reinterpret_cast<float2 *>(d_table),
-        agg_levels_for(grid));
+        agg_levels_for(grid), 0, grid->num_levels);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }
@@ -280,7 +290,7 @@ extern "C" int umhs_hash_encode_x01_bwd(const float *x01, int64_t n, const umhs_
     const int max_ctas = 0;
     hash_encode_bwd_kernel<decltype(src), true, false><<<scatter_grid(n, max_ctas), kScatterThreads, 0, as_stream(stream)>>>(
         src, n, grid->scalings, grid->num_levels, grid->log2_table_size, d_enc, reinterpret_cast<float2 *>(d_table),
-        agg_levels_for(grid));
+        agg_levels_for(grid), 0, grid->num_levels);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }

@@ -83,14 +83,14 @@ __device__ __forceinline__ void scatter_add(float2 *table, uint32_t idx, float2 
     }
 }
 
-// All levels of one sample (one lane).  Every lane of the warp must call this (the coarse levels shuffle across the
+// Levels [l_begin, l_end) of one sample (one lane).  Every lane of the warp must call this (the coarse levels shuffle across the
 // warp); lanes without a sample pass valid = false.  load_d(l) returns the gradient of encoding columns 2 l, 2 l + 1.
 template <bool PAIRS, class LoadD>
 __device__ __forceinline__ void scatter_sample(float x, float y, float z, bool valid, LoadD &&load_d,
-                                               const float *__restrict__ scalings, int L, int log2T,
+                                               const float *__restrict__ scalings, int l_begin, int l_end, int log2T,
                                                float2 *__restrict__ d_table, int agg_levels, int lane) {
     const uint32_t tmask = (log2T >= 32) ? 0xffffffffu : ((1u << log2T) - 1u);
-    for (int l = 0; l < L; ++l) {
+    for (int l = l_begin; l < l_end; ++l) {
         uint32_t idx[8];
         float ox, oy, oz;
         const bool pair = level_setup(x, y, z, __ldg(scalings + l), tmask, (uint32_t)l << log2T, idx, ox, oy, oz);

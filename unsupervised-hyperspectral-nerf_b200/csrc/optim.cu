@@ -245,7 +245,18 @@ extern "C" int umhs_dp_adam_step(const float *const *peer_grads, float *const *p
                                  float *exp_avg_sq, int64_t n, int32_t rank, int32_t world, float beta1, float beta2,
                                  float eps, const float *hyper, int64_t clamp_begin, int64_t clamp_end,
                                  const float *mc_grad, float *mc_param, void *stream) {
+    return umhs_dp_adam_step_range(peer_grads, peer_params, exp_avg, exp_avg_sq, n, 0, n, rank, world, beta1, beta2, eps,
+                                   hyper, clamp_begin, clamp_end, mc_grad, mc_param, stream);
+}
+
+extern "C" int umhs_dp_adam_step_range(const float *const *peer_grads, float *const *peer_params, float *exp_avg,
+                                       float *exp_avg_sq, int64_t n, int64_t range_begin, int64_t range_end,
+                                       int32_t rank, int32_t world, float beta1, float beta2, float eps,
+                                       const float *hyper, int64_t clamp_begin, int64_t clamp_end, const float *mc_grad,
+                                       float *mc_param, void *stream) {
     UMHS_CHECK_ARG(peer_grads && peer_params && exp_avg && exp_avg_sq && hyper, "null argument");
+    UMHS_CHECK_ARG(range_begin >= 0 && range_begin <= range_end && range_end <= n && range_begin % 4 == 0 &&
+                       range_end % 4 == 0, "the range must be inside the buffer, on multiples of 4");
     UMHS_CHECK_ARG(((uintptr_t)mc_grad | (uintptr_t)mc_param) % 16 == 0, "multicast addresses must be 16-byte aligned");
     UMHS_CHECK_ARG(world >= 1 && world <= UMHS_MAX_RANKS && rank >= 0 && rank < world, "bad rank / world");
     UMHS_CHECK_ARG(n % 4 == 0, "the flat buffer length must be a multiple of 4");
@@ -257,9 +268,11 @@ extern "C" int umhs_dp_adam_step(const float *const *peer_grads, float *const *p
         UMHS_CHECK_ARG(w >= world || (a.peer_grad[w] && a.peer_param[w] && ((uintptr_t)a.peer_grad[w] % 16 == 0) &&
                                       ((uintptr_t)a.peer_param[w] % 16 == 0)), "bad peer pointer");
     }
-    const int64_t n4 = n / 4, per = (n4 + world - 1) / world;
-    a.begin = 4 * (per * rank < n4 ? per * rank : n4);
-    a.end = 4 * (per * (rank + 1) < n4 ? per * (rank + 1) : n4);
+    // this rank's shard of the range: ceil(range / 4 / world) float4 groups
+    const int64_t n4 = (range_end - range_begin) / 4, per = (n4 + world - 1) / world;
+    a.begin = range_begin + 4 * (per * rank < n4 ? per * rank : n4);
+    a.end = range_begin + 4 * (per * (rank + 1) < n4 ? per * (rank + 1) : n4);
+    if (a.begin == a.end) return UMHS_OK;
     a.m = exp_avg; a.v = exp_avg_sq; a.world = world; a.rank = rank;
     a.mc_grad = mc_grad; a.mc_param = mc_param;
     a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.inv_world = 1.0f / (float)world; a.hyper = hyper;

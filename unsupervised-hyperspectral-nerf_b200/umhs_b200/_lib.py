@@ -101,6 +101,7 @@ _SIGNATURES = {
     "umhs_hash_encode_bwd": [POINTER(Points), c_int64, POINTER(HashGrid), P, P, P],
     "umhs_hash_encode_fwd_tiles": [POINTER(Points), c_int64, POINTER(HashGrid), P, P],
     "umhs_hash_encode_bwd_tiles": [POINTER(Points), c_int64, POINTER(HashGrid), P, P, P],
+    "umhs_hash_encode_bwd_tiles_levels": [POINTER(Points), c_int64, POINTER(HashGrid), P, P, c_int32, c_int32, P],
     "umhs_hash_encode_x01_fwd": [P, c_int64, POINTER(HashGrid), P, P],
     "umhs_hash_encode_x01_bwd": [P, c_int64, POINTER(HashGrid), P, P, P],
     "umhs_density_fwd": [POINTER(Points), c_int64, P, POINTER(MlpParams), P, P],
@@ -149,6 +150,8 @@ _SIGNATURES = {
     "umhs_train_loss": [c_int64, c_int32, c_int32, P, P, P, P, P, P, c_int32, c_float, c_float, P, P, P, P, P],
     "umhs_dp_barrier": [P, c_int32, c_int32, c_int32, P, P],
     "umhs_dp_adam_step": [P, P, P, P, c_int64, c_int32, c_int32, c_float, c_float, c_float, P, c_int64, c_int64, P, P,
+                          P],
+    "umhs_dp_adam_step_range": [P, P, P, P, c_int64, c_int64, c_int64, c_int32, c_int32, c_float, c_float, c_float, P, c_int64, c_int64, P, P,
                           P],
 }
 _RESTYPES = {"umhs_last_error": c_char_p}

@@ -20,7 +20,7 @@ ENC_DIM = 32  # 16 levels x 2 features
 
 # kernels launched per C-ABI entry point (for the bench's gpu_launches count)
 _LAUNCHES = {"umhs_hash_encode_fwd": 1, "umhs_hash_encode_bwd": 1, "umhs_hash_encode_fwd_tiles": 1,
-             "umhs_hash_encode_bwd_tiles": 1, "umhs_hash_encode_x01_fwd": 1,
+             "umhs_hash_encode_bwd_tiles": 1, "umhs_hash_encode_bwd_tiles_levels": 1, "umhs_hash_encode_x01_fwd": 1,
              "umhs_hash_encode_x01_bwd": 1, "umhs_density_fwd": 1, "umhs_field_mlp_fwd": 1, "umhs_field_mlp_bwd": 1,
              "umhs_composite_fwd": 1, "umhs_specular_tc_fwd": 1, "umhs_specular_tc_bwd": 1, "umhs_spectral_grad": 1, "umhs_depth_clip": 1, "umhs_depth_clip_chunks": 2, "umhs_composite_bwd": 1, "umhs_unmix_fwd": 1,
              "umhs_unmix_bwd": 1, "umhs_render_weights_fwd": 1, "umhs_render_weights_bwd": 1,
@@ -79,9 +79,10 @@ class Profiler:
         return out
 
 
-def _call(name: str, units: int, *args) -> None:
-    """Invoke a C-ABI entry point (kernels go to torch's current stream) and raise on error."""
-    fn = getattr(_lib.load(), name)
+def _call(name: str, units: int, *args, fn_name: Optional[str] = None) -> None:
+    """Invoke a C-ABI entry point (kernels go to torch's current stream) and raise on error.  fn_name: the symbol to
+    call when it differs from the name the launch is accounted under."""
+    fn = getattr(_lib.load(), fn_name or name)
     if Profiler.enabled:
         Profiler.launches += _LAUNCHES[name]
         if Profiler.timing:
@@ -94,6 +95,15 @@ def _call(name: str, units: int, *args) -> None:
             return
     check(fn(*args), name)
 
+
+# Data-parallel trainer, opt-in (UMHS_DP_SPLIT_LEVEL=8): scatter one half of the levels, call BETWEEN_SCATTER_HALVES()
+# (the trainer starts that half's gradient exchange on a side stream), then the other half.  Measured on 8 x B200:
+# 1.250 ms per step against 1.246 ms unsplit (2 GPUs: 1.227 / 1.229) -- what a step pays for data parallelism is the
+# two barriers (the skew between ranks) and 58.8 MB per GPU over NVLink, which the second scatter half is too short
+# and too busy (it shares the SMs with the exchange kernel) to hide.  0 = off.
+SCATTER_SPLIT_LEVEL = 0
+SCATTER_FINE_FIRST = os.environ.get("UMHS_DP_FINE_FIRST", "0") == "1"
+BETWEEN_SCATTER_HALVES = None
 
 # When True (set by UMHSTrainer), backward kernels accumulate straight into ``param.grad`` of leaf parameters
 # that already own a contiguous fp32 grad buffer (views of the trainer's flat gradient), and autograd gets None.
@@ -197,12 +207,19 @@ def hash_encode_fwd(pts: PointSet, table: Tensor, scalings: Tensor, log2_T: int,
 
 
 def hash_encode_bwd(pts: PointSet, table: Tensor, scalings: Tensor, log2_T: int, d_enc: Tensor,
-                    d_table: Optional[Tensor] = None) -> Tensor:
-    """Scatter d_enc into d_table (accumulating).  Allocates a zero table gradient when none is given."""
+                    d_table: Optional[Tensor] = None, levels: Optional[Tuple[int, int]] = None) -> Tensor:
+    """Scatter d_enc into d_table (accumulating).  Allocates a zero table gradient when none is given.
+    levels = (begin, end): those levels only (tile buffers)."""
     lib = _lib.load()
     if d_table is None:
         d_table = torch.zeros_like(table, dtype=torch.float32)
     ps, gs = pts.struct(), _grid_struct(table, scalings, log2_T)
+    if levels is not None:
+        if not is_tile_buffer(d_enc):
+            raise RuntimeError("a level range needs the bf16 tile buffer")
+        _call("umhs_hash_encode_bwd_tiles_levels", pts.units(), ctypes.byref(ps), pts.n, ctypes.byref(gs), ptr(d_enc),
+              ptr(d_table), int(levels[0]), int(levels[1]), stream_ptr(table.device))
+        return d_table
     name = "umhs_hash_encode_bwd_tiles" if is_tile_buffer(d_enc) else "umhs_hash_encode_bwd"
     _call(name, pts.units(), ctypes.byref(ps), pts.n, ctypes.byref(gs), ptr(d_enc), ptr(d_table),
           stream_ptr(table.device))
@@ -384,7 +401,18 @@ class FieldFunction(torch.autograd.Function):
             d_enc, d_w = field_mlp_bwd(pts, enc, weights, K, cfg["specular"], cfg["temperature"], grads, d_w_in)
             if AFTER_MLP_BACKWARD is not None:
                 AFTER_MLP_BACKWARD()  # trainer hook: fork work that should run beside the hash scatter and the optimiser
-            d_table = hash_encode_bwd(pts, table, scalings, cfg["log2_T"], d_enc, t_sink)
+            L = int(scalings.shape[0])
+            if BETWEEN_SCATTER_HALVES is not None and is_tile_buffer(d_enc) and 0 < SCATTER_SPLIT_LEVEL < L:
+                # one half of the levels first; the hook (data-parallel trainer) starts its gradient exchange on a side
+                # stream while the other half is being scattered
+                first, second = (0, SCATTER_SPLIT_LEVEL), (SCATTER_SPLIT_LEVEL, L)
+                if SCATTER_FINE_FIRST:
+                    first, second = second, first
+                d_table = hash_encode_bwd(pts, table, scalings, cfg["log2_T"], d_enc, t_sink, levels=first)
+                BETWEEN_SCATTER_HALVES()
+                hash_encode_bwd(pts, table, scalings, cfg["log2_T"], d_enc, d_table, levels=second)
+            else:
+                d_table = hash_encode_bwd(pts, table, scalings, cfg["log2_T"], d_enc, t_sink)
         return (None, None, None if t_sink is not None else d_table, None,
                 *[(d_w.get(n) if (p and sinks[n] is None) else None) for n, p in zip(MLP_NAMES, ctx.mlp_present)])
 
@@ -829,13 +857,17 @@ def dp_barrier(pads: Tensor, rank: int, world: int, channel: int, epochs: Tensor
 
 def dp_adam_step(peer_grads: List[int], peer_params: List[int], exp_avg: Tensor, exp_avg_sq: Tensor, n: int, rank: int,
                  world: int, beta1: float, beta2: float, eps: float, hyper: Tensor,
-                 clamp_range: Tuple[int, int] = (0, 0), mc_grad: int = 0, mc_param: int = 0) -> None:
+                 clamp_range: Tuple[int, int] = (0, 0), mc_grad: int = 0, mc_param: int = 0,
+                 span: Optional[Tuple[int, int]] = None) -> None:
     """Fused reduce-scatter + Adam + all-gather over NVLink peer memory (include/umhs.h: umhs_dp_adam_step).
-    mc_grad / mc_param: NVLS multicast addresses of the buffers (0: plain peer loads / stores)."""
+    mc_grad / mc_param: NVLS multicast addresses of the buffers (0: plain peer loads / stores).
+    span = (begin, end): that slice of the flat buffers only (umhs_dp_adam_step_range)."""
     pg = (ctypes.c_void_p * world)(*peer_grads)
     pp = (ctypes.c_void_p * world)(*peer_params)
-    _call("umhs_dp_adam_step", n // world, pg, pp, ptr(exp_avg), ptr(exp_avg_sq), n, rank, world, beta1, beta2, eps,
-          ptr(hyper), clamp_range[0], clamp_range[1], mc_grad or None, mc_param or None, stream_ptr(exp_avg.device))
+    lo, hi = (0, n) if span is None else span
+    _call("umhs_dp_adam_step", (hi - lo) // world, pg, pp, ptr(exp_avg), ptr(exp_avg_sq), n, lo, hi, rank, world, beta1,
+          beta2, eps, ptr(hyper), clamp_range[0], clamp_range[1], mc_grad or None, mc_param or None,
+          stream_ptr(exp_avg.device), fn_name="umhs_dp_adam_step_range")
 
 
 def tc05_selftest(mode: int, A: Tensor, B: Tensor, N: int, K: int) -> Tensor:

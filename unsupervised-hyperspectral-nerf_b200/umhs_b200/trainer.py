@@ -144,7 +144,17 @@ class UMHSTrainer:
         self.fused_dp = bool(fused_dp and world_size > 1 and params[0].is_cuda)
         self._peers = PeerMemory() if self.fused_dp else None
         self.flat = FlatParams(params, self._peers)
+        self._dp_cut, self._dp_side, self._dp_forked = 0, None, False
         if self.fused_dp:
+            # split exchange: levels >= dp_split_level of the hash table (and the parameters behind it) first
+            split = int(os.environ.get("UMHS_DP_SPLIT_LEVEL", ops.SCATTER_SPLIT_LEVEL))
+            table = model.field.mlp_base.encoder.hash_table
+            L = int(model.field.mlp_base.encoder.scalings.shape[0])
+            if 0 < split < L and ops.ENC_TILES and L == 16:
+                t_lo, t_hi = self.flat.range_of(table)
+                self._dp_cut = t_lo + (t_hi - t_lo) // L * split
+                assert self._dp_cut % 4 == 0
+                self.dp_split_level = split
             dev = params[0].device
             pad, pad_ptrs = self._peers.empty(256, torch.int32, dev)   # 8 channels x 8 ranks (+ slack) of uint32
             pad.zero_()
@@ -175,13 +185,26 @@ class UMHSTrainer:
         if world_size > 1:  # identical replicas
             dist.broadcast(self.flat.data, src=0)
 
-    def dp_shard(self, rank: Optional[int] = None):
-        """[begin, end) of the flat buffers whose Adam state rank ``rank`` owns in the fused data-parallel step
-        (csrc/optim.cu::umhs_dp_adam_step: ceil(n/4 / world) float4 groups per rank)."""
+    def dp_shard(self, rank: Optional[int] = None, span: Optional[tuple] = None):
+        """[begin, end) of the flat buffers (or of their slice ``span``) whose Adam state rank ``rank`` owns in the
+        fused data-parallel step (csrc/optim.cu::umhs_dp_adam_step_range: ceil(len/4 / world) float4 groups per rank)."""
         r = self.rank if rank is None else rank
-        n4 = self.flat.numel // 4
+        lo, hi = (0, self.flat.numel) if span is None else span
+        n4 = (hi - lo) // 4
         per = -(-n4 // self.world_size)
-        return 4 * min(per * r, n4), 4 * min(per * (r + 1), n4)
+        return lo + 4 * min(per * r, n4), lo + 4 * min(per * (r + 1), n4)
+
+    def dp_spans(self):
+        """The slices of the flat buffers that are exchanged separately: everything at once, or -- when the hash-grid
+        scatter is split (``dp_split_level``) -- [0, cut) and [cut, n) with cut = first element of that level's rows:
+        the fine levels (and the MLP weights behind the table) travel while the coarse levels are still being scattered."""
+        n = self.flat.numel
+        cut = getattr(self, "_dp_cut", 0)
+        return [(0, n)] if not cut else [(0, cut), (cut, n)]
+
+    def dp_shards(self, rank: Optional[int] = None):
+        """Every [begin, end) whose Adam state rank ``rank`` owns (one per span)."""
+        return [self.dp_shard(rank, sp) for sp in self.dp_spans()]
 
     def full_optimizer_state(self):
         """(exp_avg, exp_avg_sq) over ALL parameters.  In the fused data-parallel step every rank keeps the moments
@@ -193,8 +216,8 @@ class UMHSTrainer:
         out = []
         for buf in (f.exp_avg, f.exp_avg_sq):
             full = torch.zeros_like(buf)
-            lo, hi = self.dp_shard()
-            full[lo:hi] = buf[lo:hi]
+            for lo, hi in self.dp_shards():
+                full[lo:hi] = buf[lo:hi]
             dist.all_reduce(full, op=dist.ReduceOp.SUM)  # shards are disjoint: the sum is the concatenation
             out.append(full)
         return out[0], out[1]
@@ -282,6 +305,16 @@ class UMHSTrainer:
         self._hyper.copy_(row, non_blocking=True)
 
     def _forward_backward(self, ray_bundle: RayBundle, batch: Dict[str, Tensor], premarched=None):
+        if not (self.fused_dp and self._dp_cut):
+            return self._forward_backward_impl(ray_bundle, batch, premarched)
+        ops.BETWEEN_SCATTER_HALVES, keep = self._exchange_fine_levels, ops.SCATTER_SPLIT_LEVEL
+        ops.SCATTER_SPLIT_LEVEL = self.dp_split_level  # the level the spans of this trainer are cut at
+        try:
+            return self._forward_backward_impl(ray_bundle, batch, premarched)
+        finally:
+            ops.BETWEEN_SCATTER_HALVES, ops.SCATTER_SPLIT_LEVEL = None, keep
+
+    def _forward_backward_impl(self, ray_bundle: RayBundle, batch: Dict[str, Tensor], premarched=None):
         m = self.model
         outputs = m.get_outputs(m.collider(ray_bundle), per_band_views=False, premarched=premarched, lean=True)
         if self.fused_loss and outputs["spectral"].is_cuda:
@@ -322,15 +355,38 @@ class UMHSTrainer:
         loss_dict["num_samples"] = outputs["num_samples_per_ray"].sum()
         return loss_dict
 
+    def _dp_exchange(self, channel: int, span) -> None:
+        """barrier (the span's gradients are complete on every rank) + reduce-scatter / Adam / all-gather of the span"""
+        f = self.flat
+        ops.dp_barrier(self._dp_pads, self.rank, self.world_size, channel, self._dp_epochs)
+        ops.dp_adam_step(f.peer_grad, f.peer_data, f.exp_avg, f.exp_avg_sq, f.numel, self.rank, self.world_size,
+                         self.betas[0], self.betas[1], self.eps, self._hyper, clamp_range=self.clamp_range,
+                         mc_grad=f.mc_grad, mc_param=f.mc_data, span=span)
+
+    def _exchange_fine_levels(self) -> None:
+        """ops.BETWEEN_SCATTER_HALVES: the table gradient of the first half of the levels is complete -- exchange that
+        span on a side stream while the main stream scatters the other half."""
+        dev = self.flat.data.device
+        if self._dp_side is None:
+            self._dp_side = torch.cuda.Stream(device=dev)
+        self._dp_side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._dp_side):
+            self._dp_exchange(2, self.dp_spans()[1 if ops.SCATTER_FINE_FIRST else 0])
+        self._dp_forked = True
+
     def _optimizer(self) -> None:
         if self.fused_dp:
-            f = self.flat
-            ops.dp_barrier(self._dp_pads, self.rank, self.world_size, 0, self._dp_epochs)  # all gradients complete
-            ops.dp_adam_step(f.peer_grad, f.peer_data, f.exp_avg, f.exp_avg_sq, f.numel, self.rank, self.world_size,
-                             self.betas[0], self.betas[1], self.eps, self._hyper, clamp_range=self.clamp_range,
-                             mc_grad=f.mc_grad, mc_param=f.mc_data)
+            spans = self.dp_spans()
+            forked = len(spans) == 2 and self._dp_forked
+            early = 1 if ops.SCATTER_FINE_FIRST else 0
+            if len(spans) == 2 and not forked:  # no split backward ran (plain autograd path): in line
+                self._dp_exchange(2, spans[early])
+            self._dp_exchange(0, spans[-1] if len(spans) == 1 else spans[1 - early])
+            if forked:
+                torch.cuda.current_stream(self.flat.data.device).wait_stream(self._dp_side)
+                self._dp_forked = False
             ops.dp_barrier(self._dp_pads, self.rank, self.world_size, 1, self._dp_epochs)  # parameters landed
-            f.grad.zero_()
+            self.flat.grad.zero_()
             return
         ops.adam_step_dev(self.flat.data, self.flat.grad, self.flat.exp_avg, self.flat.exp_avg_sq, self.betas[0],
                           self.betas[1], self.eps, self._hyper,
