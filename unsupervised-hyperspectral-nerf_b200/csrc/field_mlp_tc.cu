@@ -27,9 +27,10 @@ using namespace tc05;
 
 constexpr int TM = 128;          // samples per tile == threads per group
 #ifndef UMHS_FWD_ISSUERS
-#define UMHS_FWD_ISSUERS 0   // MMA-issuing warps of the forward kernels: 1 = one, 2 = one per data group, 0 = what measured
-#endif                       // best at 825 k samples: density one per group (45.0 against 47.3 us), full forward one (120.8
-                             // against 124.9 us)
+#define UMHS_FWD_ISSUERS 1   // MMA-issuing warps of the forward kernels: 1 = one, 2 = one per data group.  Measured: the
+#endif                       // full forward 120.8 (one) against 124.9 us at 825 k samples; the density kernel 45.0 (one
+                             // per group) against 47.3 us alone at 825 k samples, but 0.0552 against 0.0525 ms per
+                             // training step (two calls: candidates + an occupancy chunk) -- one warp it is
 #ifndef UMHS_BWD_ISSUERS
 #define UMHS_BWD_ISSUERS 1   // ... of the backward kernel: 2 = one per data group (each group then owns a copy of the
 #endif                       // weight-gradient accumulators), 1 = one for both.  Measured equal (430 / 431 us): a round is
@@ -488,7 +489,7 @@ __device__ __forceinline__ void issuer_dispatch(int ii, uint64_t *bars, const in
 template <bool DENSITY_ONLY>
 struct TcFwdCfg {
     static constexpr int G = DENSITY_ONLY ? UMHS_DENSITY_G : 3;
-    static constexpr int I = UMHS_FWD_ISSUERS == 2 || (UMHS_FWD_ISSUERS == 0 && DENSITY_ONLY) ? G : 1;  // MMA-issuing warps
+    static constexpr int I = UMHS_FWD_ISSUERS == 2 ? G : 1;  // MMA-issuing warps
     static constexpr int kThreads = G * TM + 32 * I;
 };
 struct TcFwd {
