@@ -49,6 +49,10 @@ lib.umhs_debug_trace(None, 0, torch.cuda.current_stream().cuda_stream)
 t = buf.view(cap, 2, 2).cpu()
 ev = [(int(t[i, 0, 0]), int(t[i, 0, 1])) for i in range(cap) if int(t[i, 0, 1]) != 0]
 print("data thread events:", len(ev), "(the first tile is skipped)")
+if os.environ.get("RAW"):  # trace level 2 (-DUMHS_TRACE=2): extra stamps 200 + r (fence of round r done), 300 / 301 (outputs)
+    for (ta, ca), (tb, cb) in list(zip(ev[:-1], ev[1:]))[:int(os.environ["RAW"])]:
+        print(f"  {ta:4d} -> {tb:4d} {(cb - ca) & 0xFFFFFFFF:6d}")
+    sys.exit(0)
 seg = ev[:2 * ROUNDS + 1]  # second tile of group 0
 tot_e = tot_w = 0
 for (ta, ca), (tb, cb) in zip(seg[:-1], seg[1:]):
@@ -59,6 +63,26 @@ for (ta, ca), (tb, cb) in zip(seg[:-1], seg[1:]):
     print(f"  round {tb // 2:2d} {kind:28s} {dt:6d} cycles")
 print(f"  cycles for the tile: {(seg[-1][1] - seg[0][1]) & 0xFFFFFFFF}  (epilogues {tot_e}, waits {tot_w})")
 iv = [(int(t[i, 1, 0]), int(t[i, 1, 1])) for i in range(cap) if int(t[i, 1, 1]) != 0]
+if os.environ.get("ABS"):
+    # one round of group 0 on a common clock: operands written (data thread) -> ready seen by the issuer -> commit
+    # issued -> accumulators ready (data thread woken)
+    print("round: arrive->seen  seen->commit  commit->wake   (cycles, group 0, second traced tile)")
+    it_ev = {}
+    for tag, c in iv:
+        it_ev.setdefault(tag, []).append(c)
+    d_ev = {}
+    for tag, c in ev:
+        d_ev.setdefault(tag, []).append(c)
+    for r in range(ROUNDS):
+        try:
+            a = d_ev[2 * r][1]
+            seen = min(x for x in it_ev[3000 + r] if (x - a) & 0xFFFFFFFF < 1 << 20)
+            com = min(x for x in it_ev[4000 + r] if (x - seen) & 0xFFFFFFFF < 1 << 20)
+            w = min(x for x in d_ev[2 * r + 1] if (x - com) & 0xFFFFFFFF < 1 << 20)
+            print(f"  {r:2d}: {(seen - a) & 0xFFFFFFFF:6d} {(com - seen) & 0xFFFFFFFF:6d} {(w - com) & 0xFFFFFFFF:6d}")
+        except Exception as e:  # noqa: BLE001
+            print(f"  {r:2d}: incomplete ({e})")
+    sys.exit(0)
 print("issuer events:", len(iv), "(tag, delta): 3xxx = ready signal seen, 2xxx = + tcgen05 fence, 4xxx = critical MMAs + commit issued, "
       "5xxx = deferred MMAs issued, 1xxx = warp reconverged")
 rows = []

@@ -367,6 +367,7 @@ struct GroupSync {
         tr.stamp(2 * round);
         fence_proxy_async();  // NB: also waits for this thread's outstanding GLOBAL stores -- keep those behind it
         fence_before_sync();
+        if (UMHS_TRACE > 1) tr.stamp(200 + round);
         if (kNamedBarReady) {
             named_bar_arrive(bar_id, kReadyBarCount);  // every thread of the group; nobody waits here
             return;
@@ -501,7 +502,8 @@ struct TcFwd {
     static constexpr int kRounds = 5, kRoundsDensity = 2;
 };
 
-template <bool DENSITY_ONLY>
+// KM: compile-time bound on the number of classes K (4, 8 or 16; the density kernel ignores it)
+template <bool DENSITY_ONLY, int KM>
 __global__ void __launch_bounds__(TcFwdCfg<DENSITY_ONLY>::kThreads, 1)
 field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict__ enc, umhs_mlp_params mp,
                         umhs_field_out out) {
@@ -584,6 +586,8 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         GroupSync gs{bars + grp, bars + G + grp, 0u, lane, Tracer(tid == 0, 0, smem, 2 * ROUNDS), ready_flags(smem) + grp, kReadyBarId0 + grp};
         const uint32_t trow = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(WCOLS * grp);
         const float invT = DENSITY_ONLY ? 1.f : 1.0f / mp.temperature;
+        const bool vec_out = !DENSITY_ONLY && ((reinterpret_cast<uintptr_t>(out.scalar) |
+                                                reinterpret_cast<uintptr_t>(out.abund)) & 15u) == 0;
 
         // Inputs of a tile (hash-encoding rows + sample geometry) sit behind a chain of dependent loads (ray index ->
         // origin / direction, enc_index -> row): the NEXT tile's are issued while the tensor core works on this one --
@@ -709,8 +713,11 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             epi_relu64<false>(trow, tH, row, nullptr);
             epi_relu64<false>(trow + 64, tF, row, nullptr);
             gs.round_trip();
-            // ---------------- outputs
+            // ---------------- outputs (KM bounds the class loops at compile time: with a run-time K every one of the
+            // 16 guarded iterations still issued its ex2 / rcp -- 50 MUFU instructions per thread where K = 4 needs
+            // 13, ~2.5 k of a tile's 14 k cycles with three groups sharing the SM's 16 MUFU lanes)
             {
+                if (UMHS_TRACE > 1) gs.tr.stamp(300);
                 float zh[16], zf[16], zf2[16];
                 tmem_ld16(trow, zh);
                 tmem_ld16(trow + 64, zf);
@@ -718,32 +725,38 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                 if (valid) {
                     float mx = -3.0e38f;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        zf[k] *= invT;
-                        if (k < K) mx = fmaxf(mx, zf[k]);
-                    }
-                    float den = 0.f, e[16];
+                    for (int k = 0; k < KM; ++k)
+                        if (k < K) mx = fmaxf(mx, zf[k] * invT);
+                    float den = 0.f, e[KM], sg[KM];
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        e[k] = (k < K) ? __expf(zf[k] - mx) : 0.f;
+                    for (int k = 0; k < KM; ++k) {
+                        e[k] = (k < K) ? __expf(zf[k] * invT - mx) : 0.f;
                         den += e[k];
+                        sg[k] = __frcp_rn(1.0f + __expf(-zh[k]));
                     }
                     const float rden = __frcp_rn(den);
+                    if (KM == 4 && K == 4 && vec_out) {
+                        *reinterpret_cast<float4 *>(out.scalar + n * 4) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+                        *reinterpret_cast<float4 *>(out.abund + n * 4) =
+                            make_float4(e[0] * rden, e[1] * rden, e[2] * rden, e[3] * rden);
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        if (k < K) {
-                            out.scalar[n * K + k] = __frcp_rn(1.0f + __expf(-zh[k]));
-                            out.abund[n * K + k] = e[k] * rden;
+                        for (int k = 0; k < KM; ++k) {
+                            if (k < K) {
+                                out.scalar[n * K + k] = sg[k];
+                                out.abund[n * K + k] = e[k] * rden;
+                            }
                         }
                     }
                     if (spec && out.s1) {
-                        float z = zf2[0];
+                        float z = zf2[0];  // K = 16: the gate logit is column 16
 #pragma unroll
                         for (int k = 0; k < 16; ++k)
-                            if (k == K) z = zf[k] * mp.temperature;
+                            if (k <= KM && k == K) z = zf[k];
                         out.s1[n] = __frcp_rn(1.0f + __expf(-z));
                     }
                 }
+                if (UMHS_TRACE > 1) gs.tr.stamp(301);
             }
         }
         gs.tr.flush();
@@ -1507,9 +1520,9 @@ extern "C" int umhs_density_tc_fwd(const umhs_points *pts, int64_t n, const floa
     umhs_field_out out = {};
     out.sigma = sigma;
     const int bytes = TcSmem::groups + TcFwdCfg<true>::G * TcFwd::grp_bytes_density;
-    UMHS_CHECK_CUDA(cudaFuncSetAttribute(field_mlp_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    UMHS_CHECK_CUDA(cudaFuncSetAttribute(field_mlp_tc_fwd_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          bytes));
-    field_mlp_tc_fwd_kernel<true><<<tc_grid(n, TcFwdCfg<true>::G), TcFwdCfg<true>::kThreads, bytes, as_stream(stream)>>>(
+    field_mlp_tc_fwd_kernel<true, 4><<<tc_grid(n, TcFwdCfg<true>::G), TcFwdCfg<true>::kThreads, bytes, as_stream(stream)>>>(
         *pts, n, enc, *p, out);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
@@ -1524,10 +1537,11 @@ extern "C" int umhs_field_mlp_tc_fwd(const umhs_points *pts, int64_t n, const fl
                    "null weights");
     UMHS_CHECK_ARG(!p->specular || (p->dir_w0 && p->dir_b0), "specular weights missing");
     const int bytes = TcSmem::groups + TcFwdCfg<false>::G * TcFwd::grp_bytes;
-    UMHS_CHECK_CUDA(cudaFuncSetAttribute(field_mlp_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         bytes));
-    field_mlp_tc_fwd_kernel<false><<<tc_grid(n, TcFwdCfg<false>::G), TcFwdCfg<false>::kThreads, bytes, as_stream(stream)>>>(
-        *pts, n, enc, *p, *out);
+    auto kernel = p->num_classes <= 4 ? field_mlp_tc_fwd_kernel<false, 4>
+                : p->num_classes <= 8 ? field_mlp_tc_fwd_kernel<false, 8> : field_mlp_tc_fwd_kernel<false, 16>;
+    UMHS_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    kernel<<<tc_grid(n, TcFwdCfg<false>::G), TcFwdCfg<false>::kThreads, bytes, as_stream(stream)>>>(*pts, n, enc, *p,
+                                                                                                  *out);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }
