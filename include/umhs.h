@@ -139,7 +139,12 @@ typedef struct {
     float *abund;       /* [n,K]  or NULL softmax(logits / T)                         */
     float *s1;          /* [n]    or NULL (specular)                                  */
     float *spec_hidden; /* [n,16] or NULL (specular) ReLU(first layer mlp_directional) */
+    void *act_tiles;    /* NULL, or (umhs_field_mlp_tc_fwd only) ceil(n/128) * UMHS_ACT_TILE_BYTES bytes, 16-byte aligned:
+                         * the bf16 operand tiles of the hidden activations are kept for
+                         * umhs_field_mlp_tc_bwd_saved, which then does not recompute the forward */
 } umhs_field_out;
+/* per 128-sample tile: H0 [128x64] | X = [pe, emb, 1] [128x32] | head hidden 1, 2 | feature hidden 1, 2 [128x64 each] */
+#define UMHS_ACT_TILE_BYTES 90112
 
 typedef struct {
     const float *d_sigma;       /* [n]    */
@@ -166,6 +171,20 @@ int umhs_field_mlp_tc_fwd(const umhs_points *pts, int64_t n, const float *enc, c
  * accumulators resident in TMEM for the whole persistent CTA. */
 int umhs_field_mlp_tc_bwd(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
                           const umhs_field_out_grads *g, float *d_enc, const umhs_mlp_grads *dp, void *stream);
+/* Backward from the activations the training forward kept (umhs_field_out.act_tiles) and from its outputs: 8 tensor-core
+ * rounds per 128-sample tile instead of 16 (nothing is recomputed; the tiles come back by bulk copies).  Same results
+ * as umhs_field_mlp_tc_bwd up to the order of the weight-gradient reductions.  Needs p->enc_tiles = 1. */
+typedef struct {
+    const void *act_tiles;    /* what umhs_field_mlp_tc_fwd wrote: ceil(n/128) * UMHS_ACT_TILE_BYTES */
+    const float *sigma;       /* [n]    the forward's outputs */
+    const float *scalar;      /* [n,K]  */
+    const float *abund;       /* [n,K]  */
+    const float *s1;          /* [n]    (specular) */
+    const float *spec_hidden; /* [n,16] (specular) */
+} umhs_field_saved;
+int umhs_field_mlp_tc_bwd_saved(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
+                                const umhs_field_out_grads *g, const umhs_field_saved *saved, void *d_enc_tiles,
+                                const umhs_mlp_grads *dp, void *stream);
 /* The same backward AND the hash-grid scatter of its d_enc (umhs_hash_encode_bwd_tiles) in one kernel: 11 more warps
  * per CTA read the rows of d_enc_tiles back as the data warps publish them and add them into d_table (accumulating,
  * [L * 2^log2_T, 2] f32) -- the autograd backward of `self.mlp_base(positions_flat)` (ref umhsnerf/umhs_field.py:320)

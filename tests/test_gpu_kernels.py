@@ -625,6 +625,61 @@ def _rows_to_tile(rows):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n,K,spec,gather", [(1, 4, False, False), (129, 4, False, False), (40000, 9, True, False),
+                                             (70001, 16, True, True), (300001, 4, False, True), (5000, 16, False, False)])
+def test_mlp_backward_from_saved_activations(n, K, spec, gather):
+    """umhs_field_mlp_tc_bwd_saved (the training default: the forward keeps its bf16 activation tiles, the backward runs
+    8 rounds per tile from them) against the recomputing backward umhs_field_mlp_tc_bwd on the same inputs: the saving
+    forward returns bit-identical outputs; d_enc and the weight gradients agree to fp32 rounding of the output-layer
+    deltas (formed from the saved outputs instead of the recomputed logits).  gather: the kept samples are a subset of a
+    larger candidate set (enc_index), as in the training step."""
+    ops = _ops()
+    from helpers import mlp_precision
+    g = torch.Generator().manual_seed(n + K)
+    log2_T, L = 14, 16
+    table = ((torch.rand(L << log2_T, 2, generator=g) * 2 - 1) * 0.5).to(DEV)
+    scal = torch.floor(16 * torch.exp(torch.arange(L) * (np.log(2048 / 16) / (L - 1)))).float().to(DEV)
+    m = n * 2 + 5 if gather else n
+    pos_all = (torch.rand(m, 3, generator=g) * 2.4 - 1.2).to(DEV)
+    dirs_all = torch.nn.functional.normalize(torch.randn(m, 3, generator=g), dim=-1).to(DEV)
+    mk = lambda o_, i_: ((torch.rand(o_, i_, generator=g) * 2 - 1) / i_ ** 0.5).to(DEV).contiguous()  # noqa: E731
+    w = {}
+    for name, (o_, i_) in {"base_w0": (64, 32), "base_w1": (16, 64), "head_w0": (64, 27), "head_w1": (64, 64),
+                           "head_w2": (K, 64), "feat_w0": (64, 27), "feat_w1": (64, 64), "feat_w2": (K + spec, 64),
+                           "dir_w0": (16, 28)}.items():
+        w[name] = mk(o_, i_)
+        w[name.replace("_w", "_b")] = (torch.rand(o_, generator=g) * 0.1).to(DEV)
+    if not spec:
+        w["dir_w0"] = w["dir_b0"] = None
+    grads = {"d_sigma": torch.randn(n, generator=g).to(DEV), "d_scalar": torch.randn(n, K, generator=g).to(DEV),
+             "d_abund": torch.randn(n, K, generator=g).to(DEV), "d_embedding": torch.randn(n, 15, generator=g).to(DEV)}
+    if spec:
+        grads["d_s1"] = torch.randn(n, generator=g).to(DEV)
+        grads["d_spec_hidden"] = torch.randn(n, 16, generator=g).to(DEV)
+    with mlp_precision("bf16"):
+        enc_all = ops.hash_encode_fwd(ops.PointSet.from_positions(pos_all, dirs_all), table, scal, log2_T, tiles=True)
+        if gather:
+            keep = torch.sort(torch.randperm(m, generator=g)[:n]).values.to(DEV)
+            pts = ops.PointSet.from_positions(pos_all[keep].contiguous(), dirs_all[keep].contiguous())
+            pts.enc_src, pts.enc_index = enc_all, keep.to(torch.int32)
+        else:
+            pts = ops.PointSet.from_positions(pos_all, dirs_all)
+        plain = ops.field_mlp_fwd(pts, enc_all, w, K, spec, 0.4)
+        saved = ops.field_mlp_fwd(pts, enc_all, w, K, spec, 0.4, save_activations=True)
+        for k in ("sigma", "embedding", "scalar", "abund") + (("s1", "spec_hidden") if spec else ()):
+            assert torch.equal(plain[k], saved[k]), k
+        d_a, gw_a = ops.field_mlp_bwd(pts, enc_all, w, K, spec, 0.4, grads)
+        d_b, gw_b = ops.field_mlp_bwd(pts, enc_all, w, K, spec, 0.4, grads, saved=saved)
+    ra, rb = _tile_to_rows(d_a, n), _tile_to_rows(d_b, n)
+    assert float(ra.abs().max()) > 0
+    # bf16 rows: one ulp (2^-8 relative) where the last bit of an fp32 accumulator differs
+    assert_close(rb, ra, 1e-2, 1e-3 * float(ra.abs().max()), "d_enc")
+    assert float((rb - ra).norm() / ra.norm()) < 1e-3
+    for k in gw_a:
+        assert float((gw_b[k] - gw_a[k]).norm()) <= 2e-4 * float(gw_a[k].norm()) + 1e-9, k
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n,split", [(1, 8), (1000, 8), (70001, 3), (70001, 12)])
 def test_scatter_by_level_range(n, split):
     """umhs_hash_encode_bwd_tiles_levels: scattering levels [split, 16) and then [0, split) equals the one-pass scatter

@@ -14,7 +14,7 @@ import bench  # noqa: E402
 from umhs_b200 import _lib, ops  # noqa: E402
 
 MODE = sys.argv[1] if len(sys.argv) > 1 else "bwd"
-ROUNDS = {"bwd": 16, "fwd": 5}[MODE]
+ROUNDS = {"bwd": 8 if os.environ.get("UMHS_SAVE_ACTIVATIONS", "1") != "0" else 16, "fwd": 5}[MODE]
 D = bench.Dist()
 run = bench.TrainRun(D, "hotdog", 16384, graph=False)
 for i in range(bench.CONDITIONING_STEPS if hasattr(bench, "CONDITIONING_STEPS") else 8):

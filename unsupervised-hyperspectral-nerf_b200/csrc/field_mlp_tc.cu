@@ -459,6 +459,31 @@ __device__ __forceinline__ void issuer_rotation(uint64_t *bars, const int64_t (&
     tr.flush();
 }
 
+// ---- saved activations (training forward -> backward without recomputation).  Per 128-sample tile one block of
+// UMHS_ACT_TILE_BYTES: the operand tiles exactly as they sit in shared memory (chunk c of 8 columns at c * 2048, row r
+// inside a chunk at (r >> 3) * 128 + (r & 7) * 16): the backward brings a whole tile back with one bulk copy.
+struct ActTile {
+    static constexpr int H0 = 0, X = 16384, HH1 = 24576, HH2 = 40960, HF1 = 57344, HF2 = 73728;
+    static constexpr int bytes = UMHS_ACT_TILE_BYTES;
+};
+static_assert(ActTile::HF2 + 16384 == ActTile::bytes, "saved-activation block");
+// Each thread copies its own row (one 16-byte piece per chunk) from the shared-memory tile it has just written to the
+// block in global memory, BEHIND the hand-off of the round (the values are read back from shared memory, so nothing
+// stays in registers, and the streaming stores have a whole round to drain before the next hand-off's
+// fence.proxy.async, which waits for a thread's outstanding global stores).  A warp's 32 rows are 512 contiguous bytes
+// per chunk.  (Measured first: one bulk store, cp.async.bulk shared -> global, of those 512 bytes per warp and chunk --
+// 1.1 M copy-engine operations per forward, ~40 cycles each: 3.6 TB/s, +70 us.)
+__device__ __forceinline__ void save_row(uint8_t *dst_block, int dst_off, const uint8_t *smem_tile, int chunks, int row) {
+    const int off = (row >> 3) * 128 + (row & 7) * 16;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        if (c < chunks) {
+            const float4 v = *reinterpret_cast<const float4 *>(smem_tile + c * CH_ACT + off);
+            __stcs(reinterpret_cast<float4 *>(dst_block + dst_off + c * CH_ACT + off), v);
+        }
+    }
+}
+
 // issuer warp `ii` of `I` serves groups [ii * G / I, (ii + 1) * G / I)
 template <int I, int G, int ROUNDS, class F>
 __device__ __forceinline__ void issuer_dispatch(int ii, uint64_t *bars, const int64_t (&n_iter)[G], uint8_t *smem, int lane,
@@ -609,7 +634,8 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         // Contiguous bf16 tiles (no enc_index gather: the sampler's candidate pass, the occupancy update, evaluation
         // rendering) do not go through registers at all: ONE bulk copy (cp.async.bulk, the TMA engine) per tile brings
         // the 8 KB operand tile from global memory straight into tX, a whole tile ahead, completing on an mbarrier.
-        const bool bulk = mp.enc_tiles && P.enc_index == nullptr;
+        const bool save = !DENSITY_ONLY && out.act_tiles != nullptr;  // training: keep the activation tiles (ActTile)
+        const bool bulk = mp.enc_tiles && P.enc_index == nullptr && !save;
         uint64_t *full = reinterpret_cast<uint64_t *>(smem + TcSmem::sbias) + grp;  // (sbias is a backward-only region)
         auto bulk_issue = [&](int64_t tile) {
             if (!bulk || row != 0 || tile >= n_tiles) return;
@@ -642,6 +668,7 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
             const Point pt = make_point(P, raw_in);
             float pe[12];
             // ---------------- round 0: enc -> tX (whole rows, coalesced) ; base0
+            uint8_t *act = save ? reinterpret_cast<uint8_t *>(out.act_tiles) + tile_of(it, grp) * (int64_t)ActTile::bytes : nullptr;
             if (bulk) mbar_wait(full, (uint32_t)(it & 1));  // the copy engine has delivered this tile
             else if (mp.enc_tiles) store_enc_pieces(tX, row, e_in);
             else store_enc_rows(tX, (warp & 3) * 32, lane, e_in);
@@ -665,6 +692,7 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                 for (int c = 0; c < 4; ++c) store8(tF, row, 8 * c, CH_ACT, x2 + 8 * c);
             }
             gs.arrive();
+            if (save) save_row(act, ActTile::H0, tH, 8, row);
             if (DENSITY_ONLY && UMHS_DENSITY_PREFETCH) load_rest(tile_of(it + 1, grp));
             else if (!DENSITY_ONLY) load_idx(tile_of(it + 1, grp));
             gs.wait();
@@ -702,17 +730,28 @@ field_mlp_tc_fwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
                 for (int c = 0; c < 4; ++c) store8(tX, row, 8 * c, CH_ACT, x + 8 * c);
             }
             gs.arrive();
+            if (save) save_row(act, ActTile::X, tX, 4, row);
             load_rest(tile_of(it + 1, grp));
             gs.wait();
             bulk_issue(tile_of(it + 1, grp));  // X in tX has been consumed: the next tile's encodings may land
             // ---------------- round 3: hidden 0 of both MLPs -> tH, tF ; head1, feat1
             epi_relu64<false>(trow, tH, row, nullptr);
             epi_relu64<false>(trow + 64, tF, row, nullptr);
-            gs.round_trip();
+            gs.arrive();
+            if (save) {
+                save_row(act, ActTile::HH1, tH, 8, row);
+                save_row(act, ActTile::HF1, tF, 8, row);
+            }
+            gs.wait();
             // ---------------- round 4: hidden 1 -> tH, tF ; head2 (N = 16), feat2 (N = 32)
             epi_relu64<false>(trow, tH, row, nullptr);
             epi_relu64<false>(trow + 64, tF, row, nullptr);
-            gs.round_trip();
+            gs.arrive();
+            if (save) {
+                save_row(act, ActTile::HH2, tH, 8, row);
+                save_row(act, ActTile::HF2, tF, 8, row);
+            }
+            gs.wait();
             // ---------------- outputs (KM bounds the class loops at compile time: with a run-time K every one of the
             // 16 guarded iterations still issued its ex2 / rcp -- 50 MUFU instructions per thread where K = 4 needs
             // 13, ~2.5 k of a tile's 14 k cycles with three groups sharing the SM's 16 MUFU lanes)
@@ -865,6 +904,50 @@ __device__ __forceinline__ void flush_acc(uint32_t trow, int col0, int ncols, in
                 if (c + i < ncols) sink(c + i, v[i]);
         }
     }
+}
+
+// Flush of the persistent weight-gradient accumulators + narrow-layer bias sums (both backward kernels; every thread of
+// the CTA calls it after the role branches): row r = 16 * (warp & 3) + lane (lane < 16) of every [64 x ncols] accumulator.
+__device__ __forceinline__ void flush_weight_grads(uint32_t tbase, int tid, int grp, int G, int K, int spec,
+                                                   const umhs_mlp_grads &dp, bool any_tile, bool two_copies,
+                                                   bool hi_valid, const float *sbias) {
+    const int warp = tid >> 5, lane = tid & 31;
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (grp < G && any_tile) {
+        const uint32_t tq = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+        const int r = (warp & 3) * 16 + lane;
+        if (grp == 0) {
+            flush_acc(tq, TcBwd::P_h2t, K, lane, two_copies, hi_valid, [&](int c, float v) { if (v != 0.f) red_add(dp.head_w2 + c * 64 + r, v); });
+            flush_acc(tq, TcBwd::P_h1, 65, lane, two_copies, hi_valid, [&](int c, float v) {
+                if (v != 0.f) red_add(c < 64 ? dp.head_w1 + r * 64 + c : dp.head_b1 + r, v); });
+            flush_acc(tq, TcBwd::P_h0, 28, lane, two_copies, hi_valid, [&](int c, float v) {
+                if (v != 0.f) red_add(c < 27 ? dp.head_w0 + r * 27 + c : dp.head_b0 + r, v); });
+            flush_acc(tq, TcBwd::P_b1t, 16, lane, two_copies, hi_valid, [&](int c, float v) { if (v != 0.f) red_add(dp.base_w1 + c * 64 + r, v); });
+            if (spec)
+                flush_acc(tq, TcBwd::P_d0, 29, lane, two_copies, hi_valid, [&](int c, float v) {
+                    if (r < 16 && v != 0.f) red_add(c < 28 ? dp.dir_w0 + r * 28 + c : dp.dir_b0 + r, v); });
+        } else {
+            flush_acc(tq, TcBwd::P_f2t, K + spec, lane, two_copies, hi_valid, [&](int c, float v) { if (v != 0.f) red_add(dp.feat_w2 + c * 64 + r, v); });
+            flush_acc(tq, TcBwd::P_f1, 65, lane, two_copies, hi_valid, [&](int c, float v) {
+                if (v != 0.f) red_add(c < 64 ? dp.feat_w1 + r * 64 + c : dp.feat_b1 + r, v); });
+            flush_acc(tq, TcBwd::P_f0, 28, lane, two_copies, hi_valid, [&](int c, float v) {
+                if (v != 0.f) red_add(c < 27 ? dp.feat_w0 + r * 27 + c : dp.feat_b0 + r, v); });
+            flush_acc(tq, TcBwd::P_b0, 33, lane, two_copies, hi_valid, [&](int c, float v) {
+                if (v != 0.f) red_add(c < 32 ? dp.base_w0 + r * 32 + c : dp.base_b0 + r, v); });
+        }
+    }
+    if (tid < 64) {
+        const float a = sbias[tid];
+        float *dst = nullptr;
+        if (tid < 16) dst = (tid < K) ? dp.head_b2 + tid : nullptr;
+        else if (tid < 48) dst = (tid - 16 < K + spec) ? dp.feat_b2 + (tid - 16) : nullptr;
+        else dst = dp.base_b1 + (tid - 48);
+        if (dst != nullptr && a != 0.f) red_add(dst, a);
+    }
+    fence_before_sync();
+    __syncthreads();
 }
 
 // KM: compile-time bound on the number of classes K (4, 8 or 16): sizes the softmax / sigmoid epilogues
@@ -1299,45 +1382,365 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
         if (lane == 0 && bs_f2s != 0.f) atomicAdd(sb_f2 + KM, bs_f2s);
     }
 
-    // ================= flush the weight-gradient accumulators: row r = 16 * (warp & 3) + lane (lane < 16)
+    // ================= flush the weight-gradient accumulators
+    flush_weight_grads(tbase, tid, grp, G, K, spec, dp, tile_of(0, 0) < n_tiles, TcBwd::I == 2, tile_of(0, 1) < n_tiles, sbias);
+    if (warp == G * 4) tmem_dealloc<TcBwd::ncols>(tbase);
+}
+
+// =====================================================================================================
+// Backward from SAVED activations (umhs_field_mlp_tc_bwd_saved): 8 rounds per tile instead of 16.
+//
+// Half of the rounds of the kernel above recompute the forward (base0, base1, head0-2, feat0-2).  The training forward
+// can keep its bf16 operand tiles instead (umhs_field_out.act_tiles, 704 B per sample, written by warp-local bulk
+// stores as a by-product of its epilogues); here they come back by ONE bulk copy per tile and layer (TMA, mbarrier
+// transaction count) into two 16 KB slots, each two rounds ahead of the MMAs that read it, and the output-layer
+// deltas are formed from the forward's outputs (sigmoid' = s (1 - s), softmax Jacobian from the abundances,
+// trunc_exp' = the density itself).  Same MMAs, same accumulators, same flush as the kernel above.
+//   round  critical (dgrad)                      deferred (wgrad)                operands arriving for
+//   1      dz_h  [128x16] W_h2  -> d h2 (head)   P_h2t += Hh2^T dz_h             slot A: Hh2   slot B: Hh1   tX: X
+//   2      d2_h  W_h1           -> d h1          P_h1  += d2_h^T [Hh1 | 1]
+//   3      d1_h  W_h0           -> d X (head)    P_h0  += d1_h^T X               slot A <- Hf2
+//   4      dz_f  [128x32] W_f2  -> d h2 (feat)   P_f2t += Hf2^T dz_f             slot B <- Hf1
+//   5      d2_f  W_f1           -> d h1          P_f1  += d2_f^T [Hf1 | 1]
+//   6      d1_f  W_f0           -> d X (feat)    P_f0  += d1_f^T X               slot A <- H0
+//   7      dO    [128x16] W_b1  -> d h0          P_b1t += H0^T dO                slot B[8K:] <- enc rows (threads)
+//   8      d0    W_b0           -> d enc         P_b0  += d0^T [enc | 1] (not deferred)   tX <- next X
+// A slot is refilled as soon as the commit that covers its last reader has arrived (deferred MMAs of round r are
+// covered by the commit of round r + 1).
+// =====================================================================================================
+struct TcBwd2 {
+    static constexpr int G = 2;
+    static constexpr int sA = 0;                              // [128 x 64]
+    static constexpr int sB = sA + TM * 64 * 2;               // [128 x 64] + ones chunk
+    static constexpr int tX = sB + TM * 64 * 2 + 2048;        // [128 x 32]
+    static constexpr int tD1 = tX + TM * 32 * 2;              // [128 x 64]
+    static constexpr int tD2 = tD1 + TM * 64 * 2;             // [128 x 64]
+    static constexpr int tZ = tD2 + TM * 64 * 2;              // [128 x 32] output-layer deltas
+    static constexpr int grp_bytes = tZ + TM * 32 * 2;        // 82 KB
+    static constexpr int kRounds = 8;
+    static constexpr int kThreads = G * TM + 32;
+    static constexpr int smem_bytes = TcSmem::groups + G * grp_bytes;
+};
+static_assert(TcBwd2::smem_bytes <= 232448, "shared-memory plan exceeds 227 KB");
+
+struct SavedFwd {  // what the training forward left behind (all read-only here)
+    const uint8_t *act_tiles;
+    const float *sigma, *scalar, *abund, *s1, *spec_hidden;
+};
+
+template <int KM>
+__global__ void __launch_bounds__(TcBwd2::kThreads, 1)
+field_mlp_tc_bwd_saved_kernel(umhs_points P, int64_t n_total, const float *__restrict__ enc, umhs_mlp_params mp,
+                              umhs_field_out_grads g, SavedFwd sv, float *__restrict__ d_enc, umhs_mlp_grads dp) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int G = TcBwd2::G;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K = mp.num_classes, spec = mp.specular;
+    const int grp = warp < G * 4 ? (tid >> 7) : G, row = tid & 127;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TcSmem::ctrl);  // ready[G], done[G]
+    uint64_t *fulls = reinterpret_cast<uint64_t *>(smem + TcSmem::scat);  // [G][3]: slot A, slot B, tX filled
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TcSmem::ctrl + 64);
+    float *sbias = reinterpret_cast<float *>(smem + TcSmem::sbias);
+    uint8_t *gbase = smem + TcSmem::groups + (grp < G ? grp : 0) * TcBwd2::grp_bytes;
+
+    stage_all_weights(smem, mp, false, tid, (int)blockDim.x);
+    if (tid < G * TM) {
+        const float one[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        store8(gbase + TcBwd2::sB, row, 64, CH_ACT, one);  // the ones chunk behind slot B
+    }
+    if (tid < 64) sbias[tid] = 0.f;
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+            mbar_init(bars + q, 4);
+            mbar_init(bars + G + q, 1);
+            for (int i = 0; i < 3; ++i) mbar_init(fulls + 3 * q + i, 1);
+            ready_flags(smem)[q] = 0u;
+        }
+        fence_mbar_init();
+    }
+    if (warp == G * 4) tmem_alloc<TcBwd::ncols>(tmem_slot);
+    fence_proxy_async();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    const bool any_tile = tile_of(0, 0) < n_tiles;  // group 0 ran >= 1 tile => every accumulator was initialised
-    const bool hi_valid = tile_of(0, 1) < n_tiles;  // (two issuers) group 1 ran >= 1 tile => so was its copy
-    if (grp < G && any_tile) {
-        const uint32_t tq = tbase + ((uint32_t)((warp & 3) * 32) << 16);
-        const int r = (warp & 3) * 16 + lane;
-        if (grp == 0) {
-            flush_acc(tq, TcBwd::P_h2t, K, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) { if (v != 0.f) red_add(dp.head_w2 + c * 64 + r, v); });
-            flush_acc(tq, TcBwd::P_h1, 65, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) {
-                if (v != 0.f) red_add(c < 64 ? dp.head_w1 + r * 64 + c : dp.head_b1 + r, v); });
-            flush_acc(tq, TcBwd::P_h0, 28, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) {
-                if (v != 0.f) red_add(c < 27 ? dp.head_w0 + r * 27 + c : dp.head_b0 + r, v); });
-            flush_acc(tq, TcBwd::P_b1t, 16, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) { if (v != 0.f) red_add(dp.base_w1 + c * 64 + r, v); });
-            if (spec)
-                flush_acc(tq, TcBwd::P_d0, 29, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) {
-                    if (r < 16 && v != 0.f) red_add(c < 28 ? dp.dir_w0 + r * 28 + c : dp.dir_b0 + r, v); });
-        } else {
-            flush_acc(tq, TcBwd::P_f2t, K + spec, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) { if (v != 0.f) red_add(dp.feat_w2 + c * 64 + r, v); });
-            flush_acc(tq, TcBwd::P_f1, 65, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) {
-                if (v != 0.f) red_add(c < 64 ? dp.feat_w1 + r * 64 + c : dp.feat_b1 + r, v); });
-            flush_acc(tq, TcBwd::P_f0, 28, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) {
-                if (v != 0.f) red_add(c < 27 ? dp.feat_w0 + r * 27 + c : dp.feat_b0 + r, v); });
-            flush_acc(tq, TcBwd::P_b0, 33, lane, TcBwd::I == 2, hi_valid, [&](int c, float v) {
-                if (v != 0.f) red_add(c < 32 ? dp.base_w0 + r * 32 + c : dp.base_b0 + r, v); });
+    const uint32_t tbase = *tmem_slot;
+    n_total = effective_n(P, n_total);
+    const int64_t n_tiles = (n_total + TM - 1) / TM;
+    auto tile_of = [&](int64_t it, int q) { return (it * gridDim.x + blockIdx.x) * G + q; };
+    int64_t n_iter[G];
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+        const int64_t first = (int64_t)blockIdx.x * G + q, stride = (int64_t)gridDim.x * G;
+        n_iter[q] = first < n_tiles ? (n_tiles - 1 - first) / stride + 1 : 0;
+    }
+
+    if (grp == G) {
+        // ======================= MMA issuer warp
+        const uint32_t sbase = smem_u32(smem);
+        const bool want_denc = d_enc != nullptr;
+        issuer_dispatch<1, G, TcBwd2::kRounds>(0, bars, n_iter, smem, lane, [&](auto rc, auto gc, uint32_t acc,
+                                                                                uint32_t zero, auto ph) {
+            constexpr int r = decltype(rc)::value, q = decltype(gc)::value;
+            constexpr bool crit = decltype(ph)::value == 0, late = !crit;
+            const uint32_t B16 = desc_base16(sbase) + zero;
+            using w = WOff;
+            constexpr uint32_t b = (uint32_t)(TcSmem::groups + q * TcBwd2::grp_bytes);
+            constexpr uint32_t sA = b + TcBwd2::sA, sB = b + TcBwd2::sB, sX = b + TcBwd2::tX;
+            constexpr uint32_t sD1 = b + TcBwd2::tD1, sD2 = b + TcBwd2::tD2, sZ = b + TcBwd2::tZ;
+            const uint32_t tw = tbase + 64u * q;
+            if constexpr (r == 0) {
+                if (crit) {
+                    gemm_dgrad(tw, B16, sZ, w::h2, 16, 0, 64, 16, 0);
+                    // mlp_directional layer 0: d h (padded to 64 columns) sits in tD1, its input [sh, pe, 1] in tD2;
+                    // not deferred: the next epilogue writes tD1
+                    if (spec) gemm_wgrad(tbase + TcBwd::P_d0, B16, sD1, 0, sD2, 0, 32, acc);
+                }
+                if (late) gemm_wgrad(tbase + TcBwd::P_h2t, B16, sA, 0, sZ, 0, 16, acc);
+            } else if constexpr (r == 1) {
+                if (crit) gemm_dgrad(tw, B16, sD1, w::h1, 64, 0, 64, 64, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_h1, B16, sD1, 0, sB, 0, 72, acc);
+            } else if constexpr (r == 2) {
+                if (crit) gemm_dgrad(tw, B16, sD2, w::hf0, 128, 0, 32, 64, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_h0, B16, sD2, 0, sX, 0, 32, acc);
+            } else if constexpr (r == 3) {
+                if (crit) gemm_dgrad(tw, B16, sZ, w::f2, 32, 0, 64, 32, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_f2t, B16, sA, 0, sZ, 0, 32, acc);
+            } else if constexpr (r == 4) {
+                if (crit) gemm_dgrad(tw, B16, sD1, w::f1, 64, 0, 64, 64, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_f1, B16, sD1, 0, sB, 0, 72, acc);
+            } else if constexpr (r == 5) {
+                if (crit) gemm_dgrad(tw, B16, sD2, w::hf0, 128, 64, 32, 64, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_f0, B16, sD2, 0, sX, 0, 32, acc);
+            } else if constexpr (r == 6) {
+                if (crit) gemm_dgrad(tw, B16, sZ, w::b1, 16, 0, 64, 16, 0);
+                if (late) gemm_wgrad(tbase + TcBwd::P_b1t, B16, sA, 0, sZ, 0, 16, acc);
+            } else {
+                if (crit) {
+                    if (want_denc) gemm_dgrad(tw, B16, sD1, w::b0, 64, 0, 32, 64, 0);
+                    gemm_wgrad(tbase + TcBwd::P_b0, B16, sD1, 0, sB + 8192u, 0, 40, acc);  // [enc | ones]
+                }
+            }
+        });
+        __syncwarp();
+    } else {
+        // ======================= data groups
+        uint8_t *sA = gbase + TcBwd2::sA, *sB = gbase + TcBwd2::sB, *tX = gbase + TcBwd2::tX;
+        uint8_t *tD1 = gbase + TcBwd2::tD1, *tD2 = gbase + TcBwd2::tD2, *tZ = gbase + TcBwd2::tZ;
+        uint64_t *fullA = fulls + 3 * grp, *fullB = fullA + 1, *fullX = fullA + 2;
+        uint32_t parA = 0u, parB = 0u, parX = 0u;
+        GroupSync gs{bars + grp, bars + G + grp, 0u, lane, Tracer(tid == 0, 0, smem, 2 * TcBwd2::kRounds), ready_flags(smem) + grp, kReadyBarId0 + grp};
+        const uint32_t trow = tbase + ((uint32_t)((warp & 3) * 32) << 16) + 64u * grp;
+        float *sb_h2 = sbias, *sb_f2 = sbias + 16, *sb_b1 = sbias + 48;
+        const float invT = 1.0f / mp.temperature;
+        float bs_h2 = 0.f, bs_f2 = 0.f, bs_f2s = 0.f, bs_b1 = 0.f;
+        const uint64_t pol = l2_evict_first_policy();
+        auto fetch = [&](uint8_t *dst, uint64_t *bar, int64_t tile, int off, uint32_t bytes) {  // row 0 of the group
+            mbar_expect_tx(bar, bytes);
+            bulk_load_hint(dst, sv.act_tiles + tile * (int64_t)ActTile::bytes + off, bytes, bar, pol);
+        };
+        auto wait_full = [&](uint64_t *bar, uint32_t &par) {
+            mbar_wait(bar, par);
+            par ^= 1u;
+        };
+        auto sample_of = [&](int64_t tile) {
+            const int64_t m = tile * TM + row;
+            return m < n_total ? m : n_total - 1;
+        };
+        PointRaw raw_in;
+        PointIdx pi_in;
+        int64_t pending_row = -1;
+        // what the FIRST epilogue of a tile needs (gradient and value of the mlp_head outputs) is fetched during the
+        // last rounds of the tile before: a DRAM latency right behind the tile's first hand-off otherwise
+        float gh_in[KM], sh_in[KM];
+        auto load_head = [&](int64_t tile) {
+            const int64_t m = tile * TM + row;
+            const bool ok = m < n_total;
+#pragma unroll
+            for (int k = 0; k < KM; ++k) {
+                gh_in[k] = (ok && k < K) ? __ldg(g.d_scalar + m * K + k) : 0.f;
+                sh_in[k] = (ok && k < K) ? __ldg(sv.scalar + m * K + k) : 0.f;
+            }
+        };
+        if (tile_of(0, grp) < n_tiles) {
+            load_head(tile_of(0, grp));
+            if (row == 0) {
+                fetch(sA, fullA, tile_of(0, grp), ActTile::HH2, 16384u);
+                fetch(sB, fullB, tile_of(0, grp), ActTile::HH1, 16384u);
+                fetch(tX, fullX, tile_of(0, grp), ActTile::X, 8192u);
+            }
+            pi_in = load_point_idx(P, sample_of(tile_of(0, grp)));
+            raw_in = load_point_raw(P, sample_of(tile_of(0, grp)), pi_in);
         }
+
+        for (int64_t it = 0; tile_of(it, grp) < n_tiles; ++it) {
+            gs.round = 0;
+            const int64_t tile = tile_of(it, grp), next = tile_of(it + 1, grp);
+            const int64_t n0 = tile * TM;
+            const bool valid = n0 + row < n_total;
+            const int64_t n = valid ? n0 + row : n_total - 1;
+            // invalid (tail) rows run the chain with ZERO incoming gradients: every delta they produce is exactly zero
+            const Point pt = make_point(P, raw_in);
+            const int64_t erow = enc_row(P, n);
+            // ---------------- before round 1: dz of mlp_head -> tZ [; specular: d h -> tD1 (64 wide), X2 -> tD2]
+            {
+                float dz[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) dz[k] = 0.f;
+#pragma unroll
+                for (int k = 0; k < KM; ++k) dz[k] = gh_in[k] * sh_in[k] * (1.0f - sh_in[k]);  // (zero for tail rows)
+                store8(tZ, row, 0, CH_ACT, dz);
+                store8(tZ, row, 8, CH_ACT, dz + 8);
+                bs_h2 += warp_colsum<KM>(dz, lane);
+            }
+            if (spec) {
+                float pe[12], x2[32], sh[16], dsh[16];
+                pos_encoding_tc(pt, pe);
+                sh_deg3_tc((pt.dx + 1.0f) / 2.0f, (pt.dy + 1.0f) / 2.0f, (pt.dz + 1.0f) / 2.0f, sh);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x2[i] = sh[i];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) x2[16 + i] = pe[i];
+                x2[28] = 1.0f;
+                x2[29] = x2[30] = x2[31] = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) store8(tD2, row, 8 * c, CH_ACT, x2 + 8 * c);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float4 gq = make_float4(0.f, 0.f, 0.f, 0.f), h = gq;
+                    if (valid && g.d_spec_hidden) {
+                        gq = __ldg(reinterpret_cast<const float4 *>(g.d_spec_hidden + n * 16) + q);
+                        h = __ldg(reinterpret_cast<const float4 *>(sv.spec_hidden + n * 16) + q);
+                    }
+                    dsh[4 * q] = (h.x > 0.f) ? gq.x : 0.f;
+                    dsh[4 * q + 1] = (h.y > 0.f) ? gq.y : 0.f;
+                    dsh[4 * q + 2] = (h.z > 0.f) ? gq.z : 0.f;
+                    dsh[4 * q + 3] = (h.w > 0.f) ? gq.w : 0.f;
+                }
+                const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                store8(tD1, row, 0, CH_ACT, dsh);
+                store8(tD1, row, 8, CH_ACT, dsh + 8);
+#pragma unroll
+                for (int c = 16; c < 64; c += 8) store8(tD1, row, c, CH_ACT, z8);
+            }
+            // gradients of the second MLP's outputs and of the density: used two / six rounds from here
+            float ga[KM + 1], pa[KM + 1];
+#pragma unroll
+            for (int k = 0; k < KM; ++k) {
+                ga[k] = (valid && k < K) ? __ldg(g.d_abund + n * K + k) : 0.f;
+                pa[k] = (valid && k < K) ? __ldg(sv.abund + n * K + k) : 0.f;
+            }
+            ga[KM] = (valid && spec && g.d_s1) ? __ldg(g.d_s1 + n) : 0.f;
+            pa[KM] = (valid && spec && g.d_s1) ? __ldg(sv.s1 + n) : 0.f;
+            const float dsg = (valid && g.d_sigma) ? __ldg(g.d_sigma + n) : 0.f;
+            const float sig = valid ? __ldg(sv.sigma + n) : 0.f;
+            float demb[15];
+#pragma unroll
+            for (int i = 0; i < 15; ++i) demb[i] = (valid && g.d_embedding) ? __ldg(g.d_embedding + n * 15 + i) : 0.f;
+            wait_full(fullA, parA);  // Hh2
+            gs.arrive();
+            if (d_enc && it > 0) flush_staged_pieces(d_enc, pending_row, tD2 + 8192, row);  // (tD2's upper half: idle until round 3's epilogue... see below)
+            gs.wait();
+            // ---------------- round 2: d h2 (head) masked by Hh2 -> tD1
+            epi_mask64(trow, sA, nullptr, tD1, row);
+            wait_full(fullB, parB);  // Hh1
+            gs.round_trip();
+            // ---------------- round 3: d h1 masked by Hh1 -> tD2 ; dz of feature_mlp -> tZ ; slot A <- Hf2
+            if (row == 0) fetch(sA, fullA, tile, ActTile::HF2, 16384u);
+            epi_mask64(trow, sB, nullptr, tD2, row);
+            {
+                float dz[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) dz[k] = 0.f;
+                float dot = 0.f;
+#pragma unroll
+                for (int k = 0; k < KM; ++k) dot += pa[k] * ga[k];
+#pragma unroll
+                for (int k = 0; k < KM; ++k) dz[k] = pa[k] * invT * (ga[k] - dot);
+                if (spec) {
+                    const float ds = ga[KM] * pa[KM] * (1.0f - pa[KM]);
+#pragma unroll
+                    for (int k = 0; k <= KM; ++k)
+                        if (k == K) dz[k] = ds;
+                }
+                store8(tZ, row, 0, CH_ACT, dz);
+                store8(tZ, row, 8, CH_ACT, dz + 8);
+                store8(tZ, row, 16, CH_ACT, dz + 16);
+                store8(tZ, row, 24, CH_ACT, dz + 24);
+                bs_f2 += warp_colsum<KM>(dz, lane);
+                if (K + spec > KM) bs_f2s += warp_sum(dz[KM]);
+            }
+            wait_full(fullX, parX);  // X (first use in this tile)
+            gs.round_trip();
+            // ---------------- round 4: d X of mlp_head ; slot B <- Hf1
+            if (row == 0) fetch(sB, fullB, tile, ActTile::HF1, 16384u);
+            {
+                float dx[32];
+                tmem_ld32(trow, dx);
+#pragma unroll
+                for (int i = 0; i < 15; ++i) demb[i] += dx[12 + i];
+            }
+            float4 e_in[8];
+            load_enc_pieces(enc, erow, e_in);  // this tile's encoding rows: operand of the last weight gradient
+            wait_full(fullA, parA);  // Hf2
+            gs.round_trip();
+            // ---------------- round 5: d h2 (feat) masked by Hf2 -> tD1
+            epi_mask64(trow, sA, nullptr, tD1, row);
+            wait_full(fullB, parB);  // Hf1
+            if (next < n_tiles) pi_in = load_point_idx(P, sample_of(next));
+            gs.round_trip();
+            // ---------------- round 6: d h1 masked by Hf1 -> tD2 ; slot A <- H0
+            if (row == 0) fetch(sA, fullA, tile, ActTile::H0, 16384u);
+            epi_mask64(trow, sB, nullptr, tD2, row);
+            gs.round_trip();
+            // ---------------- round 7: d X of feature_mlp ; dO = [d o0, d emb] -> tZ ; encoding rows -> slot B[8K:]
+            {
+                float dx[32], dO[16];
+                tmem_ld32(trow, dx);
+#pragma unroll
+                for (int i = 0; i < 15; ++i) demb[i] += dx[12 + i];
+                // density = trunc_exp(o0) * sel: d o0 = d_sigma * sel * exp(clamp(o0, -15, 15)) = d_sigma * clamp(density)
+                dO[0] = dsg * pt.sel * fminf(fmaxf(sig, 3.0590232e-7f), 3269017.4f);
+#pragma unroll
+                for (int i = 0; i < 15; ++i) dO[1 + i] = demb[i];
+                store8(tZ, row, 0, CH_ACT, dO);
+                store8(tZ, row, 8, CH_ACT, dO + 8);
+                bs_b1 += warp_colsum<16>(dO, lane);
+            }
+            store_enc_pieces(sB + 8192, row, e_in);
+            if (next < n_tiles) {
+                raw_in = load_point_raw(P, sample_of(next), pi_in);
+                load_head(next);
+            }
+            wait_full(fullA, parA);  // H0
+            gs.round_trip();
+            // ---------------- round 8: d h0 masked by H0 -> tD1 ; tX <- next X
+            if (row == 0 && next < n_tiles) fetch(tX, fullX, next, ActTile::X, 8192u);
+            epi_mask64(trow, sA, nullptr, tD1, row);
+            gs.round_trip();
+            // ---------------- d enc ; slots A, B <- the next tile's Hh2, Hh1
+            if (row == 0 && next < n_tiles) {
+                fetch(sA, fullA, next, ActTile::HH2, 16384u);
+                fetch(sB, fullB, next, ActTile::HH1, 16384u);
+            }
+            if (d_enc) {
+                float v[32];
+                tmem_ld32(trow, v);
+                stage_pieces(v, tD2 + 8192, row);  // tD2's upper 8 KB (idle until round 3's epilogue of the next tile)
+                pending_row = valid ? n : -1;
+            }
+        }
+        if (d_enc && tile_of(0, grp) < n_tiles) flush_staged_pieces(d_enc, pending_row, tD2 + 8192, row);
+        gs.tr.flush();
+        if (colsum_owner<KM>(lane)) {
+            const int col = colsum_col<KM>(lane);
+            if (bs_h2 != 0.f) atomicAdd(sb_h2 + col, bs_h2);
+            if (bs_f2 != 0.f) atomicAdd(sb_f2 + col, bs_f2);
+        }
+        if (colsum_owner<16>(lane) && bs_b1 != 0.f) atomicAdd(sb_b1 + colsum_col<16>(lane), bs_b1);
+        if (lane == 0 && bs_f2s != 0.f) atomicAdd(sb_f2 + KM, bs_f2s);
     }
-    if (tid < 64) {
-        const float a = sbias[tid];
-        float *dst = nullptr;
-        if (tid < 16) dst = (tid < K) ? dp.head_b2 + tid : nullptr;
-        else if (tid < 48) dst = (tid - 16 < K + spec) ? dp.feat_b2 + (tid - 16) : nullptr;
-        else dst = dp.base_b1 + (tid - 48);
-        if (dst != nullptr && a != 0.f) red_add(dst, a);
-    }
-    fence_before_sync();
-    __syncthreads();
+    flush_weight_grads(tbase, tid, grp, G, K, spec, dp, tile_of(0, 0) < n_tiles, false, false, sbias);
     if (warp == G * 4) tmem_dealloc<TcBwd::ncols>(tbase);
 }
 
@@ -1563,6 +1966,33 @@ extern "C" int umhs_field_mlp_tc_bwd(const umhs_points *pts, int64_t n, const fl
     UMHS_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcBwd::smem_bytes));
     kernel<<<tc_grid(n, TcBwd::G), TcBwd::kThreads, TcBwd::smem_bytes, as_stream(stream)>>>(*pts, n, enc, *p, *g, d_enc,
                                                                                           *dp, ScatterArgs{});
+    UMHS_CHECK_LAUNCH();
+    return UMHS_OK;
+}
+
+extern "C" int umhs_field_mlp_tc_bwd_saved(const umhs_points *pts, int64_t n, const float *enc, const umhs_mlp_params *p,
+                                           const umhs_field_out_grads *g, const umhs_field_saved *saved,
+                                           void *d_enc_tiles, const umhs_mlp_grads *dp, void *stream) {
+    if (n <= 0) return UMHS_OK;
+    UMHS_CHECK_ARG(pts && enc && g && dp && p && saved, "null argument");
+    UMHS_CHECK_ARG(p->enc_tiles == 1, "the saved-activation backward works on the bf16 tile buffers (enc_tiles = 1)");
+    UMHS_CHECK_ARG(saved->act_tiles && saved->sigma && saved->scalar && saved->abund, "saved forward state missing");
+    UMHS_CHECK_ARG((reinterpret_cast<uintptr_t>(saved->act_tiles) & 15u) == 0, "act_tiles must be 16-byte aligned");
+    UMHS_CHECK_ARG(!p->specular || (saved->s1 && saved->spec_hidden), "saved specular outputs missing");
+    UMHS_CHECK_ARG(p->num_classes >= 1 && p->num_classes <= UMHS_MAX_CLASSES && p->temperature > 0.f, "bad K / T");
+    UMHS_CHECK_ARG(g->d_scalar && g->d_abund, "d_scalar/d_abund are required");
+    UMHS_CHECK_ARG(dp->base_w0 && dp->base_b0 && dp->base_w1 && dp->base_b1 && dp->head_w0 && dp->head_b0 &&
+                       dp->head_w1 && dp->head_b1 && dp->head_w2 && dp->head_b2 && dp->feat_w0 && dp->feat_b0 &&
+                       dp->feat_w1 && dp->feat_b1 && dp->feat_w2 && dp->feat_b2,
+                   "null parameter-gradient pointer");
+    UMHS_CHECK_ARG(!p->specular || (p->dir_w0 && p->dir_b0 && dp->dir_w0 && dp->dir_b0), "specular pointers missing");
+    auto kernel = p->num_classes <= 4 ? field_mlp_tc_bwd_saved_kernel<4>
+                : p->num_classes <= 8 ? field_mlp_tc_bwd_saved_kernel<8> : field_mlp_tc_bwd_saved_kernel<16>;
+    UMHS_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcBwd2::smem_bytes));
+    const SavedFwd sv{reinterpret_cast<const uint8_t *>(saved->act_tiles), saved->sigma, saved->scalar, saved->abund,
+                      saved->s1, saved->spec_hidden};
+    kernel<<<tc_grid(n, TcBwd2::G), TcBwd2::kThreads, TcBwd2::smem_bytes, as_stream(stream)>>>(
+        *pts, n, enc, *p, *g, sv, reinterpret_cast<float *>(d_enc_tiles), *dp);
     UMHS_CHECK_LAUNCH();
     return UMHS_OK;
 }

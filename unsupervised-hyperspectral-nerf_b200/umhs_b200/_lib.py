@@ -45,7 +45,12 @@ class MlpGrads(Structure):
 
 
 class FieldOut(Structure):
-    _fields_ = [("sigma", P), ("embedding", P), ("scalar", P), ("abund", P), ("s1", P), ("spec_hidden", P)]
+    _fields_ = [("sigma", P), ("embedding", P), ("scalar", P), ("abund", P), ("s1", P), ("spec_hidden", P),
+                ("act_tiles", P)]
+
+
+class FieldSaved(Structure):
+    _fields_ = [("act_tiles", P), ("sigma", P), ("scalar", P), ("abund", P), ("s1", P), ("spec_hidden", P)]
 
 
 class FieldOutGrads(Structure):
@@ -112,6 +117,8 @@ _SIGNATURES = {
     "umhs_field_mlp_tc_fwd": [POINTER(Points), c_int64, P, POINTER(MlpParams), POINTER(FieldOut), P],
     "umhs_field_mlp_tc_bwd": [POINTER(Points), c_int64, P, POINTER(MlpParams), POINTER(FieldOutGrads), P,
                               POINTER(MlpGrads), P],
+    "umhs_field_mlp_tc_bwd_saved": [POINTER(Points), c_int64, P, POINTER(MlpParams), POINTER(FieldOutGrads),
+                                    POINTER(FieldSaved), P, POINTER(MlpGrads), P],
     "umhs_field_mlp_tc_bwd_scatter": [POINTER(Points), c_int64, P, POINTER(MlpParams), POINTER(FieldOutGrads), P,
                                       POINTER(MlpGrads), POINTER(HashGrid), P, P],
     "umhs_debug_trace": [P, c_int32, P],

@@ -27,7 +27,7 @@ _LAUNCHES = {"umhs_hash_encode_fwd": 1, "umhs_hash_encode_bwd": 1, "umhs_hash_en
              "umhs_accumulate_fwd": 1, "umhs_accumulate_bwd": 1, "umhs_march_count": 1, "umhs_march_level_any": 1, "umhs_occ_pack_bits": 1, "umhs_pack_scan": 1,
              "umhs_march_write": 1, "umhs_visibility_mask": 1, "umhs_compact_samples": 1, "umhs_pack_info": 2,
              "umhs_occ_cell_points": 1, "umhs_occ_select_cells": 2, "umhs_occ_ema_update": 2, "umhs_occ_binarize": 2, "umhs_adam_step": 1,
-             "umhs_reduce_slabs": 1, "umhs_train_loss": 1, "umhs_dp_barrier": 1, "umhs_dp_adam_step": 1, "umhs_adam_step_dev": 1, "umhs_density_tc_fwd": 1, "umhs_field_mlp_tc_fwd": 1, "umhs_field_mlp_tc_bwd": 1, "umhs_field_mlp_tc_bwd_scatter": 1, "umhs_debug_trace": 1,
+             "umhs_reduce_slabs": 1, "umhs_train_loss": 1, "umhs_dp_barrier": 1, "umhs_dp_adam_step": 1, "umhs_adam_step_dev": 1, "umhs_density_tc_fwd": 1, "umhs_field_mlp_tc_fwd": 1, "umhs_field_mlp_tc_bwd": 1, "umhs_field_mlp_tc_bwd_scatter": 1, "umhs_field_mlp_tc_bwd_saved": 1, "umhs_debug_trace": 1,
              "umhs_tc05_selftest": 1, "umhs_sample_batch": 1}
 
 # "bf16": tensor-core MLP kernels (tcgen05 + TMEM, bf16 operands, fp32 accumulate) -- the default.
@@ -42,6 +42,10 @@ SPECULAR_TC = True
 # fp32 rows -- half the bytes on five passes and no conversion / transposition in the MLP kernels.  Bit-identical
 # forward (the tensor-core kernels round the encodings to bf16 on load anyway); fp32 mode always uses fp32 rows.
 ENC_TILES = True
+# The training forward keeps its hidden activations as bf16 operand tiles (704 B per sample) and the backward starts
+# from them instead of recomputing the forward: 8 tensor-core rounds per tile instead of 16 (UMHS_SAVE_ACTIVATIONS=0:
+# the recomputing backward).
+SAVE_ACTIVATIONS = os.environ.get("UMHS_SAVE_ACTIVATIONS", "1") != "0"
 # opt-in (UMHS_FUSED_SCATTER=1): the hash-grid scatter runs on 7 extra warps of the tensor-core MLP backward (one kernel
 # instead of two back to back).  Measured and NOT the default: 0.66 ms against 0.63 ms for the two kernels at 819 k
 # samples -- the reductions of the scatter warps and the shared-memory stores of the MLP epilogues share the SM's
@@ -290,8 +294,13 @@ def density_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], zero_tai
     return sigma
 
 
+ACT_TILE_BYTES = 90112  # include/umhs.h: UMHS_ACT_TILE_BYTES
+
+
 def field_mlp_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int, specular: bool,
-                  temperature: float, want_embedding: bool = True) -> Dict[str, Tensor]:
+                  temperature: float, want_embedding: bool = True, save_activations: bool = False) -> Dict[str, Tensor]:
+    """save_activations (tensor-core path): also returns ``act_tiles``, the hidden activations as bf16 operand tiles
+    (704 B per sample), for ``field_mlp_bwd(..., saved=...)``."""
     lib = _lib.load()
     dev, n = enc.device, pts.n
     out = {"sigma": torch.empty((n,), dtype=torch.float32, device=dev),
@@ -303,6 +312,11 @@ def field_mlp_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int
     fo = _lib.FieldOut()
     for k, v in out.items():
         setattr(fo, k, ptr(v))
+    if save_activations:
+        if MLP_PRECISION != "bf16":
+            raise RuntimeError("activations are saved by the tensor-core forward only")
+        out["act_tiles"] = torch.empty(((n + 127) // 128) * ACT_TILE_BYTES, dtype=torch.uint8, device=dev)
+        fo.act_tiles = ptr(out["act_tiles"])
     ps, ms = pts.struct(), mlp_struct(weights, K, specular, temperature, is_tile_buffer(enc))
     _call("umhs_field_mlp_tc_fwd" if MLP_PRECISION == "bf16" else "umhs_field_mlp_fwd", pts.units(), ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(fo), stream_ptr(dev))
     return out
@@ -310,8 +324,11 @@ def field_mlp_fwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int
 
 def field_mlp_bwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int, specular: bool, temperature: float,
                   grads: Dict[str, Optional[Tensor]], d_weights: Optional[Dict[str, Tensor]] = None,
-                  want_d_enc: bool = True, scatter: Optional[tuple] = None) -> Tuple[Optional[Tensor], Dict[str, Tensor]]:
+                  want_d_enc: bool = True, scatter: Optional[tuple] = None,
+                  saved: Optional[Dict[str, Tensor]] = None) -> Tuple[Optional[Tensor], Dict[str, Tensor]]:
     """-> (d_enc [n,32] or None, parameter grads).  Parameter grads are accumulated into d_weights if given.
+    saved = the dictionary field_mlp_fwd(..., save_activations=True) returned: the backward then starts from the kept
+    activation tiles and outputs instead of recomputing the forward (umhs_field_mlp_tc_bwd_saved, tile buffers only).
     scatter = (table, scalings, log2_T, d_table): the hash-grid scatter of d_enc into d_table (accumulating) runs inside
     the same kernel (tensor-core path with tile buffers only: umhs_field_mlp_tc_bwd_scatter)."""
     lib = _lib.load()
@@ -330,6 +347,15 @@ def field_mlp_bwd(pts: PointSet, enc: Tensor, weights: Dict[str, Tensor], K: int
     for name in MLP_NAMES:
         setattr(dp, name, ptr(d_weights.get(name)))
     ps, ms = pts.struct(), mlp_struct(weights, K, specular, temperature, tiles)
+    if saved is not None:
+        if not (tiles and MLP_PRECISION == "bf16"):
+            raise RuntimeError("the saved-activation backward needs the tensor-core path with tile buffers")
+        sv = _lib.FieldSaved()
+        for k in ("act_tiles", "sigma", "scalar", "abund", "s1", "spec_hidden"):
+            setattr(sv, k, ptr(saved.get(k)))
+        _call("umhs_field_mlp_tc_bwd_saved", pts.units(), ctypes.byref(ps), n, ptr(enc), ctypes.byref(ms), ctypes.byref(g),
+              ctypes.byref(sv), ptr(d_enc), ctypes.byref(dp), stream_ptr(dev))
+        return d_enc, d_weights
     if scatter is not None:
         if not (tiles and want_d_enc and MLP_PRECISION == "bf16"):
             raise RuntimeError("the fused scatter needs the tensor-core path with tile buffers")
@@ -355,8 +381,12 @@ class FieldFunction(torch.autograd.Function):
         # kept samples are a subset of the sampler's candidates: reuse their encodings when the sampler kept them
         enc = pts.enc_src if pts.enc_src is not None else hash_encode_fwd(pts, table.detach(), scalings, cfg["log2_T"],
                                                                            tiles=_tiles_on())
+        # training with the tensor-core kernels on tile buffers: keep the activation tiles for the backward
+        save = (SAVE_ACTIVATIONS and is_tile_buffer(enc) and MLP_PRECISION == "bf16" and not FUSED_SCATTER
+                and any(ctx.needs_input_grad))
         out = field_mlp_fwd(pts, enc, weights, cfg["K"], cfg["specular"], cfg["temperature"],
-                            want_embedding=cfg.get("want_embedding", True))
+                            want_embedding=cfg.get("want_embedding", True), save_activations=save)
+        ctx.saved_fwd = out if save else None
         ctx.pts, ctx.cfg = pts, cfg
         ctx.n_mlp = len(mlp)
         ctx.param_refs = (table, mlp)  # the Parameter objects themselves (for direct gradient accumulation)
@@ -398,7 +428,9 @@ class FieldFunction(torch.autograd.Function):
             if AFTER_MLP_BACKWARD is not None:
                 AFTER_MLP_BACKWARD()
         else:
-            d_enc, d_w = field_mlp_bwd(pts, enc, weights, K, cfg["specular"], cfg["temperature"], grads, d_w_in)
+            d_enc, d_w = field_mlp_bwd(pts, enc, weights, K, cfg["specular"], cfg["temperature"], grads, d_w_in,
+                                       saved=ctx.saved_fwd)
+            ctx.saved_fwd = None
             if AFTER_MLP_BACKWARD is not None:
                 AFTER_MLP_BACKWARD()  # trainer hook: fork work that should run beside the hash scatter and the optimiser
             L = int(scalings.shape[0])
