@@ -68,6 +68,7 @@ WORKLOADS = {
 L2_BYTES_PER_CYCLE = 6300.0
 # Per-launch traffic from the committed `ncu --set full` capture of the config-2 step (profiles/r2_ncu_full_summary.md):
 # name -> (dram__bytes_read.sum + dram__bytes_write.sum, lts__t_bytes.sum); None = not captured
+SAVE_ACTIVATIONS_ON = os.environ.get("UMHS_SAVE_ACTIVATIONS", "1") != "0"
 NCU_TRAFFIC = {}
 try:
     with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as _fh:
@@ -276,6 +277,13 @@ def algorithmic_bytes(name, units, samples_per_ray, K, adam_touched_frac=None):
         return units * (2 * S * (12 + 8 * K) + 8 * BANDS)
     if name == "umhs_train_loss":
         return units * 3 * 4 * BANDS
+    if name == "umhs_field_mlp_tc_fwd" and SAVE_ACTIVATIONS_ON:
+        # training forward that keeps its activation tiles: enc tile row 64 + ray data 28 in; sigma, scalar, abund out;
+        # 704 B of bf16 activation tiles out -- an HBM WRITE stream (3.9 TB/s is what a pure write reaches on this part)
+        return units * (64 + 28 + 4 + 8 * K + 704)
+    if name == "umhs_field_mlp_tc_bwd_saved":
+        # activation tiles 704 + enc row 64 + forward outputs and their gradients 2 (4 + 8 K) in; d_enc row 64 out
+        return units * (704 + 64 + 2 * (4 + 8 * K) + 28 + 64)
     if name in ("umhs_adam_step", "umhs_adam_step_dev"):
         # touched entries: p, g, m, v read + p, m, v, g written = 32 B; entries with g = m = v = 0 are skipped after
         # reading g, m, v = 12 B
@@ -286,14 +294,15 @@ def algorithmic_bytes(name, units, samples_per_ray, K, adam_touched_frac=None):
 
 def mlp_flops(name, units, K, specular):
     """(algorithmic, executed) FLOPs per launch of the tensor-core MLP kernels.  Algorithmic: forward =
-    2 x MACs/sample; backward = dgrad + wgrad = 2 x forward.  Executed: the backward also RECOMPUTES the forward in
-    shared memory (nothing but the hash encoding is kept from the forward pass): 3 x forward."""
+    2 x MACs/sample; backward = dgrad + wgrad = 2 x forward.  Executed: the recomputing backward (umhs_field_mlp_tc_bwd)
+    also runs the forward again in shared memory: 3 x forward; the backward from saved activations (the default,
+    umhs_field_mlp_tc_bwd_saved) executes what it is credited with."""
     base = 2 * (32 * 64 + 64 * 16)
     heads = 2 * ((27 * 64 + 64 * 64 + 64 * K) + (27 * 64 + 64 * 64 + 64 * (K + (1 if specular else 0))))
     spec = 2 * (28 * 16) if specular else 0  # layer 0 of mlp_directional (layer 1 lives in the compositing kernels)
     fwd = base + heads + spec
     per = {"umhs_density_tc_fwd": (base, base), "umhs_field_mlp_tc_fwd": (fwd, fwd),
-           "umhs_field_mlp_tc_bwd": (2 * fwd, 3 * fwd)}.get(name)
+           "umhs_field_mlp_tc_bwd": (2 * fwd, 3 * fwd), "umhs_field_mlp_tc_bwd_saved": (2 * fwd, 2 * fwd)}.get(name)
     return (None, None) if per is None else (units * per[0], units * per[1])
 
 
@@ -688,7 +697,8 @@ def roofline_line(summ, steps, spr, wl, peaks, sm_mhz, adam_touched_frac):
                 "unit": "TFLOP/s", "frac": kernels[top]["achieved_tflops"] / tf_peak, "peak_source": tf_src,
                 "algorithmic_flops": "backward = dgrad + wgrad = 2 x forward MACs x 2 (SURVEY 8d); forward = 2 x MACs",
                 "executed_tflops": kernels[top]["executed_tflops"],
-                "executed_note": "the backward recomputes the forward in shared memory: 3 x forward FLOPs executed",
+                "executed_note": "umhs_field_mlp_tc_bwd recomputes the forward in shared memory (3 x forward FLOPs "
+                                 "executed); umhs_field_mlp_tc_bwd_saved starts from saved activation tiles (2 x)",
                 **share}
     elif top.startswith("umhs_hash_encode"):
         roof = {"kernel": top, "bound": "l2", "achieved": kernels[top]["achieved_gbs"], "peak": l2_peak, "unit": "GB/s",

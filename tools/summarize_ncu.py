@@ -70,9 +70,9 @@ def full(path):
         import json
         import re
 
-        entry = {"field_mlp_tc_bwd": "umhs_field_mlp_tc_bwd", "field_mlp_tc_fwd_kernel<0>": "umhs_field_mlp_tc_fwd",
-                 "field_mlp_tc_fwd_kernel<false>": "umhs_field_mlp_tc_fwd", "field_mlp_tc_fwd_kernel<1>": "umhs_density_tc_fwd",
-                 "field_mlp_tc_fwd_kernel<true>": "umhs_density_tc_fwd", "hash_encode_fwd": "umhs_hash_encode_fwd",
+        entry = {"field_mlp_tc_bwd_saved": "umhs_field_mlp_tc_bwd_saved", "field_mlp_tc_bwd_kernel": "umhs_field_mlp_tc_bwd",
+                 "field_mlp_tc_fwd_kernel<0": "umhs_field_mlp_tc_fwd", "field_mlp_tc_fwd_kernel<false": "umhs_field_mlp_tc_fwd",
+                 "field_mlp_tc_fwd_kernel<1": "umhs_density_tc_fwd", "field_mlp_tc_fwd_kernel<true": "umhs_density_tc_fwd", "hash_encode_fwd": "umhs_hash_encode_fwd",
                  "hash_encode_bwd": "umhs_hash_encode_bwd", "composite_fwd": "umhs_composite_fwd",
                  "composite_bwd": "umhs_composite_bwd", "adam_kernel": "umhs_adam_step_dev", "train_loss": "umhs_train_loss",
                  "march_kernel": "umhs_march_count"}

@@ -287,32 +287,13 @@ __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, 
                  : "memory");
 }
 
-// ... and back: `bytes` from shared to global memory (bulk-group completion: only the issuing thread can wait for it).
-// Both directions of the saved-activation stream carry an evict-first L2 policy: ~0.6 GB per step that is written once
-// and read once should not push the hash table and its gradient out of the L2.
+// The saved-activation stream (~0.6 GB per step, written once by streaming stores and read once by these bulk copies)
+// carries an evict-first L2 policy: it should not push the hash table and its gradient out of the L2.
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-#ifndef UMHS_SAVE_VARIANT
-#define UMHS_SAVE_VARIANT 0   // developer switch: 1 = no L2 hint on the stores, 2 = stores dropped (timing only)
-#endif
-__device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem, uint32_t bytes, uint64_t policy) {
-#if UMHS_SAVE_VARIANT == 0
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
-                 "r"(smem_u32(src_smem)), "r"(bytes), "l"(policy)
-                 : "memory");
-#elif UMHS_SAVE_VARIANT == 1
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
-                 "r"(smem_u32(src_smem)), "r"(bytes)
-                 : "memory");
-#endif
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// all bulk stores of this thread have finished READING their shared-memory source
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_load_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
                                                uint64_t policy) {
     asm volatile(
