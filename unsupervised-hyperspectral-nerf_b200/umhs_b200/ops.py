@@ -382,8 +382,8 @@ class FieldFunction(torch.autograd.Function):
         enc = pts.enc_src if pts.enc_src is not None else hash_encode_fwd(pts, table.detach(), scalings, cfg["log2_T"],
                                                                            tiles=_tiles_on())
         # training with the tensor-core kernels on tile buffers: keep the activation tiles for the backward
-        save = (SAVE_ACTIVATIONS and is_tile_buffer(enc) and MLP_PRECISION == "bf16" and not FUSED_SCATTER
-                and any(ctx.needs_input_grad))
+        save = (SAVE_ACTIVATIONS and cfg.get("save_activations", False) and is_tile_buffer(enc)
+                and MLP_PRECISION == "bf16" and not FUSED_SCATTER and any(ctx.needs_input_grad))
         out = field_mlp_fwd(pts, enc, weights, cfg["K"], cfg["specular"], cfg["temperature"],
                             want_embedding=cfg.get("want_embedding", True), save_activations=save)
         ctx.saved_fwd = out if save else None

@@ -180,6 +180,9 @@ class UMHSField(nn.Module):
         enc = self.mlp_base.encoder
         cfg = self._cfg()
         cfg["want_embedding"] = want_embedding
+        # training steps only: the forward keeps its activation tiles for the backward (ops.SAVE_ACTIVATIONS); an
+        # evaluation image (24 M samples) must not write 17 GB of them
+        cfg["save_activations"] = bool(self.training and torch.is_grad_enabled())
         sigma, emb, scalar, abund, s1, sh = ops.FieldFunction.apply(pts, cfg, enc.hash_table, enc.scalings,
                                                                     *self._mlp_tensors())
         out = {"sigma": sigma, "embedding": emb, "scalar": scalar, "abund": abund}
