@@ -1391,8 +1391,8 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
 // Backward from SAVED activations (umhs_field_mlp_tc_bwd_saved): 8 rounds per tile instead of 16.
 //
 // Half of the rounds of the kernel above recompute the forward (base0, base1, head0-2, feat0-2).  The training forward
-// can keep its bf16 operand tiles instead (umhs_field_out.act_tiles, 704 B per sample, written by warp-local bulk
-// stores as a by-product of its epilogues); here they come back by ONE bulk copy per tile and layer (TMA, mbarrier
+// can keep its bf16 operand tiles instead (umhs_field_out.act_tiles, 704 B per sample, streamed out by its threads
+// behind each round's hand-off: save_row); here they come back by ONE bulk copy per tile and layer (TMA, mbarrier
 // transaction count) into two 16 KB slots, each two rounds ahead of the MMAs that read it, and the output-layer
 // deltas are formed from the forward's outputs (sigmoid' = s (1 - s), softmax Jacobian from the abundances,
 // trunc_exp' = the density itself).  Same MMAs, same accumulators, same flush as the kernel above.
