@@ -188,3 +188,27 @@ def test_sharded_adam_moments_are_gathered_for_saving():
     spans = [tr.dp_shard(r) for r in range(4)]
     assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
     assert all(lo % 4 == 0 for lo, _ in spans)
+
+
+def test_shard_ownership_with_a_split_exchange():
+    """``dp_spans`` / ``dp_shards``: with the exchange cut in two slices (UMHS_DP_SPLIT_LEVEL; csrc/optim.cu::
+    umhs_dp_adam_step_range) every rank owns one part of EACH slice; together the ranks' shards tile the flat buffer
+    exactly once, on multiples of 4."""
+    m = _model(3)
+    tr = UMHSTrainer(m, occ_update=False)
+    n = tr.flat.numel
+    assert tr.dp_spans() == [(0, n)] and tr.dp_shards() == [(0, n)]
+    tr.world_size = 8
+    t_lo, t_hi = tr.flat.range_of(m.field.mlp_base.encoder.hash_table)
+    tr._dp_cut = t_lo + (t_hi - t_lo) // 16 * 8  # first element of level 8
+    assert tr._dp_cut % 4 == 0
+    assert tr.dp_spans() == [(0, tr._dp_cut), (tr._dp_cut, n)]
+    owned = torch.zeros(n, dtype=torch.int32)
+    for r in range(8):
+        shards = tr.dp_shards(r)
+        assert len(shards) == 2
+        for lo, hi in shards:
+            assert lo % 4 == 0 and (hi % 4 == 0 or hi == n)
+            owned[lo:hi] += 1
+    assert int(owned.min()) == 1 and int(owned.max()) == 1
+
