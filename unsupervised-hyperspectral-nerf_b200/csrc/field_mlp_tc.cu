@@ -1397,8 +1397,8 @@ field_mlp_tc_bwd_kernel(umhs_points P, int64_t n_total, const float *__restrict_
 // deltas are formed from the forward's outputs (sigmoid' = s (1 - s), softmax Jacobian from the abundances,
 // trunc_exp' = the density itself).  Same MMAs, same accumulators, same flush as the kernel above.
 //   round  critical (dgrad)                      deferred (wgrad)                operands arriving for
-//   1      dz_h  [128x16] W_h2  -> d h2 (head)   P_h2t += Hh2^T dz_h             slot A: Hh2   slot B: Hh1   tX: X
-//   2      d2_h  W_h1           -> d h1          P_h1  += d2_h^T [Hh1 | 1]
+//   1      dz_h  [128x16] W_h2  -> d h2 (head)   --                              slot A: Hh2   slot B: Hh1   tX: X
+//   2      d2_h  W_h1 ; P_h2t += Hh2^T dz_h -> d h1   P_h1 += d2_h^T [Hh1 | 1]
 //   3      d1_h  W_h0           -> d X (head)    P_h0  += d1_h^T X               slot A <- Hf2
 //   4      dz_f  [128x32] W_f2  -> d h2 (feat)   P_f2t += Hf2^T dz_f             slot B <- Hf1
 //   5      d2_f  W_f1           -> d h1          P_f1  += d2_f^T [Hf1 | 1]
@@ -1496,9 +1496,13 @@ field_mlp_tc_bwd_saved_kernel(umhs_points P, int64_t n_total, const float *__res
                     // not deferred: the next epilogue writes tD1
                     if (spec) gemm_wgrad(tbase + TcBwd::P_d0, B16, sD1, 0, sD2, 0, 32, acc);
                 }
-                if (late) gemm_wgrad(tbase + TcBwd::P_h2t, B16, sA, 0, sZ, 0, 16, acc);
+                // (the weight gradient of this layer needs Hh2, which has only just been requested when the tile
+                // starts: it goes out with round 2, so that round 1 waits for nothing but the group's own dz)
             } else if constexpr (r == 1) {
-                if (crit) gemm_dgrad(tw, B16, sD1, w::h1, 64, 0, 64, 64, 0);
+                if (crit) {
+                    gemm_dgrad(tw, B16, sD1, w::h1, 64, 0, 64, 64, 0);
+                    gemm_wgrad(tbase + TcBwd::P_h2t, B16, sA, 0, sZ, 0, 16, acc);  // not deferred: tZ is rewritten next
+                }
                 if (late) gemm_wgrad(tbase + TcBwd::P_h1, B16, sD1, 0, sB, 0, 72, acc);
             } else if constexpr (r == 2) {
                 if (crit) gemm_dgrad(tw, B16, sD2, w::hf0, 128, 0, 32, 64, 0);
@@ -1637,11 +1641,11 @@ field_mlp_tc_bwd_saved_kernel(umhs_points P, int64_t n_total, const float *__res
             float demb[15];
 #pragma unroll
             for (int i = 0; i < 15; ++i) demb[i] = (valid && g.d_embedding) ? __ldg(g.d_embedding + n * 15 + i) : 0.f;
-            wait_full(fullA, parA);  // Hh2
             gs.arrive();
             if (d_enc && it > 0) flush_staged_pieces(d_enc, pending_row, tD2 + 8192, row);  // (tD2's upper half: idle until round 3's epilogue... see below)
             gs.wait();
             // ---------------- round 2: d h2 (head) masked by Hh2 -> tD1
+            wait_full(fullA, parA);  // Hh2 (requested when the previous tile finished: a round of slack by now)
             epi_mask64(trow, sA, nullptr, tD1, row);
             wait_full(fullB, parB);  // Hh1
             gs.round_trip();
