@@ -74,3 +74,17 @@ def test_colour_and_probe_mirrors_match_golden():
     inner, probs = umhs_b200.ClusterLookup(128, 4)(t(d["spec"]), alpha=0.2, clusters=t(d["endmembers"]))
     np.testing.assert_allclose(inner.numpy(), d["inner"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(probs.numpy(), d["probs"], rtol=1e-5, atol=1e-6)
+
+
+def test_activation_tile_size_agrees_across_header_and_host():
+    """UMHS_ACT_TILE_BYTES (include/umhs.h) is what ops.field_mlp_fwd allocates per 128-sample tile: five [128 x 64] and
+    one [128 x 32] bf16 operand tiles."""
+    import re
+
+    import umhs_b200.ops as ops
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "umhs.h")).read()
+    m = re.search(r"#define\s+UMHS_ACT_TILE_BYTES\s+(\d+)", hdr)
+    assert m and int(m.group(1)) == ops.ACT_TILE_BYTES == 5 * 128 * 64 * 2 + 128 * 32 * 2
+
